@@ -1,0 +1,187 @@
+/*
+ * loki_b200.h -- C ABI of the B200-native Vlasov right-hand-side path for LLNL/LOKI.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Every entry point
+ * replaces one interface of the reference (cited file:line into the LOKI source tree).  The
+ * reference's only FFI is its C++ -> Fortran-77 seam (KineticSpeciesF.H, PoissonF.H, MaxwellF.H:
+ * extern "C", trailing-underscore symbols, every argument by reference, boxes expanded to 8 ints by
+ * BOX4D_TO_FORT, tbox/Box.H:893-897).  Here the same operators take DEVICE pointers, a geometry
+ * struct instead of 16 box integers, and return an int status (0 = ok) instead of aborting
+ * (Loki_Defines.H:33-39); lk_last_error() gives the message.  INTEGRATION.md shows the stub a LOKI
+ * maintainer adds to KineticSpecies.H / VPSystem.C to bind them.
+ *
+ * Arrays: fp64, Fortran order (first index contiguous), 4D distribution arrays hold the interior
+ * grown by ng ghost cells in all four directions exactly like ParallelArray (ParallelArray.H:1121-1132,
+ * ParallelArray.C:664-665) so restart dumps (RestartWriter.C:543-560) can be uploaded verbatim.
+ * All indices into tables below are 0-based offsets into the data box.
+ *
+ * All functions are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream)
+ * unless stated otherwise.  There is NO CPU fallback: without a CUDA device every compute entry
+ * point fails with LK_ERR_CUDA.
+ */
+#ifndef LOKI_B200_H
+#define LOKI_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LK_OK 0
+#define LK_ERR_ARG 1
+#define LK_ERR_CUDA 2
+#define LK_ERR_UNSUPPORTED 3
+
+/* Geometry of one species' local 4D box.  Replaces BOX4D_TO_FORT(dataBox()), BOX4D_TO_FORT(interiorBox())
+ * and PROBLEMDOMAIN_TO_FORT (ProblemDomain.H:318-321). */
+typedef struct lk_geom {
+  int n[4];     /* interior cells (Nx, Ny, Nvx, Nvy) on this device                        */
+  int ng;       /* ghost width: 2 for order 4, 3 for order 6 (KineticSpecies.C:155-160)    */
+  int order;    /* spatial_solution_order, 4 or 6                                          */
+  double dx[4]; /* cell sizes                                                               */
+} lk_geom;
+
+/* How the acceleration on velocity faces is formed; replaces the materialised vel3/vel4 arrays of
+ * setphasespacevel4D / setphasespacevelmaxwell4D (KineticSpeciesF.f:42-114, 118-197): the kernels
+ * evaluate the same expression on the fly from the 2D fields. */
+typedef struct lk_accel {
+  int kind;               /* 0: Vlasov-Poisson, field = accel(n1d,n2d,2) already scaled by q/m
+                             (KineticSpecies.C:755); 1: Vlasov-Maxwell, field = em_vars(n1d,n2d,6)
+                             Ex,Ey,Ez,Bx,By,Bz and vz(n1d,n2d)                              */
+  const double* field;    /* device */
+  const double* vz;       /* device, kind 1 only */
+  const double* vxface_velocities; /* device (n3d+1, n4d, 2)  KineticSpecies.C:2033-2039 */
+  const double* vyface_velocities; /* device (n3d, n4d+1, 2)  KineticSpecies.C:2040-2046 */
+  double normalization;   /* q/m (or q when relativistic), KineticSpecies.C:748-754 */
+  double bz_const;
+} lk_accel;
+
+/* Inflow values for the velocity-boundary fill; replaces the initialconditionatpoint_ callback
+ * (ICInterface.C:36-57) that setaccelerationbcs4d_ makes per ghost cell. */
+typedef struct lk_inflow {
+  int kind;          /* 0: zero inflow; 1: factored fnorm*fv(i3,i4)*fx(i1,i2)*frac
+                        (PerturbedMaxwellianIC.C:267-289); 2: fx*fv + fx2*fv2
+                        (InterpenetratingStreamIC.C:265-286); 3: explicit ghost-layer tables */
+  const double* fx;  /* device (n1d,n2d)  */
+  const double* fv;  /* device (n3d,n4d)  */
+  const double* fx2; /* kind 2 */
+  const double* fv2; /* kind 2 */
+  double fnorm, frac;
+  const double* ghost3; /* kind 3: (n1d,n2d,2*ng,n4d): layers [0,ng) below n3a (layer k = cell n3a-ng+k), [ng,2ng) above */
+  const double* ghost4; /* kind 3: (n1d,n2d,n3d,2*ng) */
+} lk_inflow;
+
+/* One fused Runge-Kutta stage update applied to the freshly evaluated rhs (RK4Integrator.H:149-171):
+ *   delta_out = (delta_in ? delta_in : 0) + w_delta * rhs           [addSolnData(m_delta, m_rhs, a_dt_eval)]
+ *   pred      = f_old + c_pred * (use_delta ? delta_out : rhs)       [copySolnData + addSolnData]       */
+typedef struct lk_rk_update {
+  const double* f_old;
+  const double* delta_in; /* NULL in stage 1 (delta starts from zero) */
+  double* delta_out;      /* NULL in the last stage if the caller does not need it */
+  double* pred;           /* must not alias f_eval (neighbours still read the old values) */
+  double w_delta, c_pred;
+  int use_delta;          /* 1 in RK4 stage 4 */
+} lk_rk_update;
+
+/* ---- library ---- */
+int lk_version(void);
+const char* lk_last_error(void);
+/* 0 = production arithmetic (FMA contraction, one reciprocal per WENO fit; within 1e-12 of the
+ * reference), 1 = strict: the reference's operation order with no contraction, bit-identical to a
+ * gfortran -O2 build of KineticSpeciesF.f.  Returns the previous mode. */
+int lk_set_strict(int strict);
+int lk_get_strict(void);
+int lk_device_count(void);
+/* 0 = tiled shared-memory kernel (default), 1 = one-thread-per-cell cross-check kernel */
+int lk_set_rhs_variant(int variant);
+
+/* ---- a1/a2: WENO43Fit4D / WENO65Fit4D (KineticSpeciesF.f:723-790, 914-979); test hook ----
+ * u: count x order-sized stencils (um2,um1,u0,up1 | um3..up2), vel: count upwind velocities */
+int lk_weno_fit(int order, const double* u, const double* vel, double* face, int64_t count, void* stream);
+
+/* ---- a10: xpby4d_ (KineticSpeciesF.H:41-61, KineticSpeciesF.f:10-38): x += b*y on the interior ---- */
+int lk_xpby4d(double* x, const double* y, double b, const lk_geom* g, void* stream);
+
+/* ---- a4/a5: setphasespacevel4d_ / setphasespacevelmaxwell4d_ (KineticSpeciesF.H:191-250).
+ * lk_max_accel returns {axmax, aymax} (device, 2 doubles) without materialising vel3/vel4;
+ * lk_set_phase_space_vel_4d also writes the two rotated 4D arrays for callers that still want them. */
+int lk_max_accel(const lk_geom* g, const lk_accel* a, double* axaymax_dev, void* stream);
+int lk_set_phase_space_vel_4d(double* vel3, double* vel4, const lk_geom* g, const lk_accel* a,
+                              double* axaymax_dev, void* stream);
+
+/* ---- a6: setaccelerationbcs4d_ (KineticSpeciesF.H:97-127, KineticSpeciesF.f:1036-1162) ----
+ * at_[0..3] = box touches global vx-low, vx-high, vy-low, vy-high boundary */
+int lk_set_acceleration_bcs_4d(double* f, const lk_geom* g, const lk_accel* a, const lk_inflow* ic,
+                               const int at[4], void* stream);
+
+/* ---- a14: periodic wrap of x then y ghosts on one device (ParallelArray.H:580-606) ---- */
+int lk_periodic_fill_4d(double* f, const lk_geom* g, int periodic_x, int periodic_y, void* stream);
+/* halo slabs for the (x,y)-decomposed multi-GPU exchange (ParallelArray.C:925-1113, faces only).
+ * dir 0 = x, 1 = y; side 0 = low, 1 = high.  pack copies the ng interior layers next to that side
+ * into a dense buffer; unpack writes a received buffer into the ghost layers on that side.
+ * Buffer layout: x: (ng, n2, n3d, n4d); y: (n1d, ng, n3d, n4d). */
+int64_t lk_halo_count(const lk_geom* g, int dir);
+int lk_halo_pack(double* buf, const double* f, const lk_geom* g, int dir, int side, void* stream);
+int lk_halo_unpack(double* f, const double* buf, const lk_geom* g, int dir, int side, void* stream);
+
+/* ---- a3 + a8: computeadvectionderivatives4d_ + computeaccelerationderivatives4d_
+ * (KineticSpeciesF.H:293-341, KineticSpeciesF.f:1949-2245).  velocities: device (n3d,n4d,2) cell-centre
+ * table (KineticSpecies.C:2026-2032).  advection ASSIGNS rhs, acceleration ACCUMULATES. */
+int lk_advection_derivatives_4d(double* rhs, const double* f, const lk_geom* g, const double* velocities,
+                                void* stream);
+int lk_acceleration_derivatives_4d(double* rhs, const double* f, const lk_geom* g, const lk_accel* a,
+                                   void* stream);
+
+/* ---- fused production path: a3 + a4/a5 + a8 (+ a10/a11 when upd != NULL) in ONE pass ----
+ * rhs_out may be NULL when upd != NULL.  f must have valid x/y ghosts and velocity-boundary ghosts. */
+int lk_vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const double* velocities,
+                  const lk_accel* a, const lk_rk_update* upd, void* stream);
+
+/* ---- a12: ReductionSchedule 4D->2D (ReductionSchedule.C:69-113, 421-444): dst(n1d,n2d) ghosts zeroed,
+ * dst = (sum_{i3,i4} f) * dv * weight ---- */
+int lk_reduce_4d_to_2d(double* dst2d, const double* f, const lk_geom* g, double dv, double weight,
+                       void* stream);
+/* ---- a13: computecurrents_ + three reductions fused (KineticSpeciesF.f:2400-2443,
+ * KineticSpecies.C:853-895): Jx,Jy,Jz (n1d,n2d) ---- */
+int lk_current_density(double* Jx, double* Jy, double* Jz, const double* f, const lk_geom* g,
+                       const double* velocities, const double* vz, double dv, double weight, void* stream);
+/* ---- a9: computekeedot_ (KineticSpeciesF.f:2563-2602); out_dev: 1 double ---- */
+int lk_ke_e_dot(double* out_dev, const double* f, const lk_geom* g, double charge, const double* velocities,
+                const double* ext_efield, void* stream);
+
+/* ---- a16: Poisson (PoissonF.f:10-123, LokiPoissonSolveFFT.C:31-170, EMSolverBase.C:270-371) ----
+ * 2D arrays (n1d,n2d[,comp]).  lk_poisson_plan builds the symbol/twiddle tables on the device. */
+typedef struct lk_poisson_plan lk_poisson_plan;
+int lk_poisson_plan_create(lk_poisson_plan** plan, int nx, int ny, int ng, int order, double Lx, double Ly);
+void lk_poisson_plan_destroy(lk_poisson_plan* plan);
+/* rho is neutralised in place; phi gets interior + periodic ghosts; em_vars comps 0,1 = Ex,Ey with
+ * periodic ghosts (the whole electricField sequence) */
+int lk_electric_field(lk_poisson_plan* plan, double* rho, double* phi, double* em_vars, const double* dx,
+                      void* stream);
+int lk_periodic_fill_2d(double* u, int n1, int n2, int ng, int ncomp, int periodic_x, int periodic_y,
+                        void* stream);
+/* x += b*y on the interior of a (n1d,n2d,ncomp) array: xpby2d_ (MaxwellF.f:62-93) */
+int lk_xpby2d(double* x, const double* y, double b, int n1, int n2, int ng, int ncomp, void* stream);
+/* computeAcceleration glue (KineticSpecies.C:697-774): accel = (em[0:2] + ext) * normalization */
+int lk_form_accel(double* accel, const double* em_vars, const double* ext_efield, double normalization,
+                  int n1, int n2, int ng, void* stream);
+
+/* ---- a17: Maxwell (MaxwellF.f:97-355, 442-469) ---- */
+int lk_maxwell_rhs(double* rhs, const double* em, const double* Jx, const double* Jy, const double* Jz,
+                   int n1, int n2, int ng, int order, const double* dx, double light_speed, double av_weak,
+                   double av_strong, void* stream);
+
+/* ---- device memory helpers for hosts without their own allocator (synchronous) ---- */
+int lk_malloc(void** p, int64_t bytes);
+int lk_free(void* p);
+int lk_memcpy_h2d(void* dst, const void* src, int64_t bytes);
+int lk_memcpy_d2h(void* dst, const void* src, int64_t bytes);
+int lk_memset(void* p, int value, int64_t bytes);
+int lk_sync(void* stream);
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t lk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,61 @@
+"""Build the sm_100a shared library `loki_b200/libloki_b200.so` with nvcc (in-tree, no JIT cache).
+
+lk_kernels.cu is compiled twice: the production arithmetic (FMA contraction, namespace lkfast) and the
+strict arithmetic (-fmad=false, reference operation order, namespace lkstrict).  The oracle under
+oracle/ is built separately (it is test infrastructure, never linked here).
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libloki_b200.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def build(force=False, verbose=False):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+        os.path.join(HERE, "..", "include", "loki_b200.h"), os.path.abspath(__file__)]
+    if not force and _newer(OUT, srcs):
+        return OUT
+    bdir = os.path.join(HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
+    extra = ["-Xptxas", "-v"] if verbose else []
+    jobs = [
+        (["-DLK_STRICT=0"], "lk_kernels.cu", "lk_kernels_fast.o"),
+        (["-DLK_STRICT=1", "-fmad=false"], "lk_kernels.cu", "lk_kernels_strict.o"),
+        ([], "lk_capi.cu", "lk_capi.o"),
+        ([], "lk_host.cu", "lk_host.o"),
+    ]
+    procs = []
+    objs = []
+    for flags, src, obj in jobs:
+        if not os.path.exists(os.path.join(CSRC, src)):
+            continue
+        o = os.path.join(bdir, obj)
+        objs.append(o)
+        cmd = [nvcc] + ARCH + COMMON + extra + flags + ["-c", os.path.join(CSRC, src), "-o", o]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(out)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    cmd = [nvcc] + ARCH + ["-shared", "-o", OUT] + objs
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,331 @@
+// lk_capi.cu -- the extern "C" boundary declared in include/loki_b200.h.  Validates arguments,
+// picks the arithmetic build (production / strict) and owns the small device scratch buffers.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "lk_launch.h"
+
+namespace {
+thread_local std::string g_err;
+int g_strict = 0;
+int g_variant = 0;
+std::mutex g_mu;
+
+int fail(int code, const char* what) {
+  g_err = what;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s: %s", where, cudaGetErrorString(e));
+  g_err = buf;
+  return LK_ERR_CUDA;
+}
+bool geom_ok(const lk_geom* g) {
+  if (!g) return false;
+  if (!((g->order == 4 && g->ng == 2) || (g->order == 6 && g->ng == 3))) return false;
+  for (int k = 0; k < 4; ++k)
+    if (g->n[k] < 1 || !(g->dx[k] > 0.0)) return false;
+  return true;
+}
+
+// scratch buffers keyed by slot, grown on demand (device memory stays resident between calls)
+struct Scratch {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+Scratch g_scratch[4];
+double* scratch(int slot, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Scratch& s = g_scratch[slot];
+  if (s.bytes < bytes) {
+    if (s.p) cudaFree(s.p);
+    s.p = nullptr;
+    s.bytes = 0;
+    if (cudaMalloc(&s.p, bytes) != cudaSuccess) return nullptr;
+    s.bytes = bytes;
+  }
+  return (double*)s.p;
+}
+int moment_chunks(const lk_geom* g) {
+  if (g_strict) return 1;  // the reference's sequential sum order
+  // enough CTAs to fill 148 SMs a few times over: grid = ceil(Nx/64) * Ny * chunks
+  long long base = (long long)((g->n[0] + 63) / 64) * g->n[1];
+  int c = (int)((148LL * 16 + base - 1) / base);
+  if (c < 1) c = 1;
+  if (c > g->n[3]) c = g->n[3];
+  return c;
+}
+}  // namespace
+
+#define DISPATCH(call) (g_strict ? lkstrict::call : lkfast::call)
+#define CHECK_LAUNCH(expr, name)                       \
+  do {                                                 \
+    cudaError_t e__ = (expr);                          \
+    if (e__ != cudaSuccess) return cuda_fail(e__, name); \
+    return LK_OK;                                      \
+  } while (0)
+
+struct lk_poisson_plan {
+  int nx, ny, ng, order;
+  double *sx, *sy, *cx, *cy, *T, *X;  // device
+};
+
+extern "C" {
+
+int lk_version(void) { return 100; }
+const char* lk_last_error(void) { return g_err.c_str(); }
+int lk_set_strict(int strict) {
+  int old = g_strict;
+  g_strict = strict ? 1 : 0;
+  return old;
+}
+int lk_get_strict(void) { return g_strict; }
+int lk_set_rhs_variant(int variant) {
+  int old = g_variant;
+  g_variant = variant ? 1 : 0;
+  return old;
+}
+int lk_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+int64_t lk_launch_count(void) { return lkfast::launches() + lkstrict::launches(); }
+
+int lk_weno_fit(int order, const double* u, const double* vel, double* face, int64_t count, void* stream) {
+  if ((order != 4 && order != 6) || count < 0 || (count > 0 && (!u || !vel || !face))) return fail(LK_ERR_ARG, "lk_weno_fit: bad argument");
+  CHECK_LAUNCH(DISPATCH(weno_fit)(order, u, vel, face, count, (cudaStream_t)stream), "lk_weno_fit");
+}
+
+int lk_xpby4d(double* x, const double* y, double b, const lk_geom* g, void* stream) {
+  if (!geom_ok(g) || !x || !y) return fail(LK_ERR_ARG, "lk_xpby4d: bad argument");
+  CHECK_LAUNCH(DISPATCH(xpby4d)(x, y, b, g, (cudaStream_t)stream), "lk_xpby4d");
+}
+
+static bool accel_ok(const lk_accel* a) {
+  if (!a || !a->field || !a->vxface_velocities || !a->vyface_velocities) return false;
+  if (a->kind != 0 && a->kind != 1) return false;
+  if (a->kind == 1 && !a->vz) return false;
+  return true;
+}
+
+int lk_max_accel(const lk_geom* g, const lk_accel* a, double* out, void* stream) {
+  if (!geom_ok(g) || !accel_ok(a) || !out) return fail(LK_ERR_ARG, "lk_max_accel: bad argument");
+  CHECK_LAUNCH(DISPATCH(max_accel)(g, a, out, (cudaStream_t)stream), "lk_max_accel");
+}
+int lk_set_phase_space_vel_4d(double* vel3, double* vel4, const lk_geom* g, const lk_accel* a, double* out, void* stream) {
+  if (!geom_ok(g) || !accel_ok(a) || !out) return fail(LK_ERR_ARG, "lk_set_phase_space_vel_4d: bad argument");
+  CHECK_LAUNCH(DISPATCH(set_phase_space_vel)(vel3, vel4, g, a, out, (cudaStream_t)stream), "lk_set_phase_space_vel_4d");
+}
+int lk_set_acceleration_bcs_4d(double* f, const lk_geom* g, const lk_accel* a, const lk_inflow* ic, const int at[4],
+                               void* stream) {
+  if (!geom_ok(g) || !accel_ok(a) || !f || !at) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d: bad argument");
+  if (g->n[2] < 3 || g->n[3] < 3) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d: need >= 3 velocity cells");
+  if (ic) {
+    if (ic->kind < 0 || ic->kind > 3) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d: bad inflow kind");
+    if ((ic->kind == 1 || ic->kind == 2) && (!ic->fx || !ic->fv)) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d: missing inflow tables");
+    if (ic->kind == 2 && (!ic->fx2 || !ic->fv2)) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d: missing second inflow term");
+    if (ic->kind == 3 && (!ic->ghost3 || !ic->ghost4)) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d: missing ghost tables");
+  }
+  CHECK_LAUNCH(DISPATCH(set_accel_bcs)(f, g, a, ic, at, (cudaStream_t)stream), "lk_set_acceleration_bcs_4d");
+}
+int lk_periodic_fill_4d(double* f, const lk_geom* g, int px, int py, void* stream) {
+  if (!geom_ok(g) || !f) return fail(LK_ERR_ARG, "lk_periodic_fill_4d: bad argument");
+  if ((px && g->n[0] < g->ng) || (py && g->n[1] < g->ng)) return fail(LK_ERR_ARG, "lk_periodic_fill_4d: box thinner than the ghost width");
+  CHECK_LAUNCH(DISPATCH(periodic_fill_4d)(f, g, px, py, (cudaStream_t)stream), "lk_periodic_fill_4d");
+}
+int64_t lk_halo_count(const lk_geom* g, int dir) {
+  if (!geom_ok(g) || dir < 0 || dir > 1) return -1;
+  const int64_t n3d = g->n[2] + 2 * g->ng, n4d = g->n[3] + 2 * g->ng;
+  return dir == 0 ? (int64_t)g->ng * g->n[1] * n3d * n4d : (int64_t)(g->n[0] + 2 * g->ng) * g->ng * n3d * n4d;
+}
+int lk_halo_pack(double* buf, const double* f, const lk_geom* g, int dir, int side, void* stream) {
+  if (!geom_ok(g) || !buf || !f || dir < 0 || dir > 1 || side < 0 || side > 1) return fail(LK_ERR_ARG, "lk_halo_pack: bad argument");
+  CHECK_LAUNCH(DISPATCH(halo_pack)(buf, f, g, dir, side, (cudaStream_t)stream), "lk_halo_pack");
+}
+int lk_halo_unpack(double* f, const double* buf, const lk_geom* g, int dir, int side, void* stream) {
+  if (!geom_ok(g) || !buf || !f || dir < 0 || dir > 1 || side < 0 || side > 1) return fail(LK_ERR_ARG, "lk_halo_unpack: bad argument");
+  CHECK_LAUNCH(DISPATCH(halo_unpack)(f, buf, g, dir, side, (cudaStream_t)stream), "lk_halo_unpack");
+}
+
+int lk_advection_derivatives_4d(double* rhs, const double* f, const lk_geom* g, const double* velocities, void* stream) {
+  if (!geom_ok(g) || !rhs || !f || !velocities) return fail(LK_ERR_ARG, "lk_advection_derivatives_4d: bad argument");
+  CHECK_LAUNCH(DISPATCH(vlasov_rhs)(rhs, f, g, velocities, nullptr, nullptr, 1, g_variant, (cudaStream_t)stream),
+               "lk_advection_derivatives_4d");
+}
+int lk_acceleration_derivatives_4d(double* rhs, const double* f, const lk_geom* g, const lk_accel* a, void* stream) {
+  if (!geom_ok(g) || !rhs || !f || !accel_ok(a)) return fail(LK_ERR_ARG, "lk_acceleration_derivatives_4d: bad argument");
+  CHECK_LAUNCH(DISPATCH(vlasov_rhs)(rhs, f, g, nullptr, a, nullptr, 2 | 4, g_variant, (cudaStream_t)stream),
+               "lk_acceleration_derivatives_4d");
+}
+int lk_vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const double* velocities, const lk_accel* a,
+                  const lk_rk_update* upd, void* stream) {
+  if (!geom_ok(g) || !f || !velocities || !accel_ok(a)) return fail(LK_ERR_ARG, "lk_vlasov_rhs: bad argument");
+  if (!rhs_out && !upd) return fail(LK_ERR_ARG, "lk_vlasov_rhs: nothing to write");
+  if (upd) {
+    if (!upd->f_old || !upd->pred) return fail(LK_ERR_ARG, "lk_vlasov_rhs: rk update needs f_old and pred");
+    if (upd->pred == f) return fail(LK_ERR_ARG, "lk_vlasov_rhs: pred must not alias the evaluated state");
+    if (upd->delta_out && upd->delta_out == f) return fail(LK_ERR_ARG, "lk_vlasov_rhs: delta must not alias the evaluated state");
+  }
+  if (rhs_out == f) return fail(LK_ERR_ARG, "lk_vlasov_rhs: rhs must not alias the evaluated state");
+  CHECK_LAUNCH(DISPATCH(vlasov_rhs)(rhs_out, f, g, velocities, a, upd, 3, g_variant, (cudaStream_t)stream), "lk_vlasov_rhs");
+}
+
+int lk_reduce_4d_to_2d(double* dst, const double* f, const lk_geom* g, double dv, double weight, void* stream) {
+  if (!geom_ok(g) || !dst || !f) return fail(LK_ERR_ARG, "lk_reduce_4d_to_2d: bad argument");
+  const int chunks = moment_chunks(g);
+  double* s = scratch(0, sizeof(double) * (size_t)g->n[0] * g->n[1] * chunks);
+  if (!s) return cuda_fail(cudaGetLastError(), "lk_reduce_4d_to_2d: scratch");
+  CHECK_LAUNCH(DISPATCH(reduce_4d_to_2d)(dst, f, g, dv, weight, s, chunks, (cudaStream_t)stream), "lk_reduce_4d_to_2d");
+}
+int lk_current_density(double* Jx, double* Jy, double* Jz, const double* f, const lk_geom* g, const double* velocities,
+                       const double* vz, double dv, double weight, void* stream) {
+  if (!geom_ok(g) || !Jx || !Jy || !Jz || !f || !velocities || !vz) return fail(LK_ERR_ARG, "lk_current_density: bad argument");
+  const int chunks = moment_chunks(g);
+  double* s = scratch(0, sizeof(double) * 3 * (size_t)g->n[0] * g->n[1] * chunks);
+  if (!s) return cuda_fail(cudaGetLastError(), "lk_current_density: scratch");
+  CHECK_LAUNCH(DISPATCH(current_density)(Jx, Jy, Jz, f, g, velocities, vz, dv, weight, s, chunks, (cudaStream_t)stream),
+               "lk_current_density");
+}
+int lk_ke_e_dot(double* out, const double* f, const lk_geom* g, double charge, const double* velocities,
+                const double* ext, void* stream) {
+  if (!geom_ok(g) || !out || !f || !velocities || !ext) return fail(LK_ERR_ARG, "lk_ke_e_dot: bad argument");
+  const int nblocks = 148 * 4;
+  double* s = scratch(1, sizeof(double) * nblocks);
+  if (!s) return cuda_fail(cudaGetLastError(), "lk_ke_e_dot: scratch");
+  CHECK_LAUNCH(DISPATCH(ke_e_dot)(out, f, g, charge, velocities, ext, s, nblocks, (cudaStream_t)stream), "lk_ke_e_dot");
+}
+
+// ---- Poisson ----
+int lk_poisson_plan_create(lk_poisson_plan** plan, int nx, int ny, int ng, int order, double Lx, double Ly) {
+  if (!plan || nx < 1 || ny < 1 || !(Lx > 0) || !(Ly > 0) || !(order == 4 || order == 6 || order == -1) || ng < 1)
+    return fail(LK_ERR_ARG, "lk_poisson_plan_create: bad argument");
+  // symbols of the 4th/6th-order FD Laplacian, pre-multiplied by nx*ny (LokiPoissonSolveFFT.C:66-115)
+  const double pi = 4.0 * atan(1.0);
+  const int nyh = ny / 2 + 1;
+  std::vector<double> sx(nx), sy(nyh), cx(2 * nx), cy(2 * ny);
+  const double dx = Lx / nx, dy = Ly / ny;
+  auto sym = [&](double h, double k) {
+    double dpdm = (2.0 * cos(h * k) - 2.0) / pow(h, 2.0);
+    if (order == 4) return dpdm - pow(h, 2.0) / 12.0 * pow(dpdm, 2.0);
+    if (order == 6) return dpdm - pow(h, 2.0) / 12.0 * pow(dpdm, 2.0) + pow(h, 4.0) / 90.0 * pow(dpdm, 3.0);
+    return -k * k;
+  };
+  for (int i = 0; i < nx; ++i) {
+    double kx = 0.0;
+    if (i >= 1) kx = (2 * i < nx) ? (2.0 * pi / Lx) * i : (2.0 * pi / Lx) * (nx - i);
+    sx[i] = sym(dx, kx) * (nx * ny);
+  }
+  for (int i = 0; i < nyh; ++i) {
+    double ky = (i >= 1) ? (2.0 * pi / Ly) * i : 0.0;
+    sy[i] = sym(dy, ky) * (nx * ny);
+  }
+  for (int k = 0; k < nx; ++k) { cx[2 * k] = cos(2.0 * pi * k / nx); cx[2 * k + 1] = sin(2.0 * pi * k / nx); }
+  for (int k = 0; k < ny; ++k) { cy[2 * k] = cos(2.0 * pi * k / ny); cy[2 * k + 1] = sin(2.0 * pi * k / ny); }
+  lk_poisson_plan* p = new lk_poisson_plan();
+  memset(p, 0, sizeof(*p));
+  p->nx = nx; p->ny = ny; p->ng = ng; p->order = order;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](double** d, const std::vector<double>& h) {
+    if (e != cudaSuccess) return;
+    e = cudaMalloc((void**)d, sizeof(double) * h.size());
+    if (e == cudaSuccess) e = cudaMemcpy(*d, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice);
+  };
+  up(&p->sx, sx); up(&p->sy, sy); up(&p->cx, cx); up(&p->cy, cy);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->T, sizeof(double) * 2 * nx * nyh);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->X, sizeof(double) * 2 * nx * nyh);
+  if (e != cudaSuccess) {
+    lk_poisson_plan_destroy(p);
+    return cuda_fail(e, "lk_poisson_plan_create");
+  }
+  *plan = p;
+  return LK_OK;
+}
+void lk_poisson_plan_destroy(lk_poisson_plan* p) {
+  if (!p) return;
+  cudaFree(p->sx); cudaFree(p->sy); cudaFree(p->cx); cudaFree(p->cy); cudaFree(p->T); cudaFree(p->X);
+  delete p;
+}
+int lk_electric_field(lk_poisson_plan* p, double* rho, double* phi, double* em, const double* dx, void* stream) {
+  if (!p || !rho || !phi || !em || !dx) return fail(LK_ERR_ARG, "lk_electric_field: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  // EMSolverBase::electricField (EMSolverBase.C:270-371), single EM "processor" branch
+  e = DISPATCH(neutralize)(rho, p->nx, p->ny, p->ng, st);
+  if (e == cudaSuccess) e = DISPATCH(poisson_dft)(phi, rho, p->nx, p->ny, p->ng, p->sx, p->sy, p->cx, p->cy, p->T, p->X, st);
+  if (e == cudaSuccess) e = DISPATCH(periodic_fill_2d)(phi, p->nx, p->ny, p->ng, 1, 1, 1, st);
+  const size_t pl = (size_t)(p->nx + 2 * p->ng) * (p->ny + 2 * p->ng);
+  if (e == cudaSuccess) e = cudaMemsetAsync(em, 0, sizeof(double) * 2 * pl, st);  // m_em_vars = 0.0
+  if (e == cudaSuccess) e = DISPATCH(efield_from_phi)(em, phi, p->nx, p->ny, p->ng, p->order == -1 ? 4 : p->order, dx[0], dx[1], st);
+  if (e == cudaSuccess) e = DISPATCH(periodic_fill_2d)(em, p->nx, p->ny, p->ng, 2, 1, 1, st);
+  if (e != cudaSuccess) return cuda_fail(e, "lk_electric_field");
+  return LK_OK;
+}
+int lk_periodic_fill_2d(double* u, int n1, int n2, int ng, int ncomp, int px, int py, void* stream) {
+  if (!u || n1 < 1 || n2 < 1 || ng < 1 || ncomp < 1) return fail(LK_ERR_ARG, "lk_periodic_fill_2d: bad argument");
+  CHECK_LAUNCH(DISPATCH(periodic_fill_2d)(u, n1, n2, ng, ncomp, px, py, (cudaStream_t)stream), "lk_periodic_fill_2d");
+}
+int lk_xpby2d(double* x, const double* y, double b, int n1, int n2, int ng, int ncomp, void* stream) {
+  if (!x || !y || n1 < 1 || n2 < 1 || ng < 0 || ncomp < 1) return fail(LK_ERR_ARG, "lk_xpby2d: bad argument");
+  CHECK_LAUNCH(DISPATCH(xpby2d)(x, y, b, n1, n2, ng, ncomp, (cudaStream_t)stream), "lk_xpby2d");
+}
+int lk_form_accel(double* accel, const double* em, const double* ext, double normalization, int n1, int n2, int ng,
+                  void* stream) {
+  if (!accel || !em || n1 < 1 || n2 < 1 || ng < 0) return fail(LK_ERR_ARG, "lk_form_accel: bad argument");
+  CHECK_LAUNCH(DISPATCH(form_accel)(accel, em, ext, normalization, n1, n2, ng, (cudaStream_t)stream), "lk_form_accel");
+}
+int lk_maxwell_rhs(double* rhs, const double* em, const double* Jx, const double* Jy, const double* Jz, int n1, int n2,
+                   int ng, int order, const double* dx, double c, double av_weak, double av_strong, void* stream) {
+  if (!rhs || !em || !Jx || !Jy || !Jz || !dx || n1 < 1 || n2 < 1 || !((order == 4 && ng == 2) || (order == 6 && ng == 3)))
+    return fail(LK_ERR_ARG, "lk_maxwell_rhs: bad argument");
+  CHECK_LAUNCH(DISPATCH(maxwell_rhs)(rhs, em, Jx, Jy, Jz, n1, n2, ng, order, dx[0], dx[1], c, av_weak, av_strong,
+                                     (cudaStream_t)stream),
+               "lk_maxwell_rhs");
+}
+
+// ---- memory helpers ----
+int lk_malloc(void** p, int64_t bytes) {
+  if (!p || bytes < 0) return fail(LK_ERR_ARG, "lk_malloc: bad argument");
+  cudaError_t e = cudaMalloc(p, (size_t)bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "lk_malloc");
+  return LK_OK;
+}
+int lk_free(void* p) {
+  cudaError_t e = cudaFree(p);
+  if (e != cudaSuccess) return cuda_fail(e, "lk_free");
+  return LK_OK;
+}
+int lk_memcpy_h2d(void* dst, const void* src, int64_t bytes) {
+  cudaError_t e = cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return cuda_fail(e, "lk_memcpy_h2d");
+  return LK_OK;
+}
+int lk_memcpy_d2h(void* dst, const void* src, int64_t bytes) {
+  cudaError_t e = cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return cuda_fail(e, "lk_memcpy_d2h");
+  return LK_OK;
+}
+int lk_memset(void* p, int value, int64_t bytes) {
+  cudaError_t e = cudaMemset(p, value, (size_t)bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "lk_memset");
+  return LK_OK;
+}
+int lk_sync(void* stream) {
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "lk_sync");
+  return LK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,261 @@
+// lk_device.cuh -- device-side building blocks shared by all kernels of the Vlasov RHS path.
+//
+// Compiled twice (see build.py): LK_STRICT=0 -> namespace lkfast (FMA contraction on, one reciprocal
+// per WENO fit), LK_STRICT=1 with -fmad=false -> namespace lkstrict (the reference's operation order,
+// IEEE divisions, bit-identical to gfortran -O2 of KineticSpeciesF.f).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifndef LK_STRICT
+#define LK_STRICT 0
+#endif
+#if LK_STRICT
+#define LK_NS lkstrict
+#else
+#define LK_NS lkfast
+#endif
+
+namespace LK_NS {
+
+typedef long long i64;
+
+struct DGeo {
+  int n[4];    // interior cells
+  int nd[4];   // data-box extents (n + 2 ng)
+  int ng, order;
+  i64 s[4];    // element strides of f(i1,i2,i3,i4)
+  double dx[4];
+};
+
+struct DAccel {
+  int kind;  // 0 VP, 1 VM
+  const double* field;
+  const double* vz;
+  const double* vxf;  // vxface_velocities (n3d+1, n4d, 2)
+  const double* vyf;  // vyface_velocities (n3d, n4d+1, 2)
+  double norm, bz;
+};
+
+struct DUpd {
+  const double* f_old;
+  const double* delta_in;
+  double* delta_out;
+  double* pred;
+  double w_delta, c_pred;
+  int use_delta;
+  int active;
+};
+
+__device__ __forceinline__ i64 gidx(const DGeo& g, int i1, int i2, int i3, int i4) {
+  return (i64)i1 + g.s[1] * i2 + g.s[2] * i3 + g.s[3] * i4;
+}
+
+// ---------------------------------------------------------------------------------------------
+// acceleration at a vx-face (i3 = face index) / vy-face: setphasespacevel4D (KineticSpeciesF.f:78-80,
+// 98-100) and setphasespacevelmaxwell4D (:154-158, 176-180), evaluated on the fly.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double accel_x(const DAccel& a, const DGeo& g, int i1, int i2, int i3, int i4) {
+  const double vy = __ldg(a.vxf + i3 + (i64)(g.nd[2] + 1) * (i4 + (i64)g.nd[3]));
+  const i64 p = i1 + (i64)g.nd[0] * i2;
+  const i64 pl = (i64)g.nd[0] * g.nd[1];
+  if (a.kind == 0) {
+    return __ldg(a.field + p) + a.norm * vy * a.bz;
+  } else {
+    const double ex = __ldg(a.field + p), by = __ldg(a.field + p + 4 * pl), bzf = __ldg(a.field + p + 5 * pl);
+    const double vz = __ldg(a.vz + p);
+    return a.norm * (ex + vy * bzf + vy * a.bz - vz * by);
+  }
+}
+__device__ __forceinline__ double accel_y(const DAccel& a, const DGeo& g, int i1, int i2, int i3, int i4) {
+  const double vx = __ldg(a.vyf + i3 + (i64)g.nd[2] * i4);
+  const i64 p = i1 + (i64)g.nd[0] * i2;
+  const i64 pl = (i64)g.nd[0] * g.nd[1];
+  if (a.kind == 0) {
+    return __ldg(a.field + p + pl) - a.norm * vx * a.bz;
+  } else {
+    const double ey = __ldg(a.field + p + pl), bx = __ldg(a.field + p + 3 * pl), bzf = __ldg(a.field + p + 5 * pl);
+    const double vz = __ldg(a.vz + p);
+    return a.norm * (ey + vz * bx - vx * bzf - vx * a.bz);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reciprocal for the production path: MUFU.RCP64H seed (rel. err 2^-23) + two Newton steps.
+// Inputs are sums of positive smoothness products, far from 0/inf/denormal.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double s) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+  double e = fma(-s, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-s, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// WENO43Fit4D (KineticSpeciesF.f:723-790).  `pos` is the reference's `vel.gt.0.0`.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double weno43(double um2, double um1, double u0, double up1, bool pos) {
+#if LK_STRICT
+  const double eps = 1.e-10;
+  double tmp = 1.0 / 6.0;
+  double fl = tmp * (-um2 + 5.0 * um1 + 2.0 * u0);
+  double fr = tmp * (2.0 * um1 + 5.0 * u0 - up1);
+  double c1l = u0 - 2.0 * um1 + um2;
+  double c2l = u0 - um2;
+  double c1r = up1 - 2.0 * u0 + um1;
+  double c2r = up1 - um1;
+  double bl = 8.0 * tmp * (c1l * c1l) + 0.5 * c1l * c2l + 0.25 * (c2l * c2l);
+  double br = 8.0 * tmp * (c1r * c1r) - 0.5 * c1r * c2r + 0.25 * (c2r * c2r);
+  double al = 1.0 / ((eps + bl) * (eps + bl));
+  double ar = 1.0 / ((eps + br) * (eps + br));
+  tmp = 1.0 / (al + ar);
+  double wl = tmp * al;
+  double wr = tmp * ar;
+  al = wl * (0.75 + wl * (wl - 1.5));
+  ar = wr * (0.75 + wr * (wr - 1.5));
+  tmp = 1.0 / (al + ar);
+  wl = tmp * al;
+  wr = tmp * ar;
+  double wmax = fmax(wl, wr);
+  double wmin = fmin(wl, wr);
+  if (pos) { wl = wmax; wr = wmin; } else { wl = wmin; wr = wmax; }
+  return (wl * fl + wr * fr);
+#else
+  // Same function, algebraically rearranged to ONE reciprocal: with A=(eps+bl)^2, B=(eps+br)^2,
+  // S=A+B the unmapped weights are wl=B/S, wr=A/S; the Henrick-mapped, renormalised weights are
+  // nl/(nl+nr), nr/(nl+nr) with nl = B(0.75 S^2 + B(B-1.5S)), nr = A(0.75 S^2 + A(A-1.5S)).
+  const double eps = 1.e-10;
+  const double fl6 = fma(5.0, um1, fma(2.0, u0, -um2));
+  const double fr6 = fma(5.0, u0, fma(2.0, um1, -up1));
+  const double c1l = fma(-2.0, um1, u0) + um2;
+  const double c1r = fma(-2.0, u0, up1) + um1;
+  const double hl = 0.5 * (u0 - um2);
+  const double hr = 0.5 * (up1 - um1);
+  const double el = fma(c1l, fma(4.0 / 3.0, c1l, hl), fma(hl, hl, eps));
+  const double er = fma(c1r, fma(4.0 / 3.0, c1r, -hr), fma(hr, hr, eps));
+  const double A = el * el, B = er * er;
+  const double S = A + B;
+  const double q = 0.75 * (S * S);
+  const double m = -1.5 * S;
+  const double nl = B * fma(B, B + m, q);
+  const double nr = A * fma(A, A + m, q);
+  const double r = fast_rcp(nl + nr) * (1.0 / 6.0);
+  const double nmax = fmax(nl, nr), nmin = fmin(nl, nr);
+  const double wl = pos ? nmax : nmin;
+  const double wr = pos ? nmin : nmax;
+  return fma(wl, fl6, wr * fr6) * r;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// WENO65Fit4D (KineticSpeciesF.f:914-979)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double weno65(double um3, double um2, double um1, double u0, double up1,
+                                         double up2, bool pos) {
+#if LK_STRICT
+  const double eps = 1.e-10;
+  double fl = (2.0 * um3 - 13.0 * um2 + 47.0 * um1 + 27.0 * u0 - 3.0 * up1) / 60.0;
+  double fr = (-3.0 * um2 + 27.0 * um1 + 47.0 * u0 - 13.0 * up1 + 2.0 * up2) / 60.0;
+  double bl = 0.5489E4 / 0.105E3 * (um1 * um1) +
+              (-0.2242428E7 * u0 - 0.1887108E7 * um2 + 0.410226E6 * um3 + 0.557646E6 * up1) * um1 / 0.30240E5 +
+              0.75329E5 / 0.3780E4 * (um2 * um2) +
+              (0.1259696E7 * u0 - 0.275318E6 * um3 - 0.302534E6 * up1) * um2 / 0.30240E5 +
+              0.33727E5 / 0.30240E5 * (um3 * um3) +
+              (-0.264314E6 * u0 + 0.61952E5 * up1) * um3 / 0.30240E5 +
+              0.106409E6 / 0.3780E4 * (u0 * u0) -
+              0.227749E6 / 0.15120E5 * u0 * up1 +
+              0.69217E5 / 0.30240E5 * (up1 * up1);
+  double br = 0.106409E6 / 0.3780E4 * (um1 * um1) +
+              (-0.2242428E7 * u0 - 0.455498E6 * um2 + 0.1259696E7 * up1 - 0.264314E6 * up2) * um1 / 0.30240E5 +
+              0.69217E5 / 0.30240E5 * (um2 * um2) +
+              (0.557646E6 * u0 - 0.302534E6 * up1 + 0.61952E5 * up2) * um2 / 0.30240E5 +
+              0.75329E5 / 0.3780E4 * (up1 * up1) +
+              (-0.1887108E7 * u0 - 0.275318E6 * up2) * up1 / 0.30240E5 +
+              0.5489E4 / 0.105E3 * (u0 * u0) +
+              0.68371E5 / 0.5040E4 * u0 * up2 +
+              0.33727E5 / 0.30240E5 * (up2 * up2);
+  double al = 1.0 / ((eps + bl) * (eps + bl));
+  double ar = 1.0 / ((eps + br) * (eps + br));
+  double wl = al / (al + ar);
+  double wr = ar / (al + ar);
+  al = wl * (0.75 + wl * (wl - 1.5));
+  ar = wr * (0.75 + wr * (wr - 1.5));
+  wl = al / (al + ar);
+  wr = ar / (al + ar);
+  double wmax = fmax(wl, wr);
+  double wmin = fmin(wl, wr);
+  if (pos) { wl = wmax; wr = wmin; } else { wl = wmin; wr = wmax; }
+  return (wl * fl + wr * fr);
+#else
+  const double eps = 1.e-10;
+  const double k = 1.0 / 30240.0;
+  const double fl60 = fma(2.0, um3, fma(-13.0, um2, fma(47.0, um1, fma(27.0, u0, -3.0 * up1))));
+  const double fr60 = fma(-3.0, um2, fma(27.0, um1, fma(47.0, u0, fma(-13.0, up1, 2.0 * up2))));
+  // smoothness indicators as nested quadratic forms; constants pre-divided
+  double t;
+  t = fma(5489.0 / 105.0, um1, fma(-2242428.0 * k, u0, fma(-1887108.0 * k, um2, fma(410226.0 * k, um3, 557646.0 * k * up1))));
+  double bl = fma(t, um1, eps);
+  t = fma(75329.0 / 3780.0, um2, fma(1259696.0 * k, u0, fma(-275318.0 * k, um3, -302534.0 * k * up1)));
+  bl = fma(t, um2, bl);
+  t = fma(33727.0 * k, um3, fma(-264314.0 * k, u0, 61952.0 * k * up1));
+  bl = fma(t, um3, bl);
+  t = fma(106409.0 / 3780.0, u0, -227749.0 / 15120.0 * up1);
+  bl = fma(t, u0, bl);
+  bl = fma(69217.0 * k * up1, up1, bl);
+
+  t = fma(106409.0 / 3780.0, um1, fma(-2242428.0 * k, u0, fma(-455498.0 * k, um2, fma(1259696.0 * k, up1, -264314.0 * k * up2))));
+  double br = fma(t, um1, eps);
+  t = fma(69217.0 * k, um2, fma(557646.0 * k, u0, fma(-302534.0 * k, up1, 61952.0 * k * up2)));
+  br = fma(t, um2, br);
+  t = fma(75329.0 / 3780.0, up1, fma(-1887108.0 * k, u0, -275318.0 * k * up2));
+  br = fma(t, up1, br);
+  t = fma(5489.0 / 105.0, u0, 68371.0 / 5040.0 * up2);
+  br = fma(t, u0, br);
+  br = fma(33727.0 * k * up2, up2, br);
+
+  const double A = bl * bl, B = br * br;
+  const double S = A + B;
+  const double q = 0.75 * (S * S);
+  const double m = -1.5 * S;
+  const double nl = B * fma(B, B + m, q);
+  const double nr = A * fma(A, A + m, q);
+  const double r = fast_rcp(nl + nr) * (1.0 / 60.0);
+  const double nmax = fmax(nl, nr), nmin = fmin(nl, nr);
+  const double wl = pos ? nmax : nmin;
+  const double wr = pos ? nmin : nmax;
+  return fma(wl, fl60, wr * fr60) * r;
+#endif
+}
+
+// face value between cells p and p+s (p addresses cell i; the face is i+1/2)
+template <int ORDER>
+__device__ __forceinline__ double fit_right(const double* __restrict__ p, i64 s, bool pos) {
+  if (ORDER == 4) return weno43(p[-s], p[0], p[s], p[2 * s], pos);
+  return weno65(p[-2 * s], p[-s], p[0], p[s], p[2 * s], p[3 * s], pos);
+}
+
+// -(c*uR - c*uL)/d in the reference's form (KineticSpeciesF.f:2000-2002); the production build
+// multiplies by the reciprocal spacing instead of dividing.
+__device__ __forceinline__ double flux_diff(double c, double uR, double uL, double d, double rd) {
+#if LK_STRICT
+  (void)rd;
+  return (c * uR - c * uL) / d;
+#else
+  (void)d;
+  return (c * uR - c * uL) * rd;
+#endif
+}
+
+// RK stage update fused behind the rhs evaluation (RK4Integrator.H:149-171)
+__device__ __forceinline__ void rk_update(const DUpd& u, i64 idx, double rhs) {
+  double d = u.w_delta * rhs;
+  if (u.delta_in) d = u.delta_in[idx] + d;
+  if (u.delta_out) u.delta_out[idx] = d;
+  const double inc = u.use_delta ? d : rhs;
+  u.pred[idx] = u.f_old[idx] + u.c_pred * inc;
+}
+
+}  // namespace LK_NS

