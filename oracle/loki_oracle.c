@@ -643,3 +643,94 @@ void ok_efield_from_potential(double* em, const double* phi, int n1, int n2, int
     }
 #undef PH
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Maxwell (MaxwellF.f:62-93 xpby2d, 97-355 maxwellevalrhs, 442-469 maxwellevalvzrhs).  Supergrid
+ * absorbing layers are not restated: without them SGMetricFunction returns nu = 1.0 exactly
+ * (MaxwellF.f:413-421 with xi = 0), and a multiplication by 1.0 is exact.
+ * Integer powers follow the compiler's repeated-squaring expansion (x**4 = (x*x)*(x*x) ...).
+ * ------------------------------------------------------------------------------------------ */
+void ok_xpby2d(double* x, const double* y, double b, int n1, int n2, int ng, int ncomp) {
+  const int64_t n1d = n1 + 2 * ng, n2d = n2 + 2 * ng;
+  for (int c = 0; c < ncomp; ++c)
+    for (int i2 = ng; i2 < ng + n2; ++i2)
+      for (int i1 = ng; i1 < ng + n1; ++i1) {
+        int64_t o = i1 + n1d * (i2 + n2d * c);
+        x[o] = x[o] + b * y[o];
+      }
+}
+
+static inline double p2(double x) { return x * x; }
+static inline double p3(double x) { return (x * x) * x; }
+static inline double p4(double x) { double t = x * x; return t * t; }
+static inline double p5(double x) { double t = x * x; return (t * x) * t; }
+static inline double p6(double x) { double t = (x * x) * x; return t * t; }
+
+void ok_maxwell_eval_rhs(double* rhs, const double* em, const double* Jx, const double* Jy,
+                         const double* Jz, int n1, int n2, int ng, int order, const double* dx,
+                         double c, double avWeak, double avStrong) {
+  const int64_t n1d = n1 + 2 * ng, n2d = n2 + 2 * ng, pl = n1d * n2d;
+  const double csquared = p2(c);
+#define EMV(i1, i2, k) em[(i1) + n1d * (i2) + pl * ((k)-1)]
+#define DEM(i1, i2, k) rhs[(i1) + n1d * (i2) + pl * ((k)-1)]
+#define D4X(k) ((EMV(i1 - 2, i2, k) - 8.0 * EMV(i1 - 1, i2, k) + 8.0 * EMV(i1 + 1, i2, k) - EMV(i1 + 2, i2, k)) / (12.0 * dx[0]))
+#define D4Y(k) ((EMV(i1, i2 - 2, k) - 8.0 * EMV(i1, i2 - 1, k) + 8.0 * EMV(i1, i2 + 1, k) - EMV(i1, i2 + 2, k)) / (12.0 * dx[1]))
+#define D6X(k) ((-1.0 * EMV(i1 - 3, i2, k) + 9.0 * EMV(i1 - 2, i2, k) - 45.0 * EMV(i1 - 1, i2, k) + 45.0 * EMV(i1 + 1, i2, k) - 9.0 * EMV(i1 + 2, i2, k) + 1.0 * EMV(i1 + 3, i2, k)) / (60.0 * dx[0]))
+#define D6Y(k) ((-1.0 * EMV(i1, i2 - 3, k) + 9.0 * EMV(i1, i2 - 2, k) - 45.0 * EMV(i1, i2 - 1, k) + 45.0 * EMV(i1, i2 + 1, k) - 9.0 * EMV(i1, i2 + 2, k) + 1.0 * EMV(i1, i2 + 3, k)) / (60.0 * dx[1]))
+  for (int i2 = ng; i2 < ng + n2; ++i2)
+    for (int i1 = ng; i1 < ng + n1; ++i1) {
+      double Exdy, Eydx, Ezdx, Ezdy, Bxdy, Bydx, Bzdx, Bzdy;
+      const double nux = 1.0, nuy = 1.0;
+      if (order == 4) {
+        Exdy = nuy * D4Y(1); Eydx = nux * D4X(2); Ezdx = nux * D4X(3); Ezdy = nuy * D4Y(3);
+        Bxdy = nuy * D4Y(4); Bydx = nux * D4X(5); Bzdx = nux * D4X(6); Bzdy = nuy * D4Y(6);
+      } else {
+        Exdy = nuy * D6Y(1); Eydx = nux * D6X(2); Ezdx = nux * D6X(3); Ezdy = nuy * D6Y(3);
+        Bxdy = nuy * D6Y(4); Bydx = nux * D6X(5); Bzdx = nux * D6X(6); Bzdy = nuy * D6Y(6);
+      }
+      const int64_t o = i1 + n1d * i2;
+      DEM(i1, i2, 1) = csquared * (Bzdy)-Jx[o];
+      DEM(i1, i2, 2) = -csquared * (Bzdx)-Jy[o];
+      DEM(i1, i2, 3) = csquared * (Bydx - Bxdy) - Jz[o];
+      DEM(i1, i2, 4) = -Ezdy;
+      DEM(i1, i2, 5) = Ezdx;
+      DEM(i1, i2, 6) = Exdy - Eydx;
+    }
+  if (avWeak > 0.0 || avStrong > 0.0) {
+    for (int k = 1; k <= 6; ++k)
+      for (int i2 = ng; i2 < ng + n2; ++i2)
+        for (int i1 = ng; i1 < ng + n1; ++i1) {
+          if (order == 4) {
+            double uxxxx = (1.0 * EMV(i1 - 2, i2, k) - 4.0 * EMV(i1 - 1, i2, k) + 6.0 * EMV(i1, i2, k) -
+                            4.0 * EMV(i1 + 1, i2, k) + 1.0 * EMV(i1 + 2, i2, k)) / (p4(dx[0]));
+            double uyyyy = (1.0 * EMV(i1, i2 - 2, k) - 4.0 * EMV(i1, i2 - 1, k) + 6.0 * EMV(i1, i2, k) -
+                            4.0 * EMV(i1, i2 + 1, k) + 1.0 * EMV(i1, i2 + 2, k)) / (p4(dx[1]));
+            DEM(i1, i2, k) = DEM(i1, i2, k) -
+                             (avWeak * c * p4(dx[0]) + avStrong * c * p3(dx[0])) / 16.0 * uxxxx -
+                             (avWeak * c * p4(dx[1]) + avStrong * c * p3(dx[1])) / 16.0 * uyyyy;
+          } else {
+            double u6x = (1.0 * EMV(i1 - 3, i2, k) - 6.0 * EMV(i1 - 2, i2, k) + 15.0 * EMV(i1 - 1, i2, k) -
+                          20.0 * EMV(i1, i2, k) + 15.0 * EMV(i1 + 1, i2, k) - 6.0 * EMV(i1 + 2, i2, k) +
+                          1.0 * EMV(i1 + 3, i2, k)) / (p6(dx[0]));
+            double u6y = (1.0 * EMV(i1, i2 - 3, k) - 6.0 * EMV(i1, i2 - 2, k) + 15.0 * EMV(i1, i2 - 1, k) -
+                          20.0 * EMV(i1, i2, k) + 15.0 * EMV(i1, i2 + 1, k) - 6.0 * EMV(i1, i2 + 2, k) +
+                          1.0 * EMV(i1, i2 + 3, k)) / (p6(dx[1]));
+            DEM(i1, i2, k) = DEM(i1, i2, k) +
+                             (avWeak * c * p6(dx[0]) + avStrong * c * p5(dx[0])) / 64.0 * u6x +
+                             (avWeak * c * p6(dx[1]) + avStrong * c * p5(dx[1])) / 64.0 * u6y;
+          }
+        }
+  }
+#undef EMV
+#undef DEM
+#undef D4X
+#undef D4Y
+#undef D6X
+#undef D6Y
+}
+
+void ok_maxwell_eval_vz_rhs(double* rhs, const double* em, double charge_per_mass, int n1, int n2, int ng) {
+  const int64_t n1d = n1 + 2 * ng, n2d = n2 + 2 * ng, pl = n1d * n2d;
+  for (int i2 = ng; i2 < ng + n2; ++i2)
+    for (int i1 = ng; i1 < ng + n1; ++i1) rhs[i1 + n1d * i2] = charge_per_mass * em[i1 + n1d * i2 + 2 * pl];
+}

@@ -1,0 +1,168 @@
+"""Pins the hand-written oracle (oracle/loki_oracle.c) against the REFERENCE'S OWN Fortran source,
+transliterated statement by statement to C (oracle/f77toc.py -> oracle/_ref, built by oracle/Makefile
+when /root/reference is mounted) and against the golden vectors committed under tests/golden/ that
+were generated from that same library (tests/golden/make_golden.py).  Bit-for-bit."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import ref_binding
+from util import Setup
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kinetic_f77_golden.npz")
+needs_ref = pytest.mark.skipif(not ref_binding.available(), reason="oracle/_ref not built (reference tree absent)")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_binding.Ref()
+
+
+def _stencils(order, count, seed):
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(-1, 1, size=(count, order))
+    u[::3] = np.exp(-(rng.uniform(0, 6, size=(len(u[::3]), 1)) + 0.05 * np.arange(order)[None, :]) ** 2)
+    u[::5] = 0.25
+    vel = rng.uniform(-1, 1, size=count)
+    vel[::7] = 0.0
+    return u, vel
+
+
+@needs_ref
+@pytest.mark.parametrize("order", [4, 6])
+def test_pin_weno_fits(ok, ref, order):
+    u, vel = _stencils(order, 3000, order)
+    for k in range(len(vel)):
+        if order == 4:
+            assert ok.ok_weno43_fit(*u[k], vel[k]) == ref.weno43(u[k], vel[k])
+        else:
+            assert ok.ok_weno65_fit(*u[k], vel[k]) == ref.weno65(u[k], vel[k])
+
+
+CASES = [((7, 6, 9, 8), 4, (0, 0, 0, 0)), ((6, 7, 8, 7), 6, (3, -2, 5, 1))]
+
+
+@needs_ref
+@pytest.mark.parametrize("n,order,lo", CASES)
+def test_pin_kinetic_kernels(ok, ref, n, order, lo):
+    s = Setup(ok, n, order, bz=0.3)
+    R = ref
+    db, ib, data, inter = R.boxes(s, lo)
+    n1d, n2d, n3d, n4d = s.nd
+    # xpby4d
+    y = np.random.default_rng(1).uniform(-1, 1, size=s.f.shape)
+    x1, x2 = s.f.copy(), s.f.copy()
+    ok.ok_xpby4d(x1.ravel(), y.ravel(), 0.37, C.byref(s.g))
+    R.L.xpby4d_(R._p(x2), R._p(y), R._d(0.37), *db, *ib)
+    assert np.array_equal(x1, x2)
+    # setphasespacevel4D / maxwell4D
+    for maxwell in (False, True):
+        vel3, vel4, ax, ay = s.vel34(ok, maxwell)
+        r3, r4 = np.zeros_like(vel3), np.zeros_like(vel4)
+        rax, ray = C.c_double(), C.c_double()
+        if maxwell:
+            R.L.setphasespacevelmaxwell4d_(R._p(r3), R._p(r4), *db, *ib, R._p(s.vxface), R._p(s.vyface), R._d(s.norm),
+                                           R._d(s.bz), R._p(s.em), R._p(s.vz), C.byref(rax), C.byref(ray))
+        else:
+            a2 = [R._i(data[0]), R._i(data[1]), R._i(data[2]), R._i(data[3])]
+            R.L.setphasespacevel4d_(R._p(r3), R._p(r4), *db, *ib, R._p(s.vxface), R._p(s.vyface), R._d(s.norm),
+                                    R._d(s.bz), R._p(s.accel), *a2, C.byref(rax), C.byref(ray))
+        assert np.array_equal(vel3, r3) and np.array_equal(vel4, r4) and (ax, ay) == (rax.value, ray.value)
+    vel3, vel4, _, _ = s.vel34(ok, False)
+    # setAccelerationBCs4D: global box == data box interior -> touches all four velocity boundaries
+    cb = s.ic_callback(0.7, 0.9)
+    u1, u2 = s.f.copy(), s.f.copy()
+    ok.ok_set_acceleration_bcs_4d(u1.ravel(), C.byref(s.g), vel3, vel4, 1, 1, 1, 1, cb, None)
+    lower = (C.c_int * 4)(*[data[2 * k] for k in range(4)])
+    R.L.loki_ref_set_ic(cb, None, C.byref(lower))
+    R.L.setaccelerationbcs4d_(R._p(u2), *db, *db, *ib, R._i(order), R._p(vel3), R._p(vel4), C.byref(C.c_int64(0)))
+    assert np.array_equal(u1, u2)
+    # derivatives
+    dxs = np.array(s.dx)
+    r1, r2 = np.zeros_like(s.f), np.zeros_like(s.f)
+    ok.ok_advection_derivatives_4d(r1.ravel(), s.f.ravel(), C.byref(s.g), s.vel1, s.vel2)
+    R.L.computeadvectionderivatives4d_(R._p(r2), R._p(s.f), *db, *ib, R._p(s.vel1), R._p(s.vel2), R._p(dxs), R._i(order))
+    assert np.array_equal(r1, r2)
+    ok.ok_acceleration_derivatives_4d(r1.ravel(), s.f.ravel(), C.byref(s.g), vel3, vel4)
+    R.L.computeaccelerationderivatives4d_(R._p(r2), R._p(s.f), *db, *ib, R._p(vel3), R._p(vel4), R._p(dxs), R._i(order))
+    assert np.array_equal(r1, r2) and np.any(r1 != 0)
+    # currents + ke_e_dot
+    J1 = [np.zeros_like(s.f) for _ in range(3)]
+    J2 = [np.zeros_like(s.f) for _ in range(3)]
+    ok.ok_compute_currents(C.byref(s.g), s.velocities, s.f.ravel(), s.vz.ravel(), *[j.ravel() for j in J1])
+    R.L.computecurrents_(*db, *ib, R._p(s.velocities), R._p(s.f), R._p(s.vz), *[R._p(j) for j in J2])
+    assert all(np.array_equal(a, b) for a, b in zip(J1, J2))
+    ext = np.ascontiguousarray(np.random.default_rng(2).uniform(-1, 1, size=(2, n2d, n1d)))
+    k1 = ok.ok_compute_ke_e_dot(C.byref(s.g), s.f.ravel(), s.charge, s.velocities, ext.ravel(), 0.0)
+    k2 = C.c_double(0.0)
+    xlo = np.zeros(4)
+    R.L.computekeedot_(*db, *ib, R._p(xlo), R._p(xlo), R._p(dxs), R._p(s.f), R._d(s.charge), R._p(s.velocities), R._p(ext), C.byref(k2))
+    assert k1 == k2.value
+
+
+@needs_ref
+@pytest.mark.parametrize("order", [4, 6])
+def test_pin_field_kernels(ok, ref, order):
+    R = ref
+    ng = 2 if order == 4 else 3
+    n1, n2 = 9, 7
+    n1d, n2d = n1 + 2 * ng, n2 + 2 * ng
+    rng = np.random.default_rng(3)
+    b = lambda lo, n: [R._i(lo - ng), R._i(lo + n - 1 + ng)]
+    bi = lambda lo, n: [R._i(lo), R._i(lo + n - 1)]
+    db = b(0, n1) + b(0, n2)
+    ib = bi(0, n1) + bi(0, n2)
+    rho = rng.uniform(-1, 1, size=(n2d, n1d))
+    r1, r2 = rho.copy(), rho.copy()
+    ok.ok_neutralize_charge(r1.ravel(), n1, n2, ng)
+    R.L.neutralizecharge4d_(*db, *ib, R._p(r2), R._i(0))
+    assert np.array_equal(r1, r2)
+    phi = rng.uniform(-1, 1, size=(n2d, n1d))
+    dx = np.array([0.3, 0.7, 1.0, 1.0])
+    e1, e2 = np.zeros((2, n2d, n1d)), np.zeros((2, n2d, n1d))
+    ok.ok_efield_from_potential(e1.ravel(), phi.ravel(), n1, n2, ng, order, 2, dx)
+    R.L.computeefieldfrompotential_(*db, *ib, R._i(order), R._i(2), R._p(dx), R._p(e2), R._p(phi))
+    assert np.array_equal(e1, e2)
+    # Maxwell rhs (no supergrid layer: SG bounds at the domain ends), with and without dissipation
+    em = rng.uniform(-1, 1, size=(6, n2d, n1d))
+    J = [rng.uniform(-1, 1, size=(n2d, n1d)) for _ in range(3)]
+    xlo, xhi = np.array([0.0, 0.0, 0, 0]), np.array([n1 * dx[0], n2 * dx[1], 0, 0])
+    sglo, sghi = xlo[:2].copy(), xhi[:2].copy()
+    for avw, avs in ((0.0, 0.0), (0.1, 1.6 / 22.36)):
+        m1, m2 = np.zeros_like(em), np.zeros_like(em)
+        ok_fn = ok.ok_maxwell_eval_rhs
+        ok_fn.argtypes = None
+        ok_fn(R._p(m1), R._p(em), R._p(J[0]), R._p(J[1]), R._p(J[2]), n1, n2, ng, order, R._p(dx), C.c_double(22.36),
+              C.c_double(avw), C.c_double(avs))
+        R.L.maxwellevalrhs_(*db, *ib, R._p(xlo), R._p(xhi), R._p(dx), R._d(22.36), R._d(avw), R._d(avs), R._i(order),
+                            R._p(sglo), R._p(sghi), R._p(em), R._p(J[0]), R._p(J[1]), R._p(J[2]), R._p(m2))
+        assert np.array_equal(m1, m2)
+    x1, x2 = em.copy(), em.copy()
+    ok.ok_xpby2d.argtypes = None
+    ok.ok_xpby2d(R._p(x1), R._p(m1), C.c_double(0.01), n1, n2, ng, 6)
+    R.L.xpby2d_(R._p(x2), R._p(m1), R._d(0.01), *db, *ib, R._i(6))
+    assert np.array_equal(x1, x2)
+
+
+def test_oracle_matches_committed_golden_vectors(ok):
+    """golden vectors generated from the transliterated reference Fortran (tests/golden/make_golden.py)"""
+    gold = np.load(GOLD)
+    for order in (4, 6):
+        u, vel, face = gold["weno%d_u" % order], gold["weno%d_vel" % order], gold["weno%d_face" % order]
+        out = np.empty(len(vel))
+        (ok.ok_weno43_fit_v if order == 4 else ok.ok_weno65_fit_v)(np.ascontiguousarray(u).ravel(), vel, out, len(vel))
+        assert np.array_equal(out, face)
+        n = tuple(int(v) for v in gold["rhs%d_n" % order])
+        s = Setup(ok, n, order, bz=0.3, seed=int(gold["rhs%d_seed" % order]))
+        assert np.array_equal(s.f, gold["rhs%d_f" % order])          # same seeded input
+        vel3, vel4, ax, ay = s.vel34(ok)
+        r = np.zeros_like(s.f)
+        ok.ok_advection_derivatives_4d(r.ravel(), s.f.ravel(), C.byref(s.g), s.vel1, s.vel2)
+        ok.ok_acceleration_derivatives_4d(r.ravel(), s.f.ravel(), C.byref(s.g), vel3, vel4)
+        assert np.array_equal(r, gold["rhs%d_rhs" % order])
+        assert (ax, ay) == tuple(gold["rhs%d_amax" % order])
+        u1 = s.f.copy()
+        ok.ok_set_acceleration_bcs_4d(u1.ravel(), C.byref(s.g), vel3, vel4, 1, 1, 1, 1, s.ic_callback(0.7, 0.9), None)
+        assert np.array_equal(u1, gold["rhs%d_bc" % order])
