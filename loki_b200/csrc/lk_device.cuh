@@ -16,6 +16,11 @@
 #define LK_NS lkfast
 #endif
 
+// explicit round-to-nearest operations: never contracted or re-associated by the compiler
+#define FMA(a, b, c) __fma_rn((a), (b), (c))
+#define MUL(a, b) __dmul_rn((a), (b))
+#define ADD(a, b) __dadd_rn((a), (b))
+
 namespace LK_NS {
 
 typedef long long i64;
@@ -87,10 +92,10 @@ __device__ __forceinline__ double accel_y(const DAccel& a, const DGeo& g, int i1
 __device__ __forceinline__ double fast_rcp(double s) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
-  double e = fma(-s, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-s, r, 1.0);
-  r = fma(r, e, r);
+  double e = FMA(-s, r, 1.0);
+  r = FMA(r, e, r);
+  e = FMA(-s, r, 1.0);
+  r = FMA(r, e, r);
   return r;
 }
 
@@ -127,26 +132,27 @@ __device__ __forceinline__ double weno43(double um2, double um1, double u0, doub
   // Same function, algebraically rearranged to ONE reciprocal: with A=(eps+bl)^2, B=(eps+br)^2,
   // S=A+B the unmapped weights are wl=B/S, wr=A/S; the Henrick-mapped, renormalised weights are
   // nl/(nl+nr), nr/(nl+nr) with nl = B(0.75 S^2 + B(B-1.5S)), nr = A(0.75 S^2 + A(A-1.5S)).
+  // Every operation is an explicit round-to-nearest intrinsic so that the compiler cannot contract
+  // differently at different inlining sites: a cell gets the same bits wherever it sits in a tile.
   const double eps = 1.e-10;
-  const double fl6 = fma(5.0, um1, fma(2.0, u0, -um2));
-  const double fr6 = fma(5.0, u0, fma(2.0, um1, -up1));
-  const double c1l = fma(-2.0, um1, u0) + um2;
-  const double c1r = fma(-2.0, u0, up1) + um1;
-  const double hl = 0.5 * (u0 - um2);
-  const double hr = 0.5 * (up1 - um1);
-  const double el = fma(c1l, fma(4.0 / 3.0, c1l, hl), fma(hl, hl, eps));
-  const double er = fma(c1r, fma(4.0 / 3.0, c1r, -hr), fma(hr, hr, eps));
-  const double A = el * el, B = er * er;
-  const double S = A + B;
-  const double q = 0.75 * (S * S);
-  const double m = -1.5 * S;
-  const double nl = B * fma(B, B + m, q);
-  const double nr = A * fma(A, A + m, q);
-  const double r = fast_rcp(nl + nr) * (1.0 / 6.0);
+  const double fl6 = FMA(5.0, um1, FMA(2.0, u0, -um2));
+  const double fr6 = FMA(5.0, u0, FMA(2.0, um1, -up1));
+  const double c1l = ADD(FMA(-2.0, um1, u0), um2);
+  const double c1r = ADD(FMA(-2.0, u0, up1), um1);
+  const double hl = MUL(0.5, ADD(u0, -um2));
+  const double hr = MUL(0.5, ADD(up1, -um1));
+  const double el = FMA(c1l, FMA(4.0 / 3.0, c1l, hl), FMA(hl, hl, eps));
+  const double er = FMA(c1r, FMA(4.0 / 3.0, c1r, -hr), FMA(hr, hr, eps));
+  const double A = MUL(el, el), B = MUL(er, er);
+  const double S = ADD(A, B);
+  const double q = MUL(0.75, MUL(S, S));
+  const double nl = MUL(B, FMA(B, FMA(-1.5, S, B), q));
+  const double nr = MUL(A, FMA(A, FMA(-1.5, S, A), q));
+  const double r = MUL(fast_rcp(ADD(nl, nr)), 1.0 / 6.0);
   const double nmax = fmax(nl, nr), nmin = fmin(nl, nr);
   const double wl = pos ? nmax : nmin;
   const double wr = pos ? nmin : nmax;
-  return fma(wl, fl6, wr * fr6) * r;
+  return MUL(FMA(wl, fl6, MUL(wr, fr6)), r);
 #endif
 }
 
@@ -192,41 +198,40 @@ __device__ __forceinline__ double weno65(double um3, double um2, double um1, dou
 #else
   const double eps = 1.e-10;
   const double k = 1.0 / 30240.0;
-  const double fl60 = fma(2.0, um3, fma(-13.0, um2, fma(47.0, um1, fma(27.0, u0, -3.0 * up1))));
-  const double fr60 = fma(-3.0, um2, fma(27.0, um1, fma(47.0, u0, fma(-13.0, up1, 2.0 * up2))));
-  // smoothness indicators as nested quadratic forms; constants pre-divided
+  const double fl60 = FMA(2.0, um3, FMA(-13.0, um2, FMA(47.0, um1, FMA(27.0, u0, MUL(-3.0, up1)))));
+  const double fr60 = FMA(-3.0, um2, FMA(27.0, um1, FMA(47.0, u0, FMA(-13.0, up1, MUL(2.0, up2)))));
+  // smoothness indicators as nested quadratic forms; constants pre-divided (compile-time folding)
   double t;
-  t = fma(5489.0 / 105.0, um1, fma(-2242428.0 * k, u0, fma(-1887108.0 * k, um2, fma(410226.0 * k, um3, 557646.0 * k * up1))));
-  double bl = fma(t, um1, eps);
-  t = fma(75329.0 / 3780.0, um2, fma(1259696.0 * k, u0, fma(-275318.0 * k, um3, -302534.0 * k * up1)));
-  bl = fma(t, um2, bl);
-  t = fma(33727.0 * k, um3, fma(-264314.0 * k, u0, 61952.0 * k * up1));
-  bl = fma(t, um3, bl);
-  t = fma(106409.0 / 3780.0, u0, -227749.0 / 15120.0 * up1);
-  bl = fma(t, u0, bl);
-  bl = fma(69217.0 * k * up1, up1, bl);
+  t = FMA(5489.0 / 105.0, um1, FMA(-2242428.0 * k, u0, FMA(-1887108.0 * k, um2, FMA(410226.0 * k, um3, MUL(557646.0 * k, up1)))));
+  double bl = FMA(t, um1, eps);
+  t = FMA(75329.0 / 3780.0, um2, FMA(1259696.0 * k, u0, FMA(-275318.0 * k, um3, MUL(-302534.0 * k, up1))));
+  bl = FMA(t, um2, bl);
+  t = FMA(33727.0 * k, um3, FMA(-264314.0 * k, u0, MUL(61952.0 * k, up1)));
+  bl = FMA(t, um3, bl);
+  t = FMA(106409.0 / 3780.0, u0, MUL(-227749.0 / 15120.0, up1));
+  bl = FMA(t, u0, bl);
+  bl = FMA(MUL(69217.0 * k, up1), up1, bl);
 
-  t = fma(106409.0 / 3780.0, um1, fma(-2242428.0 * k, u0, fma(-455498.0 * k, um2, fma(1259696.0 * k, up1, -264314.0 * k * up2))));
-  double br = fma(t, um1, eps);
-  t = fma(69217.0 * k, um2, fma(557646.0 * k, u0, fma(-302534.0 * k, up1, 61952.0 * k * up2)));
-  br = fma(t, um2, br);
-  t = fma(75329.0 / 3780.0, up1, fma(-1887108.0 * k, u0, -275318.0 * k * up2));
-  br = fma(t, up1, br);
-  t = fma(5489.0 / 105.0, u0, 68371.0 / 5040.0 * up2);
-  br = fma(t, u0, br);
-  br = fma(33727.0 * k * up2, up2, br);
+  t = FMA(106409.0 / 3780.0, um1, FMA(-2242428.0 * k, u0, FMA(-455498.0 * k, um2, FMA(1259696.0 * k, up1, MUL(-264314.0 * k, up2)))));
+  double br = FMA(t, um1, eps);
+  t = FMA(69217.0 * k, um2, FMA(557646.0 * k, u0, FMA(-302534.0 * k, up1, MUL(61952.0 * k, up2))));
+  br = FMA(t, um2, br);
+  t = FMA(75329.0 / 3780.0, up1, FMA(-1887108.0 * k, u0, MUL(-275318.0 * k, up2)));
+  br = FMA(t, up1, br);
+  t = FMA(5489.0 / 105.0, u0, MUL(68371.0 / 5040.0, up2));
+  br = FMA(t, u0, br);
+  br = FMA(MUL(33727.0 * k, up2), up2, br);
 
-  const double A = bl * bl, B = br * br;
-  const double S = A + B;
-  const double q = 0.75 * (S * S);
-  const double m = -1.5 * S;
-  const double nl = B * fma(B, B + m, q);
-  const double nr = A * fma(A, A + m, q);
-  const double r = fast_rcp(nl + nr) * (1.0 / 60.0);
+  const double A = MUL(bl, bl), B = MUL(br, br);
+  const double S = ADD(A, B);
+  const double q = MUL(0.75, MUL(S, S));
+  const double nl = MUL(B, FMA(B, FMA(-1.5, S, B), q));
+  const double nr = MUL(A, FMA(A, FMA(-1.5, S, A), q));
+  const double r = MUL(fast_rcp(ADD(nl, nr)), 1.0 / 60.0);
   const double nmax = fmax(nl, nr), nmin = fmin(nl, nr);
   const double wl = pos ? nmax : nmin;
   const double wr = pos ? nmin : nmax;
-  return fma(wl, fl60, wr * fr60) * r;
+  return MUL(FMA(wl, fl60, MUL(wr, fr60)), r);
 #endif
 }
 
@@ -237,25 +242,40 @@ __device__ __forceinline__ double fit_right(const double* __restrict__ p, i64 s,
   return weno65(p[-2 * s], p[-s], p[0], p[s], p[2 * s], p[3 * s], pos);
 }
 
-// -(c*uR - c*uL)/d in the reference's form (KineticSpeciesF.f:2000-2002); the production build
-// multiplies by the reciprocal spacing instead of dividing.
-__device__ __forceinline__ double flux_diff(double c, double uR, double uL, double d, double rd) {
+// acc - (c*uR - c*uL)/d in the reference's form (KineticSpeciesF.f:2000-2002).  The production build
+// uses the algebraically equal acc - (c/d)*(uR - uL) as ONE explicit fma (so every cell executes the
+// same rounding sequence wherever it sits in a tile).
+__device__ __forceinline__ double sub_flux(double acc, double c, double uR, double uL, double d, double rd) {
 #if LK_STRICT
   (void)rd;
-  return (c * uR - c * uL) / d;
+  return acc - (c * uR - c * uL) / d;
 #else
   (void)d;
-  return (c * uR - c * uL) * rd;
+  return FMA(-MUL(c, rd), ADD(uR, -uL), acc);
 #endif
 }
 
 // RK stage update fused behind the rhs evaluation (RK4Integrator.H:149-171)
-__device__ __forceinline__ void rk_update(const DUpd& u, i64 idx, double rhs) {
+__device__ __forceinline__ double rk_delta(const DUpd& u, double rhs, double delta_in, bool has_in) {
+#if LK_STRICT
   double d = u.w_delta * rhs;
-  if (u.delta_in) d = u.delta_in[idx] + d;
+  if (has_in) d = delta_in + d;
+  return d;
+#else
+  return has_in ? FMA(u.w_delta, rhs, delta_in) : MUL(u.w_delta, rhs);
+#endif
+}
+__device__ __forceinline__ double rk_pred(const DUpd& u, double f_old, double inc) {
+#if LK_STRICT
+  return f_old + u.c_pred * inc;
+#else
+  return FMA(u.c_pred, inc, f_old);
+#endif
+}
+__device__ __forceinline__ void rk_update(const DUpd& u, i64 idx, double rhs) {
+  const double d = rk_delta(u, rhs, u.delta_in ? u.delta_in[idx] : 0.0, u.delta_in != nullptr);
   if (u.delta_out) u.delta_out[idx] = d;
-  const double inc = u.use_delta ? d : rhs;
-  u.pred[idx] = u.f_old[idx] + u.c_pred * inc;
+  u.pred[idx] = rk_pred(u, u.f_old[idx], u.use_delta ? d : rhs);
 }
 
 }  // namespace LK_NS

@@ -441,13 +441,12 @@ k_rhs_naive(DGeo g, const double* __restrict__ f, const double* __restrict__ vel
     {
       double uR = fit_right<ORDER>(p, 1, vx > 0.0);
       double uL = fit_right<ORDER>(p - 1, 1, vx > 0.0);
-      double t1 = flux_diff(vx, uR, uL, g.dx[0], 1.0 / g.dx[0]);
-      rhs = (flags & 4) ? rhs - t1 : -t1;  // the x pass assigns (KineticSpeciesF.f:1999)
+      rhs = sub_flux((flags & 4) ? rhs : 0.0, vx, uR, uL, g.dx[0], 1.0 / g.dx[0]);  // the x pass assigns (KineticSpeciesF.f:1999)
     }
     {
       double uR = fit_right<ORDER>(p, g.s[1], vy > 0.0);
       double uL = fit_right<ORDER>(p - g.s[1], g.s[1], vy > 0.0);
-      rhs = rhs - flux_diff(vy, uR, uL, g.dx[1], 1.0 / g.dx[1]);
+      rhs = sub_flux(rhs, vy, uR, uL, g.dx[1], 1.0 / g.dx[1]);
     }
   }
   if (flags & 2) {
@@ -456,14 +455,14 @@ k_rhs_naive(DGeo g, const double* __restrict__ f, const double* __restrict__ vel
       const double axl = (i3 > ng) ? accel_x(a, g, i1, i2, i3 - 1, i4) : ax;  // face reuse uLeft=uRight
       double uR = fit_right<ORDER>(p, g.s[2], ax > 0.0);
       double uL = fit_right<ORDER>(p - g.s[2], g.s[2], axl > 0.0);
-      rhs = rhs - flux_diff(ax, uR, uL, g.dx[2], 1.0 / g.dx[2]);
+      rhs = sub_flux(rhs, ax, uR, uL, g.dx[2], 1.0 / g.dx[2]);
     }
     {
       const double ay = accel_y(a, g, i1, i2, i3, i4);
       const double ayl = (i4 > ng) ? accel_y(a, g, i1, i2, i3, i4 - 1) : ay;
       double uR = fit_right<ORDER>(p, g.s[3], ay > 0.0);
       double uL = fit_right<ORDER>(p - g.s[3], g.s[3], ayl > 0.0);
-      rhs = rhs - flux_diff(ay, uR, uL, g.dx[3], 1.0 / g.dx[3]);
+      rhs = sub_flux(rhs, ay, uR, uL, g.dx[3], 1.0 / g.dx[3]);
     }
   }
   if (rhs_out) rhs_out[idx] = rhs;
@@ -866,10 +865,11 @@ __global__ void k_maxwell_rhs(double* __restrict__ rhs, const double* __restrict
         double dx4 = (dx * dx) * (dx * dx), dy4 = (dy * dy) * (dy * dy);
         double uxxxx = (1.0 * p[-2] - 4.0 * p[-1] + 6.0 * p[0] - 4.0 * p[1] + 1.0 * p[2]) / dx4;
         double uyyyy = (1.0 * p[-2 * n1d] - 4.0 * p[-n1d] + 6.0 * p[0] - 4.0 * p[n1d] + 1.0 * p[2 * n1d]) / dy4;
-        r[k] = r[k] - (avw * c * dx4 + avs * c * (dx * dx * dx)) / 16.0 * uxxxx -
-               (avw * c * dy4 + avs * c * (dy * dy * dy)) / 16.0 * uyyyy;
+        r[k] = r[k] - (avw * c * dx4 + avs * c * ((dx * dx) * dx)) / 16.0 * uxxxx -
+               (avw * c * dy4 + avs * c * ((dy * dy) * dy)) / 16.0 * uyyyy;
       } else {
-        double dx6 = pow(dx, 6), dy6 = pow(dy, 6), dx5 = pow(dx, 5), dy5 = pow(dy, 5);
+        double tx = (dx * dx) * dx, ty = (dy * dy) * dy, sx2 = dx * dx, sy2 = dy * dy;
+        double dx6 = tx * tx, dy6 = ty * ty, dx5 = (sx2 * dx) * sx2, dy5 = (sy2 * dy) * sy2;
         double ux6 = (1.0 * p[-3] - 6.0 * p[-2] + 15.0 * p[-1] - 20.0 * p[0] + 15.0 * p[1] - 6.0 * p[2] + 1.0 * p[3]) / dx6;
         double uy6 = (1.0 * p[-3 * n1d] - 6.0 * p[-2 * n1d] + 15.0 * p[-n1d] - 20.0 * p[0] + 15.0 * p[n1d] -
                       6.0 * p[2 * n1d] + 1.0 * p[3 * n1d]) / dy6;
