@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the B200-native Vlasov RHS path (BASELINE.json metric:
+4D cell-updates/s per RK stage; % of HBM roofline).
+
+  python bench.py --gpus N --steps K --warmup W            # own arm (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path on the host cores
+
+Workload at N=1 (BASELINE.json configs[1]): the planeIAW deck's physics (two species, electron driver,
+4th-order WENO, RK4) on 256^2 x 128^2 phase-space cells per species, synthetic (analytic) initial data.
+At N>1 configuration space grows with N (weak scaling): every GPU keeps a 256 x 256 (x,y) tile and the
+whole velocity space; per stage the ranks all-gather their charge-density tiles and exchange x/y face
+halos over NCCL.  A "step" is one RK4 time step = 4 fused stage passes over both species.
+
+The timed region keeps the state resident in HBM (`value`); `e2e` times the same step through the
+C ABI with HOST buffers: upload of the state from pinned memory, the step, download of the new state.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+TILE = (256, 256)
+NV = (128, 128)
+ORDER, RK = 4, 4
+GRIDS = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
+METRIC = "4D cell-updates/s per RK stage"
+UNIT = "cell-updates/s"
+# algorithmic bytes per cell-update of the fused RK4 stage kernel (SURVEY 8d / DESIGN.md):
+# read f_eval, f_old (+ delta) ; write (delta +) pred -> 32 B in stage 1, 40 B in stages 2,3, 32 B in stage 4
+STAGE_BYTES = (32, 40, 40, 32)
+
+
+def config_dict(n_gpus):
+    px, py = GRIDS[n_gpus]
+    return {"workload": "planeIAW physics, 2 species x %dx%dx%dx%d cells per GPU (global %dx%d), order 4 WENO, RK4"
+                        % (TILE[0], TILE[1], NV[0], NV[1], TILE[0] * px, TILE[1] * py),
+            "cells_per_species_per_gpu": TILE[0] * TILE[1] * NV[0] * NV[1], "species": 2, "stages_per_step": 4,
+            "decomposition": "%dx%d tiles in (x,y)" % (px, py), "arithmetic": "production (strict available)",
+            "l2": "inputs larger than L2 (9.4 GB per array)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    n, order, reps = args
+    import oracle_binding
+    ok = oracle_binding.load()
+    g = oracle_binding.OkGeom.make(n, order, (0.07, 0.07, 0.1, 0.1))
+    sec = ok.ok_time_rk4_stage_reference_style(C.byref(g), 1, reps)
+    return sec
+
+
+def cpu_leg(reps=4, box=(32, 32, 32, 32), cores=None):
+    """every core owns an independent periodic sub-box (the way the reference's MPI ranks each own a
+    ParallelArray block) and runs `reps` RK4 stages done the reference's way (separate sweeps,
+    materialised vel3/vel4, unfused zero/copy/axpy, separate velocity reduction)."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    cells = box[0] * box[1] * box[2] * box[3]
+    ctx = mp.get_context("fork")
+    t0 = time.time()
+    with ctx.Pool(cores) as pool:
+        secs = pool.map(_cpu_worker, [(box, ORDER, reps)] * cores)
+    wall = time.time() - t0
+    per_stage = max(secs)                      # slowest rank, like an MPI step
+    value = cells * cores / per_stage
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d cores x independent %dx%dx%dx%d periodic sub-box x %d RK4 stages, oracle C restatement of "
+                      "the reference's unfused passes (gcc -O2 -ffp-contract=off); %.1f s wall" % (cores, *box, reps, wall),
+            "_per_stage_s": per_stage}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    t0 = time.time()
+    vals = []
+    for _ in range(args.warmup):
+        cpu_leg(reps=1)
+    per = []
+    for _ in range(args.steps):
+        r = cpu_leg(reps=8)
+        vals.append(r["value"])
+        per.append(r["_per_stage_s"])
+    r.pop("_per_stage_s")
+    value = sum(vals) / len(vals)
+    r["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(per) / len(per),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args.gpus), "cpu_baseline": r,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.time() - t0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def run_own(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import loki_b200
+    from loki_b200 import host
+    import decks
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    if args.gpus not in GRIDS:
+        raise SystemExit("--gpus must be one of %s" % sorted(GRIDS))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = loki_b200.load()
+    H = host.lib()
+    if L.lk_device_count() < 1:
+        raise SystemExit("no CUDA device: the hot path has no CPU fallback")
+    L.lk_set_strict(0)
+    px, py = GRIDS[args.gpus]
+    rx, ry = rank % px, rank // px
+    tile = TILE if not args.small else (32, 32)
+    nv = NV if not args.small else (32, 32)
+    deck = decks.plane_iaw(n=(tile[0] * px, tile[1] * py), nv=nv, order=ORDER, rk=RK)
+    tile_lo = (rx * tile[0], ry * tile[1])
+    desc = deck.product_desc(tile_lo=tile_lo, tile_n=tile, ntiles=world)
+    stream = torch.cuda.current_stream().cuda_stream
+    sys_ = C.c_void_p()
+    st = H.lk_vp_create(C.byref(sys_), C.byref(desc), C.c_void_p(stream))
+    if st != 0:
+        raise SystemExit("lk_vp_create failed: %s" % L.lk_last_error().decode())
+    ng = deck.ng
+    nsp = len(deck.species)
+    geoms = []
+    for s in range(nsp):
+        g = loki_b200.Geom()
+        H.lk_vp_species_geom(sys_, s, C.byref(g))
+        geoms.append(g)
+    vols = [int(np.prod(g.nd)) for g in geoms]
+    cells_rank = sum(int(np.prod([g.n[k] for k in range(4)])) for g in geoms)
+
+    # ---- synthetic initial data: analytic Perturbed-Maxwellian tables, expanded on the device ----
+    def device_state(s, amp):
+        sp = deck.species[s]
+        fx, fv, fnorm = deck.ic_tables(sp, tile_lo, tile)
+        dfx = torch.from_numpy(fx).to(dev)
+        dfv = torch.from_numpy(fv).to(dev)
+        # a smooth spatial perturbation so that the WENO weights are exercised away from 1/2
+        x = torch.arange(fx.shape[1], device=dev, dtype=torch.float64)
+        y = torch.arange(fx.shape[0], device=dev, dtype=torch.float64)
+        pert = 1.0 + amp * torch.cos(0.11 * x)[None, :] * torch.cos(0.07 * y)[:, None]
+        f = ((fnorm * dfv)[:, :, None, None] * (dfx * pert)[None, None, :, :]).contiguous()
+        H.lk_vp_set_inflow(sys_, s, fx.ctypes.data, fv.ctypes.data, fnorm, 1.0)
+        return f
+
+    for s in range(nsp):
+        f = device_state(s, 0.05)
+        assert f.numel() == vols[s]
+        torch.cuda.synchronize()
+        # device-to-device copy into the library-owned state array
+        dst = H.lk_vp_state_ptr(sys_, s)
+        t_dst = _wrap(dst, vols[s], dev)
+        t_dst.copy_(f.view(-1))
+        del f
+    torch.cuda.synchronize()
+
+    # ---- multi-rank plumbing (torch.distributed over NCCL) ----
+    tiles_arr = None
+    halo = None
+    if world > 1:
+        tiles = []
+        for r in range(world):
+            tiles += [(r % px) * tile[0], (r // px) * tile[1], tile[0], tile[1]]
+        tiles_arr = (C.c_int * len(tiles))(*tiles)
+        rho_tile = torch.zeros(tile[0] * tile[1], dtype=torch.float64, device=dev)
+        rho_gather = torch.zeros(world * tile[0] * tile[1], dtype=torch.float64, device=dev)
+        assert H.lk_vp_set_comm_buffers(sys_, rho_tile.data_ptr(), rho_gather.data_ptr()) == 0
+        halo = []
+        for s in range(nsp):
+            bufs = {}
+            for d in (0, 1):
+                cnt = L.lk_halo_count(C.byref(geoms[s]), d)
+                bufs[d] = [torch.empty(cnt, dtype=torch.float64, device=dev) for _ in range(4)]  # send lo/hi, recv lo/hi
+            halo.append(bufs)
+        nbr = {0: (ry * px + (rx - 1) % px, ry * px + (rx + 1) % px),
+               1: (((ry - 1) % py) * px + rx, ((ry + 1) % py) * px + rx)}
+
+    def exchange_halos():
+        for s in range(nsp):
+            f = H.lk_vp_eval_ptr(sys_, s)
+            g = C.byref(geoms[s])
+            for d in (0, 1):
+                slo, shi, rlo, rhi = halo[s][d]
+                lo_n, hi_n = nbr[d]
+                if (px if d == 0 else py) == 1:
+                    L.lk_periodic_fill_4d(f, g, int(d == 0), int(d == 1), C.c_void_p(stream))
+                    continue
+                L.lk_halo_pack(slo.data_ptr(), f, g, d, 0, C.c_void_p(stream))
+                L.lk_halo_pack(shi.data_ptr(), f, g, d, 1, C.c_void_p(stream))
+                ops = [dist.P2POp(dist.isend, slo, lo_n), dist.P2POp(dist.isend, shi, hi_n),
+                       dist.P2POp(dist.irecv, rhi, hi_n), dist.P2POp(dist.irecv, rlo, lo_n)]
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+                # my low ghosts come from my low neighbour's high interior layers
+                L.lk_halo_unpack(f, rlo.data_ptr(), g, d, 0, C.c_void_p(stream))
+                L.lk_halo_unpack(f, rhi.data_ptr(), g, d, 1, C.c_void_p(stream))
+
+    def step(dt):
+        if world == 1:
+            st = H.lk_vp_advance(sys_, dt)
+            assert st == 0, L.lk_last_error()
+            return
+        H.lk_vp_begin_step(sys_, dt)
+        for stage in range(H.lk_vp_nstages(sys_)):
+            H.lk_vp_stage_moments(sys_, stage)
+            dist.all_gather_into_tensor(rho_gather, rho_tile)
+            H.lk_vp_stage_field(sys_, stage, tiles_arr)
+            exchange_halos()
+            st = H.lk_vp_stage_finish(sys_, stage)
+            assert st == 0, L.lk_last_error()
+        H.lk_vp_end_step(sys_)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dt = 0.02
+    for _ in range(args.warmup):
+        step(dt)
+    barrier()
+    launches0 = L.lk_launch_count()
+    L.lk_profile_enable(1)
+    clocks = Clocks(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(dt)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    n_l, tot_ms = C.c_int64(), C.c_double()
+    L.lk_profile_summary(C.byref(n_l), C.byref(tot_ms))
+    L.lk_profile_enable(0)
+    launches = L.lk_launch_count() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    stages = H.lk_vp_nstages(sys_)
+    total_cells = cells_rank * world
+    value = total_cells * stages * args.steps / (ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel (fused stencil + RK update), live CUDA-event durations ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    cells_launch = cells_rank / nsp
+    avg_bytes = cells_launch * (sum(STAGE_BYTES) / len(STAGE_BYTES))
+    avg_ms = tot_ms.value / max(1, n_l.value)
+    achieved = avg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        traffic = tr["dram_bytes_per_cell"] * cells_launch
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "k_stencil_tiled (fused WENO RHS + RK4 stage update)",
+                "algorithmic_bytes_per_launch": avg_bytes, "avg_launch_ms": avg_ms, "timed_launches": n_l.value,
+                "kernel_share_of_step": tot_ms.value / ms if ms > 0 else None, "peak_source": peak_src,
+                "note": "the kernel is fp64-FMA bound before it is HBM bound (about 150 fp64 instructions per "
+                        "cell-update); see DESIGN.md for the fp64 ceiling"}
+
+    # ---- e2e: the same step with HOST buffers (pinned), H2D of the state + step + D2H of the result ----
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+        need = sum(vols) * 8
+        pinned = psutil.virtual_memory().available > 3 * need * max(1, world)
+        bufs = [torch.empty(v, dtype=torch.float64, pin_memory=pinned) for v in vols]
+        for s in range(nsp):
+            H.lk_vp_get_state(sys_, s, bufs[s].data_ptr())
+
+        def e2e_step():
+            for s in range(nsp):
+                H.lk_vp_set_state(sys_, s, bufs[s].data_ptr())
+            step(dt)
+            for s in range(nsp):
+                H.lk_vp_get_state(sys_, s, bufs[s].data_ptr())
+
+        e2e_step()
+        barrier()
+        nrep = 2
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            e2e_step()
+        barrier()
+        wall = time.perf_counter() - t0
+        tt = torch.tensor([wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        wall = float(tt.item())
+        e2e = {"value": total_cells * stages * nrep / wall, "unit": UNIT, "h2d_bytes_per_step": need * world,
+               "d2h_bytes_per_step": need * world, "steps": nrep, "pinned": bool(pinned),
+               "api": "lk_vp_set_state + lk_vp_advance + lk_vp_get_state (include/loki_b200_host.h)"}
+        del bufs
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_leg(reps=4)
+        cpu.pop("_per_stage_s", None)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+        if args.small:
+            line["config"]["workload"] += " [--small: 32x32x32x32 tile, NOT the headline size]"
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    H.lk_vp_destroy(sys_)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def _wrap(ptr, count, dev):
+    """view `count` doubles of library-owned device memory as a torch tensor (plumbing only)"""
+    import torch
+
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (int(ptr), False), "version": 3, "strides": None}
+    return torch.as_tensor(h, device=dev)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--small", action="store_true", help="tiny tile for plumbing checks (not a valid bench number)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_own(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

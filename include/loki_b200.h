@@ -71,9 +71,14 @@ typedef struct lk_inflow {
   const double* ghost4; /* kind 3: (n1d,n2d,n3d,2*ng) */
 } lk_inflow;
 
-/* One fused Runge-Kutta stage update applied to the freshly evaluated rhs (RK4Integrator.H:149-171):
+/* One fused Runge-Kutta stage update applied to the freshly evaluated rhs.
+ * RK4 (RK4Integrator.H:149-171):
  *   delta_out = (delta_in ? delta_in : 0) + w_delta * rhs           [addSolnData(m_delta, m_rhs, a_dt_eval)]
- *   pred      = f_old + c_pred * (use_delta ? delta_out : rhs)       [copySolnData + addSolnData]       */
+ *   pred      = f_old + c_pred * (use_delta ? delta_out : rhs)       [copySolnData + addSolnData]
+ * RK6 (RK6Integrator.H:105-130): the stage result k_i is written through lk_vlasov_rhs's rhs_out and
+ *   pred      = ((f_old + c_prev[0]*k_prev[0]) + ... + c_prev[n_prev-1]*k_prev[n_prev-1]) + c_pred * rhs
+ * i.e. the next stage's predictor (or the end-of-step sum with the b weights), added in the reference's
+ * order.  n_prev = 0 for RK4. */
 typedef struct lk_rk_update {
   const double* f_old;
   const double* delta_in; /* NULL in stage 1 (delta starts from zero) */
@@ -81,6 +86,9 @@ typedef struct lk_rk_update {
   double* pred;           /* must not alias f_eval (neighbours still read the old values) */
   double w_delta, c_pred;
   int use_delta;          /* 1 in RK4 stage 4 */
+  int n_prev;             /* RK6: number of earlier stage results to add (0..7) */
+  const double* k_prev[7];
+  double c_prev[7];
 } lk_rk_update;
 
 /* ---- library ---- */
@@ -178,6 +186,11 @@ int lk_memcpy_h2d(void* dst, const void* src, int64_t bytes);
 int lk_memcpy_d2h(void* dst, const void* src, int64_t bytes);
 int lk_memset(void* p, int value, int64_t bytes);
 int lk_sync(void* stream);
+/* CUDA-event timing of every lk_vlasov_rhs launch on its own stream (the dominant kernel's live
+ * duration for the roofline): enable(1) resets the counters; summary synchronises and returns the
+ * number of timed launches and the sum of their durations in milliseconds. */
+int lk_profile_enable(int on);
+int lk_profile_summary(int64_t* launches, double* total_ms);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t lk_launch_count(void);
 

@@ -43,7 +43,8 @@ class Inflow(C.Structure):
 class RkUpdate(C.Structure):
     _fields_ = [("f_old", C.c_void_p), ("delta_in", C.c_void_p), ("delta_out", C.c_void_p),
                 ("pred", C.c_void_p), ("w_delta", C.c_double), ("c_pred", C.c_double),
-                ("use_delta", C.c_int)]
+                ("use_delta", C.c_int), ("n_prev", C.c_int), ("k_prev", C.c_void_p * 7),
+                ("c_prev", C.c_double * 7)]
 
 
 def library_path():
@@ -89,6 +90,8 @@ _PROTOS = {
     "lk_memset": (C.c_int, [_vp, C.c_int, C.c_int64]),
     "lk_sync": (C.c_int, [_vp]),
     "lk_launch_count": (C.c_int64, []),
+    "lk_profile_enable": (C.c_int, [C.c_int]),
+    "lk_profile_summary": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
 }
 
 

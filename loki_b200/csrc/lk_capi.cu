@@ -74,6 +74,13 @@ int moment_chunks(const lk_geom* g) {
     return LK_OK;                                      \
   } while (0)
 
+// ---- optional event timing of the fused stencil launches (bench.py's roofline.achieved) ----
+namespace {
+bool g_prof = false;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+size_t g_prof_used = 0;
+}  // namespace
+
 struct lk_poisson_plan {
   int nx, ny, ng, order;
   double *sx, *sy, *cx, *cy, *T, *X;  // device
@@ -177,10 +184,24 @@ int lk_vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const doub
   if (upd) {
     if (!upd->f_old || !upd->pred) return fail(LK_ERR_ARG, "lk_vlasov_rhs: rk update needs f_old and pred");
     if (upd->pred == f) return fail(LK_ERR_ARG, "lk_vlasov_rhs: pred must not alias the evaluated state");
+    if (upd->n_prev < 0 || upd->n_prev > 7) return fail(LK_ERR_ARG, "lk_vlasov_rhs: n_prev out of range");
+    for (int j = 0; j < upd->n_prev; ++j)
+      if (!upd->k_prev[j]) return fail(LK_ERR_ARG, "lk_vlasov_rhs: missing k_prev");
     if (upd->delta_out && upd->delta_out == f) return fail(LK_ERR_ARG, "lk_vlasov_rhs: delta must not alias the evaluated state");
   }
   if (rhs_out == f) return fail(LK_ERR_ARG, "lk_vlasov_rhs: rhs must not alias the evaluated state");
-  CHECK_LAUNCH(DISPATCH(vlasov_rhs)(rhs_out, f, g, velocities, a, upd, 3, g_variant, (cudaStream_t)stream), "lk_vlasov_rhs");
+  if (!g_prof) CHECK_LAUNCH(DISPATCH(vlasov_rhs)(rhs_out, f, g, velocities, a, upd, 3, g_variant, (cudaStream_t)stream), "lk_vlasov_rhs");
+  if (g_prof_used == g_prof_events.size()) {
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return cuda_fail(cudaGetLastError(), "lk_vlasov_rhs: event");
+    g_prof_events.push_back({e0, e1});
+  }
+  auto& ev = g_prof_events[g_prof_used++];
+  cudaEventRecord(ev.first, (cudaStream_t)stream);
+  cudaError_t e = DISPATCH(vlasov_rhs)(rhs_out, f, g, velocities, a, upd, 3, g_variant, (cudaStream_t)stream);
+  cudaEventRecord(ev.second, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "lk_vlasov_rhs");
+  return LK_OK;
 }
 
 int lk_reduce_4d_to_2d(double* dst, const double* f, const lk_geom* g, double dv, double weight, void* stream) {
@@ -293,6 +314,26 @@ int lk_maxwell_rhs(double* rhs, const double* em, const double* Jx, const double
   CHECK_LAUNCH(DISPATCH(maxwell_rhs)(rhs, em, Jx, Jy, Jz, n1, n2, ng, order, dx[0], dx[1], c, av_weak, av_strong,
                                      (cudaStream_t)stream),
                "lk_maxwell_rhs");
+}
+
+// ---- event timing of the fused stencil kernel ----
+int lk_profile_enable(int on) {
+  g_prof = on != 0;
+  g_prof_used = 0;
+  return LK_OK;
+}
+int lk_profile_summary(int64_t* launches, double* total_ms) {
+  if (!launches || !total_ms) return fail(LK_ERR_ARG, "lk_profile_summary: bad argument");
+  double tot = 0.0;
+  for (size_t k = 0; k < g_prof_used; ++k) {
+    if (cudaEventSynchronize(g_prof_events[k].second) != cudaSuccess) return cuda_fail(cudaGetLastError(), "lk_profile_summary");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_prof_events[k].first, g_prof_events[k].second);
+    tot += ms;
+  }
+  *launches = (int64_t)g_prof_used;
+  *total_ms = tot;
+  return LK_OK;
 }
 
 // ---- memory helpers ----

@@ -50,6 +50,9 @@ struct DUpd {
   double w_delta, c_pred;
   int use_delta;
   int active;
+  int n_prev;
+  const double* k_prev[7];
+  double c_prev[7];
 };
 
 __device__ __forceinline__ i64 gidx(const DGeo& g, int i1, int i2, int i3, int i4) {
@@ -265,17 +268,23 @@ __device__ __forceinline__ double rk_delta(const DUpd& u, double rhs, double del
   return has_in ? FMA(u.w_delta, rhs, delta_in) : MUL(u.w_delta, rhs);
 #endif
 }
-__device__ __forceinline__ double rk_pred(const DUpd& u, double f_old, double inc) {
+__device__ __forceinline__ double rk_axpy(double x, double b, double y) {
 #if LK_STRICT
-  return f_old + u.c_pred * inc;
+  return x + b * y;
 #else
-  return FMA(u.c_pred, inc, f_old);
+  return FMA(b, y, x);
 #endif
+}
+// pred = ((f_old + c0 k0) + c1 k1 ...) + c_pred * inc, in the reference's order of addSolnData calls
+__device__ __forceinline__ double rk_pred(const DUpd& u, double f_old, double inc, i64 idx) {
+  double p = f_old;
+  for (int j = 0; j < u.n_prev; ++j) p = rk_axpy(p, u.c_prev[j], u.k_prev[j][idx]);
+  return rk_axpy(p, u.c_pred, inc);
 }
 __device__ __forceinline__ void rk_update(const DUpd& u, i64 idx, double rhs) {
   const double d = rk_delta(u, rhs, u.delta_in ? u.delta_in[idx] : 0.0, u.delta_in != nullptr);
   if (u.delta_out) u.delta_out[idx] = d;
-  u.pred[idx] = rk_pred(u, u.f_old[idx], u.use_delta ? d : rhs);
+  u.pred[idx] = rk_pred(u, u.f_old[idx], u.use_delta ? d : rhs, idx);
 }
 
 }  // namespace LK_NS

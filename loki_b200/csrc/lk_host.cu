@@ -1,0 +1,692 @@
+// lk_host.cu -- host-side mirror of the reference's operator interface for the Vlasov-Poisson path
+// (include/loki_b200_host.h).  Class and method names follow the reference so that the call order of
+// VPSystem::evalRHS / RK4Integrator::stageAdvance can be checked line by line; every numerical step is
+// a kernel of the C ABI in loki_b200.h (this file contains only 2D glue kernels: tile pack/scatter,
+// species sum, driver field, scalar RK state).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/loki_b200_host.h"
+
+namespace loki {
+
+typedef long long i64;
+
+#define LKH_CHECK(expr)                 \
+  do {                                  \
+    int s__ = (expr);                   \
+    if (s__ != LK_OK) return s__;       \
+  } while (0)
+#define LKH_CUDA(expr)                                   \
+  do {                                                   \
+    cudaError_t e__ = (expr);                            \
+    if (e__ != cudaSuccess) return LK_ERR_CUDA;          \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    release();
+    if (count == 0) return LK_OK;
+    if (cudaMalloc((void**)&p, sizeof(T) * count) != cudaSuccess) { p = nullptr; return LK_ERR_CUDA; }
+    n = count;
+    return LK_OK;
+  }
+  int upload(const std::vector<T>& h) {
+    LKH_CHECK(alloc(h.size()));
+    LKH_CUDA(cudaMemcpy(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+    return LK_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// 2D glue kernels (explicit round-to-nearest ops: identical in both arithmetic modes)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_add_inplace(double* __restrict__ x, const double* __restrict__ y, i64 n) {  // ParallelArray::operator+=
+  i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) x[t] = __dadd_rn(x[t], y[t]);
+}
+// local rho (n1d,n2d with ghosts) -> dense interior tile
+__global__ void k_tile_pack(double* __restrict__ tile, const double* __restrict__ rho, int n1, int n2, int ng) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n1 * n2) return;
+  tile[t] = rho[(t % n1 + ng) + (i64)(n1 + 2 * ng) * (t / n1 + ng)];
+}
+// dense tile of rank r -> global rho (ng ghosts, zeroed beforehand)
+__global__ void k_tile_scatter(double* __restrict__ rho_g, const double* __restrict__ tile, int lo0, int lo1, int n0,
+                               int n1, int n1d_g, int ng) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n0 * n1) return;
+  rho_g[(lo0 + t % n0 + ng) + (i64)n1d_g * (lo1 + t / n0 + ng)] = tile[t];
+}
+// global em_vars (n1d_g,n2d_g,2) -> this rank's (n1d,n2d,2) window incl. ghosts (the expansion schedule)
+__global__ void k_extract_window(double* __restrict__ loc, const double* __restrict__ glob, int lo0, int lo1, int n1d,
+                                 int n2d, int n1d_g, int n2d_g, int ncomp) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n1d * n2d * ncomp) return;
+  int i1 = t % n1d, i2 = (t / n1d) % n2d, c = t / (n1d * n2d);
+  loc[t] = glob[(lo0 + i1) + (i64)n1d_g * ((lo1 + i2) + (i64)n2d_g * c)];
+}
+// ext_efield(i1,i2,0) = 0 + envel*h(i2)*g(i1); component 1 = 0 (evaluateShapedRampedDriver, :172-186)
+__global__ void k_driver_field(double* __restrict__ ext, const double* __restrict__ g, const double* __restrict__ h,
+                               double envel, int n1d, int n2d) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n1d * n2d) return;
+  int i1 = t % n1d, i2 = t / n1d;
+  ext[t] = __dmul_rn(__dmul_rn(envel, h[i2]), g[i1]);
+  ext[t + n1d * n2d] = 0.0;
+}
+// scalar RK state m_integrated_ke_e_dot (KineticSpecies.C:282-284): v = {state, old, delta, rhs}
+__global__ void k_scalar_rk4(double* v, double w_delta, double c_pred, int first, int use_delta) {
+  double d = __dmul_rn(w_delta, v[3]);
+  if (!first) d = __dadd_rn(v[2], d);
+  v[2] = d;
+  v[0] = __dadd_rn(v[1], __dmul_rn(c_pred, use_delta ? d : v[3]));
+}
+__global__ void k_scalar_rk6(double* v, double* k, int stage, const double* coef, int ncoef) {
+  // k[stage] = rhs; state = old + sum coef[j]*k[j]
+  k[stage] = v[3];
+  double p = v[1];
+  for (int j = 0; j < ncoef; ++j) p = __dadd_rn(p, __dmul_rn(coef[j], k[j]));
+  v[0] = p;
+}
+__global__ void k_copy_scalar(double* v, int dst, int src) { v[dst] = v[src]; }
+
+static inline unsigned nb(i64 n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// ---------------------------------------------------------------------------------------------
+// ShapedRampedCosineDriver (ShapedRampedCosineDriverF.f:10-189), separable: E = envel(t) h(y) g(x,t).
+// Evaluated on the host with libm exactly as the Fortran does; only the O(Nx)+O(Ny) factors cross
+// to the device.
+// ---------------------------------------------------------------------------------------------
+struct ShapedRampedCosineDriver {
+  double p[16];
+  double phase;
+  int shape_type;
+  bool active(double t) const { return p[5] <= t && t < p[5] + p[6] + p[7] + p[8]; }
+  double envelope(double t) const {
+    const double t0 = p[5], t_rampup = p[6], t_hold = p[7], t_rampdown = p[8], E_0 = p[4];
+    if ((t < t0) || (t >= t0 + t_rampup + t_hold + t_rampdown)) return 0.0;
+    if (t < t0 + t_rampup) return E_0 * (0.5 + 0.5 * tanh(4.0 * (2.0 * (t - t0) / t_rampup - 1.0)));
+    if (t < t0 + t_rampup + t_hold) return E_0 * (0.5 + 0.5 * tanh(4.0));
+    return E_0 * (0.5 - 0.5 * tanh(4.0 * (2.0 * (t - t0 - t_rampup - t_hold) / t_rampdown - 1.0)));
+  }
+  double ghat(double x, double t, double pi) const {
+    const double xwidth = p[0], omega = p[3], t0 = p[5], x_shape = p[9], lwidth = p[10], x0 = p[11], alpha = p[12],
+                 t_res = p[13];
+    double gh;
+    if (shape_type == 0) {
+      if (fabs(x - x0) < 0.5 * lwidth) {
+        double s = sin(pi * (x - x0) / lwidth);
+        gh = 1.0 - x_shape * (s * s);
+      } else {
+        gh = 1.0 - x_shape;
+      }
+    } else {
+      if (lwidth >= 0) {
+        gh = (x <= x0) ? 1.0 : 1.0 - x_shape * (1.0 - exp(-(x - x0) / lwidth));
+      } else {
+        gh = (x <= x0) ? 1.0 - x_shape * (1.0 - exp(-(x - x0) / lwidth)) : 1.0;
+      }
+    }
+    const double tt = t - t0 - t_res;
+    return gh * cos(pi * x / xwidth - omega * (t - t0) + phase - 0.5 * alpha * (tt * tt));
+  }
+  double hfun(double y, double pi) const {
+    const double ywidth = p[1], shape = p[2];
+    if (fabs(y) < 0.5 * ywidth) {
+      double s = sin(pi * y / ywidth);
+      return 1.0 - shape * (s * s);
+    }
+    return 1.0 - shape;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// KineticSpecies (KineticSpecies.H/C): one species' share of phase space on this rank
+// ---------------------------------------------------------------------------------------------
+struct KineticSpecies {
+  lk_geom g;
+  double mass, charge, bz_const;
+  double vlo[2], vhi[2];
+  i64 vol;
+  int n1d, n2d, n3d, n4d;
+  // RK state: f[0..2] rotate between {state/old, pred A, pred B}; delta; k[0..7] for RK6
+  DevBuf<double> farr[3], delta, karr[8], rhs_tmp;
+  int i_state = 0, i_a = 1, i_b = 2;
+  double* f_eval = nullptr;  // what the next evalRHS reads
+  // tables (KineticSpecies.C:1953-2048)
+  DevBuf<double> velocities, vxface, vyface;
+  // per-stage 2D work arrays
+  DevBuf<double> rho_s, accel, ext_efield, lam, drv_g, drv_h, ke;  // ke: {state, old, delta, rhs} + k[8]
+  DevBuf<double> ke_k, ke_coef;
+  // inflow (initial condition) tables
+  DevBuf<double> ic_fx, ic_fv;
+  lk_inflow inflow;
+  bool has_driver = false;
+  ShapedRampedCosineDriver driver;
+  double lambda_max[4] = {0, 0, 0, 0};
+
+  double* state() { return farr[i_state].p; }
+
+  lk_accel accelDesc() {
+    lk_accel a;
+    a.kind = 0;
+    a.field = accel.p;
+    a.vz = nullptr;
+    a.vxface_velocities = vxface.p;
+    a.vyface_velocities = vyface.p;
+    a.normalization = charge / mass;  // KineticSpecies.C:752-754 (non-relativistic)
+    a.bz_const = bz_const;
+    return a;
+  }
+
+  // buildVelocityArrays, non-relativistic branch (KineticSpecies.C:2024-2047)
+  int buildVelocityArrays() {
+    const double dvx = g.dx[2], dvy = g.dx[3];
+    const int ng = g.ng;
+    std::vector<double> v((size_t)n3d * n4d * 2), vxf((size_t)(n3d + 1) * n4d * 2), vyf((size_t)n3d * (n4d + 1) * 2);
+    for (int i3 = 0; i3 < n3d; ++i3) {
+      double vx = vlo[0] + ((i3 - ng) + 0.5) * dvx;
+      for (int i4 = 0; i4 < n4d; ++i4) {
+        v[i3 + (size_t)n3d * i4] = vx;
+        v[i3 + (size_t)n3d * (i4 + (size_t)n4d)] = vlo[1] + ((i4 - ng) + 0.5) * dvy;
+      }
+    }
+    for (int i3 = 0; i3 <= n3d; ++i3) {
+      double vx = vlo[0] + (i3 - ng) * dvx;
+      for (int i4 = 0; i4 < n4d; ++i4) {
+        vxf[i3 + (size_t)(n3d + 1) * i4] = vx;
+        vxf[i3 + (size_t)(n3d + 1) * (i4 + (size_t)n4d)] = vlo[1] + ((i4 - ng) + 0.5) * dvy;
+      }
+    }
+    for (int i3 = 0; i3 < n3d; ++i3) {
+      double vx = vlo[0] + ((i3 - ng) + 0.5) * dvx;
+      for (int i4 = 0; i4 <= n4d; ++i4) {
+        vyf[i3 + (size_t)n3d * i4] = vx;
+        vyf[i3 + (size_t)n3d * (i4 + (size_t)(n4d + 1))] = vlo[1] + (i4 - ng) * dvy;
+      }
+    }
+    LKH_CHECK(velocities.upload(v));
+    LKH_CHECK(vxface.upload(vxf));
+    LKH_CHECK(vyface.upload(vyf));
+    // m_lambda_max[X1], [X2] (KineticSpecies.C:1547-1555; the upper value is vhi + dv/2 as written there)
+    lambda_max[0] = std::max(fabs(vlo[0] + 0.5 * (vhi[0] - vlo[0]) / g.n[2]), fabs(vhi[0] + 0.5 * (vhi[0] - vlo[0]) / g.n[2]));
+    lambda_max[1] = std::max(fabs(vlo[1] + 0.5 * (vhi[1] - vlo[1]) / g.n[3]), fabs(vhi[1] + 0.5 * (vhi[1] - vlo[1]) / g.n[3]));
+    return LK_OK;
+  }
+
+  // chargeDensity (KineticSpecies.H:265-270; schedule set-up KineticSpecies.C:1736-1753)
+  int chargeDensity(const double* f, void* st) {
+    return lk_reduce_4d_to_2d(rho_s.p, f, &g, g.dx[2] * g.dx[3], charge, st);
+  }
+
+  // computeAcceleration (KineticSpecies.C:697-774).  em_local: this rank's window of E incl. ghosts.
+  int computeAcceleration(const double* em_local, double time, const double xlo[2], const int tile_lo[2], bool want_max,
+                          void* st) {
+    const double* ext = nullptr;
+    if (has_driver) {
+      LKH_CUDA(cudaMemsetAsync(ext_efield.p, 0, sizeof(double) * 2 * n1d * n2d, (cudaStream_t)st));  // m_ext_efield = 0.0
+      if (driver.active(time)) {
+        const double pi = 4.0 * atan(1.0);
+        const double envel = driver.envelope(time);
+        std::vector<double> gh(n1d), hh(n2d);
+        for (int i1 = 0; i1 < n1d; ++i1) gh[i1] = driver.ghat(xlo[0] + g.dx[0] * (0.5 + (tile_lo[0] + i1 - g.ng)), time, pi);
+        for (int i2 = 0; i2 < n2d; ++i2) hh[i2] = driver.hfun(xlo[1] + g.dx[1] * (0.5 + (tile_lo[1] + i2 - g.ng)), pi);
+        // stream-ordered copies from pageable memory are synchronous with respect to the host buffer
+        LKH_CUDA(cudaMemcpyAsync(drv_g.p, gh.data(), sizeof(double) * n1d, cudaMemcpyHostToDevice, (cudaStream_t)st));
+        LKH_CUDA(cudaMemcpyAsync(drv_h.p, hh.data(), sizeof(double) * n2d, cudaMemcpyHostToDevice, (cudaStream_t)st));
+        k_driver_field<<<nb((i64)n1d * n2d, 128), 128, 0, (cudaStream_t)st>>>(ext_efield.p, drv_g.p, drv_h.p, envel, n1d, n2d);
+      }
+      ext = ext_efield.p;
+    }
+    // m_accel = 0; expansion of E; drivers add; m_accel *= normalization
+    LKH_CHECK(lk_form_accel(accel.p, em_local, ext, charge / mass, g.n[0], g.n[1], g.ng, st));
+    if (want_max) {
+      lk_accel a = accelDesc();
+      LKH_CHECK(lk_max_accel(&g, &a, lam.p, st));  // axmax, aymax -> m_lambda_max[V1], [V2]
+    }
+    return LK_OK;
+  }
+
+  // setAccelerationBCs (KineticSpecies.H:421-453): velocity space is whole on every rank
+  int setAccelerationBCs(double* f, void* st) {
+    lk_accel a = accelDesc();
+    const int at[4] = {1, 1, 1, 1};
+    return lk_set_acceleration_bcs_4d(f, &g, &a, &inflow, at, st);
+  }
+
+  // computeDt (KineticSpecies.C:647-694) without collision operators
+  double computeDt(int rk_order) const {
+    const double pi = 4.0 * atan(1.0);
+    double imLam = 0.0, reLam = 0.0;
+    for (int dir = 0; dir < 4; ++dir) imLam += pi * lambda_max[dir] / g.dx[dir];
+    double alpha = (rk_order == 4) ? 2.6 : 4.95, beta = (rk_order == 4) ? 2.6 : 3.168;
+    return sqrt(1.0 / (reLam * reLam / (alpha * alpha) + imLam * imLam / (beta * beta)));
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// VPSystem (+ VPState, Poisson, the RK integrators): one rank
+// ---------------------------------------------------------------------------------------------
+struct VPSystem {
+  lk_vp_desc desc;
+  std::vector<lk_species_desc> sdesc;
+  std::vector<KineticSpecies*> species;
+  cudaStream_t st = nullptr;
+  int ng = 2;
+  int n1d_g = 0, n2d_g = 0;     // global 2D extents incl. ghosts
+  double dxg[4] = {0, 0, 1, 1};
+  lk_poisson_plan* poisson = nullptr;
+  DevBuf<double> rho_local, rho_tile_own, rho_gather_own, rho_g, phi_g, em_g, em_local;
+  double* rho_tile_p = nullptr;
+  double* rho_gather_p = nullptr;
+  size_t rho_tile_n = 0;
+  double time = 0.0, dt = 0.0;
+  bool lambda_stale = true;
+
+  ~VPSystem() {
+    for (auto* s : species) delete s;
+    if (poisson) lk_poisson_plan_destroy(poisson);
+  }
+
+  int nstages() const { return desc.rk_order == 4 ? 4 : 8; }
+
+  int create(const lk_vp_desc* d, void* stream) {
+    desc = *d;
+    sdesc.assign(d->species, d->species + d->nspecies);
+    desc.species = sdesc.data();
+    st = (cudaStream_t)stream;
+    if (!(d->order == 4 || d->order == 6) || !(d->rk_order == 4 || d->rk_order == 6) || d->nspecies < 1) return LK_ERR_ARG;
+    ng = d->order == 4 ? 2 : 3;
+    for (int k = 0; k < 2; ++k) {
+      if (d->nglobal[k] < 1 || d->tile_n[k] < ng || d->tile_lo[k] < 0 || d->tile_lo[k] + d->tile_n[k] > d->nglobal[k]) return LK_ERR_ARG;
+      dxg[k] = (d->xhi[k] - d->xlo[k]) / d->nglobal[k];  // ProblemDomain.C:20-27
+    }
+    n1d_g = d->nglobal[0] + 2 * ng;
+    n2d_g = d->nglobal[1] + 2 * ng;
+    LKH_CHECK(lk_poisson_plan_create(&poisson, d->nglobal[0], d->nglobal[1], ng, d->order, d->xhi[0] - d->xlo[0],
+                                     d->xhi[1] - d->xlo[1]));
+    const int n1d = d->tile_n[0] + 2 * ng, n2d = d->tile_n[1] + 2 * ng;
+    LKH_CHECK(rho_local.alloc((size_t)n1d * n2d));
+    rho_tile_n = (size_t)d->tile_n[0] * d->tile_n[1];
+    LKH_CHECK(rho_tile_own.alloc(rho_tile_n));
+    LKH_CHECK(rho_gather_own.alloc((size_t)d->nglobal[0] * d->nglobal[1]));
+    rho_tile_p = rho_tile_own.p;
+    rho_gather_p = rho_gather_own.p;
+    LKH_CHECK(rho_g.alloc((size_t)n1d_g * n2d_g));
+    LKH_CHECK(phi_g.alloc((size_t)n1d_g * n2d_g));
+    LKH_CHECK(em_g.alloc((size_t)n1d_g * n2d_g * 2));
+    LKH_CHECK(em_local.alloc((size_t)n1d * n2d * 2));
+    LKH_CUDA(cudaMemset(rho_g.p, 0, sizeof(double) * rho_g.n));
+    for (int s = 0; s < d->nspecies; ++s) {
+      const lk_species_desc& sd = sdesc[s];
+      KineticSpecies* ks = new KineticSpecies();
+      species.push_back(ks);
+      ks->g.n[0] = d->tile_n[0]; ks->g.n[1] = d->tile_n[1]; ks->g.n[2] = sd.nv[0]; ks->g.n[3] = sd.nv[1];
+      ks->g.ng = ng; ks->g.order = d->order;
+      ks->g.dx[0] = dxg[0]; ks->g.dx[1] = dxg[1];
+      ks->g.dx[2] = (sd.vhi[0] - sd.vlo[0]) / sd.nv[0];
+      ks->g.dx[3] = (sd.vhi[1] - sd.vlo[1]) / sd.nv[1];
+      ks->mass = sd.mass; ks->charge = sd.charge; ks->bz_const = sd.bz_const;
+      ks->vlo[0] = sd.vlo[0]; ks->vlo[1] = sd.vlo[1]; ks->vhi[0] = sd.vhi[0]; ks->vhi[1] = sd.vhi[1];
+      ks->n1d = n1d; ks->n2d = n2d; ks->n3d = sd.nv[0] + 2 * ng; ks->n4d = sd.nv[1] + 2 * ng;
+      ks->vol = (i64)n1d * n2d * ks->n3d * ks->n4d;
+      for (int k = 0; k < 3; ++k) LKH_CHECK(ks->farr[k].alloc(ks->vol));
+      if (d->rk_order == 4) {
+        LKH_CHECK(ks->delta.alloc(ks->vol));
+      } else {
+        for (int k = 0; k < 8; ++k) LKH_CHECK(ks->karr[k].alloc(ks->vol));
+      }
+      LKH_CUDA(cudaMemset(ks->farr[0].p, 0, sizeof(double) * ks->vol));
+      LKH_CHECK(ks->buildVelocityArrays());
+      LKH_CHECK(ks->rho_s.alloc((size_t)n1d * n2d));
+      LKH_CHECK(ks->accel.alloc((size_t)n1d * n2d * 2));
+      LKH_CHECK(ks->lam.alloc(2));
+      LKH_CHECK(ks->ke.alloc(4));
+      LKH_CHECK(ks->ke_k.alloc(8));
+      LKH_CHECK(ks->ke_coef.alloc(8));
+      LKH_CUDA(cudaMemset(ks->ke.p, 0, sizeof(double) * 4));
+      LKH_CUDA(cudaMemset(ks->lam.p, 0, sizeof(double) * 2));
+      memset(&ks->inflow, 0, sizeof(ks->inflow));
+      ks->has_driver = sd.has_driver != 0;
+      if (ks->has_driver) {
+        memcpy(ks->driver.p, sd.driver, sizeof(double) * 16);
+        ks->driver.phase = sd.driver_phase;
+        ks->driver.shape_type = sd.driver_shape_type;
+        LKH_CHECK(ks->ext_efield.alloc((size_t)n1d * n2d * 2));
+        LKH_CHECK(ks->drv_g.alloc(n1d));
+        LKH_CHECK(ks->drv_h.alloc(n2d));
+      }
+      ks->f_eval = ks->state();
+    }
+    return LK_OK;
+  }
+
+  // ---- stage pieces, in the order of VPSystem::evalRHS (VPSystem.C:372-476) ----
+  // (1) chargeDensity of every species, summed into the local net charge density
+  int momentsOf(bool use_eval) {
+    for (size_t s = 0; s < species.size(); ++s) {
+      KineticSpecies* ks = species[s];
+      LKH_CHECK(ks->chargeDensity(use_eval ? ks->f_eval : ks->state(), st));
+      if (s == 0) {
+        // m_net_charge_density = 0.0; += first species  (0 + x == x)
+        LKH_CUDA(cudaMemcpyAsync(rho_local.p, ks->rho_s.p, sizeof(double) * rho_local.n, cudaMemcpyDeviceToDevice, st));
+      } else {
+        k_add_inplace<<<nb((i64)rho_local.n, 128), 128, 0, st>>>(rho_local.p, ks->rho_s.p, (i64)rho_local.n);
+      }
+    }
+    k_tile_pack<<<nb((i64)rho_tile_n, 128), 128, 0, st>>>(rho_tile_p, rho_local.p, desc.tile_n[0], desc.tile_n[1], ng);
+    return LK_OK;
+  }
+  // (2) global charge density from the gathered tiles, EMSolverBase::electricField, expansion to the tile
+  int fieldSolve(const int* tiles) {
+    if (tiles == nullptr) {
+      const int one[4] = {desc.tile_lo[0], desc.tile_lo[1], desc.tile_n[0], desc.tile_n[1]};
+      k_tile_scatter<<<nb((i64)rho_tile_n, 128), 128, 0, st>>>(rho_g.p, rho_tile_p, one[0], one[1], one[2], one[3], n1d_g, ng);
+    } else {
+      size_t off = 0;
+      for (int r = 0; r < desc.ntiles; ++r) {
+        const int* t = tiles + 4 * r;
+        k_tile_scatter<<<nb((i64)t[2] * t[3], 128), 128, 0, st>>>(rho_g.p, rho_gather_p + off, t[0], t[1], t[2], t[3], n1d_g, ng);
+        off += (size_t)t[2] * t[3];
+      }
+    }
+    LKH_CHECK(lk_electric_field(poisson, rho_g.p, phi_g.p, em_g.p, dxg, st));
+    const int n1d = desc.tile_n[0] + 2 * ng, n2d = desc.tile_n[1] + 2 * ng;
+    k_extract_window<<<nb((i64)n1d * n2d * 2, 128), 128, 0, st>>>(em_local.p, em_g.p, desc.tile_lo[0], desc.tile_lo[1], n1d, n2d,
+                                                                n1d_g, n2d_g, 2);
+    return LK_OK;
+  }
+  // (3a) fillAdvectionGhostCells on one rank: periodic wrap (the multi-rank exchange is the caller's)
+  int fillAdvectionGhostCellsLocal() {
+    for (auto* ks : species) LKH_CHECK(lk_periodic_fill_4d(ks->f_eval, &ks->g, 1, 1, st));
+    return LK_OK;
+  }
+
+  // ---- RK4Integrator::stageAdvance / RK6 stage, fused behind the RHS evaluation ----
+  int stageFinish(int stage) {
+    const bool rk4 = desc.rk_order == 4;
+    const int last = nstages() - 1;
+    static const double A6[8][8] = {
+        {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+        {1.0 / 9.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+        {1.0 / 24.0, 1.0 / 8.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+        {1.0 / 6.0, -1.0 / 2.0, 2.0 / 3.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+        {935.0 / 2536.0, -2781.0 / 2536.0, 309.0 / 317.0, 321.0 / 1268.0, 0.0, 0.0, 0.0, 0.0},
+        {-12710.0 / 951.0, 8287.0 / 317.0, -40.0 / 317.0, -6335.0 / 317.0, 8.0, 0.0, 0.0, 0.0},
+        {5840285.0 / 3104064.0, -7019.0 / 2536.0, -52213.0 / 86224.0, 1278709.0 / 517344.0, -433.0 / 2448.0,
+         33.0 / 1088.0, 0.0, 0.0},
+        {-5101675.0 / 1767592.0, 112077.0 / 25994.0, 334875.0 / 441898.0, -973617.0 / 883796.0, -1421.0 / 1394.0,
+         333.0 / 5576.0, 36.0 / 41.0, 0.0}};
+    static const double b6[8] = {41.0 / 840.0, 0.0, 9.0 / 35.0, 9.0 / 280.0, 34.0 / 105.0, 9.0 / 280.0, 9.0 / 35.0, 41 / 840.0};
+    static const double c6[8] = {0.0, 1.0 / 9.0, 1.0 / 6.0, 1.0 / 3.0, 1.0 / 2.0, 2.0 / 3.0, 5.0 / 6.0, 1.0};
+    // stage time (RK4Integrator.H:84-120, RK6Integrator.H:109-121)
+    double t_stage;
+    if (rk4) {
+      const double dtOn2 = 0.5 * dt;
+      t_stage = (stage == 0) ? time : (stage == 3 ? time + dt : time + dtOn2);
+    } else {
+      t_stage = time + c6[stage] * dt;
+    }
+    for (auto* ks : species) {
+      // (4) acceleration; the maxima are only consumed by the next stableDt -> last stage
+      LKH_CHECK(ks->computeAcceleration(em_local.p, t_stage, desc.xlo, desc.tile_lo, stage == last, st));
+      // (5) velocity-boundary fill, then advection + acceleration derivatives + RK update in one pass
+      LKH_CHECK(ks->setAccelerationBCs(ks->f_eval, st));
+      lk_accel a = ks->accelDesc();
+      lk_rk_update u;
+      memset(&u, 0, sizeof(u));
+      double* pred = (ks->f_eval == ks->farr[ks->i_a].p) ? ks->farr[ks->i_b].p : ks->farr[ks->i_a].p;
+      u.f_old = ks->state();
+      u.pred = pred;
+      double* rhs_out = nullptr;
+      double ke_coef[8];
+      int ke_ncoef = 0;
+      if (rk4) {
+        static const double THIRD = 1.0 / 3.0;
+        const double dtOn2 = 0.5 * dt, dtOn3 = THIRD * dt, dtOn6 = 0.5 * dtOn3;
+        const double w_eval[4] = {dtOn6, dtOn3, dtOn3, dtOn6};
+        const double w_upd[4] = {dtOn2, dtOn2, dt, 1.0};
+        u.delta_in = (stage == 0) ? nullptr : ks->delta.p;   // zeroSolnData(m_delta)
+        u.delta_out = ks->delta.p;
+        u.w_delta = w_eval[stage];
+        u.c_pred = w_upd[stage];
+        u.use_delta = (stage == 3);
+      } else {
+        rhs_out = ks->karr[stage].p;  // m_k[i]
+        const double* coef = (stage == last) ? b6 : A6[stage + 1];
+        int np = 0;
+        for (int j = 0; j < stage; ++j) {
+          ke_coef[ke_ncoef++] = dt * coef[j];
+          u.k_prev[np] = ks->karr[j].p;
+          u.c_prev[np] = dt * coef[j];
+          ++np;
+        }
+        u.n_prev = np;
+        u.c_pred = dt * coef[stage];
+        ke_coef[ke_ncoef++] = dt * coef[stage];
+      }
+      LKH_CHECK(lk_vlasov_rhs(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, st));
+      // completeRHS: the driver's energy input rate, integrated with the state (KineticSpecies.C:1084-1093)
+      if (ks->has_driver) {
+        LKH_CHECK(lk_ke_e_dot(ks->ke.p + 3, ks->f_eval, &ks->g, ks->charge, ks->velocities.p, ks->ext_efield.p, st));
+        if (rk4) {
+          static const double THIRD = 1.0 / 3.0;
+          const double dtOn2 = 0.5 * dt, dtOn3 = THIRD * dt, dtOn6 = 0.5 * dtOn3;
+          const double w_eval[4] = {dtOn6, dtOn3, dtOn3, dtOn6};
+          const double w_upd[4] = {dtOn2, dtOn2, dt, 1.0};
+          k_scalar_rk4<<<1, 1, 0, st>>>(ks->ke.p, w_eval[stage], w_upd[stage], stage == 0, stage == 3);
+        } else {
+          LKH_CUDA(cudaMemcpyAsync(ks->ke_coef.p, ke_coef, sizeof(double) * ke_ncoef, cudaMemcpyHostToDevice, st));
+          k_scalar_rk6<<<1, 1, 0, st>>>(ks->ke.p, ks->ke_k.p, stage, ks->ke_coef.p, ke_ncoef);
+        }
+      }
+      ks->f_eval = pred;  // a_evalSoln of the next stage is the predictor
+    }
+    lambda_stale = true;
+    return LK_OK;
+  }
+
+  int beginStep(double a_dt) {
+    dt = a_dt;
+    for (auto* ks : species) {
+      ks->f_eval = ks->state();  // stage 1 evaluates the old solution
+      if (ks->has_driver) k_copy_scalar<<<1, 1, 0, st>>>(ks->ke.p, 1, 0);  // copySolnData(old, state)
+    }
+    return LK_OK;
+  }
+  int endStep() {
+    // the last predictor is the new state; the previous state's buffer becomes a free predictor buffer
+    for (auto* ks : species) {
+      int i_new = (ks->f_eval == ks->farr[ks->i_a].p) ? ks->i_a : ks->i_b;
+      int i_other = (i_new == ks->i_a) ? ks->i_b : ks->i_a;
+      int i_old = ks->i_state;
+      ks->i_state = i_new;
+      ks->i_a = i_old;
+      ks->i_b = i_other;
+      ks->f_eval = ks->state();
+    }
+    time += dt;
+    return LK_OK;
+  }
+  int advance(double a_dt) {
+    if (desc.ntiles != 1) return LK_ERR_UNSUPPORTED;
+    LKH_CHECK(beginStep(a_dt));
+    for (int stage = 0; stage < nstages(); ++stage) {
+      LKH_CHECK(momentsOf(true));
+      LKH_CHECK(fieldSolve(nullptr));
+      LKH_CHECK(fillAdvectionGhostCellsLocal());
+      LKH_CHECK(stageFinish(stage));
+    }
+    return endStep();
+  }
+
+  int refreshLambda() {
+    if (!lambda_stale) return LK_OK;
+    LKH_CUDA(cudaStreamSynchronize(st));
+    for (auto* ks : species) {
+      double l[2];
+      LKH_CUDA(cudaMemcpy(l, ks->lam.p, sizeof(l), cudaMemcpyDeviceToHost));
+      ks->lambda_max[2] = l[0];
+      ks->lambda_max[3] = l[1];
+    }
+    lambda_stale = false;
+    return LK_OK;
+  }
+
+  // VPSystem::evalRHS in the reference's unfused order (parity hook); single rank
+  int evalRHS(double** rhs_dev, double t) {
+    if (desc.ntiles != 1) return LK_ERR_UNSUPPORTED;
+    LKH_CHECK(momentsOf(false));
+    LKH_CHECK(fieldSolve(nullptr));
+    for (size_t s = 0; s < species.size(); ++s) {
+      KineticSpecies* ks = species[s];
+      double* f = ks->state();
+      LKH_CHECK(lk_periodic_fill_4d(f, &ks->g, 1, 1, st));
+      LKH_CHECK(lk_advection_derivatives_4d(rhs_dev[s], f, &ks->g, ks->velocities.p, st));
+      LKH_CHECK(ks->computeAcceleration(em_local.p, t, desc.xlo, desc.tile_lo, true, st));
+      LKH_CHECK(ks->setAccelerationBCs(f, st));
+      lk_accel a = ks->accelDesc();
+      LKH_CHECK(lk_acceleration_derivatives_4d(rhs_dev[s], f, &ks->g, &a, st));
+      if (ks->has_driver)
+        LKH_CHECK(lk_ke_e_dot(ks->ke.p + 3, f, &ks->g, ks->charge, ks->velocities.p, ks->ext_efield.p, st));
+    }
+    lambda_stale = true;
+    return LK_OK;
+  }
+};
+
+}  // namespace loki
+
+using loki::VPSystem;
+struct lk_vp_system {
+  VPSystem sys;
+};
+
+extern "C" {
+
+int lk_vp_create(lk_vp_system** out, const lk_vp_desc* desc, void* stream) {
+  if (!out || !desc || !desc->species) return LK_ERR_ARG;
+  lk_vp_system* h = new lk_vp_system();
+  int s = h->sys.create(desc, stream);
+  if (s != LK_OK) {
+    delete h;
+    return s;
+  }
+  *out = h;
+  return LK_OK;
+}
+void lk_vp_destroy(lk_vp_system* h) { delete h; }
+int lk_vp_species_geom(const lk_vp_system* h, int s, lk_geom* g) {
+  if (!h || !g || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  *g = h->sys.species[s]->g;
+  return LK_OK;
+}
+int lk_vp_set_state(lk_vp_system* h, int s, const double* f_host) {
+  if (!h || !f_host || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  auto* ks = h->sys.species[s];
+  if (cudaMemcpy(ks->state(), f_host, sizeof(double) * ks->vol, cudaMemcpyHostToDevice) != cudaSuccess) return LK_ERR_CUDA;
+  ks->f_eval = ks->state();
+  return LK_OK;
+}
+int lk_vp_get_state(lk_vp_system* h, int s, double* f_host) {
+  if (!h || !f_host || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  auto* ks = h->sys.species[s];
+  if (cudaStreamSynchronize(h->sys.st) != cudaSuccess) return LK_ERR_CUDA;
+  if (cudaMemcpy(f_host, ks->state(), sizeof(double) * ks->vol, cudaMemcpyDeviceToHost) != cudaSuccess) return LK_ERR_CUDA;
+  return LK_OK;
+}
+double* lk_vp_state_ptr(lk_vp_system* h, int s) { return (h && s >= 0 && s < (int)h->sys.species.size()) ? h->sys.species[s]->state() : nullptr; }
+double* lk_vp_eval_ptr(lk_vp_system* h, int s) { return (h && s >= 0 && s < (int)h->sys.species.size()) ? h->sys.species[s]->f_eval : nullptr; }
+int lk_vp_set_inflow(lk_vp_system* h, int s, const double* fx, const double* fv, double fnorm, double frac) {
+  if (!h || !fx || !fv || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  auto* ks = h->sys.species[s];
+  std::vector<double> a(fx, fx + (size_t)ks->n1d * ks->n2d), b(fv, fv + (size_t)ks->n3d * ks->n4d);
+  int st = ks->ic_fx.upload(a);
+  if (st == LK_OK) st = ks->ic_fv.upload(b);
+  if (st != LK_OK) return st;
+  ks->inflow.kind = 1;
+  ks->inflow.fx = ks->ic_fx.p;
+  ks->inflow.fv = ks->ic_fv.p;
+  ks->inflow.fnorm = fnorm;
+  ks->inflow.frac = frac;
+  return LK_OK;
+}
+int lk_vp_set_time(lk_vp_system* h, double t) {
+  if (!h) return LK_ERR_ARG;
+  h->sys.time = t;
+  return LK_OK;
+}
+double lk_vp_time(const lk_vp_system* h) { return h ? h->sys.time : 0.0; }
+int lk_vp_stable_dt(lk_vp_system* h, double* dt) {
+  if (!h || !dt) return LK_ERR_ARG;
+  int s = h->sys.refreshLambda();
+  if (s != LK_OK) return s;
+  double v = std::numeric_limits<double>::max();
+  for (auto* ks : h->sys.species) v = std::min(v, ks->computeDt(h->sys.desc.rk_order));
+  *dt = v;
+  return LK_OK;
+}
+int lk_vp_lambda_max(lk_vp_system* h, int s, double out[2]) {
+  if (!h || !out || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  int st = h->sys.refreshLambda();
+  if (st != LK_OK) return st;
+  out[0] = h->sys.species[s]->lambda_max[2];
+  out[1] = h->sys.species[s]->lambda_max[3];
+  return LK_OK;
+}
+int lk_vp_advance(lk_vp_system* h, double dt) { return h ? h->sys.advance(dt) : LK_ERR_ARG; }
+int lk_vp_nstages(const lk_vp_system* h) { return h ? h->sys.nstages() : 0; }
+int lk_vp_begin_step(lk_vp_system* h, double dt) { return h ? h->sys.beginStep(dt) : LK_ERR_ARG; }
+int lk_vp_stage_moments(lk_vp_system* h, int stage) {
+  (void)stage;
+  return h ? h->sys.momentsOf(true) : LK_ERR_ARG;
+}
+double* lk_vp_rho_tile_ptr(lk_vp_system* h) { return h ? h->sys.rho_tile_p : nullptr; }
+double* lk_vp_rho_gather_ptr(lk_vp_system* h) { return h ? h->sys.rho_gather_p : nullptr; }
+int lk_vp_set_comm_buffers(lk_vp_system* h, double* tile, double* gather) {
+  if (!h || !tile || !gather) return LK_ERR_ARG;
+  h->sys.rho_tile_p = tile;
+  h->sys.rho_gather_p = gather;
+  return LK_OK;
+}
+int lk_vp_stage_field(lk_vp_system* h, int stage, const int* tiles) {
+  (void)stage;
+  if (!h) return LK_ERR_ARG;
+  int s = h->sys.fieldSolve(tiles);
+  if (s != LK_OK) return s;
+  if (tiles == nullptr || h->sys.desc.ntiles == 1) return h->sys.fillAdvectionGhostCellsLocal();
+  return LK_OK;
+}
+int lk_vp_stage_finish(lk_vp_system* h, int stage) {
+  if (!h || stage < 0 || stage >= h->sys.nstages()) return LK_ERR_ARG;
+  return h->sys.stageFinish(stage);
+}
+int lk_vp_end_step(lk_vp_system* h) { return h ? h->sys.endStep() : LK_ERR_ARG; }
+int lk_vp_eval_rhs(lk_vp_system* h, double** rhs_dev, double time) { return (h && rhs_dev) ? h->sys.evalRHS(rhs_dev, time) : LK_ERR_ARG; }
+const double* lk_vp_em_vars_ptr(const lk_vp_system* h) { return h ? h->sys.em_g.p : nullptr; }
+const double* lk_vp_rho_ptr(const lk_vp_system* h) { return h ? h->sys.rho_g.p : nullptr; }
+int lk_vp_ke_e_dot(lk_vp_system* h, int s, double* value) {
+  if (!h || !value || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  if (cudaStreamSynchronize(h->sys.st) != cudaSuccess) return LK_ERR_CUDA;
+  if (cudaMemcpy(value, h->sys.species[s]->ke.p, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return LK_ERR_CUDA;
+  return LK_OK;
+}
+
+}  // extern "C"

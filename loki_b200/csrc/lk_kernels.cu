@@ -49,6 +49,11 @@ static DUpd make_upd(const lk_rk_update* u) {
     d.c_pred = u->c_pred;
     d.use_delta = u->use_delta;
     d.active = 1;
+    d.n_prev = u->n_prev;
+    for (int j = 0; j < 7; ++j) {
+      d.k_prev[j] = u->k_prev[j];
+      d.c_prev[j] = u->c_prev[j];
+    }
   }
   return d;
 }

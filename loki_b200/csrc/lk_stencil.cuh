@@ -92,6 +92,18 @@ k_stencil_tiled(const DGeo g, const double* __restrict__ f, const double* __rest
   const int ng = g.ng;  // == NG
   const i64 base = gidx(g, o0 + ng, o1 + ng, o2 + ng, o3 + ng);  // data index of tile cell (0,0,0,0)
 
+  // pull this tile's rows of the RK operands towards L2 now; the epilogue reads them ~10 us later
+  if (upd.active) {
+    for (int row = tid; row < T1 * T2 * T3; row += NT) {
+      const int b1 = row % T1, c = (row / T1) % T2, d = row / (T1 * T2);
+      if ((o1 + b1 < g.n[1]) && (o2 + c < g.n[2]) && (o3 + d < g.n[3])) {
+        const i64 o = base + g.s[1] * b1 + g.s[2] * c + g.s[3] * d;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(upd.f_old + o));
+        if (upd.delta_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(upd.delta_in + o));
+      }
+    }
+  }
+
   // ---------------- stage tile + star halo ----------------
   if (TMA) {
     if (tid == 0) {
@@ -342,7 +354,7 @@ k_stencil_tiled(const DGeo g, const double* __restrict__ f, const double* __rest
       if (upd.active) {
         const double dl = rk_delta(upd, res[d], di[d], upd.delta_in != nullptr);
         if (upd.delta_out) upd.delta_out[idx] = dl;
-        upd.pred[idx] = rk_pred(upd, fo[d], upd.use_delta ? dl : res[d]);
+        upd.pred[idx] = rk_pred(upd, fo[d], upd.use_delta ? dl : res[d], idx);
       }
     }
   }

@@ -113,21 +113,34 @@ void ok_maxwell_eval_vz_rhs(double* rhs, const double* em, double charge_per_mas
 typedef struct ok_species {
   ok_geom g;
   double mass, charge, bz_const;
-  double vlo[2];              /* velocity-domain lower bounds                          */
+  double vlo[2], vhi[2];      /* velocity-domain bounds                                */
   ok_ic_fn ic; void* ic_ctx;  /* inflow BC                                             */
-  const double* ext_efield;   /* (n1d,n2d,2) external driver field for this stage or NULL */
+  int has_driver;             /* ShapedRampedCosineDriver acting on this species       */
+  double driver[16];          /* parameter vector in the reference's enum order        */
+  double driver_phase;
+  int driver_shape_type;
 } ok_species;
 
+/* ShapedRampedCosineDriverF.f:10-189: adds the driver field into em_vars(:,:,0) and ext_efield(:,:,0)
+ * over the whole 2D data box (lo_index = global index of element 0) */
+void ok_shaped_ramped_driver(double* em_vars, double* ext_efield, int n1d, int n2d, int lo1, int lo2,
+                             const double* xlo, const double* dx, int sums_into, double t,
+                             const double* e_ext_param, double phase, int shape_type);
+
 typedef struct ok_vp_work ok_vp_work;
-ok_vp_work* ok_vp_work_create(int nspecies, const ok_species* sp, double Lx, double Ly);
+ok_vp_work* ok_vp_work_create(int nspecies, const ok_species* sp, const double* xlo, const double* xhi);
 void ok_vp_work_destroy(ok_vp_work* w);
 /* rhs[s], f[s]: 4D arrays incl. ghosts; f's ghosts are modified like the reference does.
- * ke_e_dot[s] receives rhs.m_integrated_ke_e_dot when sp[s].ext_efield != NULL. */
-void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double* ke_e_dot, double* axmax,
+ * ke_e_dot[s] receives rhs.m_integrated_ke_e_dot for driven species. */
+void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double time, double* ke_e_dot, double* axmax,
                     double* aymax);
 const double* ok_vp_em_vars(const ok_vp_work* w); /* (n1d,n2d,2) E field of the last evalRHS */
 const double* ok_vp_rho(const ok_vp_work* w);     /* neutralised net charge density          */
-void ok_vp_rk4_step(ok_vp_work* w, double** f_new, double** f_old, double dt);
+/* RK4Integrator / RK6Integrator ::advance; ke[s] = m_integrated_ke_e_dot of the state (in: old, out: new) */
+void ok_vp_rk4_step(ok_vp_work* w, double** f_new, double** f_old, double time, double dt, double* ke);
+void ok_vp_rk6_step(ok_vp_work* w, double** f_new, double** f_old, double time, double dt, double* ke);
+/* KineticSpecies::computeDt + VPSystem::stableDt from given axmax/aymax */
+double ok_vp_stable_dt(const ok_vp_work* w, const double* axmax, const double* aymax, int rk_order);
 
 /* unfused CPU timing leg used by bench.py (same passes as the reference does per RK4 stage) */
 double ok_time_rk4_stage_reference_style(const ok_geom* g, int nthreads, int reps);

@@ -15,28 +15,86 @@
 struct ok_vp_work {
   int ns;
   ok_species* sp;
-  double Lx, Ly;
+  double xlo[2], xhi[2];
   /* per species */
-  double **velocities, **vxface, **vyface, **vel1, **vel2, **vel3, **vel4, **accel, **rho_s;
+  double **velocities, **vxface, **vyface, **vel1, **vel2, **vel3, **vel4, **accel, **rho_s, **ext;
   /* field */
   double *rho, *phi, *em, *sx, *sy;
   /* RK scratch */
-  double **rhs, **delta;
-  double *ke_rhs, *ke_delta;
+  double **rhs, **delta, **k[8];
+  double *ke_rhs, *ke_delta, *ke_k[8];
 };
 
 static int64_t vol4(const ok_geom* g) { return ok_nd(g, 0) * ok_nd(g, 1) * ok_nd(g, 2) * ok_nd(g, 3); }
 
-ok_vp_work* ok_vp_work_create(int ns, const ok_species* sp, double Lx, double Ly) {
+/* ------------------------------------------------------------------------------------------
+ * ShapedRampedCosineDriver (ShapedRampedCosineDriverF.f:10-189)
+ * ------------------------------------------------------------------------------------------ */
+static double drv_ghat(double x, double t, const double* p, double phase, double pi, int shape_type) {
+  double xwidth = p[0], omega = p[3], t0 = p[5], x_shape = p[9], lwidth = p[10], x0 = p[11], alpha = p[12], t_res = p[13];
+  double ghat;
+  if (shape_type == 0) {
+    if (fabs(x - x0) < 0.5 * lwidth) {
+      double sn = sin(pi * (x - x0) / lwidth);
+      ghat = 1.0 - x_shape * (sn * sn);
+    } else {
+      ghat = 1.0 - x_shape;
+    }
+  } else {
+    if (lwidth >= 0) {
+      if (x <= x0) ghat = 1.0; else ghat = 1.0 - x_shape * (1.0 - exp(-(x - x0) / lwidth));
+    } else {
+      if (x <= x0) ghat = 1.0 - x_shape * (1.0 - exp(-(x - x0) / lwidth)); else ghat = 1.0;
+    }
+  }
+  double tt = t - t0 - t_res;
+  ghat = ghat * cos(pi * x / xwidth - omega * (t - t0) + phase - 0.5 * alpha * (tt * tt));
+  return ghat;
+}
+static double drv_h(double y, const double* p, double pi) {
+  double ywidth = p[1], shape = p[2];
+  if (fabs(y) < 0.5 * ywidth) {
+    double sn = sin(pi * y / ywidth);
+    return 1.0 - shape * (sn * sn);
+  }
+  return 1.0 - shape;
+}
+static double drv_envelope(double t, double t0, double t_rampup, double t_hold, double t_rampdown, double E_0) {
+  if ((t < t0) || (t >= t0 + t_rampup + t_hold + t_rampdown)) return 0.0;
+  if (t < t0 + t_rampup) return E_0 * (0.5 + 0.5 * tanh(4.0 * (2.0 * (t - t0) / t_rampup - 1.0)));
+  if (t < t0 + t_rampup + t_hold) return E_0 * (0.5 + 0.5 * tanh(4.0));
+  return E_0 * (0.5 - 0.5 * tanh(4.0 * (2.0 * (t - t0 - t_rampup - t_hold) / t_rampdown - 1.0)));
+}
+void ok_shaped_ramped_driver(double* em_vars, double* ext_efield, int n1d, int n2d, int lo1, int lo2,
+                             const double* xlo, const double* dx, int sums_into, double t,
+                             const double* p, double phase, int shape_type) {
+  const double one = 1.0, four = 4.0;
+  const double pi = four * atan(one);
+  const double E_0 = p[4], t0 = p[5], t_rampup = p[6], t_hold = p[7], t_rampdown = p[8];
+  if ((t < (t0 + t_rampup + t_hold + t_rampdown)) && t >= t0) {
+    double envel = drv_envelope(t, t0, t_rampup, t_hold, t_rampdown, E_0);
+    for (int i2 = 0; i2 < n2d; ++i2)
+      for (int i1 = 0; i1 < n1d; ++i1) {
+        double xcoord = xlo[0] + dx[0] * (0.5 + (lo1 + i1));
+        double ycoord = xlo[1] + dx[1] * (0.5 + (lo2 + i2));
+        double g = drv_ghat(xcoord, t, p, phase, pi, shape_type);
+        double h = drv_h(ycoord, p, pi);
+        ext_efield[i1 + (int64_t)n1d * i2] = ext_efield[i1 + (int64_t)n1d * i2] + envel * h * g;
+        if (sums_into == 2) em_vars[i1 + (int64_t)n1d * i2] = em_vars[i1 + (int64_t)n1d * i2] + envel * h * g;
+      }
+  }
+}
+
+ok_vp_work* ok_vp_work_create(int ns, const ok_species* sp, const double* xlo, const double* xhi) {
   ok_vp_work* w = (ok_vp_work*)calloc(1, sizeof(*w));
   w->ns = ns;
   w->sp = (ok_species*)malloc(sizeof(ok_species) * ns);
   memcpy(w->sp, sp, sizeof(ok_species) * ns);
-  w->Lx = Lx;
-  w->Ly = Ly;
+  for (int k = 0; k < 2; ++k) { w->xlo[k] = xlo[k]; w->xhi[k] = xhi[k]; }
 #define PP(name) w->name = (double**)calloc(ns, sizeof(double*))
-  PP(velocities); PP(vxface); PP(vyface); PP(vel1); PP(vel2); PP(vel3); PP(vel4); PP(accel); PP(rho_s);
+  PP(velocities); PP(vxface); PP(vyface); PP(vel1); PP(vel2); PP(vel3); PP(vel4); PP(accel); PP(rho_s); PP(ext);
   PP(rhs); PP(delta);
+  for (int i = 0; i < 8; ++i) { PP(k[i]); w->ke_k[i] = (double*)calloc(ns, sizeof(double)); }
 #undef PP
   w->ke_rhs = (double*)calloc(ns, sizeof(double));
   w->ke_delta = (double*)calloc(ns, sizeof(double));
@@ -53,6 +111,7 @@ ok_vp_work* ok_vp_work_create(int ns, const ok_species* sp, double Lx, double Ly
     w->vel3[s] = (double*)calloc((n3d + 1) * n4d * n1d * n2d, sizeof(double));
     w->vel4[s] = (double*)calloc((n4d + 1) * n1d * n2d * n3d, sizeof(double));
     w->accel[s] = (double*)calloc(n1d * n2d * 2, sizeof(double));
+    w->ext[s] = (double*)calloc(n1d * n2d * 2, sizeof(double));
     w->rho_s[s] = (double*)calloc(n1d * n2d, sizeof(double));
     w->rhs[s] = (double*)calloc(vol4(g), sizeof(double));
     w->delta[s] = (double*)calloc(vol4(g), sizeof(double));
@@ -65,7 +124,7 @@ ok_vp_work* ok_vp_work_create(int ns, const ok_species* sp, double Lx, double Ly
   w->em = (double*)calloc(n1d * n2d * 2, sizeof(double));
   w->sx = (double*)calloc(g0->n[0], sizeof(double));
   w->sy = (double*)calloc(g0->n[1] / 2 + 1, sizeof(double));
-  ok_poisson_symbols(g0->n[0], g0->n[1], Lx, Ly, g0->order, w->sx, w->sy);
+  ok_poisson_symbols(g0->n[0], g0->n[1], xhi[0] - xlo[0], xhi[1] - xlo[1], g0->order, w->sx, w->sy);
   return w;
 }
 
@@ -73,10 +132,13 @@ void ok_vp_work_destroy(ok_vp_work* w) {
   if (!w) return;
   for (int s = 0; s < w->ns; ++s) {
     free(w->velocities[s]); free(w->vxface[s]); free(w->vyface[s]); free(w->vel1[s]); free(w->vel2[s]);
-    free(w->vel3[s]); free(w->vel4[s]); free(w->accel[s]); free(w->rho_s[s]); free(w->rhs[s]); free(w->delta[s]);
+    free(w->vel3[s]); free(w->vel4[s]); free(w->accel[s]); free(w->ext[s]); free(w->rho_s[s]); free(w->rhs[s]);
+    free(w->delta[s]);
+    for (int i = 0; i < 8; ++i) free(w->k[i][s]);
   }
+  for (int i = 0; i < 8; ++i) { free(w->k[i]); free(w->ke_k[i]); }
   free(w->velocities); free(w->vxface); free(w->vyface); free(w->vel1); free(w->vel2); free(w->vel3);
-  free(w->vel4); free(w->accel); free(w->rho_s); free(w->rhs); free(w->delta); free(w->ke_rhs);
+  free(w->vel4); free(w->accel); free(w->ext); free(w->rho_s); free(w->rhs); free(w->delta); free(w->ke_rhs);
   free(w->ke_delta); free(w->rho); free(w->phi); free(w->em); free(w->sx); free(w->sy); free(w->sp);
   free(w);
 }
@@ -85,7 +147,7 @@ const double* ok_vp_em_vars(const ok_vp_work* w) { return w->em; }
 const double* ok_vp_rho(const ok_vp_work* w) { return w->rho; }
 
 /* VPSystem::evalRHS on one rank */
-void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double* ke_e_dot, double* axmax, double* aymax) {
+void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double time, double* ke_e_dot, double* axmax, double* aymax) {
   const ok_geom* g0 = &w->sp[0].g;
   const int ng = g0->ng, n1 = g0->n[0], n2 = g0->n[1];
   const int64_t n1d = ok_nd(g0, 0), n2d = ok_nd(g0, 1), pl = n1d * n2d;
@@ -112,8 +174,11 @@ void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double* ke_e_dot, d
     ok_advection_derivatives_4d(rhs[s], f[s], g, w->vel1[s], w->vel2[s]);
     /* 4. acceleration (KineticSpecies.C:697-774): expansion, drivers, *= q/m, face accelerations */
     for (int64_t k = 0; k < 2 * pl; ++k) w->accel[s][k] = w->em[k];
-    if (sp->ext_efield)
-      for (int64_t k = 0; k < 2 * pl; ++k) w->accel[s][k] += sp->ext_efield[k];
+    if (sp->has_driver) {
+      for (int64_t k = 0; k < 2 * pl; ++k) w->ext[s][k] = 0.0;
+      ok_shaped_ramped_driver(w->accel[s], w->ext[s], (int)n1d, (int)n2d, -ng, -ng, w->xlo, g->dx, 2, time, sp->driver,
+                              sp->driver_phase, sp->driver_shape_type);
+    }
     double normalization = sp->charge / sp->mass;
     for (int64_t k = 0; k < 2 * pl; ++k) w->accel[s][k] *= normalization;
     ok_set_phase_space_vel_4d(w->vel3[s], w->vel4[s], g, w->vxface[s], w->vyface[s], normalization,
@@ -121,24 +186,25 @@ void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double* ke_e_dot, d
     /* 5. v-boundary fill, acceleration derivatives, completeRHS */
     ok_set_acceleration_bcs_4d(f[s], g, w->vel3[s], w->vel4[s], 1, 1, 1, 1, sp->ic, sp->ic_ctx);
     ok_acceleration_derivatives_4d(rhs[s], f[s], g, w->vel3[s], w->vel4[s]);
-    if (sp->ext_efield && ke_e_dot)
-      ke_e_dot[s] = ok_compute_ke_e_dot(g, f[s], sp->charge, w->velocities[s], sp->ext_efield, 0.0);
+    if (sp->has_driver && ke_e_dot)
+      ke_e_dot[s] = ok_compute_ke_e_dot(g, f[s], sp->charge, w->velocities[s], w->ext[s], 0.0);
   }
 }
 
-/* RK4Integrator::advance with stageAdvance (RK4Integrator.H:66-171).  The external driver field is
- * frozen for the step (tests that need a time-dependent driver update sp.ext_efield between calls of
- * the stage-level API instead). */
-void ok_vp_rk4_step(ok_vp_work* w, double** f_new, double** f_old, double dt) {
+/* RK4Integrator::advance with stageAdvance (RK4Integrator.H:66-171) */
+void ok_vp_rk4_step(ok_vp_work* w, double** f_new, double** f_old, double time, double dt, double* ke) {
   static const double THIRD = 1.0 / 3.0;
   double dtOn2 = 0.5 * dt, dtOn3 = THIRD * dt, dtOn6 = 0.5 * dtOn3;
   const double w_eval[4] = {dtOn6, dtOn3, dtOn3, dtOn6};
   const double w_upd[4] = {dtOn2, dtOn2, dt, 1.0};
+  const double t_stage[4] = {time, time + dtOn2, time + dtOn2, time + dt};
   double* ax = (double*)calloc(w->ns, sizeof(double));
   double* ay = (double*)calloc(w->ns, sizeof(double));
+  double* ke_old = (double*)calloc(w->ns, sizeof(double));
   for (int s = 0; s < w->ns; ++s) {
     memset(w->delta[s], 0, sizeof(double) * vol4(&w->sp[s].g));
     w->ke_delta[s] = 0.0;
+    ke_old[s] = ke ? ke[s] : 0.0;
   }
   for (int stage = 1; stage <= 4; ++stage) {
     double** eval = (stage == 1) ? f_old : f_new;
@@ -146,19 +212,97 @@ void ok_vp_rk4_step(ok_vp_work* w, double** f_new, double** f_old, double dt) {
       memset(w->rhs[s], 0, sizeof(double) * vol4(&w->sp[s].g));
       w->ke_rhs[s] = 0.0;
     }
-    ok_vp_eval_rhs(w, w->rhs, eval, w->ke_rhs, ax, ay);
+    ok_vp_eval_rhs(w, w->rhs, eval, t_stage[stage - 1], w->ke_rhs, ax, ay);
     for (int s = 0; s < w->ns; ++s) {
       const ok_geom* g = &w->sp[s].g;
       ok_xpby4d(w->delta[s], w->rhs[s], w_eval[stage - 1], g);
+      w->ke_delta[s] += w->ke_rhs[s] * w_eval[stage - 1];
       memcpy(f_new[s], f_old[s], sizeof(double) * vol4(g)); /* copySolnData copies ghosts too */
-      if (stage < 4)
+      double kn = ke_old[s];
+      if (stage < 4) {
         ok_xpby4d(f_new[s], w->rhs[s], w_upd[stage - 1], g);
-      else
+        kn += w->ke_rhs[s] * w_upd[stage - 1];
+      } else {
         ok_xpby4d(f_new[s], w->delta[s], w_upd[stage - 1], g);
+        kn += w->ke_delta[s] * w_upd[stage - 1];
+      }
+      if (ke) ke[s] = kn;
     }
   }
-  free(ax);
-  free(ay);
+  free(ax); free(ay); free(ke_old);
+}
+
+/* RK6Integrator::advance (RK6Integrator.H:69-133) */
+void ok_vp_rk6_step(ok_vp_work* w, double** f_new, double** f_old, double time, double dt, double* ke) {
+  static const double A[8][8] =
+      {{0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+       {1.0/9.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+       {1.0/24.0, 1.0/8.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+       {1.0/6.0, -1.0/2.0, 2.0/3.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+       {935.0/2536.0, -2781.0/2536.0, 309.0/317.0, 321.0/1268.0, 0.0, 0.0, 0.0, 0.0},
+       {-12710.0/951.0, 8287.0/317.0, -40.0/317.0, -6335.0/317.0, 8.0, 0.0, 0.0, 0.0},
+       {5840285.0/3104064.0, -7019.0/2536.0, -52213.0/86224.0, 1278709.0/517344.0, -433.0/2448.0, 33.0/1088.0, 0.0, 0.0},
+       {-5101675.0/1767592.0, 112077.0/25994.0, 334875.0/441898.0, -973617.0/883796.0, -1421.0/1394.0, 333.0/5576.0, 36.0/41.0, 0.0}};
+  static const double b[8] = {41.0/840.0, 0.0, 9.0/35.0, 9.0/280.0, 34.0/105.0, 9.0/280.0, 9.0/35.0, 41/840.0};
+  static const double c[8] = {0.0, 1.0/9.0, 1.0/6.0, 1.0/3.0, 1.0/2.0, 2.0/3.0, 5.0/6.0, 1.0};
+  double* ax = (double*)calloc(w->ns, sizeof(double));
+  double* ay = (double*)calloc(w->ns, sizeof(double));
+  double* ke_old = (double*)calloc(w->ns, sizeof(double));
+  for (int s = 0; s < w->ns; ++s) {
+    ke_old[s] = ke ? ke[s] : 0.0;
+    for (int i = 0; i < 8; ++i) {
+      if (!w->k[i][s]) w->k[i][s] = (double*)malloc(sizeof(double) * vol4(&w->sp[s].g));
+      memset(w->k[i][s], 0, sizeof(double) * vol4(&w->sp[s].g));
+      w->ke_k[i][s] = 0.0;
+    }
+    memcpy(f_new[s], f_old[s], sizeof(double) * vol4(&w->sp[s].g));
+  }
+  ok_vp_eval_rhs(w, w->k[0], f_new, time + c[0] * dt, w->ke_k[0], ax, ay);
+  for (int i = 1; i < 8; ++i) {
+    for (int s = 0; s < w->ns; ++s) {
+      const ok_geom* g = &w->sp[s].g;
+      memcpy(f_new[s], f_old[s], sizeof(double) * vol4(g));
+      for (int j = 0; j < i; ++j) ok_xpby4d(f_new[s], w->k[j][s], dt * A[i][j], g);
+    }
+    ok_vp_eval_rhs(w, w->k[i], f_new, time + c[i] * dt, w->ke_k[i], ax, ay);
+  }
+  for (int s = 0; s < w->ns; ++s) {
+    const ok_geom* g = &w->sp[s].g;
+    memcpy(f_new[s], f_old[s], sizeof(double) * vol4(g));
+    double kn = ke_old[s];
+    for (int i = 0; i < 8; ++i) {
+      ok_xpby4d(f_new[s], w->k[i][s], dt * b[i], g);
+      kn += w->ke_k[i][s] * (dt * b[i]);
+    }
+    if (ke) ke[s] = kn;
+  }
+  free(ax); free(ay); free(ke_old);
+}
+
+/* KineticSpecies::computeDt (KineticSpecies.C:647-694) and VPSystem::stableDt (VPSystem.C:489-505) */
+double ok_vp_stable_dt(const ok_vp_work* w, const double* axmax, const double* aymax, int rk_order) {
+  const double pi = 4.0 * atan(1.0);
+  double dt_stable = 1.7976931348623157e308;
+  for (int s = 0; s < w->ns; ++s) {
+    const ok_geom* g = &w->sp[s].g;
+    const ok_species* sp = &w->sp[s];
+    double lam[4];
+    /* KineticSpecies.C:1547-1555: note the upper bound is vhi + dv/2 as written in the reference */
+    double vlo = sp->vlo[0] + 0.5 * (sp->vhi[0] - sp->vlo[0]) / g->n[2];
+    double vhi = sp->vhi[0] + 0.5 * (sp->vhi[0] - sp->vlo[0]) / g->n[2];
+    lam[0] = fmax(fabs(vlo), fabs(vhi));
+    vlo = sp->vlo[1] + 0.5 * (sp->vhi[1] - sp->vlo[1]) / g->n[3];
+    vhi = sp->vhi[1] + 0.5 * (sp->vhi[1] - sp->vlo[1]) / g->n[3];
+    lam[1] = fmax(fabs(vlo), fabs(vhi));
+    lam[2] = axmax[s];
+    lam[3] = aymax[s];
+    double imLam = 0.0, reLam = 0.0;
+    for (int d = 0; d < 4; ++d) imLam += pi * lam[d] / g->dx[d];
+    double alpha = rk_order == 4 ? 2.6 : 4.95, beta = rk_order == 4 ? 2.6 : 3.168;
+    double ddt = sqrt(1.0 / (reLam * reLam / (alpha * alpha) + imLam * imLam / (beta * beta)));
+    if (ddt < dt_stable) dt_stable = ddt;
+  }
+  return dt_stable;
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -33,7 +33,9 @@ class OkGeom(C.Structure):
 
 class OkSpecies(C.Structure):
     _fields_ = [("g", OkGeom), ("mass", C.c_double), ("charge", C.c_double), ("bz_const", C.c_double),
-                ("vlo", C.c_double * 2), ("ic", IC_FN), ("ic_ctx", C.c_void_p), ("ext_efield", C.c_void_p)]
+                ("vlo", C.c_double * 2), ("vhi", C.c_double * 2), ("ic", IC_FN), ("ic_ctx", C.c_void_p),
+                ("has_driver", C.c_int), ("driver", C.c_double * 16), ("driver_phase", C.c_double),
+                ("driver_shape_type", C.c_int)]
 
 
 def load():
@@ -73,14 +75,18 @@ def load():
     L.ok_poisson_fft_solve.argtypes = [dp, dp, i, i, i, dp, dp]
     L.ok_efield_from_potential.argtypes = [dp, dp, i, i, i, i, i, dp]
     L.ok_vp_work_create.restype = C.c_void_p
-    L.ok_vp_work_create.argtypes = [i, C.POINTER(OkSpecies), d, d]
+    L.ok_vp_work_create.argtypes = [i, C.POINTER(OkSpecies), C.POINTER(d * 2), C.POINTER(d * 2)]
     L.ok_vp_work_destroy.argtypes = [C.c_void_p]
-    L.ok_vp_eval_rhs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), dp, dp, dp]
+    L.ok_vp_eval_rhs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), d, dp, dp, dp]
     L.ok_vp_em_vars.restype = C.POINTER(d)
     L.ok_vp_em_vars.argtypes = [C.c_void_p]
     L.ok_vp_rho.restype = C.POINTER(d)
     L.ok_vp_rho.argtypes = [C.c_void_p]
-    L.ok_vp_rk4_step.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), d]
+    L.ok_vp_rk4_step.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), d, d, dp]
+    L.ok_vp_rk6_step.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), d, d, dp]
+    L.ok_vp_stable_dt.restype = d
+    L.ok_vp_stable_dt.argtypes = [C.c_void_p, dp, dp, i]
+    L.ok_shaped_ramped_driver.argtypes = [dp, dp, i, i, i, i, dp, dp, i, d, dp, d, i]
     L.ok_time_rk4_stage_reference_style.restype = d
     L.ok_time_rk4_stage_reference_style.argtypes = [G, i, i]
     _L = L

@@ -12,9 +12,11 @@ def test_library_exports_every_declared_symbol():
     import loki_b200
     L = loki_b200.load()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    hdr = open(os.path.join(root, "include", "loki_b200.h")).read()
-    names = set(re.findall(r"\b(lk_[a-z0-9_]+)\s*\(", hdr))
-    assert len(names) > 25
+    names = set()
+    for h in ("loki_b200.h", "loki_b200_host.h"):
+        hdr = open(os.path.join(root, "include", h)).read()
+        names |= set(re.findall(r"\b(lk_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) > 55
     missing = [n for n in sorted(names) if not hasattr(L, n)]
     assert not missing, missing
     assert L.lk_version() >= 100

@@ -1,0 +1,188 @@
+"""System-level parity: the C++ host mirror (lk_vp_*: VPSystem / KineticSpecies / RK integrators on the
+device) against the oracle's single-rank restatement of VPSystem::evalRHS and the RK4/RK6 integrators,
+on deck-shaped problems (test/planeEPW_fixedIons, test/planeIAW, test/planeIAW_6)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import decks
+from util import cell_rel_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(ok, deck):
+    keep = []
+    sp = deck.oracle_species(keep)
+    xlo = (C.c_double * 2)(deck.xlim[0], deck.xlim[2])
+    xhi = (C.c_double * 2)(deck.xlim[1], deck.xlim[3])
+    w = ok.ok_vp_work_create(len(deck.species), sp, C.byref(xlo), C.byref(xhi))
+    return w, sp, keep
+
+
+def _ptrs(arrs):
+    return (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+def _product(deck, states, tables):
+    from loki_b200 import host
+    H = host.lib()
+    d = deck.product_desc()
+    sys_ = C.c_void_p()
+    assert H.lk_vp_create(C.byref(sys_), C.byref(d), None) == 0, H.lk_last_error()
+    for s, f in enumerate(states):
+        assert H.lk_vp_set_state(sys_, s, f.ctypes.data) == 0
+        fx, fv, fnorm = tables[s]
+        assert H.lk_vp_set_inflow(sys_, s, fx.ctypes.data, fv.ctypes.data, fnorm, deck.species[s].frac) == 0
+    return H, sys_
+
+
+def _perturb(f, seed, amp=0.05):
+    rng = np.random.default_rng(seed)
+    return np.ascontiguousarray(f * (1.0 + amp * rng.uniform(-1, 1, size=f.shape)))
+
+
+DECKS = [
+    lambda: decks.plane_epw(n=(16, 8), nv=(32, 16)),
+    lambda: decks.plane_iaw(n=(12, 10), nv=(16, 12)),
+    lambda: decks.plane_iaw(n=(10, 10), nv=(16, 10), order=6, rk=6),   # planeIAW_6 deck grid verbatim
+]
+
+
+@pytest.mark.parametrize("mk", DECKS)
+def test_eval_rhs_strict_matches_reference_order(lk, ok, strict, mk):
+    """VPSystem::evalRHS, unfused and in the reference's order: rho, E, rhs, lambda_max bit for bit"""
+    import torch
+    deck = mk()
+    w, sp, keep = _oracle(ok, deck)
+    states, tables = [], []
+    for k, s in enumerate(deck.species):
+        f, fx, fv, fnorm = deck.initial_state(s)
+        states.append(_perturb(f, 10 + k))
+        tables.append((fx, fv, fnorm))
+    t = 0.37
+    ns = len(states)
+    f_o = [s.copy() for s in states]
+    rhs_o = [np.zeros_like(s) for s in states]
+    ke, ax, ay = np.zeros(ns), np.zeros(ns), np.zeros(ns)
+    ok.ok_vp_eval_rhs(w, _ptrs(rhs_o), _ptrs(f_o), t, ke, ax, ay)
+    H, sys_ = _product(deck, states, tables)
+    rhs_d = [torch.zeros(s.shape, dtype=torch.float64, device="cuda") for s in states]
+    ptrs = (C.c_void_p * ns)(*[r.data_ptr() for r in rhs_d])
+    assert H.lk_vp_eval_rhs(sys_, ptrs, t) == 0, H.lk_last_error()
+    ng = deck.ng
+    n1d, n2d = deck.n[0] + 2 * ng, deck.n[1] + 2 * ng
+    em_o = np.ctypeslib.as_array(ok.ok_vp_em_vars(w), shape=(2, n2d, n1d))
+    rho_o = np.ctypeslib.as_array(ok.ok_vp_rho(w), shape=(n2d, n1d))
+    em_d, rho_d = np.empty_like(em_o), np.empty_like(rho_o)
+    torch.cuda.synchronize()
+    assert lk.lk_memcpy_d2h(em_d.ctypes.data, H.lk_vp_em_vars_ptr(sys_), em_d.nbytes) == 0
+    assert lk.lk_memcpy_d2h(rho_d.ctypes.data, H.lk_vp_rho_ptr(sys_), rho_d.nbytes) == 0
+    assert np.array_equal(rho_d, rho_o)
+    assert np.array_equal(em_d, em_o)
+    for s in range(ns):
+        assert np.array_equal(rhs_d[s].cpu().numpy(), rhs_o[s])
+        out = np.empty_like(states[s])
+        assert H.lk_vp_get_state(sys_, s, out.ctypes.data) == 0
+        assert np.array_equal(out, f_o[s])          # ghost cells of the evaluated state, like the reference mutates them
+        lam = (C.c_double * 2)()
+        assert H.lk_vp_lambda_max(sys_, s, C.byref(lam)) == 0
+        assert (lam[0], lam[1]) == (ax[s], ay[s])
+    dt_o = ok.ok_vp_stable_dt(w, ax, ay, deck.rk)
+    dt_d = C.c_double()
+    assert H.lk_vp_stable_dt(sys_, C.byref(dt_d)) == 0
+    assert dt_d.value == dt_o
+    H.lk_vp_destroy(sys_)
+    ok.ok_vp_work_destroy(w)
+
+
+@pytest.mark.parametrize("mode", ["strict", "production"])
+@pytest.mark.parametrize("mk", DECKS)
+def test_one_step_matches_oracle(lk, ok, mk, mode):
+    """one full RK4 / RK6 step, fused on the device, against the unfused oracle.  Strict arithmetic:
+    the distribution is bit-identical.  Production arithmetic: checkTests.C:345-358 per-cell relative
+    difference <= 1e-12 (north-star tolerance for the distribution after one step)."""
+    deck = mk()
+    old = lk.lk_set_strict(1 if mode == "strict" else 0)
+    try:
+        w, sp, keep = _oracle(ok, deck)
+        states, tables = [], []
+        for k, s in enumerate(deck.species):
+            f, fx, fv, fnorm = deck.initial_state(s)
+            states.append(_perturb(f, 20 + k, amp=0.02))
+            tables.append((fx, fv, fnorm))
+        ns = len(states)
+        t0, dt = 0.25, 0.02
+        f_old = [s.copy() for s in states]
+        f_new = [np.zeros_like(s) for s in states]
+        ke = np.zeros(ns)
+        (ok.ok_vp_rk4_step if deck.rk == 4 else ok.ok_vp_rk6_step)(w, _ptrs(f_new), _ptrs(f_old), t0, dt, ke)
+        H, sys_ = _product(deck, states, tables)
+        assert H.lk_vp_set_time(sys_, t0) == 0
+        assert H.lk_vp_advance(sys_, dt) == 0, H.lk_last_error()
+        ng = deck.ng
+        I = (slice(ng, -ng),) * 4
+        for s in range(ns):
+            out = np.empty_like(states[s])
+            assert H.lk_vp_get_state(sys_, s, out.ctypes.data) == 0
+            assert np.any(out[I] != states[s][I])
+            if mode == "strict":
+                assert np.array_equal(out[I], f_new[s][I])
+            else:
+                assert cell_rel_err(out[I], f_new[s][I]) <= 1e-12
+            if deck.species[s].driver:
+                v = C.c_double()
+                assert H.lk_vp_ke_e_dot(sys_, s, C.byref(v)) == 0
+                assert abs(v.value - ke[s]) <= 1e-12 * abs(ke[s]) + 1e-300   # tree vs sequential sum
+                assert ke[s] != 0.0
+        assert abs(H.lk_vp_time(sys_) - (t0 + dt)) < 1e-15
+        H.lk_vp_destroy(sys_)
+        ok.ok_vp_work_destroy(w)
+    finally:
+        lk.lk_set_strict(old)
+
+
+def test_several_steps_production_vs_oracle(lk, ok, fast):
+    """a short run with dt from stableDt each step: distribution stays within 1e-12 per cell and the
+    field-energy trace within 1e-10 (north-star tolerance for time-history traces)"""
+    deck = decks.plane_epw(n=(12, 6), nv=(24, 12))
+    w, sp, keep = _oracle(ok, deck)
+    s0 = deck.species[0]
+    f, fx, fv, fnorm = deck.initial_state(s0)
+    state = _perturb(f, 5, amp=0.01)
+    H, sys_ = _product(deck, [state], [(fx, fv, fnorm)])
+    ng = deck.ng
+    n1d, n2d = deck.n[0] + 2 * ng, deck.n[1] + 2 * ng
+    f_old, f_new = state.copy(), np.zeros_like(state)
+    ke = np.zeros(1)
+    t = 0.0
+    # the reference seeds lambda_max with a throw-away evalRHS at init (VPSystem.C:227-230)
+    import torch
+    rhs_d = torch.zeros(state.shape, dtype=torch.float64, device="cuda")
+    assert H.lk_vp_eval_rhs(sys_, (C.c_void_p * 1)(rhs_d.data_ptr()), t) == 0
+    rhs0 = np.zeros_like(state)
+    ax, ay = np.zeros(1), np.zeros(1)
+    ok.ok_vp_eval_rhs(w, _ptrs([rhs0]), _ptrs([f_old]), t, np.zeros(1), ax, ay)
+    en_o, en_d = [], []
+    for step in range(4):
+        dt_o = deck.cfl * ok.ok_vp_stable_dt(w, ax, ay, deck.rk)
+        dt_d = C.c_double()
+        assert H.lk_vp_stable_dt(sys_, C.byref(dt_d)) == 0
+        assert abs(dt_d.value * deck.cfl - dt_o) <= 1e-13 * dt_o
+        ok.ok_vp_rk4_step(w, _ptrs([f_new]), _ptrs([f_old]), t, dt_o, ke)
+        assert H.lk_vp_set_time(sys_, t) == 0
+        assert H.lk_vp_advance(sys_, dt_o) == 0
+        t += dt_o
+        f_old, f_new = f_new, f_old
+        # accelerations for the next dt come from the last stage of this step; recompute on the oracle side
+        tmp = f_old.copy()
+        ok.ok_vp_eval_rhs(w, _ptrs([rhs0]), _ptrs([tmp]), t, np.zeros(1), ax, ay)
+        em_o = np.ctypeslib.as_array(ok.ok_vp_em_vars(w), shape=(2, n2d, n1d))
+        en_o.append(float(np.sum(em_o[:, ng:-ng, ng:-ng] ** 2)))
+        out = np.empty_like(state)
+        assert H.lk_vp_get_state(sys_, 0, out.ctypes.data) == 0
+        I = (slice(ng, -ng),) * 4
+        assert cell_rel_err(out[I], f_old[I]) <= 1e-12
+    H.lk_vp_destroy(sys_)
+    ok.ok_vp_work_destroy(w)
