@@ -100,7 +100,7 @@ const char* lk_last_error(void);
 int lk_set_strict(int strict);
 int lk_get_strict(void);
 int lk_device_count(void);
-/* 0 = tiled shared-memory kernel (default), 1 = one-thread-per-cell cross-check kernel */
+/* 0 = marching shared-memory kernel (default), 1 = one-thread-per-cell cross-check kernel */
 int lk_set_rhs_variant(int variant);
 
 /* ---- a1/a2: WENO43Fit4D / WENO65Fit4D (KineticSpeciesF.f:723-790, 914-979); test hook ----
@@ -144,6 +144,27 @@ int lk_acceleration_derivatives_4d(double* rhs, const double* f, const lk_geom* 
  * rhs_out may be NULL when upd != NULL.  f must have valid x/y ghosts and velocity-boundary ghosts. */
 int lk_vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const double* velocities,
                   const lk_accel* a, const lk_rk_update* upd, void* stream);
+
+/* Velocity moments of the stage's OUTPUT (the predictor = the next stage's input), accumulated by the
+ * fused kernel's epilogue so that chargeDensity / currentDensity / computekeedot of the next evalRHS
+ * (VPSystem.C:396, KineticSpecies.C:853-895, 1084-1093) cost no extra pass over f.
+ * partial: device scratch of nmom * lk_stage_moment_parts(g) * n[0] * n[1] doubles; nmom = 1: sum f;
+ * nmom = 3: sum f, sum vx f, sum vy f.  Sums are formed in a fixed order (deterministic), which is not the
+ * reference's sequential order: production arithmetic only (strict mode uses lk_reduce_4d_to_2d). */
+typedef struct lk_stage_moments {
+  int nmom;
+  double* partial;
+  int64_t capacity; /* doubles */
+} lk_stage_moments;
+int lk_stage_moment_parts(const lk_geom* g);
+int lk_vlasov_stage(double* rhs_out, const double* f, const lk_geom* g, const double* velocities,
+                    const lk_accel* a, const lk_rk_update* upd, const lk_stage_moments* mom, void* stream);
+/* dst_m(n1d,n2d) = (sum of partials of moment m) * dv * weight, ghosts zeroed (ReductionSchedule.C:86-89) */
+int lk_moments_finish(double* dst0, double* dst1, double* dst2, const lk_stage_moments* mom, const lk_geom* g,
+                      double dv, double weight, void* stream);
+/* computekeedot_ from the vx moment: out = charge*dx*dy*dvx*dvy * sum_xy ext(x,y,0) * M1(x,y) */
+int lk_ke_e_dot_from_moments(double* out_dev, const lk_stage_moments* mom, const lk_geom* g, double charge,
+                             const double* ext_efield, void* stream);
 
 /* ---- a12: ReductionSchedule 4D->2D (ReductionSchedule.C:69-113, 421-444): dst(n1d,n2d) ghosts zeroed,
  * dst = (sum_{i3,i4} f) * dv * weight ---- */

@@ -169,16 +169,16 @@ int lk_halo_unpack(double* f, const double* buf, const lk_geom* g, int dir, int 
 
 int lk_advection_derivatives_4d(double* rhs, const double* f, const lk_geom* g, const double* velocities, void* stream) {
   if (!geom_ok(g) || !rhs || !f || !velocities) return fail(LK_ERR_ARG, "lk_advection_derivatives_4d: bad argument");
-  CHECK_LAUNCH(DISPATCH(vlasov_rhs)(rhs, f, g, velocities, nullptr, nullptr, 1, g_variant, (cudaStream_t)stream),
+  CHECK_LAUNCH(DISPATCH(vlasov_rhs)(rhs, f, g, velocities, nullptr, nullptr, 1, g_variant, nullptr, 0, (cudaStream_t)stream),
                "lk_advection_derivatives_4d");
 }
 int lk_acceleration_derivatives_4d(double* rhs, const double* f, const lk_geom* g, const lk_accel* a, void* stream) {
   if (!geom_ok(g) || !rhs || !f || !accel_ok(a)) return fail(LK_ERR_ARG, "lk_acceleration_derivatives_4d: bad argument");
-  CHECK_LAUNCH(DISPATCH(vlasov_rhs)(rhs, f, g, nullptr, a, nullptr, 2 | 4, g_variant, (cudaStream_t)stream),
+  CHECK_LAUNCH(DISPATCH(vlasov_rhs)(rhs, f, g, nullptr, a, nullptr, 2 | 4, g_variant, nullptr, 0, (cudaStream_t)stream),
                "lk_acceleration_derivatives_4d");
 }
-int lk_vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const double* velocities, const lk_accel* a,
-                  const lk_rk_update* upd, void* stream) {
+static int stage_impl(double* rhs_out, const double* f, const lk_geom* g, const double* velocities, const lk_accel* a,
+                      const lk_rk_update* upd, const lk_stage_moments* mom, void* stream, const char* who) {
   if (!geom_ok(g) || !f || !velocities || !accel_ok(a)) return fail(LK_ERR_ARG, "lk_vlasov_rhs: bad argument");
   if (!rhs_out && !upd) return fail(LK_ERR_ARG, "lk_vlasov_rhs: nothing to write");
   if (upd) {
@@ -190,18 +190,55 @@ int lk_vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const doub
     if (upd->delta_out && upd->delta_out == f) return fail(LK_ERR_ARG, "lk_vlasov_rhs: delta must not alias the evaluated state");
   }
   if (rhs_out == f) return fail(LK_ERR_ARG, "lk_vlasov_rhs: rhs must not alias the evaluated state");
-  if (!g_prof) CHECK_LAUNCH(DISPATCH(vlasov_rhs)(rhs_out, f, g, velocities, a, upd, 3, g_variant, (cudaStream_t)stream), "lk_vlasov_rhs");
+  double* mpart = nullptr;
+  int nmom = 0;
+  if (mom) {
+    if (!upd || !mom->partial || (mom->nmom != 1 && mom->nmom != 3)) return fail(LK_ERR_ARG, "lk_vlasov_stage: bad moments request");
+    if (g_variant != 0) return fail(LK_ERR_UNSUPPORTED, "lk_vlasov_stage: moments need the marching kernel (variant 0)");
+    const int64_t need = (int64_t)mom->nmom * DISPATCH(stage_moment_parts)(g) * g->n[0] * g->n[1];
+    if (mom->capacity < need) return fail(LK_ERR_ARG, "lk_vlasov_stage: moment partial buffer too small");
+    mpart = mom->partial;
+    nmom = mom->nmom;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!g_prof) CHECK_LAUNCH(DISPATCH(vlasov_rhs)(rhs_out, f, g, velocities, a, upd, 3, g_variant, mpart, nmom, st), who);
   if (g_prof_used == g_prof_events.size()) {
     cudaEvent_t e0, e1;
     if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return cuda_fail(cudaGetLastError(), "lk_vlasov_rhs: event");
     g_prof_events.push_back({e0, e1});
   }
   auto& ev = g_prof_events[g_prof_used++];
-  cudaEventRecord(ev.first, (cudaStream_t)stream);
-  cudaError_t e = DISPATCH(vlasov_rhs)(rhs_out, f, g, velocities, a, upd, 3, g_variant, (cudaStream_t)stream);
-  cudaEventRecord(ev.second, (cudaStream_t)stream);
-  if (e != cudaSuccess) return cuda_fail(e, "lk_vlasov_rhs");
+  cudaEventRecord(ev.first, st);
+  cudaError_t e = DISPATCH(vlasov_rhs)(rhs_out, f, g, velocities, a, upd, 3, g_variant, mpart, nmom, st);
+  cudaEventRecord(ev.second, st);
+  if (e != cudaSuccess) return cuda_fail(e, who);
   return LK_OK;
+}
+int lk_vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const double* velocities, const lk_accel* a,
+                  const lk_rk_update* upd, void* stream) {
+  return stage_impl(rhs_out, f, g, velocities, a, upd, nullptr, stream, "lk_vlasov_rhs");
+}
+int lk_vlasov_stage(double* rhs_out, const double* f, const lk_geom* g, const double* velocities, const lk_accel* a,
+                    const lk_rk_update* upd, const lk_stage_moments* mom, void* stream) {
+  return stage_impl(rhs_out, f, g, velocities, a, upd, mom, stream, "lk_vlasov_stage");
+}
+int lk_stage_moment_parts(const lk_geom* g) {
+  if (!geom_ok(g)) return -1;
+  return DISPATCH(stage_moment_parts)(g);
+}
+int lk_moments_finish(double* d0, double* d1, double* d2, const lk_stage_moments* mom, const lk_geom* g, double dv,
+                      double weight, void* stream) {
+  if (!geom_ok(g) || !mom || !mom->partial || !d0 || (mom->nmom == 3 && (!d1 || !d2)) || (mom->nmom != 1 && mom->nmom != 3))
+    return fail(LK_ERR_ARG, "lk_moments_finish: bad argument");
+  CHECK_LAUNCH(DISPATCH(moments_finish)(d0, d1, d2, mom->partial, DISPATCH(stage_moment_parts)(g), mom->nmom, g, dv, weight,
+                                        (cudaStream_t)stream), "lk_moments_finish");
+}
+int lk_ke_e_dot_from_moments(double* out, const lk_stage_moments* mom, const lk_geom* g, double charge, const double* ext,
+                             void* stream) {
+  if (!geom_ok(g) || !mom || !mom->partial || mom->nmom != 3 || !out || !ext) return fail(LK_ERR_ARG, "lk_ke_e_dot_from_moments: bad argument");
+  const int nparts = DISPATCH(stage_moment_parts)(g);
+  const double* part1 = mom->partial + (size_t)nparts * g->n[0] * g->n[1];
+  CHECK_LAUNCH(DISPATCH(ke_from_moment)(out, part1, nparts, g, charge, ext, (cudaStream_t)stream), "lk_ke_e_dot_from_moments");
 }
 
 int lk_reduce_4d_to_2d(double* dst, const double* f, const lk_geom* g, double dv, double weight, void* stream) {

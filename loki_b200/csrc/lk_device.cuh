@@ -89,18 +89,55 @@ __device__ __forceinline__ double accel_y(const DAccel& a, const DGeo& g, int i1
 }
 
 // ---------------------------------------------------------------------------------------------
-// reciprocal for the production path: MUFU.RCP64H seed (rel. err 2^-23) + two Newton steps.
-// Inputs are sums of positive smoothness products, far from 0/inf/denormal.
+// reciprocal for the production path: MUFU.RCP64H seed (relative error e <= 2^-20) refined by one
+// cubic (Halley) step r0*(1 + e + e^2), error e^3 -- below the fp64 rounding unit.  Inputs are sums of
+// positive smoothness products, far from 0/inf/denormal.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double fast_rcp(double s) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
-  double e = FMA(-s, r, 1.0);
-  r = FMA(r, e, r);
-  e = FMA(-s, r, 1.0);
-  r = FMA(r, e, r);
-  return r;
+  const double e = FMA(-s, r, 1.0);
+  const double t = FMA(e, e, e);
+  return FMA(r, t, r);
 }
+
+// -x if flip else x, as one integer operation on the sign bit (keeps the select off the fp64 pipe)
+__device__ __forceinline__ double flip_sign(double x, bool flip) {
+  return __hiloint2double(__double2hiint(x) ^ (flip ? (int)0x80000000 : 0), __double2loint(x));
+}
+
+#if !LK_STRICT
+// ---------------------------------------------------------------------------------------------
+// Production form of WENO43Fit4D (KineticSpeciesF.f:723-790), algebraically equal to the reference
+// (DESIGN.md section 4).  With first differences d_j = u_{j+1}-u_j and second differences
+// c_j = d_j - d_{j-1} the reference's eps+bl and eps+br are
+//     el = d_j^2 + (13/12) c_j^2 + eps ,   er = d_j^2 + (13/12) c_{j+1}^2 + eps ,
+// the Henrick-mapped and renormalised weights are 1/2 +- rho^3/2 with
+//     rho = (er^2 - el^2) / (er^2 + el^2)
+// (the map g(w) = w(3/4 + w(w - 3/2)) obeys g(w)+g(1-w) = 1/4, so the second normalisation is an exact
+// factor 4), and the max/min upwind swap gives
+//     12*face = 7(u_j+u_{j+1}) - (u_{j-1}+u_{j+2}) -+ |rho|^3 (c_j - c_{j+1})     (- if vel > 0).
+// Every operation is an explicit round-to-nearest intrinsic: a face gets the same bits wherever it is
+// computed.  pc_j = (13/12) c_j^2 + eps is shared by the two faces of cell j.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double w43_pc(double c) { return FMA(MUL(13.0 / 12.0, c), c, 1.e-10); }
+// um,u0,up,un = u_{j-1..j+2}; d = u_{j+1}-u_j; (c,pc) of cell j; (cn,pcn) of cell j+1
+__device__ __forceinline__ double w43_face12(double um, double u0, double up, double un, double d, double c,
+                                             double pc, double cn, double pcn, bool pos) {
+  const double el = FMA(d, d, pc), er = FMA(d, d, pcn);
+  const double A = MUL(el, el), B = MUL(er, er);
+  const double rho = MUL(ADD(B, -A), fast_rcp(ADD(A, B)));
+  const double r3 = MUL(fabs(rho), MUL(rho, rho));
+  const double t = FMA(7.0, ADD(u0, up), -ADD(um, un));
+  const double dc = ADD(c, -cn);
+  return FMA(flip_sign(r3, pos), dc, t);
+}
+__device__ __forceinline__ double weno43_face12(double um2, double um1, double u0, double up1, bool pos) {
+  const double dm = ADD(um1, -um2), d = ADD(u0, -um1), dn = ADD(up1, -u0);
+  const double c = ADD(d, -dm), cn = ADD(dn, -d);
+  return w43_face12(um2, um1, u0, up1, d, c, w43_pc(c), cn, w43_pc(cn), pos);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // WENO43Fit4D (KineticSpeciesF.f:723-790).  `pos` is the reference's `vel.gt.0.0`.
@@ -132,30 +169,7 @@ __device__ __forceinline__ double weno43(double um2, double um1, double u0, doub
   if (pos) { wl = wmax; wr = wmin; } else { wl = wmin; wr = wmax; }
   return (wl * fl + wr * fr);
 #else
-  // Same function, algebraically rearranged to ONE reciprocal: with A=(eps+bl)^2, B=(eps+br)^2,
-  // S=A+B the unmapped weights are wl=B/S, wr=A/S; the Henrick-mapped, renormalised weights are
-  // nl/(nl+nr), nr/(nl+nr) with nl = B(0.75 S^2 + B(B-1.5S)), nr = A(0.75 S^2 + A(A-1.5S)).
-  // Every operation is an explicit round-to-nearest intrinsic so that the compiler cannot contract
-  // differently at different inlining sites: a cell gets the same bits wherever it sits in a tile.
-  const double eps = 1.e-10;
-  const double fl6 = FMA(5.0, um1, FMA(2.0, u0, -um2));
-  const double fr6 = FMA(5.0, u0, FMA(2.0, um1, -up1));
-  const double c1l = ADD(FMA(-2.0, um1, u0), um2);
-  const double c1r = ADD(FMA(-2.0, u0, up1), um1);
-  const double hl = MUL(0.5, ADD(u0, -um2));
-  const double hr = MUL(0.5, ADD(up1, -um1));
-  const double el = FMA(c1l, FMA(4.0 / 3.0, c1l, hl), FMA(hl, hl, eps));
-  const double er = FMA(c1r, FMA(4.0 / 3.0, c1r, -hr), FMA(hr, hr, eps));
-  const double A = MUL(el, el), B = MUL(er, er);
-  const double S = ADD(A, B);
-  const double q = MUL(0.75, MUL(S, S));
-  const double nl = MUL(B, FMA(B, FMA(-1.5, S, B), q));
-  const double nr = MUL(A, FMA(A, FMA(-1.5, S, A), q));
-  const double r = MUL(fast_rcp(ADD(nl, nr)), 1.0 / 6.0);
-  const double nmax = fmax(nl, nr), nmin = fmin(nl, nr);
-  const double wl = pos ? nmax : nmin;
-  const double wr = pos ? nmin : nmax;
-  return MUL(FMA(wl, fl6, MUL(wr, fr6)), r);
+  return MUL(weno43_face12(um2, um1, u0, up1, pos), 1.0 / 12.0);
 #endif
 }
 
@@ -201,8 +215,6 @@ __device__ __forceinline__ double weno65(double um3, double um2, double um1, dou
 #else
   const double eps = 1.e-10;
   const double k = 1.0 / 30240.0;
-  const double fl60 = FMA(2.0, um3, FMA(-13.0, um2, FMA(47.0, um1, FMA(27.0, u0, MUL(-3.0, up1)))));
-  const double fr60 = FMA(-3.0, um2, FMA(27.0, um1, FMA(47.0, u0, FMA(-13.0, up1, MUL(2.0, up2)))));
   // smoothness indicators as nested quadratic forms; constants pre-divided (compile-time folding)
   double t;
   t = FMA(5489.0 / 105.0, um1, FMA(-2242428.0 * k, u0, FMA(-1887108.0 * k, um2, FMA(410226.0 * k, um3, MUL(557646.0 * k, up1)))));
@@ -225,16 +237,13 @@ __device__ __forceinline__ double weno65(double um3, double um2, double um1, dou
   br = FMA(t, u0, br);
   br = FMA(MUL(33727.0 * k, up2), up2, br);
 
+  // mapped weights 1/2 +- rho^3/2 (see weno43_face12); 60*face = mean part +- |rho|^3 * difference part
   const double A = MUL(bl, bl), B = MUL(br, br);
-  const double S = ADD(A, B);
-  const double q = MUL(0.75, MUL(S, S));
-  const double nl = MUL(B, FMA(B, FMA(-1.5, S, B), q));
-  const double nr = MUL(A, FMA(A, FMA(-1.5, S, A), q));
-  const double r = MUL(fast_rcp(ADD(nl, nr)), 1.0 / 60.0);
-  const double nmax = fmax(nl, nr), nmin = fmin(nl, nr);
-  const double wl = pos ? nmax : nmin;
-  const double wr = pos ? nmin : nmax;
-  return MUL(FMA(wl, fl60, MUL(wr, fr60)), r);
+  const double rho = MUL(ADD(B, -A), fast_rcp(ADD(A, B)));
+  const double r3 = MUL(fabs(rho), MUL(rho, rho));
+  const double mean = FMA(37.0, ADD(um1, u0), FMA(-8.0, ADD(um2, up1), ADD(um3, up2)));
+  const double diff = FMA(10.0, ADD(um1, -u0), FMA(-5.0, ADD(um2, -up1), ADD(um3, -up2)));
+  return MUL(FMA(flip_sign(r3, !pos), diff, mean), 1.0 / 60.0);
 #endif
 }
 

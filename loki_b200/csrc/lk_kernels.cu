@@ -1,9 +1,9 @@
-// lk_kernels.cu -- sm_100a kernels of the Vlasov RHS path (everything except the tiled fused
-// stencil kernel, which lives in lk_stencil.cuh).  Compiled twice: production (lkfast) and strict
+// lk_kernels.cu -- sm_100a kernels of the Vlasov RHS path (everything except the fused marching
+// stage kernel, which lives in lk_march.cuh).  Compiled twice: production (lkfast) and strict
 // (lkstrict, -fmad=false); see lk_device.cuh.
 #include "lk_device.cuh"
 #include "lk_launch.h"
-#include "lk_stencil.cuh"
+#include "lk_march.cuh"
 
 namespace LK_NS {
 
@@ -438,44 +438,43 @@ k_rhs_naive(DGeo g, const double* __restrict__ f, const double* __restrict__ vel
   int i4 = (int)(r / g.n[2]) + ng;
   const i64 idx = gidx(g, i1, i2, i3, i4);
   const double* p = f + idx;
-  double rhs = 0.0;
+  constexpr int NG = (ORDER == 4) ? 2 : 3, W = 2 * NG;
+  const double FS = FaceScale<ORDER>::v;
+  // faces above (R) and below (L) the cell along stride s
+  auto faces = [&](i64 s, bool posR, bool posL, double& uR, double& uL) {
+    double w[W + 1];
+#pragma unroll
+    for (int k = 0; k <= W; ++k) w[k] = p[(k - NG) * s];
+    uL = fit_face<ORDER>(w, posL);
+    uR = fit_face<ORDER>(w + 1, posR);
+  };
+  double rhs = 0.0, uR, uL;
   if (flags & 4) rhs = rhs_out[idx];
   if (flags & 1) {
     const double vx = __ldg(vel + i3 + (i64)g.nd[2] * i4);
     const double vy = __ldg(vel + i3 + (i64)g.nd[2] * (i4 + (i64)g.nd[3]));
-    {
-      double uR = fit_right<ORDER>(p, 1, vx > 0.0);
-      double uL = fit_right<ORDER>(p - 1, 1, vx > 0.0);
-      rhs = sub_flux((flags & 4) ? rhs : 0.0, vx, uR, uL, g.dx[0], 1.0 / g.dx[0]);  // the x pass assigns (KineticSpeciesF.f:1999)
-    }
-    {
-      double uR = fit_right<ORDER>(p, g.s[1], vy > 0.0);
-      double uL = fit_right<ORDER>(p - g.s[1], g.s[1], vy > 0.0);
-      rhs = sub_flux(rhs, vy, uR, uL, g.dx[1], 1.0 / g.dx[1]);
-    }
+    faces(1, vx > 0.0, vx > 0.0, uR, uL);
+    rhs = sub_flux((flags & 4) ? rhs : 0.0, vx, uR, uL, g.dx[0], (1.0 / g.dx[0]) * FS);  // the x pass assigns (KineticSpeciesF.f:1999)
+    faces(g.s[1], vy > 0.0, vy > 0.0, uR, uL);
+    rhs = sub_flux(rhs, vy, uR, uL, g.dx[1], (1.0 / g.dx[1]) * FS);
   }
   if (flags & 2) {
-    {
-      const double ax = accel_x(a, g, i1, i2, i3, i4);
-      const double axl = (i3 > ng) ? accel_x(a, g, i1, i2, i3 - 1, i4) : ax;  // face reuse uLeft=uRight
-      double uR = fit_right<ORDER>(p, g.s[2], ax > 0.0);
-      double uL = fit_right<ORDER>(p - g.s[2], g.s[2], axl > 0.0);
-      rhs = sub_flux(rhs, ax, uR, uL, g.dx[2], 1.0 / g.dx[2]);
-    }
-    {
-      const double ay = accel_y(a, g, i1, i2, i3, i4);
-      const double ayl = (i4 > ng) ? accel_y(a, g, i1, i2, i3, i4 - 1) : ay;
-      double uR = fit_right<ORDER>(p, g.s[3], ay > 0.0);
-      double uL = fit_right<ORDER>(p - g.s[3], g.s[3], ayl > 0.0);
-      rhs = sub_flux(rhs, ay, uR, uL, g.dx[3], 1.0 / g.dx[3]);
-    }
+    const double ax = accel_x(a, g, i1, i2, i3, i4);
+    const double axl = (i3 > ng) ? accel_x(a, g, i1, i2, i3 - 1, i4) : ax;  // face reuse uLeft=uRight
+    faces(g.s[2], ax > 0.0, axl > 0.0, uR, uL);
+    rhs = sub_flux(rhs, ax, uR, uL, g.dx[2], (1.0 / g.dx[2]) * FS);
+    const double ay = accel_y(a, g, i1, i2, i3, i4);
+    const double ayl = (i4 > ng) ? accel_y(a, g, i1, i2, i3, i4 - 1) : ay;
+    faces(g.s[3], ay > 0.0, ayl > 0.0, uR, uL);
+    rhs = sub_flux(rhs, ay, uR, uL, g.dx[3], (1.0 / g.dx[3]) * FS);
   }
   if (rhs_out) rhs_out[idx] = rhs;
   if (upd.active) rk_update(upd, idx, rhs);
 }
 
 cudaError_t vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const double* velocities,
-                       const lk_accel* a, const lk_rk_update* upd, int flags, int variant, cudaStream_t st) {
+                       const lk_accel* a, const lk_rk_update* upd, int flags, int variant, double* mom_part,
+                       int nmom, cudaStream_t st) {
   DGeo d = make_geo(g);
   DAccel da;
   memset(&da, 0, sizeof(da));
@@ -484,17 +483,22 @@ cudaError_t vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const
   i64 total = (i64)g->n[0] * g->n[1] * g->n[2] * g->n[3];
   if (total <= 0) return cudaSuccess;
   if (variant == 0) {
-    cudaError_t e = launch_stencil_tiled(d, f, velocities, da, du, rhs_out, flags, st);
+    DMom dm;
+    dm.part = mom_part;
+    dm.nmom = (mom_part && upd) ? nmom : 0;
+    dm.nparts = march_moment_parts(d);
+    cudaError_t e = launch_stage_march(d, f, velocities, da, du, rhs_out, flags, dm, st);
     if (e == cudaSuccess) ++g_launches;
-    if (e != cudaErrorNotSupported) return e;
-    (void)cudaGetLastError();
+    return e;
   }
+  if (mom_part) return cudaErrorNotSupported;  // moments come from the marching kernel only
   if (g->order == 4)
     k_rhs_naive<4><<<nblk(total, 256), 256, 0, st>>>(d, f, velocities, da, du, rhs_out, flags);
   else
     k_rhs_naive<6><<<nblk(total, 256), 256, 0, st>>>(d, f, velocities, da, du, rhs_out, flags);
   return LK_LAUNCHED();
 }
+int stage_moment_parts(const lk_geom* g) { return march_moment_parts(make_geo(g)); }
 
 // ---------------------------------------------------------------------------------------------
 // a12/a13: velocity moments.  Grid (x-blocks, i2, chunk): each thread owns one (i1,i2) and sums its
@@ -573,6 +577,43 @@ cudaError_t current_density(double* Jx, double* Jy, double* Jz, const double* f,
   k_moment_partial<3><<<grid, 64, 0, st>>>(d, f, velocities, vz, scratch, chunks);
   ++g_launches;
   k_moment_finish<<<nblk((i64)d.nd[0] * d.nd[1], 128), 128, 0, st>>>(d, scratch, chunks, dv, w, Jx, Jy, Jz, 3);
+  return LK_LAUNCHED();
+}
+
+// finish of the moments produced by the marching kernel's epilogue: part[(m*nparts + p)*nxy + xy]
+cudaError_t moments_finish(double* d0, double* d1, double* d2, const double* part, int nparts, int nmom,
+                           const lk_geom* g, double dv, double w, cudaStream_t st) {
+  DGeo d = make_geo(g);
+  k_moment_finish<<<nblk((i64)d.nd[0] * d.nd[1], 128), 128, 0, st>>>(d, part, nparts, dv, w, d0, d1, d2, nmom);
+  return LK_LAUNCHED();
+}
+// ke_e_dot from the first vx-moment: charge*dx*dy*dvx*dvy * sum_xy ext(x,y) * (sum_p part1[p][xy]); one CTA,
+// fixed-order tree (KineticSpeciesF.f:2563-2602 sums cell by cell; tolerance in the tests)
+__global__ void k_ke_from_moment(DGeo g, const double* __restrict__ part1, int nparts, const double* __restrict__ ext,
+                                 double scale, double* out) {
+  __shared__ double sh[32];
+  const int nxy = g.n[0] * g.n[1];
+  double s = 0.0;
+  for (int t = threadIdx.x; t < nxy; t += blockDim.x) {
+    double m = 0.0;
+    for (int p = 0; p < nparts; ++p) m += part1[(i64)p * nxy + t];
+    const int i1 = t % g.n[0] + g.ng, i2 = t / g.n[0] + g.ng;
+    s += ext[i1 + (i64)g.nd[0] * i2] * m;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) b += sh[k];
+    out[0] = b * scale;
+  }
+}
+cudaError_t ke_from_moment(double* out, const double* part1, int nparts, const lk_geom* g, double charge,
+                           const double* ext, cudaStream_t st) {
+  DGeo d = make_geo(g);
+  const double scale = charge * g->dx[0] * g->dx[1] * g->dx[2] * g->dx[3];
+  k_ke_from_moment<<<1, 1024, 0, st>>>(d, part1, nparts, ext, scale, out);
   return LK_LAUNCHED();
 }
 

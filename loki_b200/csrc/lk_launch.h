@@ -24,7 +24,12 @@
   /* flags: bit0 advection terms, bit1 acceleration terms, bit2 accumulate into rhs_out */            \
   cudaError_t vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const double* velocities,\
                          const lk_accel* a, const lk_rk_update* upd, int flags, int variant,          \
-                         cudaStream_t st);                                                            \
+                         double* mom_part, int nmom, cudaStream_t st);                                \
+  int stage_moment_parts(const lk_geom* g);                                                           \
+  cudaError_t moments_finish(double* d0, double* d1, double* d2, const double* part, int nparts,      \
+                             int nmom, const lk_geom* g, double dv, double w, cudaStream_t st);       \
+  cudaError_t ke_from_moment(double* out, const double* part1, int nparts, const lk_geom* g,          \
+                             double charge, const double* ext, cudaStream_t st);                      \
   cudaError_t reduce_4d_to_2d(double* dst, const double* f, const lk_geom* g, double dv, double w,    \
                               double* scratch, int chunks, cudaStream_t st);                          \
   cudaError_t current_density(double* Jx, double* Jy, double* Jz, const double* f, const lk_geom* g,  \

@@ -1,0 +1,633 @@
+// lk_march.cuh -- the fused Vlasov stage kernel (SURVEY 8a rows a3 + a4/a5 + a8 + a9 + a10/a11 + a12/a13).
+//
+// One CTA owns a 3D tile (T0 x T1 x T2 cells in x, y, vx) and MARCHES along vy.  Per vy plane it
+//   1. sweeps the plane's lines in x, y and vx out of shared memory with a sliding register window
+//      (one shared-memory read and one WENO fit per face; the left face of a cell is the right face of
+//      its predecessor exactly as in the reference's `uLeft = uRight` loops, KineticSpeciesF.f:
+//      1990-2005, 2137-2152), accumulating ((x + y) + vx) in the reference's order;
+//   2. fits the vy face above the plane from the ring of planes it already holds (the face below is
+//      kept in a register from the previous step), so f is read ONCE along vy: no vy halo, no
+//      redundant vy fits;
+//   3. applies the Runge-Kutta stage update (RK4Integrator.H:149-171, RK6Integrator.H:105-130)
+//      straight to global memory and adds the new predictor to per-thread velocity moments (charge
+//      density / currents of the NEXT stage input, ReductionSchedule.C:421-444).
+// Planes travel HBM -> shared memory by TMA (cp.async.bulk.tensor.4d, out-of-box elements zero filled
+// by the hardware) into a ring of 2*ng-1 slots, one plane ahead of the compute; only the plane being
+// swept needs its y / vx star halos, which are single-buffered and re-armed as soon as their sweep is
+// done.  rhs never touches HBM.
+//
+// The kernel is bounded by the fp64 pipe: ~120 fp64 instructions per order-4
+// cell-update after the algebraic restatement of the fit (lk_device.cuh).
+#pragma once
+#include <cuda.h>
+
+#include "lk_device.cuh"
+
+namespace LK_NS {
+
+template <int ORDER, int T0, int T1, int T2>
+struct MarchCfg {
+  static constexpr int NG = (ORDER == 4) ? 2 : 3;
+  static constexpr int W = 2 * NG;          // stencil width of one fit
+  static constexpr int NS = W - 1;          // ring slots (the oldest plane of a vy fit lives in registers)
+  static constexpr int SX = 8;              // x-line segment walked by one thread
+  static constexpr int PC = T0 + 2 * NG;    // row pitch of every staged box (TMA writes boxes densely)
+  static constexpr int PA = T0 + 1;         // accumulator pitch (odd: conflict-free column access)
+  static constexpr int NCORE = PC * T1 * T2;
+  static constexpr int NYH = PC * NG * T2;  // one side
+  static constexpr int NVH = PC * T1 * NG;  // one side
+  static constexpr int NACC = PA * T1 * T2;
+  static constexpr int SMEM_DOUBLES = NS * NCORE + 2 * NYH + 2 * NVH + NACC;
+  static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES + 8 * (NS + 2);
+};
+
+struct MarchMaps {
+  CUtensorMap core, yh, vh;
+};
+// velocity moments of the predictor written by the epilogue: part[(m * nparts + p) * n0 * n1 + x + n0 * y],
+// p = chunk * nt2 + (vx tile); m = 0: sum f, 1: sum vx f, 2: sum vy f
+struct DMom {
+  double* part;
+  int nmom, nparts;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, void* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect(void* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+
+// ---- faces along a line: init with the first W-1 values, then one value in, one face out ----
+// Faces carry the factor 1/FaceScale (production order 4 keeps 12*face and folds 1/12 into the flux
+// coefficient).
+template <int V>
+struct IntTag {
+  static constexpr int value = V;
+};
+template <int ORDER>
+struct FaceScale {
+#if LK_STRICT
+  static constexpr double v = 1.0;
+#else
+  static constexpr double v = (ORDER == 4) ? (1.0 / 12.0) : 1.0;
+#endif
+};
+template <int ORDER>
+struct Walker {
+  static constexpr int W = (ORDER == 4) ? 4 : 6;
+  double w[W - 1];
+  template <class LD>
+  __device__ __forceinline__ void init(LD ld) {
+#pragma unroll
+    for (int k = 0; k < W - 1; ++k) w[k] = ld(k);
+  }
+  __device__ __forceinline__ double next(double un, bool pos) {
+    double F;
+    if constexpr (ORDER == 4) F = weno43(w[0], w[1], w[2], un, pos);
+    else F = weno65(w[0], w[1], w[2], w[3], w[4], un, pos);
+#pragma unroll
+    for (int k = 0; k < W - 2; ++k) w[k] = w[k + 1];
+    w[W - 2] = un;
+    return F;
+  }
+};
+#if !LK_STRICT
+template <>
+struct Walker<4> {
+  double um, u0, up, d, c, pc;  // u_{j-1}, u_j, u_{j+1}, d_j, c_j, pc_j
+  template <class LD>
+  __device__ __forceinline__ void init(LD ld) {
+    um = ld(0); u0 = ld(1); up = ld(2);
+    const double dm = ADD(u0, -um);
+    d = ADD(up, -u0);
+    c = ADD(d, -dm);
+    pc = w43_pc(c);
+  }
+  __device__ __forceinline__ double next(double un, bool pos) {
+    const double dn = ADD(un, -up), cn = ADD(dn, -d), pcn = w43_pc(cn);
+    const double F = w43_face12(um, u0, up, un, d, c, pc, cn, pcn, pos);
+    um = u0; u0 = up; up = un; d = dn; c = cn; pc = pcn;
+    return F;
+  }
+};
+#endif
+// the same face from its W values at once (vy direction, one-thread-per-cell kernel); identical bits
+template <int ORDER>
+__device__ __forceinline__ double fit_face(const double* w, bool pos) {
+#if !LK_STRICT
+  if constexpr (ORDER == 4) return weno43_face12(w[0], w[1], w[2], w[3], pos);
+#endif
+  if constexpr (ORDER == 4) return weno43(w[0], w[1], w[2], w[3], pos);
+  else return weno65(w[0], w[1], w[2], w[3], w[4], w[5], pos);
+}
+
+// LEAN: the production instantiation -- advection + acceleration, no accumulate, acceleration constant
+// along its own sweep line (Vlasov-Poisson without a constant B field: vel3 is independent of i3 and
+// vel4 of i4, KineticSpeciesF.f:78-80, 98-100), no earlier RK6 stage results to add; everything else is
+// decided at run time.
+template <int ORDER, int T0, int T1, int T2, int NT, bool TMA, bool LEAN>
+__global__ void __launch_bounds__(NT, 2)
+k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restrict__ vel, const DAccel a,
+              const DUpd upd, double* __restrict__ rhs_out, const int flags, const int nt0, const int nt1,
+              const int nt2, const int chunk_len, const DMom mom, const __grid_constant__ MarchMaps maps) {
+  using C = MarchCfg<ORDER, T0, T1, T2>;
+  constexpr int NG = C::NG, W = C::W, NS = C::NS, SX = C::SX, PC = C::PC, PA = C::PA;
+  static_assert(T0 * T1 == NT, "the vy/epilogue phase maps one thread to one (x,y) column of the tile");
+  static_assert(T0 % SX == 0 && (T0 % 2) == 0, "x segments");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* smem = reinterpret_cast<double*>(smem_raw);
+  double* sCore = smem;                       // NS slots
+  double* sYh = sCore + NS * C::NCORE;        // [side][c][h][PC]
+  double* sVh = sYh + 2 * C::NYH;             // [side][h][b1][PC]
+  double* sAcc = sVh + 2 * C::NVH;            // [c][b1][PA]
+  unsigned long long* bars = (unsigned long long*)(sAcc + C::NACC);  // NS core barriers, y, v
+
+  const int tid = threadIdx.x;
+  int b = blockIdx.x;
+  const int o0 = (b % nt0) * T0; b /= nt0;
+  const int o2 = (b % nt2) * T2; b /= nt2;
+  const int o1 = (b % nt1) * T1; b /= nt1;
+  const int chunk = b;
+  const int ng = g.ng;  // == NG
+  const int q0 = chunk * chunk_len;                       // first interior vy plane of this CTA
+  const int nq = min(chunk_len, g.n[3] - q0);
+  if (nq <= 0) return;
+  const int X0 = o0, Y0 = o1 + ng, V0 = o2 + ng;          // data-box coordinates of the staged boxes' origin (x grown by NG)
+  const int pbase = q0 + ng - NG + 1;                     // data index of the plane in ring slot 0 at start
+
+  const bool do_adv = LEAN || (flags & 1) != 0, do_acc = LEAN || (flags & 2) != 0, accumulate = !LEAN && (flags & 4) != 0;
+  const double FS = FaceScale<ORDER>::v;
+  const double rdx0 = (1.0 / g.dx[0]) * FS, rdx1 = (1.0 / g.dx[1]) * FS, rdx2 = (1.0 / g.dx[2]) * FS,
+               rdx3 = (1.0 / g.dx[3]) * FS;
+
+  // ---- staging helpers -------------------------------------------------------------------------
+  auto coop_box = [&](double* dst, int x0, int y0, int v0, int p, int by, int bv) {  // fallback: plain loads
+    for (int e = tid; e < PC * by * bv; e += NT) {
+      const int k = e % PC, r = e / PC, j = r % by, m = r / by;
+      const int x = x0 + k, y = y0 + j, v = v0 + m;
+      const bool in = x >= 0 && x < g.nd[0] && y >= 0 && y < g.nd[1] && v >= 0 && v < g.nd[2] && p >= 0 && p < g.nd[3];
+      dst[e] = in ? f[gidx(g, x, y, v, p)] : 0.0;
+    }
+  };
+  auto stage_core = [&](int p, int slot) {
+    double* dst = sCore + slot * C::NCORE;
+    if (TMA) {
+      if (tid == 0) {
+        mbar_expect(&bars[slot], (unsigned)(C::NCORE * sizeof(double)));
+        tma_load_4d(dst, &maps.core, &bars[slot], X0, Y0, V0, p);
+      }
+    } else {
+      coop_box(dst, X0, Y0, V0, p, T1, T2);
+    }
+  };
+  auto stage_yh = [&](int p) {
+    if (TMA) {
+      if (tid == 0) {
+        mbar_expect(&bars[NS], (unsigned)(2 * C::NYH * sizeof(double)));
+        tma_load_4d(sYh, &maps.yh, &bars[NS], X0, Y0 - NG, V0, p);
+        tma_load_4d(sYh + C::NYH, &maps.yh, &bars[NS], X0, Y0 + T1, V0, p);
+      }
+    } else {
+      coop_box(sYh, X0, Y0 - NG, V0, p, NG, T2);
+      coop_box(sYh + C::NYH, X0, Y0 + T1, V0, p, NG, T2);
+    }
+  };
+  auto stage_vh = [&](int p) {
+    if (TMA) {
+      if (tid == 0) {
+        mbar_expect(&bars[NS + 1], (unsigned)(2 * C::NVH * sizeof(double)));
+        tma_load_4d(sVh, &maps.vh, &bars[NS + 1], X0, Y0, V0 - NG, p);
+        tma_load_4d(sVh + C::NVH, &maps.vh, &bars[NS + 1], X0, Y0, V0 + T2, p);
+      }
+    } else {
+      coop_box(sVh, X0, Y0, V0 - NG, p, T1, NG);
+      coop_box(sVh + C::NVH, X0, Y0, V0 + T2, p, T1, NG);
+    }
+  };
+  unsigned ph_core = 0, ph_y = 0, ph_v = 0;  // phase parities (bit per core slot)
+  auto wait_core = [&](int slot) {
+    if (TMA) {
+      mbar_wait(&bars[slot], (ph_core >> slot) & 1u);
+      ph_core ^= 1u << slot;
+    }
+  };
+
+  if (TMA) {
+    if (tid == 0) {
+      for (int k = 0; k < NS + 2; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[k])));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+
+  // ---- this thread's (x,y) column for the vx sweep, the vy fit and the epilogue --------------------
+  const int ea0 = tid % T0, eb1 = tid / T0;
+  const bool col_ok = (o0 + ea0 < g.n[0]) && (o1 + eb1 < g.n[1]);
+  const int ei1 = min(o0 + ea0, g.n[0] - 1) + ng, ei2 = min(o1 + eb1, g.n[1] - 1) + ng;
+  const i64 col = (i64)(o0 + ea0 + ng) + g.s[1] * (o1 + eb1 + ng) + g.s[2] * (o2 + ng);  // + s2*c + s3*p
+  const int ecell = eb1 * PC + NG + ea0;                                                  // + c*T1*PC within a slot
+  const int ncv = col_ok ? min(T2, g.n[2] - o2) : 0;  // valid cells of this thread's column
+  const bool simple_acc = LEAN || ((a.kind == 0) && (a.bz == 0.0));
+  const i64 pxy = ei1 + (i64)g.nd[0] * ei2;
+
+  // ---- prologue: fill the ring, fit the face below the first plane ------------------------------
+  for (int k = 0; k < NS; ++k) stage_core(pbase + k, k);
+  stage_yh(q0 + ng);
+  stage_vh(q0 + ng);
+  double uold[T2], Fprev[T2];
+#pragma unroll
+  for (int c = 0; c < T2; ++c) {
+    const bool ok = col_ok && (o2 + c < g.n[2]);
+    uold[c] = ok ? f[col + g.s[2] * c + g.s[3] * (pbase - 1)] : 0.0;
+  }
+  if (!TMA) __syncthreads();
+  for (int k = 0; k < NS; ++k) wait_core(k);
+  if (do_acc) {
+    const int i4b = (q0 > 0) ? (q0 + ng - 1) : (q0 + ng);  // the cell whose coefficient fitted this face (KineticSpeciesF.f:2137-2141)
+#pragma unroll
+    for (int c = 0; c < T2; ++c) {
+      double w[W];
+      w[0] = uold[c];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) w[k + 1] = sCore[k * C::NCORE + ecell + c * T1 * PC];
+      const int i3 = min(o2 + c, g.n[2] - 1) + ng;
+      const double ayb = simple_acc ? __ldg(a.field + pxy + (i64)g.nd[0] * g.nd[1]) : accel_y(a, g, ei1, ei2, i3, i4b);
+      Fprev[c] = fit_face<ORDER>(w, ayb > 0.0);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < T2; ++c) uold[c] = sCore[ecell + c * T1 * PC];  // plane pbase
+  __syncthreads();
+  stage_core(pbase + NS, 0);
+
+  double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+  int ekind = 0;
+  if (upd.active && !rhs_out && upd.n_prev == 0 && do_adv && do_acc && !accumulate) {
+    if (!upd.delta_in && upd.delta_out && !upd.use_delta) ekind = 1;
+    else if (upd.delta_in && upd.delta_out && !upd.use_delta) ekind = 2;
+    else if (upd.delta_in && !upd.delta_out && upd.use_delta) ekind = 3;
+  }
+
+  // ---- march -------------------------------------------------------------------------------------
+  for (int q = q0; q < q0 + nq; ++q) {
+    const int p = q + ng;                       // data index of the plane being updated
+    const int sc = (p - pbase) % NS;            // its ring slot
+    const double* cur = sCore + sc * C::NCORE;
+    const bool more = (q + 1 < q0 + nq);
+
+    // pull the next plane's RK operands towards L2 (one 128-byte line per thread)
+    if (upd.active && more) {
+      constexpr int LPR = (T0 * 8 + 127) / 128;  // lines per row
+      for (int e = tid; e < T1 * T2 * LPR; e += NT) {
+        const int ln = e % LPR, row = e / LPR, b1 = row % T1, c = row / T1;
+        if ((o1 + b1 < g.n[1]) && (o2 + c < g.n[2]) && (o0 + ln * 16 < g.n[0])) {
+          const i64 o = (i64)(o0 + ng + ln * 16) + g.s[1] * (o1 + b1 + ng) + g.s[2] * (o2 + c + ng) + g.s[3] * (p + 1);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(upd.f_old + o));
+          if (upd.delta_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(upd.delta_in + o));
+        }
+      }
+    }
+
+    // ---------------- x sweep: rows (b1, c) in segments of SX cells ----------------
+    for (int l = tid; l < T1 * T2 * (T0 / SX); l += NT) {
+      const int row = l % (T1 * T2), seg = l / (T1 * T2);
+      const int b1 = row % T1, c = row / T1;
+      double* arow = sAcc + row * PA + seg * SX;
+      double init[SX];
+#pragma unroll
+      for (int k = 0; k < SX; ++k) init[k] = 0.0;
+      if (accumulate) {
+#pragma unroll
+        for (int k = 0; k < SX; ++k) {
+          const bool ok = (o0 + seg * SX + k < g.n[0]) && (o1 + b1 < g.n[1]) && (o2 + c < g.n[2]);
+          if (ok) init[k] = rhs_out[(i64)(o0 + seg * SX + k + ng) + g.s[1] * (o1 + b1 + ng) + g.s[2] * (o2 + c + ng) + g.s[3] * p];
+        }
+      }
+      if (do_adv) {
+        const int i3 = min(o2 + c, g.n[2] - 1) + ng;
+        const double vx = __ldg(vel + i3 + (i64)g.nd[2] * p);
+        const bool pos = vx > 0.0;
+        const double2* r2 = reinterpret_cast<const double2*>(cur + row * PC + seg * SX);
+        double v[SX + W];
+#pragma unroll
+        for (int k = 0; k < (SX + W) / 2; ++k) {
+          const double2 t = r2[k];
+          v[2 * k] = t.x;
+          v[2 * k + 1] = t.y;
+        }
+        Walker<ORDER> wk;
+        wk.init([&](int k) { return v[k]; });
+        double uL = wk.next(v[W - 1], pos);
+#pragma unroll
+        for (int k = 0; k < SX; ++k) {
+          const double uR = wk.next(v[k + W], pos);
+          arow[k] = sub_flux(init[k], vx, uR, uL, g.dx[0], rdx0);
+          uL = uR;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < SX; ++k) arow[k] = init[k];
+      }
+    }
+    __syncthreads();
+
+    // ---------------- y sweep: lines (a0, c) ----------------
+    if (TMA) { mbar_wait(&bars[NS], ph_y); ph_y ^= 1u; }
+    if (do_adv) {
+      for (int l = tid; l < T0 * T2; l += NT) {
+        const int a0 = l % T0, c = l / T0;
+        const int i3 = min(o2 + c, g.n[2] - 1) + ng;
+        const double vy = __ldg(vel + i3 + (i64)g.nd[2] * (p + (i64)g.nd[3]));
+        const bool pos = vy > 0.0;
+        const double* core = cur + c * T1 * PC + NG + a0;        // + b1*PC
+        const double* hlo = sYh + c * NG * PC + NG + a0;         // + h*PC
+        const double* hhi = hlo + C::NYH;
+        double* racc = sAcc + c * T1 * PA + a0;                  // + b1*PA
+        auto ld = [&](int k) -> double {  // line position k in [0, T1+W)
+          if (k < NG) return hlo[k * PC];
+          if (k < NG + T1) return core[(k - NG) * PC];
+          return hhi[(k - NG - T1) * PC];
+        };
+        Walker<ORDER> wk;
+        wk.init(ld);
+        double uL = wk.next(ld(W - 1), pos);
+#pragma unroll
+        for (int b1 = 0; b1 < T1; ++b1) {
+          const double uR = wk.next(ld(b1 + W), pos);
+          racc[b1 * PA] = sub_flux(racc[b1 * PA], vy, uR, uL, g.dx[1], rdx1);
+          uL = uR;
+        }
+      }
+    }
+    __syncthreads();
+    if (more) stage_yh(p + 1);
+
+    // ---------------- vx sweep: this thread's column (ea0, eb1), all c ----------------
+    if (TMA) { mbar_wait(&bars[NS + 1], ph_v); ph_v ^= 1u; }
+    double* const racc = sAcc + eb1 * PA + ea0;  // + c*T1*PA: this thread's column of the accumulator
+    {
+      if (do_acc) {
+        const double* core = cur + ecell;                          // + c*T1*PC
+        const double* hlo = sVh + eb1 * PC + NG + ea0;             // + h*T1*PC
+        const double* hhi = hlo + C::NVH;
+        auto ld = [&](int k) -> double {
+          if (k < NG) return hlo[k * T1 * PC];
+          if (k < NG + T2) return core[(k - NG) * T1 * PC];
+          return hhi[(k - NG - T2) * T1 * PC];
+        };
+        const double ax0 = simple_acc ? __ldg(a.field + pxy) : 0.0;
+        auto AX = [&](int i3) -> double { return simple_acc ? ax0 : accel_x(a, g, ei1, ei2, i3, p); };
+        const int i3first = o2 + ng;
+        // the face below the first cell was fitted by the cell below it with ITS coefficient, unless
+        // that cell is outside the interior (KineticSpeciesF.f:2137-2141)
+        const double axl = AX((o2 > 0) ? (i3first - 1) : i3first);
+        Walker<ORDER> wk;
+        wk.init(ld);
+        double uL = wk.next(ld(W - 1), axl > 0.0);
+#pragma unroll
+        for (int c = 0; c < T2; ++c) {
+          const double ax = AX(min(i3first + c, g.n[2] - 1 + ng));
+          const double uR = wk.next(ld(c + W), ax > 0.0);
+          racc[c * T1 * PA] = sub_flux(racc[c * T1 * PA], ax, uR, uL, g.dx[2], rdx2);
+          uL = uR;
+        }
+      }
+    }
+
+    // ---------------- vy face above this plane + epilogue ----------------
+    const int s_new = (p + NG - pbase) % NS;
+    wait_core(s_new);  // always: no TMA write may be outstanding when the CTA exits
+    // EK: epilogue kind, decided once per kernel (uniform) so that the per-cell code carries no pointer
+    // tests.  1..3 = the RK4 stage shapes (RK4Integrator.H:149-171): 1: delta = w*rhs (stage 1);
+    // 2: delta += w*rhs (stages 2,3); 3: pred = f_old + c*(delta + w*rhs), delta not stored (stage 4);
+    // 0: everything decided per cell (RK6, rhs_out, partial evaluations).
+    auto vy_phase = [&](auto ek_tag) {
+      constexpr int EK = decltype(ek_tag)::value;
+      // ring slots of the planes p-NG+2 .. p+NG (w[1..W-1] of the vy fit), this thread's cell
+      const double* wp[W];
+#pragma unroll
+      for (int k = 1; k < W; ++k) wp[k] = sCore + ((sc + k - (NG - 1) + NS) % NS) * C::NCORE + ecell;
+      const double ay0 = (do_acc && simple_acc) ? __ldg(a.field + pxy + (i64)g.nd[0] * g.nd[1]) : 0.0;
+      const i64 idx0 = col + g.s[3] * p;
+      const int s2 = (int)g.s[2];
+      const double* velp = vel + o2 + ng + (i64)g.nd[2] * p;
+      const double* fo_p = upd.f_old + idx0;
+      const double* di_p = upd.delta_in + idx0;
+      double* do_p = upd.delta_out + idx0;
+      double* pr_p = upd.pred + idx0;
+      double psum = 0.0, pvx = 0.0, pvy = 0.0;
+      // the RK operands of the whole column first: their latency hides behind the eight fits
+      double fo[T2], di[T2];
+      if constexpr (EK != 0) {
+#pragma unroll
+        for (int c = 0; c < T2; ++c) {
+          fo[c] = (c < ncv) ? fo_p[c * s2] : 0.0;
+          di[c] = (EK >= 2 && c < ncv) ? di_p[c * s2] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < T2; ++c) {
+        double res = racc[c * T1 * PA];
+        if (do_acc) {
+          double w[W];
+          w[0] = uold[c];
+#pragma unroll
+          for (int k = 1; k < W; ++k) w[k] = wp[k][c * T1 * PC];
+          const double ay = simple_acc ? ay0 : accel_y(a, g, ei1, ei2, min(o2 + c, g.n[2] - 1) + ng, p);
+          const double F = fit_face<ORDER>(w, ay > 0.0);
+          res = sub_flux(res, ay, F, Fprev[c], g.dx[3], rdx3);
+          Fprev[c] = F;
+          uold[c] = w[1];
+        }
+        if (c < ncv) {
+          const int oc = c * s2;
+          double pr;
+          if constexpr (EK == 1) {
+            do_p[oc] = rk_delta(upd, res, 0.0, false);
+            pr = rk_axpy(fo[c], upd.c_pred, res);
+          } else if constexpr (EK == 2) {
+            do_p[oc] = rk_delta(upd, res, di[c], true);
+            pr = rk_axpy(fo[c], upd.c_pred, res);
+          } else if constexpr (EK == 3) {
+            pr = rk_axpy(fo[c], upd.c_pred, rk_delta(upd, res, di[c], true));
+          } else {
+            const i64 idx = idx0 + oc;
+            if (rhs_out) rhs_out[idx] = res;
+            if (!upd.active) continue;
+            const double dl = rk_delta(upd, res, upd.delta_in ? upd.delta_in[idx] : 0.0, upd.delta_in != nullptr);
+            if (upd.delta_out) upd.delta_out[idx] = dl;
+            pr = rk_pred(upd, upd.f_old[idx], upd.use_delta ? dl : res, idx);
+          }
+          pr_p[oc] = pr;
+          if (mom.nmom > 0) {
+            psum = ADD(psum, pr);
+            if (mom.nmom > 1) {
+              pvx = FMA(__ldg(velp + c), pr, pvx);
+              pvy = FMA(__ldg(velp + c + (i64)g.nd[2] * g.nd[3]), pr, pvy);
+            }
+          }
+        }
+      }
+      if (mom.nmom > 0) {
+        m0 = ADD(m0, psum);
+        if (mom.nmom > 1) {
+          m1 = ADD(m1, pvx);
+          m2 = ADD(m2, pvy);
+        }
+      }
+    };
+    if (ekind == 1) vy_phase(IntTag<1>{});
+    else if (ekind == 2) vy_phase(IntTag<2>{});
+    else if (ekind == 3) vy_phase(IntTag<3>{});
+    else vy_phase(IntTag<0>{});
+    __syncthreads();
+    if (more) {
+      stage_vh(p + 1);
+      stage_core(p + NG + 1, (p + NG + 1 - pbase) % NS);
+    }
+  }
+
+  if (mom.nmom > 0 && col_ok) {
+    const i64 nxy = (i64)g.n[0] * g.n[1];
+    const i64 part = (i64)chunk * nt2 + (o2 / T2);
+    const i64 o = (o0 + ea0) + (i64)g.n[0] * (o1 + eb1);
+    mom.part[part * nxy + o] = m0;
+    if (mom.nmom > 1) {
+      mom.part[((i64)mom.nparts + part) * nxy + o] = m1;
+      mom.part[((i64)2 * mom.nparts + part) * nxy + o] = m2;
+    }
+  }
+}
+
+// ---- tensor maps: built on the host through the driver entry point, cached per (pointer, geometry) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+static bool encode_map(CUtensorMap* m, const DGeo& g, const double* f, int b0, int b1, int b2, int b3) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)g.nd[0], (cuuint64_t)g.nd[1], (cuuint64_t)g.nd[2], (cuuint64_t)g.nd[3]};
+  cuuint64_t strides[3] = {(cuuint64_t)g.s[1] * 8, (cuuint64_t)g.s[2] * 8, (cuuint64_t)g.s[3] * 8};
+  cuuint32_t box[4] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2, (cuuint32_t)b3};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)f, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+struct MapKey {
+  const double* f;
+  int nd[4];
+  int t[3];
+  int ng;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+template <int ORDER, int T0, int T1, int T2>
+static bool get_maps(const DGeo& g, const double* f, MarchMaps* out) {
+  using C = MarchCfg<ORDER, T0, T1, T2>;
+  // TMA needs a 16-byte aligned base and pitches
+  if (((uintptr_t)f & 15) || (g.nd[0] & 1)) return false;
+  static MapKey keys[32];
+  static MarchMaps vals[32];
+  static int count = 0, next = 0;
+  MapKey k;
+  memset(&k, 0, sizeof(k));
+  k.f = f;
+  for (int d = 0; d < 4; ++d) k.nd[d] = g.nd[d];
+  k.t[0] = T0; k.t[1] = T1; k.t[2] = T2;
+  k.ng = C::NG;
+  for (int i = 0; i < count; ++i)
+    if (keys[i] == k) { *out = vals[i]; return true; }
+  MarchMaps m;
+  if (!encode_map(&m.core, g, f, C::PC, T1, T2, 1)) return false;
+  if (!encode_map(&m.yh, g, f, C::PC, C::NG, T2, 1)) return false;
+  if (!encode_map(&m.vh, g, f, C::PC, T1, C::NG, 1)) return false;
+  const int slot = (count < 32) ? count++ : (next++ % 32);
+  keys[slot] = k;
+  vals[slot] = m;
+  *out = m;
+  return true;
+}
+
+// number of moment partials per (x,y) the march kernel writes for this geometry, and its decomposition
+template <int T2>
+static void march_plan(const DGeo& g, int tiles_xyv, int* nchunk, int* chunk_len) {
+  // enough CTAs for a few waves over 148 SMs x 2 resident CTAs; chunks no shorter than 8 planes
+  int nc = 1;
+  const int want = 148 * 2 * 2;
+  if (tiles_xyv < want) nc = (want + tiles_xyv - 1) / tiles_xyv;
+  int len = (g.n[3] + nc - 1) / nc;
+  if (len < 8) len = (g.n[3] < 8) ? g.n[3] : 8;
+  nc = (g.n[3] + len - 1) / len;
+  *nchunk = nc;
+  *chunk_len = len;
+}
+
+template <int ORDER, int T0, int T1, int T2, int NT>
+static cudaError_t launch_march_cfg(const DGeo& g, const double* f, const double* vel, const DAccel& a, const DUpd& u,
+                                    double* rhs_out, int flags, const DMom& mom, cudaStream_t st) {
+  using C = MarchCfg<ORDER, T0, T1, T2>;
+  const int nt0 = (g.n[0] + T0 - 1) / T0, nt1 = (g.n[1] + T1 - 1) / T1, nt2 = (g.n[2] + T2 - 1) / T2;
+  int nchunk, chunk_len;
+  march_plan<T2>(g, nt0 * nt1 * nt2, &nchunk, &chunk_len);
+  const long long ctas = (long long)nt0 * nt1 * nt2 * nchunk;
+  if (ctas > 0x7fffffffLL) return cudaErrorNotSupported;
+  MarchMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  static int use_tma_env = -1;
+  if (use_tma_env < 0) {
+    const char* e = getenv("LK_NO_TMA");
+    use_tma_env = (e && e[0] == '1') ? 0 : 1;
+  }
+  const bool tma = use_tma_env && get_maps<ORDER, T0, T1, T2>(g, f, &maps);
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)ctas, NT, C::SMEM_BYTES, st>>>(g, f, vel, a, u, rhs_out, flags, nt0, nt1, nt2, chunk_len, mom, maps);
+    return cudaGetLastError();
+  };
+  const bool lean = tma && flags == 3 && a.kind == 0 && a.bz == 0.0 && u.n_prev == 0;
+  if (lean) return launch(k_stage_march<ORDER, T0, T1, T2, NT, true, true>);
+  if (tma) return launch(k_stage_march<ORDER, T0, T1, T2, NT, true, false>);
+  return launch(k_stage_march<ORDER, T0, T1, T2, NT, false, false>);
+}
+
+constexpr int MARCH_T2 = 8;
+static int march_moment_parts(const DGeo& g) {
+  const int nt0 = (g.n[0] + 31) / 32, nt1 = (g.n[1] + 7) / 8, nt2 = (g.n[2] + MARCH_T2 - 1) / MARCH_T2;
+  int nchunk, chunk_len;
+  march_plan<MARCH_T2>(g, nt0 * nt1 * nt2, &nchunk, &chunk_len);
+  return nt2 * nchunk;
+}
+static cudaError_t launch_stage_march(const DGeo& g, const double* f, const double* vel, const DAccel& a, const DUpd& u,
+                                      double* rhs_out, int flags, const DMom& mom, cudaStream_t st) {
+  if (g.order == 4) return launch_march_cfg<4, 32, 8, MARCH_T2, 256>(g, f, vel, a, u, rhs_out, flags, mom, st);
+  return launch_march_cfg<6, 32, 8, MARCH_T2, 256>(g, f, vel, a, u, rhs_out, flags, mom, st);
+}
+
+}  // namespace LK_NS
