@@ -6,5 +6,5 @@ This Python package is only a ctypes loader used by the tests and bench.py; it c
 and no CPU fallback: if the CUDA library is missing or no GPU is present, compute calls raise.
 """
 from .capi import (  # noqa: F401
-    Geom, Accel, Inflow, RkUpdate, LokiError, lib, load, library_path,
+    Geom, Accel, Inflow, RkUpdate, StageMoments, LokiError, lib, load, library_path,
 )

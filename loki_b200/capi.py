@@ -47,6 +47,10 @@ class RkUpdate(C.Structure):
                 ("c_prev", C.c_double * 7)]
 
 
+class StageMoments(C.Structure):
+    _fields_ = [("nmom", C.c_int), ("partial", C.c_void_p), ("capacity", C.c_int64)]
+
+
 def library_path():
     return os.path.join(_HERE, "libloki_b200.so")
 
@@ -72,6 +76,11 @@ _PROTOS = {
     "lk_advection_derivatives_4d": (C.c_int, [_vp, _vp, C.POINTER(Geom), _vp, _vp]),
     "lk_acceleration_derivatives_4d": (C.c_int, [_vp, _vp, C.POINTER(Geom), C.POINTER(Accel), _vp]),
     "lk_vlasov_rhs": (C.c_int, [_vp, _vp, C.POINTER(Geom), _vp, C.POINTER(Accel), C.POINTER(RkUpdate), _vp]),
+    "lk_stage_moment_parts": (C.c_int, [C.POINTER(Geom)]),
+    "lk_vlasov_stage": (C.c_int, [_vp, _vp, C.POINTER(Geom), _vp, C.POINTER(Accel), C.POINTER(RkUpdate),
+                                  C.POINTER(StageMoments), _vp]),
+    "lk_moments_finish": (C.c_int, [_vp, _vp, _vp, C.POINTER(StageMoments), C.POINTER(Geom), C.c_double, C.c_double, _vp]),
+    "lk_ke_e_dot_from_moments": (C.c_int, [_vp, C.POINTER(StageMoments), C.POINTER(Geom), C.c_double, _vp, _vp]),
     "lk_reduce_4d_to_2d": (C.c_int, [_vp, _vp, C.POINTER(Geom), C.c_double, C.c_double, _vp]),
     "lk_current_density": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(Geom), _vp, _vp, C.c_double, C.c_double, _vp]),
     "lk_ke_e_dot": (C.c_int, [_vp, _vp, C.POINTER(Geom), C.c_double, _vp, _vp, _vp]),

@@ -130,7 +130,9 @@ static bool accel_ok(const lk_accel* a) {
 
 int lk_max_accel(const lk_geom* g, const lk_accel* a, double* out, void* stream) {
   if (!geom_ok(g) || !accel_ok(a) || !out) return fail(LK_ERR_ARG, "lk_max_accel: bad argument");
-  CHECK_LAUNCH(DISPATCH(max_accel)(g, a, out, (cudaStream_t)stream), "lk_max_accel");
+  double* s4 = scratch(2, sizeof(double) * 4);
+  if (!s4) return cuda_fail(cudaGetLastError(), "lk_max_accel: scratch");
+  CHECK_LAUNCH(DISPATCH(max_accel)(g, a, out, s4, (cudaStream_t)stream), "lk_max_accel");
 }
 int lk_set_phase_space_vel_4d(double* vel3, double* vel4, const lk_geom* g, const lk_accel* a, double* out, void* stream) {
   if (!geom_ok(g) || !accel_ok(a) || !out) return fail(LK_ERR_ARG, "lk_set_phase_space_vel_4d: bad argument");

@@ -63,9 +63,8 @@ __device__ __forceinline__ i64 gidx(const DGeo& g, int i1, int i2, int i3, int i
 // acceleration at a vx-face (i3 = face index) / vy-face: setphasespacevel4D (KineticSpeciesF.f:78-80,
 // 98-100) and setphasespacevelmaxwell4D (:154-158, 176-180), evaluated on the fly.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double accel_x(const DAccel& a, const DGeo& g, int i1, int i2, int i3, int i4) {
-  const double vy = __ldg(a.vxf + i3 + (i64)(g.nd[2] + 1) * (i4 + (i64)g.nd[3]));
-  const i64 p = i1 + (i64)g.nd[0] * i2;
+// p = i1 + n1d*i2; vy / vx = the velocity-table value at the face
+__device__ __forceinline__ double accel_x_v(const DAccel& a, const DGeo& g, i64 p, double vy) {
   const i64 pl = (i64)g.nd[0] * g.nd[1];
   if (a.kind == 0) {
     return __ldg(a.field + p) + a.norm * vy * a.bz;
@@ -75,9 +74,7 @@ __device__ __forceinline__ double accel_x(const DAccel& a, const DGeo& g, int i1
     return a.norm * (ex + vy * bzf + vy * a.bz - vz * by);
   }
 }
-__device__ __forceinline__ double accel_y(const DAccel& a, const DGeo& g, int i1, int i2, int i3, int i4) {
-  const double vx = __ldg(a.vyf + i3 + (i64)g.nd[2] * i4);
-  const i64 p = i1 + (i64)g.nd[0] * i2;
+__device__ __forceinline__ double accel_y_v(const DAccel& a, const DGeo& g, i64 p, double vx) {
   const i64 pl = (i64)g.nd[0] * g.nd[1];
   if (a.kind == 0) {
     return __ldg(a.field + p + pl) - a.norm * vx * a.bz;
@@ -86,6 +83,14 @@ __device__ __forceinline__ double accel_y(const DAccel& a, const DGeo& g, int i1
     const double vz = __ldg(a.vz + p);
     return a.norm * (ey + vz * bx - vx * bzf - vx * a.bz);
   }
+}
+__device__ __forceinline__ double accel_x(const DAccel& a, const DGeo& g, int i1, int i2, int i3, int i4) {
+  const double vy = __ldg(a.vxf + i3 + (i64)(g.nd[2] + 1) * (i4 + (i64)g.nd[3]));
+  return accel_x_v(a, g, i1 + (i64)g.nd[0] * i2, vy);
+}
+__device__ __forceinline__ double accel_y(const DAccel& a, const DGeo& g, int i1, int i2, int i3, int i4) {
+  const double vx = __ldg(a.vyf + i3 + (i64)g.nd[2] * i4);
+  return accel_y_v(a, g, i1 + (i64)g.nd[0] * i2, vx);
 }
 
 // ---------------------------------------------------------------------------------------------

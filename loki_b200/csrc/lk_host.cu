@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -175,6 +176,10 @@ struct KineticSpecies {
   // per-stage 2D work arrays
   DevBuf<double> rho_s, accel, ext_efield, lam, drv_g, drv_h, ke;  // ke: {state, old, delta, rhs} + k[8]
   DevBuf<double> ke_k, ke_coef;
+  // velocity moments of f_eval left behind by the fused stage kernel (production arithmetic)
+  DevBuf<double> mom_part;
+  lk_stage_moments mom;
+  bool mom_valid = false;
   // inflow (initial condition) tables
   DevBuf<double> ic_fx, ic_fv;
   lk_inflow inflow;
@@ -233,8 +238,18 @@ struct KineticSpecies {
 
   // chargeDensity (KineticSpecies.H:265-270; schedule set-up KineticSpecies.C:1736-1753)
   int chargeDensity(const double* f, void* st) {
+    // production: the stage kernel that wrote f also summed it over velocity space
+    if (mom_valid && f == f_eval && !lk_get_strict())
+      return lk_moments_finish(rho_s.p, nullptr, nullptr, &momFirst(), &g, g.dx[2] * g.dx[3], charge, st);
     return lk_reduce_4d_to_2d(rho_s.p, f, &g, g.dx[2] * g.dx[3], charge, st);
   }
+  // the charge-density finish only needs moment 0 of the partial buffer
+  const lk_stage_moments& momFirst() {
+    mom0 = mom;
+    mom0.nmom = 1;
+    return mom0;
+  }
+  lk_stage_moments mom0;
 
   // computeAcceleration (KineticSpecies.C:697-774).  em_local: this rank's window of E incl. ghosts.
   int computeAcceleration(const double* em_local, double time, const double xlo[2], const int tile_lo[2], bool want_max,
@@ -365,6 +380,16 @@ struct VPSystem {
       LKH_CUDA(cudaMemset(ks->lam.p, 0, sizeof(double) * 2));
       memset(&ks->inflow, 0, sizeof(ks->inflow));
       ks->has_driver = sd.has_driver != 0;
+      {
+        const int nmom = ks->has_driver ? 3 : 1;
+        const int parts = lk_stage_moment_parts(&ks->g);
+        if (parts < 1) return LK_ERR_ARG;
+        const size_t cap = (size_t)nmom * parts * d->tile_n[0] * d->tile_n[1];
+        LKH_CHECK(ks->mom_part.alloc(cap));
+        ks->mom.nmom = nmom;
+        ks->mom.partial = ks->mom_part.p;
+        ks->mom.capacity = (int64_t)cap;
+      }
       if (ks->has_driver) {
         memcpy(ks->driver.p, sd.driver, sizeof(double) * 16);
         ks->driver.phase = sd.driver_phase;
@@ -464,7 +489,7 @@ struct VPSystem {
         const double w_eval[4] = {dtOn6, dtOn3, dtOn3, dtOn6};
         const double w_upd[4] = {dtOn2, dtOn2, dt, 1.0};
         u.delta_in = (stage == 0) ? nullptr : ks->delta.p;   // zeroSolnData(m_delta)
-        u.delta_out = ks->delta.p;
+        u.delta_out = (stage == 3) ? nullptr : ks->delta.p;  // nothing reads m_delta after the last stage
         u.w_delta = w_eval[stage];
         u.c_pred = w_upd[stage];
         u.use_delta = (stage == 3);
@@ -482,10 +507,20 @@ struct VPSystem {
         u.c_pred = dt * coef[stage];
         ke_coef[ke_ncoef++] = dt * coef[stage];
       }
-      LKH_CHECK(lk_vlasov_rhs(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, st));
-      // completeRHS: the driver's energy input rate, integrated with the state (KineticSpecies.C:1084-1093)
+      static const bool no_fuse = getenv("LK_NO_FUSED_MOMENTS") != nullptr;  // debugging aid
+      const bool fused_moments = !lk_get_strict() && !no_fuse;
+      // completeRHS: the driver's energy input rate, integrated with the state (KineticSpecies.C:1084-1093).
+      // Production: from the vx moment of f_eval that the previous stage kernel left behind (consumed
+      // here, before this stage's kernel overwrites the partial buffer).
       if (ks->has_driver) {
-        LKH_CHECK(lk_ke_e_dot(ks->ke.p + 3, ks->f_eval, &ks->g, ks->charge, ks->velocities.p, ks->ext_efield.p, st));
+        if (fused_moments && ks->mom_valid)
+          LKH_CHECK(lk_ke_e_dot_from_moments(ks->ke.p + 3, &ks->mom, &ks->g, ks->charge, ks->ext_efield.p, st));
+        else
+          LKH_CHECK(lk_ke_e_dot(ks->ke.p + 3, ks->f_eval, &ks->g, ks->charge, ks->velocities.p, ks->ext_efield.p, st));
+      }
+      LKH_CHECK(lk_vlasov_stage(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, fused_moments ? &ks->mom : nullptr, st));
+      ks->mom_valid = fused_moments;  // moments of `pred`, the next stage's input
+      if (ks->has_driver) {
         if (rk4) {
           static const double THIRD = 1.0 / 3.0;
           const double dtOn2 = 0.5 * dt, dtOn3 = THIRD * dt, dtOn6 = 0.5 * dtOn3;
@@ -558,6 +593,7 @@ struct VPSystem {
     for (size_t s = 0; s < species.size(); ++s) {
       KineticSpecies* ks = species[s];
       double* f = ks->state();
+      ks->mom_valid = false;
       LKH_CHECK(lk_periodic_fill_4d(f, &ks->g, 1, 1, st));
       LKH_CHECK(lk_advection_derivatives_4d(rhs_dev[s], f, &ks->g, ks->velocities.p, st));
       LKH_CHECK(ks->computeAcceleration(em_local.p, t, desc.xlo, desc.tile_lo, true, st));
@@ -603,6 +639,7 @@ int lk_vp_set_state(lk_vp_system* h, int s, const double* f_host) {
   auto* ks = h->sys.species[s];
   if (cudaMemcpy(ks->state(), f_host, sizeof(double) * ks->vol, cudaMemcpyHostToDevice) != cudaSuccess) return LK_ERR_CUDA;
   ks->f_eval = ks->state();
+  ks->mom_valid = false;
   return LK_OK;
 }
 int lk_vp_get_state(lk_vp_system* h, int s, double* f_host) {

@@ -160,25 +160,49 @@ __global__ void k_vel4(DGeo g, DAccel a, double* __restrict__ vel4, double* out2
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) atomic_max_nonneg(out2 + 1, m);
 }
-// max only: one thread per (i1,i2) interior x (face index along the one dimension that matters)
-__global__ void k_max_accel(DGeo g, DAccel a, double* out2) {
-  // the acceleration depends on (i1,i2) and on the velocity tables; scan interior (i1,i2) x (i3f,i4)
-  const i64 nxy = (i64)g.n[0] * g.n[1];
-  const i64 nf3 = (i64)(g.n[2] + 1) * g.n[3];
-  const i64 nf4 = (i64)g.n[2] * (g.n[3] + 1);
-  double mx = 0.0, my = 0.0;
-  const i64 total = nxy * (nf3 + nf4);
-  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
-    i64 p = t % nxy, q = t / nxy;
-    int i1 = (int)(p % g.n[0]) + g.ng, i2 = (int)(p / g.n[0]) + g.ng;
-    if (q < nf3) {
-      int i3 = (int)(q % (g.n[2] + 1)) + g.ng, i4 = (int)(q / (g.n[2] + 1)) + g.ng;
-      mx = fmax(mx, fabs(accel_x(a, g, i1, i2, i3, i4)));
-    } else {
-      q -= nf3;
-      int i3 = (int)(q % g.n[2]) + g.ng, i4 = (int)(q / g.n[2]) + g.ng;
-      my = fmax(my, fabs(accel_y(a, g, i1, i2, i3, i4)));
+// max only.  The acceleration is a monotone (affine) function of the one velocity-table value it reads
+// (setphasespacevel4D, KineticSpeciesF.f:78-80, 98-100; Maxwell :154-158, 176-180), so its largest
+// magnitude over the interior faces is attained at the smallest or the largest table value: reduce the
+// two tables to {min, max} once (O(Nvx Nvy)), then scan (i1,i2) only.  Same expression, same bits.
+__global__ void k_table_minmax(DGeo g, DAccel a, double* out4) {  // one CTA
+  __shared__ double sh[4][32];
+  const int ng = g.ng;
+  double lo3 = 1e300, hi3 = -1e300, lo4 = 1e300, hi4 = -1e300;
+  const int nf3 = (g.n[2] + 1) * g.n[3], nf4 = g.n[2] * (g.n[3] + 1);
+  for (int t = threadIdx.x; t < nf3; t += blockDim.x) {  // vx faces: table component 1 (vy)
+    const int i3 = t % (g.n[2] + 1) + ng, i4 = t / (g.n[2] + 1) + ng;
+    const double v = a.vxf[i3 + (i64)(g.nd[2] + 1) * (i4 + (i64)g.nd[3])];
+    lo3 = fmin(lo3, v); hi3 = fmax(hi3, v);
+  }
+  for (int t = threadIdx.x; t < nf4; t += blockDim.x) {  // vy faces: table component 0 (vx)
+    const int i3 = t % g.n[2] + ng, i4 = t / g.n[2] + ng;
+    const double v = a.vyf[i3 + (i64)g.nd[2] * i4];
+    lo4 = fmin(lo4, v); hi4 = fmax(hi4, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo3 = fmin(lo3, __shfl_xor_sync(0xffffffffu, lo3, o)); hi3 = fmax(hi3, __shfl_xor_sync(0xffffffffu, hi3, o));
+    lo4 = fmin(lo4, __shfl_xor_sync(0xffffffffu, lo4, o)); hi4 = fmax(hi4, __shfl_xor_sync(0xffffffffu, hi4, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = lo3; sh[1][threadIdx.x >> 5] = hi3; sh[2][threadIdx.x >> 5] = lo4; sh[3][threadIdx.x >> 5] = hi4;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+      sh[0][0] = fmin(sh[0][0], sh[0][k]); sh[1][0] = fmax(sh[1][0], sh[1][k]);
+      sh[2][0] = fmin(sh[2][0], sh[2][k]); sh[3][0] = fmax(sh[3][0], sh[3][k]);
     }
+    for (int k = 0; k < 4; ++k) out4[k] = sh[k][0];
+  }
+}
+__global__ void k_max_accel(DGeo g, DAccel a, const double* __restrict__ mm, double* out2) {
+  const i64 nxy = (i64)g.n[0] * g.n[1];
+  double mx = 0.0, my = 0.0;
+  const double vylo = mm[0], vyhi = mm[1], vxlo = mm[2], vxhi = mm[3];
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < nxy; t += (i64)gridDim.x * blockDim.x) {
+    const i64 p = (t % g.n[0] + g.ng) + (i64)g.nd[0] * (t / g.n[0] + g.ng);
+    mx = fmax(mx, fmax(fabs(accel_x_v(a, g, p, vylo)), fabs(accel_x_v(a, g, p, vyhi))));
+    my = fmax(my, fmax(fabs(accel_y_v(a, g, p, vxlo)), fabs(accel_y_v(a, g, p, vxhi))));
   }
   mx = warp_max(mx);
   my = warp_max(my);
@@ -187,16 +211,15 @@ __global__ void k_max_accel(DGeo g, DAccel a, double* out2) {
     atomic_max_nonneg(out2 + 1, my);
   }
 }
-cudaError_t max_accel(const lk_geom* g, const lk_accel* a, double* out2, cudaStream_t st) {
+cudaError_t max_accel(const lk_geom* g, const lk_accel* a, double* out2, double* scratch4, cudaStream_t st) {
   DGeo d = make_geo(g);
   DAccel da = make_accel(a);
   k_zero2<<<1, 1, 0, st>>>(out2);
-  ++g_launches;
-  // for separable (non-relativistic) tables a(i1,i2,.,i4) is independent of i3: the scan is still
-  // only O(Nx Ny (Nvx+1) Nvy) table look-ups, tiny next to the 4D passes
-  i64 total = (i64)g->n[0] * g->n[1] * ((i64)(g->n[2] + 1) * g->n[3] + (i64)g->n[2] * (g->n[3] + 1));
-  unsigned blocks = (unsigned)min((i64)nblk(total, 256), (i64)148 * 16);
-  k_max_accel<<<blocks, 256, 0, st>>>(d, da, out2);
+  k_table_minmax<<<1, 1024, 0, st>>>(d, da, scratch4);
+  g_launches += 2;
+  const i64 total = (i64)g->n[0] * g->n[1];
+  unsigned blocks = (unsigned)min((i64)nblk(total, 256), (i64)148 * 4);
+  k_max_accel<<<blocks, 256, 0, st>>>(d, da, scratch4, out2);
   return LK_LAUNCHED();
 }
 cudaError_t set_phase_space_vel(double* vel3, double* vel4, const lk_geom* g, const lk_accel* a, double* out2,

@@ -11,7 +11,8 @@
   cudaError_t weno_fit(int order, const double* u, const double* vel, double* face, int64_t count,    \
                        cudaStream_t st);                                                              \
   cudaError_t xpby4d(double* x, const double* y, double b, const lk_geom* g, cudaStream_t st);        \
-  cudaError_t max_accel(const lk_geom* g, const lk_accel* a, double* out2, cudaStream_t st);          \
+  cudaError_t max_accel(const lk_geom* g, const lk_accel* a, double* out2, double* scratch4,          \
+                        cudaStream_t st);                                                             \
   cudaError_t set_phase_space_vel(double* vel3, double* vel4, const lk_geom* g, const lk_accel* a,    \
                                   double* out2, cudaStream_t st);                                     \
   cudaError_t set_accel_bcs(double* f, const lk_geom* g, const lk_accel* a, const lk_inflow* ic,      \

@@ -140,6 +140,9 @@ const double* ok_vp_rho(const ok_vp_work* w);     /* neutralised net charge dens
 void ok_vp_rk4_step(ok_vp_work* w, double** f_new, double** f_old, double time, double dt, double* ke);
 void ok_vp_rk6_step(ok_vp_work* w, double** f_new, double** f_old, double time, double dt, double* ke);
 /* KineticSpecies::computeDt + VPSystem::stableDt from given axmax/aymax */
+/* axmax/aymax of the most recent evalRHS (the last RK stage of the previous step): what
+ * VPSystem::stableDt sees (KineticSpecies.C:771-772) */
+void ok_vp_last_accel_max(const ok_vp_work* w, double* axmax, double* aymax);
 double ok_vp_stable_dt(const ok_vp_work* w, const double* axmax, const double* aymax, int rk_order);
 
 /* unfused CPU timing leg used by bench.py (same passes as the reference does per RK4 stage) */

@@ -23,6 +23,9 @@ struct ok_vp_work {
   /* RK scratch */
   double **rhs, **delta, **k[8];
   double *ke_rhs, *ke_delta, *ke_k[8];
+  /* m_lambda_max[V1], [V2] as the last evalRHS left them (KineticSpecies.C:771-772): what stableDt sees
+   * at the start of the next step (VPSystem.C:489-505) */
+  double *last_ax, *last_ay;
 };
 
 static int64_t vol4(const ok_geom* g) { return ok_nd(g, 0) * ok_nd(g, 1) * ok_nd(g, 2) * ok_nd(g, 3); }
@@ -98,6 +101,8 @@ ok_vp_work* ok_vp_work_create(int ns, const ok_species* sp, const double* xlo, c
 #undef PP
   w->ke_rhs = (double*)calloc(ns, sizeof(double));
   w->ke_delta = (double*)calloc(ns, sizeof(double));
+  w->last_ax = (double*)calloc(ns, sizeof(double));
+  w->last_ay = (double*)calloc(ns, sizeof(double));
   const ok_geom* g0 = &sp[0].g;
   const int64_t n1d = ok_nd(g0, 0), n2d = ok_nd(g0, 1);
   for (int s = 0; s < ns; ++s) {
@@ -128,6 +133,13 @@ ok_vp_work* ok_vp_work_create(int ns, const ok_species* sp, const double* xlo, c
   return w;
 }
 
+void ok_vp_last_accel_max(const ok_vp_work* w, double* axmax, double* aymax) {
+  for (int s = 0; s < w->ns; ++s) {
+    axmax[s] = w->last_ax[s];
+    aymax[s] = w->last_ay[s];
+  }
+}
+
 void ok_vp_work_destroy(ok_vp_work* w) {
   if (!w) return;
   for (int s = 0; s < w->ns; ++s) {
@@ -137,6 +149,7 @@ void ok_vp_work_destroy(ok_vp_work* w) {
     for (int i = 0; i < 8; ++i) free(w->k[i][s]);
   }
   for (int i = 0; i < 8; ++i) { free(w->k[i]); free(w->ke_k[i]); }
+  free(w->last_ax); free(w->last_ay);
   free(w->velocities); free(w->vxface); free(w->vyface); free(w->vel1); free(w->vel2); free(w->vel3);
   free(w->vel4); free(w->accel); free(w->ext); free(w->rho_s); free(w->rhs); free(w->delta); free(w->ke_rhs);
   free(w->ke_delta); free(w->rho); free(w->phi); free(w->em); free(w->sx); free(w->sy); free(w->sp);
@@ -183,6 +196,8 @@ void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double time, double
     for (int64_t k = 0; k < 2 * pl; ++k) w->accel[s][k] *= normalization;
     ok_set_phase_space_vel_4d(w->vel3[s], w->vel4[s], g, w->vxface[s], w->vyface[s], normalization,
                               sp->bz_const, w->accel[s], &axmax[s], &aymax[s]);
+    w->last_ax[s] = axmax[s];
+    w->last_ay[s] = aymax[s];
     /* 5. v-boundary fill, acceleration derivatives, completeRHS */
     ok_set_acceleration_bcs_4d(f[s], g, w->vel3[s], w->vel4[s], 1, 1, 1, 1, sp->ic, sp->ic_ctx);
     ok_acceleration_derivatives_4d(rhs[s], f[s], g, w->vel3[s], w->vel4[s]);

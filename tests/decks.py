@@ -124,23 +124,23 @@ class Deck:
 PI = 3.1415926535897932384626
 
 
-def plane_epw(n=(32, 32), nv=(128, 32)):
+def plane_epw(n=(32, 32), nv=(128, 32), A=0.0):
     """test/planeEPW_fixedIons/planeEPW_fixedIons.pp: one electron species, driven, order 4 / RK4"""
     xa, xb, ya, yb = -3 * PI, 3 * PI, -78 * PI, 78 * PI
     drv = driver_params(xwidth=(xb - xa) / 2.0, ywidth=300 * PI, shape=0.0, omega=1.2001, E0=0.01, t_ramp=10.0,
                         t_off=10.0, x_shape=0.0, lwidth=50.0, x0=0.0)
-    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, kx1=1.0 / 3, ky1=1.0 / 3, driver=drv)
+    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, A=A, kx1=1.0 / 3, ky1=1.0 / 78, driver=drv)
     return Deck("planeEPW_fixedIons", n, (xa, xb, ya, yb), [e], order=4, rk=4)
 
 
-def plane_iaw(n=(32, 32), nv=(64, 32), order=4, rk=4):
+def plane_iaw(n=(32, 32), nv=(64, 32), order=4, rk=4, A=0.0):
     """test/planeIAW/planeIAW.pp (order 4 / RK4) and test/planeIAW_6 (order 6 / RK6): electrons + ions"""
     klde = 1.0 / 3
     ialpha = math.sqrt(10.0) * math.sqrt(100.0)
     xa, xb, ya, yb = -PI / klde, PI / klde, -78 * PI / klde, 78 * PI / klde
     drv = driver_params(xwidth=(xb - xa) / 2.0, ywidth=300 * PI, shape=0.0, omega=0.0381, E0=0.1, t_ramp=1.0,
                         t_off=2.0, x_shape=0.0, lwidth=50.0, x0=0.0)
-    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, kx1=klde, ky1=klde, driver=drv)
+    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, A=A, kx1=klde, ky1=klde / 78, driver=drv)
     i = Species("ion", nv, (-10 / ialpha, 10 / ialpha, -10 / ialpha, 10 / ialpha), 100.0, 1.0, tx=0.1, ty=0.1,
-                kx1=klde, ky1=klde)
+                A=A, kx1=klde, ky1=klde / 78)
     return Deck("planeIAW" + ("_6" if order == 6 else ""), n, (xa, xb, ya, yb), [e, i], order=order, rk=rk)

@@ -84,6 +84,7 @@ def load():
     L.ok_vp_rho.argtypes = [C.c_void_p]
     L.ok_vp_rk4_step.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), d, d, dp]
     L.ok_vp_rk6_step.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), d, d, dp]
+    L.ok_vp_last_accel_max.argtypes = [C.c_void_p, dp, dp]
     L.ok_vp_stable_dt.restype = d
     L.ok_vp_stable_dt.argtypes = [C.c_void_p, dp, dp, i]
     L.ok_shaped_ramped_driver.argtypes = [dp, dp, i, i, i, i, dp, dp, i, d, dp, d, i]

@@ -347,6 +347,57 @@ def test_halo_pack_unpack_equals_periodic(lk, ok, n, order):
     assert np.array_equal(out[:, :, :, ng:-ng], ref[:, :, :, ng:-ng])
 
 
+@pytest.mark.parametrize("n,order", [((40, 12, 20, 11), 4), ((9, 17, 8, 21), 4), ((12, 10, 16, 10), 6)])
+@pytest.mark.parametrize("nmom", [1, 3])
+def test_fused_stage_moments(lk, ok, fast, n, order, nmom):
+    """lk_vlasov_stage leaves the velocity moments of its predictor behind: charge density, the vx / vy
+    moments and ke_e_dot computed from them equal the stand-alone reductions of the same array
+    (ReductionSchedule.C:421-444, KineticSpeciesF.f:2400-2443, 2563-2602) up to summation order"""
+    import torch
+    import loki_b200 as lkm
+    s = Setup(ok, n, order)
+    d = Dev(lk, s)
+    dfold = d.t(s.f * 1.01)
+    ddelta = d.t(0.001 * s.f)
+    pred = d.t(s.f * 0.0)
+    u = lkm.RkUpdate()
+    u.f_old, u.delta_in, u.delta_out, u.pred = dfold.data_ptr(), ddelta.data_ptr(), ddelta.data_ptr(), pred.data_ptr()
+    u.w_delta, u.c_pred, u.use_delta = 0.0123, 0.05, 0
+    parts = lk.lk_stage_moment_parts(C.byref(d.g))
+    assert parts >= 1
+    part = torch.full((nmom * parts * n[0] * n[1],), float("nan"), dtype=torch.float64, device="cuda")
+    m = lkm.StageMoments()
+    m.nmom, m.partial, m.capacity = nmom, part.data_ptr(), part.numel()
+    chk(lk, lk.lk_vlasov_stage(None, d.f.data_ptr(), C.byref(d.g), d.velocities.data_ptr(), C.byref(d.accel), C.byref(u), C.byref(m), None), "stage")
+    # the same stage without moments gives the same predictor
+    pred2 = d.t(s.f * 0.0)
+    ddelta2 = d.t(0.001 * s.f)
+    u.delta_in, u.delta_out, u.pred = ddelta2.data_ptr(), ddelta2.data_ptr(), pred2.data_ptr()
+    chk(lk, lk.lk_vlasov_rhs(None, d.f.data_ptr(), C.byref(d.g), d.velocities.data_ptr(), C.byref(d.accel), C.byref(u), None), "stage2")
+    assert torch.equal(pred, pred2)
+    n1d, n2d = s.nd[0], s.nd[1]
+    dv, wgt = s.dx[2] * s.dx[3], -1.0
+    outs = [torch.full((n2d, n1d), 7.0, dtype=torch.float64, device="cuda") for _ in range(3)]
+    chk(lk, lk.lk_moments_finish(outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), C.byref(m), C.byref(d.g), dv, wgt, None), "finish")
+    ref0 = torch.zeros((n2d, n1d), dtype=torch.float64, device="cuda")
+    chk(lk, lk.lk_reduce_4d_to_2d(ref0.data_ptr(), pred.data_ptr(), C.byref(d.g), dv, wgt, None), "rho")
+    assert rel_err(_np(outs[0]), _np(ref0)) < 1e-13
+    ng = s.ng
+    assert np.all(_np(outs[0])[:ng] == 0.0) and np.all(_np(outs[0])[:, :ng] == 0.0)
+    if nmom == 3:
+        J = [torch.zeros((n2d, n1d), dtype=torch.float64, device="cuda") for _ in range(3)]
+        ones = torch.ones((n2d, n1d), dtype=torch.float64, device="cuda")
+        chk(lk, lk.lk_current_density(J[0].data_ptr(), J[1].data_ptr(), J[2].data_ptr(), pred.data_ptr(), C.byref(d.g),
+                                      d.velocities.data_ptr(), ones.data_ptr(), dv, wgt, None), "J")
+        assert rel_err(_np(outs[1]), _np(J[0])) < 1e-13
+        assert rel_err(_np(outs[2]), _np(J[1])) < 1e-13
+        ext = d.t(np.random.default_rng(3).uniform(-1, 1, size=(2, n2d, n1d)))
+        a, b = torch.zeros(1, dtype=torch.float64, device="cuda"), torch.zeros(1, dtype=torch.float64, device="cuda")
+        chk(lk, lk.lk_ke_e_dot_from_moments(a.data_ptr(), C.byref(m), C.byref(d.g), -1.0, ext.data_ptr(), None), "ke_m")
+        chk(lk, lk.lk_ke_e_dot(b.data_ptr(), pred.data_ptr(), C.byref(d.g), -1.0, d.velocities.data_ptr(), ext.data_ptr(), None), "ke")
+        assert abs(float(a) - float(b)) <= 1e-12 * abs(float(b))
+
+
 # ---------------------------------------------------------------- properties at a larger size
 def test_roll_invariance_large(lk, ok, fast):
     """periodic translation by a non-multiple of the tile size permutes the rhs exactly (tile seams)"""

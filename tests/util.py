@@ -131,3 +131,21 @@ def cell_rel_err(test, base):
     with np.errstate(divide="ignore", invalid="ignore"):
         r = np.where(den > 0, diff / den, 0.0)
     return float(np.max(r))
+
+
+def star_rel_err(test, base, scale_from, ng):
+    """max over interior cells of |t-b| / (largest |scale_from| in the cell's 4D star stencil of radius ng).
+    One RK step updates a cell from its star neighbourhood, so this is the accuracy a cell can be held
+    to when the data are rough enough for f + dt*rhs to cancel (where the per-cell metric of
+    checkTests.C:345-358 is unbounded).  Arrays include the ghost layers."""
+    a = np.abs(np.asarray(scale_from))
+    m = a.copy()
+    for ax in range(4):
+        for k in range(1, ng + 1):
+            m = np.maximum(m, np.roll(a, k, axis=ax))
+            m = np.maximum(m, np.roll(a, -k, axis=ax))
+    I = (slice(ng, -ng),) * 4
+    d = np.abs(np.asarray(test)[I] - np.asarray(base)[I])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r = np.where(m[I] > 0, d / m[I], 0.0)
+    return float(np.max(r))
