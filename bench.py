@@ -337,11 +337,11 @@ def run_own(args):
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_stencil_tiled (fused WENO RHS + RK4 stage update)",
+                "traffic": traffic, "kernel": "k_stage_march (fused WENO RHS + RK4 stage update + velocity moments)",
                 "algorithmic_bytes_per_launch": avg_bytes, "avg_launch_ms": avg_ms, "timed_launches": n_l.value,
                 "kernel_share_of_step": tot_ms.value / ms if ms > 0 else None, "peak_source": peak_src,
-                "note": "the kernel is fp64-FMA bound before it is HBM bound (about 150 fp64 instructions per "
-                        "cell-update); see DESIGN.md for the fp64 ceiling"}
+                "note": "co-limited by the fp64 pipe (about 125 fp64 instructions per cell-update, ceiling "
+                        "~150 G cell-updates/s at 1.965 GHz); see DESIGN.md section 3"}
 
     # ---- e2e: the same step with HOST buffers (pinned), H2D of the state + step + D2H of the result ----
     e2e = None
