@@ -280,225 +280,272 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
     else if (upd.delta_in && upd.delta_out && !upd.use_delta) ekind = 2;
     else if (upd.delta_in && !upd.delta_out && upd.use_delta) ekind = 3;
   }
+  // E (times q/m) at this thread's (x,y): constant along the whole march when vel3/vel4 do not depend
+  // on the velocity indices
+  const double ax0 = (do_acc && simple_acc) ? __ldg(a.field + pxy) : 0.0;
+  const double ay0 = (do_acc && simple_acc) ? __ldg(a.field + pxy + (i64)g.nd[0] * g.nd[1]) : 0.0;
+  double* const racc = sAcc + eb1 * PA + ea0;  // + c*T1*PA: this thread's column of the accumulator
 
   // ---- march -------------------------------------------------------------------------------------
-  for (int q = q0; q < q0 + nq; ++q) {
-    const int p = q + ng;                       // data index of the plane being updated
-    const int sc = (p - pbase) % NS;            // its ring slot
-    const double* cur = sCore + sc * C::NCORE;
-    const bool more = (q + 1 < q0 + nq);
+  // EK: epilogue kind, decided once per kernel (uniform) so that the per-cell code carries no pointer
+  // tests.  1..3 = the RK4 stage shapes (RK4Integrator.H:149-171): 1: delta = w*rhs (stage 1);
+  // 2: delta += w*rhs (stages 2,3); 3: pred = f_old + c*(delta + w*rhs), delta not stored (stage 4);
+  // 0: everything decided per cell (RK6, rhs_out, partial evaluations).
+  // Every sweep loads its whole line into registers BEFORE the first fit and stores after the last: no
+  // shared-memory store sits between the loads, so the W+T fits of a line are independent instruction
+  // streams the scheduler can interleave (the fp64 dependent-issue latency is what bounds this kernel).
+  auto march = [&](auto ek_tag) {
+    constexpr int EK = decltype(ek_tag)::value;
+    for (int q = q0; q < q0 + nq; ++q) {
+      const int p = q + ng;                       // data index of the plane being updated
+      const int sc = (p - pbase) % NS;            // its ring slot
+      const double* cur = sCore + sc * C::NCORE;
+      const bool more = (q + 1 < q0 + nq);
 
-    // pull the next plane's RK operands towards L2 (one 128-byte line per thread)
-    if (upd.active && more) {
-      constexpr int LPR = (T0 * 8 + 127) / 128;  // lines per row
-      for (int e = tid; e < T1 * T2 * LPR; e += NT) {
-        const int ln = e % LPR, row = e / LPR, b1 = row % T1, c = row / T1;
-        if ((o1 + b1 < g.n[1]) && (o2 + c < g.n[2]) && (o0 + ln * 16 < g.n[0])) {
-          const i64 o = (i64)(o0 + ng + ln * 16) + g.s[1] * (o1 + b1 + ng) + g.s[2] * (o2 + c + ng) + g.s[3] * (p + 1);
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(upd.f_old + o));
-          if (upd.delta_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(upd.delta_in + o));
+      // pull the next plane's RK operands towards L2 (one 128-byte line per thread)
+      if (upd.active && more) {
+        constexpr int LPR = (T0 * 8 + 127) / 128;  // lines per row
+        for (int e = tid; e < T1 * T2 * LPR; e += NT) {
+          const int ln = e % LPR, row = e / LPR, b1 = row % T1, c = row / T1;
+          if ((o1 + b1 < g.n[1]) && (o2 + c < g.n[2]) && (o0 + ln * 16 < g.n[0])) {
+            const i64 o = (i64)(o0 + ng + ln * 16) + g.s[1] * (o1 + b1 + ng) + g.s[2] * (o2 + c + ng) + g.s[3] * (p + 1);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(upd.f_old + o));
+            if (upd.delta_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(upd.delta_in + o));
+          }
         }
       }
-    }
 
-    // ---------------- x sweep: rows (b1, c) in segments of SX cells ----------------
-    for (int l = tid; l < T1 * T2 * (T0 / SX); l += NT) {
-      const int row = l % (T1 * T2), seg = l / (T1 * T2);
-      const int b1 = row % T1, c = row / T1;
-      double* arow = sAcc + row * PA + seg * SX;
-      double init[SX];
+      // ---------------- x sweep: rows (b1, c) in segments of SX cells ----------------
+      {
+        constexpr int ITEMS = T1 * T2 * (T0 / SX);
 #pragma unroll
-      for (int k = 0; k < SX; ++k) init[k] = 0.0;
-      if (accumulate) {
+        for (int it = 0; it < (ITEMS + NT - 1) / NT; ++it) {
+          const int l = tid + it * NT;
+          if ((ITEMS % NT) != 0 && l >= ITEMS) break;
+          const int row = l % (T1 * T2), seg = l / (T1 * T2);
+          const int b1 = row % T1, c = row / T1;
+          double* arow = sAcc + row * PA + seg * SX;
+          double init[SX];
 #pragma unroll
-        for (int k = 0; k < SX; ++k) {
-          const bool ok = (o0 + seg * SX + k < g.n[0]) && (o1 + b1 < g.n[1]) && (o2 + c < g.n[2]);
-          if (ok) init[k] = rhs_out[(i64)(o0 + seg * SX + k + ng) + g.s[1] * (o1 + b1 + ng) + g.s[2] * (o2 + c + ng) + g.s[3] * p];
+          for (int k = 0; k < SX; ++k) init[k] = 0.0;
+          if (accumulate) {
+#pragma unroll
+            for (int k = 0; k < SX; ++k) {
+              const bool ok = (o0 + seg * SX + k < g.n[0]) && (o1 + b1 < g.n[1]) && (o2 + c < g.n[2]);
+              if (ok) init[k] = rhs_out[(i64)(o0 + seg * SX + k + ng) + g.s[1] * (o1 + b1 + ng) + g.s[2] * (o2 + c + ng) + g.s[3] * p];
+            }
+          }
+          if (do_adv) {
+            const int i3 = min(o2 + c, g.n[2] - 1) + ng;
+            const double vx = __ldg(vel + i3 + (i64)g.nd[2] * p);
+            const bool pos = vx > 0.0;
+            const double2* r2 = reinterpret_cast<const double2*>(cur + row * PC + seg * SX);
+            double v[SX + W];
+#pragma unroll
+            for (int k = 0; k < (SX + W) / 2; ++k) {
+              const double2 t = r2[k];
+              v[2 * k] = t.x;
+              v[2 * k + 1] = t.y;
+            }
+            Walker<ORDER> wk;
+            wk.init([&](int k) { return v[k]; });
+            double uL = wk.next(v[W - 1], pos);
+#pragma unroll
+            for (int k = 0; k < SX; ++k) {
+              const double uR = wk.next(v[k + W], pos);
+              init[k] = sub_flux(init[k], vx, uR, uL, g.dx[0], rdx0);
+              uL = uR;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < SX; ++k) arow[k] = init[k];
         }
       }
+      __syncthreads();
+
+      // ---------------- y sweep: lines (a0, c) ----------------
+      if (TMA) { mbar_wait(&bars[NS], ph_y); ph_y ^= 1u; }
       if (do_adv) {
-        const int i3 = min(o2 + c, g.n[2] - 1) + ng;
-        const double vx = __ldg(vel + i3 + (i64)g.nd[2] * p);
-        const bool pos = vx > 0.0;
-        const double2* r2 = reinterpret_cast<const double2*>(cur + row * PC + seg * SX);
-        double v[SX + W];
+        constexpr int ITEMS = T0 * T2;
 #pragma unroll
-        for (int k = 0; k < (SX + W) / 2; ++k) {
-          const double2 t = r2[k];
-          v[2 * k] = t.x;
-          v[2 * k + 1] = t.y;
-        }
-        Walker<ORDER> wk;
-        wk.init([&](int k) { return v[k]; });
-        double uL = wk.next(v[W - 1], pos);
+        for (int it = 0; it < (ITEMS + NT - 1) / NT; ++it) {
+          const int l = tid + it * NT;
+          if ((ITEMS % NT) != 0 && l >= ITEMS) break;
+          const int a0 = l % T0, c = l / T0;
+          const int i3 = min(o2 + c, g.n[2] - 1) + ng;
+          const double vy = __ldg(vel + i3 + (i64)g.nd[2] * (p + (i64)g.nd[3]));
+          const bool pos = vy > 0.0;
+          const double* core = cur + c * T1 * PC + NG + a0;        // + b1*PC
+          const double* hlo = sYh + c * NG * PC + NG + a0;         // + h*PC
+          const double* hhi = hlo + C::NYH;
+          double* yacc = sAcc + c * T1 * PA + a0;                  // + b1*PA
+          double v[T1 + W], acc[T1];
 #pragma unroll
-        for (int k = 0; k < SX; ++k) {
-          const double uR = wk.next(v[k + W], pos);
-          arow[k] = sub_flux(init[k], vx, uR, uL, g.dx[0], rdx0);
-          uL = uR;
-        }
-      } else {
+          for (int k = 0; k < NG; ++k) v[k] = hlo[k * PC];
 #pragma unroll
-        for (int k = 0; k < SX; ++k) arow[k] = init[k];
-      }
-    }
-    __syncthreads();
-
-    // ---------------- y sweep: lines (a0, c) ----------------
-    if (TMA) { mbar_wait(&bars[NS], ph_y); ph_y ^= 1u; }
-    if (do_adv) {
-      for (int l = tid; l < T0 * T2; l += NT) {
-        const int a0 = l % T0, c = l / T0;
-        const int i3 = min(o2 + c, g.n[2] - 1) + ng;
-        const double vy = __ldg(vel + i3 + (i64)g.nd[2] * (p + (i64)g.nd[3]));
-        const bool pos = vy > 0.0;
-        const double* core = cur + c * T1 * PC + NG + a0;        // + b1*PC
-        const double* hlo = sYh + c * NG * PC + NG + a0;         // + h*PC
-        const double* hhi = hlo + C::NYH;
-        double* racc = sAcc + c * T1 * PA + a0;                  // + b1*PA
-        auto ld = [&](int k) -> double {  // line position k in [0, T1+W)
-          if (k < NG) return hlo[k * PC];
-          if (k < NG + T1) return core[(k - NG) * PC];
-          return hhi[(k - NG - T1) * PC];
-        };
-        Walker<ORDER> wk;
-        wk.init(ld);
-        double uL = wk.next(ld(W - 1), pos);
+          for (int k = 0; k < T1; ++k) v[NG + k] = core[k * PC];
 #pragma unroll
-        for (int b1 = 0; b1 < T1; ++b1) {
-          const double uR = wk.next(ld(b1 + W), pos);
-          racc[b1 * PA] = sub_flux(racc[b1 * PA], vy, uR, uL, g.dx[1], rdx1);
-          uL = uR;
+          for (int k = 0; k < NG; ++k) v[NG + T1 + k] = hhi[k * PC];
+#pragma unroll
+          for (int b1 = 0; b1 < T1; ++b1) acc[b1] = yacc[b1 * PA];
+          Walker<ORDER> wk;
+          wk.init([&](int k) { return v[k]; });
+          double uL = wk.next(v[W - 1], pos);
+#pragma unroll
+          for (int b1 = 0; b1 < T1; ++b1) {
+            const double uR = wk.next(v[b1 + W], pos);
+            acc[b1] = sub_flux(acc[b1], vy, uR, uL, g.dx[1], rdx1);
+            uL = uR;
+          }
+#pragma unroll
+          for (int b1 = 0; b1 < T1; ++b1) yacc[b1 * PA] = acc[b1];
         }
       }
-    }
-    __syncthreads();
-    if (more) stage_yh(p + 1);
+      __syncthreads();
+      if (more) stage_yh(p + 1);
 
-    // ---------------- vx sweep: this thread's column (ea0, eb1), all c ----------------
-    if (TMA) { mbar_wait(&bars[NS + 1], ph_v); ph_v ^= 1u; }
-    double* const racc = sAcc + eb1 * PA + ea0;  // + c*T1*PA: this thread's column of the accumulator
-    {
+      // ---------------- vx sweep: this thread's column (ea0, eb1), all c, kept in registers ----------
+      if (TMA) { mbar_wait(&bars[NS + 1], ph_v); ph_v ^= 1u; }
+      double res[T2];
+#pragma unroll
+      for (int c = 0; c < T2; ++c) res[c] = racc[c * T1 * PA];
       if (do_acc) {
         const double* core = cur + ecell;                          // + c*T1*PC
         const double* hlo = sVh + eb1 * PC + NG + ea0;             // + h*T1*PC
         const double* hhi = hlo + C::NVH;
-        auto ld = [&](int k) -> double {
-          if (k < NG) return hlo[k * T1 * PC];
-          if (k < NG + T2) return core[(k - NG) * T1 * PC];
-          return hhi[(k - NG - T2) * T1 * PC];
-        };
-        const double ax0 = simple_acc ? __ldg(a.field + pxy) : 0.0;
+        double v[T2 + W];
+#pragma unroll
+        for (int k = 0; k < NG; ++k) v[k] = hlo[k * T1 * PC];
+#pragma unroll
+        for (int k = 0; k < T2; ++k) v[NG + k] = core[k * T1 * PC];
+#pragma unroll
+        for (int k = 0; k < NG; ++k) v[NG + T2 + k] = hhi[k * T1 * PC];
         auto AX = [&](int i3) -> double { return simple_acc ? ax0 : accel_x(a, g, ei1, ei2, i3, p); };
         const int i3first = o2 + ng;
         // the face below the first cell was fitted by the cell below it with ITS coefficient, unless
         // that cell is outside the interior (KineticSpeciesF.f:2137-2141)
         const double axl = AX((o2 > 0) ? (i3first - 1) : i3first);
         Walker<ORDER> wk;
-        wk.init(ld);
-        double uL = wk.next(ld(W - 1), axl > 0.0);
+        wk.init([&](int k) { return v[k]; });
+        double uL = wk.next(v[W - 1], axl > 0.0);
 #pragma unroll
         for (int c = 0; c < T2; ++c) {
           const double ax = AX(min(i3first + c, g.n[2] - 1 + ng));
-          const double uR = wk.next(ld(c + W), ax > 0.0);
-          racc[c * T1 * PA] = sub_flux(racc[c * T1 * PA], ax, uR, uL, g.dx[2], rdx2);
+          const double uR = wk.next(v[c + W], ax > 0.0);
+          res[c] = sub_flux(res[c], ax, uR, uL, g.dx[2], rdx2);
           uL = uR;
         }
       }
-    }
 
-    // ---------------- vy face above this plane + epilogue ----------------
-    const int s_new = (p + NG - pbase) % NS;
-    wait_core(s_new);  // always: no TMA write may be outstanding when the CTA exits
-    // EK: epilogue kind, decided once per kernel (uniform) so that the per-cell code carries no pointer
-    // tests.  1..3 = the RK4 stage shapes (RK4Integrator.H:149-171): 1: delta = w*rhs (stage 1);
-    // 2: delta += w*rhs (stages 2,3); 3: pred = f_old + c*(delta + w*rhs), delta not stored (stage 4);
-    // 0: everything decided per cell (RK6, rhs_out, partial evaluations).
-    auto vy_phase = [&](auto ek_tag) {
-      constexpr int EK = decltype(ek_tag)::value;
-      // ring slots of the planes p-NG+2 .. p+NG (w[1..W-1] of the vy fit), this thread's cell
-      const double* wp[W];
+      // ---------------- vy face above this plane + epilogue ----------------
+      const int s_new = (p + NG - pbase) % NS;
+      wait_core(s_new);  // always: no TMA write may be outstanding when the CTA exits
+      {
+        const i64 idx0 = col + g.s[3] * p;
+        const int s2 = (int)g.s[2];
+        const double* velp = vel + o2 + ng + (i64)g.nd[2] * p;
+        const double* fo_p = upd.f_old + idx0;
+        const double* di_p = upd.delta_in + idx0;
+        double* do_p = upd.delta_out + idx0;
+        double* pr_p = upd.pred + idx0;
+        // the RK operands of the whole column first: their latency hides behind the fits.  Out-of-tile
+        // cells read the column's first cell (always addressable) and are never stored.
+        double fo[T2], di[T2];
+        if constexpr (EK != 0) {
 #pragma unroll
-      for (int k = 1; k < W; ++k) wp[k] = sCore + ((sc + k - (NG - 1) + NS) % NS) * C::NCORE + ecell;
-      const double ay0 = (do_acc && simple_acc) ? __ldg(a.field + pxy + (i64)g.nd[0] * g.nd[1]) : 0.0;
-      const i64 idx0 = col + g.s[3] * p;
-      const int s2 = (int)g.s[2];
-      const double* velp = vel + o2 + ng + (i64)g.nd[2] * p;
-      const double* fo_p = upd.f_old + idx0;
-      const double* di_p = upd.delta_in + idx0;
-      double* do_p = upd.delta_out + idx0;
-      double* pr_p = upd.pred + idx0;
-      double psum = 0.0, pvx = 0.0, pvy = 0.0;
-      // the RK operands of the whole column first: their latency hides behind the eight fits
-      double fo[T2], di[T2];
-      if constexpr (EK != 0) {
-#pragma unroll
-        for (int c = 0; c < T2; ++c) {
-          fo[c] = (c < ncv) ? fo_p[c * s2] : 0.0;
-          di[c] = (EK >= 2 && c < ncv) ? di_p[c * s2] : 0.0;
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < T2; ++c) {
-        double res = racc[c * T1 * PA];
-        if (do_acc) {
-          double w[W];
-          w[0] = uold[c];
-#pragma unroll
-          for (int k = 1; k < W; ++k) w[k] = wp[k][c * T1 * PC];
-          const double ay = simple_acc ? ay0 : accel_y(a, g, ei1, ei2, min(o2 + c, g.n[2] - 1) + ng, p);
-          const double F = fit_face<ORDER>(w, ay > 0.0);
-          res = sub_flux(res, ay, F, Fprev[c], g.dx[3], rdx3);
-          Fprev[c] = F;
-          uold[c] = w[1];
-        }
-        if (c < ncv) {
-          const int oc = c * s2;
-          double pr;
-          if constexpr (EK == 1) {
-            do_p[oc] = rk_delta(upd, res, 0.0, false);
-            pr = rk_axpy(fo[c], upd.c_pred, res);
-          } else if constexpr (EK == 2) {
-            do_p[oc] = rk_delta(upd, res, di[c], true);
-            pr = rk_axpy(fo[c], upd.c_pred, res);
-          } else if constexpr (EK == 3) {
-            pr = rk_axpy(fo[c], upd.c_pred, rk_delta(upd, res, di[c], true));
-          } else {
-            const i64 idx = idx0 + oc;
-            if (rhs_out) rhs_out[idx] = res;
-            if (!upd.active) continue;
-            const double dl = rk_delta(upd, res, upd.delta_in ? upd.delta_in[idx] : 0.0, upd.delta_in != nullptr);
-            if (upd.delta_out) upd.delta_out[idx] = dl;
-            pr = rk_pred(upd, upd.f_old[idx], upd.use_delta ? dl : res, idx);
+          for (int c = 0; c < T2; ++c) {
+            const int oc = (c < ncv) ? c * s2 : 0;
+            fo[c] = (ncv > 0) ? fo_p[oc] : 0.0;
+            di[c] = (EK >= 2 && ncv > 0) ? di_p[oc] : 0.0;
           }
-          pr_p[oc] = pr;
-          if (mom.nmom > 0) {
-            psum = ADD(psum, pr);
-            if (mom.nmom > 1) {
-              pvx = FMA(__ldg(velp + c), pr, pvx);
-              pvy = FMA(__ldg(velp + c + (i64)g.nd[2] * g.nd[3]), pr, pvy);
+        }
+        if (do_acc) {
+          // ring slots of the planes p-NG+2 .. p+NG (w[1..W-1] of the vy fit), this thread's cell
+          const double* wp[W];
+#pragma unroll
+          for (int k = 1; k < W; ++k) wp[k] = sCore + ((sc + k - (NG - 1) + NS) % NS) * C::NCORE + ecell;
+#pragma unroll
+          for (int c = 0; c < T2; ++c) {
+            double w[W];
+            w[0] = uold[c];
+#pragma unroll
+            for (int k = 1; k < W; ++k) w[k] = wp[k][c * T1 * PC];
+            const double ay = simple_acc ? ay0 : accel_y(a, g, ei1, ei2, min(o2 + c, g.n[2] - 1) + ng, p);
+            const double F = fit_face<ORDER>(w, ay > 0.0);
+            res[c] = sub_flux(res[c], ay, F, Fprev[c], g.dx[3], rdx3);
+            Fprev[c] = F;
+            uold[c] = w[1];
+          }
+        }
+        double psum = 0.0, pvx = 0.0, pvy = 0.0;
+        if constexpr (EK != 0) {
+          // branch-free: every cell computes, only the stores and the moment terms are predicated
+#pragma unroll
+          for (int c = 0; c < T2; ++c) {
+            const bool live = c < ncv;
+            const int oc = c * s2;
+            double pr;
+            if constexpr (EK == 1) {
+              const double dl = rk_delta(upd, res[c], 0.0, false);
+              if (live) do_p[oc] = dl;
+              pr = rk_axpy(fo[c], upd.c_pred, res[c]);
+            } else if constexpr (EK == 2) {
+              const double dl = rk_delta(upd, res[c], di[c], true);
+              if (live) do_p[oc] = dl;
+              pr = rk_axpy(fo[c], upd.c_pred, res[c]);
+            } else {
+              pr = rk_axpy(fo[c], upd.c_pred, rk_delta(upd, res[c], di[c], true));
+            }
+            if (live) pr_p[oc] = pr;
+            if (mom.nmom > 0) {
+              const double prm = live ? pr : 0.0;
+              psum = ADD(psum, prm);
+              if (mom.nmom > 1) {
+                pvx = FMA(__ldg(velp + min(c, max(ncv - 1, 0))), prm, pvx);
+                pvy = FMA(__ldg(velp + min(c, max(ncv - 1, 0)) + (i64)g.nd[2] * g.nd[3]), prm, pvy);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < T2; ++c) {
+            if (c < ncv) {
+              const i64 idx = idx0 + c * s2;
+              if (rhs_out) rhs_out[idx] = res[c];
+              if (!upd.active) continue;
+              const double dl = rk_delta(upd, res[c], upd.delta_in ? upd.delta_in[idx] : 0.0, upd.delta_in != nullptr);
+              if (upd.delta_out) upd.delta_out[idx] = dl;
+              const double pr = rk_pred(upd, upd.f_old[idx], upd.use_delta ? dl : res[c], idx);
+              pr_p[c * s2] = pr;
+              if (mom.nmom > 0) {
+                psum = ADD(psum, pr);
+                if (mom.nmom > 1) {
+                  pvx = FMA(__ldg(velp + c), pr, pvx);
+                  pvy = FMA(__ldg(velp + c + (i64)g.nd[2] * g.nd[3]), pr, pvy);
+                }
+              }
             }
           }
         }
-      }
-      if (mom.nmom > 0) {
-        m0 = ADD(m0, psum);
-        if (mom.nmom > 1) {
-          m1 = ADD(m1, pvx);
-          m2 = ADD(m2, pvy);
+        if (mom.nmom > 0) {
+          m0 = ADD(m0, psum);
+          if (mom.nmom > 1) {
+            m1 = ADD(m1, pvx);
+            m2 = ADD(m2, pvy);
+          }
         }
       }
-    };
-    if (ekind == 1) vy_phase(IntTag<1>{});
-    else if (ekind == 2) vy_phase(IntTag<2>{});
-    else if (ekind == 3) vy_phase(IntTag<3>{});
-    else vy_phase(IntTag<0>{});
-    __syncthreads();
-    if (more) {
-      stage_vh(p + 1);
-      stage_core(p + NG + 1, (p + NG + 1 - pbase) % NS);
+      __syncthreads();
+      if (more) {
+        stage_vh(p + 1);
+        stage_core(p + NG + 1, (p + NG + 1 - pbase) % NS);
+      }
     }
-  }
+  };
+  if (ekind == 1) march(IntTag<1>{});
+  else if (ekind == 2) march(IntTag<2>{});
+  else if (ekind == 3) march(IntTag<3>{});
+  else march(IntTag<0>{});
 
   if (mom.nmom > 0 && col_ok) {
     const i64 nxy = (i64)g.n[0] * g.n[1];

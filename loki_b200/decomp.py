@@ -1,0 +1,228 @@
+"""Configuration-space decomposition over the GPUs of one box and the per-stage exchanges.
+
+The reference block-decomposes all four dimensions over MPI ranks (ParallelArray.C:545-569) and
+exchanges ghost slabs with packed MPI messages (ParallelArray.C:925-1113); the charge density is an
+MPI_Reduce over the ranks sharing an (x,y) tile (ReductionSchedule.C:69-113) and every Poisson rank
+solves the same global 2D problem (EMSolverBase.C:301-345).  Here only (x,y) is cut, the
+velocity space stays whole on each GPU, so per stage a rank
+
+  1. all-gathers its rho tile (2D, a few hundred KB),
+  2. swaps `ng` layers of f with its x neighbours, then with its y neighbours (periodic wrap is an
+     ordinary neighbour; axis-aligned stencils need no corner messages),
+
+one process per GPU over torch.distributed (NCCL on the box, gloo in the CPU tests).  This module is the
+host logic only: tile arithmetic, neighbour ranks, message ordering.  Packing, unpacking and everything
+else that touches 4D data are CUDA kernels behind the C ABI (lk_halo_pack / lk_halo_unpack); the
+exchanger takes them as callables so the CPU tests can drive the same message logic on host arrays.
+"""
+import ctypes as C
+
+
+def split_extent(n, parts):
+    """Sub-box rule of ParallelArray.C:642-660: n // parts cells each, the remainder one extra cell to the
+    lowest-index tiles.  Returns [(lo, count)]."""
+    if parts < 1 or n < parts:
+        raise ValueError("cannot cut %d cells into %d tiles" % (n, parts))
+    base, extra = divmod(n, parts)
+    out, lo = [], 0
+    for k in range(parts):
+        cnt = base + (1 if k < extra else 0)
+        out.append((lo, cnt))
+        lo += cnt
+    return out
+
+
+class TileLayout:
+    """px x py process grid over a global Nx x Ny configuration space; rank = ry * px + rx."""
+
+    def __init__(self, nglobal, px, py, min_tile=1):
+        self.nglobal, self.px, self.py = (int(nglobal[0]), int(nglobal[1])), int(px), int(py)
+        self.xs = split_extent(self.nglobal[0], self.px)
+        self.ys = split_extent(self.nglobal[1], self.py)
+        for lo, cnt in self.xs + self.ys:
+            if cnt < min_tile:
+                # stencil_width = order + 1 is the minimum interior extent per tile (KineticSpecies.C:495-504)
+                raise ValueError("tile extent %d is below the minimum %d" % (cnt, min_tile))
+
+    @property
+    def world(self):
+        return self.px * self.py
+
+    def coords(self, rank):
+        return rank % self.px, rank // self.px
+
+    def rank_of(self, rx, ry):
+        return (ry % self.py) * self.px + (rx % self.px)
+
+    def tile(self, rank):
+        """(lo_x, lo_y, n_x, n_y) of the rank's interior"""
+        rx, ry = self.coords(rank)
+        return self.xs[rx][0], self.ys[ry][0], self.xs[rx][1], self.ys[ry][1]
+
+    def tiles_flat(self):
+        out = []
+        for r in range(self.world):
+            out += list(self.tile(r))
+        return out
+
+    def neighbours(self, rank, direction):
+        """(low, high) neighbour ranks along x (0) or y (1), periodic"""
+        rx, ry = self.coords(rank)
+        if direction == 0:
+            return self.rank_of(rx - 1, ry), self.rank_of(rx + 1, ry)
+        return self.rank_of(rx, ry - 1), self.rank_of(rx, ry + 1)
+
+    def cut(self, direction):
+        return (self.px if direction == 0 else self.py) > 1
+
+    def uniform(self):
+        return len({c for _, c in self.xs}) == 1 and len({c for _, c in self.ys}) == 1
+
+
+def grid_for(world):
+    """Process grids used on one box: cut y first (x is the contiguous axis, so y slabs are long runs)."""
+    return {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}[world]
+
+
+class HaloExchanger:
+    """x-then-y face exchange of one 4D array.
+
+    pack(buf, side, direction)   -- fill `buf` with the `ng` interior layers next to face `side` (0 low, 1 high)
+    unpack(buf, side, direction) -- write `buf` into the ghost layers of face `side`
+    local_fill(direction)        -- periodic wrap inside the array (that direction is not cut)
+    bufs[direction] = (send_lo, send_hi, recv_lo, recv_hi) tensors on the communication device.
+    The y exchange runs after the x exchange has been unpacked and its messages span the x ghosts, which
+    is how the edge/corner cells get their values (ParallelArray.H:580-606 orders its periodic copies the
+    same way).
+    """
+
+    def __init__(self, layout, rank, dist):
+        self.layout, self.rank, self.dist = layout, rank, dist
+
+    def exchange(self, bufs, pack, unpack, local_fill):
+        dist = self.dist
+        for d in (0, 1):
+            if not self.layout.cut(d):
+                local_fill(d)
+                continue
+            slo, shi, rlo, rhi = bufs[d]
+            lo_n, hi_n = self.layout.neighbours(self.rank, d)
+            pack(slo, 0, d)
+            pack(shi, 1, d)
+            ops = [dist.P2POp(dist.isend, slo, lo_n, tag=2 * d), dist.P2POp(dist.isend, shi, hi_n, tag=2 * d + 1),
+                   # my high ghosts are my high neighbour's low interior layers (its send_lo) and vice versa
+                   dist.P2POp(dist.irecv, rhi, hi_n, tag=2 * d), dist.P2POp(dist.irecv, rlo, lo_n, tag=2 * d + 1)]
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            unpack(rlo, 0, d)
+            unpack(rhi, 1, d)
+
+
+class DistributedVP:
+    """The stage loop of RK4Integrator / RK6Integrator (RK4Integrator.H:66-171) around the C++ host
+    mirror when configuration space is cut over several ranks: lk_vp_* stage pieces with the two
+    exchanges between them (include/loki_b200_host.h documents the protocol)."""
+
+    def __init__(self, deck, layout, rank, device, stream, dist=None):
+        import torch
+        from . import capi, host
+        self.torch, self.dist = torch, dist
+        self.L, self.H = capi.load(), host.lib()
+        self.deck, self.layout, self.rank, self.device = deck, layout, rank, device
+        self.stream = C.c_void_p(stream)
+        lo_x, lo_y, n_x, n_y = layout.tile(rank)
+        self.tile_lo, self.tile_n = (lo_x, lo_y), (n_x, n_y)
+        self.desc = deck.product_desc(tile_lo=self.tile_lo, tile_n=self.tile_n, ntiles=layout.world)
+        self.sys = C.c_void_p()
+        capi.check(self.H.lk_vp_create(C.byref(self.sys), C.byref(self.desc), self.stream), "lk_vp_create")
+        self.nsp = len(deck.species)
+        self.geoms = []
+        for s in range(self.nsp):
+            g = capi.Geom()
+            self.H.lk_vp_species_geom(self.sys, s, C.byref(g))
+            self.geoms.append(g)
+        self.world = layout.world
+        if self.world > 1:
+            if dist is None:
+                raise ValueError("a cut layout needs torch.distributed")
+            flat = layout.tiles_flat()
+            self.tiles_arr = (C.c_int * len(flat))(*flat)
+            cells = [flat[4 * r + 2] * flat[4 * r + 3] for r in range(self.world)]
+            self.tile_cells, self.max_cells = cells, max(cells)
+            f64 = torch.float64
+            self.rho_tile = torch.zeros(self.max_cells, dtype=f64, device=device)
+            self.rho_gather = torch.zeros(sum(cells), dtype=f64, device=device)
+            self.rho_padded = None if layout.uniform() else torch.zeros(self.world * self.max_cells, dtype=f64, device=device)
+            capi.check(self.H.lk_vp_set_comm_buffers(self.sys, self.rho_tile.data_ptr(), self.rho_gather.data_ptr()),
+                       "lk_vp_set_comm_buffers")
+            self.exchanger = HaloExchanger(layout, rank, dist)
+            self.halo = []
+            for s in range(self.nsp):
+                bufs = {}
+                for d in (0, 1):
+                    cnt = self.L.lk_halo_count(C.byref(self.geoms[s]), d)
+                    bufs[d] = [torch.empty(cnt, dtype=f64, device=device) for _ in range(4)]
+                self.halo.append(bufs)
+            self.lam = torch.zeros(2 * self.nsp, dtype=f64, device=device)
+
+    def close(self):
+        if self.sys:
+            self.H.lk_vp_destroy(self.sys)
+            self.sys = C.c_void_p()
+
+    @property
+    def nstages(self):
+        return self.H.lk_vp_nstages(self.sys)
+
+    def state_ptr(self, s):
+        return self.H.lk_vp_state_ptr(self.sys, s)
+
+    def _exchange_halos(self):
+        L, st = self.L, self.stream
+        for s in range(self.nsp):
+            f = self.H.lk_vp_eval_ptr(self.sys, s)
+            g = C.byref(self.geoms[s])
+            self.exchanger.exchange(
+                self.halo[s],
+                lambda buf, side, d: L.lk_halo_pack(buf.data_ptr(), f, g, d, side, st),
+                lambda buf, side, d: L.lk_halo_unpack(f, buf.data_ptr(), g, d, side, st),
+                lambda d: L.lk_periodic_fill_4d(f, g, int(d == 0), int(d == 1), st))
+
+    def _gather_rho(self):
+        dist = self.dist
+        if self.rho_padded is None:
+            dist.all_gather_into_tensor(self.rho_gather, self.rho_tile)
+        else:
+            dist.all_gather_into_tensor(self.rho_padded, self.rho_tile)
+            off = 0
+            for r, cnt in enumerate(self.tile_cells):
+                self.rho_gather[off:off + cnt].copy_(self.rho_padded[r * self.max_cells:r * self.max_cells + cnt])
+                off += cnt
+
+    def advance(self, dt):
+        from . import capi
+        H = self.H
+        if self.world == 1:
+            capi.check(H.lk_vp_advance(self.sys, dt), "lk_vp_advance")
+            return
+        capi.check(H.lk_vp_begin_step(self.sys, dt), "lk_vp_begin_step")
+        for stage in range(self.nstages):
+            capi.check(H.lk_vp_stage_moments(self.sys, stage), "lk_vp_stage_moments")
+            self._gather_rho()
+            capi.check(H.lk_vp_stage_field(self.sys, stage, self.tiles_arr), "lk_vp_stage_field")
+            self._exchange_halos()
+            capi.check(H.lk_vp_stage_finish(self.sys, stage), "lk_vp_stage_finish")
+        capi.check(H.lk_vp_end_step(self.sys), "lk_vp_end_step")
+
+    def stable_dt(self):
+        """KineticSpecies::computeDt over all ranks: the velocity-space maxima (axmax, aymax) are maxima over
+        the local tile, so the stable step is the minimum over ranks (the reference all-reduces the same
+        way, Simulation.C:465-485 through Loki_Utilities::getMinValue)."""
+        from . import capi
+        dt = C.c_double()
+        capi.check(self.H.lk_vp_stable_dt(self.sys, C.byref(dt)), "lk_vp_stable_dt")
+        if self.world > 1:
+            t = self.torch.tensor([dt.value], dtype=self.torch.float64, device=self.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+            return float(t.item())
+        return dt.value

@@ -1,74 +1,14 @@
-"""Deck-shaped problem set-ups for the system-level parity tests: the numbers of the reference's
-regression decks (test/*/*.pp), with the configuration-space and velocity grids shrunk where stated.
-Initial conditions restate PerturbedMaxwellianIC (PerturbedMaxwellianIC.C:95-289, factorable branch,
-ic_option 1) and MaxwellianThermal (MaxwellianThermal.C:16-60) with numpy.  Test infrastructure."""
-import ctypes as C
-import math
+"""Deck set-ups for the system-level parity tests: loki_b200.decks (the product-side deck mirror) plus
+the oracle-side adapter (species descriptors with the IC as a point callback, the way the reference's
+Fortran calls back into ICInterface.C:36-57).  Test infrastructure."""
+import ctypes as C  # noqa: F401
 
-import numpy as np
-
+from loki_b200 import decks as _d
+from loki_b200.decks import Species, driver_params, PI  # noqa: F401
 from oracle_binding import OkGeom, OkSpecies, IC_FN
 
 
-class Species:
-    def __init__(self, name, nv, vlim, mass, charge, tx=1.0, ty=1.0, A=0.0, B=0.0, Cc=0.0, kx1=0.0, ky1=0.0,
-                 kx2=0.0, ky2=0.0, frac=1.0, driver=None, bz=0.0):
-        self.name, self.nv, self.vlim, self.mass, self.charge = name, nv, vlim, mass, charge
-        self.tx, self.ty, self.A, self.B, self.Cc = tx, ty, A, B, Cc
-        self.kx1, self.ky1, self.kx2, self.ky2, self.frac = kx1, ky1, kx2, ky2, frac
-        self.driver, self.bz = driver, bz
-
-
-def driver_params(xwidth, ywidth, shape, omega, E0, t_ramp, t_off, x_shape, lwidth, x0, t0=0.0):
-    """ShapedRampedCosineDriver parameter vector in enum order, old t_ramp/t_off syntax
-    (ShapedRampedCosineDriver.C:306-311)."""
-    p = [0.0] * 16
-    p[0], p[1], p[2], p[3], p[4], p[5] = xwidth, ywidth, shape, omega, E0, t0
-    p[6], p[7], p[8] = t_ramp, 0.0, t_off
-    p[9], p[10], p[11], p[12], p[13] = x_shape, lwidth, x0, 0.0, 0.0
-    return p
-
-
-class Deck:
-    def __init__(self, name, n, xlim, species, order=4, rk=4, cfl=1.0):
-        self.name, self.n, self.xlim, self.species, self.order, self.rk, self.cfl = name, n, xlim, species, order, rk, cfl
-        self.ng = 2 if order == 4 else 3
-        self.dx = ((xlim[1] - xlim[0]) / n[0], (xlim[3] - xlim[2]) / n[1])
-
-    def geom_of(self, sp):
-        dvx = (sp.vlim[1] - sp.vlim[0]) / sp.nv[0]
-        dvy = (sp.vlim[3] - sp.vlim[2]) / sp.nv[1]
-        return (self.n[0], self.n[1], sp.nv[0], sp.nv[1]), (self.dx[0], self.dx[1], dvx, dvy)
-
-    def ic_tables(self, sp, tile_lo=(0, 0), tile_n=None):
-        """fx (n2d,n1d), fv (n4d,n3d), fnorm -- PerturbedMaxwellianIC::cache, factorable, ic_option 1"""
-        ng = self.ng
-        tile_n = tile_n or self.n
-        n, dx = self.geom_of(sp)
-        xlo, ylo = self.xlim[0], self.xlim[2]
-        Lx, Ly = self.n[0] * dx[0], self.n[1] * dx[1]
-        i1 = np.arange(-ng, tile_n[0] + ng) + tile_lo[0]
-        i2 = np.arange(-ng, tile_n[1] + ng) + tile_lo[1]
-        x1 = xlo + (i1 + 0.5) * dx[0]
-        x2 = ylo + (i2 + 0.5) * dx[1]
-        x1 = np.where(x1 < self.xlim[0], x1 + Lx, np.where(x1 > self.xlim[1], x1 - Lx, x1))
-        x2 = np.where(x2 < self.xlim[2], x2 + Ly, np.where(x2 > self.xlim[3], x2 - Ly, x2))
-        phi = 0.0
-        fx = (1.0 + sp.A * np.cos(sp.kx1 * x1 + phi)[None, :] * np.cos(sp.ky1 * x2 + phi)[:, None] +
-              sp.B * np.cos(sp.kx2 * x1 + phi)[None, :] + sp.Cc * np.cos(sp.ky2 * x2 + phi)[:, None])
-        x3 = sp.vlim[0] + (np.arange(-ng, sp.nv[0] + ng) + 0.5) * dx[2]
-        x4 = sp.vlim[2] + (np.arange(-ng, sp.nv[1] + ng) + 0.5) * dx[3]
-        thx, thy = sp.tx / sp.mass, sp.ty / sp.mass
-        fv = np.exp(-0.5 * ((x3 ** 2)[None, :] / thx + (x4 ** 2)[:, None] / thy))
-        fnorm = sp.mass / (2.0 * math.pi * math.sqrt(sp.tx * sp.ty))
-        return np.ascontiguousarray(fx), np.ascontiguousarray(fv), fnorm
-
-    def initial_state(self, sp, tile_lo=(0, 0), tile_n=None):
-        fx, fv, fnorm = self.ic_tables(sp, tile_lo, tile_n)
-        # getIC_At_Pt: fnorm*fv*fx*frac in this order (PerturbedMaxwellianIC.C:279-281)
-        f = ((fnorm * fv)[:, :, None, None] * fx[None, None, :, :]) * sp.frac
-        return np.ascontiguousarray(f), fx, fv, fnorm
-
+class Deck(_d.Deck):
     # ---- oracle side ----
     def oracle_species(self, keep):
         arr = (OkSpecies * len(self.species))()
@@ -94,53 +34,15 @@ class Deck:
             arr[k].driver_shape_type = 0
         return arr
 
-    # ---- product side ----
-    def product_desc(self, tile_lo=(0, 0), tile_n=None, ntiles=1):
-        from loki_b200.host import SpeciesDesc, VPDesc
-        tile_n = tile_n or self.n
-        sd = (SpeciesDesc * len(self.species))()
-        for k, sp in enumerate(self.species):
-            sd[k].nv[0], sd[k].nv[1] = sp.nv
-            sd[k].vlo[0], sd[k].vlo[1] = sp.vlim[0], sp.vlim[2]
-            sd[k].vhi[0], sd[k].vhi[1] = sp.vlim[1], sp.vlim[3]
-            sd[k].mass, sd[k].charge, sd[k].bz_const = sp.mass, sp.charge, sp.bz
-            sd[k].has_driver = 1 if sp.driver else 0
-            if sp.driver:
-                for j in range(16):
-                    sd[k].driver[j] = sp.driver[j]
-            sd[k].driver_phase, sd[k].driver_shape_type = 0.0, 0
-        d = VPDesc()
-        d.nspecies, d.species, d.order, d.rk_order = len(self.species), sd, self.order, self.rk
-        d.nglobal[0], d.nglobal[1] = self.n
-        d.xlo[0], d.xlo[1] = self.xlim[0], self.xlim[2]
-        d.xhi[0], d.xhi[1] = self.xlim[1], self.xlim[3]
-        d.tile_lo[0], d.tile_lo[1] = tile_lo
-        d.tile_n[0], d.tile_n[1] = tile_n
-        d.ntiles = ntiles
-        d._keep = sd
-        return d
+
+def _wrap(d):
+    d.__class__ = Deck
+    return d
 
 
-PI = 3.1415926535897932384626
+def plane_epw(*a, **k):
+    return _wrap(_d.plane_epw(*a, **k))
 
 
-def plane_epw(n=(32, 32), nv=(128, 32), A=0.0):
-    """test/planeEPW_fixedIons/planeEPW_fixedIons.pp: one electron species, driven, order 4 / RK4"""
-    xa, xb, ya, yb = -3 * PI, 3 * PI, -78 * PI, 78 * PI
-    drv = driver_params(xwidth=(xb - xa) / 2.0, ywidth=300 * PI, shape=0.0, omega=1.2001, E0=0.01, t_ramp=10.0,
-                        t_off=10.0, x_shape=0.0, lwidth=50.0, x0=0.0)
-    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, A=A, kx1=1.0 / 3, ky1=1.0 / 78, driver=drv)
-    return Deck("planeEPW_fixedIons", n, (xa, xb, ya, yb), [e], order=4, rk=4)
-
-
-def plane_iaw(n=(32, 32), nv=(64, 32), order=4, rk=4, A=0.0):
-    """test/planeIAW/planeIAW.pp (order 4 / RK4) and test/planeIAW_6 (order 6 / RK6): electrons + ions"""
-    klde = 1.0 / 3
-    ialpha = math.sqrt(10.0) * math.sqrt(100.0)
-    xa, xb, ya, yb = -PI / klde, PI / klde, -78 * PI / klde, 78 * PI / klde
-    drv = driver_params(xwidth=(xb - xa) / 2.0, ywidth=300 * PI, shape=0.0, omega=0.0381, E0=0.1, t_ramp=1.0,
-                        t_off=2.0, x_shape=0.0, lwidth=50.0, x0=0.0)
-    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, A=A, kx1=klde, ky1=klde / 78, driver=drv)
-    i = Species("ion", nv, (-10 / ialpha, 10 / ialpha, -10 / ialpha, 10 / ialpha), 100.0, 1.0, tx=0.1, ty=0.1,
-                A=A, kx1=klde, ky1=klde / 78)
-    return Deck("planeIAW" + ("_6" if order == 6 else ""), n, (xa, xb, ya, yb), [e, i], order=order, rk=rk)
+def plane_iaw(*a, **k):
+    return _wrap(_d.plane_iaw(*a, **k))
