@@ -26,7 +26,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 TILE = (256, 256)
 NV = (128, 128)
@@ -53,6 +52,7 @@ def config_dict(n_gpus):
 # ------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
     n, order, reps = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))  # the oracle binding is test infrastructure
     import oracle_binding
     ok = oracle_binding.load()
     g = oracle_binding.OkGeom.make(n, order, (0.07, 0.07, 0.1, 0.1))
@@ -60,7 +60,7 @@ def _cpu_worker(args):
     return sec
 
 
-def cpu_leg(reps=4, box=(32, 32, 32, 32), cores=None):
+def cpu_leg(reps=4, box=(32, 32, 64, 64), cores=None):
     """every core owns an independent periodic sub-box (the way the reference's MPI ranks each own a
     ParallelArray block) and runs `reps` RK4 stages done the reference's way (separate sweeps,
     materialised vel3/vel4, unfused zero/copy/axpy, separate velocity reduction)."""
@@ -160,8 +160,7 @@ def run_own(args):
     import torch
     import torch.distributed as dist
     import loki_b200
-    from loki_b200 import host
-    import decks
+    from loki_b200 import decks, decomp, host
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -181,24 +180,16 @@ def run_own(args):
         raise SystemExit("no CUDA device: the hot path has no CPU fallback")
     L.lk_set_strict(0)
     px, py = GRIDS[args.gpus]
-    rx, ry = rank % px, rank // px
     tile = TILE if not args.small else (32, 32)
     nv = NV if not args.small else (32, 32)
     deck = decks.plane_iaw(n=(tile[0] * px, tile[1] * py), nv=nv, order=ORDER, rk=RK)
-    tile_lo = (rx * tile[0], ry * tile[1])
-    desc = deck.product_desc(tile_lo=tile_lo, tile_n=tile, ntiles=world)
+    layout = decomp.TileLayout(deck.n, px, py, min_tile=ORDER + 1)
     stream = torch.cuda.current_stream().cuda_stream
-    sys_ = C.c_void_p()
-    st = H.lk_vp_create(C.byref(sys_), C.byref(desc), C.c_void_p(stream))
-    if st != 0:
-        raise SystemExit("lk_vp_create failed: %s" % L.lk_last_error().decode())
-    ng = deck.ng
-    nsp = len(deck.species)
-    geoms = []
-    for s in range(nsp):
-        g = loki_b200.Geom()
-        H.lk_vp_species_geom(sys_, s, C.byref(g))
-        geoms.append(g)
+    vp = decomp.DistributedVP(deck, layout, rank, dev, stream, dist if world > 1 else None)
+    sys_ = vp.sys
+    tile_lo = vp.tile_lo
+    nsp = vp.nsp
+    geoms = vp.geoms
     vols = [int(np.prod(g.nd)) for g in geoms]
     cells_rank = sum(int(np.prod([g.n[k] for k in range(4)])) for g in geoms)
 
@@ -221,67 +212,12 @@ def run_own(args):
         assert f.numel() == vols[s]
         torch.cuda.synchronize()
         # device-to-device copy into the library-owned state array
-        dst = H.lk_vp_state_ptr(sys_, s)
-        t_dst = _wrap(dst, vols[s], dev)
+        t_dst = _wrap(vp.state_ptr(s), vols[s], dev)
         t_dst.copy_(f.view(-1))
         del f
     torch.cuda.synchronize()
 
-    # ---- multi-rank plumbing (torch.distributed over NCCL) ----
-    tiles_arr = None
-    halo = None
-    if world > 1:
-        tiles = []
-        for r in range(world):
-            tiles += [(r % px) * tile[0], (r // px) * tile[1], tile[0], tile[1]]
-        tiles_arr = (C.c_int * len(tiles))(*tiles)
-        rho_tile = torch.zeros(tile[0] * tile[1], dtype=torch.float64, device=dev)
-        rho_gather = torch.zeros(world * tile[0] * tile[1], dtype=torch.float64, device=dev)
-        assert H.lk_vp_set_comm_buffers(sys_, rho_tile.data_ptr(), rho_gather.data_ptr()) == 0
-        halo = []
-        for s in range(nsp):
-            bufs = {}
-            for d in (0, 1):
-                cnt = L.lk_halo_count(C.byref(geoms[s]), d)
-                bufs[d] = [torch.empty(cnt, dtype=torch.float64, device=dev) for _ in range(4)]  # send lo/hi, recv lo/hi
-            halo.append(bufs)
-        nbr = {0: (ry * px + (rx - 1) % px, ry * px + (rx + 1) % px),
-               1: (((ry - 1) % py) * px + rx, ((ry + 1) % py) * px + rx)}
-
-    def exchange_halos():
-        for s in range(nsp):
-            f = H.lk_vp_eval_ptr(sys_, s)
-            g = C.byref(geoms[s])
-            for d in (0, 1):
-                slo, shi, rlo, rhi = halo[s][d]
-                lo_n, hi_n = nbr[d]
-                if (px if d == 0 else py) == 1:
-                    L.lk_periodic_fill_4d(f, g, int(d == 0), int(d == 1), C.c_void_p(stream))
-                    continue
-                L.lk_halo_pack(slo.data_ptr(), f, g, d, 0, C.c_void_p(stream))
-                L.lk_halo_pack(shi.data_ptr(), f, g, d, 1, C.c_void_p(stream))
-                ops = [dist.P2POp(dist.isend, slo, lo_n), dist.P2POp(dist.isend, shi, hi_n),
-                       dist.P2POp(dist.irecv, rhi, hi_n), dist.P2POp(dist.irecv, rlo, lo_n)]
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
-                # my low ghosts come from my low neighbour's high interior layers
-                L.lk_halo_unpack(f, rlo.data_ptr(), g, d, 0, C.c_void_p(stream))
-                L.lk_halo_unpack(f, rhi.data_ptr(), g, d, 1, C.c_void_p(stream))
-
-    def step(dt):
-        if world == 1:
-            st = H.lk_vp_advance(sys_, dt)
-            assert st == 0, L.lk_last_error()
-            return
-        H.lk_vp_begin_step(sys_, dt)
-        for stage in range(H.lk_vp_nstages(sys_)):
-            H.lk_vp_stage_moments(sys_, stage)
-            dist.all_gather_into_tensor(rho_gather, rho_tile)
-            H.lk_vp_stage_field(sys_, stage, tiles_arr)
-            exchange_halos()
-            st = H.lk_vp_stage_finish(sys_, stage)
-            assert st == 0, L.lk_last_error()
-        H.lk_vp_end_step(sys_)
+    step = vp.advance
 
     def barrier():
         torch.cuda.synchronize()
@@ -379,7 +315,7 @@ def run_own(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_leg(reps=4)
+        cpu = cpu_leg(reps=8)
         cpu.pop("_per_stage_s", None)
 
     if rank == 0:
@@ -392,7 +328,7 @@ def run_own(args):
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
-    H.lk_vp_destroy(sys_)
+    vp.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -36,13 +36,20 @@ struct MarchCfg {
   static constexpr int NCORE = PC * T1 * T2;
   static constexpr int NYH = PC * NG * T2;  // one side
   static constexpr int NVH = PC * T1 * NG;  // one side
-  static constexpr int NACC = PA * T1 * T2;
-  static constexpr int SMEM_DOUBLES = NS * NCORE + 2 * NYH + 2 * NVH + NACC;
-  static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES + 8 * (NS + 2);
+  // RK operand tiles (f_old, delta_in) staged by TMA: the box starts on a 16-byte boundary of the row
+  // (x = o0 + OPX, OPX even) and is OPW wide; the tile's first cell sits OPO elements into it
+  static constexpr int OPX = NG & ~1, OPO = NG & 1, OPW = T0 + 2 * OPO;
+  static constexpr int NOP = OPW * T1 * T2;
+  static constexpr int NACC = (PA * T1 * T2 > NOP) ? PA * T1 * T2 : NOP;  // accumulator, then f_old tile
+  // sAcc doubles as the landing zone of the f_old tile (TMA, once the accumulator has been read into
+  // registers); NACC more doubles hold the delta_in tile
+  static constexpr int SMEM_DOUBLES = NS * NCORE + 2 * NYH + 2 * NVH + 2 * NACC;
+  static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES + 8 * (NS + 3);
 };
 
 struct MarchMaps {
-  CUtensorMap core, yh, vh;
+  CUtensorMap core, yh, vh;  // boxes of the array being differentiated
+  CUtensorMap fo, di;        // dense tile boxes of the RK operands f_old and delta_in
 };
 // velocity moments of the predictor written by the epilogue: part[(m * nparts + p) * n0 * n1 + x + n0 * y],
 // p = chunk * nt2 + (vx tile); m = 0: sum f, 1: sum vx f, 2: sum vy f
@@ -153,7 +160,8 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
   double* sYh = sCore + NS * C::NCORE;        // [side][c][h][PC]
   double* sVh = sYh + 2 * C::NYH;             // [side][h][b1][PC]
   double* sAcc = sVh + 2 * C::NVH;            // [c][b1][PA]
-  unsigned long long* bars = (unsigned long long*)(sAcc + C::NACC);  // NS core barriers, y, v
+  double* sDi = sAcc + C::NACC;               // [c][b1][PA]  delta_in of the plane being updated
+  unsigned long long* bars = (unsigned long long*)(sDi + C::NACC);  // NS core barriers, y, v, RK operands
 
   const int tid = threadIdx.x;
   int b = blockIdx.x;
@@ -217,7 +225,7 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
       coop_box(sVh + C::NVH, X0, Y0, V0 + T2, p, T1, NG);
     }
   };
-  unsigned ph_core = 0, ph_y = 0, ph_v = 0;  // phase parities (bit per core slot)
+  unsigned ph_core = 0, ph_y = 0, ph_v = 0, ph_o = 0;  // phase parities (bit per core slot)
   auto wait_core = [&](int slot) {
     if (TMA) {
       mbar_wait(&bars[slot], (ph_core >> slot) & 1u);
@@ -227,7 +235,7 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
 
   if (TMA) {
     if (tid == 0) {
-      for (int k = 0; k < NS + 2; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[k])));
+      for (int k = 0; k < NS + 3; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[k])));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -294,8 +302,12 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
   // Every sweep loads its whole line into registers BEFORE the first fit and stores after the last: no
   // shared-memory store sits between the loads, so the W+T fits of a line are independent instruction
   // streams the scheduler can interleave (the fp64 dependent-issue latency is what bounds this kernel).
-  auto march = [&](auto ek_tag) {
+  // RK operand tiles land dense: [c][b1][T0]
+  const double* const ofo = sAcc + eb1 * C::OPW + C::OPO + ea0;
+  const double* const odi = sDi + eb1 * C::OPW + C::OPO + ea0;
+  auto march = [&](auto ek_tag, auto full_tag) {
     constexpr int EK = decltype(ek_tag)::value;
+    constexpr bool FULL = decltype(full_tag)::value != 0;  // the tile lies inside the interior in x, y and vx
     for (int q = q0; q < q0 + nq; ++q) {
       const int p = q + ng;                       // data index of the plane being updated
       const int sc = (p - pbase) % NS;            // its ring slot
@@ -409,6 +421,20 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
       double res[T2];
 #pragma unroll
       for (int c = 0; c < T2; ++c) res[c] = racc[c * T1 * PA];
+      const i64 idx0 = col + g.s[3] * p;
+      const int s2 = (int)g.s[2];
+      if constexpr (EK != 0 && TMA) {
+        // the RK operands of the tile travel HBM -> shared memory by TMA while the vx and vy fits run:
+        // f_old into the accumulator (every thread has just moved its column of it into registers),
+        // delta_in next to it.  Out-of-range cells are zero filled and never stored.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes of sAcc before the async ones
+        __syncthreads();
+        if (tid == 0) {
+          mbar_expect(&bars[NS + 2], (unsigned)((EK >= 2 ? 2 : 1) * C::NOP * sizeof(double)));
+          tma_load_4d(sAcc, &maps.fo, &bars[NS + 2], o0 + C::OPX, o1 + ng, o2 + ng, p);
+          if (EK >= 2) tma_load_4d(sDi, &maps.di, &bars[NS + 2], o0 + C::OPX, o1 + ng, o2 + ng, p);
+        }
+      }
       if (do_acc) {
         const double* core = cur + ecell;                          // + c*T1*PC
         const double* hlo = sVh + eb1 * PC + NG + ea0;             // + h*T1*PC
@@ -441,24 +467,9 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
       const int s_new = (p + NG - pbase) % NS;
       wait_core(s_new);  // always: no TMA write may be outstanding when the CTA exits
       {
-        const i64 idx0 = col + g.s[3] * p;
-        const int s2 = (int)g.s[2];
         const double* velp = vel + o2 + ng + (i64)g.nd[2] * p;
-        const double* fo_p = upd.f_old + idx0;
-        const double* di_p = upd.delta_in + idx0;
         double* do_p = upd.delta_out + idx0;
         double* pr_p = upd.pred + idx0;
-        // the RK operands of the whole column first: their latency hides behind the fits.  Out-of-tile
-        // cells read the column's first cell (always addressable) and are never stored.
-        double fo[T2], di[T2];
-        if constexpr (EK != 0) {
-#pragma unroll
-          for (int c = 0; c < T2; ++c) {
-            const int oc = (c < ncv) ? c * s2 : 0;
-            fo[c] = (ncv > 0) ? fo_p[oc] : 0.0;
-            di[c] = (EK >= 2 && ncv > 0) ? di_p[oc] : 0.0;
-          }
-        }
         if (do_acc) {
           // ring slots of the planes p-NG+2 .. p+NG (w[1..W-1] of the vy fit), this thread's cell
           const double* wp[W];
@@ -480,9 +491,28 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
         double psum = 0.0, pvx = 0.0, pvy = 0.0;
         if constexpr (EK != 0) {
           // branch-free: every cell computes, only the stores and the moment terms are predicated
+          double fo[T2], di[T2];
+          if constexpr (TMA) {
+            mbar_wait(&bars[NS + 2], ph_o);
+            ph_o ^= 1u;
+#pragma unroll
+            for (int c = 0; c < T2; ++c) {
+              fo[c] = ofo[c * T1 * C::OPW];
+              di[c] = (EK >= 2) ? odi[c * T1 * C::OPW] : 0.0;
+            }
+          } else {
+            const double* fo_p = upd.f_old + idx0;
+            const double* di_p = upd.delta_in + idx0;
+#pragma unroll
+            for (int c = 0; c < T2; ++c) {
+              const int oc = (FULL || c < ncv) ? c * s2 : 0;
+              fo[c] = (FULL || ncv > 0) ? fo_p[oc] : 0.0;
+              di[c] = (EK >= 2 && (FULL || ncv > 0)) ? di_p[oc] : 0.0;
+            }
+          }
 #pragma unroll
           for (int c = 0; c < T2; ++c) {
-            const bool live = c < ncv;
+            const bool live = FULL || c < ncv;
             const int oc = c * s2;
             double pr;
             if constexpr (EK == 1) {
@@ -499,10 +529,11 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
             if (live) pr_p[oc] = pr;
             if (mom.nmom > 0) {
               const double prm = live ? pr : 0.0;
+              const int cc = FULL ? c : min(c, max(ncv - 1, 0));
               psum = ADD(psum, prm);
               if (mom.nmom > 1) {
-                pvx = FMA(__ldg(velp + min(c, max(ncv - 1, 0))), prm, pvx);
-                pvy = FMA(__ldg(velp + min(c, max(ncv - 1, 0)) + (i64)g.nd[2] * g.nd[3]), prm, pvy);
+                pvx = FMA(__ldg(velp + cc), prm, pvx);
+                pvy = FMA(__ldg(velp + cc + (i64)g.nd[2] * g.nd[3]), prm, pvy);
               }
             }
           }
@@ -542,10 +573,17 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
       }
     }
   };
-  if (ekind == 1) march(IntTag<1>{});
-  else if (ekind == 2) march(IntTag<2>{});
-  else if (ekind == 3) march(IntTag<3>{});
-  else march(IntTag<0>{});
+  const bool full = (o0 + T0 <= g.n[0]) && (o1 + T1 <= g.n[1]) && (o2 + T2 <= g.n[2]);
+  if (ekind == 0) march(IntTag<0>{}, IntTag<0>{});
+  else if (full) {
+    if (ekind == 1) march(IntTag<1>{}, IntTag<1>{});
+    else if (ekind == 2) march(IntTag<2>{}, IntTag<1>{});
+    else march(IntTag<3>{}, IntTag<1>{});
+  } else {
+    if (ekind == 1) march(IntTag<1>{}, IntTag<0>{});
+    else if (ekind == 2) march(IntTag<2>{}, IntTag<0>{});
+    else march(IntTag<3>{}, IntTag<0>{});
+  }
 
   if (mom.nmom > 0 && col_ok) {
     const i64 nxy = (i64)g.n[0] * g.n[1];
@@ -590,34 +628,42 @@ static bool encode_map(CUtensorMap* m, const DGeo& g, const double* f, int b0, i
 struct MapKey {
   const double* f;
   int nd[4];
-  int t[3];
-  int ng;
+  int box[4];
   bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
 };
-template <int ORDER, int T0, int T1, int T2>
-static bool get_maps(const DGeo& g, const double* f, MarchMaps* out) {
-  using C = MarchCfg<ORDER, T0, T1, T2>;
+static bool get_map(const DGeo& g, const double* f, int b0, int b1, int b2, CUtensorMap* out) {
   // TMA needs a 16-byte aligned base and pitches
-  if (((uintptr_t)f & 15) || (g.nd[0] & 1)) return false;
-  static MapKey keys[32];
-  static MarchMaps vals[32];
+  if (f == nullptr || ((uintptr_t)f & 15) || (g.nd[0] & 1)) return false;
+  constexpr int CAP = 128;
+  static MapKey keys[CAP];
+  static CUtensorMap vals[CAP];
   static int count = 0, next = 0;
   MapKey k;
   memset(&k, 0, sizeof(k));
   k.f = f;
   for (int d = 0; d < 4; ++d) k.nd[d] = g.nd[d];
-  k.t[0] = T0; k.t[1] = T1; k.t[2] = T2;
-  k.ng = C::NG;
+  k.box[0] = b0; k.box[1] = b1; k.box[2] = b2; k.box[3] = 1;
   for (int i = 0; i < count; ++i)
     if (keys[i] == k) { *out = vals[i]; return true; }
-  MarchMaps m;
-  if (!encode_map(&m.core, g, f, C::PC, T1, T2, 1)) return false;
-  if (!encode_map(&m.yh, g, f, C::PC, C::NG, T2, 1)) return false;
-  if (!encode_map(&m.vh, g, f, C::PC, T1, C::NG, 1)) return false;
-  const int slot = (count < 32) ? count++ : (next++ % 32);
+  CUtensorMap m;
+  if (!encode_map(&m, g, f, b0, b1, b2, 1)) return false;
+  const int slot = (count < CAP) ? count++ : (next++ % CAP);
   keys[slot] = k;
   vals[slot] = m;
   *out = m;
+  return true;
+}
+template <int ORDER, int T0, int T1, int T2>
+static bool get_maps(const DGeo& g, const double* f, const DUpd& u, MarchMaps* out) {
+  using C = MarchCfg<ORDER, T0, T1, T2>;
+  if (!get_map(g, f, C::PC, T1, T2, &out->core)) return false;
+  if (!get_map(g, f, C::PC, C::NG, T2, &out->yh)) return false;
+  if (!get_map(g, f, C::PC, T1, C::NG, &out->vh)) return false;
+  // the RK operand tiles (only read by the RK4-shaped epilogues; a missing operand keeps a valid dummy map)
+  out->fo = out->core;
+  out->di = out->core;
+  if (u.active && u.f_old && !get_map(g, u.f_old, C::OPW, T1, T2, &out->fo)) return false;
+  if (u.active && u.delta_in && !get_map(g, u.delta_in, C::OPW, T1, T2, &out->di)) return false;
   return true;
 }
 
@@ -651,7 +697,7 @@ static cudaError_t launch_march_cfg(const DGeo& g, const double* f, const double
     const char* e = getenv("LK_NO_TMA");
     use_tma_env = (e && e[0] == '1') ? 0 : 1;
   }
-  const bool tma = use_tma_env && get_maps<ORDER, T0, T1, T2>(g, f, &maps);
+  const bool tma = use_tma_env && get_maps<ORDER, T0, T1, T2>(g, f, u, &maps);
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
