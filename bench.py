@@ -315,7 +315,7 @@ def run_own(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_leg(reps=8)
+        cpu = cpu_leg(reps=32)
         cpu.pop("_per_stage_s", None)
 
     if rank == 0:

@@ -105,6 +105,50 @@ const double* lk_vp_rho_ptr(const lk_vp_system* sys);
 /* integrated_ke_e_dot of species s (KineticSpecies.C:282-284); synchronises */
 int lk_vp_ke_e_dot(lk_vp_system* sys, int s, double* value);
 
+/* ---------------------------------------------------------------------------------------------
+ * Vlasov-Maxwell: the host mirror of VMSystem / VMState / Maxwell (VMSystem.C:407-581, Maxwell.C:299-353,
+ * 562-623, Maxwell.H:199-204, 371-381) driven by RK4Integrator (RK4Integrator.H:66-171).  The RK state is
+ * the distribution functions plus em_vars (n1d,n2d,6: Ex,Ey,Ez,Bx,By,Bz) and one transverse drift
+ * velocity vz (n1d,n2d) per species; x and y periodic; no E-field drivers, antennae or particles.
+ * Runs on one GPU (base.ntiles must be 1 and the tile must be the whole configuration space).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct lk_vm_desc {
+  lk_vp_desc base;      /* rk_order must be 4 */
+  double light_speed;   /* Simulation::s_LIGHT_SPEED */
+  double av_weak, av_strong; /* maxwell.avWeak / avStrong (MaxwellF.f:298-352) */
+} lk_vm_desc;
+typedef struct lk_vm_system lk_vm_system;
+
+int lk_vm_create(lk_vm_system** sys, const lk_vm_desc* desc, void* stream);
+void lk_vm_destroy(lk_vm_system* sys);
+int lk_vm_species_geom(const lk_vm_system* sys, int s, lk_geom* g);
+/* restart-layout state I/O (dataBox incl. ghosts, x fastest); synchronous */
+int lk_vm_set_state(lk_vm_system* sys, int s, const double* f_host);
+int lk_vm_get_state(lk_vm_system* sys, int s, double* f_host);
+double* lk_vm_state_ptr(lk_vm_system* sys, int s);
+int lk_vm_set_fields(lk_vm_system* sys, const double* em_host); /* (n1d,n2d,6) */
+int lk_vm_get_fields(lk_vm_system* sys, double* em_host);
+int lk_vm_set_vz(lk_vm_system* sys, int s, const double* vz_host); /* (n1d,n2d) */
+int lk_vm_get_vz(lk_vm_system* sys, int s, double* vz_host);
+const double* lk_vm_fields_ptr(lk_vm_system* sys);              /* device em_vars of the current state */
+const double* lk_vm_current_ptr(lk_vm_system* sys, int comp);   /* device net Jx/Jy/Jz of the last evalRHS */
+/* inflow values at the velocity boundaries: factored tables, or -- for initial conditions that do not
+ * factor (PerturbedMaxwellianIC.C:176-246 with a flow-velocity wave, the emDamping deck) -- the
+ * velocity-ghost layers of the cached IC array: ghost3 (n1d,n2d,2*ng,n4d), ghost4 (n1d,n2d,n3d,2*ng),
+ * layers [0,ng) below the interior, [ng,2ng) above; host pointers */
+int lk_vm_set_inflow(lk_vm_system* sys, int s, const double* fx, const double* fv, double fnorm, double frac);
+int lk_vm_set_inflow_ghosts(lk_vm_system* sys, int s, const double* ghost3, const double* ghost4);
+int lk_vm_set_time(lk_vm_system* sys, double t);
+double lk_vm_time(const lk_vm_system* sys);
+/* VMSystem::advance (copySolnData(old, state); RK4 over the whole VMState) */
+int lk_vm_advance(lk_vm_system* sys, double dt);
+/* VMSystem::stableDt: min over species of computeDt and Maxwell::computeDt = 1/(c(1/dx+1/dy)) */
+int lk_vm_stable_dt(lk_vm_system* sys, double* dt);
+int lk_vm_lambda_max(lk_vm_system* sys, int s, double out[2]);
+/* VMSystem::evalRHS of the current state in the reference's UNFUSED order (parity hook): rhs_dev[s] 4D,
+ * rhs_em_dev (n1d,n2d,6), rhs_vz_dev[s] (n1d,n2d); device pointers, interior written */
+int lk_vm_eval_rhs(lk_vm_system* sys, double** rhs_dev, double* rhs_em_dev, double** rhs_vz_dev, double time);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,8 @@ def _newer(target, sources):
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
-        os.path.join(HERE, "..", "include", "loki_b200.h"), os.path.abspath(__file__)]
+        os.path.join(HERE, "..", "include", "loki_b200.h"), os.path.join(HERE, "..", "include", "loki_b200_host.h"),
+        os.path.abspath(__file__)]
     if not force and _newer(OUT, srcs):
         return OUT
     bdir = os.path.join(HERE, "build")
@@ -39,11 +40,17 @@ def build(force=False, verbose=False):
     ]
     procs = []
     objs = []
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [
+        os.path.join(HERE, "..", "include", f) for f in os.listdir(os.path.join(HERE, "..", "include"))] + [
+        os.path.abspath(__file__)]
     for flags, src, obj in jobs:
         if not os.path.exists(os.path.join(CSRC, src)):
             continue
         o = os.path.join(bdir, obj)
         objs.append(o)
+        deps = [h for h in hdrs if src == "lk_host.cu" or not h.endswith("loki_b200_host.h")]
+        if not force and not verbose and _newer(o, [os.path.join(CSRC, src)] + deps):
+            continue  # this object is current: only changed translation units are recompiled
         cmd = [nvcc] + ARCH + COMMON + extra + flags + ["-c", os.path.join(CSRC, src), "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:

@@ -180,6 +180,10 @@ struct KineticSpecies {
   DevBuf<double> mom_part;
   lk_stage_moments mom;
   bool mom_valid = false;
+  // Vlasov-Maxwell: per-species current densities (n1d,n2d) and the explicit inflow ghost tables of a
+  // non-factorable initial condition (PerturbedMaxwellianIC.C:176-246 caches the full m_f; only its
+  // velocity-ghost layers are ever read by setaccelerationbcs4d)
+  DevBuf<double> Jx_s, Jy_s, Jz_s, ic_ghost3, ic_ghost4;
   // inflow (initial condition) tables
   DevBuf<double> ic_fx, ic_fv;
   lk_inflow inflow;
@@ -608,6 +612,289 @@ struct VPSystem {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// VMSystem (+ VMState, Maxwell, RK4Integrator): one rank, whole configuration space
+// (VMSystem.C:407-581, Maxwell.C:299-353, 562-623, Maxwell.H:199-204, 371-381)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_mul2d(double* __restrict__ dst, const double* __restrict__ a, const double* __restrict__ b, i64 n) {
+  i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] = __dmul_rn(a[t], b[t]);
+}
+// maxwellevalvzrhs (MaxwellF.f:442-469): dvz = (q/m) Ez on the interior
+__global__ void k_vz_rhs(double* __restrict__ dvz, const double* __restrict__ em, double qm, int n1, int n2, int ng) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n1 * n2) return;
+  const i64 n1d = n1 + 2 * ng, pl = n1d * (n2 + 2 * ng);
+  const i64 o = (t % n1 + ng) + n1d * (t / n1 + ng);
+  dvz[o] = __dmul_rn(qm, em[o + 2 * pl]);
+}
+
+struct VMSystem {
+  lk_vm_desc desc;
+  std::vector<lk_species_desc> sdesc;
+  std::vector<KineticSpecies*> species;
+  cudaStream_t st = nullptr;
+  int ng = 2, n1 = 0, n2 = 0, n1d = 0, n2d = 0;
+  i64 pl = 0;
+  double dxg[2] = {0, 0};
+  // Maxwell state: em_vars (n1d,n2d,6) and vz per species; [0] = state/old, [1] = new (predictor)
+  DevBuf<double> em[2], em_rhs, em_delta, Jx, Jy, Jz, sumf;
+  std::vector<DevBuf<double>*> vz[2], vz_rhs, vz_delta;
+  int i_state = 0;
+  double time = 0.0, dt = 0.0;
+  bool lambda_stale = true;
+
+  ~VMSystem() {
+    for (auto* s : species) delete s;
+    for (int k = 0; k < 2; ++k) for (auto* b : vz[k]) delete b;
+    for (auto* b : vz_rhs) delete b;
+    for (auto* b : vz_delta) delete b;
+  }
+  double* emState() { return em[i_state].p; }
+  double* emNew() { return em[1 - i_state].p; }
+  double* vzState(int s) { return vz[i_state][s]->p; }
+  double* vzNew(int s) { return vz[1 - i_state][s]->p; }
+
+  int create(const lk_vm_desc* d, void* stream) {
+    desc = *d;
+    const lk_vp_desc& b = d->base;
+    sdesc.assign(b.species, b.species + b.nspecies);
+    desc.base.species = sdesc.data();
+    st = (cudaStream_t)stream;
+    if (!(b.order == 4 || b.order == 6) || b.rk_order != 4 || b.nspecies < 1) return LK_ERR_ARG;
+    if (b.ntiles != 1 || b.tile_lo[0] != 0 || b.tile_lo[1] != 0 || b.tile_n[0] != b.nglobal[0] || b.tile_n[1] != b.nglobal[1])
+      return LK_ERR_UNSUPPORTED;  // the Maxwell path runs on one GPU
+    ng = b.order == 4 ? 2 : 3;
+    n1 = b.nglobal[0]; n2 = b.nglobal[1];
+    if (n1 < b.order + 1 || n2 < b.order + 1) return LK_ERR_ARG;  // stencil width (KineticSpecies.C:495-504)
+    n1d = n1 + 2 * ng; n2d = n2 + 2 * ng;
+    pl = (i64)n1d * n2d;
+    for (int k = 0; k < 2; ++k) dxg[k] = (b.xhi[k] - b.xlo[k]) / b.nglobal[k];
+    for (int k = 0; k < 2; ++k) {
+      LKH_CHECK(em[k].alloc(pl * 6));
+      LKH_CUDA(cudaMemset(em[k].p, 0, sizeof(double) * pl * 6));
+    }
+    LKH_CHECK(em_rhs.alloc(pl * 6));
+    LKH_CHECK(em_delta.alloc(pl * 6));
+    LKH_CUDA(cudaMemset(em_rhs.p, 0, sizeof(double) * pl * 6));
+    LKH_CUDA(cudaMemset(em_delta.p, 0, sizeof(double) * pl * 6));
+    LKH_CHECK(Jx.alloc(pl)); LKH_CHECK(Jy.alloc(pl)); LKH_CHECK(Jz.alloc(pl)); LKH_CHECK(sumf.alloc(pl));
+    for (int s = 0; s < b.nspecies; ++s) {
+      const lk_species_desc& sd = sdesc[s];
+      if (sd.has_driver) return LK_ERR_UNSUPPORTED;
+      KineticSpecies* ks = new KineticSpecies();
+      species.push_back(ks);
+      ks->g.n[0] = n1; ks->g.n[1] = n2; ks->g.n[2] = sd.nv[0]; ks->g.n[3] = sd.nv[1];
+      ks->g.ng = ng; ks->g.order = b.order;
+      ks->g.dx[0] = dxg[0]; ks->g.dx[1] = dxg[1];
+      ks->g.dx[2] = (sd.vhi[0] - sd.vlo[0]) / sd.nv[0];
+      ks->g.dx[3] = (sd.vhi[1] - sd.vlo[1]) / sd.nv[1];
+      ks->mass = sd.mass; ks->charge = sd.charge; ks->bz_const = sd.bz_const;
+      ks->vlo[0] = sd.vlo[0]; ks->vlo[1] = sd.vlo[1]; ks->vhi[0] = sd.vhi[0]; ks->vhi[1] = sd.vhi[1];
+      ks->n1d = n1d; ks->n2d = n2d; ks->n3d = sd.nv[0] + 2 * ng; ks->n4d = sd.nv[1] + 2 * ng;
+      ks->vol = (i64)n1d * n2d * ks->n3d * ks->n4d;
+      for (int k = 0; k < 3; ++k) LKH_CHECK(ks->farr[k].alloc(ks->vol));
+      LKH_CHECK(ks->delta.alloc(ks->vol));
+      LKH_CUDA(cudaMemset(ks->farr[0].p, 0, sizeof(double) * ks->vol));
+      LKH_CHECK(ks->buildVelocityArrays());
+      LKH_CHECK(ks->Jx_s.alloc(pl)); LKH_CHECK(ks->Jy_s.alloc(pl)); LKH_CHECK(ks->Jz_s.alloc(pl));
+      LKH_CHECK(ks->lam.alloc(2));
+      LKH_CUDA(cudaMemset(ks->lam.p, 0, sizeof(double) * 2));
+      memset(&ks->inflow, 0, sizeof(ks->inflow));
+      {
+        const int parts = lk_stage_moment_parts(&ks->g);
+        if (parts < 1) return LK_ERR_ARG;
+        const size_t cap = (size_t)3 * parts * n1 * n2;
+        LKH_CHECK(ks->mom_part.alloc(cap));
+        ks->mom.nmom = 3;
+        ks->mom.partial = ks->mom_part.p;
+        ks->mom.capacity = (int64_t)cap;
+      }
+      ks->f_eval = ks->state();
+      for (int k = 0; k < 2; ++k) {
+        vz[k].push_back(new DevBuf<double>());
+        LKH_CHECK(vz[k].back()->alloc(pl));
+        LKH_CUDA(cudaMemset(vz[k].back()->p, 0, sizeof(double) * pl));
+      }
+      vz_rhs.push_back(new DevBuf<double>());
+      vz_delta.push_back(new DevBuf<double>());
+      LKH_CHECK(vz_rhs.back()->alloc(pl));
+      LKH_CHECK(vz_delta.back()->alloc(pl));
+      LKH_CUDA(cudaMemset(vz_rhs.back()->p, 0, sizeof(double) * pl));
+      LKH_CUDA(cudaMemset(vz_delta.back()->p, 0, sizeof(double) * pl));
+    }
+    return LK_OK;
+  }
+
+  lk_accel accelDesc(KineticSpecies* ks, const double* em_eval, const double* vz_eval) {
+    lk_accel a;
+    a.kind = 1;
+    a.field = em_eval;        // the expansion of em_vars / vz to the species covers the whole box on one rank
+    a.vz = vz_eval;
+    a.vxface_velocities = ks->vxface.p;
+    a.vyface_velocities = ks->vyface.p;
+    a.normalization = ks->charge / ks->mass;
+    a.bz_const = ks->bz_const;
+    return a;
+  }
+
+  // (1) currentDensity of every species (KineticSpecies.C:853-895) + (2) Maxwell::fillGhostCells and the
+  // net current sums (VMSystem.C:453-470)
+  int currentsOf(int s_first_only, const double* const* f_of, double* em_eval, double* const* vz_eval, bool allow_fused) {
+    (void)s_first_only;
+    for (size_t s = 0; s < species.size(); ++s) {
+      KineticSpecies* ks = species[s];
+      const double dv = ks->g.dx[2] * ks->g.dx[3];
+      if (allow_fused && ks->mom_valid && f_of[s] == ks->f_eval && !lk_get_strict()) {
+        // production: sum f, sum vx f, sum vy f were left behind by the stage kernel that wrote f;
+        // Jz = q dv vz(x,y) sum f (the reference sums f*vz(x,y): same value up to rounding)
+        LKH_CHECK(lk_moments_finish(sumf.p, ks->Jx_s.p, ks->Jy_s.p, &ks->mom, &ks->g, dv, ks->charge, st));
+        k_mul2d<<<nb(pl, 128), 128, 0, st>>>(ks->Jz_s.p, sumf.p, vz_eval[s], pl);
+      } else {
+        LKH_CHECK(lk_current_density(ks->Jx_s.p, ks->Jy_s.p, ks->Jz_s.p, f_of[s], &ks->g, ks->velocities.p, vz_eval[s], dv,
+                                     ks->charge, st));
+      }
+    }
+    LKH_CHECK(lk_periodic_fill_2d(em_eval, n1, n2, ng, 6, 1, 1, st));
+    for (size_t s = 0; s < species.size(); ++s) LKH_CHECK(lk_periodic_fill_2d(vz_eval[s], n1, n2, ng, 1, 1, 1, st));
+    for (size_t s = 0; s < species.size(); ++s) {
+      KineticSpecies* ks = species[s];
+      if (s == 0) {
+        LKH_CUDA(cudaMemcpyAsync(Jx.p, ks->Jx_s.p, sizeof(double) * pl, cudaMemcpyDeviceToDevice, st));
+        LKH_CUDA(cudaMemcpyAsync(Jy.p, ks->Jy_s.p, sizeof(double) * pl, cudaMemcpyDeviceToDevice, st));
+        LKH_CUDA(cudaMemcpyAsync(Jz.p, ks->Jz_s.p, sizeof(double) * pl, cudaMemcpyDeviceToDevice, st));
+      } else {
+        k_add_inplace<<<nb(pl, 128), 128, 0, st>>>(Jx.p, ks->Jx_s.p, pl);
+        k_add_inplace<<<nb(pl, 128), 128, 0, st>>>(Jy.p, ks->Jy_s.p, pl);
+        k_add_inplace<<<nb(pl, 128), 128, 0, st>>>(Jz.p, ks->Jz_s.p, pl);
+      }
+    }
+    return LK_OK;
+  }
+  // (6) Maxwell::evalRHS (Maxwell.C:562-623)
+  int maxwellRHS(double* rhs_em, double* const* rhs_vz, const double* em_eval) {
+    LKH_CHECK(lk_maxwell_rhs(rhs_em, em_eval, Jx.p, Jy.p, Jz.p, n1, n2, ng, desc.base.order, dxg, desc.light_speed,
+                             desc.av_weak, desc.av_strong, st));
+    for (size_t s = 0; s < species.size(); ++s)
+      k_vz_rhs<<<nb((i64)n1 * n2, 128), 128, 0, st>>>(rhs_vz[s], em_eval, species[s]->charge / species[s]->mass, n1, n2, ng);
+    return LK_OK;
+  }
+
+  // one RK4 stage (RK4Integrator.H:149-171) over the whole VMState
+  int stage(int stg) {
+    static const double THIRD = 1.0 / 3.0;
+    const double dtOn2 = 0.5 * dt, dtOn3 = THIRD * dt, dtOn6 = 0.5 * dtOn3;
+    const double w_eval[4] = {dtOn6, dtOn3, dtOn3, dtOn6};
+    const double w_upd[4] = {dtOn2, dtOn2, dt, 1.0};
+    double* em_eval = (stg == 0) ? emState() : emNew();
+    std::vector<double*> vz_eval(species.size()), rhs_vz(species.size());
+    std::vector<const double*> f_of(species.size());
+    for (size_t s = 0; s < species.size(); ++s) {
+      vz_eval[s] = (stg == 0) ? vzState((int)s) : vzNew((int)s);
+      rhs_vz[s] = vz_rhs[s]->p;
+      f_of[s] = species[s]->f_eval;
+    }
+    LKH_CHECK(currentsOf(0, f_of.data(), em_eval, vz_eval.data(), true));
+    static const bool no_fuse = getenv("LK_NO_FUSED_MOMENTS") != nullptr;
+    const bool fused_moments = !lk_get_strict() && !no_fuse;
+    for (size_t s = 0; s < species.size(); ++s) {
+      KineticSpecies* ks = species[s];
+      LKH_CHECK(lk_periodic_fill_4d(ks->f_eval, &ks->g, 1, 1, st));  // fillAdvectionGhostCells
+      lk_accel a = accelDesc(ks, em_eval, vz_eval[s]);
+      if (stg == 3) LKH_CHECK(lk_max_accel(&ks->g, &a, ks->lam.p, st));  // consumed by the next stableDt only
+      const int at[4] = {1, 1, 1, 1};
+      LKH_CHECK(lk_set_acceleration_bcs_4d(ks->f_eval, &ks->g, &a, &ks->inflow, at, st));
+      lk_rk_update u;
+      memset(&u, 0, sizeof(u));
+      double* pred = (ks->f_eval == ks->farr[ks->i_a].p) ? ks->farr[ks->i_b].p : ks->farr[ks->i_a].p;
+      u.f_old = ks->state();
+      u.pred = pred;
+      u.delta_in = (stg == 0) ? nullptr : ks->delta.p;
+      u.delta_out = (stg == 3) ? nullptr : ks->delta.p;
+      u.w_delta = w_eval[stg];
+      u.c_pred = w_upd[stg];
+      u.use_delta = (stg == 3);
+      LKH_CHECK(lk_vlasov_stage(nullptr, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, fused_moments ? &ks->mom : nullptr, st));
+      ks->mom_valid = fused_moments;
+      ks->f_eval = pred;
+    }
+    // Maxwell: rhs (ghosts of m_rhs stay zero), delta += w rhs, new = old (ghosts too) + c (rhs | delta)
+    LKH_CHECK(maxwellRHS(em_rhs.p, rhs_vz.data(), em_eval));
+    if (stg == 0) {
+      LKH_CUDA(cudaMemsetAsync(em_delta.p, 0, sizeof(double) * pl * 6, st));
+      for (size_t s = 0; s < species.size(); ++s) LKH_CUDA(cudaMemsetAsync(vz_delta[s]->p, 0, sizeof(double) * pl, st));
+    }
+    LKH_CHECK(lk_xpby2d(em_delta.p, em_rhs.p, w_eval[stg], n1, n2, ng, 6, st));
+    LKH_CUDA(cudaMemcpyAsync(emNew(), emState(), sizeof(double) * pl * 6, cudaMemcpyDeviceToDevice, st));
+    LKH_CHECK(lk_xpby2d(emNew(), (stg < 3) ? em_rhs.p : em_delta.p, w_upd[stg], n1, n2, ng, 6, st));
+    for (size_t s = 0; s < species.size(); ++s) {
+      LKH_CHECK(lk_xpby2d(vz_delta[s]->p, vz_rhs[s]->p, w_eval[stg], n1, n2, ng, 1, st));
+      LKH_CUDA(cudaMemcpyAsync(vzNew((int)s), vzState((int)s), sizeof(double) * pl, cudaMemcpyDeviceToDevice, st));
+      LKH_CHECK(lk_xpby2d(vzNew((int)s), (stg < 3) ? vz_rhs[s]->p : vz_delta[s]->p, w_upd[stg], n1, n2, ng, 1, st));
+    }
+    lambda_stale = true;
+    return LK_OK;
+  }
+
+  int advance(double a_dt) {
+    dt = a_dt;
+    for (auto* ks : species) ks->f_eval = ks->state();
+    for (int stg = 0; stg < 4; ++stg) LKH_CHECK(stage(stg));
+    for (auto* ks : species) {
+      int i_new = (ks->f_eval == ks->farr[ks->i_a].p) ? ks->i_a : ks->i_b;
+      int i_other = (i_new == ks->i_a) ? ks->i_b : ks->i_a;
+      int i_old = ks->i_state;
+      ks->i_state = i_new;
+      ks->i_a = i_old;
+      ks->i_b = i_other;
+      ks->f_eval = ks->state();
+    }
+    i_state = 1 - i_state;
+    time += dt;
+    return LK_OK;
+  }
+
+  // VMSystem::evalRHS in the reference's unfused order (parity hook)
+  int evalRHS(double** rhs_dev, double* rhs_em, double** rhs_vz, double t) {
+    (void)t;
+    std::vector<double*> vz_eval(species.size());
+    std::vector<const double*> f_of(species.size());
+    for (size_t s = 0; s < species.size(); ++s) {
+      vz_eval[s] = vzState((int)s);
+      f_of[s] = species[s]->state();
+      species[s]->mom_valid = false;
+    }
+    LKH_CHECK(currentsOf(0, f_of.data(), emState(), vz_eval.data(), false));
+    for (size_t s = 0; s < species.size(); ++s) {
+      KineticSpecies* ks = species[s];
+      double* f = ks->state();
+      LKH_CHECK(lk_periodic_fill_4d(f, &ks->g, 1, 1, st));
+      LKH_CHECK(lk_advection_derivatives_4d(rhs_dev[s], f, &ks->g, ks->velocities.p, st));
+      lk_accel a = accelDesc(ks, emState(), vz_eval[s]);
+      LKH_CHECK(lk_max_accel(&ks->g, &a, ks->lam.p, st));
+      const int at[4] = {1, 1, 1, 1};
+      LKH_CHECK(lk_set_acceleration_bcs_4d(f, &ks->g, &a, &ks->inflow, at, st));
+      LKH_CHECK(lk_acceleration_derivatives_4d(rhs_dev[s], f, &ks->g, &a, st));
+    }
+    LKH_CHECK(maxwellRHS(rhs_em, rhs_vz, emState()));
+    lambda_stale = true;
+    return LK_OK;
+  }
+
+  int refreshLambda() {
+    if (!lambda_stale) return LK_OK;
+    LKH_CUDA(cudaStreamSynchronize(st));
+    for (auto* ks : species) {
+      double l[2];
+      LKH_CUDA(cudaMemcpy(l, ks->lam.p, sizeof(l), cudaMemcpyDeviceToHost));
+      ks->lambda_max[2] = l[0];
+      ks->lambda_max[3] = l[1];
+    }
+    lambda_stale = false;
+    return LK_OK;
+  }
+};
+
 }  // namespace loki
 
 using loki::VPSystem;
@@ -724,6 +1011,125 @@ int lk_vp_ke_e_dot(lk_vp_system* h, int s, double* value) {
   if (cudaStreamSynchronize(h->sys.st) != cudaSuccess) return LK_ERR_CUDA;
   if (cudaMemcpy(value, h->sys.species[s]->ke.p, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return LK_ERR_CUDA;
   return LK_OK;
+}
+
+/* ---- Vlasov-Maxwell ---- */
+struct lk_vm_system {
+  loki::VMSystem sys;
+};
+#define VM_SP_OK(h, s) ((h) && (s) >= 0 && (s) < (int)(h)->sys.species.size())
+int lk_vm_create(lk_vm_system** out, const lk_vm_desc* desc, void* stream) {
+  if (!out || !desc || !desc->base.species) return LK_ERR_ARG;
+  lk_vm_system* h = new lk_vm_system();
+  int s = h->sys.create(desc, stream);
+  if (s != LK_OK) {
+    delete h;
+    return s;
+  }
+  *out = h;
+  return LK_OK;
+}
+void lk_vm_destroy(lk_vm_system* h) { delete h; }
+int lk_vm_species_geom(const lk_vm_system* h, int s, lk_geom* g) {
+  if (!VM_SP_OK(h, s) || !g) return LK_ERR_ARG;
+  *g = h->sys.species[s]->g;
+  return LK_OK;
+}
+int lk_vm_set_state(lk_vm_system* h, int s, const double* f_host) {
+  if (!VM_SP_OK(h, s) || !f_host) return LK_ERR_ARG;
+  auto* ks = h->sys.species[s];
+  if (cudaMemcpy(ks->state(), f_host, sizeof(double) * ks->vol, cudaMemcpyHostToDevice) != cudaSuccess) return LK_ERR_CUDA;
+  ks->f_eval = ks->state();
+  ks->mom_valid = false;
+  return LK_OK;
+}
+int lk_vm_get_state(lk_vm_system* h, int s, double* f_host) {
+  if (!VM_SP_OK(h, s) || !f_host) return LK_ERR_ARG;
+  auto* ks = h->sys.species[s];
+  if (cudaStreamSynchronize(h->sys.st) != cudaSuccess) return LK_ERR_CUDA;
+  if (cudaMemcpy(f_host, ks->state(), sizeof(double) * ks->vol, cudaMemcpyDeviceToHost) != cudaSuccess) return LK_ERR_CUDA;
+  return LK_OK;
+}
+double* lk_vm_state_ptr(lk_vm_system* h, int s) { return VM_SP_OK(h, s) ? h->sys.species[s]->state() : nullptr; }
+int lk_vm_set_fields(lk_vm_system* h, const double* em_host) {
+  if (!h || !em_host) return LK_ERR_ARG;
+  return cudaMemcpy(h->sys.emState(), em_host, sizeof(double) * h->sys.pl * 6, cudaMemcpyHostToDevice) == cudaSuccess ? LK_OK : LK_ERR_CUDA;
+}
+int lk_vm_get_fields(lk_vm_system* h, double* em_host) {
+  if (!h || !em_host) return LK_ERR_ARG;
+  if (cudaStreamSynchronize(h->sys.st) != cudaSuccess) return LK_ERR_CUDA;
+  return cudaMemcpy(em_host, h->sys.emState(), sizeof(double) * h->sys.pl * 6, cudaMemcpyDeviceToHost) == cudaSuccess ? LK_OK : LK_ERR_CUDA;
+}
+int lk_vm_set_vz(lk_vm_system* h, int s, const double* vz_host) {
+  if (!VM_SP_OK(h, s) || !vz_host) return LK_ERR_ARG;
+  return cudaMemcpy(h->sys.vzState(s), vz_host, sizeof(double) * h->sys.pl, cudaMemcpyHostToDevice) == cudaSuccess ? LK_OK : LK_ERR_CUDA;
+}
+int lk_vm_get_vz(lk_vm_system* h, int s, double* vz_host) {
+  if (!VM_SP_OK(h, s) || !vz_host) return LK_ERR_ARG;
+  if (cudaStreamSynchronize(h->sys.st) != cudaSuccess) return LK_ERR_CUDA;
+  return cudaMemcpy(vz_host, h->sys.vzState(s), sizeof(double) * h->sys.pl, cudaMemcpyDeviceToHost) == cudaSuccess ? LK_OK : LK_ERR_CUDA;
+}
+const double* lk_vm_fields_ptr(lk_vm_system* h) { return h ? h->sys.emState() : nullptr; }
+const double* lk_vm_current_ptr(lk_vm_system* h, int comp) {
+  if (!h) return nullptr;
+  return comp == 0 ? h->sys.Jx.p : (comp == 1 ? h->sys.Jy.p : (comp == 2 ? h->sys.Jz.p : nullptr));
+}
+int lk_vm_set_inflow(lk_vm_system* h, int s, const double* fx, const double* fv, double fnorm, double frac) {
+  if (!VM_SP_OK(h, s) || !fx || !fv) return LK_ERR_ARG;
+  auto* ks = h->sys.species[s];
+  std::vector<double> a(fx, fx + (size_t)ks->n1d * ks->n2d), b(fv, fv + (size_t)ks->n3d * ks->n4d);
+  int st = ks->ic_fx.upload(a);
+  if (st == LK_OK) st = ks->ic_fv.upload(b);
+  if (st != LK_OK) return st;
+  memset(&ks->inflow, 0, sizeof(ks->inflow));
+  ks->inflow.kind = 1;
+  ks->inflow.fx = ks->ic_fx.p;
+  ks->inflow.fv = ks->ic_fv.p;
+  ks->inflow.fnorm = fnorm;
+  ks->inflow.frac = frac;
+  return LK_OK;
+}
+int lk_vm_set_inflow_ghosts(lk_vm_system* h, int s, const double* ghost3, const double* ghost4) {
+  if (!VM_SP_OK(h, s) || !ghost3 || !ghost4) return LK_ERR_ARG;
+  auto* ks = h->sys.species[s];
+  const size_t n3 = (size_t)ks->n1d * ks->n2d * 2 * ks->g.ng * ks->n4d, n4 = (size_t)ks->n1d * ks->n2d * ks->n3d * 2 * ks->g.ng;
+  std::vector<double> a(ghost3, ghost3 + n3), b(ghost4, ghost4 + n4);
+  int st = ks->ic_ghost3.upload(a);
+  if (st == LK_OK) st = ks->ic_ghost4.upload(b);
+  if (st != LK_OK) return st;
+  memset(&ks->inflow, 0, sizeof(ks->inflow));
+  ks->inflow.kind = 3;
+  ks->inflow.ghost3 = ks->ic_ghost3.p;
+  ks->inflow.ghost4 = ks->ic_ghost4.p;
+  return LK_OK;
+}
+int lk_vm_set_time(lk_vm_system* h, double t) {
+  if (!h) return LK_ERR_ARG;
+  h->sys.time = t;
+  return LK_OK;
+}
+double lk_vm_time(const lk_vm_system* h) { return h ? h->sys.time : 0.0; }
+int lk_vm_advance(lk_vm_system* h, double dt) { return h ? h->sys.advance(dt) : LK_ERR_ARG; }
+int lk_vm_stable_dt(lk_vm_system* h, double* dt) {
+  if (!h || !dt) return LK_ERR_ARG;
+  int s = h->sys.refreshLambda();
+  if (s != LK_OK) return s;
+  double v = std::numeric_limits<double>::max();
+  for (auto* ks : h->sys.species) v = std::min(v, ks->computeDt(4));
+  const double dt_maxwell = 1.0 / (h->sys.desc.light_speed * (1.0 / h->sys.dxg[0] + 1.0 / h->sys.dxg[1]));  // Maxwell.H:199-204
+  *dt = std::min(v, dt_maxwell);
+  return LK_OK;
+}
+int lk_vm_lambda_max(lk_vm_system* h, int s, double out[2]) {
+  if (!VM_SP_OK(h, s) || !out) return LK_ERR_ARG;
+  int st = h->sys.refreshLambda();
+  if (st != LK_OK) return st;
+  out[0] = h->sys.species[s]->lambda_max[2];
+  out[1] = h->sys.species[s]->lambda_max[3];
+  return LK_OK;
+}
+int lk_vm_eval_rhs(lk_vm_system* h, double** rhs_dev, double* rhs_em_dev, double** rhs_vz_dev, double time) {
+  return (h && rhs_dev && rhs_em_dev && rhs_vz_dev) ? h->sys.evalRHS(rhs_dev, rhs_em_dev, rhs_vz_dev, time) : LK_ERR_ARG;
 }
 
 }  // extern "C"

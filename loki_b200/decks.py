@@ -11,11 +11,19 @@ import numpy as np
 
 class Species:
     def __init__(self, name, nv, vlim, mass, charge, tx=1.0, ty=1.0, A=0.0, B=0.0, Cc=0.0, kx1=0.0, ky1=0.0,
-                 kx2=0.0, ky2=0.0, frac=1.0, driver=None, bz=0.0):
+                 kx2=0.0, ky2=0.0, frac=1.0, driver=None, bz=0.0, vx0=0.0, vy0=0.0, x_wave_number=0.0,
+                 y_wave_number=0.0, flow_phase=0.0):
         self.name, self.nv, self.vlim, self.mass, self.charge = name, nv, vlim, mass, charge
         self.tx, self.ty, self.A, self.B, self.Cc = tx, ty, A, B, Cc
         self.kx1, self.ky1, self.kx2, self.ky2, self.frac = kx1, ky1, kx2, ky2, frac
         self.driver, self.bz = driver, bz
+        # flow-velocity wave of the Perturbed Maxwellian (PerturbedMaxwellianIC.C:393-410): a non-zero vx0/vy0
+        # makes the initial condition non-factorable (:395-397)
+        self.vx0, self.vy0, self.x_wave_number, self.y_wave_number, self.flow_phase = vx0, vy0, x_wave_number, y_wave_number, flow_phase
+
+    @property
+    def factorable(self):
+        return self.vx0 == 0.0 and self.vy0 == 0.0
 
 
 def driver_params(xwidth, ywidth, shape, omega, E0, t_ramp, t_off, x_shape, lwidth, x0, t0=0.0):
@@ -64,9 +72,40 @@ class Deck:
 
     def initial_state(self, sp, tile_lo=(0, 0), tile_n=None):
         fx, fv, fnorm = self.ic_tables(sp, tile_lo, tile_n)
+        if not sp.factorable:
+            return self.initial_state_full(sp, fx, fnorm), fx, fv, fnorm
         # getIC_At_Pt: fnorm*fv*fx*frac in this order (PerturbedMaxwellianIC.C:279-281)
         f = ((fnorm * fv)[:, :, None, None] * fx[None, None, :, :]) * sp.frac
         return np.ascontiguousarray(f), fx, fv, fnorm
+
+    def initial_state_full(self, sp, fx, fnorm):
+        """PerturbedMaxwellianIC::cache, non-factorable branch (PerturbedMaxwellianIC.C:176-246): the drift
+        of the Maxwellian follows cos(x_wave_number x + y_wave_number y + phase); whole configuration space"""
+        ng = self.ng
+        n, dx = self.geom_of(sp)
+        Lx, Ly = self.n[0] * dx[0], self.n[1] * dx[1]
+        x1 = self.xlim[0] + (np.arange(-ng, self.n[0] + ng) + 0.5) * dx[0]
+        x2 = self.xlim[2] + (np.arange(-ng, self.n[1] + ng) + 0.5) * dx[1]
+        x1 = np.where(x1 < self.xlim[0], x1 + Lx, np.where(x1 > self.xlim[1], x1 - Lx, x1))
+        x2 = np.where(x2 < self.xlim[2], x2 + Ly, np.where(x2 > self.xlim[3], x2 - Ly, x2))
+        x3 = sp.vlim[0] + (np.arange(-ng, sp.nv[0] + ng) + 0.5) * dx[2]
+        x4 = sp.vlim[2] + (np.arange(-ng, sp.nv[1] + ng) + 0.5) * dx[3]
+        sf = np.cos(sp.x_wave_number * x1[None, :] + sp.y_wave_number * x2[:, None] + sp.flow_phase)  # (n2d,n1d)
+        thx, thy = sp.tx / sp.mass, sp.ty / sp.mass
+        c3 = sp.vx0 * sf + 0.0   # m_x0*spatial_factor + m_flowinitx (MaxwellianThermal.C:48-49)
+        c4 = sp.vy0 * sf + 0.0
+        d3 = x3[None, :, None, None] - c3[None, None, :, :]
+        d4 = x4[:, None, None, None] - c4[None, None, :, :]
+        fv = np.exp(-0.5 * ((d3 * d3) / thx + (d4 * d4) / thy))
+        return np.ascontiguousarray(((fnorm * fv) * fx[None, None, :, :]) * sp.frac)
+
+    def inflow_ghost_tables(self, f_ic):
+        """velocity-ghost layers of a cached IC array in the layout of lk_inflow kind 3:
+        ghost3 (2ng,n4d -> stored [n4d][2ng][n2d][n1d]), ghost4 ([2ng][n3d][n2d][n1d])"""
+        ng = self.ng
+        g3 = np.concatenate([f_ic[:, :ng], f_ic[:, -ng:]], axis=1)
+        g4 = np.concatenate([f_ic[:ng], f_ic[-ng:]], axis=0)
+        return np.ascontiguousarray(g3), np.ascontiguousarray(g4)
 
     # ---- product side ----
     def product_desc(self, tile_lo=(0, 0), tile_n=None, ntiles=1):
@@ -118,3 +157,68 @@ def plane_iaw(n=(32, 32), nv=(64, 32), order=4, rk=4, A=0.0):
     i = Species("ion", nv, (-10 / ialpha, 10 / ialpha, -10 / ialpha, 10 / ialpha), 100.0, 1.0, tx=0.1, ty=0.1,
                 A=A, kx1=klde, ky1=klde / 78)
     return Deck("planeIAW" + ("_6" if order == 6 else ""), n, (xa, xb, ya, yb), [e, i], order=order, rk=rk)
+
+
+def perl15(x):
+    """deck constants reach Loki through Perl string interpolation: 15 significant digits
+    (LokiParser.C:104-118)"""
+    return float("%.15g" % x)
+
+
+class VMDeck(Deck):
+    """a Vlasov-Maxwell deck: Deck + light speed, Maxwell hyper-dissipation and the field initial conditions
+    (SimpleEMIC / SimpleVELIC single waves)"""
+
+    def __init__(self, name, n, xlim, species, light_speed, av_weak, av_strong, em_ics, vel_ics, order=4, cfl=1.0):
+        Deck.__init__(self, name, n, xlim, species, order=order, rk=4, cfl=cfl)
+        self.light_speed, self.av_weak, self.av_strong = light_speed, av_weak, av_strong
+        self.em_ics, self.vel_ics = em_ics, vel_ics
+
+    def initial_fields(self):
+        """em_vars (6,n2d,n1d) and vz per species (n2d,n1d): setsimpleemic / setsimplevelic over the whole
+        data box, ghost cells included (SimpleEMICF.f:10-47, SimpleVELICF.f:10-40)"""
+        ng = self.ng
+        x1 = self.xlim[0] + (np.arange(-ng, self.n[0] + ng) + 0.5) * self.dx[0]
+        x2 = self.xlim[2] + (np.arange(-ng, self.n[1] + ng) + 0.5) * self.dx[1]
+        em = np.zeros((6, x2.size, x1.size))
+        for ic in self.em_ics:
+            env = np.cos(ic["kx"] * x1[None, :] + ic["ky"] * x2[:, None] + ic["phase"])
+            o = 0 if ic["field"] == "E" else 3
+            em[o] = em[o] + ic["xamp"] * env
+            em[o + 1] = em[o + 1] + ic["yamp"] * env
+            em[o + 2] = em[o + 2] + ic["zamp"] * env
+        vz = []
+        for k in range(len(self.species)):
+            v = np.zeros((x2.size, x1.size))
+            if k < len(self.vel_ics):
+                ic = self.vel_ics[k]
+                v = v + ic["amp"] * np.cos(ic["kx"] * x1[None, :] + ic["ky"] * x2[:, None] + ic["phase"])
+            vz.append(np.ascontiguousarray(v))
+        return np.ascontiguousarray(em), vz
+
+    def product_vm_desc(self):
+        from .host import VMDesc
+        d = VMDesc()
+        d.base = self.product_desc()
+        d._keep = d.base._keep if hasattr(d.base, "_keep") else None
+        d.light_speed, d.av_weak, d.av_strong = self.light_speed, self.av_weak, self.av_strong
+        return d
+
+
+def em_damping(n=(32, 5), nv=(64, 64), order=4):
+    """test/emDamping/emDamping.pp: one electron species, Vlasov-Maxwell, order 4 / RK4, cfl 0.8"""
+    omega, clight = 3.16, 22.36
+    klde = perl15(math.sqrt(omega ** 2 - 1) / clight)
+    Ey = 1.0e-4
+    Bz = perl15(klde * Ey / omega)
+    uy = perl15(-Ey / omega)
+    av_strong = perl15(1.6 / clight)
+    pi = PI
+    xa, xb = perl15(-pi / klde), perl15(pi / klde)
+    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, vy0=uy, x_wave_number=klde,
+                flow_phase=perl15(pi / 2.0))
+    em_ics = [dict(field="E", xamp=0.0, yamp=Ey, zamp=0.0, kx=klde, ky=0.0, phase=0.0),
+              dict(field="B", xamp=0.0, yamp=0.0, zamp=Bz, kx=klde, ky=0.0, phase=0.0)]
+    vel_ics = [dict(amp=0.0, kx=0.0, ky=0.0, phase=0.0)]
+    return VMDeck("emDamping", n, (xa, xb, -10.0, 10.0), [e], clight, 0.0, av_strong, em_ics, vel_ics, order=order,
+                  cfl=0.8)

@@ -19,7 +19,31 @@ class VPDesc(C.Structure):
                 ("tile_lo", C.c_int * 2), ("tile_n", C.c_int * 2), ("ntiles", C.c_int)]
 
 
+class VMDesc(C.Structure):
+    _fields_ = [("base", VPDesc), ("light_speed", C.c_double), ("av_weak", C.c_double), ("av_strong", C.c_double)]
+
+
 _PROTOS = {
+    "lk_vm_create": (C.c_int, [C.POINTER(_vp), C.POINTER(VMDesc), _vp]),
+    "lk_vm_destroy": (None, [_vp]),
+    "lk_vm_species_geom": (C.c_int, [_vp, C.c_int, C.POINTER(Geom)]),
+    "lk_vm_set_state": (C.c_int, [_vp, C.c_int, _vp]),
+    "lk_vm_get_state": (C.c_int, [_vp, C.c_int, _vp]),
+    "lk_vm_state_ptr": (_vp, [_vp, C.c_int]),
+    "lk_vm_set_fields": (C.c_int, [_vp, _vp]),
+    "lk_vm_get_fields": (C.c_int, [_vp, _vp]),
+    "lk_vm_set_vz": (C.c_int, [_vp, C.c_int, _vp]),
+    "lk_vm_get_vz": (C.c_int, [_vp, C.c_int, _vp]),
+    "lk_vm_fields_ptr": (_vp, [_vp]),
+    "lk_vm_current_ptr": (_vp, [_vp, C.c_int]),
+    "lk_vm_set_inflow": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_double, C.c_double]),
+    "lk_vm_set_inflow_ghosts": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "lk_vm_set_time": (C.c_int, [_vp, C.c_double]),
+    "lk_vm_time": (C.c_double, [_vp]),
+    "lk_vm_advance": (C.c_int, [_vp, C.c_double]),
+    "lk_vm_stable_dt": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "lk_vm_lambda_max": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double * 2)]),
+    "lk_vm_eval_rhs": (C.c_int, [_vp, C.POINTER(_vp), _vp, C.POINTER(_vp), C.c_double]),
     "lk_vp_create": (C.c_int, [C.POINTER(_vp), C.POINTER(VPDesc), _vp]),
     "lk_vp_destroy": (None, [_vp]),
     "lk_vp_species_geom": (C.c_int, [_vp, C.c_int, C.POINTER(Geom)]),

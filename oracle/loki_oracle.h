@@ -145,6 +145,25 @@ void ok_vp_rk6_step(ok_vp_work* w, double** f_new, double** f_old, double time, 
 void ok_vp_last_accel_max(const ok_vp_work* w, double* axmax, double* aymax);
 double ok_vp_stable_dt(const ok_vp_work* w, const double* axmax, const double* aymax, int rk_order);
 
+/* ---- composite: single-rank Vlasov-Maxwell (VMSystem.C:407-549, Maxwell.C:299-353, 562-623); x/y periodic,
+ *      no drivers/antennae/particles.  em: (n1d,n2d,6) Ex,Ey,Ez,Bx,By,Bz; vz[s]: (n1d,n2d).  loki_oracle_vm.c */
+typedef struct ok_vm_work ok_vm_work;
+ok_vm_work* ok_vm_work_create(int nspecies, const ok_species* sp, const double* xlo, const double* xhi,
+                              double light_speed, double av_weak, double av_strong);
+void ok_vm_work_destroy(ok_vm_work* w);
+void ok_vm_eval_rhs(ok_vm_work* w, double** rhs, double* rhs_em, double** rhs_vz, double** f, double* em,
+                    double** vz, double time, double* axmax, double* aymax);
+const double* ok_vm_net_current(const ok_vm_work* w, int comp); /* net Jx/Jy/Jz of the last evalRHS */
+void ok_vm_rk4_step(ok_vm_work* w, double** f_new, double** f_old, double* em_new, double* em_old,
+                    double** vz_new, double** vz_old, double time, double dt);
+void ok_vm_last_accel_max(const ok_vm_work* w, double* axmax, double* aymax);
+double ok_vm_stable_dt(const ok_vm_work* w, const double* axmax, const double* aymax, int rk_order);
+/* SimpleEMICF.f:10-47 (field = 1: E, 4: B) and SimpleVELICF.f:10-40, one wave, whole data box */
+void ok_simple_em_ic(double* em, int n1, int n2, int ng, const double* xlo, const double* dx, int field,
+                     double xamp, double yamp, double zamp, double kx, double ky, double phi);
+void ok_simple_vel_ic(double* vz, int n1, int n2, int ng, const double* xlo, const double* dx, double amp,
+                      double kx, double ky, double phi);
+
 /* unfused CPU timing leg used by bench.py (same passes as the reference does per RK4 stage) */
 double ok_time_rk4_stage_reference_style(const ok_geom* g, int nthreads, int reps);
 

@@ -1,0 +1,282 @@
+/*
+ * loki_oracle_vm.c -- CPU ORACLE (test infrastructure only; see loki_oracle.h).
+ *
+ * Single-rank restatement of the reference's Vlasov-Maxwell stage sequencing:
+ * VMSystem::evalRHS (VMSystem.C:407-549), KineticSpecies::currentDensity (KineticSpecies.C:853-895,
+ * schedules :1895-1950), KineticSpecies::computeAcceleration, Maxwell flavour (KineticSpecies.C:777-850),
+ * Maxwell::fillGhostCells / setPhysicalBCs (Maxwell.H:371-381, Maxwell.C:1239-1288; x and y periodic, so
+ * the Fortran BC routines are no-ops and only communicatePeriodicBoundaries acts), Maxwell::evalRHS
+ * (Maxwell.C:562-623), Maxwell::addData / copySolnData (Maxwell.C:299-353), Maxwell::computeDt
+ * (Maxwell.H:199-204), VMSystem::stableDt (VMSystem.C:563-581), RK4Integrator (RK4Integrator.H:66-171),
+ * and the two field initial conditions SimpleEMICF.f:10-47, SimpleVELICF.f:10-40.
+ * No external E-field drivers, antennae or particles (none of the Maxwell decks in scope has them).
+ *
+ * Parity pinning: every Fortran kernel this file sequences is pinned bit-for-bit against the
+ * transliterated reference Fortran (tests/test_oracle_pin.py); the sequencing itself restates C++ and
+ * has no in-repo golden output ("parity unpinned" for the C++ call order, like loki_oracle_vp.c).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "loki_oracle.h"
+
+struct ok_vm_work {
+  int ns;
+  ok_species* sp;
+  double xlo[2], xhi[2];
+  double light_speed, av_weak, av_strong;
+  /* per species */
+  double **velocities, **vxface, **vyface, **vel1, **vel2, **vel3, **vel4, **em_s, **vz_s;
+  double **J4x, **J4y, **J4z, **Jx_s, **Jy_s, **Jz_s;
+  /* net currents */
+  double *Jx, *Jy, *Jz;
+  /* RK scratch: rhs and delta of the whole VMState */
+  double **rhs, **delta, *rhs_em, *delta_em, **rhs_vz, **delta_vz;
+  double *last_ax, *last_ay;
+};
+
+static int64_t vol4(const ok_geom* g) { return ok_nd(g, 0) * ok_nd(g, 1) * ok_nd(g, 2) * ok_nd(g, 3); }
+
+/* SimpleEMICF.f:10-47: u(:,:,field..field+2) += amp * cos(kx x + ky y + phi) over the whole data box;
+ * field = 1 (E) or 4 (B), 1-based like the Fortran */
+void ok_simple_em_ic(double* em, int n1, int n2, int ng, const double* xlo, const double* dx, int field,
+                     double xamp, double yamp, double zamp, double kx, double ky, double phi) {
+  const int64_t n1d = n1 + 2 * ng, n2d = n2 + 2 * ng, pl = n1d * n2d;
+  for (int j = 0; j < n2d; ++j) {
+    int i2 = j - ng;
+    double x2 = xlo[1] + (i2 + 0.5) * dx[1];
+    for (int i = 0; i < n1d; ++i) {
+      int i1 = i - ng;
+      double x1 = xlo[0] + (i1 + 0.5) * dx[0];
+      double env = cos(kx * x1 + ky * x2 + phi);
+      int64_t o = i + n1d * j;
+      em[o + pl * (field - 1)] = em[o + pl * (field - 1)] + xamp * env;
+      em[o + pl * (field)] = em[o + pl * (field)] + yamp * env;
+      em[o + pl * (field + 1)] = em[o + pl * (field + 1)] + zamp * env;
+    }
+  }
+}
+/* SimpleVELICF.f:10-40 */
+void ok_simple_vel_ic(double* vz, int n1, int n2, int ng, const double* xlo, const double* dx, double amp,
+                      double kx, double ky, double phi) {
+  const int64_t n1d = n1 + 2 * ng, n2d = n2 + 2 * ng;
+  for (int j = 0; j < n2d; ++j) {
+    double x2 = xlo[1] + ((j - ng) + 0.5) * dx[1];
+    for (int i = 0; i < n1d; ++i) {
+      double x1 = xlo[0] + ((i - ng) + 0.5) * dx[0];
+      vz[i + n1d * j] = vz[i + n1d * j] + amp * cos(kx * x1 + ky * x2 + phi);
+    }
+  }
+}
+
+ok_vm_work* ok_vm_work_create(int ns, const ok_species* sp, const double* xlo, const double* xhi,
+                              double light_speed, double av_weak, double av_strong) {
+  ok_vm_work* w = (ok_vm_work*)calloc(1, sizeof(*w));
+  w->ns = ns;
+  w->sp = (ok_species*)malloc(sizeof(ok_species) * ns);
+  memcpy(w->sp, sp, sizeof(ok_species) * ns);
+  for (int k = 0; k < 2; ++k) { w->xlo[k] = xlo[k]; w->xhi[k] = xhi[k]; }
+  w->light_speed = light_speed; w->av_weak = av_weak; w->av_strong = av_strong;
+#define PP(name) w->name = (double**)calloc(ns, sizeof(double*))
+  PP(velocities); PP(vxface); PP(vyface); PP(vel1); PP(vel2); PP(vel3); PP(vel4); PP(em_s); PP(vz_s);
+  PP(J4x); PP(J4y); PP(J4z); PP(Jx_s); PP(Jy_s); PP(Jz_s); PP(rhs); PP(delta); PP(rhs_vz); PP(delta_vz);
+#undef PP
+  w->last_ax = (double*)calloc(ns, sizeof(double));
+  w->last_ay = (double*)calloc(ns, sizeof(double));
+  const ok_geom* g0 = &sp[0].g;
+  const int64_t n1d = ok_nd(g0, 0), n2d = ok_nd(g0, 1), pl = n1d * n2d;
+  for (int s = 0; s < ns; ++s) {
+    const ok_geom* g = &sp[s].g;
+    const int64_t n3d = ok_nd(g, 2), n4d = ok_nd(g, 3);
+    w->velocities[s] = (double*)calloc(n3d * n4d * 2, sizeof(double));
+    w->vxface[s] = (double*)calloc((n3d + 1) * n4d * 2, sizeof(double));
+    w->vyface[s] = (double*)calloc(n3d * (n4d + 1) * 2, sizeof(double));
+    w->vel1[s] = (double*)calloc((n1d + 1) * n2d * n3d * n4d, sizeof(double));
+    w->vel2[s] = (double*)calloc((n2d + 1) * n3d * n4d * n1d, sizeof(double));
+    w->vel3[s] = (double*)calloc((n3d + 1) * n4d * n1d * n2d, sizeof(double));
+    w->vel4[s] = (double*)calloc((n4d + 1) * n1d * n2d * n3d, sizeof(double));
+    w->em_s[s] = (double*)calloc(pl * 6, sizeof(double));
+    w->vz_s[s] = (double*)calloc(pl, sizeof(double));
+    w->J4x[s] = (double*)calloc(vol4(g), sizeof(double));
+    w->J4y[s] = (double*)calloc(vol4(g), sizeof(double));
+    w->J4z[s] = (double*)calloc(vol4(g), sizeof(double));
+    w->Jx_s[s] = (double*)calloc(pl, sizeof(double));
+    w->Jy_s[s] = (double*)calloc(pl, sizeof(double));
+    w->Jz_s[s] = (double*)calloc(pl, sizeof(double));
+    w->rhs[s] = (double*)calloc(vol4(g), sizeof(double));
+    w->delta[s] = (double*)calloc(vol4(g), sizeof(double));
+    w->rhs_vz[s] = (double*)calloc(pl, sizeof(double));
+    w->delta_vz[s] = (double*)calloc(pl, sizeof(double));
+    int lo34[2] = {-g->ng, -g->ng};
+    ok_build_velocity_tables(g, lo34, sp[s].vlo[0], sp[s].vlo[1], w->velocities[s], w->vxface[s], w->vyface[s]);
+    ok_initialize_velocity(g, w->velocities[s], w->vel1[s], w->vel2[s]);
+  }
+  w->Jx = (double*)calloc(pl, sizeof(double));
+  w->Jy = (double*)calloc(pl, sizeof(double));
+  w->Jz = (double*)calloc(pl, sizeof(double));
+  w->rhs_em = (double*)calloc(pl * 6, sizeof(double));
+  w->delta_em = (double*)calloc(pl * 6, sizeof(double));
+  return w;
+}
+
+void ok_vm_work_destroy(ok_vm_work* w) {
+  if (!w) return;
+  for (int s = 0; s < w->ns; ++s) {
+    free(w->velocities[s]); free(w->vxface[s]); free(w->vyface[s]); free(w->vel1[s]); free(w->vel2[s]);
+    free(w->vel3[s]); free(w->vel4[s]); free(w->em_s[s]); free(w->vz_s[s]); free(w->J4x[s]); free(w->J4y[s]);
+    free(w->J4z[s]); free(w->Jx_s[s]); free(w->Jy_s[s]); free(w->Jz_s[s]); free(w->rhs[s]); free(w->delta[s]);
+    free(w->rhs_vz[s]); free(w->delta_vz[s]);
+  }
+  free(w->velocities); free(w->vxface); free(w->vyface); free(w->vel1); free(w->vel2); free(w->vel3);
+  free(w->vel4); free(w->em_s); free(w->vz_s); free(w->J4x); free(w->J4y); free(w->J4z); free(w->Jx_s);
+  free(w->Jy_s); free(w->Jz_s); free(w->rhs); free(w->delta); free(w->rhs_vz); free(w->delta_vz);
+  free(w->Jx); free(w->Jy); free(w->Jz); free(w->rhs_em); free(w->delta_em); free(w->last_ax); free(w->last_ay);
+  free(w->sp);
+  free(w);
+}
+
+const double* ok_vm_net_current(const ok_vm_work* w, int comp) { return comp == 0 ? w->Jx : (comp == 1 ? w->Jy : w->Jz); }
+
+/* VMSystem::evalRHS on one rank.  f[s], em (n1d,n2d,6), vz[s] (n1d,n2d) are the state being evaluated
+ * (their ghost cells are refreshed exactly like the reference does); rhs_* receive the derivative. */
+void ok_vm_eval_rhs(ok_vm_work* w, double** rhs, double* rhs_em, double** rhs_vz, double** f, double* em,
+                    double** vz, double time, double* axmax, double* aymax) {
+  (void)time;
+  const ok_geom* g0 = &w->sp[0].g;
+  const int ng = g0->ng, n1 = g0->n[0], n2 = g0->n[1];
+  const int64_t n1d = ok_nd(g0, 0), n2d = ok_nd(g0, 1), pl = n1d * n2d;
+  /* 1. current density of every species (VMSystem.C:432-440): vz expansion, computecurrents,
+   *    three velocity reductions with measure dvx*dvy and weight q */
+  for (int s = 0; s < w->ns; ++s) {
+    const ok_geom* g = &w->sp[s].g;
+    memcpy(w->vz_s[s], vz[s], sizeof(double) * pl);          /* m_vz = 0; expansion (whole data box) */
+    memset(w->J4x[s], 0, sizeof(double) * vol4(g));
+    memset(w->J4y[s], 0, sizeof(double) * vol4(g));
+    memset(w->J4z[s], 0, sizeof(double) * vol4(g));
+    ok_compute_currents(g, w->velocities[s], f[s], w->vz_s[s], w->J4x[s], w->J4y[s], w->J4z[s]);
+    ok_reduce_4d_to_2d(w->Jx_s[s], w->J4x[s], g, g->dx[2] * g->dx[3], w->sp[s].charge);
+    ok_reduce_4d_to_2d(w->Jy_s[s], w->J4y[s], g, g->dx[2] * g->dx[3], w->sp[s].charge);
+    ok_reduce_4d_to_2d(w->Jz_s[s], w->J4z[s], g, g->dx[2] * g->dx[3], w->sp[s].charge);
+  }
+  /* 2. Maxwell::fillGhostCells(false) (periodic: wrap em_vars and every vz), net currents */
+  ok_periodic_fill_2d(em, n1, n2, ng, 6, 1, 1);
+  for (int s = 0; s < w->ns; ++s) ok_periodic_fill_2d(vz[s], n1, n2, ng, 1, 1, 1);
+  for (int64_t k = 0; k < pl; ++k) { w->Jx[k] = 0.0; w->Jy[k] = 0.0; w->Jz[k] = 0.0; }
+  for (int s = 0; s < w->ns; ++s)
+    for (int64_t k = 0; k < pl; ++k) {
+      w->Jx[k] += w->Jx_s[s][k];
+      w->Jy[k] += w->Jy_s[s][k];
+      w->Jz[k] += w->Jz_s[s][k];
+    }
+  /* 3. advection (VMSystem.C:483-494) */
+  for (int s = 0; s < w->ns; ++s) {
+    const ok_geom* g = &w->sp[s].g;
+    ok_periodic_fill_4d(f[s], g, 1, 1);
+    ok_advection_derivatives_4d(rhs[s], f[s], g, w->vel1[s], w->vel2[s]);
+  }
+  /* 4. acceleration (KineticSpecies.C:777-850): EM expansion, Lorentz force on the v faces.  The
+   *    species-local m_vz is the one expanded in step 1. */
+  for (int s = 0; s < w->ns; ++s) {
+    const ok_species* sp = &w->sp[s];
+    const ok_geom* g = &sp->g;
+    memcpy(w->em_s[s], em, sizeof(double) * pl * 6);
+    double normalization = sp->charge / sp->mass;
+    ok_set_phase_space_vel_maxwell_4d(w->vel3[s], w->vel4[s], g, w->vxface[s], w->vyface[s], normalization,
+                                      sp->bz_const, w->em_s[s], w->vz_s[s], &axmax[s], &aymax[s]);
+    w->last_ax[s] = axmax[s];
+    w->last_ay[s] = aymax[s];
+  }
+  /* 5. v-boundary fill + acceleration derivatives (VMSystem.C:513-529); completeRHS adds nothing */
+  for (int s = 0; s < w->ns; ++s) {
+    const ok_species* sp = &w->sp[s];
+    const ok_geom* g = &sp->g;
+    ok_set_acceleration_bcs_4d(f[s], g, w->vel3[s], w->vel4[s], 1, 1, 1, 1, sp->ic, sp->ic_ctx);
+    ok_acceleration_derivatives_4d(rhs[s], f[s], g, w->vel3[s], w->vel4[s]);
+  }
+  /* 6. Maxwell::evalRHS (Maxwell.C:562-623) */
+  ok_maxwell_eval_rhs(rhs_em, em, w->Jx, w->Jy, w->Jz, n1, n2, ng, g0->order, g0->dx, w->light_speed, w->av_weak,
+                      w->av_strong);
+  for (int s = 0; s < w->ns; ++s)
+    ok_maxwell_eval_vz_rhs(rhs_vz[s], em, w->sp[s].charge / w->sp[s].mass, n1, n2, ng);
+}
+
+/* RK4Integrator::advance over a VMState (kinetic species + em_vars + vz per species) */
+void ok_vm_rk4_step(ok_vm_work* w, double** f_new, double** f_old, double* em_new, double* em_old, double** vz_new,
+                    double** vz_old, double time, double dt) {
+  static const double THIRD = 1.0 / 3.0;
+  double dtOn2 = 0.5 * dt, dtOn3 = THIRD * dt, dtOn6 = 0.5 * dtOn3;
+  const double w_eval[4] = {dtOn6, dtOn3, dtOn3, dtOn6};
+  const double w_upd[4] = {dtOn2, dtOn2, dt, 1.0};
+  const double t_stage[4] = {time, time + dtOn2, time + dtOn2, time + dt};
+  const ok_geom* g0 = &w->sp[0].g;
+  const int ng = g0->ng, n1 = g0->n[0], n2 = g0->n[1];
+  const int64_t pl = ok_nd(g0, 0) * ok_nd(g0, 1);
+  double* ax = (double*)calloc(w->ns, sizeof(double));
+  double* ay = (double*)calloc(w->ns, sizeof(double));
+  for (int s = 0; s < w->ns; ++s) {
+    memset(w->delta[s], 0, sizeof(double) * vol4(&w->sp[s].g));
+    memset(w->delta_vz[s], 0, sizeof(double) * pl);
+  }
+  memset(w->delta_em, 0, sizeof(double) * pl * 6);
+  for (int stage = 1; stage <= 4; ++stage) {
+    double** ef = (stage == 1) ? f_old : f_new;
+    double* eem = (stage == 1) ? em_old : em_new;
+    double** evz = (stage == 1) ? vz_old : vz_new;
+    for (int s = 0; s < w->ns; ++s) {
+      memset(w->rhs[s], 0, sizeof(double) * vol4(&w->sp[s].g));
+      memset(w->rhs_vz[s], 0, sizeof(double) * pl);
+    }
+    memset(w->rhs_em, 0, sizeof(double) * pl * 6);
+    ok_vm_eval_rhs(w, w->rhs, w->rhs_em, w->rhs_vz, ef, eem, evz, t_stage[stage - 1], ax, ay);
+    const double we = w_eval[stage - 1], wu = w_upd[stage - 1];
+    for (int s = 0; s < w->ns; ++s) {
+      const ok_geom* g = &w->sp[s].g;
+      ok_xpby4d(w->delta[s], w->rhs[s], we, g);
+      ok_xpby2d(w->delta_vz[s], w->rhs_vz[s], we, n1, n2, ng, 1);
+    }
+    ok_xpby2d(w->delta_em, w->rhs_em, we, n1, n2, ng, 6);
+    for (int s = 0; s < w->ns; ++s) {
+      const ok_geom* g = &w->sp[s].g;
+      memcpy(f_new[s], f_old[s], sizeof(double) * vol4(g));
+      memcpy(vz_new[s], vz_old[s], sizeof(double) * pl);
+      ok_xpby4d(f_new[s], (stage < 4) ? w->rhs[s] : w->delta[s], wu, g);
+      ok_xpby2d(vz_new[s], (stage < 4) ? w->rhs_vz[s] : w->delta_vz[s], wu, n1, n2, ng, 1);
+    }
+    memcpy(em_new, em_old, sizeof(double) * pl * 6);
+    ok_xpby2d(em_new, (stage < 4) ? w->rhs_em : w->delta_em, wu, n1, n2, ng, 6);
+  }
+  free(ax); free(ay);
+}
+
+void ok_vm_last_accel_max(const ok_vm_work* w, double* axmax, double* aymax) {
+  for (int s = 0; s < w->ns; ++s) { axmax[s] = w->last_ax[s]; aymax[s] = w->last_ay[s]; }
+}
+
+/* VMSystem::stableDt (VMSystem.C:563-581): min of the species' computeDt and Maxwell::computeDt */
+double ok_vm_stable_dt(const ok_vm_work* w, const double* axmax, const double* aymax, int rk_order) {
+  const double pi = 4.0 * atan(1.0);
+  double dt_stable = 1.7976931348623157e308;
+  for (int s = 0; s < w->ns; ++s) {
+    const ok_geom* g = &w->sp[s].g;
+    const ok_species* sp = &w->sp[s];
+    double lam[4];
+    double vlo = sp->vlo[0] + 0.5 * (sp->vhi[0] - sp->vlo[0]) / g->n[2];
+    double vhi = sp->vhi[0] + 0.5 * (sp->vhi[0] - sp->vlo[0]) / g->n[2];
+    lam[0] = fmax(fabs(vlo), fabs(vhi));
+    vlo = sp->vlo[1] + 0.5 * (sp->vhi[1] - sp->vlo[1]) / g->n[3];
+    vhi = sp->vhi[1] + 0.5 * (sp->vhi[1] - sp->vlo[1]) / g->n[3];
+    lam[1] = fmax(fabs(vlo), fabs(vhi));
+    lam[2] = axmax[s];
+    lam[3] = aymax[s];
+    double imLam = 0.0, reLam = 0.0;
+    for (int d = 0; d < 4; ++d) imLam += pi * lam[d] / g->dx[d];
+    double alpha = rk_order == 4 ? 2.6 : 4.95, beta = rk_order == 4 ? 2.6 : 3.168;
+    double ddt = sqrt(1.0 / (reLam * reLam / (alpha * alpha) + imLam * imLam / (beta * beta)));
+    if (ddt < dt_stable) dt_stable = ddt;
+  }
+  const ok_geom* g0 = &w->sp[0].g;
+  double dt_maxwell = 1.0 / (w->light_speed * (1.0 / g0->dx[0] + 1.0 / g0->dx[1]));
+  if (dt_maxwell < dt_stable) dt_stable = dt_maxwell;
+  return dt_stable;
+}

@@ -20,9 +20,14 @@ class Deck(_d.Deck):
             arr[k].vhi[0], arr[k].vhi[1] = sp.vlim[1], sp.vlim[3]
             fx, fv, fnorm = self.ic_tables(sp)
             frac = sp.frac
+            if sp.factorable:
+                def cb(ctx, i1, i2, i3, i4, fx=fx, fv=fv, fnorm=fnorm, frac=frac):
+                    return fnorm * fv[i4, i3] * fx[i2, i1] * frac
+            else:
+                fic = self.initial_state_full(sp, fx, fnorm)  # the cached m_f (PerturbedMaxwellianIC.C:176-246)
 
-            def cb(ctx, i1, i2, i3, i4, fx=fx, fv=fv, fnorm=fnorm, frac=frac):
-                return fnorm * fv[i4, i3] * fx[i2, i1] * frac
+                def cb(ctx, i1, i2, i3, i4, fic=fic):
+                    return fic[i4, i3, i2, i1]
             fn = IC_FN(cb)
             keep.append(fn)
             arr[k].ic = fn
@@ -35,9 +40,17 @@ class Deck(_d.Deck):
         return arr
 
 
+class VMDeck(_d.VMDeck, Deck):
+    pass
+
+
 def _wrap(d):
-    d.__class__ = Deck
+    d.__class__ = VMDeck if isinstance(d, _d.VMDeck) else Deck
     return d
+
+
+def em_damping(*a, **k):
+    return _wrap(_d.em_damping(*a, **k))
 
 
 def plane_epw(*a, **k):

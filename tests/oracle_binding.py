@@ -43,7 +43,7 @@ def load():
     if _L is not None:
         return _L
     so = os.path.join(ODIR, "libloki_oracle.so")
-    srcs = [os.path.join(ODIR, f) for f in ("loki_oracle.c", "loki_oracle_vp.c", "loki_oracle.h")]
+    srcs = [os.path.join(ODIR, f) for f in ("loki_oracle.c", "loki_oracle_vp.c", "loki_oracle_vm.c", "loki_oracle.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", ODIR, "libloki_oracle.so"], stdout=subprocess.DEVNULL)
     L = C.CDLL(so)
@@ -88,6 +88,22 @@ def load():
     L.ok_vp_stable_dt.restype = d
     L.ok_vp_stable_dt.argtypes = [C.c_void_p, dp, dp, i]
     L.ok_shaped_ramped_driver.argtypes = [dp, dp, i, i, i, i, dp, dp, i, d, dp, d, i]
+    vp, pvp = C.c_void_p, C.POINTER(C.c_void_p)
+    L.ok_xpby2d.argtypes = [dp, dp, d, i, i, i, i]
+    L.ok_maxwell_eval_rhs.argtypes = [dp, dp, dp, dp, dp, i, i, i, i, dp, d, d, d]
+    L.ok_maxwell_eval_vz_rhs.argtypes = [dp, dp, d, i, i, i]
+    L.ok_vm_work_create.restype = vp
+    L.ok_vm_work_create.argtypes = [i, C.POINTER(OkSpecies), C.POINTER(d * 2), C.POINTER(d * 2), d, d, d]
+    L.ok_vm_work_destroy.argtypes = [vp]
+    L.ok_vm_eval_rhs.argtypes = [vp, pvp, dp, pvp, pvp, dp, pvp, d, dp, dp]
+    L.ok_vm_net_current.restype = C.POINTER(d)
+    L.ok_vm_net_current.argtypes = [vp, i]
+    L.ok_vm_rk4_step.argtypes = [vp, pvp, pvp, dp, dp, pvp, pvp, d, d]
+    L.ok_vm_last_accel_max.argtypes = [vp, dp, dp]
+    L.ok_vm_stable_dt.restype = d
+    L.ok_vm_stable_dt.argtypes = [vp, dp, dp, i]
+    L.ok_simple_em_ic.argtypes = [dp, i, i, i, dp, dp, i, d, d, d, d, d, d]
+    L.ok_simple_vel_ic.argtypes = [dp, i, i, i, dp, dp, d, d, d, d]
     L.ok_time_rk4_stage_reference_style.restype = d
     L.ok_time_rk4_stage_reference_style.argtypes = [G, i, i]
     _L = L

@@ -113,3 +113,126 @@ def test_poisson_solve_inverts_the_fd_laplacian(ok):
     core = p[I, I]
     lap = d2(core, 1, dx) + d2(core, 0, dy)     # periodic rolls on the interior
     assert np.max(np.abs(lap - rho[I, I])) < 1e-11
+
+
+# ---------------------------------------------------------------------------------------------
+# Vlasov-Maxwell sequencing (oracle/loki_oracle_vm.c)
+# ---------------------------------------------------------------------------------------------
+def _vm_oracle(ok, deck):
+    import ctypes as C
+    keep = []
+    sp = deck.oracle_species(keep)
+    xlo = (C.c_double * 2)(deck.xlim[0], deck.xlim[2])
+    xhi = (C.c_double * 2)(deck.xlim[1], deck.xlim[3])
+    w = ok.ok_vm_work_create(len(deck.species), sp, C.byref(xlo), C.byref(xhi), deck.light_speed, deck.av_weak,
+                             deck.av_strong)
+    return w, sp, keep
+
+
+def test_vm_field_ics_match_deck_mirror(ok):
+    """SimpleEMICF.f / SimpleVELICF.f restated in C against the numpy deck mirror (last-ulp cos differences)"""
+    import decks
+    deck = decks.em_damping(n=(12, 5), nv=(8, 8))
+    em, vz = deck.initial_fields()
+    ng = deck.ng
+    em_c = np.zeros_like(em)
+    xlo = np.array([deck.xlim[0], deck.xlim[2]])
+    dx = np.array(deck.dx)
+    for ic in deck.em_ics:
+        ok.ok_simple_em_ic(em_c, deck.n[0], deck.n[1], ng, xlo, dx, 1 if ic["field"] == "E" else 4, ic["xamp"], ic["yamp"],
+                           ic["zamp"], ic["kx"], ic["ky"], ic["phase"])
+    assert np.max(np.abs(em_c - em)) <= 1e-15 * np.max(np.abs(em))
+    assert np.count_nonzero(em_c[1]) > 0 and np.count_nonzero(em_c[5]) > 0 and np.count_nonzero(em_c[0]) == 0
+    vz_c = np.zeros_like(vz[0])
+    ok.ok_simple_vel_ic(vz_c, deck.n[0], deck.n[1], ng, xlo, dx, 0.3, 0.7, 0.2, 0.1)
+    x1 = deck.xlim[0] + (np.arange(-ng, deck.n[0] + ng) + 0.5) * deck.dx[0]
+    x2 = deck.xlim[2] + (np.arange(-ng, deck.n[1] + ng) + 0.5) * deck.dx[1]
+    assert np.max(np.abs(vz_c - 0.3 * np.cos(0.7 * x1[None, :] + 0.2 * x2[:, None] + 0.1))) <= 1e-15
+
+
+def test_vm_eval_rhs_structure(ok):
+    """VMSystem::evalRHS sequencing: with zero fields the Vlasov RHS is pure advection and dE/dt = -J;
+    dvz/dt = (q/m) Ez; stableDt is capped by Maxwell::computeDt"""
+    import ctypes as C
+    import decks
+    deck = decks.em_damping(n=(8, 5), nv=(12, 8))
+    w, sp, keep = _vm_oracle(ok, deck)
+    s0 = deck.species[0]
+    f = deck.initial_state(s0)[0]
+    rng = np.random.default_rng(2)
+    f = np.ascontiguousarray(f * (1 + 0.05 * rng.uniform(-1, 1, f.shape)))
+    em = np.zeros((6,) + f.shape[2:])
+    vz = np.zeros(f.shape[2:])
+    P = lambda a: (C.c_void_p * 1)(a.ctypes.data)
+    rhs, rem, rvz = np.zeros_like(f), np.zeros_like(em), np.zeros_like(vz)
+    ax, ay = np.zeros(1), np.zeros(1)
+    fe = f.copy()
+    ok.ok_vm_eval_rhs(w, P(rhs), rem, P(rvz), P(fe), em, P(vz), 0.0, ax, ay)
+    assert ax[0] == 0.0 and ay[0] == 0.0
+    # advection only
+    g = sp[0].g
+    nd = g.nd
+    vel = np.zeros(nd[2] * nd[3] * 2)
+    vxf = np.zeros((nd[2] + 1) * nd[3] * 2)
+    vyf = np.zeros(nd[2] * (nd[3] + 1) * 2)
+    lo = (C.c_int * 2)(-g.ng, -g.ng)
+    ok.ok_build_velocity_tables(C.byref(g), C.byref(lo), s0.vlim[0], s0.vlim[2], vel, vxf, vyf)
+    vel1 = np.zeros((nd[0] + 1) * nd[1] * nd[2] * nd[3])
+    vel2 = np.zeros((nd[1] + 1) * nd[2] * nd[3] * nd[0])
+    ok.ok_initialize_velocity(C.byref(g), vel, vel1, vel2)
+    fa = f.copy()
+    ok.ok_periodic_fill_4d(fa, C.byref(g), 1, 1)
+    adv = np.zeros_like(f)
+    ok.ok_advection_derivatives_4d(adv, fa, C.byref(g), vel1, vel2)
+    ng = g.ng
+    I = (slice(ng, -ng),) * 4
+    assert np.array_equal(rhs[I], adv[I])
+    # dE/dt = -J, dB/dt = 0 when all fields vanish
+    n1d, n2d = nd[0], nd[1]
+    I2 = (slice(ng, -ng), slice(ng, -ng))
+    for c in range(3):
+        J = np.ctypeslib.as_array(ok.ok_vm_net_current(w, c), shape=(n2d, n1d))
+        assert np.array_equal(rem[c][I2], -J[I2])
+        assert not np.any(rem[3 + c])
+    Jx = np.ctypeslib.as_array(ok.ok_vm_net_current(w, 0), shape=(n2d, n1d))
+    assert np.any(Jx[I2] != 0.0)
+    # dvz/dt = (q/m) Ez
+    em2 = np.ascontiguousarray(0.01 * rng.uniform(-1, 1, em.shape))
+    fe = f.copy()
+    ok.ok_vm_eval_rhs(w, P(rhs), rem, P(rvz), P(fe), em2, P(vz), 0.0, ax, ay)
+    assert np.array_equal(rvz[I2], (s0.charge / s0.mass) * em2[2][I2])
+    assert ax[0] > 0.0 and ay[0] > 0.0
+    dt = ok.ok_vm_stable_dt(w, ax, ay, 4)
+    dt_maxwell = 1.0 / (deck.light_speed * (1.0 / deck.dx[0] + 1.0 / deck.dx[1]))
+    assert dt <= dt_maxwell
+    ok.ok_vm_work_destroy(w)
+
+
+def test_vm_rk4_step_small_dt_limit(ok):
+    """RK4Integrator over a VMState: (new - old)/dt -> evalRHS(old) as dt -> 0, for f, em_vars and vz"""
+    import ctypes as C
+    import decks
+    deck = decks.em_damping(n=(8, 5), nv=(10, 8))
+    w, sp, keep = _vm_oracle(ok, deck)
+    s0 = deck.species[0]
+    f = deck.initial_state(s0)[0]
+    em, vzl = deck.initial_fields()
+    rng = np.random.default_rng(4)
+    em = np.ascontiguousarray(em * 100 + 1e-3 * rng.uniform(-1, 1, em.shape))
+    vz = np.ascontiguousarray(vzl[0] + 0.1 * rng.uniform(-1, 1, vzl[0].shape))
+    P = lambda a: (C.c_void_p * 1)(a.ctypes.data)
+    rhs, rem, rvz = np.zeros_like(f), np.zeros_like(em), np.zeros_like(vz)
+    ax, ay = np.zeros(1), np.zeros(1)
+    fe, eme, vze = f.copy(), em.copy(), vz.copy()
+    ok.ok_vm_eval_rhs(w, P(rhs), rem, P(rvz), P(fe), eme, P(vze), 0.0, ax, ay)
+    dt = 1e-6
+    fo, emo, vzo = f.copy(), em.copy(), vz.copy()
+    fn, emn, vzn = np.zeros_like(f), np.zeros_like(em), np.zeros_like(vz)
+    ok.ok_vm_rk4_step(w, P(fn), P(fo), emn, emo, P(vzn), P(vzo), 0.0, dt)
+    ng = deck.ng
+    I = (slice(ng, -ng),) * 4
+    I2 = (slice(None), slice(ng, -ng), slice(ng, -ng))
+    assert np.max(np.abs((fn[I] - f[I]) / dt - rhs[I])) <= 1e-4 * np.max(np.abs(rhs[I]))
+    assert np.max(np.abs((emn[I2] - em[I2]) / dt - rem[I2])) <= 1e-3 * np.max(np.abs(rem[I2]))
+    assert np.max(np.abs((vzn[I2[1:]] - vz[I2[1:]]) / dt - rvz[I2[1:]])) <= 1e-3 * np.max(np.abs(rvz))
+    ok.ok_vm_work_destroy(w)
