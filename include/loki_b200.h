@@ -89,6 +89,9 @@ typedef struct lk_rk_update {
   int n_prev;             /* RK6: number of earlier stage results to add (0..7) */
   const double* k_prev[7];
   double c_prev[7];
+  int wrap;               /* bit 0 / bit 1: also write pred's periodic ghost cells in x / y (the copies
+                             communicatePeriodicBoundaries would make, ParallelArray.H:580-606), so that the
+                             next stage needs no separate wrap pass; needs n >= 2*ng in that direction */
 } lk_rk_update;
 
 /* ---- library ---- */

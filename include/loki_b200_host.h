@@ -93,6 +93,9 @@ double* lk_vp_rho_tile_ptr(lk_vp_system* sys);
 double* lk_vp_rho_gather_ptr(lk_vp_system* sys);
 /* tiles: ntiles x {lo0, lo1, n0, n1} in rank order; tiles == NULL means "single rank" */
 int lk_vp_stage_field(lk_vp_system* sys, int stage, const int* tiles);
+/* periodic wrap of lk_vp_eval_ptr(s) inside this rank for a direction that is not cut (0: x, 1: y); a
+ * no-op when the fused stage kernel has already written those ghost cells (lk_rk_update::wrap) */
+int lk_vp_local_fill(lk_vp_system* sys, int s, int dir);
 int lk_vp_stage_finish(lk_vp_system* sys, int stage);
 int lk_vp_end_step(lk_vp_system* sys);
 

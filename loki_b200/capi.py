@@ -44,7 +44,7 @@ class RkUpdate(C.Structure):
     _fields_ = [("f_old", C.c_void_p), ("delta_in", C.c_void_p), ("delta_out", C.c_void_p),
                 ("pred", C.c_void_p), ("w_delta", C.c_double), ("c_pred", C.c_double),
                 ("use_delta", C.c_int), ("n_prev", C.c_int), ("k_prev", C.c_void_p * 7),
-                ("c_prev", C.c_double * 7)]
+                ("c_prev", C.c_double * 7), ("wrap", C.c_int)]
 
 
 class StageMoments(C.Structure):

@@ -187,6 +187,8 @@ static int stage_impl(double* rhs_out, const double* f, const lk_geom* g, const 
     if (!upd->f_old || !upd->pred) return fail(LK_ERR_ARG, "lk_vlasov_rhs: rk update needs f_old and pred");
     if (upd->pred == f) return fail(LK_ERR_ARG, "lk_vlasov_rhs: pred must not alias the evaluated state");
     if (upd->n_prev < 0 || upd->n_prev > 7) return fail(LK_ERR_ARG, "lk_vlasov_rhs: n_prev out of range");
+    if (upd->wrap && g_variant != 0) return fail(LK_ERR_UNSUPPORTED, "lk_vlasov_rhs: wrap needs the marching kernel (variant 0)");
+    if (upd->wrap & ~3) return fail(LK_ERR_ARG, "lk_vlasov_rhs: bad wrap bits");
     for (int j = 0; j < upd->n_prev; ++j)
       if (!upd->k_prev[j]) return fail(LK_ERR_ARG, "lk_vlasov_rhs: missing k_prev");
     if (upd->delta_out && upd->delta_out == f) return fail(LK_ERR_ARG, "lk_vlasov_rhs: delta must not alias the evaluated state");

@@ -53,6 +53,7 @@ struct DUpd {
   int n_prev;
   const double* k_prev[7];
   double c_prev[7];
+  int wrap;  // bit 0 / 1: write the periodic x / y ghost copies of pred too
 };
 
 __device__ __forceinline__ i64 gidx(const DGeo& g, int i1, int i2, int i3, int i4) {
@@ -178,6 +179,52 @@ __device__ __forceinline__ double weno43(double um2, double um1, double u0, doub
 #endif
 }
 
+#if !LK_STRICT
+// ---------------------------------------------------------------------------------------------
+// Production form of WENO65Fit4D (KineticSpeciesF.f:914-979).  The Maple-generated smoothness forms
+// bl, br (:936-950) vanish on constants, so each is a quadratic form in the four first differences of its
+// five cells; an exact rational LDL^T factorisation (tools/derive_weno65.py) writes it as a sum of four
+// squares,  bl = d0 * [ s0^2 + r1 s1^2 + r2 s2^2 + r3 s3^2 ],  s_k = E_k + sum_{j>k} l_kj E_j , and br is
+// the same form on the differences taken in mirror order.  13 fp64 operations per indicator instead of
+// 20, no cancellation between O(u^2) terms, and the common factor d0 drops out of
+//     rho = (br'^2 - bl'^2) / (br'^2 + bl'^2)          (eps scaled by 1/d0 accordingly).
+// Mapped, renormalised weights are 1/2 +- rho^3/2 as for order 4, so
+//     60*face = 37(um1+u0) - 8(um2+up1) + (um3+up2)  -+ |rho|^3 * (E0 + E4 - 4(E1+E3) + 6 E2)   (- if vel > 0)
+// with E_k the forward differences of (um3..up2); the last bracket is the 5th difference of u.
+// ---------------------------------------------------------------------------------------------
+constexpr double W65_L01 = -103932.0 / 33727.0, W65_L03 = -30976.0 / 33727.0;                 // l02 = 3 exactly
+constexpr double W65_L12 = -105363148.0 / 65474723.0, W65_L13 = 39888425.0 / 65474723.0;
+constexpr double W65_L23 = -1110161041.0 / 2419655501.0;
+constexpr double W65_R1 = 1374969183.0 / 1137510529.0, W65_R2 = 3658519117512.0 / 2208265982621.0;
+constexpr double W65_R3 = 33571269879840.0 / 81607721082227.0;
+constexpr double W65_EPS = 1.e-10 * 30240.0 / 33727.0;                                         // eps / d0
+__device__ __forceinline__ double w65_beta(double a, double b, double c, double d) {
+  const double s0 = FMA(W65_L03, d, FMA(3.0, c, FMA(W65_L01, b, a)));
+  const double s1 = FMA(W65_L13, d, FMA(W65_L12, c, b));
+  const double s2 = FMA(W65_L23, d, c);
+  double q = FMA(s0, s0, W65_EPS);
+  q = FMA(MUL(W65_R1, s1), s1, q);
+  q = FMA(MUL(W65_R2, s2), s2, q);
+  return FMA(MUL(W65_R3, d), d, q);
+}
+// u = um3..up2, E0..E4 their forward differences
+__device__ __forceinline__ double w65_face60(double um3, double um2, double um1, double u0, double up1, double up2,
+                                             double E0, double E1, double E2, double E3, double E4, bool pos) {
+  const double bl = w65_beta(E0, E1, E2, E3), br = w65_beta(E4, E3, E2, E1);
+  const double A = MUL(bl, bl), B = MUL(br, br);
+  const double rho = MUL(ADD(B, -A), fast_rcp(ADD(A, B)));
+  const double r3 = MUL(fabs(rho), MUL(rho, rho));
+  const double mean = FMA(37.0, ADD(um1, u0), FMA(-8.0, ADD(um2, up1), ADD(um3, up2)));
+  const double d5 = FMA(6.0, E2, FMA(-4.0, ADD(E1, E3), ADD(E0, E4)));
+  return FMA(flip_sign(r3, pos), d5, mean);
+}
+__device__ __forceinline__ double weno65_face60(double um3, double um2, double um1, double u0, double up1, double up2,
+                                                bool pos) {
+  return w65_face60(um3, um2, um1, u0, up1, up2, ADD(um2, -um3), ADD(um1, -um2), ADD(u0, -um1), ADD(up1, -u0),
+                    ADD(up2, -up1), pos);
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // WENO65Fit4D (KineticSpeciesF.f:914-979)
 // ---------------------------------------------------------------------------------------------
@@ -218,37 +265,7 @@ __device__ __forceinline__ double weno65(double um3, double um2, double um1, dou
   if (pos) { wl = wmax; wr = wmin; } else { wl = wmin; wr = wmax; }
   return (wl * fl + wr * fr);
 #else
-  const double eps = 1.e-10;
-  const double k = 1.0 / 30240.0;
-  // smoothness indicators as nested quadratic forms; constants pre-divided (compile-time folding)
-  double t;
-  t = FMA(5489.0 / 105.0, um1, FMA(-2242428.0 * k, u0, FMA(-1887108.0 * k, um2, FMA(410226.0 * k, um3, MUL(557646.0 * k, up1)))));
-  double bl = FMA(t, um1, eps);
-  t = FMA(75329.0 / 3780.0, um2, FMA(1259696.0 * k, u0, FMA(-275318.0 * k, um3, MUL(-302534.0 * k, up1))));
-  bl = FMA(t, um2, bl);
-  t = FMA(33727.0 * k, um3, FMA(-264314.0 * k, u0, MUL(61952.0 * k, up1)));
-  bl = FMA(t, um3, bl);
-  t = FMA(106409.0 / 3780.0, u0, MUL(-227749.0 / 15120.0, up1));
-  bl = FMA(t, u0, bl);
-  bl = FMA(MUL(69217.0 * k, up1), up1, bl);
-
-  t = FMA(106409.0 / 3780.0, um1, FMA(-2242428.0 * k, u0, FMA(-455498.0 * k, um2, FMA(1259696.0 * k, up1, MUL(-264314.0 * k, up2)))));
-  double br = FMA(t, um1, eps);
-  t = FMA(69217.0 * k, um2, FMA(557646.0 * k, u0, FMA(-302534.0 * k, up1, MUL(61952.0 * k, up2))));
-  br = FMA(t, um2, br);
-  t = FMA(75329.0 / 3780.0, up1, FMA(-1887108.0 * k, u0, MUL(-275318.0 * k, up2)));
-  br = FMA(t, up1, br);
-  t = FMA(5489.0 / 105.0, u0, MUL(68371.0 / 5040.0, up2));
-  br = FMA(t, u0, br);
-  br = FMA(MUL(33727.0 * k, up2), up2, br);
-
-  // mapped weights 1/2 +- rho^3/2 (see weno43_face12); 60*face = mean part +- |rho|^3 * difference part
-  const double A = MUL(bl, bl), B = MUL(br, br);
-  const double rho = MUL(ADD(B, -A), fast_rcp(ADD(A, B)));
-  const double r3 = MUL(fabs(rho), MUL(rho, rho));
-  const double mean = FMA(37.0, ADD(um1, u0), FMA(-8.0, ADD(um2, up1), ADD(um3, up2)));
-  const double diff = FMA(10.0, ADD(um1, -u0), FMA(-5.0, ADD(um2, -up1), ADD(um3, -up2)));
-  return MUL(FMA(flip_sign(r3, !pos), diff, mean), 1.0 / 60.0);
+  return MUL(weno65_face60(um3, um2, um1, u0, up1, up2, pos), 1.0 / 60.0);
 #endif
 }
 

@@ -188,6 +188,21 @@ struct KineticSpecies {
   DevBuf<double> ic_fx, ic_fv;
   lk_inflow inflow;
   bool has_driver = false;
+  // periodic x/y ghost cells already written by the fused stage kernel (lk_rk_update::wrap) for this array
+  const double* wrap_ptr = nullptr;
+  int wrap_bits = 0;
+  // periodic wrap of f in the uncut directions `dirs` (bit 0 x, bit 1 y), skipping what the kernel did
+  int periodicFill(double* f, int dirs, void* st) {
+    const int need = (f == wrap_ptr) ? (dirs & ~wrap_bits) : dirs;
+    if (!need) return LK_OK;
+    return lk_periodic_fill_4d(f, &g, need & 1, (need >> 1) & 1, st);
+  }
+  int wrapFor(int dirs) const {
+    int w = 0;
+    if ((dirs & 1) && g.n[0] >= 2 * g.ng) w |= 1;
+    if ((dirs & 2) && g.n[1] >= 2 * g.ng) w |= 2;
+    return w;
+  }
   ShapedRampedCosineDriver driver;
   double lambda_max[4] = {0, 0, 0, 0};
 
@@ -443,8 +458,11 @@ struct VPSystem {
     return LK_OK;
   }
   // (3a) fillAdvectionGhostCells on one rank: periodic wrap (the multi-rank exchange is the caller's)
+  int uncutDirs() const {
+    return (desc.tile_n[0] == desc.nglobal[0] ? 1 : 0) | (desc.tile_n[1] == desc.nglobal[1] ? 2 : 0);
+  }
   int fillAdvectionGhostCellsLocal() {
-    for (auto* ks : species) LKH_CHECK(lk_periodic_fill_4d(ks->f_eval, &ks->g, 1, 1, st));
+    for (auto* ks : species) LKH_CHECK(ks->periodicFill(ks->f_eval, 3, st));
     return LK_OK;
   }
 
@@ -522,7 +540,11 @@ struct VPSystem {
         else
           LKH_CHECK(lk_ke_e_dot(ks->ke.p + 3, ks->f_eval, &ks->g, ks->charge, ks->velocities.p, ks->ext_efield.p, st));
       }
+      // production: the kernel also writes pred's periodic ghost copies in the directions this rank wraps itself
+      u.wrap = fused_moments ? ks->wrapFor(uncutDirs()) : 0;
       LKH_CHECK(lk_vlasov_stage(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, fused_moments ? &ks->mom : nullptr, st));
+      ks->wrap_ptr = pred;
+      ks->wrap_bits = u.wrap;
       ks->mom_valid = fused_moments;  // moments of `pred`, the next stage's input
       if (ks->has_driver) {
         if (rk4) {
@@ -598,6 +620,7 @@ struct VPSystem {
       KineticSpecies* ks = species[s];
       double* f = ks->state();
       ks->mom_valid = false;
+      ks->wrap_ptr = nullptr;
       LKH_CHECK(lk_periodic_fill_4d(f, &ks->g, 1, 1, st));
       LKH_CHECK(lk_advection_derivatives_4d(rhs_dev[s], f, &ks->g, ks->velocities.p, st));
       LKH_CHECK(ks->computeAcceleration(em_local.p, t, desc.xlo, desc.tile_lo, true, st));
@@ -799,7 +822,7 @@ struct VMSystem {
     const bool fused_moments = !lk_get_strict() && !no_fuse;
     for (size_t s = 0; s < species.size(); ++s) {
       KineticSpecies* ks = species[s];
-      LKH_CHECK(lk_periodic_fill_4d(ks->f_eval, &ks->g, 1, 1, st));  // fillAdvectionGhostCells
+      LKH_CHECK(ks->periodicFill(ks->f_eval, 3, st));  // fillAdvectionGhostCells
       lk_accel a = accelDesc(ks, em_eval, vz_eval[s]);
       if (stg == 3) LKH_CHECK(lk_max_accel(&ks->g, &a, ks->lam.p, st));  // consumed by the next stableDt only
       const int at[4] = {1, 1, 1, 1};
@@ -814,7 +837,10 @@ struct VMSystem {
       u.w_delta = w_eval[stg];
       u.c_pred = w_upd[stg];
       u.use_delta = (stg == 3);
+      u.wrap = fused_moments ? ks->wrapFor(3) : 0;
       LKH_CHECK(lk_vlasov_stage(nullptr, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, fused_moments ? &ks->mom : nullptr, st));
+      ks->wrap_ptr = pred;
+      ks->wrap_bits = u.wrap;
       ks->mom_valid = fused_moments;
       ks->f_eval = pred;
     }
@@ -927,6 +953,7 @@ int lk_vp_set_state(lk_vp_system* h, int s, const double* f_host) {
   if (cudaMemcpy(ks->state(), f_host, sizeof(double) * ks->vol, cudaMemcpyHostToDevice) != cudaSuccess) return LK_ERR_CUDA;
   ks->f_eval = ks->state();
   ks->mom_valid = false;
+  ks->wrap_ptr = nullptr;
   return LK_OK;
 }
 int lk_vp_get_state(lk_vp_system* h, int s, double* f_host) {
@@ -998,6 +1025,11 @@ int lk_vp_stage_field(lk_vp_system* h, int stage, const int* tiles) {
   if (tiles == nullptr || h->sys.desc.ntiles == 1) return h->sys.fillAdvectionGhostCellsLocal();
   return LK_OK;
 }
+int lk_vp_local_fill(lk_vp_system* h, int s, int dir) {
+  if (!h || s < 0 || s >= (int)h->sys.species.size() || dir < 0 || dir > 1) return LK_ERR_ARG;
+  auto* ks = h->sys.species[s];
+  return ks->periodicFill(ks->f_eval, 1 << dir, h->sys.st);
+}
 int lk_vp_stage_finish(lk_vp_system* h, int stage) {
   if (!h || stage < 0 || stage >= h->sys.nstages()) return LK_ERR_ARG;
   return h->sys.stageFinish(stage);
@@ -1041,6 +1073,7 @@ int lk_vm_set_state(lk_vm_system* h, int s, const double* f_host) {
   if (cudaMemcpy(ks->state(), f_host, sizeof(double) * ks->vol, cudaMemcpyHostToDevice) != cudaSuccess) return LK_ERR_CUDA;
   ks->f_eval = ks->state();
   ks->mom_valid = false;
+  ks->wrap_ptr = nullptr;
   return LK_OK;
 }
 int lk_vm_get_state(lk_vm_system* h, int s, double* f_host) {

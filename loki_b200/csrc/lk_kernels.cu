@@ -50,6 +50,7 @@ static DUpd make_upd(const lk_rk_update* u) {
     d.use_delta = u->use_delta;
     d.active = 1;
     d.n_prev = u->n_prev;
+    d.wrap = u->wrap;
     for (int j = 0; j < 7; ++j) {
       d.k_prev[j] = u->k_prev[j];
       d.c_prev[j] = u->c_prev[j];
@@ -610,14 +611,18 @@ cudaError_t moments_finish(double* d0, double* d1, double* d2, const double* par
   k_moment_finish<<<nblk((i64)d.nd[0] * d.nd[1], 128), 128, 0, st>>>(d, part, nparts, dv, w, d0, d1, d2, nmom);
   return LK_LAUNCHED();
 }
-// ke_e_dot from the first vx-moment: charge*dx*dy*dvx*dvy * sum_xy ext(x,y) * (sum_p part1[p][xy]); one CTA,
-// fixed-order tree (KineticSpeciesF.f:2563-2602 sums cell by cell; tolerance in the tests)
+// ke_e_dot from the first vx-moment: charge*dx*dy*dvx*dvy * sum_xy ext(x,y) * (sum_p part1[p][xy]);
+// fixed-order two-level tree (KineticSpeciesF.f:2563-2602 sums cell by cell; tolerance in the tests)
+constexpr int KE_BLOCKS = 148;
+__device__ double g_ke_part[KE_BLOCKS];
+__device__ unsigned int g_ke_count = 0;
 __global__ void k_ke_from_moment(DGeo g, const double* __restrict__ part1, int nparts, const double* __restrict__ ext,
                                  double scale, double* out) {
   __shared__ double sh[32];
+  __shared__ bool last;
   const int nxy = g.n[0] * g.n[1];
   double s = 0.0;
-  for (int t = threadIdx.x; t < nxy; t += blockDim.x) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nxy; t += gridDim.x * blockDim.x) {
     double m = 0.0;
     for (int p = 0; p < nparts; ++p) m += part1[(i64)p * nxy + t];
     const int i1 = t % g.n[0] + g.ng, i2 = t / g.n[0] + g.ng;
@@ -629,14 +634,27 @@ __global__ void k_ke_from_moment(DGeo g, const double* __restrict__ part1, int n
   if (threadIdx.x == 0) {
     double b = 0.0;
     for (int k = 0; k < (int)(blockDim.x >> 5); ++k) b += sh[k];
+    g_ke_part[blockIdx.x] = b;
+    __threadfence();
+    last = (atomicAdd(&g_ke_count, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  // the last block to finish adds the per-block sums in block order: deterministic whatever the schedule
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double b = 0.0;
+    for (int k = 0; k < (int)gridDim.x; ++k) b += ((volatile double*)g_ke_part)[k];
     out[0] = b * scale;
+    g_ke_count = 0;
   }
 }
 cudaError_t ke_from_moment(double* out, const double* part1, int nparts, const lk_geom* g, double charge,
                            const double* ext, cudaStream_t st) {
   DGeo d = make_geo(g);
   const double scale = charge * g->dx[0] * g->dx[1] * g->dx[2] * g->dx[3];
-  k_ke_from_moment<<<1, 1024, 0, st>>>(d, part1, nparts, ext, scale, out);
+  const int nxy = g->n[0] * g->n[1];
+  const int blocks = (int)min((i64)KE_BLOCKS, (i64)nblk(nxy, 256));
+  k_ke_from_moment<<<blocks, 256, 0, st>>>(d, part1, nparts, ext, scale, out);
   return LK_LAUNCHED();
 }
 

@@ -89,7 +89,7 @@ struct FaceScale {
 #if LK_STRICT
   static constexpr double v = 1.0;
 #else
-  static constexpr double v = (ORDER == 4) ? (1.0 / 12.0) : 1.0;
+  static constexpr double v = (ORDER == 4) ? (1.0 / 12.0) : (1.0 / 60.0);
 #endif
 };
 template <int ORDER>
@@ -130,12 +130,29 @@ struct Walker<4> {
     return F;
   }
 };
+template <>
+struct Walker<6> {
+  double u0, u1, u2, u3, u4, E0, E1, E2, E3;  // um3..up1 and their forward differences
+  template <class LD>
+  __device__ __forceinline__ void init(LD ld) {
+    u0 = ld(0); u1 = ld(1); u2 = ld(2); u3 = ld(3); u4 = ld(4);
+    E0 = ADD(u1, -u0); E1 = ADD(u2, -u1); E2 = ADD(u3, -u2); E3 = ADD(u4, -u3);
+  }
+  __device__ __forceinline__ double next(double un, bool pos) {
+    const double E4 = ADD(un, -u4);
+    const double F = w65_face60(u0, u1, u2, u3, u4, un, E0, E1, E2, E3, E4, pos);
+    u0 = u1; u1 = u2; u2 = u3; u3 = u4; u4 = un;
+    E0 = E1; E1 = E2; E2 = E3; E3 = E4;
+    return F;
+  }
+};
 #endif
 // the same face from its W values at once (vy direction, one-thread-per-cell kernel); identical bits
 template <int ORDER>
 __device__ __forceinline__ double fit_face(const double* w, bool pos) {
 #if !LK_STRICT
   if constexpr (ORDER == 4) return weno43_face12(w[0], w[1], w[2], w[3], pos);
+  else return weno65_face60(w[0], w[1], w[2], w[3], w[4], w[5], pos);
 #endif
   if constexpr (ORDER == 4) return weno43(w[0], w[1], w[2], w[3], pos);
   else return weno65(w[0], w[1], w[2], w[3], w[4], w[5], pos);
@@ -146,7 +163,7 @@ __device__ __forceinline__ double fit_face(const double* w, bool pos) {
 // vel4 of i4, KineticSpeciesF.f:78-80, 98-100), no earlier RK6 stage results to add; everything else is
 // decided at run time.
 template <int ORDER, int T0, int T1, int T2, int NT, bool TMA, bool LEAN>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, (MarchCfg<ORDER, T0, T1, T2>::SMEM_BYTES <= 113 * 1024) ? 2 : 1)
 k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restrict__ vel, const DAccel a,
               const DUpd upd, double* __restrict__ rhs_out, const int flags, const int nt0, const int nt1,
               const int nt2, const int chunk_len, const DMom mom, const __grid_constant__ MarchMaps maps) {
@@ -293,6 +310,14 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
   const double ax0 = (do_acc && simple_acc) ? __ldg(a.field + pxy) : 0.0;
   const double ay0 = (do_acc && simple_acc) ? __ldg(a.field + pxy + (i64)g.nd[0] * g.nd[1]) : 0.0;
   double* const racc = sAcc + eb1 * PA + ea0;  // + c*T1*PA: this thread's column of the accumulator
+  // periodic ghost copies of the predictor written by the cell that owns the value (upd.wrap): element
+  // offsets of this column's images, 0 = none.  The corner image keeps the whole data box consistent.
+  int gxo = 0, gyo = 0;
+  if (upd.active && col_ok) {
+    const int x = o0 + ea0, y = o1 + eb1;
+    if ((upd.wrap & 1) && g.n[0] >= 2 * ng) gxo = (x < ng) ? g.n[0] : ((x >= g.n[0] - ng) ? -g.n[0] : 0);
+    if ((upd.wrap & 2) && g.n[1] >= 2 * ng) gyo = (y < ng) ? g.n[1] * (int)g.s[1] : ((y >= g.n[1] - ng) ? -g.n[1] * (int)g.s[1] : 0);
+  }
 
   // ---- march -------------------------------------------------------------------------------------
   // EK: epilogue kind, decided once per kernel (uniform) so that the per-cell code carries no pointer
@@ -526,7 +551,14 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
             } else {
               pr = rk_axpy(fo[c], upd.c_pred, rk_delta(upd, res[c], di[c], true));
             }
-            if (live) pr_p[oc] = pr;
+            if (live) {
+              pr_p[oc] = pr;
+              if (gxo) pr_p[oc + gxo] = pr;
+              if (gyo) {
+                pr_p[oc + gyo] = pr;
+                if (gxo) pr_p[oc + gyo + gxo] = pr;
+              }
+            }
             if (mom.nmom > 0) {
               const double prm = live ? pr : 0.0;
               const int cc = FULL ? c : min(c, max(ncv - 1, 0));
@@ -548,6 +580,11 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
               if (upd.delta_out) upd.delta_out[idx] = dl;
               const double pr = rk_pred(upd, upd.f_old[idx], upd.use_delta ? dl : res[c], idx);
               pr_p[c * s2] = pr;
+              if (gxo) pr_p[c * s2 + gxo] = pr;
+              if (gyo) {
+                pr_p[c * s2 + gyo] = pr;
+                if (gxo) pr_p[c * s2 + gyo + gxo] = pr;
+              }
               if (mom.nmom > 0) {
                 psum = ADD(psum, pr);
                 if (mom.nmom > 1) {

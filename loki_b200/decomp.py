@@ -178,7 +178,7 @@ class DistributedVP:
         return self.H.lk_vp_state_ptr(self.sys, s)
 
     def _exchange_halos(self):
-        L, st = self.L, self.stream
+        L, H, st = self.L, self.H, self.stream
         for s in range(self.nsp):
             f = self.H.lk_vp_eval_ptr(self.sys, s)
             g = C.byref(self.geoms[s])
@@ -186,7 +186,7 @@ class DistributedVP:
                 self.halo[s],
                 lambda buf, side, d: L.lk_halo_pack(buf.data_ptr(), f, g, d, side, st),
                 lambda buf, side, d: L.lk_halo_unpack(f, buf.data_ptr(), g, d, side, st),
-                lambda d: L.lk_periodic_fill_4d(f, g, int(d == 0), int(d == 1), st))
+                lambda d, s=s: H.lk_vp_local_fill(self.sys, s, d))
 
     def _gather_rho(self):
         dist = self.dist
