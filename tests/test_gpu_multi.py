@@ -101,7 +101,11 @@ def test_two_rank_step_matches_single_rank(lk, px, py, order, rk):
             den = np.where(want != 0.0, np.abs(want), 1.0)
             err = np.max(np.abs(got - want) / den)
             assert err <= 1e-12, "species %d rank %d: %g" % (s, rank, err)
-    # the stable time step is a global minimum: every rank reports the single-rank value
+    # the stable time step is a global minimum: every rank reports the same value, equal to the single-rank
+    # one up to the rounding of the net charge density (electron and ion densities cancel to ~1e-5 of
+    # their size, and the partial-sum partition of the velocity integrals depends on the tile shape, so
+    # the field -- and max|a| with it -- moves at the 1e-11 level; the reference's MPI_Reduce has the same
+    # sensitivity to the rank count)
     for rank, lo, n, res, dts in multi:
-        assert abs(dts - single[4]) <= 1e-12 * abs(single[4])
+        assert abs(dts - single[4]) <= 1e-9 * abs(single[4])
         assert dts == multi[0][4]
