@@ -292,7 +292,9 @@ def run_own(args):
         def e2e_step():
             for s in range(nsp):
                 H.lk_vp_set_state(sys_, s, bufs[s].data_ptr())
+            vp.invalidate_halos()
             step(dt)
+            vp.synchronize()
             for s in range(nsp):
                 H.lk_vp_get_state(sys_, s, bufs[s].data_ptr())
 

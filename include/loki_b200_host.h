@@ -97,6 +97,9 @@ int lk_vp_stage_field(lk_vp_system* sys, int stage, const int* tiles);
  * no-op when the fused stage kernel has already written those ghost cells (lk_rk_update::wrap) */
 int lk_vp_local_fill(lk_vp_system* sys, int s, int dir);
 int lk_vp_stage_finish(lk_vp_system* sys, int stage);
+/* the same for one species: lets the caller start the halo exchange of species s's new predictor
+ * (lk_vp_eval_ptr(s) after this call) on another stream while the next species' stage kernel runs */
+int lk_vp_stage_finish_species(lk_vp_system* sys, int stage, int s);
 int lk_vp_end_step(lk_vp_system* sys);
 
 /* reference-ordered, UNFUSED evaluation of one RHS (VPSystem::evalRHS) of the current state into

@@ -36,6 +36,7 @@ def build(force=False, verbose=False):
         (["-DLK_STRICT=0"], "lk_kernels.cu", "lk_kernels_fast.o"),
         (["-DLK_STRICT=1", "-fmad=false"], "lk_kernels.cu", "lk_kernels_strict.o"),
         ([], "lk_capi.cu", "lk_capi.o"),
+        ([], "lk_fft.cu", "lk_fft.o"),
         ([], "lk_host.cu", "lk_host.o"),
     ]
     procs = []

@@ -84,7 +84,18 @@ size_t g_prof_used = 0;
 struct lk_poisson_plan {
   int nx, ny, ng, order;
   double *sx, *sy, *cx, *cy, *T, *X;  // device
+  double *F1, *F2, *npart;            // device: FFT work arrays (power-of-two grids, production arithmetic)
 };
+
+// lk_fft.cu: O(N log N) production solve for power-of-two grids
+namespace lkfft {
+bool supported(int nx, int ny);
+int neutralize_scratch_doubles();
+cudaError_t neutralize(double* rho, int n1, int n2, int ng, double* part, cudaStream_t st, int64_t* launches);
+cudaError_t poisson_fft(double* phi, const double* rho, int nx, int ny, int ng, const double* sx, const double* sy,
+                        const double* cx, const double* cy, double* F1, double* F2, cudaStream_t st, int64_t* launches);
+}
+static int64_t g_fft_launches = 0;
 
 extern "C" {
 
@@ -109,7 +120,7 @@ int lk_device_count(void) {
   }
   return n;
 }
-int64_t lk_launch_count(void) { return lkfast::launches() + lkstrict::launches(); }
+int64_t lk_launch_count(void) { return lkfast::launches() + lkstrict::launches() + g_fft_launches; }
 
 int lk_weno_fit(int order, const double* u, const double* vel, double* face, int64_t count, void* stream) {
   if ((order != 4 && order != 6) || count < 0 || (count > 0 && (!u || !vel || !face))) return fail(LK_ERR_ARG, "lk_weno_fit: bad argument");
@@ -308,6 +319,11 @@ int lk_poisson_plan_create(lk_poisson_plan** plan, int nx, int ny, int ng, int o
   up(&p->sx, sx); up(&p->sy, sy); up(&p->cx, cx); up(&p->cy, cy);
   if (e == cudaSuccess) e = cudaMalloc((void**)&p->T, sizeof(double) * 2 * nx * nyh);
   if (e == cudaSuccess) e = cudaMalloc((void**)&p->X, sizeof(double) * 2 * nx * nyh);
+  if (lkfft::supported(nx, ny)) {
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->F1, sizeof(double) * 2 * (size_t)nx * ny);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->F2, sizeof(double) * 2 * (size_t)nx * ny);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->npart, sizeof(double) * lkfft::neutralize_scratch_doubles());
+  }
   if (e != cudaSuccess) {
     lk_poisson_plan_destroy(p);
     return cuda_fail(e, "lk_poisson_plan_create");
@@ -318,6 +334,7 @@ int lk_poisson_plan_create(lk_poisson_plan** plan, int nx, int ny, int ng, int o
 void lk_poisson_plan_destroy(lk_poisson_plan* p) {
   if (!p) return;
   cudaFree(p->sx); cudaFree(p->sy); cudaFree(p->cx); cudaFree(p->cy); cudaFree(p->T); cudaFree(p->X);
+  cudaFree(p->F1); cudaFree(p->F2); cudaFree(p->npart);
   delete p;
 }
 int lk_electric_field(lk_poisson_plan* p, double* rho, double* phi, double* em, const double* dx, void* stream) {
@@ -325,8 +342,14 @@ int lk_electric_field(lk_poisson_plan* p, double* rho, double* phi, double* em, 
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   // EMSolverBase::electricField (EMSolverBase.C:270-371), single EM "processor" branch
-  e = DISPATCH(neutralize)(rho, p->nx, p->ny, p->ng, st);
-  if (e == cudaSuccess) e = DISPATCH(poisson_dft)(phi, rho, p->nx, p->ny, p->ng, p->sx, p->sy, p->cx, p->cy, p->T, p->X, st);
+  if (!g_strict && p->F1) {
+    // production arithmetic on a power-of-two grid: two-level neutralisation sum + FFT passes
+    e = lkfft::neutralize(rho, p->nx, p->ny, p->ng, p->npart, st, &g_fft_launches);
+    if (e == cudaSuccess) e = lkfft::poisson_fft(phi, rho, p->nx, p->ny, p->ng, p->sx, p->sy, p->cx, p->cy, p->F1, p->F2, st, &g_fft_launches);
+  } else {
+    e = DISPATCH(neutralize)(rho, p->nx, p->ny, p->ng, st);
+    if (e == cudaSuccess) e = DISPATCH(poisson_dft)(phi, rho, p->nx, p->ny, p->ng, p->sx, p->sy, p->cx, p->cy, p->T, p->X, st);
+  }
   if (e == cudaSuccess) e = DISPATCH(periodic_fill_2d)(phi, p->nx, p->ny, p->ng, 1, 1, 1, st);
   const size_t pl = (size_t)(p->nx + 2 * p->ng) * (p->ny + 2 * p->ng);
   if (e == cudaSuccess) e = cudaMemsetAsync(em, 0, sizeof(double) * 2 * pl, st);  // m_em_vars = 0.0

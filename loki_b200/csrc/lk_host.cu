@@ -467,7 +467,9 @@ struct VPSystem {
   }
 
   // ---- RK4Integrator::stageAdvance / RK6 stage, fused behind the RHS evaluation ----
-  int stageFinish(int stage) {
+  // `only`: restrict to one species (the multi-rank driver interleaves the species' halo exchanges with
+  // the other species' stage kernels); nullptr = all species in order
+  int stageFinish(int stage, KineticSpecies* only = nullptr) {
     const bool rk4 = desc.rk_order == 4;
     const int last = nstages() - 1;
     static const double A6[8][8] = {
@@ -492,6 +494,7 @@ struct VPSystem {
       t_stage = time + c6[stage] * dt;
     }
     for (auto* ks : species) {
+      if (only && ks != only) continue;
       // (4) acceleration; the maxima are only consumed by the next stableDt -> last stage
       LKH_CHECK(ks->computeAcceleration(em_local.p, t_stage, desc.xlo, desc.tile_lo, stage == last, st));
       // (5) velocity-boundary fill, then advection + acceleration derivatives + RK update in one pass
@@ -1033,6 +1036,10 @@ int lk_vp_local_fill(lk_vp_system* h, int s, int dir) {
 int lk_vp_stage_finish(lk_vp_system* h, int stage) {
   if (!h || stage < 0 || stage >= h->sys.nstages()) return LK_ERR_ARG;
   return h->sys.stageFinish(stage);
+}
+int lk_vp_stage_finish_species(lk_vp_system* h, int stage, int s) {
+  if (!h || stage < 0 || stage >= h->sys.nstages() || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  return h->sys.stageFinish(stage, h->sys.species[s]);
 }
 int lk_vp_end_step(lk_vp_system* h) { return h ? h->sys.endStep() : LK_ERR_ARG; }
 int lk_vp_eval_rhs(lk_vp_system* h, double** rhs_dev, double time) { return (h && rhs_dev) ? h->sys.evalRHS(rhs_dev, time) : LK_ERR_ARG; }

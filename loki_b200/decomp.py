@@ -10,8 +10,11 @@ velocity space stays whole on each GPU, so per stage a rank
   2. swaps `ng` layers of f with its x neighbours, then with its y neighbours (periodic wrap is an
      ordinary neighbour; axis-aligned stencils need no corner messages),
 
-one process per GPU over torch.distributed (NCCL on the box, gloo in the CPU tests).  This module is the
-host logic only: tile arithmetic, neighbour ranks, message ordering.  Packing, unpacking and everything
+one process per GPU over torch.distributed (NCCL on the box, gloo in the CPU tests).  The exchange of a
+species' new predictor is issued on a second CUDA stream and its own NCCL communicator as soon as that
+species' stage kernel has been queued, so it travels over NVLink while the next species' stage kernel (and
+the small moment / field work of the next stage) runs; a stage kernel only waits for its own species'
+halos.  This module is the host logic only: tile arithmetic, neighbour ranks, message ordering.  Packing, unpacking and everything
 else that touches 4D data are CUDA kernels behind the C ABI (lk_halo_pack / lk_halo_unpack); the
 exchanger takes them as callables so the CPU tests can drive the same message logic on host arrays.
 """
@@ -118,6 +121,22 @@ class HaloExchanger:
             unpack(rhi, 1, d)
 
 
+class _GroupDist:
+    """torch.distributed with every point-to-point op bound to one process group"""
+
+    def __init__(self, dist, group):
+        self._d, self._g = dist, group
+        self.isend, self.irecv = dist.isend, dist.irecv
+
+    def P2POp(self, op, tensor, peer, tag=0):
+        if self._g is None:
+            return self._d.P2POp(op, tensor, peer, tag=tag)
+        return self._d.P2POp(op, tensor, peer, group=self._g, tag=tag)
+
+    def batch_isend_irecv(self, ops):
+        return self._d.batch_isend_irecv(ops)
+
+
 class DistributedVP:
     """The stage loop of RK4Integrator / RK6Integrator (RK4Integrator.H:66-171) around the C++ host
     mirror when configuration space is cut over several ranks: lk_vp_* stage pieces with the two
@@ -155,7 +174,16 @@ class DistributedVP:
             self.rho_padded = None if layout.uniform() else torch.zeros(self.world * self.max_cells, dtype=f64, device=device)
             capi.check(self.H.lk_vp_set_comm_buffers(self.sys, self.rho_tile.data_ptr(), self.rho_gather.data_ptr()),
                        "lk_vp_set_comm_buffers")
-            self.exchanger = HaloExchanger(layout, rank, dist)
+            # halo traffic gets its own communicator: c10d gives every process group one NCCL stream, and the
+            # (tiny) rho all-gather of the next stage must not queue behind a species' face messages
+            self.halo_group = dist.new_group(ranks=list(range(self.world))) if hasattr(dist, "new_group") else None
+            self.exchanger = HaloExchanger(layout, rank, _GroupDist(dist, self.halo_group))
+            on_gpu = device is not None and str(device).startswith("cuda")
+            self.main_stream = torch.cuda.current_stream(device) if on_gpu else None
+            self.comm_stream = torch.cuda.Stream(device=device) if on_gpu else None
+            self.ev_stage = [torch.cuda.Event() for _ in range(self.nsp)] if on_gpu else None
+            self.ev_halo = [torch.cuda.Event() for _ in range(self.nsp)] if on_gpu else None
+            self.halo_ready = [False] * self.nsp   # the evaluated state of species s has its x/y ghosts
             self.halo = []
             for s in range(self.nsp):
                 bufs = {}
@@ -177,16 +205,50 @@ class DistributedVP:
     def state_ptr(self, s):
         return self.H.lk_vp_state_ptr(self.sys, s)
 
-    def _exchange_halos(self):
-        L, H, st = self.L, self.H, self.stream
-        for s in range(self.nsp):
-            f = self.H.lk_vp_eval_ptr(self.sys, s)
-            g = C.byref(self.geoms[s])
-            self.exchanger.exchange(
-                self.halo[s],
-                lambda buf, side, d: L.lk_halo_pack(buf.data_ptr(), f, g, d, side, st),
-                lambda buf, side, d: L.lk_halo_unpack(f, buf.data_ptr(), g, d, side, st),
-                lambda d, s=s: H.lk_vp_local_fill(self.sys, s, d))
+    def _exchange_halos(self, s, stream):
+        """x-then-y face exchange of species s's evaluated state; every kernel and message on `stream`"""
+        L, H = self.L, self.H
+        st = C.c_void_p(stream.cuda_stream) if stream is not None else self.stream
+        f = self.H.lk_vp_eval_ptr(self.sys, s)
+        g = C.byref(self.geoms[s])
+
+        def local_fill(d):
+            # a direction that is not cut wraps inside the rank; the fused stage kernel has normally written
+            # those ghost cells already and the call is a no-op.  It runs on the system's own stream, so the
+            # two streams are ordered around it (x before y, ParallelArray.H:580-606).
+            if stream is not None:
+                e = self.torch.cuda.Event()
+                e.record(stream)
+                self.main_stream.wait_event(e)
+            H.lk_vp_local_fill(self.sys, s, d)
+            if stream is not None:
+                e = self.torch.cuda.Event()
+                e.record(self.main_stream)
+                stream.wait_event(e)
+
+        self.exchanger.exchange(
+            self.halo[s],
+            lambda buf, side, d: L.lk_halo_pack(buf.data_ptr(), f, g, d, side, st),
+            lambda buf, side, d: L.lk_halo_unpack(f, buf.data_ptr(), g, d, side, st),
+            local_fill)
+
+    def _start_exchange(self, s):
+        """queue the exchange of species s's evaluated state behind everything the main stream holds now"""
+        torch = self.torch
+        if self.comm_stream is None:
+            self._exchange_halos(s, None)
+        else:
+            self.ev_stage[s].record(self.main_stream)
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(self.ev_stage[s])
+                self._exchange_halos(s, self.comm_stream)
+                self.ev_halo[s].record(self.comm_stream)
+        self.halo_ready[s] = True
+
+    def invalidate_halos(self):
+        """call after writing a state from outside (lk_vp_set_state): its ghosts must be exchanged again"""
+        if self.world > 1:
+            self.halo_ready = [False] * self.nsp
 
     def _gather_rho(self):
         dist = self.dist
@@ -210,9 +272,19 @@ class DistributedVP:
             capi.check(H.lk_vp_stage_moments(self.sys, stage), "lk_vp_stage_moments")
             self._gather_rho()
             capi.check(H.lk_vp_stage_field(self.sys, stage, self.tiles_arr), "lk_vp_stage_field")
-            self._exchange_halos()
-            capi.check(H.lk_vp_stage_finish(self.sys, stage), "lk_vp_stage_finish")
+            for s in range(self.nsp):
+                if not self.halo_ready[s]:
+                    self._start_exchange(s)       # first stage after a state upload
+                if self.comm_stream is not None:
+                    self.main_stream.wait_event(self.ev_halo[s])
+                capi.check(H.lk_vp_stage_finish_species(self.sys, stage, s), "lk_vp_stage_finish_species")
+                # the new predictor's faces leave now, under the next species' stage kernel
+                self._start_exchange(s)
         capi.check(H.lk_vp_end_step(self.sys), "lk_vp_end_step")
+
+    def synchronize(self):
+        if self.world > 1 and self.comm_stream is not None:
+            self.comm_stream.synchronize()
 
     def stable_dt(self):
         """KineticSpecies::computeDt over all ranks: the velocity-space maxima (axmax, aymax) are maxima over

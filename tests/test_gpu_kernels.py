@@ -277,8 +277,11 @@ def test_ke_e_dot(lk, ok):
 
 
 # ---------------------------------------------------------------- Poisson
-@pytest.mark.parametrize("nx,ny,order", [(32, 32, 4), (10, 10, 6), (16, 7, 4), (12, 5, 6)])
+@pytest.mark.parametrize("nx,ny,order", [(32, 32, 4), (10, 10, 6), (16, 7, 4), (12, 5, 6), (64, 128, 4), (256, 16, 6),
+                                         (4, 8, 4)])
 def test_electric_field(lk, ok, nx, ny, order):
+    """power-of-two grids take the shared-memory FFT path in production arithmetic (lk_fft.cu), all others
+    and the strict build the direct DFT; both against the oracle's DFT and numpy's FFT"""
     import torch
     ng = 2 if order == 4 else 3
     Lx, Ly = 18.85, 31.4
@@ -317,7 +320,12 @@ def test_electric_field(lk, ok, nx, ny, order):
         if strict_mode:
             assert np.array_equal(_np(drho), r) and np.array_equal(_np(dphi), phi) and np.array_equal(_np(dem), em)
         else:
-            assert rel_err(_np(dphi), phi) < tol and rel_err(_np(dem), em) < tol
+            # the (0,0) mode is left as it is (LokiPoissonSolveFFT.C:150-158): phi carries the rounding residue
+            # of sum(rho - mean), N*eps-sized and dependent on the summation order, as a constant offset
+            dp = _np(dphi) - phi
+            dp[ng:-ng, ng:-ng] -= dp[ng:-ng, ng:-ng].mean()
+            assert np.max(np.abs(dp[ng:-ng, ng:-ng])) < tol * np.max(np.abs(phi))
+            assert rel_err(_np(dem), em) < tol
     lk.lk_poisson_plan_destroy(plan)
 
 

@@ -58,6 +58,7 @@ def _run_rank(rank, world, port, px, py, order, rk, nsteps, dt, out):
         for _ in range(nsteps):
             vp.advance(dt)
         dts = vp.stable_dt()
+        vp.synchronize()
         for s in range(vp.nsp):
             o = np.empty(tuple(reversed(vp.geoms[s].nd)))
             assert vp.H.lk_vp_get_state(vp.sys, s, o.ctypes.data) == 0
