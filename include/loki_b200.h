@@ -61,7 +61,8 @@ typedef struct lk_accel {
 typedef struct lk_inflow {
   int kind;          /* 0: zero inflow; 1: factored fnorm*fv(i3,i4)*fx(i1,i2)*frac
                         (PerturbedMaxwellianIC.C:267-289); 2: fx*fv + fx2*fv2
-                        (InterpenetratingStreamIC.C:265-286); 3: explicit ghost-layer tables */
+                        (InterpenetratingStreamIC.C:275-278, two-sided); 3: explicit ghost-layer tables;
+                        4: fv*fx*fx2 (InterpenetratingStreamIC.C:279-281, centred) */
   const double* fx;  /* device (n1d,n2d)  */
   const double* fv;  /* device (n3d,n4d)  */
   const double* fx2; /* kind 2 */

@@ -62,7 +62,11 @@ double* lk_vp_eval_ptr(lk_vp_system* sys, int s);
 /* factored initial condition used for inflow at the velocity boundaries
  * (PerturbedMaxwellianIC.C:267-289); fx: (n1d,n2d) of this rank, fv: (n3d,n4d); host pointers */
 int lk_vp_set_inflow(lk_vp_system* sys, int s, const double* fx, const double* fv, double fnorm, double frac);
-/* 1: refill ghosts in evalRHS exactly like the reference (default); cheap, kept for clarity */
+/* the two factored forms of InterpenetratingStreamIC::getIC_At_Pt (InterpenetratingStreamIC.C:265-286):
+ * kind 2 (two-sided) fx*fv + fx2*fv2, kind 4 (centred) fv*fx*fx2; fnorm is folded into fv / fv2 as the
+ * reference's cache does (:240-252) */
+int lk_vp_set_inflow2(lk_vp_system* sys, int s, int kind, const double* fx, const double* fv, const double* fx2,
+                      const double* fv2);
 int lk_vp_set_time(lk_vp_system* sys, double t);
 double lk_vp_time(const lk_vp_system* sys);
 

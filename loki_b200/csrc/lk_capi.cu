@@ -154,7 +154,8 @@ int lk_set_acceleration_bcs_4d(double* f, const lk_geom* g, const lk_accel* a, c
   if (!geom_ok(g) || !accel_ok(a) || !f || !at) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d: bad argument");
   if (g->n[2] < 3 || g->n[3] < 3) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d: need >= 3 velocity cells");
   if (ic) {
-    if (ic->kind < 0 || ic->kind > 3) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d: bad inflow kind");
+    if (ic->kind < 0 || ic->kind > 4) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d: bad inflow kind");
+    if (ic->kind == 4 && (!ic->fx || !ic->fv || !ic->fx2)) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d: missing inflow tables");
     if ((ic->kind == 1 || ic->kind == 2) && (!ic->fx || !ic->fv)) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d: missing inflow tables");
     if (ic->kind == 2 && (!ic->fx2 || !ic->fv2)) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d: missing second inflow term");
     if (ic->kind == 3 && (!ic->ghost3 || !ic->ghost4)) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d: missing ghost tables");

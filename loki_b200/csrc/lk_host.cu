@@ -185,7 +185,7 @@ struct KineticSpecies {
   // velocity-ghost layers are ever read by setaccelerationbcs4d)
   DevBuf<double> Jx_s, Jy_s, Jz_s, ic_ghost3, ic_ghost4;
   // inflow (initial condition) tables
-  DevBuf<double> ic_fx, ic_fv;
+  DevBuf<double> ic_fx, ic_fv, ic_fx2, ic_fv2;
   lk_inflow inflow;
   bool has_driver = false;
   // periodic x/y ghost cells already written by the fused stage kernel (lk_rk_update::wrap) for this array
@@ -980,6 +980,25 @@ int lk_vp_set_inflow(lk_vp_system* h, int s, const double* fx, const double* fv,
   ks->inflow.fv = ks->ic_fv.p;
   ks->inflow.fnorm = fnorm;
   ks->inflow.frac = frac;
+  return LK_OK;
+}
+int lk_vp_set_inflow2(lk_vp_system* h, int s, int kind, const double* fx, const double* fv, const double* fx2,
+                      const double* fv2) {
+  if (!h || !fx || !fv || !fx2 || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  if (!(kind == 2 || kind == 4) || (kind == 2 && !fv2)) return LK_ERR_ARG;
+  auto* ks = h->sys.species[s];
+  const size_t nxy = (size_t)ks->n1d * ks->n2d, nv = (size_t)ks->n3d * ks->n4d;
+  int st = ks->ic_fx.upload(std::vector<double>(fx, fx + nxy));
+  if (st == LK_OK) st = ks->ic_fv.upload(std::vector<double>(fv, fv + nv));
+  if (st == LK_OK) st = ks->ic_fx2.upload(std::vector<double>(fx2, fx2 + nxy));
+  if (st == LK_OK && kind == 2) st = ks->ic_fv2.upload(std::vector<double>(fv2, fv2 + nv));
+  if (st != LK_OK) return st;
+  memset(&ks->inflow, 0, sizeof(ks->inflow));
+  ks->inflow.kind = kind;
+  ks->inflow.fx = ks->ic_fx.p;
+  ks->inflow.fv = ks->ic_fv.p;
+  ks->inflow.fx2 = ks->ic_fx2.p;
+  ks->inflow.fv2 = (kind == 2) ? ks->ic_fv2.p : nullptr;
   return LK_OK;
 }
 int lk_vp_set_time(lk_vp_system* h, double t) {

@@ -254,8 +254,10 @@ __device__ __forceinline__ double inflow_value(const DInflow& ic, const DGeo& g,
   switch (ic.kind) {
     case 1:  // PerturbedMaxwellianIC.C:279-281
       return ic.fnorm * ic.fv[pv] * ic.fx[pxy] * ic.frac;
-    case 2:  // InterpenetratingStreamIC.C:265-286
+    case 2:  // InterpenetratingStreamIC.C:275-278, two-sided
       return ic.fx[pxy] * ic.fv[pv] + ic.fx2[pxy] * ic.fv2[pv];
+    case 4:  // InterpenetratingStreamIC.C:279-281, centred: fv*fx*fx2 in this order
+      return ic.fv[pv] * ic.fx[pxy] * ic.fx2[pxy];
     case 3: {
       if (dir == 3) {
         int layer = (i3 < g.ng) ? i3 : (i3 - g.n[2]);  // [0,ng) below, [ng,2ng) above

@@ -12,7 +12,7 @@ import numpy as np
 class Species:
     def __init__(self, name, nv, vlim, mass, charge, tx=1.0, ty=1.0, A=0.0, B=0.0, Cc=0.0, kx1=0.0, ky1=0.0,
                  kx2=0.0, ky2=0.0, frac=1.0, driver=None, bz=0.0, vx0=0.0, vy0=0.0, x_wave_number=0.0,
-                 y_wave_number=0.0, flow_phase=0.0):
+                 y_wave_number=0.0, flow_phase=0.0, stream=None):
         self.name, self.nv, self.vlim, self.mass, self.charge = name, nv, vlim, mass, charge
         self.tx, self.ty, self.A, self.B, self.Cc = tx, ty, A, B, Cc
         self.kx1, self.ky1, self.kx2, self.ky2, self.frac = kx1, ky1, kx2, ky2, frac
@@ -20,6 +20,10 @@ class Species:
         # flow-velocity wave of the Perturbed Maxwellian (PerturbedMaxwellianIC.C:393-410): a non-zero vx0/vy0
         # makes the initial condition non-factorable (:395-397)
         self.vx0, self.vy0, self.x_wave_number, self.y_wave_number, self.flow_phase = vx0, vy0, x_wave_number, y_wave_number, flow_phase
+
+        # "Interpenetrating Stream" initial condition, half-plane syntax (InterpenetratingStreamIC.C:496-540):
+        # dict(tl, tt, theta, d, beta, floor, frac, frac2, two_sided, centered)
+        self.stream = stream
 
     @property
     def factorable(self):
@@ -70,7 +74,60 @@ class Deck:
         fnorm = sp.mass / (2.0 * math.pi * math.sqrt(sp.tx * sp.ty))
         return np.ascontiguousarray(fx), np.ascontiguousarray(fv), fnorm
 
+    def stream_tables(self, sp, tile_lo=(0, 0), tile_n=None):
+        """InterpenetratingStreamIC::cache, half-plane syntax (InterpenetratingStreamIC.C:112-252):
+        fx, fx2 (n2d,n1d) and fv, fv2 (n4d,n3d) with fnorm folded into fv; fx2 / fv2 None when unused"""
+        st = sp.stream
+        ng = self.ng
+        tile_n = tile_n or self.n
+        n, dx = self.geom_of(sp)
+        Lx, Ly = self.n[0] * dx[0], self.n[1] * dx[1]
+        x1 = self.xlim[0] + (np.arange(-ng, tile_n[0] + ng) + tile_lo[0] + 0.5) * dx[0]
+        x2 = self.xlim[2] + (np.arange(-ng, tile_n[1] + ng) + tile_lo[1] + 0.5) * dx[1]
+        x1 = np.where(x1 < self.xlim[0], x1 + Lx, np.where(x1 > self.xlim[1], x1 - Lx, x1))
+        x2 = np.where(x2 < self.xlim[2], x2 + Ly, np.where(x2 > self.xlim[3], x2 - Ly, x2))
+        erf = np.vectorize(math.erf)
+        th, beta, floor = st["theta"], st["beta"], st.get("floor", 0.0)
+        xi0 = -st["d"]
+        xi = x1[None, :] * math.cos(th) + x2[:, None] * math.sin(th)
+        fx2 = None
+        if st.get("two_sided"):
+            fx = floor / 2.0 + (st["frac"] - floor) * 0.5 * (1.0 + erf(-beta * (xi - xi0)))
+            fx2 = floor / 2.0 + (st["frac2"] - floor) * 0.5 * (1.0 + erf(beta * (xi + xi0)))
+        elif st.get("centered"):
+            fx = floor + (math.sqrt(st["frac"]) - floor) * 0.5 * (1.0 + erf(-beta * (xi - xi0)))
+            fx2 = floor + (math.sqrt(st["frac"]) - floor) * 0.5 * (1.0 + erf(beta * (xi + xi0)))
+        else:
+            fx = floor + (st["frac"] - floor) * 0.5 * (1.0 + erf(-beta * (xi - xi0)))
+        x3 = sp.vlim[0] + (np.arange(-ng, sp.nv[0] + ng) + 0.5) * dx[2]
+        x4 = sp.vlim[2] + (np.arange(-ng, sp.nv[1] + ng) + 0.5) * dx[3]
+        vl = x3[None, :] * math.cos(th) + x4[:, None] * math.sin(th)
+        vt = -x3[None, :] * math.sin(th) + x4[:, None] * math.cos(th)
+        thl, tht = st["tl"] / sp.mass, st["tt"] / sp.mass
+        fnorm = sp.mass / (2.0 * math.pi * math.sqrt(st["tl"] * st["tt"]))
+        # vl0 = vt0 = 0 in the decks: both thermal objects are the same Maxwellian (MaxwellianThermal.C:40-59)
+        fv = fnorm * np.exp(-0.5 * ((vl - 0.0) * (vl - 0.0) / thl + (vt - 0.0) * (vt - 0.0) / tht))
+        fv2 = fv.copy() if st.get("two_sided") else None
+        c = np.ascontiguousarray
+        return c(fx), (c(fx2) if fx2 is not None else None), c(fv), (c(fv2) if fv2 is not None else None)
+
+    def inflow_kind(self, sp):
+        if sp.stream is None:
+            return 1 if sp.factorable else 3
+        return 2 if sp.stream.get("two_sided") else (4 if sp.stream.get("centered") else 1)
+
     def initial_state(self, sp, tile_lo=(0, 0), tile_n=None):
+        if sp.stream is not None:
+            # getIC_At_Pt (InterpenetratingStreamIC.C:265-286); returns fnorm = 1 (already inside fv)
+            fx, fx2, fv, fv2 = self.stream_tables(sp, tile_lo, tile_n)
+            X, V = fx[None, None, :, :], fv[:, :, None, None]
+            if sp.stream.get("two_sided"):
+                f = X * V + fx2[None, None, :, :] * fv2[:, :, None, None]
+            elif sp.stream.get("centered"):
+                f = (V * X) * fx2[None, None, :, :]
+            else:
+                f = V * X
+            return np.ascontiguousarray(f), fx, fv, 1.0
         fx, fv, fnorm = self.ic_tables(sp, tile_lo, tile_n)
         if not sp.factorable:
             return self.initial_state_full(sp, fx, fnorm), fx, fv, fnorm
@@ -108,6 +165,20 @@ class Deck:
         return np.ascontiguousarray(g3), np.ascontiguousarray(g4)
 
     # ---- product side ----
+    def set_inflow(self, H, sys_, s, tile_lo=(0, 0), tile_n=None):
+        """hand species s's inflow (initial-condition) tables to a lk_vp_system in the form its IC class has"""
+        sp = self.species[s]
+        kind = self.inflow_kind(sp)
+        if sp.stream is not None and kind in (2, 4):
+            fx, fx2, fv, fv2 = self.stream_tables(sp, tile_lo, tile_n)
+            return H.lk_vp_set_inflow2(sys_, s, kind, fx.ctypes.data, fv.ctypes.data, fx2.ctypes.data,
+                                       fv2.ctypes.data if fv2 is not None else None)
+        if sp.stream is not None:
+            fx, fx2, fv, fv2 = self.stream_tables(sp, tile_lo, tile_n)
+            return H.lk_vp_set_inflow(sys_, s, fx.ctypes.data, fv.ctypes.data, 1.0, 1.0)
+        fx, fv, fnorm = self.ic_tables(sp, tile_lo, tile_n)
+        return H.lk_vp_set_inflow(sys_, s, fx.ctypes.data, fv.ctypes.data, fnorm, sp.frac)
+
     def product_desc(self, tile_lo=(0, 0), tile_n=None, ntiles=1):
         from .host import SpeciesDesc, VPDesc
         tile_n = tile_n or self.n
@@ -157,6 +228,26 @@ def plane_iaw(n=(32, 32), nv=(64, 32), order=4, rk=4, A=0.0):
     i = Species("ion", nv, (-10 / ialpha, 10 / ialpha, -10 / ialpha, 10 / ialpha), 100.0, 1.0, tx=0.1, ty=0.1,
                 A=A, kx1=klde, ky1=klde / 78)
     return Deck("planeIAW" + ("_6" if order == 6 else ""), n, (xa, xb, ya, yb), [e, i], order=order, rk=rk)
+
+
+def interpenetrating_streams(n=(128, 7), nv=(24, 16), order=6, rk=6):
+    """test/InterpenetratingStreams/InterpenetratingStreams.pp: electrons, He, C; order 6 / RK6, cfl 0.95;
+    y limits scale with Ny so that dx = dy as in the deck"""
+    mp_over_me = 1836.0
+    m_he, m_c = 4.0 * mp_over_me, 12.0 * mp_over_me
+    vth_he, vth_c = perl15(math.sqrt(1.0 / m_he)), perl15(math.sqrt(1.0 / m_c))
+    xa, xb = -62.5, 62.5
+    dx = perl15((xb - xa) / n[0])
+    ya, yb = perl15(-0.5 * n[1] * dx), perl15(0.5 * n[1] * dx)
+    common = dict(tl=1.0, tt=1.0, theta=0.0, d=31.25)
+    e = Species("electron", nv, (-7.5, 7.5, -7.5, 7.5), 1.0, -1.0,
+                stream=dict(common, beta=0.768, two_sided=True, floor=0.05, frac=10.0, frac2=10.0))
+    lim_he = tuple(perl15(v * 7.5 * vth_he) for v in (-1, 1, -1, 1))
+    he = Species("He", nv, lim_he, m_he, 2.0, stream=dict(common, beta=-0.768, centered=True, floor=0.0, frac=0.025))
+    lim_c = tuple(perl15(v * 7.5 * vth_c) for v in (-1, 1, -1, 1))
+    cfrac = perl15(5.0 / 3.0)
+    c = Species("C", nv, lim_c, m_c, 6.0, stream=dict(common, beta=0.768, two_sided=True, floor=0.0, frac=cfrac, frac2=cfrac))
+    return Deck("InterpenetratingStreams", n, (xa, xb, ya, yb), [e, he, c], order=order, rk=rk, cfl=0.95)
 
 
 def perl15(x):

@@ -52,6 +52,7 @@ _PROTOS = {
     "lk_vp_state_ptr": (_vp, [_vp, C.c_int]),
     "lk_vp_eval_ptr": (_vp, [_vp, C.c_int]),
     "lk_vp_set_inflow": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_double, C.c_double]),
+    "lk_vp_set_inflow2": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "lk_vp_set_time": (C.c_int, [_vp, C.c_double]),
     "lk_vp_time": (C.c_double, [_vp]),
     "lk_vp_stable_dt": (C.c_int, [_vp, C.POINTER(C.c_double)]),

@@ -18,9 +18,25 @@ class Deck(_d.Deck):
             arr[k].mass, arr[k].charge, arr[k].bz_const = sp.mass, sp.charge, sp.bz
             arr[k].vlo[0], arr[k].vlo[1] = sp.vlim[0], sp.vlim[2]
             arr[k].vhi[0], arr[k].vhi[1] = sp.vlim[1], sp.vlim[3]
-            fx, fv, fnorm = self.ic_tables(sp)
+            if sp.stream is not None:
+                fx, fx2, fv, fv2 = self.stream_tables(sp)
+                kind = self.inflow_kind(sp)
+                if kind == 2:      # InterpenetratingStreamIC.C:275-278
+                    def cb(ctx, i1, i2, i3, i4, fx=fx, fv=fv, fx2=fx2, fv2=fv2):
+                        return fx[i2, i1] * fv[i4, i3] + fx2[i2, i1] * fv2[i4, i3]
+                elif kind == 4:    # :279-281
+                    def cb(ctx, i1, i2, i3, i4, fx=fx, fv=fv, fx2=fx2):
+                        return fv[i4, i3] * fx[i2, i1] * fx2[i2, i1]
+                else:
+                    def cb(ctx, i1, i2, i3, i4, fx=fx, fv=fv):
+                        return fv[i4, i3] * fx[i2, i1]
+                fx = fv = None
+            else:
+                fx, fv, fnorm = self.ic_tables(sp)
             frac = sp.frac
-            if sp.factorable:
+            if sp.stream is not None:
+                pass
+            elif sp.factorable:
                 def cb(ctx, i1, i2, i3, i4, fx=fx, fv=fv, fnorm=fnorm, frac=frac):
                     return fnorm * fv[i4, i3] * fx[i2, i1] * frac
             else:
@@ -47,6 +63,10 @@ class VMDeck(_d.VMDeck, Deck):
 def _wrap(d):
     d.__class__ = VMDeck if isinstance(d, _d.VMDeck) else Deck
     return d
+
+
+def interpenetrating_streams(*a, **k):
+    return _wrap(_d.interpenetrating_streams(*a, **k))
 
 
 def em_damping(*a, **k):

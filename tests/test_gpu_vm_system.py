@@ -191,8 +191,8 @@ def test_vm_deck_run_traces(lk, ok, fast):
     rvz_d = torch.zeros(vz[0].shape, dtype=torch.float64, device="cuda")
     assert H.lk_vm_eval_rhs(sys_, (C.c_void_p * 1)(rhs_d.data_ptr()), rem_d.data_ptr(), (C.c_void_p * 1)(rvz_d.data_ptr()), 0.0) == 0
     ax, ay = np.zeros(1), np.zeros(1)
-    ok.ok_vm_eval_rhs(w, _ptrs([np.zeros_like(states[0])]), np.zeros_like(em), _ptrs([np.zeros_like(vz[0])]),
-                      _ptrs(f_old), em_old, _ptrs(vz_old), 0.0, ax, ay)
+    rhs0, rvz0 = [np.zeros_like(states[0])], [np.zeros_like(vz[0])]   # kept alive: written through raw pointers
+    ok.ok_vm_eval_rhs(w, _ptrs(rhs0), np.zeros_like(em), _ptrs(rvz0), _ptrs(f_old), em_old, _ptrs(vz_old), 0.0, ax, ay)
     t = 0.0
     for step in range(4):
         dt_o = deck.cfl * ok.ok_vm_stable_dt(w, ax, ay, 4)
