@@ -266,18 +266,22 @@ def run_own(args):
     avg_bytes = cells_launch * (sum(STAGE_BYTES) / len(STAGE_BYTES))
     avg_ms = tot_ms.value / max(1, n_l.value)
     achieved = avg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    traffic = None
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, averaged over the launches of
+    # one step, from the committed ncu pass of this same command (tools/ncu_traffic.py writes the file)
+    traffic, traffic_src = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        traffic = tr["dram_bytes_per_cell"] * cells_launch
+        if abs(tr["cells_per_launch"] - cells_launch) < 0.5:
+            traffic, traffic_src = tr["dram_bytes_per_launch"], tr.get("source")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "k_stage_march (fused WENO RHS + RK4 stage update + velocity moments)",
                 "algorithmic_bytes_per_launch": avg_bytes, "avg_launch_ms": avg_ms, "timed_launches": n_l.value,
                 "kernel_share_of_step": tot_ms.value / ms if ms > 0 else None, "peak_source": peak_src,
-                "note": "co-limited by the fp64 pipe (about 125 fp64 instructions per cell-update, ceiling "
-                        "~150 G cell-updates/s at 1.965 GHz); see DESIGN.md section 3"}
+                "traffic_source": traffic_src,
+                "note": "co-limited by the fp64 pipe (111 fp64 instructions per cell-update by ncu, ceiling "
+                        "168 G cell-updates/s at 1.965 GHz); see DESIGN.md section 3"}
 
     # ---- e2e: the same step with HOST buffers (pinned), H2D of the state + step + D2H of the result ----
     e2e = None

@@ -65,5 +65,21 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_variant(name, defines):
+    """development aid: a second library `libloki_b200_<name>.so` whose production kernels are compiled
+    with extra -D flags (A/B experiments on one GPU box; LOKI_B200_LIB selects it at load time).  The other
+    objects are shared with the main build."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    build()
+    bdir = os.path.join(HERE, "build")
+    o = os.path.join(bdir, "lk_kernels_fast_%s.o" % name)
+    cmd = [nvcc] + ARCH + COMMON + ["-DLK_STRICT=0"] + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, "lk_kernels.cu"), "-o", o]
+    subprocess.check_call(cmd)
+    out = os.path.join(HERE, "libloki_b200_%s.so" % name)
+    objs = [o] + [os.path.join(bdir, f) for f in ("lk_kernels_strict.o", "lk_capi.o", "lk_fft.o", "lk_host.o")]
+    subprocess.check_call([nvcc] + ARCH + ["-shared", "-o", out] + objs)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -52,7 +52,8 @@ class StageMoments(C.Structure):
 
 
 def library_path():
-    return os.path.join(_HERE, "libloki_b200.so")
+    # LOKI_B200_LIB: development aid for A/B kernel experiments (loki_b200.build.build_variant)
+    return os.environ.get("LOKI_B200_LIB") or os.path.join(_HERE, "libloki_b200.so")
 
 
 _vp = C.c_void_p

@@ -44,7 +44,8 @@ struct MarchCfg {
   // sAcc doubles as the landing zone of the f_old tile (TMA, once the accumulator has been read into
   // registers); NACC more doubles hold the delta_in tile
   static constexpr int SMEM_DOUBLES = NS * NCORE + 2 * NYH + 2 * NVH + 2 * NACC;
-  static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES + 8 * (NS + 3);
+  // + the (vx, vy) cell-centre velocities of the tile's T2 slices for the current and the next vy plane
+  static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES + 8 * (NS + 3) + sizeof(double) * 4 * T2;
 };
 
 struct MarchMaps {
@@ -171,6 +172,11 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
   constexpr int NG = C::NG, W = C::W, NS = C::NS, SX = C::SX, PC = C::PC, PA = C::PA;
   static_assert(T0 * T1 == NT, "the vy/epilogue phase maps one thread to one (x,y) column of the tile");
   static_assert(T0 % SX == 0 && (T0 % 2) == 0, "x segments");
+#ifdef LK_EXP_NOSLICE
+  constexpr bool WARP_SLICE = false;
+#else
+  constexpr bool WARP_SLICE = (T0 == 32) && (T1 * (T0 / SX) == 32) && (NT == 32 * T2);
+#endif
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* smem = reinterpret_cast<double*>(smem_raw);
   double* sCore = smem;                       // NS slots
@@ -179,12 +185,21 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
   double* sAcc = sVh + 2 * C::NVH;            // [c][b1][PA]
   double* sDi = sAcc + C::NACC;               // [c][b1][PA]  delta_in of the plane being updated
   unsigned long long* bars = (unsigned long long*)(sDi + C::NACC);  // NS core barriers, y, v, RK operands
+  double* sVel = (double*)(bars + NS + 3);                          // [plane parity][vx | vy][T2]
 
   const int tid = threadIdx.x;
   int b = blockIdx.x;
+  // x tiles fastest, then y, then vx: the CTAs resident together cover whole (x,y) planes of a few vx
+  // slices (measured 1 % faster than vx-before-y)
+#ifdef LK_EXP_ORDER_V
   const int o0 = (b % nt0) * T0; b /= nt0;
   const int o2 = (b % nt2) * T2; b /= nt2;
   const int o1 = (b % nt1) * T1; b /= nt1;
+#else
+  const int o0 = (b % nt0) * T0; b /= nt0;
+  const int o1 = (b % nt1) * T1; b /= nt1;
+  const int o2 = (b % nt2) * T2; b /= nt2;
+#endif
   const int chunk = b;
   const int ng = g.ng;  // == NG
   const int q0 = chunk * chunk_len;                       // first interior vy plane of this CTA
@@ -278,6 +293,15 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
     const bool ok = col_ok && (o2 + c < g.n[2]);
     uold[c] = ok ? f[col + g.s[2] * c + g.s[3] * (pbase - 1)] : 0.0;
   }
+  // velocities of the slices at plane p: one warp fetches them a plane ahead, every sweep reads shared memory
+  auto stage_vel = [&](int p) {
+    if (tid < 2 * T2) {
+      const int c = tid % T2, comp = tid / T2;
+      const int i3 = min(o2 + c, g.n[2] - 1) + ng;
+      sVel[(p & 1) * 2 * T2 + tid] = __ldg(vel + i3 + (i64)g.nd[2] * (p + (i64)comp * g.nd[3]));
+    }
+  };
+  if (vel) stage_vel(q0 + ng);
   if (!TMA) __syncthreads();
   for (int k = 0; k < NS; ++k) wait_core(k);
   if (do_acc) {
@@ -338,8 +362,9 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
       const int sc = (p - pbase) % NS;            // its ring slot
       const double* cur = sCore + sc * C::NCORE;
       const bool more = (q + 1 < q0 + nq);
+      const double* const sv = sVel + (p & 1) * 2 * T2;  // [vx(c) | vy(c)] of this plane
 
-      // pull the next plane's RK operands towards L2 (one 128-byte line per thread)
+#ifdef LK_EXP_L2PF  // measured: the explicit L2 prefetch of the next plane's RK operands costs 2 % (A/B on one box)
       if (upd.active && more) {
         constexpr int LPR = (T0 * 8 + 127) / 128;  // lines per row
         for (int e = tid; e < T1 * T2 * LPR; e += NT) {
@@ -351,6 +376,7 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
           }
         }
       }
+#endif
 
       // ---------------- x sweep: rows (b1, c) in segments of SX cells ----------------
       {
@@ -359,7 +385,11 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
         for (int it = 0; it < (ITEMS + NT - 1) / NT; ++it) {
           const int l = tid + it * NT;
           if ((ITEMS % NT) != 0 && l >= ITEMS) break;
-          const int row = l % (T1 * T2), seg = l / (T1 * T2);
+          // WARP_SLICE: warp w owns the vx slice c = w in both the x and the y sweep (its 32 lanes are the
+          // slice's T1 rows x T0/SX segments here, its T0 columns there), so the two sweeps of a slice are
+          // ordered by __syncwarp() and the CTA needs no barrier between them
+          const int row = WARP_SLICE ? ((l >> 5) * T1 + (l & 31) % T1) : l % (T1 * T2);
+          const int seg = WARP_SLICE ? ((l & 31) / T1) : l / (T1 * T2);
           const int b1 = row % T1, c = row / T1;
           double* arow = sAcc + row * PA + seg * SX;
           double init[SX];
@@ -373,8 +403,7 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
             }
           }
           if (do_adv) {
-            const int i3 = min(o2 + c, g.n[2] - 1) + ng;
-            const double vx = __ldg(vel + i3 + (i64)g.nd[2] * p);
+            const double vx = sv[c];
             const bool pos = vx > 0.0;
             const double2* r2 = reinterpret_cast<const double2*>(cur + row * PC + seg * SX);
             double v[SX + W];
@@ -398,7 +427,8 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
           for (int k = 0; k < SX; ++k) arow[k] = init[k];
         }
       }
-      __syncthreads();
+      if constexpr (WARP_SLICE) __syncwarp();
+      else __syncthreads();
 
       // ---------------- y sweep: lines (a0, c) ----------------
       if (TMA) { mbar_wait(&bars[NS], ph_y); ph_y ^= 1u; }
@@ -409,8 +439,7 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
           const int l = tid + it * NT;
           if ((ITEMS % NT) != 0 && l >= ITEMS) break;
           const int a0 = l % T0, c = l / T0;
-          const int i3 = min(o2 + c, g.n[2] - 1) + ng;
-          const double vy = __ldg(vel + i3 + (i64)g.nd[2] * (p + (i64)g.nd[3]));
+          const double vy = sv[T2 + c];
           const bool pos = vy > 0.0;
           const double* core = cur + c * T1 * PC + NG + a0;        // + b1*PC
           const double* hlo = sYh + c * NG * PC + NG + a0;         // + h*PC
@@ -492,7 +521,6 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
       const int s_new = (p + NG - pbase) % NS;
       wait_core(s_new);  // always: no TMA write may be outstanding when the CTA exits
       {
-        const double* velp = vel + o2 + ng + (i64)g.nd[2] * p;
         double* do_p = upd.delta_out + idx0;
         double* pr_p = upd.pred + idx0;
         if (do_acc) {
@@ -564,8 +592,8 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
               const int cc = FULL ? c : min(c, max(ncv - 1, 0));
               psum = ADD(psum, prm);
               if (mom.nmom > 1) {
-                pvx = FMA(__ldg(velp + cc), prm, pvx);
-                pvy = FMA(__ldg(velp + cc + (i64)g.nd[2] * g.nd[3]), prm, pvy);
+                pvx = FMA(sv[cc], prm, pvx);
+                pvy = FMA(sv[T2 + cc], prm, pvy);
               }
             }
           }
@@ -588,8 +616,8 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
               if (mom.nmom > 0) {
                 psum = ADD(psum, pr);
                 if (mom.nmom > 1) {
-                  pvx = FMA(__ldg(velp + c), pr, pvx);
-                  pvy = FMA(__ldg(velp + c + (i64)g.nd[2] * g.nd[3]), pr, pvy);
+                  pvx = FMA(sv[c], pr, pvx);
+                  pvy = FMA(sv[T2 + c], pr, pvy);
                 }
               }
             }
@@ -603,6 +631,7 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
           }
         }
       }
+      if (more && vel) stage_vel(p + 1);
       __syncthreads();
       if (more) {
         stage_vh(p + 1);

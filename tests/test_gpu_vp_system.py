@@ -285,3 +285,76 @@ def test_several_steps_production_vs_oracle(lk, ok, fast):
         assert star_rel_err(out, f_old, f_old, ng) <= 1e-12
     H.lk_vp_destroy(sys_)
     ok.ok_vp_work_destroy(w)
+
+
+def _select_dt(time, dt_stable_cfl, last_save, save_times, max_time):
+    """Simulation::selectTimeStep (Simulation.C:464-485): dt honours the plot frequency"""
+    next_time = (last_save + 1) * save_times
+    final_time = min(next_time, max_time)
+    remaining = final_time - time
+    if dt_stable_cfl <= remaining:
+        n = int(np.ceil(remaining / dt_stable_cfl))
+        return remaining / n
+    return remaining * (1.0 + 10 * np.finfo(float).eps)
+
+
+def test_regression_run_traces_plane_iaw(lk, ok, fast):
+    """a regression-style run of the planeIAW deck (two species, driven electrons) on a reduced grid: the
+    reference's own time-step selection (cfl * stableDt snapped to save_times = 0.2) to t = 0.4, production
+    arithmetic on the device against the oracle.  North-star tolerances: time-history traces (field energy,
+    max |Ex|, the integrated driver work ke_e_dot) within 1e-10 at every step, the distribution within 1e-12
+    relative to its stencil neighbourhood at the end."""
+    import torch
+    deck = decks.plane_iaw(n=(12, 8), nv=(20, 12), A=0.03)
+    w, sp, keep = _oracle(ok, deck)
+    states = [deck.initial_state(s)[0] for s in deck.species]
+    ns = len(states)
+    H, sys_ = _product(deck, states, None)
+    ng = deck.ng
+    n1d, n2d = deck.n[0] + 2 * ng, deck.n[1] + 2 * ng
+    I2 = (slice(None), slice(ng, -ng), slice(ng, -ng))
+    # seeding evalRHS (VPSystem.C:227-230)
+    rhs_d = [torch.zeros(s.shape, dtype=torch.float64, device="cuda") for s in states]
+    assert H.lk_vp_eval_rhs(sys_, (C.c_void_p * ns)(*[r.data_ptr() for r in rhs_d]), 0.0) == 0
+    f_old = [s.copy() for s in states]
+    f_new = [np.zeros_like(s) for s in states]
+    rhs0 = [np.zeros_like(s) for s in states]
+    ax, ay = np.zeros(ns), np.zeros(ns)
+    ok.ok_vp_eval_rhs(w, _ptrs(rhs0), _ptrs(f_old), 0.0, np.zeros(ns), ax, ay)
+    ke = np.zeros(ns)
+    t, last_save, save_times, t_final = 0.0, 0, 0.2, 0.4
+    nsteps = 0
+    while t < t_final - 1e-12:
+        dt_o = _select_dt(t, deck.cfl * ok.ok_vp_stable_dt(w, ax, ay, deck.rk), last_save, save_times, t_final)
+        dt_d = C.c_double()
+        assert H.lk_vp_stable_dt(sys_, C.byref(dt_d)) == 0
+        dt_dev = _select_dt(t, deck.cfl * dt_d.value, last_save, save_times, t_final)
+        assert abs(dt_dev - dt_o) <= 1e-10 * dt_o          # same number of sub-steps to the next save time
+        ok.ok_vp_rk4_step(w, _ptrs(f_new), _ptrs(f_old), t, dt_o, ke)
+        assert H.lk_vp_set_time(sys_, t) == 0
+        assert H.lk_vp_advance(sys_, dt_o) == 0
+        t += dt_o
+        nsteps += 1
+        if t >= (last_save + 1) * save_times - 1e-12:
+            last_save += 1
+        f_old, f_new = f_new, f_old
+        ok.ok_vp_last_accel_max(w, ax, ay)
+        em_o = np.ctypeslib.as_array(ok.ok_vp_em_vars(w), shape=(2, n2d, n1d))
+        em_d = np.empty_like(em_o)
+        assert lk.lk_sync(None) == 0
+        assert lk.lk_memcpy_d2h(em_d.ctypes.data, H.lk_vp_em_vars_ptr(sys_), em_d.nbytes) == 0
+        # the field of the last RK stage of the step, as both sides hold it
+        e_o, e_d = float(np.sum(em_o[I2] ** 2)), float(np.sum(em_d[I2] ** 2))
+        assert abs(e_d - e_o) <= 1e-10 * e_o
+        m_o, m_d = float(np.max(np.abs(em_o[0][I2[1:]]))), float(np.max(np.abs(em_d[0][I2[1:]])))
+        assert abs(m_d - m_o) <= 1e-10 * m_o
+        v = C.c_double()
+        assert H.lk_vp_ke_e_dot(sys_, 0, C.byref(v)) == 0
+        assert abs(v.value - ke[0]) <= 1e-10 * abs(ke[0]) + 1e-300
+    assert nsteps >= 4 and abs(t - t_final) < 1e-12
+    for s in range(ns):
+        out = np.empty_like(states[s])
+        assert H.lk_vp_get_state(sys_, s, out.ctypes.data) == 0
+        assert star_rel_err(out, f_old[s], f_old[s], ng) <= 1e-12
+    H.lk_vp_destroy(sys_)
+    ok.ok_vp_work_destroy(w)

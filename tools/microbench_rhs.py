@@ -69,16 +69,18 @@ def main():
     for _ in range(2):
         run()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.reps):
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.reps)]
+    for e0, e1 in evs:
+        e0.record()
         run()
-    e1.record()
+        e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / a.reps
+    times = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
+    ms = sum(times) / len(times)
     bpc = 40 if a.mode == "stage" else 16
-    print("n=%s order=%d variant=%d strict=%d mode=%s: %.3f ms/launch, %.2f Gcell/s, %.1f GB/s algorithmic (%d B/cell)" % (
-        n, a.order, a.variant, int(a.strict), a.mode, ms, cells / ms / 1e6, cells * bpc / ms / 1e6, bpc))
+    print("n=%s order=%d variant=%d strict=%d mode=%s: %.3f ms/launch, %.2f Gcell/s, %.1f GB/s algorithmic (%d B/cell)  [min %.3f median %.3f ms, %s]" % (
+        n, a.order, a.variant, int(a.strict), a.mode, ms, cells / ms / 1e6, cells * bpc / ms / 1e6, bpc, times[0],
+        times[len(times) // 2], os.path.basename(os.environ.get("LOKI_B200_LIB", "libloki_b200.so"))))
 
 
 if __name__ == "__main__":
