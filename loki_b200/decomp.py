@@ -176,11 +176,22 @@ class DistributedVP:
                        "lk_vp_set_comm_buffers")
             # halo traffic gets its own communicator: c10d gives every process group one NCCL stream, and the
             # (tiny) rho all-gather of the next stage must not queue behind a species' face messages
-            self.halo_group = dist.new_group(ranks=list(range(self.world))) if hasattr(dist, "new_group") else None
+            # (high-priority streams: the stage kernel fills every SM, so the small pack / NCCL / unpack kernels
+            # of the exchange must win the CTA slots that free up instead of queueing behind its 4096 CTAs)
+            self.halo_group = None
+            if hasattr(dist, "new_group"):
+                opts = None
+                try:
+                    if dist.get_backend() == "nccl":
+                        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                except Exception:
+                    opts = None
+                self.halo_group = dist.new_group(ranks=list(range(self.world)), pg_options=opts) if opts is not None \
+                    else dist.new_group(ranks=list(range(self.world)))
             self.exchanger = HaloExchanger(layout, rank, _GroupDist(dist, self.halo_group))
             on_gpu = device is not None and str(device).startswith("cuda")
             self.main_stream = torch.cuda.current_stream(device) if on_gpu else None
-            self.comm_stream = torch.cuda.Stream(device=device) if on_gpu else None
+            self.comm_stream = torch.cuda.Stream(device=device, priority=-1) if on_gpu else None
             self.ev_stage = [torch.cuda.Event() for _ in range(self.nsp)] if on_gpu else None
             self.ev_halo = [torch.cuda.Event() for _ in range(self.nsp)] if on_gpu else None
             self.halo_ready = [False] * self.nsp   # the evaluated state of species s has its x/y ghosts
