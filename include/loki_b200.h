@@ -204,6 +204,17 @@ int lk_maxwell_rhs(double* rhs, const double* em, const double* Jx, const double
                    int n1, int n2, int ng, int order, const double* dx, double light_speed, double av_weak,
                    double av_strong, void* stream);
 
+/* ---- time-history diagnostics (called at sequence_write_times, not on the stage path) ----
+ * computeke_ / computekemaxwell_ (KineticSpeciesF.f:2447-2559): out5_dev = {ke, ke_x, ke_y, px, py}; with
+ * vz != NULL the Maxwell flavour: ke includes 0.5 m vz(x,y)^2 f and px = py = 0.  Tree sums (deterministic). */
+int lk_compute_ke(double* out5_dev, const double* f, const lk_geom* g, double mass, const double* velocities,
+                  const double* vz, void* stream);
+/* Poisson::accumulateSequences (Poisson.C:796-860), ncomp = 2: out_dev = {e_max, e_tot, ex_max, ey_max,
+ * e_sum_tot}; Maxwell::accumulateSequences (Maxwell.C:753-875), ncomp = 6: {e_max, e_tot, ex_max, ey_max,
+ * ez_max, e_sum_tot, b_max, b_tot, bx_max, by_max, bz_max, b_sum_tot} */
+int lk_field_history(double* out_dev, const double* em_vars, int n1, int n2, int ng, int ncomp, const double* dx,
+                     void* stream);
+
 /* ---- device memory helpers for hosts without their own allocator (synchronous) ---- */
 int lk_malloc(void** p, int64_t bytes);
 int lk_free(void* p);

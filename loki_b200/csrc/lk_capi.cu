@@ -96,6 +96,14 @@ cudaError_t poisson_fft(double* phi, const double* rho, int nx, int ny, int ng, 
                         const double* cx, const double* cy, double* F1, double* F2, cudaStream_t st, int64_t* launches);
 }
 static int64_t g_fft_launches = 0;
+// lk_diag.cu: time-history diagnostics
+namespace lkdiag {
+int ke_scratch_doubles();
+cudaError_t compute_ke(double* out5, const double* f, const lk_geom* g, double mass, const double* velocities,
+                       const double* vz, double* scratch, cudaStream_t st, int64_t* launches);
+cudaError_t field_history(double* out, const double* em, int n1, int n2, int ng, int ncomp, double dx, double dy,
+                          cudaStream_t st, int64_t* launches);
+}
 
 extern "C" {
 
@@ -358,6 +366,17 @@ int lk_electric_field(lk_poisson_plan* p, double* rho, double* phi, double* em, 
   if (e == cudaSuccess) e = DISPATCH(periodic_fill_2d)(em, p->nx, p->ny, p->ng, 2, 1, 1, st);
   if (e != cudaSuccess) return cuda_fail(e, "lk_electric_field");
   return LK_OK;
+}
+int lk_compute_ke(double* out5, const double* f, const lk_geom* g, double mass, const double* velocities, const double* vz,
+                  void* stream) {
+  if (!geom_ok(g) || !out5 || !f || !velocities) return fail(LK_ERR_ARG, "lk_compute_ke: bad argument");
+  double* s = scratch(3, sizeof(double) * lkdiag::ke_scratch_doubles());
+  if (!s) return cuda_fail(cudaGetLastError(), "lk_compute_ke: scratch");
+  CHECK_LAUNCH(lkdiag::compute_ke(out5, f, g, mass, velocities, vz, s, (cudaStream_t)stream, &g_fft_launches), "lk_compute_ke");
+}
+int lk_field_history(double* out, const double* em, int n1, int n2, int ng, int ncomp, const double* dx, void* stream) {
+  if (!out || !em || !dx || n1 < 1 || n2 < 1 || ng < 0 || !(ncomp == 2 || ncomp == 6)) return fail(LK_ERR_ARG, "lk_field_history: bad argument");
+  CHECK_LAUNCH(lkdiag::field_history(out, em, n1, n2, ng, ncomp, dx[0], dx[1], (cudaStream_t)stream, &g_fft_launches), "lk_field_history");
 }
 int lk_periodic_fill_2d(double* u, int n1, int n2, int ng, int ncomp, int px, int py, void* stream) {
   if (!u || n1 < 1 || n2 < 1 || ng < 1 || ncomp < 1) return fail(LK_ERR_ARG, "lk_periodic_fill_2d: bad argument");

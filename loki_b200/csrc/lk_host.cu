@@ -1064,6 +1064,36 @@ int lk_vp_end_step(lk_vp_system* h) { return h ? h->sys.endStep() : LK_ERR_ARG; 
 int lk_vp_eval_rhs(lk_vp_system* h, double** rhs_dev, double time) { return (h && rhs_dev) ? h->sys.evalRHS(rhs_dev, time) : LK_ERR_ARG; }
 const double* lk_vp_em_vars_ptr(const lk_vp_system* h) { return h ? h->sys.em_g.p : nullptr; }
 const double* lk_vp_rho_ptr(const lk_vp_system* h) { return h ? h->sys.rho_g.p : nullptr; }
+int lk_vp_time_history(lk_vp_system* h, double* out, int capacity) {
+  // VPSystem::accumulateSequences (VPSystem.C:591-636) without probes / particles / flux histories:
+  // Poisson's five field histories of the field of the last evalRHS, then per species computeke's five
+  // and the integrated driver work
+  if (!h || !out) return LK_ERR_ARG;
+  auto& S = h->sys;
+  const int ns = (int)S.species.size(), count = 5 + 6 * ns;
+  if (capacity < count) return LK_ERR_ARG;
+  loki::DevBuf<double> d;
+  int st = d.alloc(5 + 5 * ns);
+  if (st != LK_OK) return st;
+  st = lk_field_history(d.p, S.em_g.p, S.desc.nglobal[0], S.desc.nglobal[1], S.ng, 2, S.dxg, S.st);
+  for (int s = 0; s < ns && st == LK_OK; ++s) {
+    auto* ks = S.species[s];
+    st = lk_compute_ke(d.p + 5 + 5 * s, ks->state(), &ks->g, ks->mass, ks->velocities.p, nullptr, S.st);
+  }
+  if (st != LK_OK) return st;
+  if (cudaStreamSynchronize(S.st) != cudaSuccess) return LK_ERR_CUDA;
+  std::vector<double> hbuf(5 + 5 * ns);
+  if (cudaMemcpy(hbuf.data(), d.p, sizeof(double) * hbuf.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return LK_ERR_CUDA;
+  for (int k = 0; k < 5; ++k) out[k] = hbuf[k];
+  for (int s = 0; s < ns; ++s) {
+    for (int k = 0; k < 5; ++k) out[5 + 6 * s + k] = hbuf[5 + 5 * s + k];
+    double v = 0.0;
+    if (S.species[s]->has_driver && cudaMemcpy(&v, S.species[s]->ke.p, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+      return LK_ERR_CUDA;
+    out[5 + 6 * s + 5] = v;
+  }
+  return count;
+}
 int lk_vp_ke_e_dot(lk_vp_system* h, int s, double* value) {
   if (!h || !value || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
   if (cudaStreamSynchronize(h->sys.st) != cudaSuccess) return LK_ERR_CUDA;
@@ -1186,6 +1216,26 @@ int lk_vm_lambda_max(lk_vm_system* h, int s, double out[2]) {
   out[0] = h->sys.species[s]->lambda_max[2];
   out[1] = h->sys.species[s]->lambda_max[3];
   return LK_OK;
+}
+int lk_vm_time_history(lk_vm_system* h, double* out, int capacity) {
+  // VMSystem's histories without probes / particles: Maxwell's twelve field histories of the current
+  // em_vars, then per species computekemaxwell's {ke, ke_x, ke_y, px = 0, py = 0}
+  if (!h || !out) return LK_ERR_ARG;
+  auto& S = h->sys;
+  const int ns = (int)S.species.size(), count = 12 + 5 * ns;
+  if (capacity < count) return LK_ERR_ARG;
+  loki::DevBuf<double> d;
+  int st = d.alloc(count);
+  if (st != LK_OK) return st;
+  st = lk_field_history(d.p, S.emState(), S.n1, S.n2, S.ng, 6, S.dxg, S.st);
+  for (int s = 0; s < ns && st == LK_OK; ++s) {
+    auto* ks = S.species[s];
+    st = lk_compute_ke(d.p + 12 + 5 * s, ks->state(), &ks->g, ks->mass, ks->velocities.p, S.vzState(s), S.st);
+  }
+  if (st != LK_OK) return st;
+  if (cudaStreamSynchronize(S.st) != cudaSuccess) return LK_ERR_CUDA;
+  if (cudaMemcpy(out, d.p, sizeof(double) * count, cudaMemcpyDeviceToHost) != cudaSuccess) return LK_ERR_CUDA;
+  return count;
 }
 int lk_vm_eval_rhs(lk_vm_system* h, double** rhs_dev, double* rhs_em_dev, double** rhs_vz_dev, double time) {
   return (h && rhs_dev && rhs_em_dev && rhs_vz_dev) ? h->sys.evalRHS(rhs_dev, rhs_em_dev, rhs_vz_dev, time) : LK_ERR_ARG;

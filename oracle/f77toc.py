@@ -25,7 +25,8 @@ import sys
 ROUTINES = {
     "KineticSpeciesF.f": ["xpby4d", "setphasespacevel4d", "setphasespacevelmaxwell4d", "weno43fit4d",
                           "weno65fit4d", "setaccelerationbcs4d", "computeadvectionderivatives4d",
-                          "computeaccelerationderivatives4d", "computecurrents", "computekeedot"],
+                          "computeaccelerationderivatives4d", "computecurrents", "computekeedot", "computeke",
+                          "computekemaxwell"],
     "PoissonF.f": ["neutralizecharge4d", "computeefieldfrompotential"],
     "MaxwellF.f": ["maxwellevalrhs", "sgmetricfunction", "maxwellevalvzrhs", "xpby2d"],
 }

@@ -734,3 +734,110 @@ void ok_maxwell_eval_vz_rhs(double* rhs, const double* em, double charge_per_mas
   for (int i2 = ng; i2 < ng + n2; ++i2)
     for (int i1 = ng; i1 < ng + n1; ++i1) rhs[i1 + n1d * i2] = charge_per_mass * em[i1 + n1d * i2 + 2 * pl];
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Time-history diagnostics.
+ * computeke (KineticSpeciesF.f:2447-2500): out = {ke, ke_x, ke_y, px, py}; the running sums start from
+ * the incoming values like the Fortran's (the caller zeroes them, KineticSpecies.C:1198-1213).
+ * computekemaxwell (KineticSpeciesF.f:2504-2559): out = {ke, ke_x, ke_y} with ke = ke_x + ke_y + ke_z.
+ * ------------------------------------------------------------------------------------------ */
+void ok_compute_ke(const ok_geom* g, const double* u, double mass, const double* velocities, double* out5) {
+  const int ng = g->ng;
+  const int64_t n3d = ND(2), n4d = ND(3);
+  double ke_x = out5[1], ke_y = out5[2], px = out5[3], py = out5[4];
+  const double dx = g->dx[0], dy = g->dx[1], dvx = g->dx[2], dvy = g->dx[3];
+  for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
+    for (int i3 = ng; i3 < ng + g->n[2]; ++i3) {
+      double vx = velocities[i3 + n3d * (i4 + n4d * 0)];
+      double vx2 = vx * vx;
+      double vy = velocities[i3 + n3d * (i4 + n4d * 1)];
+      double vy2 = vy * vy;
+      for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
+        for (int i1 = ng; i1 < ng + g->n[0]; ++i1) {
+          double this_u = F4(u, i1, i2, i3, i4);
+          ke_x = ke_x + 0.5 * this_u * vx2;
+          ke_y = ke_y + 0.5 * this_u * vy2;
+          px = px + this_u * vx;
+          py = py + this_u * vy;
+        }
+    }
+  ke_x = ke_x * mass * dx * dy * dvx * dvy;
+  ke_y = ke_y * mass * dx * dy * dvx * dvy;
+  px = px * mass * dx * dy * dvx * dvy;
+  py = py * mass * dx * dy * dvx * dvy;
+  out5[0] = ke_x + ke_y;
+  out5[1] = ke_x; out5[2] = ke_y; out5[3] = px; out5[4] = py;
+}
+void ok_compute_ke_maxwell(const ok_geom* g, const double* u, double mass, const double* velocities,
+                           const double* vz_in, double* out3) {
+  const int ng = g->ng;
+  const int64_t n3d = ND(2), n4d = ND(3), n1d = ND(0);
+  double ke_x = out3[1], ke_y = out3[2], ke_z = 0.0;
+  const double dx = g->dx[0], dy = g->dx[1], dvx = g->dx[2], dvy = g->dx[3];
+  for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
+    for (int i3 = ng; i3 < ng + g->n[2]; ++i3) {
+      double vx = velocities[i3 + n3d * (i4 + n4d * 0)];
+      double vx2 = vx * vx;
+      double vy = velocities[i3 + n3d * (i4 + n4d * 1)];
+      double vy2 = vy * vy;
+      for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
+        for (int i1 = ng; i1 < ng + g->n[0]; ++i1) {
+          double vz = vz_in[i1 + n1d * i2];
+          double vz2 = vz * vz;
+          double this_u = F4(u, i1, i2, i3, i4);
+          ke_x = ke_x + 0.5 * this_u * vx2;
+          ke_y = ke_y + 0.5 * this_u * vy2;
+          ke_z = ke_z + 0.5 * this_u * vz2;
+        }
+    }
+  ke_x = ke_x * mass * dx * dy * dvx * dvy;
+  ke_y = ke_y * mass * dx * dy * dvx * dvy;
+  ke_z = ke_z * mass * dx * dy * dvx * dvy;
+  out3[0] = ke_x + ke_y + ke_z;
+  out3[1] = ke_x; out3[2] = ke_y;
+}
+/* Poisson::accumulateSequences (Poisson.C:796-860, ncomp = 2): out = {e_max, e_tot, ex_max, ey_max, e_sum_tot};
+ * Maxwell::accumulateSequences (Maxwell.C:753-875, ncomp = 6; note its loop nest has i1 outer): out =
+ * {e_max, e_tot, ex_max, ey_max, ez_max, e_sum_tot, b_max, b_tot, bx_max, by_max, bz_max, b_sum_tot} */
+void ok_field_history(const double* em, int n1, int n2, int ng, int ncomp, const double* dx, double* out) {
+  const int64_t n1d = n1 + 2 * ng, pl = n1d * (n2 + 2 * ng);
+  const double area = dx[0] * dx[1];
+  if (ncomp == 2) {
+    double e_sum_tot = 0.0, e_max = 0.0, e_tot = 0.0, ex_max = 0.0, ey_max = 0.0;
+    for (int i2 = ng; i2 < ng + n2; ++i2)
+      for (int i1 = ng; i1 < ng + n1; ++i1) {
+        const double ex = em[i1 + n1d * i2], ey = em[i1 + n1d * i2 + pl];
+        double tmp = ex * ex + ey * ey;
+        double e_loc = sqrt(tmp);
+        e_sum_tot += 0.5 * tmp;
+        e_max = fmax(e_max, e_loc);
+        e_tot += e_loc;
+        ex_max = fmax(ex_max, fabs(ex));
+        ey_max = fmax(ey_max, fabs(ey));
+      }
+    e_sum_tot *= area;
+    e_tot *= area;
+    out[0] = e_max; out[1] = e_tot; out[2] = ex_max; out[3] = ey_max; out[4] = e_sum_tot;
+    return;
+  }
+  double s[2] = {0.0, 0.0}, mx[2] = {0.0, 0.0}, tot[2] = {0.0, 0.0}, cm[6] = {0, 0, 0, 0, 0, 0};
+  for (int i1 = ng; i1 < ng + n1; ++i1)
+    for (int i2 = ng; i2 < ng + n2; ++i2)
+      for (int h = 0; h < 2; ++h) {
+        const double a = em[i1 + n1d * i2 + pl * (3 * h)], b = em[i1 + n1d * i2 + pl * (3 * h + 1)],
+                     c = em[i1 + n1d * i2 + pl * (3 * h + 2)];
+        double tmp = a * a + b * b + c * c;
+        double loc = sqrt(tmp);
+        s[h] += 0.5 * tmp;
+        mx[h] = fmax(mx[h], loc);
+        tot[h] += loc;
+        cm[3 * h] = fmax(cm[3 * h], fabs(a));
+        cm[3 * h + 1] = fmax(cm[3 * h + 1], fabs(b));
+        cm[3 * h + 2] = fmax(cm[3 * h + 2], fabs(c));
+      }
+  for (int h = 0; h < 2; ++h) {
+    out[6 * h] = mx[h]; out[6 * h + 1] = tot[h] * area;
+    out[6 * h + 2] = cm[3 * h]; out[6 * h + 3] = cm[3 * h + 1]; out[6 * h + 4] = cm[3 * h + 2];
+    out[6 * h + 5] = s[h] * area;
+  }
+}

@@ -80,6 +80,13 @@ void ok_compute_currents(const ok_geom* g, const double* velocities, const doubl
 double ok_compute_ke_e_dot(const ok_geom* g, const double* u, double charge, const double* velocities,
                            const double* ext_efield, double ke_e_dot_in);
 
+/* time-history diagnostics: computeke / computekemaxwell (KineticSpeciesF.f:2447-2559) and the field
+ * histories of Poisson / Maxwell ::accumulateSequences (Poisson.C:796-860, Maxwell.C:753-875) */
+void ok_compute_ke(const ok_geom* g, const double* u, double mass, const double* velocities, double* out5);
+void ok_compute_ke_maxwell(const ok_geom* g, const double* u, double mass, const double* velocities,
+                           const double* vz_in, double* out3);
+void ok_field_history(const double* em, int n1, int n2, int ng, int ncomp, const double* dx, double* out);
+
 /* ---- ReductionSchedule.C: 4D -> 2D velocity moment on one rank ---- */
 void ok_reduce_4d_to_2d(double* dst2d, const double* src4d, const ok_geom* g, double dv, double weight);
 

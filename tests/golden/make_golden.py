@@ -58,6 +58,14 @@ def main():
         out["rhs%d_rhs" % order] = rhs
         out["rhs%d_bc" % order] = bc
         out["rhs%d_amax" % order] = np.array([ax.value, ay.value])
+        xlo = np.zeros(4)
+        r5 = [C.c_double(0.0) for _ in range(5)]
+        R.L.computeke_(*db, *ib, R._p(xlo), R._p(xlo), R._p(dxs), R._p(s.f), R._d(1.7), R._p(s.velocities), *[C.byref(v) for v in r5])
+        out["rhs%d_ke" % order] = np.array([v.value for v in r5])
+        r3 = [C.c_double(0.0) for _ in range(3)]
+        R.L.computekemaxwell_(*db, *ib, R._p(xlo), R._p(xlo), R._p(dxs), R._p(s.f), R._d(1.7), R._p(s.velocities), R._p(s.vz),
+                              *[C.byref(v) for v in r3])
+        out["rhs%d_kem" % order] = np.array([v.value for v in r3])
     path = os.path.join(HERE, "kinetic_f77_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -66,6 +66,9 @@ def load():
     L.ok_compute_ke_e_dot.restype = d
     L.ok_compute_ke_e_dot.argtypes = [G, dp, d, dp, dp, d]
     L.ok_reduce_4d_to_2d.argtypes = [dp, dp, G, d, d]
+    L.ok_compute_ke.argtypes = [G, dp, d, dp, dp]
+    L.ok_compute_ke_maxwell.argtypes = [G, dp, d, dp, dp, dp]
+    L.ok_field_history.argtypes = [dp, i, i, i, i, dp, dp]
     L.ok_periodic_fill_4d.argtypes = [dp, G, i, i]
     L.ok_periodic_fill_2d.argtypes = [dp, i, i, i, i, i, i]
     L.ok_build_velocity_tables.argtypes = [G, C.POINTER(i * 2), d, d, dp, dp, dp]

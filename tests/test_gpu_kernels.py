@@ -463,3 +463,37 @@ def test_argument_errors(lk):
     g.ng = 3
     assert lk.lk_periodic_fill_4d(1, C.byref(g), 1, 1, None) == 1
     assert b"bad argument" in lk.lk_last_error()
+
+
+# ---------------------------------------------------------------- time-history diagnostics
+@pytest.mark.parametrize("n,order", [((9, 6, 10, 7), 4), ((7, 7, 8, 9), 6), ((40, 12, 24, 16), 4)])
+def test_compute_ke_and_field_history(lk, ok, n, order):
+    """computeke / computekemaxwell and the Poisson / Maxwell field histories on the device against the
+    oracle (pinned to the reference Fortran): tree sums vs the reference's cell-by-cell sums, 1e-13"""
+    import torch
+    s = Setup(ok, n, order)
+    d = Dev(lk, s)
+    out = torch.zeros(5, dtype=torch.float64, device="cuda")
+    o5 = np.zeros(5)
+    ok.ok_compute_ke(C.byref(s.g), s.f.ravel(), 1.7, s.velocities, o5)
+    chk(lk, lk.lk_compute_ke(out.data_ptr(), d.f.data_ptr(), C.byref(d.g), 1.7, d.velocities.data_ptr(), None, None), "ke")
+    got = _np(out)
+    assert np.all(np.abs(got - o5) <= 1e-13 * np.abs(o5).max()) and o5[0] > 0
+    o3 = np.zeros(3)
+    ok.ok_compute_ke_maxwell(C.byref(s.g), s.f.ravel(), 1.7, s.velocities, s.vz.ravel(), o3)
+    dvz = d.t(s.vz)
+    chk(lk, lk.lk_compute_ke(out.data_ptr(), d.f.data_ptr(), C.byref(d.g), 1.7, d.velocities.data_ptr(), dvz.data_ptr(), None), "kem")
+    got = _np(out)
+    assert np.all(np.abs(got[:3] - o3) <= 1e-13 * np.abs(o3).max()) and got[3] == 0.0 and got[4] == 0.0
+    dx = np.array(s.dx)
+    cdx = (C.c_double * 4)(*dx)
+    for ncomp in (2, 6):
+        em = np.ascontiguousarray(s.em[:ncomp])
+        ref = np.zeros(12)
+        ok.ok_field_history(em.ravel(), n[0], n[1], s.ng, ncomp, dx, ref)
+        dem = d.t(em)
+        o = torch.zeros(12, dtype=torch.float64, device="cuda")
+        chk(lk, lk.lk_field_history(o.data_ptr(), dem.data_ptr(), n[0], n[1], s.ng, ncomp, cdx, None), "fh")
+        cnt = 5 if ncomp == 2 else 12
+        got = _np(o)[:cnt]
+        assert np.all(np.abs(got - ref[:cnt]) <= 1e-13 * np.abs(ref[:cnt])) and np.all(ref[:cnt] > 0)

@@ -322,6 +322,15 @@ def test_regression_run_traces_plane_iaw(lk, ok, fast):
     ax, ay = np.zeros(ns), np.zeros(ns)
     ok.ok_vp_eval_rhs(w, _ptrs(rhs0), _ptrs(f_old), 0.0, np.zeros(ns), ax, ay)
     ke = np.zeros(ns)
+    vel_tables = []
+    for s_ in range(ns):
+        g_ = sp[s_].g
+        nd_ = g_.nd
+        vt = np.zeros(nd_[2] * nd_[3] * 2)
+        lo_ = (C.c_int * 2)(-g_.ng, -g_.ng)
+        ok.ok_build_velocity_tables(C.byref(g_), C.byref(lo_), deck.species[s_].vlim[0], deck.species[s_].vlim[2], vt,
+                                    np.zeros((nd_[2] + 1) * nd_[3] * 2), np.zeros(nd_[2] * (nd_[3] + 1) * 2))
+        vel_tables.append(vt)
     t, last_save, save_times, t_final = 0.0, 0, 0.2, 0.4
     nsteps = 0
     while t < t_final - 1e-12:
@@ -351,6 +360,26 @@ def test_regression_run_traces_plane_iaw(lk, ok, fast):
         v = C.c_double()
         assert H.lk_vp_ke_e_dot(sys_, 0, C.byref(v)) == 0
         assert abs(v.value - ke[0]) <= 1e-10 * abs(ke[0]) + 1e-300
+        # the whole time-history record of the step (VPSystem::accumulateSequences): field histories of the
+        # field both sides hold, species kinetic energies and momenta of the new state
+        hist = np.zeros(5 + 6 * ns)
+        assert H.lk_vp_time_history(sys_, hist.ctypes.data, hist.size) == hist.size
+        fh = np.zeros(12)
+        ok.ok_field_history(np.ascontiguousarray(em_o).ravel(), deck.n[0], deck.n[1], ng, 2, np.array(deck.dx + (1.0, 1.0)), fh)
+        # e_max, e_tot, ex_max, e_sum_tot within 1e-10; ey_max is 1 % of ex_max in this deck and carries the
+        # white rounding noise of the net charge density (electron and ion densities cancel to 1e-5 of their
+        # size and the device sums them as trees): its difference is bounded relative to the field scale
+        for k_ in (0, 1, 2, 4):
+            assert abs(hist[k_] - fh[k_]) <= 1e-10 * abs(fh[k_])
+        assert abs(hist[3] - fh[3]) <= 1e-9 * fh[0]
+        for s_ in range(ns):
+            sp_ = deck.species[s_]
+            o5 = np.zeros(5)
+            ok.ok_compute_ke(C.byref(sp[s_].g), f_old[s_].ravel(), sp_.mass, vel_tables[s_], o5)
+            got = hist[5 + 6 * s_: 5 + 6 * s_ + 5]
+            assert np.all(np.abs(got[:3] - o5[:3]) <= 1e-10 * np.abs(o5[:3]))                 # energies
+            assert np.all(np.abs(got[3:] - o5[3:]) <= 1e-10 * (sp_.mass * np.sqrt(2 * o5[0] / sp_.mass)))  # momenta ~ 0
+        assert abs(hist[5 + 5] - ke[0]) <= 1e-10 * abs(ke[0]) + 1e-300
     assert nsteps >= 4 and abs(t - t_final) < 1e-12
     for s in range(ns):
         out = np.empty_like(states[s])

@@ -100,6 +100,18 @@ def test_pin_kinetic_kernels(ok, ref, n, order, lo):
     xlo = np.zeros(4)
     R.L.computekeedot_(*db, *ib, R._p(xlo), R._p(xlo), R._p(dxs), R._p(s.f), R._d(s.charge), R._p(s.velocities), R._p(ext), C.byref(k2))
     assert k1 == k2.value
+    # time-history kinetic energies: computeke, computekemaxwell
+    o5 = np.zeros(5)
+    ok.ok_compute_ke(C.byref(s.g), s.f.ravel(), 1.7, s.velocities, o5)
+    r5 = [C.c_double(0.0) for _ in range(5)]
+    R.L.computeke_(*db, *ib, R._p(xlo), R._p(xlo), R._p(dxs), R._p(s.f), R._d(1.7), R._p(s.velocities), *[C.byref(v) for v in r5])
+    assert [v.value for v in r5] == list(o5) and o5[0] > 0.0
+    o3 = np.zeros(3)
+    ok.ok_compute_ke_maxwell(C.byref(s.g), s.f.ravel(), 1.7, s.velocities, s.vz.ravel(), o3)
+    r3k = [C.c_double(0.0) for _ in range(3)]
+    R.L.computekemaxwell_(*db, *ib, R._p(xlo), R._p(xlo), R._p(dxs), R._p(s.f), R._d(1.7), R._p(s.velocities), R._p(s.vz),
+                          *[C.byref(v) for v in r3k])
+    assert [v.value for v in r3k] == list(o3) and o3[0] > o5[0]
 
 
 @needs_ref
@@ -166,3 +178,10 @@ def test_oracle_matches_committed_golden_vectors(ok):
         u1 = s.f.copy()
         ok.ok_set_acceleration_bcs_4d(u1.ravel(), C.byref(s.g), vel3, vel4, 1, 1, 1, 1, s.ic_callback(0.7, 0.9), None)
         assert np.array_equal(u1, gold["rhs%d_bc" % order])
+        if "rhs%d_ke" % order in gold.files:
+            o5 = np.zeros(5)
+            ok.ok_compute_ke(C.byref(s.g), s.f.ravel(), 1.7, s.velocities, o5)
+            assert np.array_equal(o5, gold["rhs%d_ke" % order])
+            o3 = np.zeros(3)
+            ok.ok_compute_ke_maxwell(C.byref(s.g), s.f.ravel(), 1.7, s.velocities, s.vz.ravel(), o3)
+            assert np.array_equal(o3, gold["rhs%d_kem" % order])
