@@ -38,8 +38,14 @@ UNIT = "cell-updates/s"
 STAGE_BYTES = (32, 40, 40, 32)
 
 
-def config_dict(n_gpus):
+def config_dict(n_gpus, workload="iaw"):
     px, py = GRIDS[n_gpus]
+    if workload == "streams":
+        return {"workload": "InterpenetratingStreams electrons, 1 species x 256x128x256x256 cells per GPU (global 512x512 "
+                            "x 256x256 on 8 GPUs), order 6 WENO, RK4 (SURVEY 8d S5 variant)",
+                "cells_per_species_per_gpu": 256 * 128 * 256 * 256, "species": 1, "stages_per_step": 4,
+                "decomposition": "%dx%d tiles in (x,y)" % (px, py), "arithmetic": "production (strict available)",
+                "l2": "inputs larger than L2 (19.3 GB per array)"}
     return {"workload": "planeIAW physics, 2 species x %dx%dx%dx%d cells per GPU (global %dx%d), order 4 WENO, RK4"
                         % (TILE[0], TILE[1], NV[0], NV[1], TILE[0] * px, TILE[1] * py),
             "cells_per_species_per_gpu": TILE[0] * TILE[1] * NV[0] * NV[1], "species": 2, "stages_per_step": 4,
@@ -182,8 +188,18 @@ def run_own(args):
     px, py = GRIDS[args.gpus]
     tile = TILE if not args.small else (32, 32)
     nv = NV if not args.small else (32, 32)
-    deck = decks.plane_iaw(n=(tile[0] * px, tile[1] * py), nv=nv, order=ORDER, rk=RK)
-    layout = decomp.TileLayout(deck.n, px, py, min_tile=ORDER + 1)
+    if args.workload == "streams":
+        # BASELINE.json configs[4]: InterpenetratingStreams scaled to 512^2 x 256^2, electrons only, order 6 in
+        # space with the fused RK4 (the variant SURVEY 8d recommends: 4 arrays of 19.3 GB per GPU)
+        if args.gpus != 8 and not args.small:
+            raise SystemExit("--workload streams is the 8-GPU configuration (one array is 137 GB globally)")
+        tile = (256, 128) if not args.small else (32, 16)
+        nv = (256, 256) if not args.small else (32, 32)
+        deck = decks.interpenetrating_streams(n=(tile[0] * px, tile[1] * py), nv=nv, order=6, rk=4)
+        deck.species = deck.species[:1]
+    else:
+        deck = decks.plane_iaw(n=(tile[0] * px, tile[1] * py), nv=nv, order=ORDER, rk=RK)
+    layout = decomp.TileLayout(deck.n, px, py, min_tile=deck.order + 1)
     stream = torch.cuda.current_stream().cuda_stream
     vp = decomp.DistributedVP(deck, layout, rank, dev, stream, dist if world > 1 else None)
     sys_ = vp.sys
@@ -196,6 +212,13 @@ def run_own(args):
     # ---- synthetic initial data: analytic Perturbed-Maxwellian tables, expanded on the device ----
     def device_state(s, amp):
         sp = deck.species[s]
+        if sp.stream is not None:
+            fx, fx2, fv, fv2 = deck.stream_tables(sp, tile_lo, tile)
+            t = lambda a: torch.from_numpy(a).to(dev)
+            f = (t(fv)[:, :, None, None] * t(fx)[None, None, :, :])
+            f.addcmul_(t(fv2)[:, :, None, None], t(fx2)[None, None, :, :])
+            assert deck.set_inflow(H, sys_, s, tile_lo, tile) == 0
+            return f.contiguous()
         fx, fv, fnorm = deck.ic_tables(sp, tile_lo, tile)
         dfx = torch.from_numpy(fx).to(dev)
         dfv = torch.from_numpy(fv).to(dev)
@@ -280,8 +303,10 @@ def run_own(args):
                 "algorithmic_bytes_per_launch": avg_bytes, "avg_launch_ms": avg_ms, "timed_launches": n_l.value,
                 "kernel_share_of_step": tot_ms.value / ms if ms > 0 else None, "peak_source": peak_src,
                 "traffic_source": traffic_src,
-                "note": "co-limited by the fp64 pipe (111 fp64 instructions per cell-update by ncu, ceiling "
-                        "168 G cell-updates/s at 1.965 GHz); see DESIGN.md section 3"}
+                "note": ("co-limited by the fp64 pipe (111 fp64 instructions per cell-update by ncu, ceiling "
+                         "168 G cell-updates/s at 1.965 GHz); see DESIGN.md section 3") if deck.order == 4 else
+                        ("fp64-bound: 222 fp64 instructions per order-6 cell-update by ncu, ceiling 84 G "
+                         "cell-updates/s at 1.965 GHz; see DESIGN.md section 3")}
 
     # ---- e2e: the same step with HOST buffers (pinned), H2D of the state + step + D2H of the result ----
     e2e = None
@@ -327,7 +352,7 @@ def run_own(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus, args.workload),
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
         if args.small:
             line["config"]["workload"] += " [--small: 32x32x32x32 tile, NOT the headline size]"
@@ -360,6 +385,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--small", action="store_true", help="tiny tile for plumbing checks (not a valid bench number)")
+    ap.add_argument("--workload", default="iaw", choices=["iaw", "streams"],
+                    help="iaw: the headline configuration (BASELINE.json configs[1]); streams: configs[4], 8 GPUs only")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -766,8 +766,7 @@ struct VMSystem {
 
   // (1) currentDensity of every species (KineticSpecies.C:853-895) + (2) Maxwell::fillGhostCells and the
   // net current sums (VMSystem.C:453-470)
-  int currentsOf(int s_first_only, const double* const* f_of, double* em_eval, double* const* vz_eval, bool allow_fused) {
-    (void)s_first_only;
+  int currentsOf(const double* const* f_of, double* em_eval, double* const* vz_eval, bool allow_fused) {
     for (size_t s = 0; s < species.size(); ++s) {
       KineticSpecies* ks = species[s];
       const double dv = ks->g.dx[2] * ks->g.dx[3];
@@ -820,7 +819,7 @@ struct VMSystem {
       rhs_vz[s] = vz_rhs[s]->p;
       f_of[s] = species[s]->f_eval;
     }
-    LKH_CHECK(currentsOf(0, f_of.data(), em_eval, vz_eval.data(), true));
+    LKH_CHECK(currentsOf(f_of.data(), em_eval, vz_eval.data(), true));
     static const bool no_fuse = getenv("LK_NO_FUSED_MOMENTS") != nullptr;
     const bool fused_moments = !lk_get_strict() && !no_fuse;
     for (size_t s = 0; s < species.size(); ++s) {
@@ -893,7 +892,7 @@ struct VMSystem {
       f_of[s] = species[s]->state();
       species[s]->mom_valid = false;
     }
-    LKH_CHECK(currentsOf(0, f_of.data(), emState(), vz_eval.data(), false));
+    LKH_CHECK(currentsOf(f_of.data(), emState(), vz_eval.data(), false));
     for (size_t s = 0; s < species.size(); ++s) {
       KineticSpecies* ks = species[s];
       double* f = ks->state();
