@@ -45,7 +45,7 @@ struct MarchCfg {
   // registers); NACC more doubles hold the delta_in tile
   static constexpr int SMEM_DOUBLES = NS * NCORE + 2 * NYH + 2 * NVH + 2 * NACC;
   // + the (vx, vy) cell-centre velocities of the tile's T2 slices for the current and the next vy plane
-  static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES + 8 * (NS + 3) + sizeof(double) * 4 * T2;
+  static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES + 8 * (NS + 4) + sizeof(double) * 4 * T2;
 };
 
 struct MarchMaps {
@@ -184,8 +184,8 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
   double* sVh = sYh + 2 * C::NYH;             // [side][h][b1][PC]
   double* sAcc = sVh + 2 * C::NVH;            // [c][b1][PA]
   double* sDi = sAcc + C::NACC;               // [c][b1][PA]  delta_in of the plane being updated
-  unsigned long long* bars = (unsigned long long*)(sDi + C::NACC);  // NS core barriers, y, v, RK operands
-  double* sVel = (double*)(bars + NS + 3);                          // [plane parity][vx | vy][T2]
+  unsigned long long* bars = (unsigned long long*)(sDi + C::NACC);  // NS core barriers, y, v, f_old tile, delta_in tile
+  double* sVel = (double*)(bars + NS + 4);                          // [plane parity][vx | vy][T2]
 
   const int tid = threadIdx.x;
   int b = blockIdx.x;
@@ -267,7 +267,7 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
 
   if (TMA) {
     if (tid == 0) {
-      for (int k = 0; k < NS + 3; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[k])));
+      for (int k = 0; k < NS + 4; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[k])));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -363,6 +363,15 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
       const double* cur = sCore + sc * C::NCORE;
       const bool more = (q + 1 < q0 + nq);
       const double* const sv = sVel + (p & 1) * 2 * T2;  // [vx(c) | vy(c)] of this plane
+      if constexpr (EK >= 2 && TMA) {
+        // the delta_in tile of this plane has its own buffer, free since the barrier that closed the previous
+        // plane: fetch it now, a whole plane ahead of the epilogue (only the f_old tile has to wait for the
+        // accumulator to be drained)
+        if (tid == 0) {
+          mbar_expect(&bars[NS + 3], (unsigned)(C::NOP * sizeof(double)));
+          tma_load_4d(sDi, &maps.di, &bars[NS + 3], o0 + C::OPX, o1 + ng, o2 + ng, p);
+        }
+      }
 
 #ifdef LK_EXP_L2PF  // measured: the explicit L2 prefetch of the next plane's RK operands costs 2 % (A/B on one box)
       if (upd.active && more) {
@@ -482,11 +491,20 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
         // f_old into the accumulator (every thread has just moved its column of it into registers),
         // delta_in next to it.  Out-of-range cells are zero filled and never stored.
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes of sAcc before the async ones
-        __syncthreads();
-        if (tid == 0) {
-          mbar_expect(&bars[NS + 2], (unsigned)((EK >= 2 ? 2 : 1) * C::NOP * sizeof(double)));
-          tma_load_4d(sAcc, &maps.fo, &bars[NS + 2], o0 + C::OPX, o1 + ng, o2 + ng, p);
-          if (EK >= 2) tma_load_4d(sDi, &maps.di, &bars[NS + 2], o0 + C::OPX, o1 + ng, o2 + ng, p);
+        // split barrier: every warp announces that its columns of the accumulator are in registers and goes
+        // on to the vx sweep; only warp 0 waits for the announcements before it lets the TMA overwrite sAcc
+        // (measured on one box: +1 % with one resident CTA per SM -- order 6 --, -1.3 % with two, where the
+        // second CTA already fills the wait and warp 0 only becomes a straggler)
+        constexpr bool SPLIT_BARRIER = C::SMEM_BYTES > 113 * 1024;
+        if (SPLIT_BARRIER && tid >= 32) {
+          asm volatile("bar.arrive 1, %0;" ::"r"(NT) : "memory");
+        } else {
+          if constexpr (SPLIT_BARRIER) asm volatile("bar.sync 1, %0;" ::"r"(NT) : "memory");
+          else __syncthreads();
+          if (tid == 0) {
+            mbar_expect(&bars[NS + 2], (unsigned)(C::NOP * sizeof(double)));
+            tma_load_4d(sAcc, &maps.fo, &bars[NS + 2], o0 + C::OPX, o1 + ng, o2 + ng, p);
+          }
         }
       }
       if (do_acc) {
@@ -547,6 +565,7 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
           double fo[T2], di[T2];
           if constexpr (TMA) {
             mbar_wait(&bars[NS + 2], ph_o);
+            if (EK >= 2) mbar_wait(&bars[NS + 3], ph_o);
             ph_o ^= 1u;
 #pragma unroll
             for (int c = 0; c < T2; ++c) {
