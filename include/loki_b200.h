@@ -128,6 +128,12 @@ int lk_set_acceleration_bcs_4d(double* f, const lk_geom* g, const lk_accel* a, c
 
 /* ---- a14: periodic wrap of x then y ghosts on one device (ParallelArray.H:580-606) ---- */
 int lk_periodic_fill_4d(double* f, const lk_geom* g, int periodic_x, int periodic_y, void* stream);
+/* a7: setadvectionbcs4d_ (KineticSpeciesF.f:1166-1297; wrapper KineticSpecies.H:998-1031): physical boundaries
+ * of a NON-periodic x / y direction (outflow extrapolation or inflow from the IC tables, by the sign of the
+ * face velocity).  at_boundary = {x lo, x hi, y lo, y hi}: does this box touch that global boundary.
+ * velocities: the cell-centre table (n3d,n4d,2); inflow kinds 0, 1, 2, 4. */
+int lk_set_advection_bcs_4d(double* f, const lk_geom* g, const double* velocities, const lk_inflow* ic,
+                            const int at_boundary[4], int periodic_x, int periodic_y, void* stream);
 /* halo slabs for the (x,y)-decomposed multi-GPU exchange (ParallelArray.C:925-1113, faces only).
  * dir 0 = x, 1 = y; side 0 = low, 1 = high.  pack copies the ng interior layers next to that side
  * into a dense buffer; unpack writes a received buffer into the ghost layers on that side.

@@ -38,6 +38,7 @@ def build(force=False, verbose=False):
         ([], "lk_capi.cu", "lk_capi.o"),
         ([], "lk_fft.cu", "lk_fft.o"),
         ([], "lk_diag.cu", "lk_diag.o"),
+        (["-fmad=false"], "lk_bcs.cu", "lk_bcs.o"),
         ([], "lk_host.cu", "lk_host.o"),
     ]
     procs = []
@@ -77,7 +78,7 @@ def build_variant(name, defines):
     cmd = [nvcc] + ARCH + COMMON + ["-DLK_STRICT=0"] + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, "lk_kernels.cu"), "-o", o]
     subprocess.check_call(cmd)
     out = os.path.join(HERE, "libloki_b200_%s.so" % name)
-    objs = [o] + [os.path.join(bdir, f) for f in ("lk_kernels_strict.o", "lk_capi.o", "lk_fft.o", "lk_diag.o", "lk_host.o")]
+    objs = [o] + [os.path.join(bdir, f) for f in ("lk_kernels_strict.o", "lk_capi.o", "lk_fft.o", "lk_diag.o", "lk_bcs.o", "lk_host.o")]
     subprocess.check_call([nvcc] + ARCH + ["-shared", "-o", out] + objs)
     return out
 

@@ -96,6 +96,11 @@ cudaError_t poisson_fft(double* phi, const double* rho, int nx, int ny, int ng, 
                         const double* cx, const double* cy, double* F1, double* F2, cudaStream_t st, int64_t* launches);
 }
 static int64_t g_fft_launches = 0;
+// lk_bcs.cu: non-periodic x / y physical boundaries
+namespace lkbcs {
+cudaError_t set_advection_bcs(double* f, const lk_geom* g, const double* velocities, const lk_inflow* ic, const int at[4],
+                              int periodic_x, int periodic_y, cudaStream_t st, int64_t* launches);
+}
 // lk_diag.cu: time-history diagnostics
 namespace lkdiag {
 int ke_scratch_doubles();
@@ -169,6 +174,19 @@ int lk_set_acceleration_bcs_4d(double* f, const lk_geom* g, const lk_accel* a, c
     if (ic->kind == 3 && (!ic->ghost3 || !ic->ghost4)) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d: missing ghost tables");
   }
   CHECK_LAUNCH(DISPATCH(set_accel_bcs)(f, g, a, ic, at, (cudaStream_t)stream), "lk_set_acceleration_bcs_4d");
+}
+int lk_set_advection_bcs_4d(double* f, const lk_geom* g, const double* velocities, const lk_inflow* ic, const int at[4],
+                            int periodic_x, int periodic_y, void* stream) {
+  if (!geom_ok(g) || !f || !velocities || !at) return fail(LK_ERR_ARG, "lk_set_advection_bcs_4d: bad argument");
+  if ((!periodic_x && g->n[0] < 3) || (!periodic_y && g->n[1] < 3)) return fail(LK_ERR_ARG, "lk_set_advection_bcs_4d: need >= 3 cells");
+  if (ic) {
+    if (ic->kind == 3) return fail(LK_ERR_UNSUPPORTED, "lk_set_advection_bcs_4d: ghost-table inflow holds velocity ghosts only");
+    if (ic->kind < 0 || ic->kind > 4) return fail(LK_ERR_ARG, "lk_set_advection_bcs_4d: bad inflow kind");
+    if (ic->kind != 0 && (!ic->fx || !ic->fv)) return fail(LK_ERR_ARG, "lk_set_advection_bcs_4d: missing inflow tables");
+    if ((ic->kind == 2 && (!ic->fx2 || !ic->fv2)) || (ic->kind == 4 && !ic->fx2)) return fail(LK_ERR_ARG, "lk_set_advection_bcs_4d: missing second inflow term");
+  }
+  CHECK_LAUNCH(lkbcs::set_advection_bcs(f, g, velocities, ic, at, periodic_x, periodic_y, (cudaStream_t)stream, &g_fft_launches),
+               "lk_set_advection_bcs_4d");
 }
 int lk_periodic_fill_4d(double* f, const lk_geom* g, int px, int py, void* stream) {
   if (!geom_ok(g) || !f) return fail(LK_ERR_ARG, "lk_periodic_fill_4d: bad argument");

@@ -24,7 +24,7 @@ import sys
 
 ROUTINES = {
     "KineticSpeciesF.f": ["xpby4d", "setphasespacevel4d", "setphasespacevelmaxwell4d", "weno43fit4d",
-                          "weno65fit4d", "setaccelerationbcs4d", "computeadvectionderivatives4d",
+                          "weno65fit4d", "setaccelerationbcs4d", "setadvectionbcs4d", "computeadvectionderivatives4d",
                           "computeaccelerationderivatives4d", "computecurrents", "computekeedot", "computeke",
                           "computekemaxwell"],
     "PoissonF.f": ["neutralizecharge4d", "computeefieldfrompotential"],

@@ -736,6 +736,75 @@ void ok_maxwell_eval_vz_rhs(double* rhs, const double* em, double charge_per_mas
 }
 
 /* ------------------------------------------------------------------------------------------
+ * setAdvectionBCs4D (KineticSpeciesF.f:1166-1297): physical x / y boundaries of a non-periodic direction.
+ * Same rule as the velocity boundaries: outflow (sign of the face velocity vel1 / vel2 at the boundary
+ * face) -> quadratic extrapolation marching outward, inflow -> the initial condition.  x first over the
+ * full data box of the other three directions, then y over the full x extent (ghosts just set included).
+ * vel1: (n1d+1,n2d,n3d,n4d), vel2: (n2d+1,n3d,n4d,n1d) as the reference holds them.
+ * ------------------------------------------------------------------------------------------ */
+void ok_set_advection_bcs_4d(double* u, const ok_geom* g, const double* vel1, const double* vel2, int at_lo1,
+                             int at_hi1, int at_lo2, int at_hi2, int x_periodic, int y_periodic, ok_ic_fn ic,
+                             void* ic_ctx) {
+  const int ng = g->ng;
+  const int64_t n1d = ND(0), n2d = ND(1), n3d = ND(2), n4d = ND(3);
+  const int n1a = ng, n1b = ng + g->n[0] - 1, n2a = ng, n2b = ng + g->n[1] - 1;
+#define V1(i1, i2, i3, i4) vel1[(i1) + (n1d + 1) * ((i2) + n2d * ((i3) + n3d * (int64_t)(i4)))]
+#define V2(i2, i3, i4, i1) vel2[(i2) + (n2d + 1) * ((i3) + n3d * ((i4) + n4d * (int64_t)(i1)))]
+  if ((x_periodic != 1) && (at_hi1 || at_lo1)) {
+    for (int i4 = 0; i4 < n4d; ++i4)
+      for (int i3 = 0; i3 < n3d; ++i3) {
+        if (at_hi1)
+          for (int i2 = 0; i2 < n2d; ++i2) {
+            if (V1(n1b + 1, i2, i3, i4) >= 0.0) {
+              for (int ig = 1; ig <= ng; ++ig)
+                F4(u, n1b + ig, i2, i3, i4) = 3.0 * F4(u, n1b + ig - 1, i2, i3, i4) -
+                                              3.0 * F4(u, n1b + ig - 2, i2, i3, i4) + F4(u, n1b + ig - 3, i2, i3, i4);
+            } else {
+              for (int ig = 1; ig <= ng; ++ig) F4(u, n1b + ig, i2, i3, i4) = ic(ic_ctx, n1b + ig, i2, i3, i4);
+            }
+          }
+        if (at_lo1)
+          for (int i2 = 0; i2 < n2d; ++i2) {
+            if (V1(n1a, i2, i3, i4) > 0.0) {
+              for (int ig = 1; ig <= ng; ++ig) F4(u, n1a - ig, i2, i3, i4) = ic(ic_ctx, n1a - ig, i2, i3, i4);
+            } else {
+              for (int ig = 1; ig <= ng; ++ig)
+                F4(u, n1a - ig, i2, i3, i4) = 3.0 * F4(u, n1a - ig + 1, i2, i3, i4) -
+                                              3.0 * F4(u, n1a - ig + 2, i2, i3, i4) + F4(u, n1a - ig + 3, i2, i3, i4);
+            }
+          }
+      }
+  }
+  if ((y_periodic != 1) && (at_hi2 || at_lo2)) {
+    for (int i4 = 0; i4 < n4d; ++i4)
+      for (int i3 = 0; i3 < n3d; ++i3) {
+        if (at_hi2)
+          for (int i1 = 0; i1 < n1d; ++i1) {
+            if (V2(n2b + 1, i3, i4, i1) >= 0.0) {
+              for (int ig = 1; ig <= ng; ++ig)
+                F4(u, i1, n2b + ig, i3, i4) = 3.0 * F4(u, i1, n2b + ig - 1, i3, i4) -
+                                              3.0 * F4(u, i1, n2b + ig - 2, i3, i4) + F4(u, i1, n2b + ig - 3, i3, i4);
+            } else {
+              for (int ig = 1; ig <= ng; ++ig) F4(u, i1, n2b + ig, i3, i4) = ic(ic_ctx, i1, n2b + ig, i3, i4);
+            }
+          }
+        if (at_lo2)
+          for (int i1 = 0; i1 < n1d; ++i1) {
+            if (V2(n2a, i3, i4, i1) > 0.0) {
+              for (int ig = 1; ig <= ng; ++ig) F4(u, i1, n2a - ig, i3, i4) = ic(ic_ctx, i1, n2a - ig, i3, i4);
+            } else {
+              for (int ig = 1; ig <= ng; ++ig)
+                F4(u, i1, n2a - ig, i3, i4) = 3.0 * F4(u, i1, n2a - ig + 1, i3, i4) -
+                                              3.0 * F4(u, i1, n2a - ig + 2, i3, i4) + F4(u, i1, n2a - ig + 3, i3, i4);
+            }
+          }
+      }
+  }
+#undef V1
+#undef V2
+}
+
+/* ------------------------------------------------------------------------------------------
  * Time-history diagnostics.
  * computeke (KineticSpeciesF.f:2447-2500): out = {ke, ke_x, ke_y, px, py}; the running sums start from
  * the incoming values like the Fortran's (the caller zeroes them, KineticSpecies.C:1198-1213).

@@ -68,6 +68,10 @@ void ok_set_acceleration_bcs_4d(double* u, const ok_geom* g, const double* vel3,
                                 int at_lo3, int at_hi3, int at_lo4, int at_hi4, ok_ic_fn ic,
                                 void* ic_ctx);
 
+/* setAdvectionBCs4D (KineticSpeciesF.f:1166-1297): non-periodic x / y physical boundaries */
+void ok_set_advection_bcs_4d(double* u, const ok_geom* g, const double* vel1, const double* vel2, int at_lo1,
+                             int at_hi1, int at_lo2, int at_hi2, int x_periodic, int y_periodic, ok_ic_fn ic,
+                             void* ic_ctx);
 /* vel1 (n1d+1,n2d,n3d,n4d), vel2 (n2d+1,n3d,n4d,n1d): face-velocity arrays as the reference holds them */
 void ok_advection_derivatives_4d(double* rhs, const double* f, const ok_geom* g, const double* vel1,
                                  const double* vel2);

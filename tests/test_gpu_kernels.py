@@ -133,6 +133,37 @@ def test_acceleration_bcs(lk, ok, strict, n, order):
     assert np.any(out[:, :ng] != s.f[:, :ng])
 
 
+@pytest.mark.parametrize("xper,yper", [(0, 0), (1, 0), (0, 1)])
+@pytest.mark.parametrize("n,order", CASES)
+def test_advection_bcs_nonperiodic(lk, ok, n, order, xper, yper):
+    """setAdvectionBCs4D (non-periodic x / y physical boundaries) against the oracle, which
+    is pinned to the reference Fortran: bit for bit in both arithmetic modes (the kernel has one build)"""
+    import loki_b200 as lkm
+    s = Setup(ok, n, order)
+    cb = s.ic_callback(0.7, 0.9)
+    ref = s.f.copy()
+    ok.ok_set_advection_bcs_4d(ref.ravel(), C.byref(s.g), s.vel1, s.vel2, 1, 1, 1, 1, xper, yper, cb, None)
+    for strict_mode in (0, 1):
+        old = lk.lk_set_strict(strict_mode)
+        try:
+            d = Dev(lk, s)
+            ic = lkm.Inflow()
+            dfx, dfv = d.t(s.fx), d.t(s.fv)
+            ic.kind, ic.fx, ic.fv, ic.fnorm, ic.frac = 1, dfx.data_ptr(), dfv.data_ptr(), 0.7, 0.9
+            at = (C.c_int * 4)(1, 1, 1, 1)
+            chk(lk, lk.lk_set_advection_bcs_4d(d.f.data_ptr(), C.byref(d.g), d.velocities.data_ptr(), C.byref(ic), C.byref(at),
+                                               xper, yper, None), "advbcs")
+            out = _np(d.f)
+        finally:
+            lk.lk_set_strict(old)
+        assert np.array_equal(out, ref)
+    ng = s.ng
+    if not xper:
+        assert np.any(ref[:, :, :, :ng] != s.f[:, :, :, :ng])
+    if not yper:
+        assert np.any(ref[:, :, :ng, :] != s.f[:, :, :ng, :])
+
+
 def _oracle_rhs(ok, s, maxwell=False):
     vel3, vel4, _, _ = s.vel34(ok, maxwell)
     adv = np.zeros_like(s.f)

@@ -79,6 +79,15 @@ def test_pin_kinetic_kernels(ok, ref, n, order, lo):
     R.L.loki_ref_set_ic(cb, None, C.byref(lower))
     R.L.setaccelerationbcs4d_(R._p(u2), *db, *db, *ib, R._i(order), R._p(vel3), R._p(vel4), C.byref(C.c_int64(0)))
     assert np.array_equal(u1, u2)
+    # setAdvectionBCs4D: non-periodic x and y, box touching all four configuration-space boundaries; the
+    # velocity tables change sign inside the box, so both the outflow and the inflow branch run
+    for xper, yper in ((0, 0), (1, 0), (0, 1)):
+        u1, u2 = s.f.copy(), s.f.copy()
+        ok.ok_set_advection_bcs_4d(u1.ravel(), C.byref(s.g), s.vel1, s.vel2, 1, 1, 1, 1, xper, yper, cb, None)
+        R.L.loki_ref_set_ic(cb, None, C.byref(lower))
+        R.L.setadvectionbcs4d_(R._p(u2), *db, *db, *ib, R._i(order), R._p(s.vel1), R._p(s.vel2), R._i(xper), R._i(yper),
+                               C.byref(C.c_int64(0)))
+        assert np.array_equal(u1, u2) and np.any(u1 != s.f)
     # derivatives
     dxs = np.array(s.dx)
     r1, r2 = np.zeros_like(s.f), np.zeros_like(s.f)
