@@ -134,6 +134,15 @@ int lk_periodic_fill_4d(double* f, const lk_geom* g, int periodic_x, int periodi
  * velocities: the cell-centre table (n3d,n4d,2); inflow kinds 0, 1, 2, 4. */
 int lk_set_advection_bcs_4d(double* f, const lk_geom* g, const double* velocities, const lk_inflow* ic,
                             const int at_boundary[4], int periodic_x, int periodic_y, void* stream);
+/* a6': the "JB" variants selected by use_new_bcs (VPSystem.C:819-821): setaccelerationbcs4djb_ /
+ * setadvectionbcs4djb_ (KineticSpeciesF.f:1301-1520, 1524-1733).  Inflow (lower side: face velocity > 0, upper
+ * side: < 0) samples the IC tables, otherwise ghosts are extrapolated with the binomial formula of order
+ * min(interior extent, solution_order).  at_boundary as above ({vx lo, vx hi, vy lo, vy hi} for the
+ * acceleration flavour): the reference derives it from the cell coordinate (:1368-1371). */
+int lk_set_acceleration_bcs_4d_jb(double* f, const lk_geom* g, const lk_accel* a, const lk_inflow* ic,
+                                  const int at_boundary[4], void* stream);
+int lk_set_advection_bcs_4d_jb(double* f, const lk_geom* g, const double* velocities, const lk_inflow* ic,
+                               const int at_boundary[4], int periodic_x, int periodic_y, void* stream);
 /* halo slabs for the (x,y)-decomposed multi-GPU exchange (ParallelArray.C:925-1113, faces only).
  * dir 0 = x, 1 = y; side 0 = low, 1 = high.  pack copies the ng interior layers next to that side
  * into a dense buffer; unpack writes a received buffer into the ghost layers on that side.

@@ -71,6 +71,10 @@ _PROTOS = {
     "lk_set_acceleration_bcs_4d": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Accel), C.POINTER(Inflow),
                                              C.POINTER(C.c_int * 4), _vp]),
     "lk_periodic_fill_4d": (C.c_int, [_vp, C.POINTER(Geom), C.c_int, C.c_int, _vp]),
+    "lk_set_acceleration_bcs_4d_jb": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Accel), C.POINTER(Inflow),
+                                                C.POINTER(C.c_int * 4), _vp]),
+    "lk_set_advection_bcs_4d_jb": (C.c_int, [_vp, C.POINTER(Geom), _vp, C.POINTER(Inflow), C.POINTER(C.c_int * 4), C.c_int,
+                                             C.c_int, _vp]),
     "lk_set_advection_bcs_4d": (C.c_int, [_vp, C.POINTER(Geom), _vp, C.POINTER(Inflow), C.POINTER(C.c_int * 4), C.c_int,
                                           C.c_int, _vp]),
     "lk_halo_count": (C.c_int64, [C.POINTER(Geom), C.c_int]),

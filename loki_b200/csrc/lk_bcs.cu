@@ -7,8 +7,13 @@
 // Compiled with -fmad=false: the extrapolation is the reference's expression, bit for bit in both modes.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/loki_b200.h"
+// the face-acceleration expressions of setphasespacevel4D / maxwell4D (strict flavour: this file is built
+// with -fmad=false); only inline device functions and plain structs come from this header
+#define LK_STRICT 1
+#include "lk_device.cuh"
 
 namespace lkbcs {
 
@@ -29,6 +34,14 @@ __device__ __forceinline__ double inflow_value(const lk_inflow& ic, const Geo& g
       return ic.fx[pxy] * ic.fv[pv] + ic.fx2[pxy] * ic.fv2[pv];
     case 4:  // InterpenetratingStreamIC.C:279-281
       return ic.fv[pv] * ic.fx[pxy] * ic.fx2[pxy];
+    case 3: {  // velocity-ghost layers of a cached non-factorable IC (only meaningful at velocity boundaries)
+      if (i3 < g.ng || i3 >= g.ng + g.n[2]) {
+        const int layer = (i3 < g.ng) ? i3 : (i3 - g.n[2]);
+        return ic.ghost3[pxy + (i64)g.nd[0] * g.nd[1] * (layer + (i64)2 * g.ng * i4)];
+      }
+      const int layer = (i4 < g.ng) ? i4 : (i4 - g.n[3]);
+      return ic.ghost4[pxy + (i64)g.nd[0] * g.nd[1] * (i3 + (i64)g.nd[2] * layer)];
+    }
     default:
       return 0.0;
   }
@@ -71,6 +84,98 @@ __global__ void k_advection_bcs(Geo g, const double* __restrict__ vel, lk_inflow
         p[(na - ig) * s] = 3.0 * p[(na - ig + 1) * s] - 3.0 * p[(na - ig + 2) * s] + p[(na - ig + 3) * s];
     }
   }
+}
+
+// ---- the "JB" boundary conditions (use_new_bcs): setAccelerationBCs4DJB / setAdvectionBCs4DJB
+// (KineticSpeciesF.f:1301-1520, 1524-1733).  One launch per side of a direction d, one thread per boundary
+// line: inflow (lower: face velocity > 0, upper: < 0) -> IC tables, else the binomial extrapolation of order
+// e = min(interior extent, solution_order), accumulated from 0.0 in stencil order like the Fortran.
+__constant__ double JB_ECOEFFS[6][6] = {{1.0, 0, 0, 0, 0, 0},        {2.0, -1.0, 0, 0, 0, 0},
+                                        {3.0, -3.0, 1.0, 0, 0, 0},   {4.0, -6.0, 4.0, -1.0, 0, 0},
+                                        {5.0, -10.0, 10.0, -5.0, 1.0, 0}, {6.0, -15.0, 20.0, -15.0, 6.0, -1.0}};
+__global__ void k_bcs_jb(Geo g, lkstrict::DGeo dg, lkstrict::DAccel a, const double* __restrict__ vel, lk_inflow ic,
+                         double* __restrict__ u, int d, int hi, int order) {
+  const int ng = g.ng;
+  // the three directions other than d, fastest first
+  int od[3], k = 0;
+  for (int q = 0; q < 4; ++q)
+    if (q != d) od[k++] = q;
+  const i64 total = (i64)g.nd[od[0]] * g.nd[od[1]] * g.nd[od[2]];
+  const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int i[4];
+  i[od[0]] = (int)(t % g.nd[od[0]]);
+  const i64 r = t / g.nd[od[0]];
+  i[od[1]] = (int)(r % g.nd[od[1]]);
+  i[od[2]] = (int)(r / g.nd[od[1]]);
+  const int na = ng, nb = ng + g.n[d] - 1;
+  const int face = hi ? nb + 1 : na;
+  double v;
+  if (d == 0) v = vel[i[2] + (i64)g.nd[2] * i[3]];                              // vel1 = vx(i3,i4)
+  else if (d == 1) v = vel[i[2] + (i64)g.nd[2] * (i[3] + (i64)g.nd[3])];        // vel2 = vy(i3,i4)
+  else if (d == 2) v = lkstrict::accel_x(a, dg, i[0], i[1], face, i[3]);         // vel3(face,i4,i1,i2)
+  else v = lkstrict::accel_y(a, dg, i[0], i[1], i[2], face);                      // vel4(face,i1,i2,i3)
+  const bool inflow = hi ? (v < 0.0) : (v > 0.0);
+  const int e = min(g.n[d], order);
+  i[d] = 0;
+  double* p = u + (i64)i[0] + g.s[1] * i[1] + g.s[2] * i[2] + g.s[3] * i[3];
+  const i64 s = g.s[d];
+  for (int ig = 1; ig <= ng; ++ig) {
+    const int c = hi ? nb + ig : na - ig;
+    if (inflow) {
+      int q[4] = {i[0], i[1], i[2], i[3]};
+      q[d] = c;
+      p[c * s] = inflow_value(ic, g, q[0], q[1], q[2], q[3]);
+    } else {
+      double acc = 0.0;
+      for (int m = 1; m <= e; ++m) acc = acc + JB_ECOEFFS[e - 1][m - 1] * p[(hi ? c - m : c + m) * s];
+      p[c * s] = acc;
+    }
+  }
+}
+
+static Geo make_geo(const lk_geom* g) {
+  Geo d;
+  d.ng = g->ng;
+  i64 s = 1;
+  for (int k = 0; k < 4; ++k) {
+    d.n[k] = g->n[k];
+    d.nd[k] = g->n[k] + 2 * g->ng;
+    d.s[k] = s;
+    s *= d.nd[k];
+  }
+  return d;
+}
+// sides[8] = {x lo, x hi, y lo, y hi, vx lo, vx hi, vy lo, vy hi}: which sides to set, in the reference's order
+cudaError_t set_bcs_jb(double* f, const lk_geom* g, const lk_accel* a, const double* velocities, const lk_inflow* ic,
+                       const int sides[8], cudaStream_t st, int64_t* launches) {
+  Geo d = make_geo(g);
+  lkstrict::DGeo dg;
+  lkstrict::DAccel da;
+  memset(&dg, 0, sizeof(dg));
+  memset(&da, 0, sizeof(da));
+  for (int k = 0; k < 4; ++k) { dg.n[k] = d.n[k]; dg.nd[k] = d.nd[k]; dg.s[k] = d.s[k]; dg.dx[k] = g->dx[k]; }
+  dg.ng = g->ng; dg.order = g->order;
+  if (a) {
+    da.kind = a->kind; da.field = a->field; da.vz = a->vz; da.vxf = a->vxface_velocities; da.vyf = a->vyface_velocities;
+    da.norm = a->normalization; da.bz = a->bz_const;
+  }
+  lk_inflow di;
+  if (ic) di = *ic;
+  else {
+    lk_inflow z = {};
+    di = z;
+  }
+  for (int dir = 0; dir < 4; ++dir)
+    for (int hi = 0; hi < 2; ++hi) {
+      if (!sides[2 * dir + hi]) continue;
+      i64 total = 1;
+      for (int q = 0; q < 4; ++q)
+        if (q != dir) total *= d.nd[q];
+      k_bcs_jb<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(d, dg, da, velocities, di, f, dir, hi, g->order);
+      ++*launches;
+    }
+  return cudaGetLastError();
 }
 
 cudaError_t set_advection_bcs(double* f, const lk_geom* g, const double* velocities, const lk_inflow* ic, const int at[4],

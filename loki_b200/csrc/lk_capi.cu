@@ -101,6 +101,10 @@ namespace lkbcs {
 cudaError_t set_advection_bcs(double* f, const lk_geom* g, const double* velocities, const lk_inflow* ic, const int at[4],
                               int periodic_x, int periodic_y, cudaStream_t st, int64_t* launches);
 }
+namespace lkbcs {
+cudaError_t set_bcs_jb(double* f, const lk_geom* g, const lk_accel* a, const double* velocities, const lk_inflow* ic,
+                       const int sides[8], cudaStream_t st, int64_t* launches);
+}
 // lk_diag.cu: time-history diagnostics
 namespace lkdiag {
 int ke_scratch_doubles();
@@ -187,6 +191,27 @@ int lk_set_advection_bcs_4d(double* f, const lk_geom* g, const double* velocitie
   }
   CHECK_LAUNCH(lkbcs::set_advection_bcs(f, g, velocities, ic, at, periodic_x, periodic_y, (cudaStream_t)stream, &g_fft_launches),
                "lk_set_advection_bcs_4d");
+}
+static int inflow_tables_ok(const lk_inflow* ic) {
+  if (!ic) return 1;
+  if (ic->kind < 0 || ic->kind > 4) return 0;
+  if ((ic->kind == 1 || ic->kind == 2 || ic->kind == 4) && (!ic->fx || !ic->fv)) return 0;
+  if ((ic->kind == 2 && (!ic->fx2 || !ic->fv2)) || (ic->kind == 4 && !ic->fx2)) return 0;
+  if (ic->kind == 3 && (!ic->ghost3 || !ic->ghost4)) return 0;
+  return 1;
+}
+int lk_set_acceleration_bcs_4d_jb(double* f, const lk_geom* g, const lk_accel* a, const lk_inflow* ic, const int at[4],
+                                  void* stream) {
+  if (!geom_ok(g) || !accel_ok(a) || !f || !at || !inflow_tables_ok(ic)) return fail(LK_ERR_ARG, "lk_set_acceleration_bcs_4d_jb: bad argument");
+  const int sides[8] = {0, 0, 0, 0, at[0], at[1], at[2], at[3]};
+  CHECK_LAUNCH(lkbcs::set_bcs_jb(f, g, a, nullptr, ic, sides, (cudaStream_t)stream, &g_fft_launches), "lk_set_acceleration_bcs_4d_jb");
+}
+int lk_set_advection_bcs_4d_jb(double* f, const lk_geom* g, const double* velocities, const lk_inflow* ic, const int at[4],
+                               int periodic_x, int periodic_y, void* stream) {
+  if (!geom_ok(g) || !f || !velocities || !at || !inflow_tables_ok(ic)) return fail(LK_ERR_ARG, "lk_set_advection_bcs_4d_jb: bad argument");
+  if (ic && ic->kind == 3) return fail(LK_ERR_UNSUPPORTED, "lk_set_advection_bcs_4d_jb: ghost-table inflow holds velocity ghosts only");
+  const int sides[8] = {!periodic_x && at[0], !periodic_x && at[1], !periodic_y && at[2], !periodic_y && at[3], 0, 0, 0, 0};
+  CHECK_LAUNCH(lkbcs::set_bcs_jb(f, g, nullptr, velocities, ic, sides, (cudaStream_t)stream, &g_fft_launches), "lk_set_advection_bcs_4d_jb");
 }
 int lk_periodic_fill_4d(double* f, const lk_geom* g, int px, int py, void* stream) {
   if (!geom_ok(g) || !f) return fail(LK_ERR_ARG, "lk_periodic_fill_4d: bad argument");

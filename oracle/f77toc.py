@@ -24,7 +24,7 @@ import sys
 
 ROUTINES = {
     "KineticSpeciesF.f": ["xpby4d", "setphasespacevel4d", "setphasespacevelmaxwell4d", "weno43fit4d",
-                          "weno65fit4d", "setaccelerationbcs4d", "setadvectionbcs4d", "computeadvectionderivatives4d",
+                          "weno65fit4d", "setaccelerationbcs4d", "setadvectionbcs4d", "setaccelerationbcs4djb", "setadvectionbcs4djb", "computeadvectionderivatives4d",
                           "computeaccelerationderivatives4d", "computecurrents", "computekeedot", "computeke",
                           "computekemaxwell"],
     "PoissonF.f": ["neutralizecharge4d", "computeefieldfrompotential"],
@@ -343,7 +343,15 @@ def translate(name, stmts):
         if n in ctx.dummies or n in ctx.funcs:
             continue
         if n in ctx.dims:
-            raise SyntaxError("%s: local arrays unsupported (%s)" % (name, n))
+            # local array with constant bounds (e.g. eCoeffs(1:6,1:6)): a flat, zero-initialised C array,
+            # indexed column-major by index_expr like the dummy arrays
+            size = " * ".join("(%s - %s + 1)" % (hi, lo) for lo, hi in ctx.dims[n])
+            try:
+                count = int(eval(size, {"__builtins__": {}}))
+            except Exception:
+                raise SyntaxError("%s: local array %s needs constant bounds" % (name, n))
+            out.append("  %s %s[%d] = {0};" % (t, n, count))
+            continue
         out.append("  %s %s = 0;" % (t, n))
     ind = 1
 

@@ -805,6 +805,70 @@ void ok_set_advection_bcs_4d(double* u, const ok_geom* g, const double* vel1, co
 }
 
 /* ------------------------------------------------------------------------------------------
+ * The "JB" boundary conditions (use_new_bcs = true): setAccelerationBCs4DJB (KineticSpeciesF.f:1301-1520) and
+ * setAdvectionBCs4DJB (:1524-1733).  Inflow (lower side: face velocity > 0, upper side: < 0) samples the
+ * initial condition; otherwise ghost ig is extrapolated with the binomial formula of order
+ * extrapEq = min(interior extent, solution_order), accumulated from 0.0 in stencil order.  Sides in the
+ * reference's order: lower then upper of the first direction, then of the second.  The reference detects a
+ * global boundary from the cell coordinate (:1368-1371); here the caller passes at_* like for the default BCs.
+ * ------------------------------------------------------------------------------------------ */
+static const double JB_ECOEFFS[6][6] = {{1.0, 0, 0, 0, 0, 0},        {2.0, -1.0, 0, 0, 0, 0},
+                                        {3.0, -3.0, 1.0, 0, 0, 0},   {4.0, -6.0, 4.0, -1.0, 0, 0},
+                                        {5.0, -10.0, 10.0, -5.0, 1.0, 0}, {6.0, -15.0, 20.0, -15.0, 6.0, -1.0}};
+/* one side of direction d (0..3).  vsel: which face-velocity array, indexed like the reference does */
+static void jb_side(double* u, const ok_geom* g, int d, int hi, const double* vel, ok_ic_fn ic, void* ic_ctx) {
+  const int ng = g->ng;
+  const int64_t nd[4] = {ND(0), ND(1), ND(2), ND(3)};
+  const int na = ng, nb = ng + g->n[d] - 1;
+  int e = g->n[d] < g->order ? g->n[d] : g->order; /* extrapEq */
+  int lo_[4] = {0, 0, 0, 0}, hi_[4] = {(int)nd[0], (int)nd[1], (int)nd[2], (int)nd[3]};
+  lo_[d] = 0; hi_[d] = 1; /* the swept direction is fixed at the boundary */
+  int i[4];
+  for (i[3] = lo_[3]; i[3] < hi_[3]; ++i[3])
+    for (i[2] = lo_[2]; i[2] < hi_[2]; ++i[2])
+      for (i[1] = lo_[1]; i[1] < hi_[1]; ++i[1])
+        for (i[0] = lo_[0]; i[0] < hi_[0]; ++i[0]) {
+          int f = hi ? nb + 1 : na; /* face index whose velocity decides */
+          double v;
+          if (d == 0) v = vel[f + (nd[0] + 1) * (i[1] + nd[1] * (i[2] + nd[2] * (int64_t)i[3]))];         /* vel1(i1,i2,i3,i4) */
+          else if (d == 1) v = vel[f + (nd[1] + 1) * (i[2] + nd[2] * (i[3] + nd[3] * (int64_t)i[0]))];    /* vel2(i2,i3,i4,i1) */
+          else if (d == 2) v = vel[f + (nd[2] + 1) * (i[3] + nd[3] * (i[0] + nd[0] * (int64_t)i[1]))];    /* vel3(i3,i4,i1,i2) */
+          else v = vel[f + (nd[3] + 1) * (i[0] + nd[0] * (i[1] + nd[1] * (int64_t)i[2]))];                /* vel4(i4,i1,i2,i3) */
+          int inflow = hi ? (v < 0.0) : (v > 0.0);
+          for (int ig = 1; ig <= ng; ++ig) {
+            int c[4] = {i[0], i[1], i[2], i[3]};
+            c[d] = hi ? nb + ig : na - ig;
+            if (inflow) {
+              F4(u, c[0], c[1], c[2], c[3]) = ic(ic_ctx, c[0], c[1], c[2], c[3]);
+            } else {
+              double acc = 0.0;
+              for (int k = 1; k <= e; ++k) {
+                int q[4] = {c[0], c[1], c[2], c[3]};
+                q[d] = hi ? c[d] - k : c[d] + k;
+                acc = acc + JB_ECOEFFS[e - 1][k - 1] * F4(u, q[0], q[1], q[2], q[3]);
+              }
+              F4(u, c[0], c[1], c[2], c[3]) = acc;
+            }
+          }
+        }
+}
+void ok_set_acceleration_bcs_4d_jb(double* u, const ok_geom* g, const double* vel3, const double* vel4, int at_lo3,
+                                   int at_hi3, int at_lo4, int at_hi4, ok_ic_fn ic, void* ic_ctx) {
+  if (at_lo3) jb_side(u, g, 2, 0, vel3, ic, ic_ctx);
+  if (at_hi3) jb_side(u, g, 2, 1, vel3, ic, ic_ctx);
+  if (at_lo4) jb_side(u, g, 3, 0, vel4, ic, ic_ctx);
+  if (at_hi4) jb_side(u, g, 3, 1, vel4, ic, ic_ctx);
+}
+void ok_set_advection_bcs_4d_jb(double* u, const ok_geom* g, const double* vel1, const double* vel2, int at_lo1,
+                                int at_hi1, int at_lo2, int at_hi2, int x_periodic, int y_periodic, ok_ic_fn ic,
+                                void* ic_ctx) {
+  if (at_lo1 && x_periodic != 1) jb_side(u, g, 0, 0, vel1, ic, ic_ctx);
+  if (at_hi1 && x_periodic != 1) jb_side(u, g, 0, 1, vel1, ic, ic_ctx);
+  if (at_lo2 && y_periodic != 1) jb_side(u, g, 1, 0, vel2, ic, ic_ctx);
+  if (at_hi2 && y_periodic != 1) jb_side(u, g, 1, 1, vel2, ic, ic_ctx);
+}
+
+/* ------------------------------------------------------------------------------------------
  * Time-history diagnostics.
  * computeke (KineticSpeciesF.f:2447-2500): out = {ke, ke_x, ke_y, px, py}; the running sums start from
  * the incoming values like the Fortran's (the caller zeroes them, KineticSpecies.C:1198-1213).

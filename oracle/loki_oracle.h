@@ -72,6 +72,12 @@ void ok_set_acceleration_bcs_4d(double* u, const ok_geom* g, const double* vel3,
 void ok_set_advection_bcs_4d(double* u, const ok_geom* g, const double* vel1, const double* vel2, int at_lo1,
                              int at_hi1, int at_lo2, int at_hi2, int x_periodic, int y_periodic, ok_ic_fn ic,
                              void* ic_ctx);
+/* the "JB" variants (use_new_bcs): KineticSpeciesF.f:1301-1520, 1524-1733 */
+void ok_set_acceleration_bcs_4d_jb(double* u, const ok_geom* g, const double* vel3, const double* vel4, int at_lo3,
+                                   int at_hi3, int at_lo4, int at_hi4, ok_ic_fn ic, void* ic_ctx);
+void ok_set_advection_bcs_4d_jb(double* u, const ok_geom* g, const double* vel1, const double* vel2, int at_lo1,
+                                int at_hi1, int at_lo2, int at_hi2, int x_periodic, int y_periodic, ok_ic_fn ic,
+                                void* ic_ctx);
 /* vel1 (n1d+1,n2d,n3d,n4d), vel2 (n2d+1,n3d,n4d,n1d): face-velocity arrays as the reference holds them */
 void ok_advection_derivatives_4d(double* rhs, const double* f, const ok_geom* g, const double* vel1,
                                  const double* vel2);

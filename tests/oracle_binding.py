@@ -61,6 +61,8 @@ def load():
     L.ok_set_phase_space_vel_maxwell_4d.argtypes = [dp, dp, G, dp, dp, d, d, dp, dp, C.POINTER(d), C.POINTER(d)]
     L.ok_set_acceleration_bcs_4d.argtypes = [dp, G, dp, dp, i, i, i, i, IC_FN, C.c_void_p]
     L.ok_set_advection_bcs_4d.argtypes = [dp, G, dp, dp, i, i, i, i, i, i, IC_FN, C.c_void_p]
+    L.ok_set_acceleration_bcs_4d_jb.argtypes = [dp, G, dp, dp, i, i, i, i, IC_FN, C.c_void_p]
+    L.ok_set_advection_bcs_4d_jb.argtypes = [dp, G, dp, dp, i, i, i, i, i, i, IC_FN, C.c_void_p]
     L.ok_advection_derivatives_4d.argtypes = [dp, dp, G, dp, dp]
     L.ok_acceleration_derivatives_4d.argtypes = [dp, dp, G, dp, dp]
     L.ok_compute_currents.argtypes = [G, dp, dp, dp, dp, dp, dp]

@@ -164,6 +164,36 @@ def test_advection_bcs_nonperiodic(lk, ok, n, order, xper, yper):
         assert np.any(ref[:, :, :ng, :] != s.f[:, :, :ng, :])
 
 
+@pytest.mark.parametrize("maxwell", [False, True])
+@pytest.mark.parametrize("n,order", CASES)
+def test_jb_boundary_conditions(lk, ok, n, order, maxwell):
+    """the "JB" boundary conditions (use_new_bcs; SURVEY 8a row a6'): setAccelerationBCs4DJB and
+    setAdvectionBCs4DJB against the oracle (pinned to the reference Fortran), bit for bit"""
+    import loki_b200 as lkm
+    s = Setup(ok, n, order, bz=0.2)
+    cb = s.ic_callback(0.7, 0.9)
+    vel3, vel4, _, _ = s.vel34(ok, maxwell)
+    ref = s.f.copy()
+    ok.ok_set_acceleration_bcs_4d_jb(ref.ravel(), C.byref(s.g), vel3, vel4, 1, 1, 1, 1, cb, None)
+    d = Dev(lk, s, maxwell=maxwell)
+    ic = lkm.Inflow()
+    dfx, dfv = d.t(s.fx), d.t(s.fv)
+    ic.kind, ic.fx, ic.fv, ic.fnorm, ic.frac = 1, dfx.data_ptr(), dfv.data_ptr(), 0.7, 0.9
+    at = (C.c_int * 4)(1, 1, 1, 1)
+    chk(lk, lk.lk_set_acceleration_bcs_4d_jb(d.f.data_ptr(), C.byref(d.g), C.byref(d.accel), C.byref(ic), C.byref(at), None), "jb")
+    out = _np(d.f)
+    assert np.array_equal(out, ref) and np.any(out != s.f)
+    if not maxwell:
+        for xper, yper in ((0, 0), (1, 0), (0, 1)):
+            ref = s.f.copy()
+            ok.ok_set_advection_bcs_4d_jb(ref.ravel(), C.byref(s.g), s.vel1, s.vel2, 1, 1, 1, 1, xper, yper, cb, None)
+            d = Dev(lk, s)
+            chk(lk, lk.lk_set_advection_bcs_4d_jb(d.f.data_ptr(), C.byref(d.g), d.velocities.data_ptr(), C.byref(ic), C.byref(at),
+                                                  xper, yper, None), "jbadv")
+            out = _np(d.f)
+            assert np.array_equal(out, ref) and np.any(out != s.f)
+
+
 def _oracle_rhs(ok, s, maxwell=False):
     vel3, vel4, _, _ = s.vel34(ok, maxwell)
     adv = np.zeros_like(s.f)

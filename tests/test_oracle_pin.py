@@ -88,6 +88,26 @@ def test_pin_kinetic_kernels(ok, ref, n, order, lo):
         R.L.setadvectionbcs4d_(R._p(u2), *db, *db, *ib, R._i(order), R._p(s.vel1), R._p(s.vel2), R._i(xper), R._i(yper),
                                C.byref(C.c_int64(0)))
         assert np.array_equal(u1, u2) and np.any(u1 != s.f)
+    # the "JB" boundary conditions (use_new_bcs).  The Fortran finds a global boundary from the cell coordinate
+    # (KineticSpeciesF.f:1368-1371, lower + index * dx): a box is at the lower boundary iff its first
+    # interior index is 0, and here at the upper one because the domain is made to end with the box
+    dxs_ = np.array(s.dx)
+    xlo_ = np.zeros(4)
+    xhi_ = np.array([(inter[2 * k + 1] + 1) * s.dx[k] for k in range(4)])
+    atl = [int(inter[2 * k] == 0) for k in range(4)]
+    u1, u2 = s.f.copy(), s.f.copy()
+    ok.ok_set_acceleration_bcs_4d_jb(u1.ravel(), C.byref(s.g), vel3, vel4, atl[2], 1, atl[3], 1, cb, None)
+    R.L.loki_ref_set_ic(cb, None, C.byref(lower))
+    R.L.setaccelerationbcs4djb_(R._p(u2), *db, *db, *ib, R._i(order), R._i(s.ng), R._p(vel3), R._p(vel4), R._p(xlo_), R._p(xhi_),
+                                R._p(dxs_), C.byref(C.c_int64(0)))
+    assert np.array_equal(u1, u2) and np.any(u1 != s.f)
+    for xper, yper in ((0, 0), (1, 0), (0, 1)):
+        u1, u2 = s.f.copy(), s.f.copy()
+        ok.ok_set_advection_bcs_4d_jb(u1.ravel(), C.byref(s.g), s.vel1, s.vel2, atl[0], 1, atl[1], 1, xper, yper, cb, None)
+        R.L.loki_ref_set_ic(cb, None, C.byref(lower))
+        R.L.setadvectionbcs4djb_(R._p(u2), *db, *ib, R._i(order), R._i(s.ng), R._p(s.vel1), R._p(s.vel2), R._p(xlo_), R._p(xhi_),
+                                 R._p(dxs_), R._i(xper), R._i(yper), C.byref(C.c_int64(0)))
+        assert np.array_equal(u1, u2) and np.any(u1 != s.f)
     # derivatives
     dxs = np.array(s.dx)
     r1, r2 = np.zeros_like(s.f), np.zeros_like(s.f)
