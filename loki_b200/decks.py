@@ -208,26 +208,39 @@ class Deck:
 PI = 3.1415926535897932384626
 
 
-def plane_epw(n=(32, 32), nv=(128, 32), A=0.0):
-    """test/planeEPW_fixedIons/planeEPW_fixedIons.pp: one electron species, driven, order 4 / RK4"""
+def perl15(x):
+    """deck constants reach Loki through Perl string interpolation: 15 significant digits
+    (LokiParser.C:104-118).  Perl keeps the constants themselves in full precision; only their use in a
+    parameter line rounds, so the mirrors below compute in full precision and round at the point of use
+    (loki_b200.pp does the same from the deck text; tests compare the two on the reference's own decks)."""
+    return float("%.15g" % x)
+
+
+P = perl15
+
+
+def plane_epw(n=(32, 32), nv=(128, 32), A=0.0, ky1=None):
+    """test/planeEPW_fixedIons/planeEPW_fixedIons.pp: one electron species, driven, order 4 / RK4.
+    The deck has A = 0 (spatially uniform start); tests that switch the spatial mode on pass a ky1 that is
+    periodic over the box."""
     xa, xb, ya, yb = -3 * PI, 3 * PI, -78 * PI, 78 * PI
-    drv = driver_params(xwidth=(xb - xa) / 2.0, ywidth=300 * PI, shape=0.0, omega=1.2001, E0=0.01, t_ramp=10.0,
-                        t_off=10.0, x_shape=0.0, lwidth=50.0, x0=0.0)
-    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, A=A, kx1=1.0 / 3, ky1=1.0 / 78, driver=drv)
-    return Deck("planeEPW_fixedIons", n, (xa, xb, ya, yb), [e], order=4, rk=4)
+    drv = driver_params(xwidth=P(3 * PI), ywidth=P(144 * PI), shape=0.0, omega=1.2001, E0=0.01, t_ramp=10.0,
+                        t_off=100.0, x_shape=0.0, lwidth=50.0, x0=0.0)
+    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, A=A, kx1=P(1.0 / 3), ky1=P(1.0 / 12) if ky1 is None else ky1, driver=drv)
+    return Deck("planeEPW_fixedIons", n, (P(xa), P(xb), P(ya), P(yb)), [e], order=4, rk=4)
 
 
-def plane_iaw(n=(32, 32), nv=(64, 32), order=4, rk=4, A=0.0):
+def plane_iaw(n=(32, 32), nv=(64, 32), order=4, rk=4, A=0.0, ky1=None):
     """test/planeIAW/planeIAW.pp (order 4 / RK4) and test/planeIAW_6 (order 6 / RK6): electrons + ions"""
     klde = 1.0 / 3
     ialpha = math.sqrt(10.0) * math.sqrt(100.0)
     xa, xb, ya, yb = -PI / klde, PI / klde, -78 * PI / klde, 78 * PI / klde
-    drv = driver_params(xwidth=(xb - xa) / 2.0, ywidth=300 * PI, shape=0.0, omega=0.0381, E0=0.1, t_ramp=1.0,
+    drv = driver_params(xwidth=P((xb - xa) / 2.0), ywidth=P(300 * PI), shape=0.0, omega=0.0381, E0=0.1, t_ramp=1.0,
                         t_off=2.0, x_shape=0.0, lwidth=50.0, x0=0.0)
-    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, A=A, kx1=klde, ky1=klde / 78, driver=drv)
-    i = Species("ion", nv, (-10 / ialpha, 10 / ialpha, -10 / ialpha, 10 / ialpha), 100.0, 1.0, tx=0.1, ty=0.1,
-                A=A, kx1=klde, ky1=klde / 78)
-    return Deck("planeIAW" + ("_6" if order == 6 else ""), n, (xa, xb, ya, yb), [e, i], order=order, rk=rk)
+    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, A=A, kx1=P(klde), ky1=P(klde) if ky1 is None else ky1, driver=drv)
+    vi = P(10 / ialpha)
+    i = Species("ion", nv, (-vi, vi, -vi, vi), 100.0, 1.0, tx=0.1, ty=0.1, A=A, kx1=P(klde), ky1=P(klde) if ky1 is None else ky1)
+    return Deck("planeIAW" + ("_6" if order == 6 else ""), n, (P(xa), P(xb), P(ya), P(yb)), [e, i], order=order, rk=rk)
 
 
 def interpenetrating_streams(n=(128, 7), nv=(24, 16), order=6, rk=6):
@@ -235,25 +248,19 @@ def interpenetrating_streams(n=(128, 7), nv=(24, 16), order=6, rk=6):
     y limits scale with Ny so that dx = dy as in the deck"""
     mp_over_me = 1836.0
     m_he, m_c = 4.0 * mp_over_me, 12.0 * mp_over_me
-    vth_he, vth_c = perl15(math.sqrt(1.0 / m_he)), perl15(math.sqrt(1.0 / m_c))
+    vth_he, vth_c = math.sqrt(1.0 / m_he), math.sqrt(1.0 / m_c)
     xa, xb = -62.5, 62.5
-    dx = perl15((xb - xa) / n[0])
-    ya, yb = perl15(-0.5 * n[1] * dx), perl15(0.5 * n[1] * dx)
+    dx = (xb - xa) / n[0]
+    ya, yb = -0.5 * n[1] * dx, 0.5 * n[1] * dx
     common = dict(tl=1.0, tt=1.0, theta=0.0, d=31.25)
     e = Species("electron", nv, (-7.5, 7.5, -7.5, 7.5), 1.0, -1.0,
-                stream=dict(common, beta=0.768, two_sided=True, floor=0.05, frac=10.0, frac2=10.0))
-    lim_he = tuple(perl15(v * 7.5 * vth_he) for v in (-1, 1, -1, 1))
-    he = Species("He", nv, lim_he, m_he, 2.0, stream=dict(common, beta=-0.768, centered=True, floor=0.0, frac=0.025))
-    lim_c = tuple(perl15(v * 7.5 * vth_c) for v in (-1, 1, -1, 1))
-    cfrac = perl15(5.0 / 3.0)
-    c = Species("C", nv, lim_c, m_c, 6.0, stream=dict(common, beta=0.768, two_sided=True, floor=0.0, frac=cfrac, frac2=cfrac))
-    return Deck("InterpenetratingStreams", n, (xa, xb, ya, yb), [e, he, c], order=order, rk=rk, cfl=0.95)
-
-
-def perl15(x):
-    """deck constants reach Loki through Perl string interpolation: 15 significant digits
-    (LokiParser.C:104-118)"""
-    return float("%.15g" % x)
+                stream=dict(common, beta=0.768, floor=0.05, frac=10.0, two_sided=True, frac2=10.0))
+    lim_he = (P(-7.5 * vth_he), P(7.5 * vth_he), P(-7.5 * vth_he), P(7.5 * vth_he))
+    he = Species("He", nv, lim_he, P(m_he), 2.0, stream=dict(common, beta=-0.768, floor=0.0, frac=0.025, centered=True))
+    lim_c = (P(-7.5 * vth_c), P(7.5 * vth_c), P(-7.5 * vth_c), P(7.5 * vth_c))
+    cfrac = P(5.0 / 3.0)
+    c = Species("C", nv, lim_c, P(m_c), 6.0, stream=dict(common, beta=0.768, floor=0.0, frac=cfrac, two_sided=True, frac2=cfrac))
+    return Deck("InterpenetratingStreams", n, (P(xa), P(xb), P(ya), P(yb)), [e, he, c], order=order, rk=rk, cfl=0.95)
 
 
 class VMDeck(Deck):
@@ -299,17 +306,15 @@ class VMDeck(Deck):
 def em_damping(n=(32, 5), nv=(64, 64), order=4):
     """test/emDamping/emDamping.pp: one electron species, Vlasov-Maxwell, order 4 / RK4, cfl 0.8"""
     omega, clight = 3.16, 22.36
-    klde = perl15(math.sqrt(omega ** 2 - 1) / clight)
+    klde = math.sqrt(omega ** 2 - 1) / clight
     Ey = 1.0e-4
-    Bz = perl15(klde * Ey / omega)
-    uy = perl15(-Ey / omega)
-    av_strong = perl15(1.6 / clight)
-    pi = PI
-    xa, xb = perl15(-pi / klde), perl15(pi / klde)
-    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, vy0=uy, x_wave_number=klde,
-                flow_phase=perl15(pi / 2.0))
-    em_ics = [dict(field="E", xamp=0.0, yamp=Ey, zamp=0.0, kx=klde, ky=0.0, phase=0.0),
-              dict(field="B", xamp=0.0, yamp=0.0, zamp=Bz, kx=klde, ky=0.0, phase=0.0)]
+    Bz = klde * Ey / omega
+    uy = -Ey / omega
+    av_strong = 1.6 / clight
+    xa, xb = -PI / klde, PI / klde
+    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, vy0=P(uy), x_wave_number=P(klde), flow_phase=P(PI / 2.0))
+    em_ics = [dict(field="E", xamp=0.0, yamp=P(Ey), zamp=0.0, kx=P(klde), ky=0.0, phase=0.0),
+              dict(field="B", xamp=0.0, yamp=0.0, zamp=P(Bz), kx=P(klde), ky=0.0, phase=0.0)]
     vel_ics = [dict(amp=0.0, kx=0.0, ky=0.0, phase=0.0)]
-    return VMDeck("emDamping", n, (xa, xb, -10.0, 10.0), [e], clight, 0.0, av_strong, em_ics, vel_ics, order=order,
+    return VMDeck("emDamping", n, (P(xa), P(xb), -10.0, 10.0), [e], P(clight), 0.0, P(av_strong), em_ics, vel_ics, order=order,
                   cfl=0.8)

@@ -4,6 +4,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 from util import Setup
 
@@ -236,3 +237,96 @@ def test_vm_rk4_step_small_dt_limit(ok):
     assert np.max(np.abs((emn[I2] - em[I2]) / dt - rem[I2])) <= 1e-3 * np.max(np.abs(rem[I2]))
     assert np.max(np.abs((vzn[I2[1:]] - vz[I2[1:]]) / dt - rvz[I2[1:]])) <= 1e-3 * np.max(np.abs(rvz))
     ok.ok_vm_work_destroy(w)
+
+
+# ---------------------------------------------------------------------------------------------
+# deck reader (loki_b200/pp.py) and the deck mirrors (loki_b200/decks.py)
+# ---------------------------------------------------------------------------------------------
+OWN_DECK = """
+# a Vlasov-Maxwell deck in the reference's .pp syntax, written for this test
+$w = 2.5;            # carrier
+$c = 20.0;
+$k = sqrt($w**2-1)/$c;
+$third = 1/3;
+$xa = -3.1415926535897932384626/$k;
+domain_limits = $xa 27.4 -5. 5.
+N = 24 6
+periodic_dir = true true
+cfl = 0.75
+spatial_solution_order = 6
+light_speed = $c
+sys_type = "maxwell"
+number_of_species = 1
+kinetic_species.1.name = "electron"
+kinetic_species.1.velocity_limits = -6 6 -6 6
+kinetic_species.1.Nv = 20 18
+kinetic_species.1.mass = 1.0
+kinetic_species.1.charge = -1.0
+kinetic_species.1.ic.name = "Perturbed Maxwellian"
+kinetic_species.1.ic.tx = 1.0
+kinetic_species.1.ic.ty = 2.0
+kinetic_species.1.ic.vy0 = $third
+kinetic_species.1.ic.x_wave_number = $k
+kinetic_species.1.num_external_drivers = 1
+kinetic_species.1.external_driver.1.name = "Shaped Ramped Cosine Driver"
+kinetic_species.1.external_driver.1.xwidth = 12.5
+kinetic_species.1.external_driver.1.ywidth = 40
+kinetic_species.1.external_driver.1.omega = $w
+kinetic_species.1.external_driver.1.E_0 = 0.02
+kinetic_species.1.external_driver.1.t_rampup = 3.0
+kinetic_species.1.external_driver.1.t_hold = 4.0
+kinetic_species.1.external_driver.1.t_rampdown = 5.0
+kinetic_species.1.external_driver.1.lwidth = 50
+maxwell.avStrong = 0.08
+maxwell.em_ic.1.name = "SimpleEMIC"
+maxwell.em_ic.1.field = "B"
+maxwell.em_ic.1.zamp = 1.e-4
+maxwell.em_ic.1.x_wave_number = $k
+maxwell.vel_ic.1.name = "SimpleVELIC"
+maxwell.vel_ic.1.amp = 0.5
+"""
+
+
+def test_pp_reader_constants_and_interpolation():
+    """Perl-style constants in full precision, 15 significant digits where a parameter line uses them
+    (LokiParser.C:94-130); old and new driver syntax; Maxwell field initial conditions"""
+    import math
+    from loki_b200 import pp
+    from loki_b200.decks import VMDeck
+    d = pp.deck_from_params(pp.parse(OWN_DECK), name="own")
+    assert isinstance(d, VMDeck) and d.order == 6 and d.rk == 4 and d.n == (24, 6) and d.cfl == 0.75
+    k = math.sqrt(2.5 ** 2 - 1) / 20.0
+    assert d.xlim[0] == float("%.15g" % (-3.1415926535897932384626 / k)) and d.xlim[1] == 27.4
+    e = d.species[0]
+    assert e.vy0 == 0.333333333333333 and not e.factorable and e.x_wave_number == float("%.15g" % k)
+    assert e.ty == 2.0 and e.nv == (20, 18) and e.vlim == (-6.0, 6.0, -6.0, 6.0)
+    assert e.driver[3] == 2.5 and e.driver[6:9] == [3.0, 4.0, 5.0] and e.driver[10] == 50.0
+    assert d.light_speed == 20.0 and d.av_strong == 0.08 and d.av_weak == 0.0
+    assert d.em_ics == [dict(field="B", xamp=0.0, yamp=0.0, zamp=1e-4, kx=float("%.15g" % k), ky=0.0, phase=0.0)]
+    assert d.vel_ics == [dict(amp=0.5, kx=0.0, ky=0.0, phase=0.0)]
+
+
+def _deck_fields(a, b, path=""):
+    out = []
+    for key in sorted(set(vars(a)) | set(vars(b))):
+        va, vb = getattr(a, key, None), getattr(b, key, None)
+        if key == "species":
+            assert len(va) == len(vb)
+            for i_, (sa, sb) in enumerate(zip(va, vb)):
+                out += _deck_fields(sa, sb, path + "species[%d]." % i_)
+        elif key != "name" and va != vb:
+            out.append((path + key, va, vb))
+    return out
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/test"), reason="the reference's decks are only mounted in the build container")
+def test_deck_mirrors_equal_the_reference_decks():
+    """every number of the five benchmark decks, read from the reference's own .pp files, equals the mirror
+    in loki_b200/decks.py that the tests, smoke() and bench.py are built from"""
+    from loki_b200 import pp, decks
+    mirrors = {"planeEPW_fixedIons": decks.plane_epw(), "planeIAW": decks.plane_iaw(),
+               "planeIAW_6": decks.plane_iaw(n=(10, 10), nv=(16, 10), order=6, rk=6), "emDamping": decks.em_damping(),
+               "InterpenetratingStreams": decks.interpenetrating_streams()}
+    for name, mirror in mirrors.items():
+        d = pp.load(os.path.join("/root/reference/test", name, name + ".pp"))
+        assert _deck_fields(d, mirror) == [], name

@@ -32,7 +32,7 @@ def _free_port():
 
 
 def _mk_deck(order, rk):
-    return decks.plane_iaw(n=(16, 20), nv=(16, 12), order=order, rk=rk, A=0.05)
+    return decks.plane_iaw(n=(16, 20), nv=(16, 12), order=order, rk=rk, A=0.05, ky1=1.0 / 234)
 
 
 def _run_rank(rank, world, port, px, py, order, rk, nsteps, dt, out):
