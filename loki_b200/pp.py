@@ -127,9 +127,14 @@ def deck_from_params(params, name="deck"):
             k += 1
         if rk != 4:
             raise ValueError("the Vlasov-Maxwell host mirror integrates with RK4")
-        return _d.VMDeck(name, n, xlim, species, _f(params, "light_speed"), _f(params, "maxwell.avWeak", 0.0),
+        deck = _d.VMDeck(name, n, xlim, species, _f(params, "light_speed"), _f(params, "maxwell.avWeak", 0.0),
                          _f(params, "maxwell.avStrong", 0.0), em_ics, vel_ics, order=order, cfl=cfl)
-    return _d.Deck(name, n, xlim, species, order=order, rk=rk, cfl=cfl)
+    else:
+        deck = _d.Deck(name, n, xlim, species, order=order, rk=rk, cfl=cfl)
+    # time-step controls of Simulation (Simulation.C:415-440); not part of the deck's physics, kept aside
+    deck.run = dict(final_time=_f(params, "final_time", 1.0), save_times=_f(params, "save_times", 1.0),
+                    max_step=int(_f(params, "max_step", 1000000.0)))
+    return deck
 
 
 def load(path):

@@ -1,0 +1,153 @@
+"""Run a `.pp` deck on one GPU through the host mirror: `python -m loki_b200.run deck.pp [--max-steps N]`.
+
+The loop is Simulation::advance (Simulation.C:302-351): dt = cfl * stableDt snapped to the next multiple of
+save_times (selectTimeStep, :464-485), System::advance, and one time-history record per step
+(VPSystem::accumulateSequences / the Maxwell analogue) printed as a JSON line.  Vlasov-Poisson (RK4/RK6) and
+Vlasov-Maxwell (RK4) decks with the initial conditions and the driver the five benchmark decks use.  No
+restart / plot files (HDF5 is out of scope)."""
+import argparse
+import ctypes as C
+import json
+import math
+import sys
+
+import numpy as np
+
+from . import capi, host, pp
+
+
+def select_dt(time, dt_stable_cfl, last_save, save_times, max_time):
+    """Simulation::selectTimeStep (Simulation.C:464-485)"""
+    final_time = min((last_save + 1) * save_times, max_time)
+    remaining = final_time - time
+    if dt_stable_cfl <= remaining:
+        return remaining / int(math.ceil(remaining / dt_stable_cfl))
+    return remaining * (1.0 + 10 * np.finfo(float).eps)
+
+
+class Runner:
+    def __init__(self, deck, stream=None):
+        self.deck, self.L, self.H = deck, capi.load(), host.lib()
+        if self.L.lk_device_count() < 1:
+            raise capi.LokiError("no CUDA device: the hot path has no CPU fallback")
+        self.vm = hasattr(deck, "light_speed")
+        self.sys = C.c_void_p()
+        H = self.H
+        ns = len(deck.species)
+        if self.vm:
+            self.desc = deck.product_vm_desc()
+            capi.check(H.lk_vm_create(C.byref(self.sys), C.byref(self.desc), stream), "lk_vm_create")
+        else:
+            self.desc = deck.product_desc()
+            capi.check(H.lk_vp_create(C.byref(self.sys), C.byref(self.desc), stream), "lk_vp_create")
+        self.shapes = []
+        for s, sp in enumerate(deck.species):
+            f, fx, fv, fnorm = deck.initial_state(sp)
+            self.shapes.append(f.shape)
+            if self.vm:
+                capi.check(H.lk_vm_set_state(self.sys, s, f.ctypes.data), "lk_vm_set_state")
+                if sp.factorable:
+                    capi.check(H.lk_vm_set_inflow(self.sys, s, fx.ctypes.data, fv.ctypes.data, fnorm, sp.frac), "inflow")
+                else:
+                    g3, g4 = deck.inflow_ghost_tables(f)
+                    capi.check(H.lk_vm_set_inflow_ghosts(self.sys, s, g3.ctypes.data, g4.ctypes.data), "inflow")
+            else:
+                capi.check(H.lk_vp_set_state(self.sys, s, f.ctypes.data), "lk_vp_set_state")
+                capi.check(deck.set_inflow(H, self.sys, s), "inflow")
+        if self.vm:
+            em, vz = deck.initial_fields()
+            capi.check(H.lk_vm_set_fields(self.sys, em.ctypes.data), "lk_vm_set_fields")
+            for s in range(ns):
+                capi.check(H.lk_vm_set_vz(self.sys, s, vz[s].ctypes.data), "lk_vm_set_vz")
+        self.time, self.last_save, self.step = 0.0, 0, 0
+        self._seed()
+
+    def _seed(self):
+        """the throw-away evalRHS that seeds lambda_max (VPSystem.C:227-230, VMSystem.C:262-265)"""
+        L, H = self.L, self.H
+        bufs = []
+
+        def dev(count):
+            p = C.c_void_p()
+            capi.check(L.lk_malloc(C.byref(p), 8 * count), "lk_malloc")
+            bufs.append(p)
+            return p
+        ns = len(self.deck.species)
+        rhs = (C.c_void_p * ns)(*[dev(int(np.prod(sh))) for sh in self.shapes])
+        if self.vm:
+            n2d, n1d = self.shapes[0][2], self.shapes[0][3]
+            rvz = (C.c_void_p * ns)(*[dev(n1d * n2d) for _ in range(ns)])
+            capi.check(H.lk_vm_eval_rhs(self.sys, rhs, dev(6 * n1d * n2d), rvz, 0.0), "lk_vm_eval_rhs")
+        else:
+            capi.check(H.lk_vp_eval_rhs(self.sys, rhs, 0.0), "lk_vp_eval_rhs")
+        L.lk_sync(None)
+        for p in bufs:
+            L.lk_free(p)
+
+    def history(self):
+        ns = len(self.deck.species)
+        out = np.zeros((12 + 5 * ns) if self.vm else (5 + 6 * ns))
+        fn = self.H.lk_vm_time_history if self.vm else self.H.lk_vp_time_history
+        got = fn(self.sys, out.ctypes.data, out.size)
+        if got != out.size:
+            raise capi.LokiError("time history failed (%d): %s" % (got, self.L.lk_last_error().decode()))
+        return out
+
+    def advance(self):
+        H, run = self.H, self.deck.run
+        dt = C.c_double()
+        capi.check((H.lk_vm_stable_dt if self.vm else H.lk_vp_stable_dt)(self.sys, C.byref(dt)), "stable_dt")
+        step = select_dt(self.time, self.deck.cfl * dt.value, self.last_save, run["save_times"], run["final_time"])
+        if self.vm:
+            capi.check(H.lk_vm_set_time(self.sys, self.time), "set_time")
+            capi.check(H.lk_vm_advance(self.sys, step), "lk_vm_advance")
+        else:
+            capi.check(H.lk_vp_set_time(self.sys, self.time), "set_time")
+            capi.check(H.lk_vp_advance(self.sys, step), "lk_vp_advance")
+        self.time += step
+        self.step += 1
+        if self.time >= (self.last_save + 1) * run["save_times"] - 1e-12:
+            self.last_save += 1
+        return step
+
+    def done(self):
+        run = self.deck.run
+        return self.time >= run["final_time"] - 1e-12 or self.step >= run["max_step"]
+
+    def state(self, s):
+        out = np.empty(self.shapes[s])
+        capi.check((self.H.lk_vm_get_state if self.vm else self.H.lk_vp_get_state)(self.sys, s, out.ctypes.data), "get_state")
+        return out
+
+    def close(self):
+        if self.sys:
+            (self.H.lk_vm_destroy if self.vm else self.H.lk_vp_destroy)(self.sys)
+            self.sys = C.c_void_p()
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__.splitlines()[0])
+    ap.add_argument("deck")
+    ap.add_argument("--max-steps", type=int, default=None)
+    ap.add_argument("--final-time", type=float, default=None)
+    a = ap.parse_args(argv)
+    deck = pp.load(a.deck)
+    if a.max_steps is not None:
+        deck.run["max_step"] = a.max_steps
+    if a.final_time is not None:
+        deck.run["final_time"] = a.final_time
+    r = Runner(deck)
+    names = (["e_max", "e_tot", "ex_max", "ey_max", "ez_max", "e_sum_tot", "b_max", "b_tot", "bx_max", "by_max", "bz_max",
+              "b_sum_tot"] if r.vm else ["e_max", "e_tot", "ex_max", "ey_max", "e_sum_tot"])
+    per = ["ke", "ke_x", "ke_y", "px", "py"] + ([] if r.vm else ["ke_e_dot"])
+    for sp in deck.species:
+        names += ["%s_%s" % (sp.name, k) for k in per]
+    while not r.done():
+        dt = r.advance()
+        print(json.dumps(dict(step=r.step, time=r.time, dt=dt, **dict(zip(names, r.history().tolist())))))
+    r.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -314,7 +314,7 @@ def _deck_fields(a, b, path=""):
             assert len(va) == len(vb)
             for i_, (sa, sb) in enumerate(zip(va, vb)):
                 out += _deck_fields(sa, sb, path + "species[%d]." % i_)
-        elif key != "name" and va != vb:
+        elif key not in ("name", "run") and va != vb:
             out.append((path + key, va, vb))
     return out
 

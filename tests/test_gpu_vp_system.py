@@ -388,3 +388,89 @@ def test_regression_run_traces_plane_iaw(lk, ok, fast):
         assert star_rel_err(out, f_old[s], f_old[s], ng) <= 1e-12
     H.lk_vp_destroy(sys_)
     ok.ok_vp_work_destroy(w)
+
+
+RUN_DECK = """
+# a small two-species deck in the reference's .pp syntax, written for this test
+$pi = 3.1415926535897932384626;
+$klde = 1/3;
+$xa = -$pi/$klde;
+$xb =  $pi/$klde;
+domain_limits = $xa $xb -30. 30.
+N = 12 6
+periodic_dir = true true
+cfl = 0.9
+final_time = 0.3
+save_times = 0.1
+number_of_species = 2
+kinetic_species.1.name = "electron"
+kinetic_species.1.velocity_limits = -7 7 -7 7
+kinetic_species.1.Nv = 20 12
+kinetic_species.1.mass = 1.0
+kinetic_species.1.charge = -1.0
+kinetic_species.1.ic.name = "Perturbed Maxwellian"
+kinetic_species.1.ic.A = 0.02
+kinetic_species.1.ic.kx1 = $klde
+kinetic_species.1.num_external_drivers = 1
+kinetic_species.1.external_driver.1.name = "Shaped Ramped Cosine Driver"
+kinetic_species.1.external_driver.1.xwidth = 9.42477796076938
+kinetic_species.1.external_driver.1.ywidth = 200
+kinetic_species.1.external_driver.1.omega = 1.1
+kinetic_species.1.external_driver.1.E_0 = 0.05
+kinetic_species.1.external_driver.1.t_ramp = 1.0
+kinetic_species.1.external_driver.1.t_off = 2.0
+kinetic_species.1.external_driver.1.lwidth = 50
+kinetic_species.2.name = "ion"
+kinetic_species.2.velocity_limits = -0.4 0.4 -0.4 0.4
+kinetic_species.2.Nv = 16 12
+kinetic_species.2.mass = 100.0
+kinetic_species.2.charge = 1.0
+kinetic_species.2.ic.name = "Perturbed Maxwellian"
+kinetic_species.2.ic.tx = 0.1
+kinetic_species.2.ic.ty = 0.1
+"""
+
+
+def test_run_deck_file_end_to_end(lk, ok, fast, tmp_path):
+    """deck text -> loki_b200.pp -> loki_b200.run.Runner (Simulation::advance loop on the device) against the
+    same loop driven through the oracle: times, dt sequence, final distribution and kinetic energies"""
+    from loki_b200 import pp, run
+    path = tmp_path / "two_species.pp"
+    path.write_text(RUN_DECK)
+    deck = decks._wrap(pp.load(str(path)))
+    r = run.Runner(deck)
+    w, sp, keep = _oracle(ok, deck)
+    ns = len(deck.species)
+    f_old = [deck.initial_state(s)[0] for s in deck.species]
+    f_new = [np.zeros_like(f) for f in f_old]
+    rhs0 = [np.zeros_like(f) for f in f_old]
+    ax, ay = np.zeros(ns), np.zeros(ns)
+    ok.ok_vp_eval_rhs(w, _ptrs(rhs0), _ptrs(f_old), 0.0, np.zeros(ns), ax, ay)
+    ke = np.zeros(ns)
+    t, last_save = 0.0, 0
+    while not r.done():
+        dt_o = run.select_dt(t, deck.cfl * ok.ok_vp_stable_dt(w, ax, ay, deck.rk), last_save, 0.1, 0.3)
+        dt_d = r.advance()
+        assert abs(dt_d - dt_o) <= 1e-10 * dt_o
+        ok.ok_vp_rk4_step(w, _ptrs(f_new), _ptrs(f_old), t, dt_o, ke)
+        t += dt_o
+        if t >= (last_save + 1) * 0.1 - 1e-12:
+            last_save += 1
+        f_old, f_new = f_new, f_old
+        ok.ok_vp_last_accel_max(w, ax, ay)
+        hist = r.history()
+        for s_ in range(ns):
+            o5 = np.zeros(5)
+            vt = np.zeros(sp[s_].g.nd[2] * sp[s_].g.nd[3] * 2)
+            lo_ = (C.c_int * 2)(-deck.ng, -deck.ng)
+            nd_ = sp[s_].g.nd
+            ok.ok_build_velocity_tables(C.byref(sp[s_].g), C.byref(lo_), deck.species[s_].vlim[0], deck.species[s_].vlim[2], vt,
+                                        np.zeros((nd_[2] + 1) * nd_[3] * 2), np.zeros(nd_[2] * (nd_[3] + 1) * 2))
+            ok.ok_compute_ke(C.byref(sp[s_].g), f_old[s_].ravel(), deck.species[s_].mass, vt, o5)
+            assert abs(hist[5 + 6 * s_] - o5[0]) <= 1e-10 * o5[0]
+    assert r.step >= 3 and abs(r.time - 0.3) < 1e-12 and abs(t - 0.3) < 1e-12
+    ng = deck.ng
+    for s_ in range(ns):
+        assert star_rel_err(r.state(s_), f_old[s_], f_old[s_], ng) <= 1e-12
+    r.close()
+    ok.ok_vp_work_destroy(w)
