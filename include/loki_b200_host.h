@@ -114,10 +114,10 @@ const double* lk_vp_em_vars_ptr(const lk_vp_system* sys);
 const double* lk_vp_rho_ptr(const lk_vp_system* sys);
 /* VPSystem::accumulateSequences (VPSystem.C:591-636) without probes, particles and flux histories:
  * out = {e_max, e_tot, ex_max, ey_max, e_sum_tot} of the field of the last evalRHS (Poisson.C:796-860), then
- * per species {ke, ke_x, ke_y, px, py} (computeke_) and the integrated driver work.  Returns the number of
- * values written, 5 + 6*nspecies (>= 11), or LK_ERR_* (1..3) on failure.  Local to this rank: sums / maxima
- * over ranks are the caller's (Loki_Utilities::getSum / getMaxValue).  Synchronises. */
-int lk_vp_time_history(lk_vp_system* sys, double* out, int capacity);
+ * per species {ke, ke_x, ke_y, px, py} (computeke_) and the integrated driver work: 5 + 6*nspecies values,
+ * *written receives the count.  Local to this rank: sums / maxima over ranks are the caller's
+ * (Loki_Utilities::getSum / getMaxValue).  Synchronises. */
+int lk_vp_time_history(lk_vp_system* sys, double* out, int capacity, int* written);
 /* integrated_ke_e_dot of species s (KineticSpecies.C:282-284); synchronises */
 int lk_vp_ke_e_dot(lk_vp_system* sys, int s, double* value);
 
@@ -163,8 +163,9 @@ int lk_vm_stable_dt(lk_vm_system* sys, double* dt);
 int lk_vm_lambda_max(lk_vm_system* sys, int s, double out[2]);
 /* Maxwell::accumulateSequences (Maxwell.C:753-875) field histories {e_max, e_tot, ex_max, ey_max, ez_max,
  * e_sum_tot, b_max, b_tot, bx_max, by_max, bz_max, b_sum_tot} of the current em_vars, then per species
- * {ke, ke_x, ke_y, 0, 0} (computekemaxwell_); returns 12 + 5*nspecies or LK_ERR_* (1..3).  Synchronises. */
-int lk_vm_time_history(lk_vm_system* sys, double* out, int capacity);
+ * {ke, ke_x, ke_y, 0, 0} (computekemaxwell_): 12 + 5*nspecies values, *written receives the count.
+ * Synchronises. */
+int lk_vm_time_history(lk_vm_system* sys, double* out, int capacity, int* written);
 /* VMSystem::evalRHS of the current state in the reference's UNFUSED order (parity hook): rhs_dev[s] 4D,
  * rhs_em_dev (n1d,n2d,6), rhs_vz_dev[s] (n1d,n2d); device pointers, interior written */
 int lk_vm_eval_rhs(lk_vm_system* sys, double** rhs_dev, double* rhs_em_dev, double** rhs_vz_dev, double time);

@@ -1063,13 +1063,14 @@ int lk_vp_end_step(lk_vp_system* h) { return h ? h->sys.endStep() : LK_ERR_ARG; 
 int lk_vp_eval_rhs(lk_vp_system* h, double** rhs_dev, double time) { return (h && rhs_dev) ? h->sys.evalRHS(rhs_dev, time) : LK_ERR_ARG; }
 const double* lk_vp_em_vars_ptr(const lk_vp_system* h) { return h ? h->sys.em_g.p : nullptr; }
 const double* lk_vp_rho_ptr(const lk_vp_system* h) { return h ? h->sys.rho_g.p : nullptr; }
-int lk_vp_time_history(lk_vp_system* h, double* out, int capacity) {
+int lk_vp_time_history(lk_vp_system* h, double* out, int capacity, int* written) {
   // VPSystem::accumulateSequences (VPSystem.C:591-636) without probes / particles / flux histories:
   // Poisson's five field histories of the field of the last evalRHS, then per species computeke's five
   // and the integrated driver work
-  if (!h || !out) return LK_ERR_ARG;
+  if (!h || !out || !written) return LK_ERR_ARG;
   auto& S = h->sys;
   const int ns = (int)S.species.size(), count = 5 + 6 * ns;
+  *written = 0;
   if (capacity < count) return LK_ERR_ARG;
   loki::DevBuf<double> d;
   int st = d.alloc(5 + 5 * ns);
@@ -1091,7 +1092,8 @@ int lk_vp_time_history(lk_vp_system* h, double* out, int capacity) {
       return LK_ERR_CUDA;
     out[5 + 6 * s + 5] = v;
   }
-  return count;
+  *written = count;
+  return LK_OK;
 }
 int lk_vp_ke_e_dot(lk_vp_system* h, int s, double* value) {
   if (!h || !value || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
@@ -1216,12 +1218,13 @@ int lk_vm_lambda_max(lk_vm_system* h, int s, double out[2]) {
   out[1] = h->sys.species[s]->lambda_max[3];
   return LK_OK;
 }
-int lk_vm_time_history(lk_vm_system* h, double* out, int capacity) {
+int lk_vm_time_history(lk_vm_system* h, double* out, int capacity, int* written) {
   // VMSystem's histories without probes / particles: Maxwell's twelve field histories of the current
   // em_vars, then per species computekemaxwell's {ke, ke_x, ke_y, px = 0, py = 0}
-  if (!h || !out) return LK_ERR_ARG;
+  if (!h || !out || !written) return LK_ERR_ARG;
   auto& S = h->sys;
   const int ns = (int)S.species.size(), count = 12 + 5 * ns;
+  *written = 0;
   if (capacity < count) return LK_ERR_ARG;
   loki::DevBuf<double> d;
   int st = d.alloc(count);
@@ -1234,7 +1237,8 @@ int lk_vm_time_history(lk_vm_system* h, double* out, int capacity) {
   if (st != LK_OK) return st;
   if (cudaStreamSynchronize(S.st) != cudaSuccess) return LK_ERR_CUDA;
   if (cudaMemcpy(out, d.p, sizeof(double) * count, cudaMemcpyDeviceToHost) != cudaSuccess) return LK_ERR_CUDA;
-  return count;
+  *written = count;
+  return LK_OK;
 }
 int lk_vm_eval_rhs(lk_vm_system* h, double** rhs_dev, double* rhs_em_dev, double** rhs_vz_dev, double time) {
   return (h && rhs_dev && rhs_em_dev && rhs_vz_dev) ? h->sys.evalRHS(rhs_dev, rhs_em_dev, rhs_vz_dev, time) : LK_ERR_ARG;

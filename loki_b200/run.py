@@ -88,9 +88,9 @@ class Runner:
         ns = len(self.deck.species)
         out = np.zeros((12 + 5 * ns) if self.vm else (5 + 6 * ns))
         fn = self.H.lk_vm_time_history if self.vm else self.H.lk_vp_time_history
-        got = fn(self.sys, out.ctypes.data, out.size)
-        if got != out.size:
-            raise capi.LokiError("time history failed (%d): %s" % (got, self.L.lk_last_error().decode()))
+        got = C.c_int()
+        capi.check(fn(self.sys, out.ctypes.data, out.size, C.byref(got)), "time_history")
+        assert got.value == out.size
         return out
 
     def advance(self):

@@ -193,6 +193,12 @@ def test_vm_deck_run_traces(lk, ok, fast):
     ax, ay = np.zeros(1), np.zeros(1)
     rhs0, rvz0 = [np.zeros_like(states[0])], [np.zeros_like(vz[0])]   # kept alive: written through raw pointers
     ok.ok_vm_eval_rhs(w, _ptrs(rhs0), np.zeros_like(em), _ptrs(rvz0), _ptrs(f_old), em_old, _ptrs(vz_old), 0.0, ax, ay)
+    g_ = sp[0].g
+    nd_ = g_.nd
+    vel_table = np.zeros(nd_[2] * nd_[3] * 2)
+    lo_ = (C.c_int * 2)(-ng, -ng)
+    ok.ok_build_velocity_tables(C.byref(g_), C.byref(lo_), deck.species[0].vlim[0], deck.species[0].vlim[2], vel_table,
+                                np.zeros((nd_[2] + 1) * nd_[3] * 2), np.zeros(nd_[2] * (nd_[3] + 1) * 2))
     t = 0.0
     for step in range(4):
         dt_o = deck.cfl * ok.ok_vm_stable_dt(w, ax, ay, 4)
@@ -215,6 +221,21 @@ def test_vm_deck_run_traces(lk, ok, fast):
         assert H.lk_vm_get_fields(sys_, em_d.ctypes.data) == 0
         e_o, e_d = float(np.sum(em_old[I2] ** 2)), float(np.sum(em_d[I2] ** 2))
         assert abs(e_d - e_o) <= 1e-10 * e_o
+        # the time-history record (Maxwell::accumulateSequences + computekemaxwell) of the new state
+        hist = np.zeros(12 + 5)
+        nh = C.c_int()
+        assert H.lk_vm_time_history(sys_, hist.ctypes.data, hist.size, C.byref(nh)) == 0 and nh.value == 17
+        fh = np.zeros(12)
+        ok.ok_field_history(np.ascontiguousarray(em_old).ravel(), deck.n[0], deck.n[1], ng, 6, np.array(deck.dx + (1.0, 1.0)), fh)
+        # the wave lives in Ey and Bz: their maxima, the |E|, |B| maxima and the integrals to 1e-10; the
+        # other components are rounding noise, bounded relative to the field they belong to
+        for k_ in (0, 1, 3, 5, 6, 7, 10, 11):
+            assert abs(hist[k_] - fh[k_]) <= 1e-10 * fh[k_], k_
+        for k_, scale in ((2, fh[0]), (4, fh[0]), (8, fh[6]), (9, fh[6])):
+            assert abs(hist[k_] - fh[k_]) <= 1e-10 * scale, k_
+        o3 = np.zeros(3)
+        ok.ok_compute_ke_maxwell(C.byref(sp[0].g), f_old[0].ravel(), deck.species[0].mass, vel_table, vz_old[0].ravel(), o3)
+        assert np.all(np.abs(hist[12:15] - o3) <= 1e-10 * np.abs(o3)) and hist[15] == 0.0 and hist[16] == 0.0
     assert np.any(em_old[I2] != em[I2])
     H.lk_vm_destroy(sys_)
     ok.ok_vm_work_destroy(w)

@@ -363,7 +363,8 @@ def test_regression_run_traces_plane_iaw(lk, ok, fast):
         # the whole time-history record of the step (VPSystem::accumulateSequences): field histories of the
         # field both sides hold, species kinetic energies and momenta of the new state
         hist = np.zeros(5 + 6 * ns)
-        assert H.lk_vp_time_history(sys_, hist.ctypes.data, hist.size) == hist.size
+        nh = C.c_int()
+        assert H.lk_vp_time_history(sys_, hist.ctypes.data, hist.size, C.byref(nh)) == 0 and nh.value == hist.size
         fh = np.zeros(12)
         ok.ok_field_history(np.ascontiguousarray(em_o).ravel(), deck.n[0], deck.n[1], ng, 2, np.array(deck.dx + (1.0, 1.0)), fh)
         # e_max, e_tot, ex_max, e_sum_tot within 1e-10; ey_max is 1 % of ex_max in this deck and is made of
