@@ -314,7 +314,12 @@ def run_own(args):
         import psutil
         need = sum(vols) * 8
         pinned = psutil.virtual_memory().available > 3 * need * max(1, world)
-        bufs = [torch.empty(v, dtype=torch.float64, pin_memory=pinned) for v in vols]
+        try:
+            bufs = [torch.empty(v, dtype=torch.float64, pin_memory=pinned) for v in vols]
+        except RuntimeError:
+            # page-locking that much host memory can fail on a loaded box: fall back to pageable buffers
+            pinned = False
+            bufs = [torch.empty(v, dtype=torch.float64) for v in vols]
         for s in range(nsp):
             H.lk_vp_get_state(sys_, s, bufs[s].data_ptr())
 
