@@ -249,13 +249,15 @@ def run_own(args):
         torch.cuda.synchronize()
 
     dt = 0.02
+    # the clock sampler starts with the warm-up steps (same workload, same load): nvidia-smi needs about a
+    # second to come up on an 8-GPU box, longer than a short timed region
+    clocks = Clocks(local)
+    clocks.start()
     for _ in range(args.warmup):
         step(dt)
     barrier()
     launches0 = L.lk_launch_count()
     L.lk_profile_enable(1)
-    clocks = Clocks(local)
-    clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()

@@ -34,9 +34,12 @@ def _setup(lkm, torch, n, order=4, seed=3):
     fx = 1.0 + 0.1 * torch.cos(2 * np.pi * 3 * xi / n[0])[None, :] * torch.cos(2 * np.pi * 2 * yi / n[1])[:, None]
     fv = torch.exp(-0.5 * (v4[:, None] ** 2 + v3[None, :] ** 2)) / (2 * np.pi)
     f = torch.zeros(nd[3], nd[2], nd[1], nd[0], device=dev, dtype=torch.float64)
-    inner = f[:, :, ng:-ng, ng:-ng]
-    inner.copy_(fv[:, :, None, None] * fx[None, None, :, :])
-    inner.mul_(1.0 + 0.02 * (torch.rand(inner.shape, generator=gen, device=dev, dtype=torch.float64) - 0.5))
+    for lo in range(0, nd[3], 8):            # in slabs of vy planes: bounded temporaries at the 2^31-cell size
+        sl = slice(lo, min(lo + 8, nd[3]))
+        blk = fv[sl, :, None, None] * fx[None, None, :, :]
+        blk.mul_(1.0 + 0.02 * (torch.rand(blk.shape, generator=gen, device=dev, dtype=torch.float64) - 0.5))
+        f[sl, :, ng:-ng, ng:-ng] = blk
+    del blk
     accel = torch.zeros(2, nd[1], nd[0], device=dev, dtype=torch.float64)
     accel[:, ng:-ng, ng:-ng] = 0.05 * (torch.rand(2, n[1], n[0], generator=gen, device=dev, dtype=torch.float64) - 0.5)
     vel = torch.stack([v3[None, :].expand(nd[3], nd[2]), v4[:, None].expand(nd[3], nd[2])]).contiguous()
@@ -82,12 +85,16 @@ def _rhs(lk, lkm, S, out):
         lk.lk_last_error()
 
 
-def test_fullsize_translation_and_two_kernels(lk, fast):
+# the headline single-GPU size (order 4) and the per-GPU tile of the 8-GPU InterpenetratingStreams
+# configuration (order 6): 2^31 interior cells, 2.4e9 elements per array -- every offset needs 64 bits
+@pytest.mark.parametrize("n,order,need_gb", [(N, 4, 60), ((256, 128, 256, 256), 6, 130)])
+def test_fullsize_translation_and_two_kernels(lk, fast, n, order, need_gb):
     import torch
     import loki_b200 as lkm
-    if torch.cuda.get_device_properties(0).total_memory < 60e9:
-        pytest.skip("needs 60 GB of device memory")
-    S = _setup(lkm, torch, N)
+    if torch.cuda.get_device_properties(0).total_memory < need_gb * 1e9:
+        pytest.skip("needs %d GB of device memory" % need_gb)
+    N = n
+    S = _setup(lkm, torch, N, order=order)
     ng = S["ng"]
     _prepare(lk, lkm, S)
     rhs = torch.zeros_like(S["f"])
@@ -102,6 +109,7 @@ def test_fullsize_translation_and_two_kernels(lk, fast):
     line = adv[I].sum(dim=(2, 3))
     assert float(line.abs().max()) <= 1e-9 * scale / (N[2] * N[3])
     del adv, line
+    torch.cuda.empty_cache()
     # ---- the one-thread-per-cell kernel computes the same bits ----
     rhs1 = torch.zeros_like(S["f"])
     old = lk.lk_set_rhs_variant(1)
@@ -111,17 +119,19 @@ def test_fullsize_translation_and_two_kernels(lk, fast):
         lk.lk_set_rhs_variant(old)
     # the two kernels fold 1/12 at different places (face vs flux coefficient): agreement to rounding of the
     # neighbourhood, not bit for bit
-    d = (rhs1[I] - rhs[I]).abs()
+    d = (rhs1[I] - rhs[I]).abs_()
     den = rhs[I].abs().amax(dim=(2, 3), keepdim=True).clamp_min(1e-300)
-    assert float((d / den).max()) <= 1e-12
+    d.div_(den)
+    assert float(d.max()) <= 1e-12
     del rhs1, d, den
+    torch.cuda.empty_cache()
     # ---- translation by (37, 5) cells in (x, y): bit-identical ----
     sx, sy = 37, 5
     f2 = torch.zeros_like(S["f"])
     f2[:, :, ng:-ng, ng:-ng] = torch.roll(S["f"][:, :, ng:-ng, ng:-ng], shifts=(sy, sx), dims=(2, 3))
     a2 = torch.zeros_like(S["accel"])
     a2[:, ng:-ng, ng:-ng] = torch.roll(S["accel"][:, ng:-ng, ng:-ng], shifts=(sy, sx), dims=(1, 2))
-    want = torch.roll(rhs[I], shifts=(sy, sx), dims=(2, 3)).clone()
+    want = torch.roll(rhs[I], shifts=(sy, sx), dims=(2, 3))
     del rhs
     S2 = dict(S, f=f2, accel=a2)
     _prepare(lk, lkm, S2)
