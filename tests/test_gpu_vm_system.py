@@ -239,3 +239,65 @@ def test_vm_deck_run_traces(lk, ok, fast):
     assert np.any(em_old[I2] != em[I2])
     H.lk_vm_destroy(sys_)
     ok.ok_vm_work_destroy(w)
+
+
+def test_full_regression_run_em_damping(lk, ok, fast):
+    """the emDamping regression run in full length (final_time = 10, save_times = 0.2, cfl = 0.8; about 210 RK4
+    steps, limited by Maxwell::computeDt) on the deck's own configuration-space grid with a 32 x 32 velocity
+    grid, production arithmetic on the device against the oracle: the time-history traces of the wave (|E|,
+    Ey, |B|, Bz maxima, field energies, species kinetic energy) within 1e-10 in the norm of the run and 1e-9
+    sample by sample; the distribution within 1e-10 per cell on the bulk at the end"""
+    from loki_b200 import run
+    deck = decks.em_damping(n=(32, 5), nv=(32, 32))
+    deck.run = dict(final_time=10.0, save_times=0.2, max_step=1000000)
+    r = run.Runner(deck)
+    w, sp, keep = _oracle(ok, deck)
+    states, em, vz = _setup(deck, 0, 0.0)
+    ng = deck.ng
+    f_old, f_new = [states[0].copy()], [np.zeros_like(states[0])]
+    em_old, em_new = em.copy(), np.zeros_like(em)
+    vz_old, vz_new = [vz[0].copy()], [np.zeros_like(vz[0])]
+    rhs0, rvz0 = [np.zeros_like(states[0])], [np.zeros_like(vz[0])]
+    ax, ay = np.zeros(1), np.zeros(1)
+    ok.ok_vm_eval_rhs(w, _ptrs(rhs0), np.zeros_like(em), _ptrs(rvz0), _ptrs(f_old), em_old, _ptrs(vz_old), 0.0, ax, ay)
+    g_ = sp[0].g
+    nd_ = g_.nd
+    vt = np.zeros(nd_[2] * nd_[3] * 2)
+    lo_ = (C.c_int * 2)(-ng, -ng)
+    ok.ok_build_velocity_tables(C.byref(g_), C.byref(lo_), deck.species[0].vlim[0], deck.species[0].vlim[2], vt,
+                                np.zeros((nd_[2] + 1) * nd_[3] * 2), np.zeros(nd_[2] * (nd_[3] + 1) * 2))
+    t, last_save = 0.0, 0
+    dev_tr, ora_tr = [], []
+    while not r.done():
+        dt_o = run.select_dt(t, deck.cfl * ok.ok_vm_stable_dt(w, ax, ay, 4), last_save, 0.2, 10.0)
+        dt_d = r.advance()
+        assert abs(dt_d - dt_o) <= 1e-10 * dt_o
+        ok.ok_vm_rk4_step(w, _ptrs(f_new), _ptrs(f_old), em_new, em_old, _ptrs(vz_new), _ptrs(vz_old), t, dt_o)
+        t += dt_o
+        if t >= (last_save + 1) * 0.2 - 1e-12:
+            last_save += 1
+        f_old, f_new = f_new, f_old
+        em_old, em_new = em_new, em_old
+        vz_old, vz_new = vz_new, vz_old
+        ok.ok_vm_last_accel_max(w, ax, ay)
+        hist = r.history()
+        fh = np.zeros(12)
+        ok.ok_field_history(np.ascontiguousarray(em_old).ravel(), deck.n[0], deck.n[1], ng, 6, np.array(deck.dx + (1.0, 1.0)), fh)
+        o3 = np.zeros(3)
+        ok.ok_compute_ke_maxwell(C.byref(g_), f_old[0].ravel(), deck.species[0].mass, vt, vz_old[0].ravel(), o3)
+        idx = (0, 1, 3, 5, 6, 7, 10, 11)
+        dev_tr.append([hist[k_] for k_ in idx] + list(hist[12:15]))
+        ora_tr.append([fh[k_] for k_ in idx] + list(o3))
+    assert r.step >= 150 and abs(r.time - 10.0) < 1e-9
+    dev_tr, ora_tr = np.array(dev_tr), np.array(ora_tr)
+    worst = np.max(np.abs(dev_tr - ora_tr), axis=0) / np.max(np.abs(ora_tr), axis=0)
+    assert np.all(worst <= 1e-10), worst
+    rel = np.abs(dev_tr - ora_tr) / np.abs(ora_tr)
+    assert np.all(rel <= 1e-9), rel.max(axis=0)
+    out = r.state(0)
+    I = (slice(ng, -ng),) * 4
+    big = f_old[0][I] >= 1e-6 * f_old[0][I].max()
+    assert cell_rel_err(out[I][big], f_old[0][I][big]) <= 1e-10
+    print("emDamping regression run: %d steps, worst trace difference %.2e" % (r.step, float(worst.max())))
+    r.close()
+    ok.ok_vm_work_destroy(w)
