@@ -543,3 +543,85 @@ def test_full_regression_run_plane_epw_reduced_grid(lk, ok, fast):
     print("planeEPW regression run: %d steps, worst trace difference %.2e" % (r.step, worst))
     r.close()
     ok.ok_vp_work_destroy(w)
+
+
+def _full_run_vs_oracle(ok, deck, final_time, save_times):
+    """Simulation::advance's loop on the device (loki_b200.run.Runner) and through the oracle, side by side;
+    returns (steps, device traces, oracle traces, device states, oracle states).  Traces per step: e_max,
+    e_tot, ex_max, e_sum_tot, then ke of every species."""
+    from loki_b200 import run
+    deck.run = dict(final_time=final_time, save_times=save_times, max_step=1000000)
+    r = run.Runner(deck)
+    w, sp, keep = _oracle(ok, deck)
+    ns = len(deck.species)
+    f_old = [deck.initial_state(s)[0] for s in deck.species]
+    f_new = [np.zeros_like(f) for f in f_old]
+    rhs0 = [np.zeros_like(f) for f in f_old]
+    ax, ay = np.zeros(ns), np.zeros(ns)
+    ok.ok_vp_eval_rhs(w, _ptrs(rhs0), _ptrs(f_old), 0.0, np.zeros(ns), ax, ay)
+    ng = deck.ng
+    n1d, n2d = deck.n[0] + 2 * ng, deck.n[1] + 2 * ng
+    vts = []
+    for s_ in range(ns):
+        nd_ = sp[s_].g.nd
+        vt = np.zeros(nd_[2] * nd_[3] * 2)
+        lo_ = (C.c_int * 2)(-ng, -ng)
+        ok.ok_build_velocity_tables(C.byref(sp[s_].g), C.byref(lo_), deck.species[s_].vlim[0], deck.species[s_].vlim[2], vt,
+                                    np.zeros((nd_[2] + 1) * nd_[3] * 2), np.zeros(nd_[2] * (nd_[3] + 1) * 2))
+        vts.append(vt)
+    ke = np.zeros(ns)
+    step_fn = ok.ok_vp_rk4_step if deck.rk == 4 else ok.ok_vp_rk6_step
+    t, last_save = 0.0, 0
+    dev_tr, ora_tr = [], []
+    while not r.done():
+        dt_o = run.select_dt(t, deck.cfl * ok.ok_vp_stable_dt(w, ax, ay, deck.rk), last_save, save_times, final_time)
+        dt_d = r.advance()
+        assert abs(dt_d - dt_o) <= 1e-9 * dt_o
+        step_fn(w, _ptrs(f_new), _ptrs(f_old), t, dt_o, ke)
+        t += dt_o
+        if t >= (last_save + 1) * save_times - 1e-12:
+            last_save += 1
+        f_old, f_new = f_new, f_old
+        ok.ok_vp_last_accel_max(w, ax, ay)
+        hist = r.history()
+        em_o = np.ctypeslib.as_array(ok.ok_vp_em_vars(w), shape=(2, n2d, n1d))
+        fh = np.zeros(12)
+        ok.ok_field_history(np.ascontiguousarray(em_o).ravel(), deck.n[0], deck.n[1], ng, 2, np.array(deck.dx + (1.0, 1.0)), fh)
+        d_row, o_row = [hist[0], hist[1], hist[2], hist[4]], [fh[0], fh[1], fh[2], fh[4]]
+        for s_ in range(ns):
+            o5 = np.zeros(5)
+            ok.ok_compute_ke(C.byref(sp[s_].g), f_old[s_].ravel(), deck.species[s_].mass, vts[s_], o5)
+            d_row.append(hist[5 + 6 * s_])
+            o_row.append(o5[0])
+        dev_tr.append(d_row)
+        ora_tr.append(o_row)
+    assert abs(r.time - final_time) < 1e-9
+    states = [r.state(s_) for s_ in range(ns)]
+    steps = r.step
+    r.close()
+    ok.ok_vp_work_destroy(w)
+    return steps, np.array(dev_tr), np.array(ora_tr), states, f_old
+
+
+FULL_RUNS = [
+    # (deck, final_time, save_times, minimum number of steps)
+    (lambda: decks.plane_iaw(n=(16, 8), nv=(24, 16)), 5.0, 1.0, 30),                       # planeIAW, reduced grid
+    (lambda: decks.plane_iaw(n=(10, 10), nv=(16, 10), order=6, rk=6), 5.0, 1.0, 10),        # planeIAW_6, the deck's grid
+    (lambda: decks.interpenetrating_streams(n=(32, 7), nv=(16, 12)), 5.0, 1.0, 10),         # InterpenetratingStreams
+]
+
+
+@pytest.mark.parametrize("mk,final_time,save_times,min_steps", FULL_RUNS)
+def test_full_regression_runs_vp(lk, ok, fast, mk, final_time, save_times, min_steps):
+    """the Vlasov-Poisson regression decks run in full length (final_time = 5) with the reference's time-step
+    selection, production arithmetic on the device against the oracle: every time-history trace within 1e-10
+    in the norm of the run (north-star tolerance), the distribution within 1e-10 of its stencil neighbourhood
+    at the end"""
+    deck = mk()
+    steps, dev_tr, ora_tr, got, want = _full_run_vs_oracle(ok, deck, final_time, save_times)
+    assert steps >= min_steps
+    worst = np.max(np.abs(dev_tr - ora_tr), axis=0) / np.max(np.abs(ora_tr), axis=0)
+    assert np.all(worst <= 1e-10), worst
+    for s_ in range(len(got)):
+        assert star_rel_err(got[s_], want[s_], want[s_], deck.ng) <= 1e-10
+    print("%s regression run: %d steps, worst trace difference %.2e" % (deck.name, steps, float(worst.max())))
