@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from loki_b200.decomp import HaloExchanger, TileLayout, grid_for, split_extent
+from loki_b200.decomp import HaloExchanger, TileLayout, _GroupDist, grid_for, split_extent
 
 
 def test_split_extent_matches_parallel_array_rule():
@@ -89,7 +89,10 @@ def _worker(rank, world, port, px, py, nglobal, ng, out):
         # process row/column by construction
         bufs = {0: [torch.empty(nv4 * nv3 * ny * ng, dtype=torch.float64) for _ in range(4)],
                 1: [torch.empty(nv4 * nv3 * ng * n1d, dtype=torch.float64) for _ in range(4)]}
-        HaloExchanger(lay, rank, dist).exchange(bufs, pack, unpack, local_fill)
+        # the product driver binds the halo messages to their own process group (own NCCL communicator and
+        # stream on the GPU box, so the rho all-gather never queues behind them): same wrapper here
+        halo_group = dist.new_group(ranks=list(range(world)))
+        HaloExchanger(lay, rank, _GroupDist(dist, halo_group)).exchange(bufs, pack, unpack, local_fill)
         # expected: the global array with periodic wrap, this rank's window
         ix = (np.arange(lx - ng, lx + nx + ng)) % nglobal[0]
         iy = (np.arange(ly - ng, ly + ny + ng)) % nglobal[1]
