@@ -201,7 +201,11 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
   const int o2 = (b % nt2) * T2; b /= nt2;
 #endif
   const int chunk = b;
-  const int ng = g.ng;  // == NG
+  // g.ng == NG by construction.  Order 4 (two CTAs per SM, 128 registers): a constant, and the plane stride
+  // below pinned in registers -- the compiler otherwise re-reads both from the constant bank every plane and
+  // the epilogue's address arithmetic waits on those loads (A/B on one box: +1.3 %).  The 255-register
+  // order-6 instantiation is better off without (-1.2 %).
+  const int ng = (ORDER == 4) ? NG : g.ng;
   const int q0 = chunk * chunk_len;                       // first interior vy plane of this CTA
   const int nq = min(chunk_len, g.n[3] - q0);
   if (nq <= 0) return;
@@ -354,6 +358,8 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
   // RK operand tiles land dense: [c][b1][T0]
   const double* const ofo = sAcc + eb1 * C::OPW + C::OPO + ea0;
   const double* const odi = sDi + eb1 * C::OPW + C::OPO + ea0;
+  i64 s3 = g.s[3];
+  if constexpr (ORDER == 4) asm volatile("" : "+l"(s3));  // opaque to the compiler: stays in registers
   auto march = [&](auto ek_tag, auto full_tag) {
     constexpr int EK = decltype(ek_tag)::value;
     constexpr bool FULL = decltype(full_tag)::value != 0;  // the tile lies inside the interior in x, y and vx
@@ -484,7 +490,7 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
       double res[T2];
 #pragma unroll
       for (int c = 0; c < T2; ++c) res[c] = racc[c * T1 * PA];
-      const i64 idx0 = col + g.s[3] * p;
+      const i64 idx0 = col + s3 * p;
       const int s2 = (int)g.s[2];
       if constexpr (EK != 0 && TMA) {
         // the RK operands of the tile travel HBM -> shared memory by TMA while the vx and vy fits run:
