@@ -369,6 +369,16 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
       const double* cur = sCore + sc * C::NCORE;
       const bool more = (q + 1 < q0 + nq);
       const double* const sv = sVel + (p & 1) * 2 * T2;  // [vx(c) | vy(c)] of this plane
+#ifndef LK_EXP_LATEVEL
+      // the next plane's velocities are fetched now and stored at the end of the plane: the load latency of
+      // the sixteen fetching threads must not delay the barrier that closes the plane
+      double vel_next = 0.0;
+      if (more && vel && tid < 2 * T2) {
+        const int c = tid % T2, comp = tid / T2;
+        const int i3 = min(o2 + c, g.n[2] - 1) + ng;
+        vel_next = __ldg(vel + i3 + (i64)g.nd[2] * ((p + 1) + (i64)comp * g.nd[3]));
+      }
+#endif
       if constexpr (EK >= 2 && TMA) {
         // the delta_in tile of this plane has its own buffer, free since the barrier that closed the previous
         // plane: fetch it now, a whole plane ahead of the epilogue (only the f_old tile has to wait for the
@@ -656,7 +666,11 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
           }
         }
       }
+#ifdef LK_EXP_LATEVEL
       if (more && vel) stage_vel(p + 1);
+#else
+      if (more && vel && tid < 2 * T2) sVel[((p + 1) & 1) * 2 * T2 + tid] = vel_next;
+#endif
       __syncthreads();
       if (more) {
         stage_vh(p + 1);
