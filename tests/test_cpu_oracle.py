@@ -330,3 +330,26 @@ def test_deck_mirrors_equal_the_reference_decks():
     for name, mirror in mirrors.items():
         d = pp.load(os.path.join("/root/reference/test", name, name + ".pp"))
         assert _deck_fields(d, mirror) == [], name
+
+
+def test_select_dt_follows_the_reference_rule():
+    """Simulation::selectTimeStep (Simulation.C:464-485): an integer number of equal sub-steps to the next
+    multiple of save_times, or the remaining time stretched by 10 eps when the stable step exceeds it"""
+    from loki_b200.run import select_dt
+    dt = select_dt(0.0, 0.13, 0, 1.0, 5.0)
+    assert dt == 1.0 / 8 and abs(8 * dt - 1.0) < 1e-15
+    assert select_dt(0.95, 0.13, 0, 1.0, 5.0) == (1.0 - 0.95) * (1.0 + 10 * np.finfo(float).eps)
+    assert select_dt(4.0, 0.3, 4, 1.0, 4.5) == 0.5 / 2          # final_time caps the target
+    assert select_dt(1.0, 0.25, 1, 1.0, 5.0) == 0.25             # an exact multiple needs no stretching
+
+
+def test_runner_needs_a_gpu():
+    """the deck runner (like every product path) fails loudly without a CUDA device: no CPU fallback"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from loki_b200 import pp, run
+    from loki_b200.capi import LokiError
+    deck = pp.deck_from_params(pp.parse(OWN_DECK), name="own")
+    with pytest.raises(LokiError):
+        run.Runner(deck)
