@@ -219,6 +219,12 @@ int lk_maxwell_rhs(double* rhs, const double* em, const double* Jx, const double
                    int n1, int n2, int ng, int order, const double* dx, double light_speed, double av_weak,
                    double av_strong, void* stream);
 
+/* appendkrook_ (KineticSpeciesF.f:2995-3034; completeRHS, KineticSpecies.C:1049-1080): Krook-layer damping of an
+ * UNFUSED rhs towards the initial condition, rhs -= nu(x,y)/dt * (u - IC) where nu != 0; nu: (n1d,n2d) device.
+ * Level-0 only: the fused stage never materialises rhs, and no benchmark deck has a Krook layer. */
+int lk_append_krook(double* rhs, const double* u, const lk_geom* g, const double* nu, double dt, const lk_inflow* ic,
+                    void* stream);
+
 /* ---- time-history diagnostics (called at sequence_write_times, not on the stage path) ----
  * computeke_ / computekemaxwell_ (KineticSpeciesF.f:2447-2559): out5_dev = {ke, ke_x, ke_y, px, py}; with
  * vz != NULL the Maxwell flavour: ke includes 0.5 m vz(x,y)^2 f and px = py = 0.  Tree sums (deterministic). */

@@ -99,6 +99,7 @@ _PROTOS = {
     "lk_form_accel": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_int, C.c_int, C.c_int, _vp]),
     "lk_maxwell_rhs": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double, _vp]),
+    "lk_append_krook": (C.c_int, [_vp, _vp, C.POINTER(Geom), _vp, C.c_double, C.POINTER(Inflow), _vp]),
     "lk_compute_ke": (C.c_int, [_vp, _vp, C.POINTER(Geom), C.c_double, _vp, _vp, _vp]),
     "lk_field_history": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), _vp]),
     "lk_malloc": (C.c_int, [C.POINTER(_vp), C.c_int64]),

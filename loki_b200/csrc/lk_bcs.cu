@@ -178,6 +178,27 @@ cudaError_t set_bcs_jb(double* f, const lk_geom* g, const lk_accel* a, const dou
   return cudaGetLastError();
 }
 
+// ---- appendkrook (KineticSpeciesF.f:2995-3034): rhs -= nu(x,y)/dt * (u - f0) where nu != 0, f0 from the IC tables
+__global__ void k_append_krook(Geo g, const double* __restrict__ nu, double dt, lk_inflow ic, const double* __restrict__ u,
+                               double* __restrict__ rhs) {
+  const i64 total = (i64)g.n[0] * g.n[1] * g.n[2] * g.n[3];
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+    const int i1 = (int)(t % g.n[0]) + g.ng;
+    i64 r = t / g.n[0];
+    const int i2 = (int)(r % g.n[1]) + g.ng;
+    r /= g.n[1];
+    const int i3 = (int)(r % g.n[2]) + g.ng, i4 = (int)(r / g.n[2]) + g.ng;
+    const double v = nu[i1 + (i64)g.nd[0] * i2];
+    if (v != 0.0) {
+      const i64 o = i1 + g.s[1] * i2 + g.s[2] * i3 + g.s[3] * i4;
+      const double f0 = inflow_value(ic, g, i1, i2, i3, i4);
+      rhs[o] = rhs[o] - v / dt * (u[o] - f0);
+    }
+  }
+}
+cudaError_t append_krook(double* rhs, const double* u, const lk_geom* g, const double* nu, double dt, const lk_inflow* ic,
+                         cudaStream_t st, int64_t* launches);
+
 cudaError_t set_advection_bcs(double* f, const lk_geom* g, const double* velocities, const lk_inflow* ic, const int at[4],
                               int periodic_x, int periodic_y, cudaStream_t st, int64_t* launches) {
   Geo d;
@@ -205,6 +226,23 @@ cudaError_t set_advection_bcs(double* f, const lk_geom* g, const double* velocit
     k_advection_bcs<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(d, velocities, di, f, 1, at[2], at[3]);
     ++*launches;
   }
+  return cudaGetLastError();
+}
+
+cudaError_t append_krook(double* rhs, const double* u, const lk_geom* g, const double* nu, double dt, const lk_inflow* ic,
+                         cudaStream_t st, int64_t* launches) {
+  Geo d = make_geo(g);
+  lk_inflow di;
+  if (ic) di = *ic;
+  else {
+    lk_inflow z = {};
+    di = z;
+  }
+  const i64 total = (i64)d.n[0] * d.n[1] * d.n[2] * d.n[3];
+  i64 blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_append_krook<<<(unsigned)blocks, 256, 0, st>>>(d, nu, dt, di, u, rhs);
+  ++*launches;
   return cudaGetLastError();
 }
 

@@ -102,6 +102,8 @@ cudaError_t set_advection_bcs(double* f, const lk_geom* g, const double* velocit
                               int periodic_x, int periodic_y, cudaStream_t st, int64_t* launches);
 }
 namespace lkbcs {
+cudaError_t append_krook(double* rhs, const double* u, const lk_geom* g, const double* nu, double dt, const lk_inflow* ic,
+                         cudaStream_t st, int64_t* launches);
 cudaError_t set_bcs_jb(double* f, const lk_geom* g, const lk_accel* a, const double* velocities, const lk_inflow* ic,
                        const int sides[8], cudaStream_t st, int64_t* launches);
 }
@@ -199,6 +201,11 @@ static int inflow_tables_ok(const lk_inflow* ic) {
   if ((ic->kind == 2 && (!ic->fx2 || !ic->fv2)) || (ic->kind == 4 && !ic->fx2)) return 0;
   if (ic->kind == 3 && (!ic->ghost3 || !ic->ghost4)) return 0;
   return 1;
+}
+int lk_append_krook(double* rhs, const double* u, const lk_geom* g, const double* nu, double dt, const lk_inflow* ic, void* stream) {
+  if (!geom_ok(g) || !rhs || !u || !nu || !(dt != 0.0) || !inflow_tables_ok(ic)) return fail(LK_ERR_ARG, "lk_append_krook: bad argument");
+  if (ic && ic->kind == 3) return fail(LK_ERR_UNSUPPORTED, "lk_append_krook: ghost-table inflow holds velocity ghosts only");
+  CHECK_LAUNCH(lkbcs::append_krook(rhs, u, g, nu, dt, ic, (cudaStream_t)stream, &g_fft_launches), "lk_append_krook");
 }
 int lk_set_acceleration_bcs_4d_jb(double* f, const lk_geom* g, const lk_accel* a, const lk_inflow* ic, const int at[4],
                                   void* stream) {

@@ -26,7 +26,7 @@ ROUTINES = {
     "KineticSpeciesF.f": ["xpby4d", "setphasespacevel4d", "setphasespacevelmaxwell4d", "weno43fit4d",
                           "weno65fit4d", "setaccelerationbcs4d", "setadvectionbcs4d", "setaccelerationbcs4djb", "setadvectionbcs4djb", "computeadvectionderivatives4d",
                           "computeaccelerationderivatives4d", "computecurrents", "computekeedot", "computeke",
-                          "computekemaxwell"],
+                          "computekemaxwell", "appendkrook"],
     "PoissonF.f": ["neutralizecharge4d", "computeefieldfrompotential"],
     "MaxwellF.f": ["maxwellevalrhs", "sgmetricfunction", "maxwellevalvzrhs", "xpby2d"],
 }

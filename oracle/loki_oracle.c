@@ -869,6 +869,24 @@ void ok_set_advection_bcs_4d_jb(double* u, const ok_geom* g, const double* vel1,
 }
 
 /* ------------------------------------------------------------------------------------------
+ * appendkrook (KineticSpeciesF.f:2995-3034; called from completeRHS, KineticSpecies.C:1049-1080): Krook-layer
+ * damping towards the initial condition, rhs -= nu(x,y)/dt * (u - f0) wherever nu != 0.
+ * ------------------------------------------------------------------------------------------ */
+void ok_append_krook(double* rhs, const double* u, const ok_geom* g, const double* nu, double dt, ok_ic_fn ic,
+                     void* ic_ctx) {
+  const int ng = g->ng;
+  const int64_t n1d = ND(0);
+  for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
+    for (int i3 = ng; i3 < ng + g->n[2]; ++i3)
+      for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
+        for (int i1 = ng; i1 < ng + g->n[0]; ++i1)
+          if (nu[i1 + n1d * i2] != 0.0) {
+            double f0 = ic(ic_ctx, i1, i2, i3, i4);
+            F4(rhs, i1, i2, i3, i4) = F4(rhs, i1, i2, i3, i4) - nu[i1 + n1d * i2] / dt * (F4(u, i1, i2, i3, i4) - f0);
+          }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Time-history diagnostics.
  * computeke (KineticSpeciesF.f:2447-2500): out = {ke, ke_x, ke_y, px, py}; the running sums start from
  * the incoming values like the Fortran's (the caller zeroes them, KineticSpecies.C:1198-1213).

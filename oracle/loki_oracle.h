@@ -90,6 +90,9 @@ void ok_compute_currents(const ok_geom* g, const double* velocities, const doubl
 double ok_compute_ke_e_dot(const ok_geom* g, const double* u, double charge, const double* velocities,
                            const double* ext_efield, double ke_e_dot_in);
 
+/* appendkrook (KineticSpeciesF.f:2995-3034): rhs -= nu(x,y)/dt * (u - IC) where nu != 0; nu: (n1d,n2d) */
+void ok_append_krook(double* rhs, const double* u, const ok_geom* g, const double* nu, double dt, ok_ic_fn ic,
+                     void* ic_ctx);
 /* time-history diagnostics: computeke / computekemaxwell (KineticSpeciesF.f:2447-2559) and the field
  * histories of Poisson / Maxwell ::accumulateSequences (Poisson.C:796-860, Maxwell.C:753-875) */
 void ok_compute_ke(const ok_geom* g, const double* u, double mass, const double* velocities, double* out5);

@@ -69,6 +69,7 @@ def load():
     L.ok_compute_ke_e_dot.restype = d
     L.ok_compute_ke_e_dot.argtypes = [G, dp, d, dp, dp, d]
     L.ok_reduce_4d_to_2d.argtypes = [dp, dp, G, d, d]
+    L.ok_append_krook.argtypes = [dp, dp, G, dp, d, IC_FN, C.c_void_p]
     L.ok_compute_ke.argtypes = [G, dp, d, dp, dp]
     L.ok_compute_ke_maxwell.argtypes = [G, dp, d, dp, dp, dp]
     L.ok_field_history.argtypes = [dp, i, i, i, i, dp, dp]

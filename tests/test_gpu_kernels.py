@@ -194,6 +194,29 @@ def test_jb_boundary_conditions(lk, ok, n, order, maxwell):
             assert np.array_equal(out, ref) and np.any(out != s.f)
 
 
+@pytest.mark.parametrize("n,order", CASES)
+def test_append_krook(lk, ok, n, order):
+    """appendkrook (Krook-layer damping towards the initial condition) against the oracle, pinned to the
+    reference Fortran: bit for bit"""
+    import loki_b200 as lkm
+    s = Setup(ok, n, order)
+    cb = s.ic_callback(0.7, 0.9)
+    n1d, n2d = s.nd[0], s.nd[1]
+    nu = np.zeros((n2d, n1d))
+    nu[:, : n1d // 3] = np.random.default_rng(4).uniform(0.1, 1.0, size=(n2d, n1d // 3))
+    rhs0 = np.random.default_rng(5).uniform(-1, 1, size=s.f.shape)
+    ref = rhs0.copy()
+    ok.ok_append_krook(ref.ravel(), s.f.ravel(), C.byref(s.g), nu.ravel(), 0.037, cb, None)
+    d = Dev(lk, s)
+    ic = lkm.Inflow()
+    dfx, dfv = d.t(s.fx), d.t(s.fv)
+    ic.kind, ic.fx, ic.fv, ic.fnorm, ic.frac = 1, dfx.data_ptr(), dfv.data_ptr(), 0.7, 0.9
+    drhs, dnu = d.t(rhs0), d.t(nu)
+    chk(lk, lk.lk_append_krook(drhs.data_ptr(), d.f.data_ptr(), C.byref(d.g), dnu.data_ptr(), 0.037, C.byref(ic), None), "krook")
+    out = _np(drhs)
+    assert np.array_equal(out, ref) and np.any(out != rhs0)
+
+
 def _oracle_rhs(ok, s, maxwell=False):
     vel3, vel4, _, _ = s.vel34(ok, maxwell)
     adv = np.zeros_like(s.f)

@@ -129,6 +129,15 @@ def test_pin_kinetic_kernels(ok, ref, n, order, lo):
     xlo = np.zeros(4)
     R.L.computekeedot_(*db, *ib, R._p(xlo), R._p(xlo), R._p(dxs), R._p(s.f), R._d(s.charge), R._p(s.velocities), R._p(ext), C.byref(k2))
     assert k1 == k2.value
+    # appendkrook: a layer that covers part of configuration space
+    nu = np.zeros((n2d, n1d))
+    nu[:, : n1d // 3] = np.random.default_rng(4).uniform(0.1, 1.0, size=(n2d, n1d // 3))
+    r1k = np.random.default_rng(5).uniform(-1, 1, size=s.f.shape)
+    r2k = r1k.copy()
+    ok.ok_append_krook(r1k.ravel(), s.f.ravel(), C.byref(s.g), nu.ravel(), 0.037, cb, None)
+    R.L.loki_ref_set_ic(cb, None, C.byref(lower))
+    R.L.appendkrook_(*db, *ib, R._d(0.037), C.byref(C.c_int64(0)), R._p(nu), R._p(s.f), R._p(r2k))
+    assert np.array_equal(r1k, r2k)
     # time-history kinetic energies: computeke, computekemaxwell
     o5 = np.zeros(5)
     ok.ok_compute_ke(C.byref(s.g), s.f.ravel(), 1.7, s.velocities, o5)
