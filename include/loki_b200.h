@@ -104,7 +104,9 @@ const char* lk_last_error(void);
 int lk_set_strict(int strict);
 int lk_get_strict(void);
 int lk_device_count(void);
-/* 0 = marching shared-memory kernel (default), 1 = one-thread-per-cell cross-check kernel */
+/* 0 = marching shared-memory kernel (default; aligned grids with an RK4-shaped update take its pipelined
+ * instantiation, lk_pipe.cuh), 1 = one-thread-per-cell cross-check kernel, 2 = marching kernel, generic
+ * instantiation only (cross-check of the pipelined one: the two give identical bits) */
 int lk_set_rhs_variant(int variant);
 
 /* ---- a1/a2: WENO43Fit4D / WENO65Fit4D (KineticSpeciesF.f:723-790, 914-979); test hook ----
@@ -250,6 +252,8 @@ int lk_profile_enable(int on);
 int lk_profile_summary(int64_t* launches, double* total_ms);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t lk_launch_count(void);
+/* how many of those were the pipelined instantiation of the stage kernel (lk_pipe.cuh) */
+int64_t lk_pipe_launch_count(void);
 
 #ifdef __cplusplus
 }

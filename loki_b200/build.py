@@ -52,6 +52,8 @@ def build(force=False, verbose=False):
         o = os.path.join(bdir, obj)
         objs.append(o)
         deps = [h for h in hdrs if src == "lk_host.cu" or not h.endswith("loki_b200_host.h")]
+        if "-DLK_STRICT=1" in flags:  # the pipelined stage kernel is production arithmetic only
+            deps = [h for h in deps if not h.endswith("lk_pipe.cuh")]
         if not force and not verbose and _newer(o, [os.path.join(CSRC, src)] + deps):
             continue  # this object is current: only changed translation units are recompiled
         cmd = [nvcc] + ARCH + COMMON + extra + flags + ["-c", os.path.join(CSRC, src), "-o", o]

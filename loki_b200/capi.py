@@ -109,6 +109,7 @@ _PROTOS = {
     "lk_memset": (C.c_int, [_vp, C.c_int, C.c_int64]),
     "lk_sync": (C.c_int, [_vp]),
     "lk_launch_count": (C.c_int64, []),
+    "lk_pipe_launch_count": (C.c_int64, []),
     "lk_profile_enable": (C.c_int, [C.c_int]),
     "lk_profile_summary": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
 }

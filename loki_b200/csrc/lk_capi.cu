@@ -128,7 +128,7 @@ int lk_set_strict(int strict) {
 int lk_get_strict(void) { return g_strict; }
 int lk_set_rhs_variant(int variant) {
   int old = g_variant;
-  g_variant = variant ? 1 : 0;
+  g_variant = (variant == 1 || variant == 2) ? variant : 0;
   return old;
 }
 int lk_device_count(void) {
@@ -139,6 +139,7 @@ int lk_device_count(void) {
   }
   return n;
 }
+int64_t lk_pipe_launch_count(void) { return lkfast::pipe_launches(); }
 int64_t lk_launch_count(void) { return lkfast::launches() + lkstrict::launches() + g_fft_launches; }
 
 int lk_weno_fit(int order, const double* u, const double* vel, double* face, int64_t count, void* stream) {
@@ -257,7 +258,7 @@ static int stage_impl(double* rhs_out, const double* f, const lk_geom* g, const 
     if (!upd->f_old || !upd->pred) return fail(LK_ERR_ARG, "lk_vlasov_rhs: rk update needs f_old and pred");
     if (upd->pred == f) return fail(LK_ERR_ARG, "lk_vlasov_rhs: pred must not alias the evaluated state");
     if (upd->n_prev < 0 || upd->n_prev > 7) return fail(LK_ERR_ARG, "lk_vlasov_rhs: n_prev out of range");
-    if (upd->wrap && g_variant != 0) return fail(LK_ERR_UNSUPPORTED, "lk_vlasov_rhs: wrap needs the marching kernel (variant 0)");
+    if (upd->wrap && g_variant == 1) return fail(LK_ERR_UNSUPPORTED, "lk_vlasov_rhs: wrap needs the marching kernel (variant 0)");
     if (upd->wrap & ~3) return fail(LK_ERR_ARG, "lk_vlasov_rhs: bad wrap bits");
     for (int j = 0; j < upd->n_prev; ++j)
       if (!upd->k_prev[j]) return fail(LK_ERR_ARG, "lk_vlasov_rhs: missing k_prev");
@@ -268,7 +269,7 @@ static int stage_impl(double* rhs_out, const double* f, const lk_geom* g, const 
   int nmom = 0;
   if (mom) {
     if (!upd || !mom->partial || (mom->nmom != 1 && mom->nmom != 3)) return fail(LK_ERR_ARG, "lk_vlasov_stage: bad moments request");
-    if (g_variant != 0) return fail(LK_ERR_UNSUPPORTED, "lk_vlasov_stage: moments need the marching kernel (variant 0)");
+    if (g_variant == 1) return fail(LK_ERR_UNSUPPORTED, "lk_vlasov_stage: moments need the marching kernel (variant 0)");
     const int64_t need = (int64_t)mom->nmom * DISPATCH(stage_moment_parts)(g) * g->n[0] * g->n[1];
     if (mom->capacity < need) return fail(LK_ERR_ARG, "lk_vlasov_stage: moment partial buffer too small");
     mpart = mom->partial;

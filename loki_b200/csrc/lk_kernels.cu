@@ -4,11 +4,14 @@
 #include "lk_device.cuh"
 #include "lk_launch.h"
 #include "lk_march.cuh"
+#include "lk_pipe.cuh"
 
 namespace LK_NS {
 
 static int64_t g_launches = 0;
 int64_t launches() { return g_launches; }
+static int64_t g_pipe_launches = 0;
+int64_t pipe_launches() { return g_pipe_launches; }
 #define LK_LAUNCHED() (++g_launches, cudaGetLastError())
 
 static DGeo make_geo(const lk_geom* g) {
@@ -508,11 +511,24 @@ cudaError_t vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const
   DUpd du = make_upd(upd);
   i64 total = (i64)g->n[0] * g->n[1] * g->n[2] * g->n[3];
   if (total <= 0) return cudaSuccess;
-  if (variant == 0) {
+  if (variant == 0 || variant == 2) {
     DMom dm;
     dm.part = mom_part;
     dm.nmom = (mom_part && upd) ? nmom : 0;
     dm.nparts = march_moment_parts(d);
+#if !LK_STRICT
+    // aligned grids, RK4-shaped update, acceleration independent of the swept velocity: the pipelined kernel
+    static const bool no_pipe = getenv("LK_NO_PIPE") != nullptr;
+    if (!no_pipe && variant == 0 && pipe_eligible(d, da, du, rhs_out, flags)) {
+      bool used = false;
+      cudaError_t e = (d.order == 4) ? launch_pipe<4>(d, f, velocities, da, du, dm, st, &used)
+                                     : launch_pipe<6>(d, f, velocities, da, du, dm, st, &used);
+      if (used) {
+        if (e == cudaSuccess) { ++g_launches; ++g_pipe_launches; }
+        return e;
+      }
+    }
+#endif
     cudaError_t e = launch_stage_march(d, f, velocities, da, du, rhs_out, flags, dm, st);
     if (e == cudaSuccess) ++g_launches;
     return e;

@@ -55,6 +55,7 @@
                           const double* Jz, int n1, int n2, int ng, int order, double dx, double dy,  \
                           double c, double av_weak, double av_strong, cudaStream_t st);               \
   int64_t launches();                                                                                 \
+  int64_t pipe_launches();                                                                            \
   }
 
 LK_DECLARE_LAUNCHERS(lkfast)

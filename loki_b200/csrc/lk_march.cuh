@@ -191,7 +191,25 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
   int b = blockIdx.x;
   // x tiles fastest, then y, then vx: the CTAs resident together cover whole (x,y) planes of a few vx
   // slices (measured 1 % faster than vx-before-y)
-#ifdef LK_EXP_ORDER_V
+#if defined(LK_GY) && defined(LK_GV)
+  // supertile order: the CTAs resident together cover a block of LK_GY x LK_GV (y, vx) tiles over all x, so
+  // both the y and the vx star halos of a tile are mostly the core boxes of co-resident neighbours (L2 hits)
+  const int o0 = (b % nt0) * T0; b /= nt0;
+  int o1, o2;
+  {
+    const int nyv = nt1 * nt2;
+    int r = b % nyv;
+    b /= nyv;
+    const int gv = r / (nt1 * LK_GV);
+    r -= gv * nt1 * LK_GV;
+    const int hv = min(LK_GV, nt2 - gv * LK_GV);
+    const int gy = r / (LK_GY * hv);
+    r -= gy * LK_GY * hv;
+    const int hy = min(LK_GY, nt1 - gy * LK_GY);
+    o1 = (gy * LK_GY + r % hy) * T1;
+    o2 = (gv * LK_GV + r / hy) * T2;
+  }
+#elif defined(LK_EXP_ORDER_V)
   const int o0 = (b % nt0) * T0; b /= nt0;
   const int o2 = (b % nt2) * T2; b /= nt2;
   const int o1 = (b % nt1) * T1; b /= nt1;

@@ -1,0 +1,121 @@
+"""The pipelined instantiation of the fused stage kernel (loki_b200/csrc/lk_pipe.cuh) against (a) the generic
+marching kernel, bit for bit (same per-cell arithmetic by construction; this pins the synchronisation: a
+missed hand-over shows up as a stale or torn value), and (b) the oracle's unfused RHS + RK4 stage update
+(KineticSpeciesF.f:1949-2245, 10-38; RK4Integrator.H:149-171) within the north-star tolerance."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import Setup, Dev, star_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def chk(lk, status, what):
+    assert status == 0, "%s: %s" % (what, lk.lk_last_error().decode())
+
+
+def _stage(lk, d, s, stage, nmom, wrap, variant, seed=5):
+    """one RK4-shaped fused stage; returns (pred, delta, moment partials, pipelined launches used)"""
+    import torch
+    import loki_b200 as lkm
+    rng = np.random.default_rng(seed)
+    f_old = d.t(s.f * (1.0 + 0.01 * rng.uniform(-1, 1, size=s.f.shape)))
+    delta = d.t(0.001 * s.f * rng.uniform(-1, 1, size=s.f.shape))
+    pred = torch.full_like(d.f, 3.0)
+    u = lkm.RkUpdate()
+    u.f_old, u.pred = f_old.data_ptr(), pred.data_ptr()
+    u.delta_in = None if stage == 1 else delta.data_ptr()
+    u.delta_out = None if stage == 4 else delta.data_ptr()
+    u.w_delta, u.c_pred, u.use_delta = 0.0123, 0.05, int(stage == 4)
+    u.wrap = wrap
+    m, part = None, None
+    if nmom:
+        parts = lk.lk_stage_moment_parts(C.byref(d.g))
+        part = torch.full((nmom * parts * s.n[0] * s.n[1],), float("nan"), dtype=torch.float64, device="cuda")
+        m = lkm.StageMoments()
+        m.nmom, m.partial, m.capacity = nmom, part.data_ptr(), part.numel()
+    old = lk.lk_set_rhs_variant(variant)
+    before = lk.lk_pipe_launch_count()
+    chk(lk, lk.lk_vlasov_stage(None, d.f.data_ptr(), C.byref(d.g), d.velocities.data_ptr(), C.byref(d.accel), C.byref(u),
+                               C.byref(m) if m else None, None), "stage")
+    torch.cuda.synchronize()
+    used = lk.lk_pipe_launch_count() - before
+    lk.lk_set_rhs_variant(old)
+    return pred, delta, part, used
+
+
+SHAPES = [
+    ((32, 8, 8, 5), 4),       # one tile, fewer planes than a chunk
+    ((64, 16, 16, 20), 4),    # 2 x 2 x 2 tiles, several chunks
+    ((32, 24, 40, 9), 4),     # supertile remainders (3 y-tiles, 5 vx-tiles)
+    ((96, 8, 8, 33), 4),
+    ((32, 8, 8, 7), 6),
+    ((64, 16, 24, 18), 6),
+]
+
+
+@pytest.mark.parametrize("wrap", [0, 3])
+@pytest.mark.parametrize("nmom", [0, 1, 3])
+@pytest.mark.parametrize("stage", [1, 2, 4])
+@pytest.mark.parametrize("n,order", SHAPES)
+def test_pipe_equals_generic_kernel(lk, ok, fast, n, order, stage, nmom, wrap):
+    import torch
+    s = Setup(ok, n, order, rough=0.3)
+    d = Dev(lk, s)
+    chk(lk, lk.lk_periodic_fill_4d(d.f.data_ptr(), C.byref(d.g), 1, 1, None), "per")
+    pa, da, ma, used_a = _stage(lk, d, s, stage, nmom, wrap, 0)
+    pb, db, mb, used_b = _stage(lk, d, s, stage, nmom, wrap, 2)
+    assert used_a == 1 and used_b == 0, "the aligned RK4-shaped stage must take the pipelined kernel"
+    assert torch.equal(pa, pb)
+    assert torch.equal(da, db)
+    if nmom:
+        assert torch.equal(ma, mb)
+
+
+@pytest.mark.parametrize("n,order", [((64, 16, 16, 12), 4), ((32, 16, 16, 10), 6)])
+def test_pipe_repeated_launches_are_deterministic(lk, ok, fast, n, order):
+    """scheduling-independent: the hand-overs are data-race free, so 20 launches give one answer"""
+    import torch
+    s = Setup(ok, n, order, rough=0.3)
+    d = Dev(lk, s)
+    chk(lk, lk.lk_periodic_fill_4d(d.f.data_ptr(), C.byref(d.g), 1, 1, None), "per")
+    ref = _stage(lk, d, s, 2, 3, 3, 2)
+    for _ in range(20):
+        got = _stage(lk, d, s, 2, 3, 3, 0)
+        assert got[3] == 1
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2])
+
+
+@pytest.mark.parametrize("stage", [1, 2, 4])
+@pytest.mark.parametrize("n,order", [((32, 16, 16, 12), 4), ((32, 8, 16, 9), 6)])
+def test_pipe_against_oracle(lk, ok, fast, n, order, stage):
+    """the pipelined stage against the oracle's unfused passes on the same inputs"""
+    s = Setup(ok, n, order, rough=0.3)
+    d = Dev(lk, s)
+    # periodic ghosts on both sides
+    ok.ok_periodic_fill_4d(s.f.ravel(), C.byref(s.g), 1, 1)
+    d.f.copy_(d.t(s.f))
+    pred, delta, _, used = _stage(lk, d, s, stage, 0, 0, 0)
+    assert used == 1
+    rng = np.random.default_rng(5)
+    f_old = s.f * (1.0 + 0.01 * rng.uniform(-1, 1, size=s.f.shape))
+    delta0 = 0.001 * s.f * rng.uniform(-1, 1, size=s.f.shape)
+    rhs = np.zeros_like(s.f)
+    vel3, vel4, _, _ = s.vel34(ok)
+    ok.ok_advection_derivatives_4d(rhs.ravel(), s.f.ravel(), C.byref(s.g), s.vel1, s.vel2)
+    ok.ok_acceleration_derivatives_4d(rhs.ravel(), s.f.ravel(), C.byref(s.g), vel3, vel4)
+    w, c = 0.0123, 0.05
+    ng = s.ng
+    I = (slice(ng, -ng),) * 4
+    dl = np.zeros_like(s.f)
+    dl[I] = (w * rhs[I]) if stage == 1 else (delta0[I] + w * rhs[I])
+    pr = f_old.copy()
+    pr[I] = f_old[I] + c * (dl[I] if stage == 4 else rhs[I])
+    got = pred.cpu().numpy()
+    scale = np.maximum(np.abs(s.f), np.abs(f_old))
+    assert star_rel_err(got, pr, scale, ng) <= 1e-12
+    if stage != 4:
+        gd = delta.cpu().numpy()
+        assert star_rel_err(gd, dl, w * np.abs(rhs) + np.abs(delta0) + 1e-3 * scale, ng) <= 1e-12
