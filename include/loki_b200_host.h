@@ -70,11 +70,16 @@ int lk_vp_set_inflow2(lk_vp_system* sys, int s, int kind, const double* fx, cons
 int lk_vp_set_time(lk_vp_system* sys, double t);
 double lk_vp_time(const lk_vp_system* sys);
 
-/* VPSystem::stableDt (VPSystem.C:489-505) from the accelerations of the last evalRHS; local to this
- * rank: the caller takes the MIN over ranks (Loki_Utilities::getMinValue).  Synchronises. */
+/* VPSystem::stableDt (VPSystem.C:489-505) from the accelerations of the last evalRHS.  With configuration
+ * space cut over several ranks the caller first makes the velocity-space maxima global, component by
+ * component, as KineticSpecies::computeDt does with its MPI_Allreduce(MAX) over m_lambda_max
+ * (KineticSpecies.C:650-656): lk_vp_lambda_max on every rank -> MAX over ranks -> lk_vp_set_lambda_max ->
+ * lk_vp_stable_dt (loki_b200/decomp.py::DistributedVP.stable_dt).  Synchronises. */
 int lk_vp_stable_dt(lk_vp_system* sys, double* dt);
-/* {axmax, aymax} of species s from the last evalRHS (m_lambda_max[V1], [V2]) */
+/* {axmax, aymax} of species s from the last evalRHS (m_lambda_max[V1], [V2]); local to this rank's tile */
 int lk_vp_lambda_max(lk_vp_system* sys, int s, double out[2]);
+/* overwrite them with the maxima over all ranks (valid until the next evalRHS) */
+int lk_vp_set_lambda_max(lk_vp_system* sys, int s, const double in[2]);
 
 /* whole step, single rank: copySolnData(old, state); integrator->advance (VPSystem.C:508-525) */
 int lk_vp_advance(lk_vp_system* sys, double dt);

@@ -1023,6 +1023,14 @@ int lk_vp_lambda_max(lk_vp_system* h, int s, double out[2]) {
   out[1] = h->sys.species[s]->lambda_max[3];
   return LK_OK;
 }
+int lk_vp_set_lambda_max(lk_vp_system* h, int s, const double in[2]) {
+  if (!h || !in || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  int st = h->sys.refreshLambda();  // drain the device values first so that they do not overwrite the global ones
+  if (st != LK_OK) return st;
+  h->sys.species[s]->lambda_max[2] = in[0];
+  h->sys.species[s]->lambda_max[3] = in[1];
+  return LK_OK;
+}
 int lk_vp_advance(lk_vp_system* h, double dt) { return h ? h->sys.advance(dt) : LK_ERR_ARG; }
 int lk_vp_nstages(const lk_vp_system* h) { return h ? h->sys.nstages() : 0; }
 int lk_vp_begin_step(lk_vp_system* h, double dt) { return h ? h->sys.beginStep(dt) : LK_ERR_ARG; }

@@ -541,6 +541,13 @@ cudaError_t vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const
   return LK_LAUNCHED();
 }
 int stage_moment_parts(const lk_geom* g) { return march_moment_parts(make_geo(g)); }
+#if defined(LK_PIPE_TRACE) && !LK_STRICT
+extern "C" int lk_debug_pipe_trace(long long* stamps, int* smid) {
+  if (cudaMemcpyFromSymbol(stamps, g_pipe_trace, sizeof(long long) * 296 * 8 * 4 * 8) != cudaSuccess) return 1;
+  if (cudaMemcpyFromSymbol(smid, g_pipe_smid, sizeof(int) * 296) != cudaSuccess) return 1;
+  return 0;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // a12/a13: velocity moments.  Grid (x-blocks, i2, chunk): each thread owns one (i1,i2) and sums its

@@ -139,10 +139,19 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+#ifdef LK_PIPE_TRACE
+// development aid (build_variant "trace"): per-warp clock stamps of 4 planes of 296 CTAs, read back by
+// lk_debug_pipe_trace (tools/pipe_trace.py)
+__device__ long long g_pipe_trace[296 * 8 * 4 * 8];
+__device__ int g_pipe_smid[296];
+#endif
 // EK: 1 = RK4 stage 1 (delta = w rhs), 2 = stages 2,3 (delta += w rhs), 3 = stage 4 (pred = f_old + c (delta + w rhs))
 // NMOM: velocity moments of the new predictor left behind (0, 1: sum f, 3: + sum vx f, sum vy f)
 template <int ORDER, int EK, int NMOM>
-__global__ void __launch_bounds__(256, (PipeCfg<ORDER>::SMEM_BYTES <= 113 * 1024) ? 2 : 1)
+#ifndef LK_PIPE_MINB
+#define LK_PIPE_MINB ((PipeCfg<ORDER>::SMEM_BYTES <= 113 * 1024) ? 2 : 1)
+#endif
+__global__ void __launch_bounds__(256, LK_PIPE_MINB)
 k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restrict__ vel,
              const double* __restrict__ afield, const DUpd upd, const int nt0, const int nt1, const int nt2,
              const int gy, const int gv, const int chunk_len, const DMom mom,
@@ -289,6 +298,12 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
   double* do_p = (EK == 3) ? nullptr : upd.delta_out + col + s3 * (q0 + NG);
   const double w_delta = upd.w_delta, c_pred = upd.c_pred;
 
+#ifdef LK_PIPE_TRACE
+  int smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  const bool trace_on = (blockIdx.x >= 1480 && blockIdx.x < 1480 + 296);
+  if (trace_on && tid == 0) g_pipe_smid[blockIdx.x - 1480] = smid;
+#endif
   int sc = NG - 1;       // ring slot of the plane being updated
   unsigned vb = 0;       // velocity buffer of the plane being updated (byte offset into O_VEL)
   unsigned pp = 0;       // parity of the per-plane barriers (yh, vh, f_old / delta_in, Q); P runs one behind
@@ -304,6 +319,12 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
       vel_next = __ldg(velp);
     }
 
+#ifdef LK_PIPE_TRACE
+#define LK_TR(ev) do { if (trace_on && lane == 0 && q >= q0 + 40 && q < q0 + 44) g_pipe_trace[((((int)blockIdx.x - 1480) * 8 + warp) * 4 + (q - q0 - 40)) * 8 + ev] = clock64(); } while (0)
+#else
+#define LK_TR(ev)
+#endif
+    LK_TR(0);
     // ---------------- A: x fits of slice c = warp, rows b1 = lane % 8, segments of SX cells ----------------
     double xr[SX];
     {
@@ -324,7 +345,9 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
       }
     }
     // ---------------- B: the accumulator is free once every column of the previous plane has its operands ----
+    LK_TR(1);
     if (q > q0) p_wait(sb + B_P, pp ^ 1u);
+    LK_TR(2);
     if (more && tid < 2 * T2) sts(sb + O_VEL + vbn + 8u * tid, vel_next);
 #pragma unroll
     for (int k = 0; k < SX; ++k) sts(sb + t_xa + 8u * k, xr[k]);
@@ -369,6 +392,7 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
 #pragma unroll
       for (int k = 0; k < NG; ++k) v[NG + T2 + k] = lds(sb + O_VH + 8u * C::NVH + t_col + 8u * (k * T1 * PC));
       __syncwarp();
+      LK_TR(3);
       if (p_handover(sb + B_Q, sb + O_CNT, pp, NW, lane) && more) {
         if (elect_one()) issue_halos(p + 1);
       }
@@ -385,7 +409,9 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
       }
     }
     // ---------------- E: add the x+y accumulator, hand its rows over to the f_old tile ----------------
+    LK_TR(4);
     p_wait(sb + B_Q, pp);
+    LK_TR(5);
 #pragma unroll
     for (int c = 0; c < T2; ++c) res[c] = FMA(-kax, res[c], lds(sb + t_ca + 8u * (c * 32)));
     __syncwarp();
@@ -423,7 +449,9 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
     }
 
     // ---------------- G/H: RK stage update straight to global memory, moments of the new predictor ----------
+    LK_TR(6);
     p_wait(sb + B_FO + 8u * warp, pp);
+    LK_TR(7);
     {
       double pr[T2];
 #pragma unroll

@@ -17,6 +17,8 @@ class Species:
         self.tx, self.ty, self.A, self.B, self.Cc = tx, ty, A, B, Cc
         self.kx1, self.ky1, self.kx2, self.ky2, self.frac = kx1, ky1, kx2, ky2, frac
         self.driver, self.bz = driver, bz
+        # ShapedRampedCosineDriver.C:262-268, 293-304: phase in radians; shape_type 0 = "sin2", 1 = "exp"
+        self.driver_phase, self.driver_shape_type = 0.0, 0
         # flow-velocity wave of the Perturbed Maxwellian (PerturbedMaxwellianIC.C:393-410): a non-zero vx0/vy0
         # makes the initial condition non-factorable (:395-397)
         self.vx0, self.vy0, self.x_wave_number, self.y_wave_number, self.flow_phase = vx0, vy0, x_wave_number, y_wave_number, flow_phase
@@ -41,7 +43,7 @@ def driver_params(xwidth, ywidth, shape, omega, E0, t_ramp, t_off, x_shape, lwid
 
 
 class Deck:
-    def __init__(self, name, n, xlim, species, order=4, rk=4, cfl=1.0):
+    def __init__(self, name, n, xlim, species, order=4, rk=4, cfl=0.9):  # Simulation.C:174
         self.name, self.n, self.xlim, self.species, self.order, self.rk, self.cfl = name, n, xlim, species, order, rk, cfl
         self.ng = 2 if order == 4 else 3
         self.dx = ((xlim[1] - xlim[0]) / n[0], (xlim[3] - xlim[2]) / n[1])
@@ -192,7 +194,8 @@ class Deck:
             if sp.driver:
                 for j in range(16):
                     sd[k].driver[j] = sp.driver[j]
-            sd[k].driver_phase, sd[k].driver_shape_type = 0.0, 0
+            sd[k].driver_phase = float(getattr(sp, "driver_phase", 0.0))
+            sd[k].driver_shape_type = int(getattr(sp, "driver_shape_type", 0))
         d = VPDesc()
         d.nspecies, d.species, d.order, d.rk_order = len(self.species), sd, self.order, self.rk
         d.nglobal[0], d.nglobal[1] = self.n
@@ -227,7 +230,7 @@ def plane_epw(n=(32, 32), nv=(128, 32), A=0.0, ky1=None):
     drv = driver_params(xwidth=P(3 * PI), ywidth=P(144 * PI), shape=0.0, omega=1.2001, E0=0.01, t_ramp=10.0,
                         t_off=100.0, x_shape=0.0, lwidth=50.0, x0=0.0)
     e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, A=A, kx1=P(1.0 / 3), ky1=P(1.0 / 12) if ky1 is None else ky1, driver=drv)
-    return Deck("planeEPW_fixedIons", n, (P(xa), P(xb), P(ya), P(yb)), [e], order=4, rk=4)
+    return Deck("planeEPW_fixedIons", n, (P(xa), P(xb), P(ya), P(yb)), [e], order=4, rk=4, cfl=1.0)
 
 
 def plane_iaw(n=(32, 32), nv=(64, 32), order=4, rk=4, A=0.0, ky1=None):
@@ -240,7 +243,7 @@ def plane_iaw(n=(32, 32), nv=(64, 32), order=4, rk=4, A=0.0, ky1=None):
     e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, A=A, kx1=P(klde), ky1=P(klde) if ky1 is None else ky1, driver=drv)
     vi = P(10 / ialpha)
     i = Species("ion", nv, (-vi, vi, -vi, vi), 100.0, 1.0, tx=0.1, ty=0.1, A=A, kx1=P(klde), ky1=P(klde) if ky1 is None else ky1)
-    return Deck("planeIAW" + ("_6" if order == 6 else ""), n, (P(xa), P(xb), P(ya), P(yb)), [e, i], order=order, rk=rk)
+    return Deck("planeIAW" + ("_6" if order == 6 else ""), n, (P(xa), P(xb), P(ya), P(yb)), [e, i], order=order, rk=rk, cfl=1.0)
 
 
 def interpenetrating_streams(n=(128, 7), nv=(24, 16), order=6, rk=6):
@@ -267,7 +270,7 @@ class VMDeck(Deck):
     """a Vlasov-Maxwell deck: Deck + light speed, Maxwell hyper-dissipation and the field initial conditions
     (SimpleEMIC / SimpleVELIC single waves)"""
 
-    def __init__(self, name, n, xlim, species, light_speed, av_weak, av_strong, em_ics, vel_ics, order=4, cfl=1.0):
+    def __init__(self, name, n, xlim, species, light_speed, av_weak, av_strong, em_ics, vel_ics, order=4, cfl=0.9):
         Deck.__init__(self, name, n, xlim, species, order=order, rk=4, cfl=cfl)
         self.light_speed, self.av_weak, self.av_strong = light_speed, av_weak, av_strong
         self.em_ics, self.vel_ics = em_ics, vel_ics

@@ -202,7 +202,6 @@ class DistributedVP:
                     cnt = self.L.lk_halo_count(C.byref(self.geoms[s]), d)
                     bufs[d] = [torch.empty(cnt, dtype=f64, device=device) for _ in range(4)]
                 self.halo.append(bufs)
-            self.lam = torch.zeros(2 * self.nsp, dtype=f64, device=device)
 
     def close(self):
         if self.sys:
@@ -298,14 +297,42 @@ class DistributedVP:
             self.comm_stream.synchronize()
 
     def stable_dt(self):
-        """KineticSpecies::computeDt over all ranks: the velocity-space maxima (axmax, aymax) are maxima over
-        the local tile, so the stable step is the minimum over ranks (the reference all-reduces the same
-        way, Simulation.C:465-485 through Loki_Utilities::getMinValue)."""
+        """KineticSpecies::computeDt with configuration space cut over the ranks.  The reference all-reduces
+        MAX over each component of m_lambda_max on the species communicator BEFORE it forms
+        imLam = sum_d pi lambda_d / dx_d (KineticSpecies.C:650-656), i.e. dt comes from sum_d max_r lambda_d, which
+        is >= max_r sum_d lambda_d: when |a_x| peaks in one tile and |a_y| in another, a MIN over per-rank time
+        steps would be too large.  So: local (axmax, aymax) of every species -> MAX over ranks -> back into the
+        host mirror -> lk_vp_stable_dt (identical on every rank, equal to the single-rank value)."""
         from . import capi
+        if self.world > 1:
+            pair = (C.c_double * 2)()
+            vals = []
+            for s in range(self.nsp):
+                capi.check(self.H.lk_vp_lambda_max(self.sys, s, C.byref(pair)), "lk_vp_lambda_max")
+                vals += [pair[0], pair[1]]
+            glob = allreduce_lambda_max(self.torch, self.dist, vals, self.device)
+            for s in range(self.nsp):
+                pair[0], pair[1] = glob[2 * s], glob[2 * s + 1]
+                capi.check(self.H.lk_vp_set_lambda_max(self.sys, s, C.byref(pair)), "lk_vp_set_lambda_max")
         dt = C.c_double()
         capi.check(self.H.lk_vp_stable_dt(self.sys, C.byref(dt)), "lk_vp_stable_dt")
-        if self.world > 1:
-            t = self.torch.tensor([dt.value], dtype=self.torch.float64, device=self.device)
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
-            return float(t.item())
         return dt.value
+
+
+def allreduce_lambda_max(torch, dist, local_values, device=None):
+    """component-wise MAX over the ranks (KineticSpecies.C:651-656: MPI_Allreduce(MPI_MAX) on m_lambda_max)"""
+    t = torch.tensor(list(local_values), dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.tolist()]
+
+
+def compute_dt(lambda_max, dx, rk_order):
+    """KineticSpecies::computeDt without collision operators (KineticSpecies.C:647-694); host-side restatement
+    of the formula the C++ mirror evaluates (loki_b200/csrc/lk_host.cu KineticSpecies::computeDt)"""
+    import math
+    pi = 4.0 * math.atan(1.0)
+    im = 0.0
+    for d in range(4):
+        im += pi * lambda_max[d] / dx[d]
+    beta = 2.6 if rk_order == 4 else 3.168
+    return math.sqrt(1.0 / (im * im / (beta * beta)))

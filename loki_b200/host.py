@@ -57,6 +57,7 @@ _PROTOS = {
     "lk_vp_time": (C.c_double, [_vp]),
     "lk_vp_stable_dt": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "lk_vp_lambda_max": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double * 2)]),
+    "lk_vp_set_lambda_max": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double * 2)]),
     "lk_vp_advance": (C.c_int, [_vp, C.c_double]),
     "lk_vp_nstages": (C.c_int, [_vp]),
     "lk_vp_begin_step": (C.c_int, [_vp, C.c_double]),

@@ -8,14 +8,68 @@ deck parsed here gives the numbers Loki sees.  Host-side set-up only.
     params = pp.parse(open("planeIAW.pp").read())
     deck = pp.deck_from_params(params)          # loki_b200.decks.Deck / VMDeck
 """
+import ast
 import math
+import operator
 import re
 
 from . import decks as _d
 
 _CONST = re.compile(r"^\s*\$([A-Za-z_]\w*)\s*=\s*(.+?);\s*(#.*)?$")
-_SAFE = {"sqrt": math.sqrt, "exp": math.exp, "log": math.log, "sin": math.sin, "cos": math.cos, "atan2": math.atan2,
-         "abs": abs, "__builtins__": {}}
+_FUNCS = {"sqrt": math.sqrt, "exp": math.exp, "log": math.log, "sin": math.sin, "cos": math.cos, "atan2": math.atan2,
+          "abs": abs}
+_BINOPS = {ast.Add: operator.add, ast.Sub: operator.sub, ast.Mult: operator.mul, ast.Div: operator.truediv,
+           ast.Pow: operator.pow}
+
+
+def _arith(expr):
+    """numbers, + - * / **, parentheses and the functions above -- nothing else (deck text is untrusted input;
+    no eval)"""
+    def ev(n):
+        if isinstance(n, ast.Expression):
+            return ev(n.body)
+        if isinstance(n, ast.Constant) and isinstance(n.value, (int, float)) and not isinstance(n.value, bool):
+            return float(n.value)
+        if isinstance(n, ast.BinOp) and type(n.op) in _BINOPS:
+            return _BINOPS[type(n.op)](ev(n.left), ev(n.right))
+        if isinstance(n, ast.UnaryOp) and isinstance(n.op, (ast.UAdd, ast.USub)):
+            v = ev(n.operand)
+            return -v if isinstance(n.op, ast.USub) else v
+        if isinstance(n, ast.Call) and isinstance(n.func, ast.Name) and n.func.id in _FUNCS and not n.keywords:
+            return float(_FUNCS[n.func.id](*[ev(a) for a in n.args]))
+        raise ValueError("unsupported expression in a deck constant: %r" % expr)
+    return ev(ast.parse(expr.strip(), mode="eval"))
+
+
+class Params(dict):
+    """key -> tokens, remembering which keys the deck builder consumed: whatever it did not consume is either
+    known not to change the physics of the path (output, restart, probes ...) or an error"""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.used = set()
+
+    def __getitem__(self, key):
+        self.used.add(key)
+        return super().__getitem__(key)
+
+    def __contains__(self, key):
+        if super().__contains__(key):
+            self.used.add(key)
+            return True
+        return False
+
+    def get(self, key, default=None):
+        if super().__contains__(key):
+            return self[key]
+        return default
+
+
+# keys that never reach the Vlasov RHS path: output cadence and files, restart, probes, verbosity
+_IGNORABLE = re.compile(
+    r"^(verbosity|start_from_restart|restart\..*|number_of_probes|probe\.\d+\..*|save_data|save_coll_data|plot_ke_fluxes|"
+    r"plot_times_per_file|kinetic_species\.\d+\.name|poisson\.solver_type|poisson\.discretization|"
+    r"kinetic_species\.\d+\.num_tracking_particles|kinetic_species\.\d+\.num_noise_source_particles)$")
 
 
 def _perl_number_string(v):
@@ -25,7 +79,7 @@ def _perl_number_string(v):
 
 def parse(text):
     """-> dict key -> list of tokens (strings; quotes stripped)"""
-    consts, params = {}, {}
+    consts, params = {}, Params()
     for raw in text.splitlines():
         line = raw.strip()
         if not line or line.startswith("#"):
@@ -33,7 +87,7 @@ def parse(text):
         m = _CONST.match(line)
         if m:
             expr = re.sub(r"\$([A-Za-z_]\w*)", lambda mm: repr(consts[mm.group(1)]), m.group(2))
-            consts[m.group(1)] = float(eval(expr, _SAFE, {}))
+            consts[m.group(1)] = _arith(expr)
             continue
         if "=" not in line:
             continue
@@ -67,8 +121,11 @@ def _species(params, k):
     name = _s(params, pre + "name", "species%d" % k)
     icn = _s(params, pre + "ic.name")
     g = lambda key, dflt=0.0: _f(params, pre + "ic." + key, dflt)
-    driver = None
-    if int(_f(params, pre + "num_external_drivers", 0.0)) > 0:
+    driver, driver_phase, driver_shape_type = None, 0.0, 0
+    ndrv = int(_f(params, pre + "num_external_drivers", 0.0))
+    if ndrv > 1:
+        raise ValueError("species %d: %d external drivers; the host mirror applies one" % (k, ndrv))
+    if ndrv > 0:
         dp = pre + "external_driver.1."
         if _s(params, dp + "name") != "Shaped Ramped Cosine Driver":
             raise ValueError("unsupported driver %r" % _s(params, dp + "name"))
@@ -82,11 +139,32 @@ def _species(params, k):
         driver[0], driver[1], driver[2], driver[3], driver[4], driver[5] = q("xwidth"), q("ywidth"), q("shape"), q("omega"), q("E_0"), q("t0")
         driver[6], driver[7], driver[8] = tr, th, td
         driver[9], driver[10], driver[11], driver[12], driver[13] = q("x_shape"), q("lwidth"), q("x0"), q("alpha"), q("t_res")
+        # ShapedRampedCosineDriver.C:262-268: phase (radians) and shape_type (0 sinusoidal / 1 exponential envelope)
+        driver_phase = q("phase")
+        st = _s(params, dp + "shape_type", "sin2")
+        if st not in ("sin2", "exp"):
+            raise ValueError("unknown driver shape_type %r" % st)   # LOKI_ABORT("Unknown shape type")
+        driver_shape_type = 0 if st == "sin2" else 1
+        for old in ("kx", "Lx", "ky", "Ly", "kl", "Ll"):
+            if (dp + old) in params:
+                raise ValueError("driver key %r (old k/L syntax) is not supported; use xwidth / ywidth / lwidth" % old)
+    # physics this mirror does not implement must not be dropped silently
+    for key in ("vflowinitx", "vflowinity", "phi"):
+        if g(key) != 0.0:
+            raise ValueError("species %d: ic.%s != 0 is not supported (MaxwellianThermal / PerturbedMaxwellianIC)" % (k, key))
+    if int(_f(params, pre + "num_collision_operators", 0.0)) > 0:
+        raise ValueError("species %d: collision operators are out of scope of the Vlasov RHS path" % k)
+    if any(key.startswith(pre + "krook.") or key.startswith(pre + "external_dist_krook.") for key in list(params.keys())):
+        raise ValueError("species %d: Krook layers are not wired into the host mirror (lk_append_krook is Level 0 only)" % k)
+    if any(key.startswith(pre + "tz.") for key in list(params.keys())):
+        raise ValueError("species %d: twilight-zone sources are out of scope" % k)
     if icn == "Perturbed Maxwellian":
-        return _d.Species(name, nv, vlim, mass, charge, tx=g("tx", 1.0), ty=g("ty", 1.0), A=g("A"), B=g("B"), Cc=g("C"),
+        sp = _d.Species(name, nv, vlim, mass, charge, tx=g("tx", 1.0), ty=g("ty", 1.0), A=g("A"), B=g("B"), Cc=g("C"),
                           kx1=g("kx1"), ky1=g("ky1"), kx2=g("kx2"), ky2=g("ky2"), frac=g("frac", 1.0), driver=driver,
                           vx0=g("vx0"), vy0=g("vy0"), x_wave_number=g("x_wave_number"), y_wave_number=g("y_wave_number"),
                           flow_phase=g("phase"))
+        sp.driver_phase, sp.driver_shape_type = driver_phase, driver_shape_type
+        return sp
     if icn == "Interpenetrating Stream":
         if _s(params, pre + "ic.syntax", "half plane") != "half plane":
             raise ValueError("only the half-plane syntax of the Interpenetrating Stream IC is supported")
@@ -96,7 +174,9 @@ def _species(params, k):
             st["frac2"] = g("frac2")
         if _s(params, pre + "ic.centered", "false") == "true":
             st["centered"] = True
-        return _d.Species(name, nv, vlim, mass, charge, stream=st, driver=driver)
+        sp = _d.Species(name, nv, vlim, mass, charge, stream=st, driver=driver)
+        sp.driver_phase, sp.driver_shape_type = driver_phase, driver_shape_type
+        return sp
     raise ValueError("unsupported initial condition %r" % icn)
 
 
@@ -107,7 +187,13 @@ def deck_from_params(params, name="deck"):
         raise ValueError("the host mirror is periodic in x and y")
     order = int(_f(params, "spatial_solution_order", 4.0))
     rk = int(_f(params, "temporal_solution_order", 4.0))
-    cfl = _f(params, "cfl", 1.0)
+    cfl = _f(params, "cfl", 0.9)                      # Simulation.C:174
+    if _s(params, "do_relativity", "false") == "true":
+        raise ValueError("do_relativity = true is not supported (non-relativistic velocity tables)")
+    if _s(params, "use_new_bcs", "false") == "true":
+        raise ValueError("use_new_bcs = true: the JB boundary conditions are Level-0 kernels only, not wired into the host mirror")
+    if _s(params, "do_new_algorithm", "true") != "true":
+        raise ValueError("do_new_algorithm = false (flux form) is not the path this library accelerates")
     ns = int(_f(params, "number_of_species"))
     species = [_species(params, k) for k in range(1, ns + 1)]
     if _s(params, "sys_type", "poisson") == "maxwell":
@@ -132,8 +218,13 @@ def deck_from_params(params, name="deck"):
     else:
         deck = _d.Deck(name, n, xlim, species, order=order, rk=rk, cfl=cfl)
     # time-step controls of Simulation (Simulation.C:415-440); not part of the deck's physics, kept aside
+    # Simulation's defaults (Simulation.C:166-181): final_time 1, save_times 1, sequence_write_times 1, max_step 0
     deck.run = dict(final_time=_f(params, "final_time", 1.0), save_times=_f(params, "save_times", 1.0),
-                    max_step=int(_f(params, "max_step", 1000000.0)))
+                    sequence_write_times=_f(params, "sequence_write_times", 1.0), max_step=int(_f(params, "max_step", 0.0)))
+    if isinstance(params, Params):
+        left = sorted(key for key in params.keys() if key not in params.used and not _IGNORABLE.match(key))
+        if left:
+            raise ValueError("deck keys this reader does not implement (they would change the run): " + ", ".join(left))
     return deck
 
 

@@ -1,7 +1,7 @@
 """Run a `.pp` deck on one GPU through the host mirror: `python -m loki_b200.run deck.pp [--max-steps N]`.
 
 The loop is Simulation::advance (Simulation.C:302-351): dt = cfl * stableDt snapped to the next multiple of
-save_times (selectTimeStep, :464-485), System::advance, and one time-history record per step
+save_times (selectTimeStep, :464-485), System::advance, and a time-history record every sequence_write_times
 (VPSystem::accumulateSequences / the Maxwell analogue) printed as a JSON line.  Vlasov-Poisson (RK4/RK6) and
 Vlasov-Maxwell (RK4) decks with the initial conditions and the driver the five benchmark decks use.  No
 restart / plot files (HDF5 is out of scope)."""
@@ -59,7 +59,7 @@ class Runner:
             capi.check(H.lk_vm_set_fields(self.sys, em.ctypes.data), "lk_vm_set_fields")
             for s in range(ns):
                 capi.check(H.lk_vm_set_vz(self.sys, s, vz[s].ctypes.data), "lk_vm_set_vz")
-        self.time, self.last_save, self.step = 0.0, 0, 0
+        self.time, self.last_save, self.last_seq, self.step = 0.0, 0, 0, 0
         self._seed()
 
     def _seed(self):
@@ -106,13 +106,20 @@ class Runner:
             capi.check(H.lk_vp_advance(self.sys, step), "lk_vp_advance")
         self.time += step
         self.step += 1
-        if self.time >= (self.last_save + 1) * run["save_times"] - 1e-12:
-            self.last_save += 1
+        # exact comparisons as in Simulation::advance (Simulation.C:318-327): when rounding leaves the time one ulp
+        # short of a save time, selectTimeStep's remaining * (1 + 10 eps) micro-step closes the gap next
+        self.record = False
+        if self.time >= (self.last_seq + 1) * run.get("sequence_write_times", 1.0):
+            self.record = True          # accumulateSequences()
+            self.last_seq += 1
+        if self.time >= (self.last_save + 1) * run["save_times"]:
+            self.last_save += 1         # writePlotFile()
         return step
 
     def done(self):
+        """!Simulation::notDone (Simulation.H:126-129)"""
         run = self.deck.run
-        return self.time >= run["final_time"] - 1e-12 or self.step >= run["max_step"]
+        return not (self.step < run["max_step"] and self.time < run["final_time"])
 
     def state(self, s):
         out = np.empty(self.shapes[s])
@@ -130,6 +137,7 @@ def main(argv=None):
     ap.add_argument("deck")
     ap.add_argument("--max-steps", type=int, default=None)
     ap.add_argument("--final-time", type=float, default=None)
+    ap.add_argument("--every-step", action="store_true", help="emit the time histories after every step, not every sequence_write_times")
     a = ap.parse_args(argv)
     deck = pp.load(a.deck)
     if a.max_steps is not None:
@@ -142,9 +150,13 @@ def main(argv=None):
     per = ["ke", "ke_x", "ke_y", "px", "py"] + ([] if r.vm else ["ke_e_dot"])
     for sp in deck.species:
         names += ["%s_%s" % (sp.name, k) for k in per]
+    ap_every = a.every_step
     while not r.done():
         dt = r.advance()
-        print(json.dumps(dict(step=r.step, time=r.time, dt=dt, **dict(zip(names, r.history().tolist())))))
+        rec = dict(step=r.step, time=r.time, dt=dt)
+        if r.record or ap_every:   # time histories are collected every sequence_write_times (Simulation.C:318-321)
+            rec.update(zip(names, r.history().tolist()))
+        print(json.dumps(rec))
     r.close()
     return 0
 

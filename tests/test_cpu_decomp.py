@@ -141,3 +141,42 @@ def test_halo_exchange_and_rho_gather_world2_gloo(px, py, nglobal, ng):
     for rank, ok_halo, ok_rho in res:
         assert ok_halo, "rank %d: ghost cells differ from the periodic global array" % rank
         assert ok_rho, "rank %d: gathered rho tiles do not assemble to the global field" % rank
+
+
+def _dt_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from loki_b200.decomp import allreduce_lambda_max
+        # |a_x| peaks in rank 0's tile, |a_y| in rank 1's (two species)
+        local = [[3.0, 0.2, 0.5, 0.1], [0.3, 2.0, 0.4, 0.7]][rank]
+        out.put((rank, allreduce_lambda_max(torch, dist, local)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_stable_dt_uses_componentwise_global_maxima_world2_gloo():
+    """KineticSpecies::computeDt all-reduces MAX on every component of m_lambda_max before it forms the time step
+    (KineticSpecies.C:650-656): sum_d max_r lambda_d, not max_r sum_d lambda_d.  With |a_x| largest in one tile
+    and |a_y| in the other the minimum over per-rank time steps would be too large."""
+    from loki_b200.decomp import compute_dt
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dt_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0] == res[1] == [3.0, 2.0, 0.5, 0.7]
+    dx = (0.5, 0.5, 0.1, 0.1)
+    lam_xy = (7.05, 7.05)
+    dt_global = compute_dt(lam_xy + (3.0, 2.0), dx, 4)        # what the reference (and one rank) computes
+    dt_rank0 = compute_dt(lam_xy + (3.0, 0.2), dx, 4)
+    dt_rank1 = compute_dt(lam_xy + (0.3, 2.0), dx, 4)
+    assert dt_global < min(dt_rank0, dt_rank1)
+    # closed form: beta / (pi * sum_d lambda_d / dx_d)
+    assert abs(dt_global - 2.6 / (np.pi * (2 * 7.05 / 0.5 + 3.0 / 0.1 + 2.0 / 0.1))) < 1e-15

@@ -306,6 +306,38 @@ def test_pp_reader_constants_and_interpolation():
     assert d.vel_ics == [dict(amp=0.5, kx=0.0, ky=0.0, phase=0.0)]
 
 
+def test_pp_reader_rejects_physics_it_does_not_implement():
+    """a deck key that would change the run is an error, never silently dropped (collision operators, twilight
+    zones, Krook layers, a flow-shifted Maxwellian, several drivers, relativity, the JB boundary conditions,
+    anything unknown); output-only keys are fine; constants are arithmetic, not Python"""
+    from loki_b200 import pp
+    base = OWN_DECK
+    assert pp.deck_from_params(pp.parse(base + "verbosity = 3\nrestart.time_interval = 10\nprobe.1.location = 0.5 0.5\n"))
+    for extra in ("kinetic_species.1.num_collision_operators = 1\n",
+                  "kinetic_species.1.collision_operator.1.name = \"Pitch Angle Collision Operator\"\n",
+                  "kinetic_species.1.tz.name = \"TrigTZSource\"\n",
+                  "kinetic_species.1.krook.power = 3\n",
+                  "kinetic_species.1.ic.vflowinitx = 0.3\n",
+                  "kinetic_species.1.num_external_drivers = 2\n",
+                  "kinetic_species.1.external_driver.1.shape_type = \"gauss\"\n",
+                  "do_relativity = true\n", "use_new_bcs = true\n", "do_new_algorithm = false\n",
+                  "some_future_switch = 1\n"):
+        with pytest.raises(ValueError):
+            pp.deck_from_params(pp.parse(base + extra))
+    d = pp.deck_from_params(pp.parse(base + "kinetic_species.1.external_driver.1.shape_type = \"exp\"\n"
+                                            "kinetic_species.1.external_driver.1.phase = 0.25\n"))
+    assert d.species[0].driver_shape_type == 1 and d.species[0].driver_phase == 0.25
+    assert d.product_vm_desc().base.species[0].driver_shape_type == 1
+    with pytest.raises(ValueError):
+        pp.parse("$x = ().__class__.__bases__[0];\n")
+    with pytest.raises(ValueError):
+        pp.parse("$x = __import__('os').getcwd();\n")
+    # the reference's defaults (Simulation.C:166-181): cfl 0.9, max_step 0, sequence_write_times 1
+    minimal = "\n".join(l for l in base.splitlines() if not l.startswith("cfl"))
+    d = pp.deck_from_params(pp.parse(minimal))
+    assert d.cfl == 0.9 and d.run["max_step"] == 0 and d.run["sequence_write_times"] == 1.0
+
+
 def _deck_fields(a, b, path=""):
     out = []
     for key in sorted(set(vars(a)) | set(vars(b))):
