@@ -47,7 +47,10 @@ typedef struct lk_geom {
 typedef struct lk_accel {
   int kind;               /* 0: Vlasov-Poisson, field = accel(n1d,n2d,2) already scaled by q/m
                              (KineticSpecies.C:755); 1: Vlasov-Maxwell, field = em_vars(n1d,n2d,6)
-                             Ex,Ey,Ez,Bx,By,Bz and vz(n1d,n2d)                              */
+                             Ex,Ey,Ez,Bx,By,Bz and vz(n1d,n2d);
+                             2: the materialised arrays themselves (what the Fortran-ABI entry points of
+                             loki_b200_f77.h receive): field = vel3(n3d+1,n4d,n1d,n2d), vz = vel4(n4d+1,n1d,
+                             n2d,n3d), the other members unused; not for lk_max_accel / lk_set_phase_space_vel_4d */
   const double* field;    /* device */
   const double* vz;       /* device, kind 1 only */
   const double* vxface_velocities; /* device (n3d+1, n4d, 2)  KineticSpecies.C:2033-2039 */
@@ -210,6 +213,11 @@ int lk_electric_field(lk_poisson_plan* plan, double* rho, double* phi, double* e
                       void* stream);
 int lk_periodic_fill_2d(double* u, int n1, int n2, int ng, int ncomp, int periodic_x, int periodic_y,
                         void* stream);
+/* the two Fortran pieces of electricField on their own (Level 0): neutralizecharge4d_ (PoissonF.f:10-64) and
+ * computeefieldfrompotential_ (PoissonF.f:68-123: Ex, Ey into comps 0, 1 of em_vars, interior only) */
+int lk_neutralize_charge(double* rho, int n1, int n2, int ng, void* stream);
+int lk_efield_from_potential(double* em_vars, const double* phi, int n1, int n2, int ng, int order, double dx,
+                             double dy, void* stream);
 /* x += b*y on the interior of a (n1d,n2d,ncomp) array: xpby2d_ (MaxwellF.f:62-93) */
 int lk_xpby2d(double* x, const double* y, double b, int n1, int n2, int ng, int ncomp, void* stream);
 /* computeAcceleration glue (KineticSpecies.C:697-774): accel = (em[0:2] + ext) * normalization */
@@ -220,6 +228,9 @@ int lk_form_accel(double* accel, const double* em_vars, const double* ext_efield
 int lk_maxwell_rhs(double* rhs, const double* em, const double* Jx, const double* Jy, const double* Jz,
                    int n1, int n2, int ng, int order, const double* dx, double light_speed, double av_weak,
                    double av_strong, void* stream);
+
+/* maxwellevalvzrhs_ (MaxwellF.f:442-469): dvz = (q/m) Ez on the interior of a (n1d,n2d) array */
+int lk_maxwell_vz_rhs(double* dvz, const double* em, int n1, int n2, int ng, double charge_per_mass, void* stream);
 
 /* appendkrook_ (KineticSpeciesF.f:2995-3034; completeRHS, KineticSpecies.C:1049-1080): Krook-layer damping of an
  * UNFUSED rhs towards the initial condition, rhs -= nu(x,y)/dt * (u - IC) where nu != 0; nu: (n1d,n2d) device.

@@ -99,6 +99,10 @@ _PROTOS = {
     "lk_form_accel": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_int, C.c_int, C.c_int, _vp]),
     "lk_maxwell_rhs": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double, _vp]),
+    "lk_neutralize_charge": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "lk_efield_from_potential": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp]),
+    "lk_maxwell_vz_rhs": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp]),
+    "lk_f77_status": (C.c_int, []),
     "lk_append_krook": (C.c_int, [_vp, _vp, C.POINTER(Geom), _vp, C.c_double, C.POINTER(Inflow), _vp]),
     "lk_compute_ke": (C.c_int, [_vp, _vp, C.POINTER(Geom), C.c_double, _vp, _vp, _vp]),
     "lk_field_history": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), _vp]),

@@ -153,20 +153,22 @@ int lk_xpby4d(double* x, const double* y, double b, const lk_geom* g, void* stre
 }
 
 static bool accel_ok(const lk_accel* a) {
-  if (!a || !a->field || !a->vxface_velocities || !a->vyface_velocities) return false;
+  if (!a || !a->field) return false;
+  if (a->kind == 2) return a->vz != nullptr;  // materialised vel3 / vel4
+  if (!a->vxface_velocities || !a->vyface_velocities) return false;
   if (a->kind != 0 && a->kind != 1) return false;
   if (a->kind == 1 && !a->vz) return false;
   return true;
 }
 
 int lk_max_accel(const lk_geom* g, const lk_accel* a, double* out, void* stream) {
-  if (!geom_ok(g) || !accel_ok(a) || !out) return fail(LK_ERR_ARG, "lk_max_accel: bad argument");
+  if (!geom_ok(g) || !accel_ok(a) || !out || a->kind == 2) return fail(LK_ERR_ARG, "lk_max_accel: bad argument");
   double* s4 = scratch(2, sizeof(double) * 4);
   if (!s4) return cuda_fail(cudaGetLastError(), "lk_max_accel: scratch");
   CHECK_LAUNCH(DISPATCH(max_accel)(g, a, out, s4, (cudaStream_t)stream), "lk_max_accel");
 }
 int lk_set_phase_space_vel_4d(double* vel3, double* vel4, const lk_geom* g, const lk_accel* a, double* out, void* stream) {
-  if (!geom_ok(g) || !accel_ok(a) || !out) return fail(LK_ERR_ARG, "lk_set_phase_space_vel_4d: bad argument");
+  if (!geom_ok(g) || !accel_ok(a) || !out || a->kind == 2) return fail(LK_ERR_ARG, "lk_set_phase_space_vel_4d: bad argument");
   CHECK_LAUNCH(DISPATCH(set_phase_space_vel)(vel3, vel4, g, a, out, (cudaStream_t)stream), "lk_set_phase_space_vel_4d");
 }
 int lk_set_acceleration_bcs_4d(double* f, const lk_geom* g, const lk_accel* a, const lk_inflow* ic, const int at[4],
@@ -417,6 +419,16 @@ int lk_electric_field(lk_poisson_plan* p, double* rho, double* phi, double* em, 
   if (e == cudaSuccess) e = DISPATCH(periodic_fill_2d)(em, p->nx, p->ny, p->ng, 2, 1, 1, st);
   if (e != cudaSuccess) return cuda_fail(e, "lk_electric_field");
   return LK_OK;
+}
+int lk_neutralize_charge(double* rho, int n1, int n2, int ng, void* stream) {
+  if (!rho || n1 < 1 || n2 < 1 || ng < 0) return fail(LK_ERR_ARG, "lk_neutralize_charge: bad argument");
+  CHECK_LAUNCH(DISPATCH(neutralize)(rho, n1, n2, ng, (cudaStream_t)stream), "lk_neutralize_charge");
+}
+int lk_efield_from_potential(double* em, const double* phi, int n1, int n2, int ng, int order, double dx, double dy,
+                             void* stream) {
+  if (!em || !phi || n1 < 1 || n2 < 1 || !((order == 4 && ng >= 2) || (order == 6 && ng >= 3)) || !(dx > 0.0) || !(dy > 0.0))
+    return fail(LK_ERR_ARG, "lk_efield_from_potential: bad argument");
+  CHECK_LAUNCH(DISPATCH(efield_from_phi)(em, phi, n1, n2, ng, order, dx, dy, (cudaStream_t)stream), "lk_efield_from_potential");
 }
 int lk_compute_ke(double* out5, const double* f, const lk_geom* g, double mass, const double* velocities, const double* vz,
                   void* stream) {

@@ -34,7 +34,7 @@ struct DGeo {
 };
 
 struct DAccel {
-  int kind;  // 0 VP, 1 VM
+  int kind;  // 0 VP, 1 VM, 2 materialised vel3 (field) / vel4 (vz) arrays of the Fortran-ABI entry points
   const double* field;
   const double* vz;
   const double* vxf;  // vxface_velocities (n3d+1, n4d, 2)
@@ -86,10 +86,14 @@ __device__ __forceinline__ double accel_y_v(const DAccel& a, const DGeo& g, i64 
   }
 }
 __device__ __forceinline__ double accel_x(const DAccel& a, const DGeo& g, int i1, int i2, int i3, int i4) {
+  // vel3(i3,i4,i1,i2), extents (n3d+1, n4d, n1d, n2d) (KineticSpeciesF.f:65, KineticSpecies.C:1569-1584)
+  if (a.kind == 2) return __ldg(a.field + i3 + (i64)(g.nd[2] + 1) * (i4 + (i64)g.nd[3] * (i1 + (i64)g.nd[0] * i2)));
   const double vy = __ldg(a.vxf + i3 + (i64)(g.nd[2] + 1) * (i4 + (i64)g.nd[3]));
   return accel_x_v(a, g, i1 + (i64)g.nd[0] * i2, vy);
 }
 __device__ __forceinline__ double accel_y(const DAccel& a, const DGeo& g, int i1, int i2, int i3, int i4) {
+  // vel4(i4,i1,i2,i3), extents (n4d+1, n1d, n2d, n3d) (KineticSpeciesF.f:66)
+  if (a.kind == 2) return __ldg(a.vz + i4 + (i64)(g.nd[3] + 1) * (i1 + (i64)g.nd[0] * (i2 + (i64)g.nd[1] * i3)));
   const double vx = __ldg(a.vyf + i3 + (i64)g.nd[2] * i4);
   return accel_y_v(a, g, i1 + (i64)g.nd[0] * i2, vx);
 }

@@ -655,6 +655,12 @@ __global__ void k_vz_rhs(double* __restrict__ dvz, const double* __restrict__ em
   dvz[o] = __dmul_rn(qm, em[o + 2 * pl]);
 }
 
+extern "C" int lk_maxwell_vz_rhs(double* dvz, const double* em, int n1, int n2, int ng, double charge_per_mass, void* stream) {
+  if (!dvz || !em || n1 < 1 || n2 < 1 || ng < 0) return LK_ERR_ARG;
+  k_vz_rhs<<<nb((i64)n1 * n2, 128), 128, 0, (cudaStream_t)stream>>>(dvz, em, charge_per_mass, n1, n2, ng);
+  return cudaGetLastError() == cudaSuccess ? LK_OK : LK_ERR_CUDA;
+}
+
 struct VMSystem {
   lk_vm_desc desc;
   std::vector<lk_species_desc> sdesc;

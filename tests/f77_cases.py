@@ -1,0 +1,219 @@
+"""Seeded calls of the reference's Fortran-ABI routines (KineticSpeciesF.H, PoissonF.H, MaxwellF.H), written ONCE
+against a small backend interface so that the very same argument lists drive
+
+  * oracle/_ref/libloki_ref.so -- the reference's own Fortran, transliterated to C (HostBackend), and
+  * loki_b200/libloki_b200.so  -- the CUDA kernels behind the same symbols on device arrays (DeviceBackend,
+    include/loki_b200_f77.h).
+
+tests/golden/make_golden.py stores the HostBackend outputs in tests/golden/f77abi_golden.npz;
+tests/test_gpu_f77abi.py compares the DeviceBackend outputs (strict arithmetic) with them bit for bit.
+Test infrastructure only."""
+import ctypes as C
+
+import numpy as np
+
+from util import Setup
+
+
+class HostBackend:
+    """arrays stay numpy; the routine works in place"""
+    name = "ref"
+
+    def __init__(self, lib, set_ic):
+        self.L, self._set_ic, self._keep = lib, set_ic, []
+
+    def arr(self, a):
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data_as(C.c_void_p)
+
+    def i(self, v):
+        return C.byref(C.c_int(int(v)))
+
+    def d(self, v):
+        return C.byref(C.c_double(float(v)))
+
+    def ic(self, s, lower):
+        cb = s.ic_callback(0.7, 0.9)
+        self._keep.append(cb)
+        self._set_ic(cb, None, C.byref((C.c_int * 4)(*lower)))
+        return C.byref(C.c_int64(0))
+
+    def call(self, name, *args):
+        getattr(self.L, name)(*args)
+
+    def finish(self):
+        pass
+
+
+class DeviceBackend:
+    """arrays are uploaded on first use and copied back by finish(); scalars and boxes stay host references"""
+    name = "cuda"
+
+    def __init__(self, lib):
+        import torch
+        import loki_b200 as lkm
+        self.torch, self.lkm, self.L = torch, lkm, lib
+        self._dev, self._keep = [], []
+
+    def arr(self, a):
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        for host, t in self._dev:
+            if host is a:
+                return C.c_void_p(t.data_ptr())
+        t = self.torch.from_numpy(a).cuda()
+        self._dev.append((a, t))
+        return C.c_void_p(t.data_ptr())
+
+    def i(self, v):
+        return C.byref(C.c_int(int(v)))
+
+    def d(self, v):
+        return C.byref(C.c_double(float(v)))
+
+    def ic(self, s, lower):
+        # the same initial condition as Setup.ic_callback(0.7, 0.9): fnorm * fv(i3,i4) * fx(i1,i2) * frac
+        fx = self.torch.from_numpy(s.fx).cuda()
+        fv = self.torch.from_numpy(s.fv).cuda()
+        I = self.lkm.Inflow()
+        I.kind, I.fx, I.fv, I.fnorm, I.frac = 1, fx.data_ptr(), fv.data_ptr(), 0.7, 0.9
+        self._keep += [fx, fv, I]
+        return C.byref(C.c_int64(C.addressof(I)))
+
+    def call(self, name, *args):
+        fn = getattr(self.L, name)
+        fn.restype = None
+        fn(*args)
+        st = self.L.lk_f77_status()
+        assert st == 0, "%s: status %d: %s" % (name, st, self.L.lk_last_error().decode())
+
+    def finish(self):
+        self.torch.cuda.synchronize()
+        for host, t in self._dev:
+            host[...] = t.cpu().numpy()
+        self._dev = []
+
+
+def _boxes(B, s, lo=(0, 0, 0, 0)):
+    ng = s.ng
+    data, inter = [], []
+    for k in range(4):
+        data += [lo[k] - ng, lo[k] + s.n[k] - 1 + ng]
+        inter += [lo[k], lo[k] + s.n[k] - 1]
+    return [B.i(v) for v in data], [B.i(v) for v in inter], data, inter
+
+
+GRIDS = {4: (6, 5, 7, 6), 6: (7, 7, 8, 7)}
+LOWER = {4: (0, 0, 0, 0), 6: (3, -2, 5, 1)}
+
+
+def kinetic_cases(B, ok, order):
+    """every 4D routine of the path on one seeded box; returns name -> output array"""
+    n, lo = GRIDS[order], LOWER[order]
+    s = Setup(ok, n, order, bz=0.3, seed=300 + order)
+    db, ib, data, inter = _boxes(B, s, lo)
+    n1d, n2d, n3d, n4d = s.nd
+    out = {}
+    rng = np.random.default_rng(17 + order)
+    # xpby4d
+    x, y = s.f.copy(), np.ascontiguousarray(rng.uniform(-1, 1, size=s.f.shape))
+    B.call("xpby4d_", B.arr(x), B.arr(y), B.d(0.37), *db, *ib)
+    B.finish()
+    out["xpby4d"] = x
+    # setphasespacevel4d / setphasespacevelmaxwell4d
+    for maxwell in (False, True):
+        v3 = np.zeros((n3d + 1) * n4d * n1d * n2d)
+        v4 = np.zeros((n4d + 1) * n1d * n2d * n3d)
+        ax, ay = C.c_double(), C.c_double()
+        if maxwell:
+            B.call("setphasespacevelmaxwell4d_", B.arr(v3), B.arr(v4), *db, *ib, B.arr(s.vxface), B.arr(s.vyface), B.d(s.norm),
+                   B.d(s.bz), B.arr(s.em), B.arr(s.vz), C.byref(ax), C.byref(ay))
+        else:
+            a2 = [B.i(data[0]), B.i(data[1]), B.i(data[2]), B.i(data[3])]
+            B.call("setphasespacevel4d_", B.arr(v3), B.arr(v4), *db, *ib, B.arr(s.vxface), B.arr(s.vyface), B.d(s.norm),
+                   B.d(s.bz), B.arr(s.accel), *a2, C.byref(ax), C.byref(ay))
+        B.finish()
+        tag = "m" if maxwell else ""
+        out["vel3" + tag], out["vel4" + tag], out["amax" + tag] = v3, v4, np.array([ax.value, ay.value])
+    vel3, vel4 = out["vel3"], out["vel4"]
+    # setaccelerationbcs4d: the box touches all four velocity boundaries
+    u = s.f.copy()
+    B.call("setaccelerationbcs4d_", B.arr(u), *db, *db, *ib, B.i(order), B.arr(vel3), B.arr(vel4), B.ic(s, [data[2 * k] for k in range(4)]))
+    B.finish()
+    out["accel_bcs"] = u
+    # setadvectionbcs4d: non-periodic x and / or y
+    for xper, yper in ((0, 0), (1, 0), (0, 1)):
+        u = s.f.copy()
+        B.call("setadvectionbcs4d_", B.arr(u), *db, *db, *ib, B.i(order), B.arr(s.vel1), B.arr(s.vel2), B.i(xper), B.i(yper),
+               B.ic(s, [data[2 * k] for k in range(4)]))
+        B.finish()
+        out["adv_bcs_%d%d" % (xper, yper)] = u
+    # derivatives: advection assigns, acceleration accumulates
+    dxs = np.array(s.dx)
+    rhs = np.zeros_like(s.f)
+    B.call("computeadvectionderivatives4d_", B.arr(rhs), B.arr(s.f), *db, *ib, B.arr(s.vel1), B.arr(s.vel2), B.arr(dxs), B.i(order))
+    B.finish()
+    out["rhs_adv"] = rhs.copy()
+    B.call("computeaccelerationderivatives4d_", B.arr(rhs), B.arr(s.f), *db, *ib, B.arr(vel3), B.arr(vel4), B.arr(dxs), B.i(order))
+    B.finish()
+    out["rhs_full"] = rhs
+    # currents
+    J = [np.zeros_like(s.f) for _ in range(3)]
+    B.call("computecurrents_", *db, *ib, B.arr(s.velocities), B.arr(s.f), B.arr(s.vz), *[B.arr(j) for j in J])
+    B.finish()
+    out["jx"], out["jy"], out["jz"] = J
+    # computekeedot
+    ext = np.ascontiguousarray(rng.uniform(-1, 1, size=(2, n2d, n1d)))
+    k = C.c_double(0.0)
+    xlo = np.zeros(4)
+    B.call("computekeedot_", *db, *ib, B.arr(xlo), B.arr(xlo), B.arr(dxs), B.arr(s.f), B.d(s.charge), B.arr(s.velocities), B.arr(ext),
+           C.byref(k))
+    B.finish()
+    out["ke_e_dot"] = np.array([k.value])
+    # appendkrook: a layer over part of configuration space
+    nu = np.zeros((n2d, n1d))
+    nu[:, : n1d // 3] = rng.uniform(0.1, 1.0, size=(n2d, n1d // 3))
+    rk = np.ascontiguousarray(rng.uniform(-1, 1, size=s.f.shape))
+    B.call("appendkrook_", *db, *ib, B.d(0.037), B.ic(s, [data[2 * k] for k in range(4)]), B.arr(nu), B.arr(s.f), B.arr(rk))
+    B.finish()
+    out["krook"] = rk
+    return out
+
+
+def field_cases(B, order):
+    """the 2D routines (Poisson pieces, Maxwell rhs, vz rhs, xpby2d)"""
+    ng = 2 if order == 4 else 3
+    n1, n2 = 9, 7
+    n1d, n2d = n1 + 2 * ng, n2 + 2 * ng
+    rng = np.random.default_rng(40 + order)
+    db = [B.i(-ng), B.i(n1 - 1 + ng), B.i(-ng), B.i(n2 - 1 + ng)]
+    ib = [B.i(0), B.i(n1 - 1), B.i(0), B.i(n2 - 1)]
+    out = {}
+    rho = np.ascontiguousarray(rng.uniform(-1, 1, size=(n2d, n1d)))
+    B.call("neutralizecharge4d_", *db, *ib, B.arr(rho), B.i(0))
+    B.finish()
+    out["neutral"] = rho
+    phi = np.ascontiguousarray(rng.uniform(-1, 1, size=(n2d, n1d)))
+    dx = np.array([0.3, 0.7, 1.0, 1.0])
+    e = np.zeros((2, n2d, n1d))
+    B.call("computeefieldfrompotential_", *db, *ib, B.i(order), B.i(2), B.arr(dx), B.arr(e), B.arr(phi))
+    B.finish()
+    out["efield"] = e
+    em = np.ascontiguousarray(rng.uniform(-1, 1, size=(6, n2d, n1d)))
+    J = [np.ascontiguousarray(rng.uniform(-1, 1, size=(n2d, n1d))) for _ in range(3)]
+    xlo, xhi = np.array([0.0, 0.0, 0, 0]), np.array([n1 * dx[0], n2 * dx[1], 0, 0])
+    sglo, sghi = xlo[:2].copy(), xhi[:2].copy()
+    for tag, avw, avs in (("", 0.0, 0.0), ("_av", 0.1, 1.6 / 22.36)):
+        m = np.zeros_like(em)
+        B.call("maxwellevalrhs_", *db, *ib, B.arr(xlo), B.arr(xhi), B.arr(dx), B.d(22.36), B.d(avw), B.d(avs), B.i(order),
+               B.arr(sglo), B.arr(sghi), B.arr(em), B.arr(J[0]), B.arr(J[1]), B.arr(J[2]), B.arr(m))
+        B.finish()
+        out["maxwell" + tag] = m
+    dvz = np.zeros((n2d, n1d))
+    B.call("maxwellevalvzrhs_", *db, *ib, B.d(-1.25), B.arr(em), B.arr(dvz))
+    B.finish()
+    out["vzrhs"] = dvz
+    x = em.copy()
+    B.call("xpby2d_", B.arr(x), B.arr(out["maxwell_av"]), B.d(0.01), *db, *ib, B.i(6))
+    B.finish()
+    out["xpby2d"] = x
+    return out

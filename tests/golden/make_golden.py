@@ -1,4 +1,4 @@
-"""Generates tests/golden/kinetic_f77_golden.npz from oracle/_ref/libloki_ref.so, i.e. from the
+"""Generates tests/golden/kinetic_f77_golden.npz and tests/golden/f77abi_golden.npz from oracle/_ref/libloki_ref.so, i.e. from the
 reference's own Fortran kernels (KineticSpeciesF.f) transliterated by oracle/f77toc.py and compiled with
 gcc -O2 -ffp-contract=off.  Run in the build container (needs /root/reference):
     make -C oracle ref && python tests/golden/make_golden.py
@@ -68,6 +68,19 @@ def main():
         out["rhs%d_kem" % order] = np.array([v.value for v in r3])
     path = os.path.join(HERE, "kinetic_f77_golden.npz")
     np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+    # every routine of the Fortran ABI the CUDA library re-exports (include/loki_b200_f77.h), through the argument
+    # lists of tests/f77_cases.py: the GPU tests replay the same calls on device arrays and compare bits
+    from f77_cases import HostBackend, kinetic_cases, field_cases
+    B = HostBackend(R.L, R.L.loki_ref_set_ic)
+    out2 = {}
+    for order in (4, 6):
+        for k, v in kinetic_cases(B, ok, order).items():
+            out2["k%d_%s" % (order, k)] = v
+        for k, v in field_cases(B, order).items():
+            out2["f%d_%s" % (order, k)] = v
+    path = os.path.join(HERE, "f77abi_golden.npz")
+    np.savez_compressed(path, **out2)
     print("wrote", path, os.path.getsize(path), "bytes")
 
 

@@ -18,6 +18,12 @@ def test_library_exports_every_declared_symbol():
         hdr = open(os.path.join(root, "include", h)).read()
         names |= set(re.findall(r"\b(lk_[a-z0-9_]+)\s*\(", hdr))
     assert len(names) > 55
+    # Level 0: the reference's own Fortran symbols (trailing underscore, KineticSpeciesF.H:13-35)
+    f77 = open(os.path.join(root, "include", "loki_b200_f77.h")).read()
+    f77_names = set(re.findall(r"^void\s+([a-z0-9]+_)\s*\(", f77, flags=re.M))
+    assert {"xpby4d_", "computeadvectionderivatives4d_", "computeaccelerationderivatives4d_", "setaccelerationbcs4d_",
+            "setphasespacevel4d_", "maxwellevalrhs_", "neutralizecharge4d_", "appendkrook_"} <= f77_names and len(f77_names) >= 15
+    names |= f77_names | {"lk_f77_status"}
     missing = [n for n in sorted(names) if not hasattr(L, n)]
     assert not missing, missing
     assert L.lk_version() >= 100

@@ -274,7 +274,7 @@ def test_full_regression_run_em_damping(lk, ok, fast):
         assert abs(dt_d - dt_o) <= 1e-10 * dt_o
         ok.ok_vm_rk4_step(w, _ptrs(f_new), _ptrs(f_old), em_new, em_old, _ptrs(vz_new), _ptrs(vz_old), t, dt_o)
         t += dt_o
-        if t >= (last_save + 1) * 0.2 - 1e-12:
+        if t >= (last_save + 1) * 0.2:
             last_save += 1
         f_old, f_new = f_new, f_old
         em_old, em_new = em_new, em_old

@@ -223,3 +223,21 @@ def test_oracle_matches_committed_golden_vectors(ok):
             o3 = np.zeros(3)
             ok.ok_compute_ke_maxwell(C.byref(s.g), s.f.ravel(), 1.7, s.velocities, s.vz.ravel(), o3)
             assert np.array_equal(o3, gold["rhs%d_kem" % order])
+
+
+@needs_ref
+def test_fortran_abi_golden_file_is_current(ok, ref):
+    """tests/golden/f77abi_golden.npz (what the GPU tests compare the CUDA library with on the box) equals what
+    the transliterated reference Fortran returns today for the calls of tests/f77_cases.py"""
+    import f77_cases
+    gold = np.load(os.path.join(os.path.dirname(GOLD), "f77abi_golden.npz"))
+    B = f77_cases.HostBackend(ref.L, ref.L.loki_ref_set_ic)
+    n = 0
+    for order in (4, 6):
+        for k, v in f77_cases.kinetic_cases(B, ok, order).items():
+            assert np.array_equal(v, gold["k%d_%s" % (order, k)]), k
+            n += 1
+        for k, v in f77_cases.field_cases(B, order).items():
+            assert np.array_equal(v, gold["f%d_%s" % (order, k)]), k
+            n += 1
+    assert n == len(gold.files)
