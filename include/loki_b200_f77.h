@@ -8,9 +8,10 @@
  * argument lists, so the inline wrappers of KineticSpecies.H:404-562, Poisson.C and Maxwell.C link against it
  * unchanged (relink, not edit).  Differences a caller must know:
  *
- *   * every array argument is a DEVICE pointer (the first element of the array, as `*array.getData()` is
- *     in the reference); scalar and box arguments stay host references; scalar RESULTS (axmax, aymax,
- *     ke_e_dot, ke ...) are written to the host reference before the call returns (these calls synchronise);
+ *   * every ParallelArray argument is a DEVICE pointer (the first element of the array, as `*array.getData()`
+ *     is in the reference); scalars, boxes and the domain metadata arrays of PROBLEMDOMAIN_TO_FORT
+ *     (xlo, xhi, dx / deltax, supergrid_lo / hi; ProblemDomain.H:318-321) stay HOST references; scalar RESULTS
+ *     (axmax, aymax, ke_e_dot ...) are written to the host reference before the call returns (the calls synchronise);
  *   * `ic` (KineticSpecies.H:439: the initial-condition object laundered through an int64) must hold the
  *     address of an lk_inflow (loki_b200.h) describing the same initial condition as device tables: device
  *     code cannot call back into ICInterface.C:36-57;

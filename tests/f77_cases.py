@@ -26,6 +26,9 @@ class HostBackend:
         assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
         return a.ctypes.data_as(C.c_void_p)
 
+    def meta(self, a):
+        return a.ctypes.data_as(C.c_void_p)
+
     def i(self, v):
         return C.byref(C.c_int(int(v)))
 
@@ -63,6 +66,11 @@ class DeviceBackend:
         t = self.torch.from_numpy(a).cuda()
         self._dev.append((a, t))
         return C.c_void_p(t.data_ptr())
+
+    def meta(self, a):
+        """domain metadata (xlo, xhi, dx: PROBLEMDOMAIN_TO_FORT, ProblemDomain.H:318-321) stays on the host"""
+        self._keep.append(a)
+        return a.ctypes.data_as(C.c_void_p)
 
     def i(self, v):
         return C.byref(C.c_int(int(v)))
@@ -150,10 +158,10 @@ def kinetic_cases(B, ok, order):
     # derivatives: advection assigns, acceleration accumulates
     dxs = np.array(s.dx)
     rhs = np.zeros_like(s.f)
-    B.call("computeadvectionderivatives4d_", B.arr(rhs), B.arr(s.f), *db, *ib, B.arr(s.vel1), B.arr(s.vel2), B.arr(dxs), B.i(order))
+    B.call("computeadvectionderivatives4d_", B.arr(rhs), B.arr(s.f), *db, *ib, B.arr(s.vel1), B.arr(s.vel2), B.meta(dxs), B.i(order))
     B.finish()
     out["rhs_adv"] = rhs.copy()
-    B.call("computeaccelerationderivatives4d_", B.arr(rhs), B.arr(s.f), *db, *ib, B.arr(vel3), B.arr(vel4), B.arr(dxs), B.i(order))
+    B.call("computeaccelerationderivatives4d_", B.arr(rhs), B.arr(s.f), *db, *ib, B.arr(vel3), B.arr(vel4), B.meta(dxs), B.i(order))
     B.finish()
     out["rhs_full"] = rhs
     # currents
@@ -165,7 +173,7 @@ def kinetic_cases(B, ok, order):
     ext = np.ascontiguousarray(rng.uniform(-1, 1, size=(2, n2d, n1d)))
     k = C.c_double(0.0)
     xlo = np.zeros(4)
-    B.call("computekeedot_", *db, *ib, B.arr(xlo), B.arr(xlo), B.arr(dxs), B.arr(s.f), B.d(s.charge), B.arr(s.velocities), B.arr(ext),
+    B.call("computekeedot_", *db, *ib, B.meta(xlo), B.meta(xlo), B.meta(dxs), B.arr(s.f), B.d(s.charge), B.arr(s.velocities), B.arr(ext),
            C.byref(k))
     B.finish()
     out["ke_e_dot"] = np.array([k.value])
@@ -195,7 +203,7 @@ def field_cases(B, order):
     phi = np.ascontiguousarray(rng.uniform(-1, 1, size=(n2d, n1d)))
     dx = np.array([0.3, 0.7, 1.0, 1.0])
     e = np.zeros((2, n2d, n1d))
-    B.call("computeefieldfrompotential_", *db, *ib, B.i(order), B.i(2), B.arr(dx), B.arr(e), B.arr(phi))
+    B.call("computeefieldfrompotential_", *db, *ib, B.i(order), B.i(2), B.meta(dx), B.arr(e), B.arr(phi))
     B.finish()
     out["efield"] = e
     em = np.ascontiguousarray(rng.uniform(-1, 1, size=(6, n2d, n1d)))
@@ -204,8 +212,8 @@ def field_cases(B, order):
     sglo, sghi = xlo[:2].copy(), xhi[:2].copy()
     for tag, avw, avs in (("", 0.0, 0.0), ("_av", 0.1, 1.6 / 22.36)):
         m = np.zeros_like(em)
-        B.call("maxwellevalrhs_", *db, *ib, B.arr(xlo), B.arr(xhi), B.arr(dx), B.d(22.36), B.d(avw), B.d(avs), B.i(order),
-               B.arr(sglo), B.arr(sghi), B.arr(em), B.arr(J[0]), B.arr(J[1]), B.arr(J[2]), B.arr(m))
+        B.call("maxwellevalrhs_", *db, *ib, B.meta(xlo), B.meta(xhi), B.meta(dx), B.d(22.36), B.d(avw), B.d(avs), B.i(order),
+               B.meta(sglo), B.meta(sghi), B.arr(em), B.arr(J[0]), B.arr(J[1]), B.arr(J[2]), B.arr(m))
         B.finish()
         out["maxwell" + tag] = m
     dvz = np.zeros((n2d, n1d))

@@ -15,6 +15,15 @@ import ref_binding
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "f77abi_golden.npz")
+# computekeedot_ is ONE sequential sum over the whole 4D box (KineticSpeciesF.f:2590-2599); the device adds the same
+# terms in a fixed two-level tree, so the scalar agrees to the rounding of a sum of ~3000 terms of either sign (2e-12 relative), not bit for bit
+SUMS = {"ke_e_dot": 2e-12}
+
+
+def _same(name, got, want):
+    if name in SUMS:
+        return bool(np.all(np.abs(got - want) <= SUMS[name] * np.abs(want)))
+    return bool(np.array_equal(got, want))
 
 
 @pytest.mark.parametrize("order", [4, 6])
@@ -24,14 +33,14 @@ def test_fortran_abi_kinetic_routines_match_reference_bits(lk, ok, strict, order
     assert len(got) >= 17
     for name, val in got.items():
         want = gold["k%d_%s" % (order, name)]
-        assert np.array_equal(val, want), "%s (order %d) differs from the reference Fortran's output" % (name, order)
+        assert _same(name, val, want), "%s (order %d) differs from the reference Fortran's output" % (name, order)
     # the calls did something: boundary fills changed ghosts, the derivative is not zero
     assert np.any(got["accel_bcs"] != got["adv_bcs_00"]) and np.any(got["rhs_full"] != got["rhs_adv"])
     if ref_binding.available():
         R = ref_binding.Ref()
         live = f77_cases.kinetic_cases(f77_cases.HostBackend(R.L, R.L.loki_ref_set_ic), ok, order)
         for name, val in got.items():
-            assert np.array_equal(val, live[name]), name
+            assert _same(name, val, live[name]), name
 
 
 @pytest.mark.parametrize("order", [4, 6])
