@@ -18,6 +18,21 @@
 static inline double dmax(double a, double b) { return a > b ? a : b; }
 static inline double dmin(double a, double b) { return a < b ? a : b; }
 
+/* The heavy loop nests run on all host cores when built with -fopenmp (oracle/Makefile): only loops whose
+ * iterations write disjoint outputs are split, so every output element executes the reference's operation
+ * sequence and the results stay bit-identical to the serial run (tests/test_oracle_pin.py compares with the
+ * transliterated Fortran).  OMP_NUM_THREADS=1 gives the serial oracle (bench.py's per-core baseline). */
+#ifdef _OPENMP
+#define OK_PRAGMA(x) _Pragma(#x)
+#define OK_PARALLEL_FOR OK_PRAGMA(omp parallel for schedule(static))
+#define OK_PARALLEL_FOR2 OK_PRAGMA(omp parallel for collapse(2) schedule(static))
+#define OK_PARALLEL_FOR2_MAX(v) OK_PRAGMA(omp parallel for collapse(2) schedule(static) reduction(max : v))
+#else
+#define OK_PARALLEL_FOR
+#define OK_PARALLEL_FOR2
+#define OK_PARALLEL_FOR2_MAX(v)
+#endif
+
 /* ------------------------------------------------------------------------------------------
  * WENO43Fit4D  (KineticSpeciesF.f:723-790)
  * um2,um1,u0,up1 are f(i-1),f(i),f(i+1),f(i+2) for the face between i and i+1.
@@ -122,9 +137,22 @@ void ok_weno65_fit_v(const double* u6, const double* vel, double* face, int64_t 
                             u6[6 * k + 5], vel[k]);
 }
 
+double ok_ic_from_tables(void* ctx, int i1, int i2, int i3, int i4) {
+  const ok_ic_tables* t = (const ok_ic_tables*)ctx;
+  const int64_t pxy = i1 + (int64_t)t->n1d * i2, pv = i3 + (int64_t)t->n3d * i4;
+  switch (t->kind) {
+    case 1: return t->fnorm * t->fv[pv] * t->fx[pxy] * t->frac;
+    case 2: return t->fx[pxy] * t->fv[pv] + t->fx2[pxy] * t->fv2[pv];
+    case 4: return t->fv[pv] * t->fx[pxy] * t->fx2[pxy];
+    case 3: return t->full[pxy + (int64_t)t->n1d * t->n2d * pv];
+    default: return t->fv[pv] * t->fx[pxy];
+  }
+}
+
 /* xpby4d (KineticSpeciesF.f:10-38): x += b*y on the interior only */
 void ok_xpby4d(double* x, const double* y, double b, const ok_geom* g) {
   const int ng = g->ng;
+  OK_PARALLEL_FOR2
   for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
     for (int i3 = ng; i3 < ng + g->n[2]; ++i3)
       for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
@@ -153,6 +181,7 @@ void ok_set_phase_space_vel_4d(double* vel3, double* vel4, const ok_geom* g, con
   const int ng = g->ng;
   const int n1d = (int)ND(0), n2d = (int)ND(1), n3d = (int)ND(2), n4d = (int)ND(3);
   double axmax = 0.0;
+  OK_PARALLEL_FOR2_MAX(axmax)
   for (int i4 = 0; i4 < n4d; ++i4)
     for (int i3 = 0; i3 <= n3d; ++i3) {
       double vy = vxface_vel[(int64_t)i3 + (int64_t)(n3d + 1) * (i4 + (int64_t)n4d * 1)];
@@ -166,6 +195,7 @@ void ok_set_phase_space_vel_4d(double* vel3, double* vel4, const ok_geom* g, con
         }
     }
   double aymax = 0.0;
+  OK_PARALLEL_FOR2_MAX(aymax)
   for (int i3 = 0; i3 < n3d; ++i3)
     for (int i2 = 0; i2 < n2d; ++i2)
       for (int i1 = 0; i1 < n1d; ++i1)
@@ -191,6 +221,7 @@ void ok_set_phase_space_vel_maxwell_4d(double* vel3, double* vel4, const ok_geom
   const int64_t pl = (int64_t)n1d * n2d;
 #define EM(i1, i2, c) em_vars[(i1) + (int64_t)n1d * (i2) + pl * ((c)-1)]
   double axmax = 0.0;
+  OK_PARALLEL_FOR2_MAX(axmax)
   for (int i3 = 0; i3 <= n3d; ++i3)
     for (int i4 = 0; i4 < n4d; ++i4) {
       double vy = vxface_vel[(int64_t)i3 + (int64_t)(n3d + 1) * (i4 + (int64_t)n4d * 1)];
@@ -205,6 +236,7 @@ void ok_set_phase_space_vel_maxwell_4d(double* vel3, double* vel4, const ok_geom
         }
     }
   double aymax = 0.0;
+  OK_PARALLEL_FOR2_MAX(aymax)
   for (int i4 = 0; i4 <= n4d; ++i4)
     for (int i1 = 0; i1 < n1d; ++i1)
       for (int i2 = 0; i2 < n2d; ++i2)
@@ -301,6 +333,7 @@ void ok_advection_derivatives_4d(double* rhs, const double* f, const ok_geom* g,
   const int n1a = ng, n1b = ng + g->n[0] - 1, n2a = ng, n2b = ng + g->n[1] - 1;
   const int64_t s1 = 1, s2 = ND(0);
   const double dx = g->dx[0], dy = g->dx[1];
+  OK_PARALLEL_FOR2
   for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
     for (int i3 = ng; i3 < ng + g->n[2]; ++i3) {
       double vx = vel1[v1idx(g, n1a, n2a, i3, i4)];
@@ -333,6 +366,7 @@ void ok_acceleration_derivatives_4d(double* rhs, const double* f, const ok_geom*
   const int n3a = ng, n3b = ng + g->n[2] - 1, n4a = ng, n4b = ng + g->n[3] - 1;
   const int64_t s3 = ND(0) * ND(1), s4 = ND(0) * ND(1) * ND(2);
   const double dvx = g->dx[2], dvy = g->dx[3];
+  OK_PARALLEL_FOR2
   for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
     for (int i1 = ng; i1 < ng + g->n[0]; ++i1) {
       for (int i4 = n4a; i4 <= n4b; ++i4) {
@@ -399,9 +433,11 @@ void ok_reduce_4d_to_2d(double* dst, const double* src, const ok_geom* g, double
   const int ng = g->ng;
   const int64_t n1d = ND(0), n2d = ND(1);
   for (int64_t k = 0; k < n1d * n2d; ++k) dst[k] = 0.0;
-  for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
-    for (int i3 = ng; i3 < ng + g->n[2]; ++i3)
-      for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
+  /* every dst(i1,i2) is its own sequential sum, i3 inner / i4 outer: the threads split i2, the order stays */
+  OK_PARALLEL_FOR
+  for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
+    for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
+      for (int i3 = ng; i3 < ng + g->n[2]; ++i3)
         for (int i1 = ng; i1 < ng + g->n[0]; ++i1) dst[i1 + n1d * i2] += F4(src, i1, i2, i3, i4);
   /* ParallelArray::operator*= runs over the whole data box (ParallelArray.H:708-716) */
   for (int64_t k = 0; k < n1d * n2d; ++k) dst[k] *= dv;

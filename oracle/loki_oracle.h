@@ -43,6 +43,15 @@ static inline int64_t ok_idx(const ok_geom* g, int i1, int i2, int i3, int i4) {
 
 /* callback standing in for initialconditionatpoint_ (ICInterface.C:36-57); data-box indices */
 typedef double (*ok_ic_fn)(void* ctx, int i1, int i2, int i3, int i4);
+/* the IC classes' cached tables as a C point callback (what initialconditionatpoint_ evaluates, ICInterface.C:36-57):
+ * kind 1 fnorm*fv*fx*frac (PerturbedMaxwellianIC.C:279-281), 2 fx*fv + fx2*fv2 and 4 fv*fx*fx2
+ * (InterpenetratingStreamIC.C:275-281), 0 fv*fx, 3 the cached full array m_f (PerturbedMaxwellianIC.C:176-246) */
+typedef struct ok_ic_tables {
+  int kind, n1d, n2d, n3d, n4d;
+  const double *fx, *fv, *fx2, *fv2, *full;
+  double fnorm, frac;
+} ok_ic_tables;
+double ok_ic_from_tables(void* ctx, int i1, int i2, int i3, int i4);
 
 /* ---- KineticSpeciesF.f ---- */
 double ok_weno43_fit(double um2, double um1, double u0, double up1, double vel);

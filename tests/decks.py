@@ -5,11 +5,17 @@ import ctypes as C  # noqa: F401
 
 from loki_b200 import decks as _d
 from loki_b200.decks import Species, driver_params, PI  # noqa: F401
-from oracle_binding import OkGeom, OkSpecies, IC_FN
+import numpy as np
+
+from oracle_binding import OkGeom, OkSpecies, OkIcTables, IC_FN, load as _load_oracle
 
 
 class Deck(_d.Deck):
     # ---- oracle side ----
+    @staticmethod
+    def _ok_ic_fn():
+        return _load_oracle().ok_ic_from_tables
+
     def oracle_species(self, keep):
         arr = (OkSpecies * len(self.species))()
         for k, sp in enumerate(self.species):
@@ -18,35 +24,35 @@ class Deck(_d.Deck):
             arr[k].mass, arr[k].charge, arr[k].bz_const = sp.mass, sp.charge, sp.bz
             arr[k].vlo[0], arr[k].vlo[1] = sp.vlim[0], sp.vlim[2]
             arr[k].vhi[0], arr[k].vhi[1] = sp.vlim[1], sp.vlim[3]
+            # the IC as the C point callback of the oracle over the IC classes' cached tables (same products in the
+            # same order as the classes' getIC_At_Pt; a Python callback per ghost cell would dominate the run time)
+            t = OkIcTables()
+            nd = arr[k].g.nd
+            t.n1d, t.n2d, t.n3d, t.n4d = nd
+            tabs = []
             if sp.stream is not None:
                 fx, fx2, fv, fv2 = self.stream_tables(sp)
-                kind = self.inflow_kind(sp)
-                if kind == 2:      # InterpenetratingStreamIC.C:275-278
-                    def cb(ctx, i1, i2, i3, i4, fx=fx, fv=fv, fx2=fx2, fv2=fv2):
-                        return fx[i2, i1] * fv[i4, i3] + fx2[i2, i1] * fv2[i4, i3]
-                elif kind == 4:    # :279-281
-                    def cb(ctx, i1, i2, i3, i4, fx=fx, fv=fv, fx2=fx2):
-                        return fv[i4, i3] * fx[i2, i1] * fx2[i2, i1]
-                else:
-                    def cb(ctx, i1, i2, i3, i4, fx=fx, fv=fv):
-                        return fv[i4, i3] * fx[i2, i1]
-                fx = fv = None
+                t.kind = {2: 2, 4: 4}.get(self.inflow_kind(sp), 0)
+                tabs = [fx, fv, fx2, fv2]
+                t.fx, t.fv = fx.ctypes.data, fv.ctypes.data
+                if fx2 is not None:
+                    t.fx2 = fx2.ctypes.data
+                if fv2 is not None:
+                    t.fv2 = fv2.ctypes.data
             else:
                 fx, fv, fnorm = self.ic_tables(sp)
-            frac = sp.frac
-            if sp.stream is not None:
-                pass
-            elif sp.factorable:
-                def cb(ctx, i1, i2, i3, i4, fx=fx, fv=fv, fnorm=fnorm, frac=frac):
-                    return fnorm * fv[i4, i3] * fx[i2, i1] * frac
-            else:
-                fic = self.initial_state_full(sp, fx, fnorm)  # the cached m_f (PerturbedMaxwellianIC.C:176-246)
-
-                def cb(ctx, i1, i2, i3, i4, fic=fic):
-                    return fic[i4, i3, i2, i1]
-            fn = IC_FN(cb)
-            keep.append(fn)
-            arr[k].ic = fn
+                if sp.factorable:
+                    t.kind, t.fnorm, t.frac = 1, fnorm, sp.frac
+                    tabs = [fx, fv]
+                    t.fx, t.fv = fx.ctypes.data, fv.ctypes.data
+                else:
+                    fic = np.ascontiguousarray(self.initial_state_full(sp, fx, fnorm))  # the cached m_f (PerturbedMaxwellianIC.C:176-246)
+                    t.kind = 3
+                    tabs = [fic]
+                    t.full = fic.ctypes.data
+            keep.append((t, tabs))
+            arr[k].ic = C.cast(self._ok_ic_fn(), IC_FN)
+            arr[k].ic_ctx = C.addressof(t)
             arr[k].has_driver = 1 if sp.driver else 0
             if sp.driver:
                 for j in range(16):

@@ -31,6 +31,12 @@ class OkGeom(C.Structure):
         return tuple(self.n[k] + 2 * self.ng for k in range(4))
 
 
+class OkIcTables(C.Structure):
+    _fields_ = [("kind", C.c_int), ("n1d", C.c_int), ("n2d", C.c_int), ("n3d", C.c_int), ("n4d", C.c_int),
+                ("fx", C.c_void_p), ("fv", C.c_void_p), ("fx2", C.c_void_p), ("fv2", C.c_void_p), ("full", C.c_void_p),
+                ("fnorm", C.c_double), ("frac", C.c_double)]
+
+
 class OkSpecies(C.Structure):
     _fields_ = [("g", OkGeom), ("mass", C.c_double), ("charge", C.c_double), ("bz_const", C.c_double),
                 ("vlo", C.c_double * 2), ("vhi", C.c_double * 2), ("ic", IC_FN), ("ic_ctx", C.c_void_p),
