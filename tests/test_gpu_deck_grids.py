@@ -143,3 +143,10 @@ def test_em_damping_one_step_at_the_decks_own_grid(lk, ok, mode):
         ok.ok_vm_work_destroy(w)
     finally:
         lk.lk_set_strict(old)
+
+
+def test_em_damping_regression_run_at_the_decks_own_grid(lk, ok, fast):
+    """emDamping in full length (final_time = 10, about 300 RK4 steps) at 32 x 5 x 64 x 64"""
+    res = tvm._em_damping_full_run(ok, decks.em_damping())
+    _record(test="run", deck="emDamping", final_time=10.0, **res)
+    assert res["worst_trace"] <= 1e-10 and res["stencil_neighbourhood_max"] <= 1e-10

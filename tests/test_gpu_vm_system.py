@@ -242,13 +242,16 @@ def test_vm_deck_run_traces(lk, ok, fast):
 
 
 def test_full_regression_run_em_damping(lk, ok, fast):
+    _em_damping_full_run(ok, decks.em_damping(n=(32, 5), nv=(32, 32)))
+
+
+def _em_damping_full_run(ok, deck):
     """the emDamping regression run in full length (final_time = 10, save_times = 0.2, cfl = 0.8; about 210 RK4
     steps, limited by Maxwell::computeDt) on the deck's own configuration-space grid with a 32 x 32 velocity
     grid, production arithmetic on the device against the oracle: the time-history traces of the wave (|E|,
     Ey, |B|, Bz maxima, field energies, species kinetic energy) within 1e-10 in the norm of the run and 1e-9
     sample by sample; the distribution within 1e-10 per cell on the bulk at the end"""
     from loki_b200 import run
-    deck = decks.em_damping(n=(32, 5), nv=(32, 32))
     deck.run = dict(final_time=10.0, save_times=0.2, max_step=1000000)
     r = run.Runner(deck)
     w, sp, keep = _oracle(ok, deck)
@@ -299,5 +302,9 @@ def test_full_regression_run_em_damping(lk, ok, fast):
     big = f_old[0][I] >= 1e-6 * f_old[0][I].max()
     assert cell_rel_err(out[I][big], f_old[0][I][big]) <= 1e-10
     print("emDamping regression run: %d steps, worst trace difference %.2e" % (r.step, float(worst.max())))
+    res = dict(steps=r.step, worst_trace=float(worst.max()), per_cell_max_all_cells=cell_rel_err(out[I], f_old[0][I]),
+               per_cell_max_above_1e6_of_peak=cell_rel_err(out[I][big], f_old[0][I][big]),
+               stencil_neighbourhood_max=star_rel_err(out, f_old[0], f_old[0], ng))
     r.close()
     ok.ok_vm_work_destroy(w)
+    return res

@@ -30,7 +30,7 @@ def main(path, cells, per_step=8):
     rd = [to_bytes(*per[i]["dram__bytes_read.sum"]) for i in ids]
     wr = [to_bytes(*per[i]["dram__bytes_write.sum"]) for i in ids]
     tot = [a + b for a, b in zip(rd, wr)]
-    out = {"kernel": "k_stage_march", "cells_per_launch": cells, "launches_averaged": len(ids),
+    out = {"kernel": "k_stage_pipe (k_stage_march for the shapes it does not cover)", "cells_per_launch": cells, "launches_averaged": len(ids),
            "dram_bytes_per_launch": sum(tot) / len(tot), "dram_read_bytes_per_launch": sum(rd) / len(rd),
            "dram_write_bytes_per_launch": sum(wr) / len(wr), "dram_bytes_per_cell": sum(tot) / len(tot) / cells,
            "per_launch_bytes": tot,
