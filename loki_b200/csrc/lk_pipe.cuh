@@ -46,7 +46,7 @@ struct PipeCfg {
   static constexpr int NDI = OPW * T1 * T2;
   static constexpr int NBAR = NS + 2 + NW + 1 + 2;      // core slots, yh, vh, f_old per warp, delta_in, Q, P
   static constexpr int SMEM_DOUBLES = NS * NCORE + 2 * NYH + 2 * NVH + NACC + NDI;
-  static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES + 8 * NBAR + sizeof(double) * 3 * 2 * T2 + 16;
+  static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES + 8 * NBAR + sizeof(double) * 3 * 2 * T2 + 16;  // + counters, TMEM base
 };
 
 struct PipeMaps {
@@ -87,7 +87,16 @@ __device__ __forceinline__ void p_prefetch_l2(const CUtensorMap* map, int c0, in
 // so a bare retry loop would burn the issue slots (and the scheduler priority) the other warps of the SM
 // sub-partition need for their fp64 stream: the retry loop sleeps 64 ns between polls.  Watchdog: a hand-over
 // that never completes -- a protocol bug -- traps after 2^22 polls (~0.3 s) instead of hanging the device.
+#ifndef LK_PIPE_SLEEP_NS
+#define LK_PIPE_SLEEP_NS 64
+#endif
+#ifndef LK_PIPE_WATCHDOG
+#define LK_PIPE_WATCHDOG 1
+#endif
+#define LK_STR2(x) #x
+#define LK_STR(x) LK_STR2(x)
 __device__ __forceinline__ void p_wait(unsigned bar, unsigned parity) {
+#if LK_PIPE_WATCHDOG
   asm volatile(
       "{\n\t"
       ".reg .pred p, q;\n\t"
@@ -96,7 +105,7 @@ __device__ __forceinline__ void p_wait(unsigned bar, unsigned parity) {
       "@p bra LK_DONE;\n\t"
       "mov.u32 n, 0;\n\t"
       "LK_RETRY:\n\t"
-      "nanosleep.u32 64;\n\t"
+      "nanosleep.u32 " LK_STR(LK_PIPE_SLEEP_NS) ";\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra LK_DONE;\n\t"
       "add.u32 n, n, 1;\n\t"
@@ -106,6 +115,20 @@ __device__ __forceinline__ void p_wait(unsigned bar, unsigned parity) {
       "LK_DONE:\n\t"
       "}"
       ::"r"(bar), "r"(parity) : "memory");
+#else
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LK_DONE;\n\t"
+      "LK_RETRY:\n\t"
+      "nanosleep.u32 " LK_STR(LK_PIPE_SLEEP_NS) ";\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra LK_RETRY;\n\t"
+      "LK_DONE:\n\t"
+      "}"
+      ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 // one arrival per warp at a hand-over; true (for the whole warp) in the warp that arrived last: it then owns the
 // buffers the hand-over frees.  The count is relaxed; the last warp acquires the others' releases by
@@ -145,6 +168,47 @@ __device__ __forceinline__ bool elect_one() {
 __device__ long long g_pipe_trace[296 * 8 * 4 * 8];
 __device__ int g_pipe_smid[296];
 #endif
+// ---- tensor memory as a parking lot for loop-carried column state ----
+// The vy fit of a column carries 2*T2 doubles from plane to plane (the oldest ring plane and the face below, per
+// cell).  They are dead in every other phase of a plane, but as loop-carried registers they take 32 of the 128
+// registers a thread has at two CTAs per SM -- exactly what the compiler needs to interleave independent fits in
+// the x / y / vx sweeps (tools/fit_peak.cu: 89 % of the fp64 ceiling with that state live, 99 % without).  The SM's
+// 256 KB of tensor memory is otherwise unused by this kernel and its 32x32b access shape is "lane i of warp w owns
+// row 32 (w % 4) + i": a per-thread spill space.  One tcgen05.st after the vy fit, one tcgen05.ld before the next.
+#ifndef LK_PIPE_TMEM
+#define LK_PIPE_TMEM 0
+#endif
+// LK_PIPE_HWBAR = 1: the two hand-overs of a plane are hardware named barriers (bar.sync: a blocked warp costs no
+// issue slot) instead of split mbarrier arrive / wait pairs whose retry path polls; warp 0 issues the copies
+#ifndef LK_PIPE_HWBAR
+#define LK_PIPE_HWBAR 0
+#endif
+__device__ __forceinline__ void tmem_st16(unsigned taddr, const double (&v)[8]) {
+  unsigned r[16];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    r[2 * k] = (unsigned)__double2loint(v[k]);
+    r[2 * k + 1] = (unsigned)__double2hiint(v[k]);
+  }
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, double (&v)[8]) {
+  unsigned r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = __hiloint2double((int)r[2 * k + 1], (int)r[2 * k]);
+}
+
 // EK: 1 = RK4 stage 1 (delta = w rhs), 2 = stages 2,3 (delta += w rhs), 3 = stage 4 (pred = f_old + c (delta + w rhs))
 // NMOM: velocity moments of the new predictor left behind (0, 1: sum f, 3: + sum vx f, sum vy f)
 template <int ORDER, int EK, int NMOM>
@@ -230,7 +294,22 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
     asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(sb + O_CNT), "r"(0u));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+#if LK_PIPE_TMEM
+  static_assert(T2 == 8, "the parked state is two groups of 8 doubles per thread");
+  // 64 columns: (uold, Fprev) = 32 columns for warps 0-3 (lane quarters 0..3), 32 more for warps 4-7 on the same lanes
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sb + O_CNT + 8u), "r"(64u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#endif
   __syncthreads();
+#if LK_PIPE_TMEM
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  unsigned tm_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tm_base) : "r"(sb + O_CNT + 8u));
+  const unsigned tm_u = tm_base + ((32u * (warp & 3)) << 16) + 32u * (warp >> 2);  // uold: 16 columns, Fprev: the next 16
+#endif
 
   // ---- this thread's (x,y) column for the vx sweep, the vy fit and the epilogue: (lane, warp) ----
   const i64 col = (i64)(o0 + lane + NG) + g.s[1] * (o1 + warp + NG) + g.s[2] * (o2 + NG);  // + s2*c + s3*p
@@ -253,7 +332,7 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
     issue_halos(q0 + NG);
     p_prefetch_l2(&maps.fot, o0 + C::OPX, o1 + NG, o2 + NG, q0 + NG);
   }
-  double uold[T2], Fprev[T2];
+  double uold[T2], Fprev[T2];  // with LK_PIPE_TMEM: the prologue's copy only (parked below, shadowed in the vy phase)
 #pragma unroll
   for (int c = 0; c < T2; ++c) uold[c] = f[col + g.s[2] * c + g.s[3] * (pbase - 1)];
   // velocities of the slices: threads 0..2*T2-1 fetch them a plane ahead; running pointer, one plane per step
@@ -278,6 +357,11 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
   }
 #pragma unroll
   for (int c = 0; c < T2; ++c) uold[c] = lds(sb + O_CORE + 8u * (c * T1 * PC) + t_col);  // plane pbase
+#if LK_PIPE_TMEM
+  tmem_st16(tm_u, uold);
+  tmem_st16(tm_u + 16u, Fprev);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#endif
   __syncthreads();
   if (tid == 0) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -346,7 +430,20 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
     }
     // ---------------- B: the accumulator is free once every column of the previous plane has its operands ----
     LK_TR(1);
+#if LK_PIPE_HWBAR
+    if (q > q0) {
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (warp == 0 && elect_one()) {   // everything plane p-1 was staged in is free
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        int sf = sc + NG;             // the slot the previous plane's oldest ring plane lived in
+        if (sf >= NS) sf -= NS;
+        issue_core(p + NG, sf, EK >= 2, p);
+        p_prefetch_l2(&maps.fot, o0 + C::OPX, o1 + NG, o2 + NG, p);
+      }
+    }
+#else
     if (q > q0) p_wait(sb + B_P, pp ^ 1u);
+#endif
     LK_TR(2);
     if (more && tid < 2 * T2) sts(sb + O_VEL + vbn + 8u * tid, vel_next);
 #pragma unroll
@@ -393,9 +490,11 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
       for (int k = 0; k < NG; ++k) v[NG + T2 + k] = lds(sb + O_VH + 8u * C::NVH + t_col + 8u * (k * T1 * PC));
       __syncwarp();
       LK_TR(3);
+#if !LK_PIPE_HWBAR
       if (p_handover(sb + B_Q, sb + O_CNT, pp, NW, lane) && more) {
         if (elect_one()) issue_halos(p + 1);
       }
+#endif
 
       // ---------------- D: vx fits of this thread's column (lane, warp), all c ----------------
       Walker<ORDER> wk;
@@ -410,7 +509,15 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
     }
     // ---------------- E: add the x+y accumulator, hand its rows over to the f_old tile ----------------
     LK_TR(4);
+#if LK_PIPE_HWBAR
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (more && warp == 0 && elect_one()) {   // every warp has its vx line in registers and its y sweep stored
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue_halos(p + 1);
+    }
+#else
     p_wait(sb + B_Q, pp);
+#endif
     LK_TR(5);
 #pragma unroll
     for (int c = 0; c < T2; ++c) res[c] = FMA(-kax, res[c], lds(sb + t_ca + 8u * (c * 32)));
@@ -427,6 +534,11 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
       if (sn >= NS) sn -= NS;
       p_wait(sb + B_CORE + 8u * sn, (phc >> sn) & 1u);  // plane p+NG
       phc ^= 1u << sn;
+#if LK_PIPE_TMEM
+      double uold[T2], Fprev[T2];
+      tmem_ld16(tm_u, uold);
+      tmem_ld16(tm_u + 16u, Fprev);
+#endif
       unsigned wp[W];
 #pragma unroll
       for (int k = 1; k < W; ++k) {  // planes p-NG+2 .. p+NG
@@ -446,6 +558,13 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
         Fprev[c] = F;
         uold[c] = w[1];
       }
+#if LK_PIPE_TMEM
+      if (more) {
+        tmem_st16(tm_u, uold);
+        tmem_st16(tm_u + 16u, Fprev);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+#endif
     }
 
     // ---------------- G/H: RK stage update straight to global memory, moments of the new predictor ----------
@@ -471,6 +590,7 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
       }
       // every operand of this plane is in registers: hand the plane's buffers over
       __syncwarp();
+#if !LK_PIPE_HWBAR
       if (more) {
         if (p_handover(sb + B_P, sb + O_CNT + 4u, pp, NW, lane)) {
           if (elect_one()) {
@@ -482,6 +602,7 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
           }
         }
       }
+#endif
 #pragma unroll
       for (int c = 0; c < T2; ++c) stg(ptr_off(pr_p, s2, c), pr[c]);
       if (gxo) {
@@ -520,6 +641,11 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
     pp ^= 1u;
   }
 
+#if LK_PIPE_TMEM
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "r"(64u) : "memory");
+#endif
   if constexpr (NMOM > 0) {
     const i64 nxy = (i64)g.n[0] * g.n[1];
     const i64 part = (i64)chunk * nt2 + (o2 / T2);
