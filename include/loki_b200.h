@@ -83,6 +83,7 @@ typedef struct lk_inflow {
  *   pred      = ((f_old + c_prev[0]*k_prev[0]) + ... + c_prev[n_prev-1]*k_prev[n_prev-1]) + c_pred * rhs
  * i.e. the next stage's predictor (or the end-of-step sum with the b weights), added in the reference's
  * order.  n_prev = 0 for RK4. */
+struct lk_inflow;
 typedef struct lk_rk_update {
   const double* f_old;
   const double* delta_in; /* NULL in stage 1 (delta starts from zero) */
@@ -96,6 +97,15 @@ typedef struct lk_rk_update {
   int wrap;               /* bit 0 / bit 1: also write pred's periodic ghost cells in x / y (the copies
                              communicatePeriodicBoundaries would make, ParallelArray.H:580-606), so that the
                              next stage needs no separate wrap pass; needs n >= 2*ng in that direction */
+  const struct lk_inflow* accel_bcs; /* non-NULL: the stage also does setaccelerationbcs4d_ (KineticSpecies.H:421-453) for
+                             the evaluated state f -- all four velocity boundaries on this device, this inflow description,
+                             the stage's own acceleration */
+  int inflow_preset;      /* with accel_bcs.  1: the caller guarantees that f's velocity ghost layers hold the inflow sample
+                             (lk_preset_inflow_ghosts_4d).  The pipelined kernel then folds the fill into its boundary tiles:
+                             ghosts facing an outflow are extrapolated in shared memory, f's ghost layers are neither
+                             rewritten nor invalidated (lk_vlasov_stage_folds_bcs tells whether a given call does this).
+                             0, or a call the pipelined kernel does not take: lk_set_acceleration_bcs_4d runs on f first and
+                             WRITES f's velocity ghosts (f is then no longer preset) */
 } lk_rk_update;
 
 /* ---- library ---- */
@@ -130,6 +140,12 @@ int lk_set_phase_space_vel_4d(double* vel3, double* vel4, const lk_geom* g, cons
  * at_[0..3] = box touches global vx-low, vx-high, vy-low, vy-high boundary */
 int lk_set_acceleration_bcs_4d(double* f, const lk_geom* g, const lk_accel* a, const lk_inflow* ic,
                                const int at[4], void* stream);
+
+/* The inflow half of a6, once: every velocity ghost cell of f := the inflow sample of `ic` at that cell (what
+ * setaccelerationbcs4d_ stores where the acceleration points inward, KineticSpeciesF.f:1087-1112, 1132-1159; it
+ * depends on the position only).  An array prepared this way can be handed to lk_vlasov_stage with
+ * lk_rk_update.inflow_preset = 1. */
+int lk_preset_inflow_ghosts_4d(double* f, const lk_geom* g, const lk_inflow* ic, void* stream);
 
 /* ---- a14: periodic wrap of x then y ghosts on one device (ParallelArray.H:580-606) ---- */
 int lk_periodic_fill_4d(double* f, const lk_geom* g, int periodic_x, int periodic_y, void* stream);
@@ -183,6 +199,9 @@ typedef struct lk_stage_moments {
 int lk_stage_moment_parts(const lk_geom* g);
 int lk_vlasov_stage(double* rhs_out, const double* f, const lk_geom* g, const double* velocities,
                     const lk_accel* a, const lk_rk_update* upd, const lk_stage_moments* mom, void* stream);
+/* 1 when lk_vlasov_stage(rhs_out, ., g, ., a, upd, ...) would fold upd->accel_bcs into the pipelined kernel (f's velocity
+ * ghosts stay as they are), 0 when it would run lk_set_acceleration_bcs_4d on f first */
+int lk_vlasov_stage_folds_bcs(const double* rhs_out, const lk_geom* g, const lk_accel* a, const lk_rk_update* upd);
 /* dst_m(n1d,n2d) = (sum of partials of moment m) * dv * weight, ghosts zeroed (ReductionSchedule.C:86-89) */
 int lk_moments_finish(double* dst0, double* dst1, double* dst2, const lk_stage_moments* mom, const lk_geom* g,
                       double dv, double weight, void* stream);

@@ -44,7 +44,7 @@ class RkUpdate(C.Structure):
     _fields_ = [("f_old", C.c_void_p), ("delta_in", C.c_void_p), ("delta_out", C.c_void_p),
                 ("pred", C.c_void_p), ("w_delta", C.c_double), ("c_pred", C.c_double),
                 ("use_delta", C.c_int), ("n_prev", C.c_int), ("k_prev", C.c_void_p * 7),
-                ("c_prev", C.c_double * 7), ("wrap", C.c_int)]
+                ("c_prev", C.c_double * 7), ("wrap", C.c_int), ("accel_bcs", C.c_void_p), ("inflow_preset", C.c_int)]
 
 
 class StageMoments(C.Structure):
@@ -70,6 +70,8 @@ _PROTOS = {
     "lk_set_phase_space_vel_4d": (C.c_int, [_vp, _vp, C.POINTER(Geom), C.POINTER(Accel), _vp, _vp]),
     "lk_set_acceleration_bcs_4d": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Accel), C.POINTER(Inflow),
                                              C.POINTER(C.c_int * 4), _vp]),
+    "lk_preset_inflow_ghosts_4d": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Inflow), _vp]),
+    "lk_vlasov_stage_folds_bcs": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Accel), C.POINTER(RkUpdate)]),
     "lk_periodic_fill_4d": (C.c_int, [_vp, C.POINTER(Geom), C.c_int, C.c_int, _vp]),
     "lk_set_acceleration_bcs_4d_jb": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Accel), C.POINTER(Inflow),
                                                 C.POINTER(C.c_int * 4), _vp]),

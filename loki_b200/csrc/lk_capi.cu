@@ -278,6 +278,18 @@ static int stage_impl(double* rhs_out, const double* f, const lk_geom* g, const 
     nmom = mom->nmom;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  // setaccelerationbcs4d_ on behalf of the caller: folded into the pipelined kernel's boundary tiles, or run here
+  lk_rk_update upd_local;
+  if (upd && upd->accel_bcs) {
+    if (!lk_vlasov_stage_folds_bcs(rhs_out, g, a, upd)) {
+      const int at[4] = {1, 1, 1, 1};
+      int s = lk_set_acceleration_bcs_4d(const_cast<double*>(f), g, a, upd->accel_bcs, at, stream);
+      if (s != LK_OK) return s;
+      upd_local = *upd;
+      upd_local.accel_bcs = nullptr;
+      upd = &upd_local;
+    }
+  }
   if (!g_prof) CHECK_LAUNCH(DISPATCH(vlasov_rhs)(rhs_out, f, g, velocities, a, upd, 3, g_variant, mpart, nmom, st), who);
   if (g_prof_used == g_prof_events.size()) {
     cudaEvent_t e0, e1;
@@ -294,6 +306,19 @@ static int stage_impl(double* rhs_out, const double* f, const lk_geom* g, const 
 int lk_vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const double* velocities, const lk_accel* a,
                   const lk_rk_update* upd, void* stream) {
   return stage_impl(rhs_out, f, g, velocities, a, upd, nullptr, stream, "lk_vlasov_rhs");
+}
+int lk_vlasov_stage_folds_bcs(const double* rhs_out, const lk_geom* g, const lk_accel* a, const lk_rk_update* upd) {
+  if (!g || !a || !upd || !upd->accel_bcs || g_strict) return 0;
+  return lkfast::stage_folds_bcs(g, a, upd, const_cast<double*>(rhs_out), 3, g_variant) ? 1 : 0;
+}
+int lk_preset_inflow_ghosts_4d(double* f, const lk_geom* g, const lk_inflow* ic, void* stream) {
+  if (!geom_ok(g) || !f || !ic) return fail(LK_ERR_ARG, "lk_preset_inflow_ghosts_4d: bad argument");
+  if (ic->kind < 0 || ic->kind > 4) return fail(LK_ERR_ARG, "lk_preset_inflow_ghosts_4d: bad inflow kind");
+  if ((ic->kind == 1 || ic->kind == 2 || ic->kind == 4) && (!ic->fx || !ic->fv)) return fail(LK_ERR_ARG, "lk_preset_inflow_ghosts_4d: missing inflow tables");
+  if ((ic->kind == 2 || ic->kind == 4) && !ic->fx2) return fail(LK_ERR_ARG, "lk_preset_inflow_ghosts_4d: missing second inflow term");
+  if (ic->kind == 2 && !ic->fv2) return fail(LK_ERR_ARG, "lk_preset_inflow_ghosts_4d: missing second inflow term");
+  if (ic->kind == 3 && (!ic->ghost3 || !ic->ghost4)) return fail(LK_ERR_ARG, "lk_preset_inflow_ghosts_4d: missing ghost tables");
+  CHECK_LAUNCH(DISPATCH(preset_inflow)(f, g, ic, (cudaStream_t)stream), "lk_preset_inflow_ghosts_4d");
 }
 int lk_vlasov_stage(double* rhs_out, const double* f, const lk_geom* g, const double* velocities, const lk_accel* a,
                     const lk_rk_update* upd, const lk_stage_moments* mom, void* stream) {

@@ -99,6 +99,45 @@ __device__ __forceinline__ double accel_y(const DAccel& a, const DGeo& g, int i1
 }
 
 // ---------------------------------------------------------------------------------------------
+// velocity-boundary fill (setAccelerationBCs4D, KineticSpeciesF.f:1036-1162): the outflow extrapolation
+// u_g = 3 u_-1 - 3 u_-2 + u_-3 in the reference's evaluation order ((3a - 3b) + c, every product and sum rounded:
+// the same bits from the stand-alone kernel and from the fused stage kernel, strict or not), and the inflow
+// value from the IC classes' cached tables (replaces the initialconditionatpoint_ callback, ICInterface.C:36-57)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double bc_extrap(double a, double b, double c) {
+  return ADD(ADD(MUL(3.0, a), -MUL(3.0, b)), c);
+}
+struct DInflow {
+  int kind;
+  const double *fx, *fv, *fx2, *fv2, *ghost3, *ghost4;
+  double fnorm, frac;
+};
+__device__ __forceinline__ double inflow_value(const DInflow& ic, const DGeo& g, int i1, int i2, int i3, int i4,
+                                               int dir) {
+  const i64 pxy = i1 + (i64)g.nd[0] * i2;
+  const i64 pv = i3 + (i64)g.nd[2] * i4;
+  switch (ic.kind) {
+    case 1:  // PerturbedMaxwellianIC.C:279-281
+      return ic.fnorm * ic.fv[pv] * ic.fx[pxy] * ic.frac;
+    case 2:  // InterpenetratingStreamIC.C:275-278, two-sided
+      return ADD(MUL(ic.fx[pxy], ic.fv[pv]), MUL(ic.fx2[pxy], ic.fv2[pv]));
+    case 4:  // InterpenetratingStreamIC.C:279-281, centred: fv*fx*fx2 in this order
+      return ic.fv[pv] * ic.fx[pxy] * ic.fx2[pxy];
+    case 3: {
+      if (dir == 3) {
+        int layer = (i3 < g.ng) ? i3 : (i3 - g.n[2]);  // [0,ng) below, [ng,2ng) above
+        return ic.ghost3[pxy + (i64)g.nd[0] * g.nd[1] * (layer + (i64)2 * g.ng * i4)];
+      } else {
+        int layer = (i4 < g.ng) ? i4 : (i4 - g.n[3]);
+        return ic.ghost4[pxy + (i64)g.nd[0] * g.nd[1] * (i3 + (i64)g.nd[2] * layer)];
+      }
+    }
+    default:
+      return 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // reciprocal for the production path: MUFU.RCP64H seed (relative error e <= 2^-20) refined by one
 // cubic (Halley) step r0*(1 + e + e^2), error e^3 -- below the fp64 rounding unit.  Inputs are sums of
 // positive smoothness products, far from 0/inf/denormal.

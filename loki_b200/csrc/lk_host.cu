@@ -207,6 +207,11 @@ struct KineticSpecies {
   double lambda_max[4] = {0, 0, 0, 0};
 
   double* state() { return farr[i_state].p; }
+  // which of the rotating arrays currently hold the inflow sample in their velocity ghost layers
+  // (lk_rk_update.inflow_preset: the pipelined stage kernel then needs no separate velocity-boundary fill)
+  bool preset[3] = {false, false, false};
+  int arrayIndex(const double* p) const { return (p == farr[0].p) ? 0 : ((p == farr[1].p) ? 1 : 2); }
+  void forgetPresets() { preset[0] = preset[1] = preset[2] = false; }
 
   lk_accel accelDesc() {
     lk_accel a;
@@ -300,6 +305,7 @@ struct KineticSpecies {
 
   // setAccelerationBCs (KineticSpecies.H:421-453): velocity space is whole on every rank
   int setAccelerationBCs(double* f, void* st) {
+    preset[arrayIndex(f)] = false;
     lk_accel a = accelDesc();
     const int at[4] = {1, 1, 1, 1};
     return lk_set_acceleration_bcs_4d(f, &g, &a, &inflow, at, st);
@@ -497,11 +503,13 @@ struct VPSystem {
       if (only && ks != only) continue;
       // (4) acceleration; the maxima are only consumed by the next stableDt -> last stage
       LKH_CHECK(ks->computeAcceleration(em_local.p, t_stage, desc.xlo, desc.tile_lo, stage == last, st));
-      // (5) velocity-boundary fill, then advection + acceleration derivatives + RK update in one pass
-      LKH_CHECK(ks->setAccelerationBCs(ks->f_eval, st));
+      // (5) velocity-boundary fill + advection + acceleration derivatives + RK update in one pass: the stage does
+      // setAccelerationBCs itself (folded into the pipelined kernel's boundary tiles, or a separate fill first)
       lk_accel a = ks->accelDesc();
       lk_rk_update u;
       memset(&u, 0, sizeof(u));
+      u.accel_bcs = &ks->inflow;
+      u.inflow_preset = 1;
       double* pred = (ks->f_eval == ks->farr[ks->i_a].p) ? ks->farr[ks->i_b].p : ks->farr[ks->i_a].p;
       u.f_old = ks->state();
       u.pred = pred;
@@ -545,6 +553,16 @@ struct VPSystem {
       }
       // production: the kernel also writes pred's periodic ghost copies in the directions this rank wraps itself
       u.wrap = fused_moments ? ks->wrapFor(uncutDirs()) : 0;
+      {
+        const int ie = ks->arrayIndex(ks->f_eval);
+        if (lk_vlasov_stage_folds_bcs(rhs_out, &ks->g, &a, &u)) {
+          if (!ks->preset[ie]) LKH_CHECK(lk_preset_inflow_ghosts_4d(ks->f_eval, &ks->g, &ks->inflow, st));
+          ks->preset[ie] = true;
+        } else {
+          u.inflow_preset = 0;     // the stage runs the separate fill: f_eval's ghosts get the extrapolations as well
+          ks->preset[ie] = false;
+        }
+      }
       LKH_CHECK(lk_vlasov_stage(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, fused_moments ? &ks->mom : nullptr, st));
       ks->wrap_ptr = pred;
       ks->wrap_bits = u.wrap;
@@ -962,6 +980,7 @@ int lk_vp_set_state(lk_vp_system* h, int s, const double* f_host) {
   ks->f_eval = ks->state();
   ks->mom_valid = false;
   ks->wrap_ptr = nullptr;
+  ks->preset[ks->i_state] = false;
   return LK_OK;
 }
 int lk_vp_get_state(lk_vp_system* h, int s, double* f_host) {
@@ -985,6 +1004,7 @@ int lk_vp_set_inflow(lk_vp_system* h, int s, const double* fx, const double* fv,
   ks->inflow.fv = ks->ic_fv.p;
   ks->inflow.fnorm = fnorm;
   ks->inflow.frac = frac;
+  ks->forgetPresets();
   return LK_OK;
 }
 int lk_vp_set_inflow2(lk_vp_system* h, int s, int kind, const double* fx, const double* fv, const double* fx2,
@@ -1004,6 +1024,7 @@ int lk_vp_set_inflow2(lk_vp_system* h, int s, int kind, const double* fx, const 
   ks->inflow.fv = ks->ic_fv.p;
   ks->inflow.fx2 = ks->ic_fx2.p;
   ks->inflow.fv2 = (kind == 2) ? ks->ic_fv2.p : nullptr;
+  ks->forgetPresets();
   return LK_OK;
 }
 int lk_vp_set_time(lk_vp_system* h, double t) {

@@ -245,35 +245,6 @@ cudaError_t set_phase_space_vel(double* vel3, double* vel4, const lk_geom* g, co
 // (i1,i2,i4) of the data box; pass 1: vy boundaries, one thread per (i1,i2,i3) of the data box (it
 // reads the vx ghosts written by pass 0, as the reference's second loop nest does).
 // ---------------------------------------------------------------------------------------------
-struct DInflow {
-  int kind;
-  const double *fx, *fv, *fx2, *fv2, *ghost3, *ghost4;
-  double fnorm, frac;
-};
-__device__ __forceinline__ double inflow_value(const DInflow& ic, const DGeo& g, int i1, int i2, int i3, int i4,
-                                               int dir) {
-  const i64 pxy = i1 + (i64)g.nd[0] * i2;
-  const i64 pv = i3 + (i64)g.nd[2] * i4;
-  switch (ic.kind) {
-    case 1:  // PerturbedMaxwellianIC.C:279-281
-      return ic.fnorm * ic.fv[pv] * ic.fx[pxy] * ic.frac;
-    case 2:  // InterpenetratingStreamIC.C:275-278, two-sided
-      return ic.fx[pxy] * ic.fv[pv] + ic.fx2[pxy] * ic.fv2[pv];
-    case 4:  // InterpenetratingStreamIC.C:279-281, centred: fv*fx*fx2 in this order
-      return ic.fv[pv] * ic.fx[pxy] * ic.fx2[pxy];
-    case 3: {
-      if (dir == 3) {
-        int layer = (i3 < g.ng) ? i3 : (i3 - g.n[2]);  // [0,ng) below, [ng,2ng) above
-        return ic.ghost3[pxy + (i64)g.nd[0] * g.nd[1] * (layer + (i64)2 * g.ng * i4)];
-      } else {
-        int layer = (i4 < g.ng) ? i4 : (i4 - g.n[3]);
-        return ic.ghost4[pxy + (i64)g.nd[0] * g.nd[1] * (i3 + (i64)g.nd[2] * layer)];
-      }
-    }
-    default:
-      return 0.0;
-  }
-}
 __global__ void k_accel_bcs(DGeo g, DAccel a, DInflow ic, double* __restrict__ u, int pass, int at_lo, int at_hi) {
   const int ng = g.ng;
   const int nother = (pass == 0) ? g.nd[3] : g.nd[2];
@@ -290,7 +261,7 @@ __global__ void k_accel_bcs(DGeo g, DAccel a, DInflow ic, double* __restrict__ u
     if (at_hi) {
       if (accel_x(a, g, i1, i2, n3b + 1, i4) >= 0.0) {
         double* p = u + gidx(g, i1, i2, n3b, i4);
-        for (int ig = 1; ig <= ng; ++ig) p[ig * s] = 3.0 * p[(ig - 1) * s] - 3.0 * p[(ig - 2) * s] + p[(ig - 3) * s];
+        for (int ig = 1; ig <= ng; ++ig) p[ig * s] = bc_extrap(p[(ig - 1) * s], p[(ig - 2) * s], p[(ig - 3) * s]);
       } else {
         for (int ig = 1; ig <= ng; ++ig) u[gidx(g, i1, i2, n3b + ig, i4)] = inflow_value(ic, g, i1, i2, n3b + ig, i4, 3);
       }
@@ -300,7 +271,7 @@ __global__ void k_accel_bcs(DGeo g, DAccel a, DInflow ic, double* __restrict__ u
         for (int ig = 1; ig <= ng; ++ig) u[gidx(g, i1, i2, n3a - ig, i4)] = inflow_value(ic, g, i1, i2, n3a - ig, i4, 3);
       } else {
         double* p = u + gidx(g, i1, i2, n3a, i4);
-        for (int ig = 1; ig <= ng; ++ig) p[-ig * s] = 3.0 * p[(1 - ig) * s] - 3.0 * p[(2 - ig) * s] + p[(3 - ig) * s];
+        for (int ig = 1; ig <= ng; ++ig) p[-ig * s] = bc_extrap(p[(1 - ig) * s], p[(2 - ig) * s], p[(3 - ig) * s]);
       }
     }
   } else {
@@ -309,7 +280,7 @@ __global__ void k_accel_bcs(DGeo g, DAccel a, DInflow ic, double* __restrict__ u
     if (at_hi) {
       if (accel_y(a, g, i1, i2, i3, n4b + 1) >= 0.0) {
         double* p = u + gidx(g, i1, i2, i3, n4b);
-        for (int ig = 1; ig <= ng; ++ig) p[ig * s] = 3.0 * p[(ig - 1) * s] - 3.0 * p[(ig - 2) * s] + p[(ig - 3) * s];
+        for (int ig = 1; ig <= ng; ++ig) p[ig * s] = bc_extrap(p[(ig - 1) * s], p[(ig - 2) * s], p[(ig - 3) * s]);
       } else {
         for (int ig = 1; ig <= ng; ++ig) u[gidx(g, i1, i2, i3, n4b + ig)] = inflow_value(ic, g, i1, i2, i3, n4b + ig, 4);
       }
@@ -319,7 +290,7 @@ __global__ void k_accel_bcs(DGeo g, DAccel a, DInflow ic, double* __restrict__ u
         for (int ig = 1; ig <= ng; ++ig) u[gidx(g, i1, i2, i3, n4a - ig)] = inflow_value(ic, g, i1, i2, i3, n4a - ig, 4);
       } else {
         double* p = u + gidx(g, i1, i2, i3, n4a);
-        for (int ig = 1; ig <= ng; ++ig) p[-ig * s] = 3.0 * p[(1 - ig) * s] - 3.0 * p[(2 - ig) * s] + p[(3 - ig) * s];
+        for (int ig = 1; ig <= ng; ++ig) p[-ig * s] = bc_extrap(p[(1 - ig) * s], p[(2 - ig) * s], p[(3 - ig) * s]);
       }
     }
   }
@@ -344,6 +315,50 @@ cudaError_t set_accel_bcs(double* f, const lk_geom* g, const lk_accel* a, const 
     k_accel_bcs<<<nblk(total, 128), 128, 0, st>>>(d, da, di, f, 1, at[2], at[3]);
     ++g_launches;
   }
+  return cudaGetLastError();
+}
+
+// The inflow sample in EVERY velocity ghost cell of the data box (the value setAccelerationBCs4D gives a ghost whose
+// face has the acceleration pointing inward; it depends on the position only).  The pipelined stage kernel relies on
+// it (lk_rk_update.inflow_preset): it extrapolates the outflow ghosts on the fly and leaves memory alone.
+__global__ void k_preset_inflow(DGeo g, DInflow ic, double* __restrict__ u) {
+  const int ng = g.ng;
+  const i64 nfull = (i64)2 * ng * g.nd[2];                 // the 2 ng whole vy ghost planes
+  const i64 nv = nfull + (i64)2 * ng * g.n[3];             // + 2 ng vx ghost cells of every interior vy plane
+  const i64 total = (i64)g.nd[0] * g.nd[1] * nv;
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+    const int i1 = (int)(t % g.nd[0]);
+    const i64 r = t / g.nd[0];
+    const int i2 = (int)(r % g.nd[1]);
+    const i64 j = r / g.nd[1];
+    int i3, i4, dir;
+    if (j < nfull) {
+      i3 = (int)(j % g.nd[2]);
+      const int l = (int)(j / g.nd[2]);
+      i4 = (l < ng) ? l : l - ng + ng + g.n[3];
+      dir = 4;
+      if (i3 < ng || i3 >= ng + g.n[2]) dir = 3;           // corner cells: never read by a stencil; any table will do
+    } else {
+      const i64 k = j - nfull;
+      const int l = (int)(k % (2 * ng));
+      i4 = ng + (int)(k / (2 * ng));
+      i3 = (l < ng) ? l : l - ng + ng + g.n[2];
+      dir = 3;
+    }
+    u[gidx(g, i1, i2, i3, i4)] = inflow_value(ic, g, i1, i2, i3, i4, dir);
+  }
+}
+cudaError_t preset_inflow(double* f, const lk_geom* g, const lk_inflow* ic, cudaStream_t st) {
+  DGeo d = make_geo(g);
+  DInflow di;
+  memset(&di, 0, sizeof(di));
+  if (ic) {
+    di.kind = ic->kind; di.fx = ic->fx; di.fv = ic->fv; di.fx2 = ic->fx2; di.fv2 = ic->fv2;
+    di.ghost3 = ic->ghost3; di.ghost4 = ic->ghost4; di.fnorm = ic->fnorm; di.frac = ic->frac;
+  }
+  const i64 total = (i64)d.nd[0] * d.nd[1] * ((i64)2 * d.ng * d.nd[2] + (i64)2 * d.ng * d.n[3]);
+  k_preset_inflow<<<(unsigned)min((i64)nblk(total, 256), (i64)148 * 32), 256, 0, st>>>(d, di, f);
+  ++g_launches;
   return cudaGetLastError();
 }
 
@@ -521,8 +536,10 @@ cudaError_t vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const
     static const bool no_pipe = getenv("LK_NO_PIPE") != nullptr;
     if (!no_pipe && variant == 0 && pipe_eligible(d, da, du, rhs_out, flags)) {
       bool used = false;
-      cudaError_t e = (d.order == 4) ? launch_pipe<4>(d, f, velocities, da, du, dm, st, &used)
-                                     : launch_pipe<6>(d, f, velocities, da, du, dm, st, &used);
+      // velocity-boundary fill folded into the boundary tiles: f's ghosts hold the inflow sample (k_preset_inflow)
+      const int bcfold = (LK_PIPE_FOLD && upd && upd->accel_bcs && upd->inflow_preset) ? 3 : 0;
+      cudaError_t e = (d.order == 4) ? launch_pipe<4>(d, f, velocities, da, du, dm, bcfold, st, &used)
+                                     : launch_pipe<6>(d, f, velocities, da, du, dm, bcfold, st, &used);
       if (used) {
         if (e == cudaSuccess) { ++g_launches; ++g_pipe_launches; }
         return e;
@@ -541,6 +558,19 @@ cudaError_t vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const
   return LK_LAUNCHED();
 }
 int stage_moment_parts(const lk_geom* g) { return march_moment_parts(make_geo(g)); }
+bool stage_folds_bcs(const lk_geom* g, const lk_accel* a, const lk_rk_update* upd, double* rhs_out, int flags, int variant) {
+#if LK_STRICT
+  (void)g; (void)a; (void)upd; (void)rhs_out; (void)flags; (void)variant;
+  return false;
+#else
+  static const bool no_pipe = getenv("LK_NO_PIPE") != nullptr;
+  if (no_pipe || variant != 0 || !a || !upd || !upd->inflow_preset) return false;
+  DGeo d = make_geo(g);
+  // the TMA path needs a 16-byte aligned array base and an even row length (get_map); every cudaMalloc'ed array has them
+  // ... and the extrapolations of the two ends of the march must not feed each other
+  return LK_PIPE_FOLD && pipe_eligible(d, make_accel(a), make_upd(upd), rhs_out, flags) && (d.nd[0] % 2 == 0) && d.n[3] >= 2 * d.ng;
+#endif
+}
 #if defined(LK_PIPE_TRACE) && !LK_STRICT
 extern "C" int lk_debug_pipe_trace(long long* stamps, int* smid) {
   if (cudaMemcpyFromSymbol(stamps, g_pipe_trace, sizeof(long long) * 296 * 8 * 4 * 8) != cudaSuccess) return 1;

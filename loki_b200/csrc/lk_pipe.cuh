@@ -209,6 +209,10 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, double (&v)[8]) {
   for (int k = 0; k < 8; ++k) v[k] = __hiloint2double((int)r[2 * k + 1], (int)r[2 * k]);
 }
 
+#ifndef LK_PIPE_FOLD
+#define LK_PIPE_FOLD 1
+#endif
+
 // EK: 1 = RK4 stage 1 (delta = w rhs), 2 = stages 2,3 (delta += w rhs), 3 = stage 4 (pred = f_old + c (delta + w rhs))
 // NMOM: velocity moments of the new predictor left behind (0, 1: sum f, 3: + sum vx f, sum vy f)
 template <int ORDER, int EK, int NMOM>
@@ -218,7 +222,7 @@ template <int ORDER, int EK, int NMOM>
 __global__ void __launch_bounds__(256, LK_PIPE_MINB)
 k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restrict__ vel,
              const double* __restrict__ afield, const DUpd upd, const int nt0, const int nt1, const int nt2,
-             const int gy, const int gv, const int chunk_len, const DMom mom,
+             const int gy, const int gv, const int chunk_len, const DMom mom, const int bcfold,
              const __grid_constant__ PipeMaps maps) {
   using C = PipeCfg<ORDER>;
   constexpr int T0 = C::T0, T1 = C::T1, T2 = C::T2, NW = C::NW, NG = C::NG, W = C::W, NS = C::NS, SX = C::SX, PC = C::PC;
@@ -345,11 +349,63 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
   const double kax = MUL(ax0, rdx2), kay = MUL(ay0, rdx3);
   for (int k = 0; k < NS; ++k) p_wait(sb + B_CORE + 8u * k, 0);
   unsigned phc = (1u << NS) - 1;  // phase parity of every core slot's next completion
+  // Folded velocity-boundary fill (setAccelerationBCs4D, KineticSpeciesF.f:1036-1162; bcfold bit 0: vx, bit 1: vy).
+  // The caller keeps the INFLOW sample of the initial condition in f's velocity ghost layers (it depends on the
+  // position only: lk_preset_inflow_ghosts_4d writes it once per array), so a ghost cell whose face has the
+  // acceleration pointing inward is already right when TMA brings it in.  Where it points outward the ghost is the
+  // extrapolation 3 u_-1 - 3 u_-2 + u_-3 marching outward (:1079-1096, :1124-1141): computed here by the thread that
+  // owns the column and written over the staged copy in shared memory -- never to global memory, so the preset
+  // survives.  Rolled loops: boundary tiles only, the march loop's code must stay small.
+#if LK_PIPE_FOLD
+  const bool fold_vx = (bcfold & 1) != 0, fold_vy = (bcfold & 2) != 0;
+#else
+  constexpr bool fold_vx = false, fold_vy = false;
+#endif
+  // the NG planes below the first interior vy plane: outflow if a_y <= 0 at the lower face (:1143)
+  const bool low_ghosts = fold_vy && q0 == 0 && !aypos;
+  if (low_ghosts) {
+#pragma unroll 1
+    for (int c = 0; c < T2; ++c) {
+      const unsigned cell = sb + O_CORE + 8u * (c * T1 * PC) + t_col;   // + slot*NCORE: plane 1 + slot
+      // interior planes NG, NG+1, NG+2 = ring slots NG-1, NG, NG+1 (the last one is not staged yet at order 4)
+      double u0 = lds(cell + 8u * C::NCORE * (NG - 1)), u1 = lds(cell + 8u * C::NCORE * NG);
+      double u2 = (NG + 1 < NS) ? lds(cell + 8u * C::NCORE * ((NG + 1 < NS) ? NG + 1 : 0))
+                                : f[col + g.s[2] * c + g.s[3] * (NG + 2)];
+#pragma unroll 1
+      for (int ig = 1; ig <= NG; ++ig) {   // ghost plane NG - ig
+        const double gv_ = bc_extrap(u0, u1, u2);
+        u2 = u1; u1 = u0; u0 = gv_;
+        // planes 1 .. NG-1 live in slots 0 .. NG-2; plane 0 (the first window's lowest) in this thread's accumulator cell
+        sts((ig < NG) ? (cell + 8u * C::NCORE * (NG - 1 - ig)) : (sb + t_ca + 8u * (c * 32)), gv_);
+      }
+    }
+  }
+  // a last chunk shorter than NG planes already holds planes above the last interior one in its first window (the
+  // march patches the newest plane of each later window, below): outflow if a_y >= 0 at the upper face (:1124)
+  // one register of loop-invariant flags for the march: bit 0 / 1: this tile extrapolates its vx-low / vx-high ghosts
+  // (bottom: inflow if a_x > 0 at the lower face, :1098; top: outflow if a_x >= 0 at the upper face, :1079), bit 2: its
+  // vy-high ghosts
+  const unsigned bcf = ((fold_vx && o2 == 0 && !axpos) ? 1u : 0u) | ((fold_vx && o2 + T2 == g.n[2] && ax0 >= 0.0) ? 2u : 0u) |
+                       ((fold_vy && ay0 >= 0.0) ? 4u : 0u);
+  if ((bcf & 4u) && pbase + NS - 1 > g.n[3] + NG - 1) {
+#pragma unroll 1
+    for (int c = 0; c < T2; ++c) {
+      const unsigned cell = sb + O_CORE + 8u * (c * T1 * PC) + t_col;
+#pragma unroll 1
+      for (int k = 0; k < NS; ++k) {
+        if (pbase + k <= g.n[3] + NG - 1) continue;
+        auto below = [&](int j) -> double {   // plane pbase + j: interior planes when they are not in the ring (n4 >= 2 NG)
+          return (j >= 0) ? lds(cell + 8u * C::NCORE * (j >= 0 ? j : 0)) : f[col + g.s[2] * c + g.s[3] * (pbase + j)];
+        };
+        sts(cell + 8u * C::NCORE * k, bc_extrap(below(k - 1), below(k - 2), below(k - 3)));
+      }
+    }
+  }
   {
 #pragma unroll
     for (int c = 0; c < T2; ++c) {
       double w[W];
-      w[0] = uold[c];
+      w[0] = low_ghosts ? lds(sb + t_ca + 8u * (c * 32)) : uold[c];
 #pragma unroll
       for (int k = 0; k < NS; ++k) w[k + 1] = lds(sb + O_CORE + 8u * (k * C::NCORE + c * T1 * PC) + t_col);
       Fprev[c] = fit_face<ORDER>(w, aypos);
@@ -480,6 +536,24 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
     // the vx line of this thread's column goes into registers BEFORE the hand-over, so that the hand-over frees
     // the vx halos as well as the y halos and both are re-armed a whole plane ahead of their use
     double res[T2];
+    // folded velocity-boundary fill in vx (KineticSpeciesF.f:1072-1113): the tiles at the two ends of the vx range
+    // overwrite the staged ghost cells of their outflow columns before the line is loaded
+    if (bcf & 3u) {
+      auto cell = [&](int k) -> unsigned {   // window position k = data index o2 + k along vx
+        return (k < NG) ? (sb + O_VH + t_col + 8u * (k * T1 * PC))
+                        : ((k < NG + T2) ? (cur + t_col + 8u * ((k - NG) * T1 * PC)) : (sb + O_VH + 8u * C::NVH + t_col + 8u * ((k - NG - T2) * T1 * PC)));
+      };
+#pragma unroll 1
+      for (int side = 0; side < 2; ++side) {
+        if (!(bcf & (1u << side))) continue;
+        const int k0 = (side == 0) ? NG : NG + T2 - 1, step = (side == 0) ? -1 : 1;   // the boundary cell, outward step
+#pragma unroll 1
+        for (int ig = 1; ig <= NG; ++ig) {
+          const int k = k0 + step * ig;
+          sts(cell(k), bc_extrap(lds(cell(k - step)), lds(cell(k - 2 * step)), lds(cell(k - 3 * step))));
+        }
+      }
+    }
     {
       double v[T2 + W];
 #pragma unroll
@@ -546,6 +620,18 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
         if (s < 0) s += NS;
         if (s >= NS) s -= NS;
         wp[k] = sb + O_CORE + 8u * C::NCORE * s + t_col;
+      }
+      // folded velocity-boundary fill above the last interior vy plane (KineticSpeciesF.f:1117-1140): the newest plane
+      // of the window is a ghost plane for the last NG planes of the march -- an outflow column extrapolates it from
+      // the three values below it and writes it over the ring's copy, where the next planes' windows read it
+      if ((bcf & 4u) && p >= g.n[3]) {
+#pragma unroll 1
+        for (int c = 0; c < T2; ++c) {
+          const unsigned o = 8u * (c * T1 * PC);
+          // the window's lowest plane left the ring a plane ago (order 4 only needs it): an interior plane, from memory
+          const double w3 = (W - 4 >= 1) ? lds(wp[(W - 4 >= 1) ? W - 4 : 1] + o) : __ldg(f + col + g.s[2] * c + g.s[3] * (p - NG + 1));
+          sts(wp[W - 1] + o, bc_extrap(lds(wp[W - 2] + o), lds(wp[W - 3] + o), w3));
+        }
       }
 #pragma unroll
       for (int c = 0; c < T2; ++c) {
@@ -672,7 +758,7 @@ static bool pipe_eligible(const DGeo& g, const DAccel& a, const DUpd& u, const d
 
 template <int ORDER>
 static cudaError_t launch_pipe(const DGeo& g, const double* f, const double* vel, const DAccel& a, const DUpd& u,
-                               const DMom& mom, cudaStream_t st, bool* used) {
+                               const DMom& mom, int bcfold, cudaStream_t st, bool* used) {
   using C = PipeCfg<ORDER>;
   *used = false;
   PipeMaps maps;
@@ -713,7 +799,7 @@ static cudaError_t launch_pipe(const DGeo& g, const double* f, const double* vel
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)ctas, C::NT, C::SMEM_BYTES, st>>>(g, f, vel, a.field, u, nt0, nt1, nt2, gy, gv, chunk_len, mom, maps);
+    kern<<<(unsigned)ctas, C::NT, C::SMEM_BYTES, st>>>(g, f, vel, a.field, u, nt0, nt1, nt2, gy, gv, chunk_len, mom, bcfold, maps);
     return cudaGetLastError();
   };
   *used = true;

@@ -16,7 +16,7 @@ def chk(lk, status, what):
     assert status == 0, "%s: %s" % (what, lk.lk_last_error().decode())
 
 
-def _stage(lk, d, s, stage, nmom, wrap, variant, seed=5):
+def _stage(lk, d, s, stage, nmom, wrap, variant, seed=5, bcs=None, f=None, preset=False):
     """one RK4-shaped fused stage; returns (pred, delta, moment partials, pipelined launches used)"""
     import torch
     import loki_b200 as lkm
@@ -30,6 +30,9 @@ def _stage(lk, d, s, stage, nmom, wrap, variant, seed=5):
     u.delta_out = None if stage == 4 else delta.data_ptr()
     u.w_delta, u.c_pred, u.use_delta = 0.0123, 0.05, int(stage == 4)
     u.wrap = wrap
+    if bcs is not None:
+        u.accel_bcs, u.inflow_preset = C.addressof(bcs), int(preset)
+    f = d.f if f is None else f
     m, part = None, None
     if nmom:
         parts = lk.lk_stage_moment_parts(C.byref(d.g))
@@ -38,7 +41,7 @@ def _stage(lk, d, s, stage, nmom, wrap, variant, seed=5):
         m.nmom, m.partial, m.capacity = nmom, part.data_ptr(), part.numel()
     old = lk.lk_set_rhs_variant(variant)
     before = lk.lk_pipe_launch_count()
-    chk(lk, lk.lk_vlasov_stage(None, d.f.data_ptr(), C.byref(d.g), d.velocities.data_ptr(), C.byref(d.accel), C.byref(u),
+    chk(lk, lk.lk_vlasov_stage(None, f.data_ptr(), C.byref(d.g), d.velocities.data_ptr(), C.byref(d.accel), C.byref(u),
                                C.byref(m) if m else None, None), "stage")
     torch.cuda.synchronize()
     used = lk.lk_pipe_launch_count() - before
@@ -119,3 +122,62 @@ def test_pipe_against_oracle(lk, ok, fast, n, order, stage):
     if stage != 4:
         gd = delta.cpu().numpy()
         assert star_rel_err(gd, dl, w * np.abs(rhs) + np.abs(delta0) + 1e-3 * scale, ng) <= 1e-12
+
+
+def _inflow(d, s, kind):
+    """the three table-driven inflow descriptions of lk_inflow (PerturbedMaxwellianIC / InterpenetratingStreamIC)"""
+    import loki_b200 as lkm
+    ic = lkm.Inflow()
+    rng = np.random.default_rng(77)
+    keep = [d.t(s.fx), d.t(s.fv), d.t(s.fx * rng.uniform(0.5, 1.5, size=s.fx.shape)), d.t(s.fv * rng.uniform(0.5, 1.5, size=s.fv.shape))]
+    ic.kind, ic.fx, ic.fv, ic.fnorm, ic.frac = kind, keep[0].data_ptr(), keep[1].data_ptr(), 0.7, 0.9
+    if kind in (2, 4):
+        ic.fx2 = keep[2].data_ptr()
+    if kind == 2:
+        ic.fv2 = keep[3].data_ptr()
+    return ic, keep
+
+
+@pytest.mark.parametrize("kind", [1, 2, 4])
+@pytest.mark.parametrize("stage", [1, 4])
+@pytest.mark.parametrize("n,order", [((32, 8, 8, 5), 4), ((64, 16, 16, 20), 4), ((32, 24, 40, 9), 4), ((32, 8, 8, 7), 6),
+                                     ((64, 16, 24, 18), 6), ((32, 8, 16, 17), 6)])
+def test_pipe_folds_the_velocity_boundary_fill(lk, ok, fast, n, order, stage, kind):
+    """lk_rk_update.accel_bcs + inflow_preset: the pipelined kernel does setaccelerationbcs4d_ (KineticSpeciesF.f:1036-1162)
+    inside its boundary tiles -- same bits as `lk_set_acceleration_bcs_4d, then the generic kernel` -- on an array whose
+    velocity ghosts hold the inflow sample, and leaves those ghosts alone.  The random acceleration has both signs, so
+    inflow and extrapolation are both taken on each of the four boundaries; the grids put the last chunk of the march
+    at 1 plane (9 = 8 + 1, 17 = 2 * 8 + 1: top ghosts already in the first window) and at a whole chunk."""
+    import torch
+    s = Setup(ok, n, order, rough=0.3)
+    d = Dev(lk, s)
+    ng = s.ng
+    chk(lk, lk.lk_periodic_fill_4d(d.f.data_ptr(), C.byref(d.g), 1, 1, None), "per")
+    ic, keep = _inflow(d, s, kind)
+    # reference: explicit fill, then the generic kernel
+    f_ref = d.f.clone()
+    at = (C.c_int * 4)(1, 1, 1, 1)
+    chk(lk, lk.lk_set_acceleration_bcs_4d(f_ref.data_ptr(), C.byref(d.g), C.byref(d.accel), C.byref(ic), C.byref(at), None), "bcs")
+    assert not torch.equal(f_ref, d.f)
+    pb, db, mb, used_b = _stage(lk, d, s, stage, 3, 3, 2, f=f_ref)
+    # folded: ghosts preset to the inflow sample
+    f_pre = d.f.clone()
+    chk(lk, lk.lk_preset_inflow_ghosts_4d(f_pre.data_ptr(), C.byref(d.g), C.byref(ic), None), "preset")
+    I = (slice(ng, -ng),) * 2
+    assert torch.equal(f_pre[I], d.f[I]) and not torch.equal(f_pre, d.f)
+    # the preset agrees with the explicit fill wherever that took the inflow branch: some ghost cells, not all
+    same = (f_pre == f_ref)
+    ghost = torch.ones_like(same)
+    ghost[I] = False
+    frac = same[ghost].double().mean().item()
+    assert 0.2 < frac < 0.9, frac
+    before = f_pre.clone()
+    pa, da, ma, used_a = _stage(lk, d, s, stage, 3, 3, 0, bcs=ic, f=f_pre, preset=True)
+    assert used_a == 1 and used_b == 0
+    assert torch.equal(pa, pb) and torch.equal(da, db) and torch.equal(ma, mb)
+    assert torch.equal(f_pre, before)
+    # without the preset promise, or on the generic kernel (variant 2), the stage runs the fill first: f's ghosts are written
+    for variant, preset in ((0, False), (2, True)):
+        f2 = d.f.clone()
+        pc, dc, mc, used_c = _stage(lk, d, s, stage, 3, 3, variant, bcs=ic, f=f2, preset=preset)
+        assert used_c == (1 if variant == 0 else 0) and torch.equal(pc, pb) and torch.equal(mc, mb) and torch.equal(f2, f_ref)

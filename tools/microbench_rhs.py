@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--strict", action="store_true")
     ap.add_argument("--mode", default="stage", choices=["stage", "rhs"])
+    ap.add_argument("--fold", action="store_true", help="hand the inflow over (lk_rk_update.accel_bcs): velocity-boundary fill inside the stage")
     a = ap.parse_args()
     lk = lkm.load()
     lk.lk_set_strict(int(a.strict))
@@ -58,9 +59,17 @@ def main():
     U.f_old, U.delta_in, U.delta_out, U.pred = f_old.data_ptr(), delta.data_ptr(), delta.data_ptr(), pred.data_ptr()
     U.w_delta, U.c_pred, U.use_delta = 1e-3, 5e-4, 0
     st = torch.cuda.current_stream().cuda_stream
+    if a.fold:
+        I = lkm.Inflow()
+        fxc, fvc = fx.contiguous(), fv.contiguous()
+        I.kind, I.fx, I.fv, I.fnorm, I.frac = 1, fxc.data_ptr(), fvc.data_ptr(), 1.0, 1.0
+        U.accel_bcs, U.inflow_preset = C.addressof(I), 1
+        assert lk.lk_preset_inflow_ghosts_4d(f.data_ptr(), C.byref(g), C.byref(I), st) == 0
 
     def run():
-        if a.mode == "stage":
+        if a.mode == "stage" and a.fold:
+            s = lk.lk_vlasov_stage(None, f.data_ptr(), C.byref(g), vel.data_ptr(), C.byref(A), C.byref(U), None, st)
+        elif a.mode == "stage":
             s = lk.lk_vlasov_rhs(None, f.data_ptr(), C.byref(g), vel.data_ptr(), C.byref(A), C.byref(U), st)
         else:
             s = lk.lk_vlasov_rhs(pred.data_ptr(), f.data_ptr(), C.byref(g), vel.data_ptr(), C.byref(A), None, st)
@@ -78,8 +87,8 @@ def main():
     times = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
     ms = sum(times) / len(times)
     bpc = 40 if a.mode == "stage" else 16
-    print("n=%s order=%d variant=%d strict=%d mode=%s: %.3f ms/launch, %.2f Gcell/s, %.1f GB/s algorithmic (%d B/cell)  [min %.3f median %.3f ms, %s]" % (
-        n, a.order, a.variant, int(a.strict), a.mode, ms, cells / ms / 1e6, cells * bpc / ms / 1e6, bpc, times[0],
+    print("n=%s order=%d variant=%d strict=%d mode=%s fold=%d: %.3f ms/launch, %.2f Gcell/s, %.1f GB/s algorithmic (%d B/cell)  [min %.3f median %.3f ms, %s]" % (
+        n, a.order, a.variant, int(a.strict), a.mode, int(a.fold), ms, cells / ms / 1e6, cells * bpc / ms / 1e6, bpc, times[0],
         times[len(times) // 2], os.path.basename(os.environ.get("LOKI_B200_LIB", "libloki_b200.so"))))
 
 
