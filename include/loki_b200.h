@@ -285,6 +285,35 @@ int64_t lk_launch_count(void);
 /* how many of those were the pipelined instantiation of the stage kernel (lk_pipe.cuh) */
 int64_t lk_pipe_launch_count(void);
 
+/* ---- f2: flux-form diagnostics (loki_b200/csrc/lk_flux.cu) ----
+ * The kinetic-energy flux through the eight phase-space boundaries that KineticSpecies::accumulateSequencesCommon
+ * (KineticSpecies.C:2052-2097) adds to the time histories.  Face values and fluxes carry the reference's bits in
+ * both arithmetic modes; boundary sums are deterministic trees (not the reference's sequential order).
+ *
+ * lk_face_fluxes_4d: WENO43Avg4D / WENO65Avg4D + computeFlux4D (KineticSpeciesF.f:630-720, 797-910, 2359-2396) for
+ * direction dir (0..3), as computeadvectionfluxes4d_ / computeaccelerationfluxes4d_ (:1838-1945, 2249-2355) call
+ * them.  vel, face, flux: the rotated face arrays of KineticSpecies.C:1569-1584, extents (nd[dir]+1, nd[dir+1],
+ * nd[dir+2], nd[dir+3]) with the direction numbers mod 4.  Entries outside the reference's loop ranges are left alone. */
+int lk_face_fluxes_4d(double* flux, double* face, const double* u, const lk_geom* g, const double* vel, int dir,
+                      void* stream);
+/* accumfluxdiv4d_ (KineticSpeciesF.f:985-1032): rhs = -div(flux) on the interior (the vy term over dvx, as there) */
+int lk_accum_flux_div_4d(double* rhs, const lk_geom* g, const double* flux1, const double* flux2, const double* flux3,
+                         const double* flux4, void* stream);
+/* computekeflux_ (:2734-2893) for a box that touches boundary (dir, side): out_dev[0] = mass * ddir * sum over the
+ * boundary face of 0.5 * flux * v^2; flux = the flux array of direction dir */
+int lk_ke_flux_from_fluxes(double* out_dev, const lk_geom* g, const double* flux, const double* velocities,
+                           const double* vxface_velocities, const double* vyface_velocities, int dir, int side,
+                           double mass, void* stream);
+/* computekevelspaceflux_ (:2897-2990), dir 2 or 3: ke_flux_xy (n1d,n2d) += the flux through that velocity boundary */
+int lk_ke_vel_space_flux(double* ke_flux_xy, const lk_geom* g, const double* flux, const double* vxface_velocities,
+                         const double* vyface_velocities, int dir, int side, double mass, void* stream);
+/* The product path: all eight boundary fluxes of f straight from f (one face fit per boundary cell, no face or flux
+ * arrays).  f needs valid x / y ghosts and velocity-boundary ghosts (lk_set_acceleration_bcs_4d with the same
+ * acceleration); out8_dev[2*dir+side]; at_boundary[2*dir+side] = this box touches that boundary of the domain
+ * (`n1a .eq. ng1a` ..., :2781-2793), 0 leaves a 0. */
+int lk_ke_flux_boundaries(double* out8_dev, const double* f, const lk_geom* g, const double* velocities, const lk_accel* a,
+                          double mass, const int at_boundary[8], void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,38 @@ void computekeedot_(const int* nd1a, const int* nd1b, const int* nd2a, const int
                     const int* n3a, const int* n3b, const int* n4a, const int* n4b, const double* xlo, const double* xhi,
                     const double* dx, const double* u, const double* charge, const double* velocities,
                     const double* ext_efield, double* ke_e_dot);
+/* KineticSpeciesF.H:273-291 (KineticSpeciesF.f:1838-1945): face fits and fluxes in x and y on the rotated face arrays */
+void computeadvectionfluxes4d_(double* flux1, double* flux2, const int* nd1a, const int* nd1b, const int* nd2a,
+                               const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b,
+                               const double* vel1, const double* vel2, double* face1, double* face2, const double* u,
+                               const double* dx, const int* solution_order);
+/* KineticSpeciesF.H:343-361 (KineticSpeciesF.f:2249-2355): the same in vx and vy */
+void computeaccelerationfluxes4d_(double* flux3, double* flux4, const int* nd1a, const int* nd1b, const int* nd2a,
+                                  const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b,
+                                  const double* vel3, const double* vel4, double* face3, double* face4, const double* u,
+                                  const double* dx, const int* solution_order);
+/* KineticSpeciesF.H:363-380 (KineticSpeciesF.f:985-1032) */
+void accumfluxdiv4d_(double* rhs, const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a,
+                     const int* nd3b, const int* nd4a, const int* nd4b, const int* n1a, const int* n1b, const int* n2a,
+                     const int* n2b, const int* n3a, const int* n3b, const int* n4a, const int* n4b, const double* fluxx1,
+                     const double* fluxx2, const double* fluxx3, const double* fluxx4, const double* deltax);
+/* KineticSpeciesF.H:554-591 (KineticSpeciesF.f:2734-2893); ng*: the domain box; ke_flux is a HOST scalar that must come in
+ * as 0 for a box that touches the boundary (the reference's callers zero it); summed as a tree, not sequentially */
+void computekeflux_(const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a, const int* nd3b,
+                    const int* nd4a, const int* nd4b, const int* n1a, const int* n1b, const int* n2a, const int* n2b,
+                    const int* n3a, const int* n3b, const int* n4a, const int* n4b, const int* ng1a, const int* ng1b,
+                    const int* ng2a, const int* ng2b, const int* ng3a, const int* ng3b, const int* ng4a, const int* ng4b,
+                    const double* dx, const double* face_flux1, const double* face_flux2, const double* face_flux3,
+                    const double* face_flux4, const double* velocities, const double* vxface_velocities,
+                    const double* vyface_velocities, const int* dir, const int* side, const double* mass, double* ke_flux);
+/* KineticSpeciesF.H:593-625 (KineticSpeciesF.f:2897-2990); ke_flux: device (n1d,n2d), accumulated into */
+void computekevelspaceflux_(const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a,
+                            const int* nd3b, const int* nd4a, const int* nd4b, const int* n1a, const int* n1b,
+                            const int* n2a, const int* n2b, const int* n3a, const int* n3b, const int* n4a, const int* n4b,
+                            const int* ng1a, const int* ng1b, const int* ng2a, const int* ng2b, const int* ng3a,
+                            const int* ng3b, const int* ng4a, const int* ng4b, const double* dx, const double* face_flux3,
+                            const double* face_flux4, double* ke_flux, const double* mass, const double* vxface_velocities,
+                            const double* vyface_velocities, const int* side, const int* dir);
 /* KineticSpeciesF.f:2995-3034 */
 void appendkrook_(const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a, const int* nd3b,
                   const int* nd4a, const int* nd4b, const int* n1a, const int* n1b, const int* n2a, const int* n2b,

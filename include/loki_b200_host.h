@@ -123,6 +123,13 @@ const double* lk_vp_rho_ptr(const lk_vp_system* sys);
  * *written receives the count.  Local to this rank: sums / maxima over ranks are the caller's
  * (Loki_Utilities::getSum / getMaxValue).  Synchronises. */
 int lk_vp_time_history(lk_vp_system* sys, double* out, int capacity, int* written);
+/* The flux histories of KineticSpecies::accumulateSequencesCommon (KineticSpecies.C:2052-2097): per species the
+ * kinetic-energy flux through the eight phase-space boundaries, out[8 s + 2 dir + side] (dir 0..3 = x, y, vx, vy; side
+ * 0 = low), 8 * nspecies values.  Uses the face accelerations of the last evalRHS, as the reference does; rewrites the
+ * state's ghost cells (periodic wrap in the directions this rank is not cut in, velocity-boundary fill).  A rank only
+ * sums the boundaries its tile touches: add over ranks (Loki_Utilities::getSum).  In a cut direction the caller
+ * exchanges the halos of lk_vp_state_ptr first.  Synchronises. */
+int lk_vp_flux_history(lk_vp_system* sys, double* out, int capacity, int* written);
 /* integrated_ke_e_dot of species s (KineticSpecies.C:282-284); synchronises */
 int lk_vp_ke_e_dot(lk_vp_system* sys, int s, double* value);
 

@@ -70,6 +70,11 @@ _PROTOS = {
     "lk_set_phase_space_vel_4d": (C.c_int, [_vp, _vp, C.POINTER(Geom), C.POINTER(Accel), _vp, _vp]),
     "lk_set_acceleration_bcs_4d": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Accel), C.POINTER(Inflow),
                                              C.POINTER(C.c_int * 4), _vp]),
+    "lk_face_fluxes_4d": (C.c_int, [_vp, _vp, _vp, C.POINTER(Geom), _vp, C.c_int, _vp]),
+    "lk_accum_flux_div_4d": (C.c_int, [_vp, C.POINTER(Geom), _vp, _vp, _vp, _vp, _vp]),
+    "lk_ke_flux_from_fluxes": (C.c_int, [_vp, C.POINTER(Geom), _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, _vp]),
+    "lk_ke_vel_space_flux": (C.c_int, [_vp, C.POINTER(Geom), _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, _vp]),
+    "lk_ke_flux_boundaries": (C.c_int, [_vp, _vp, C.POINTER(Geom), _vp, C.POINTER(Accel), C.c_double, C.POINTER(C.c_int * 8), _vp]),
     "lk_preset_inflow_ghosts_4d": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Inflow), _vp]),
     "lk_vlasov_stage_folds_bcs": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Accel), C.POINTER(RkUpdate)]),
     "lk_periodic_fill_4d": (C.c_int, [_vp, C.POINTER(Geom), C.c_int, C.c_int, _vp]),

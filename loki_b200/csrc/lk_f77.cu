@@ -279,6 +279,126 @@ void computekeedot_(const int* nd1a, const int* nd1b, const int* nd2a, const int
   check(lk_memcpy_d2h(ke_e_dot, out.p, sizeof(double)));
 }
 
+// geometry from the data box alone (the flux routines get no interior box): ghost width from solution_order
+static bool geom_from_data(const char* who, const int* const nd[8], int order, const double* dx, lk_geom* g) {
+  if (order != 4 && order != 6) {
+    fail(who, "solution_order must be 4 or 6");
+    return false;
+  }
+  g->order = order;
+  g->ng = (order == 4) ? 2 : 3;
+  for (int k = 0; k < 4; ++k) {
+    g->n[k] = *nd[2 * k + 1] - *nd[2 * k] + 1 - 2 * g->ng;
+    g->dx[k] = dx ? dx[k] : 1.0;
+    if (g->n[k] < 1) {
+      fail(who, "data box narrower than the ghost layers");
+      return false;
+    }
+  }
+  return true;
+}
+
+void computeadvectionfluxes4d_(double* flux1, double* flux2, const int* nd1a, const int* nd1b, const int* nd2a,
+                               const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b,
+                               const double* vel1, const double* vel2, double* face1, double* face2, const double* u,
+                               const double* dx, const int* solution_order) {
+  const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
+  lk_geom g;
+  if (!geom_from_data("computeadvectionfluxes4d_", nd, *solution_order, dx, &g)) return;
+  if (!check(lk_face_fluxes_4d(flux1, face1, u, &g, vel1, 0, nullptr))) return;
+  if (!check(lk_face_fluxes_4d(flux2, face2, u, &g, vel2, 1, nullptr))) return;
+  check(cudaDeviceSynchronize() == cudaSuccess ? LK_OK : LK_ERR_CUDA);
+}
+
+void computeaccelerationfluxes4d_(double* flux3, double* flux4, const int* nd1a, const int* nd1b, const int* nd2a,
+                                  const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b,
+                                  const double* vel3, const double* vel4, double* face3, double* face4, const double* u,
+                                  const double* dx, const int* solution_order) {
+  const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
+  lk_geom g;
+  if (!geom_from_data("computeaccelerationfluxes4d_", nd, *solution_order, dx, &g)) return;
+  if (!check(lk_face_fluxes_4d(flux3, face3, u, &g, vel3, 2, nullptr))) return;
+  if (!check(lk_face_fluxes_4d(flux4, face4, u, &g, vel4, 3, nullptr))) return;
+  check(cudaDeviceSynchronize() == cudaSuccess ? LK_OK : LK_ERR_CUDA);
+}
+
+void accumfluxdiv4d_(double* rhs, const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a,
+                     const int* nd3b, const int* nd4a, const int* nd4b, const int* n1a, const int* n1b, const int* n2a,
+                     const int* n2b, const int* n3a, const int* n3b, const int* n4a, const int* n4b, const double* fluxx1,
+                     const double* fluxx2, const double* fluxx3, const double* fluxx4, const double* deltax) {
+  const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
+  const int* const n[8] = {n1a, n1b, n2a, n2b, n3a, n3b, n4a, n4b};
+  lk_geom g;
+  if (!geom_from("accumfluxdiv4d_", nd, n, 0, &g)) return;
+  for (int k = 0; k < 4; ++k) g.dx[k] = deltax[k];
+  if (!check(lk_accum_flux_div_4d(rhs, &g, fluxx1, fluxx2, fluxx3, fluxx4, nullptr))) return;
+  check(cudaDeviceSynchronize() == cudaSuccess ? LK_OK : LK_ERR_CUDA);
+}
+
+void computekeflux_(const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a, const int* nd3b,
+                    const int* nd4a, const int* nd4b, const int* n1a, const int* n1b, const int* n2a, const int* n2b,
+                    const int* n3a, const int* n3b, const int* n4a, const int* n4b, const int* ng1a, const int* ng1b,
+                    const int* ng2a, const int* ng2b, const int* ng3a, const int* ng3b, const int* ng4a, const int* ng4b,
+                    const double* dx, const double* face_flux1, const double* face_flux2, const double* face_flux3,
+                    const double* face_flux4, const double* velocities, const double* vxface_velocities,
+                    const double* vyface_velocities, const int* dir, const int* side, const double* mass, double* ke_flux) {
+  const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
+  const int* const n[8] = {n1a, n1b, n2a, n2b, n3a, n3b, n4a, n4b};
+  const int* const dom[8] = {ng1a, ng1b, ng2a, ng2b, ng3a, ng3b, ng4a, ng4b};
+  lk_geom g;
+  if (!geom_from("computekeflux_", nd, n, 0, &g)) return;
+  for (int k = 0; k < 4; ++k) g.dx[k] = dx[k];
+  if (*dir < 0 || *dir > 3 || *side < 0 || *side > 1) return fail("computekeflux_", "dir / side out of range");
+  // `dosum`: only a box that touches that boundary of the domain box sums (KineticSpeciesF.f:2781-2793); either way the
+  // incoming value is scaled by mass * ddir (:2889)
+  const bool touches = (*side == 0) ? (*n[2 * *dir] == *dom[2 * *dir]) : (*n[2 * *dir + 1] == *dom[2 * *dir + 1]);
+  double ddir = 1.0;
+  {
+    bool first = true;
+    for (int d = 0; d < 4; ++d)
+      if (d != *dir) {
+        ddir = first ? dx[d] : ddir * dx[d];
+        first = false;
+      }
+  }
+  if (!touches) {
+    *ke_flux = *ke_flux * *mass * ddir;
+    g_status = LK_OK;
+    return;
+  }
+  if (*ke_flux != 0.0) return fail("computekeflux_", "ke_flux must come in as 0 (the reference's callers zero it, KineticSpecies.C:2076)");
+  const double* fl[4] = {face_flux1, face_flux2, face_flux3, face_flux4};
+  DevTmp out(sizeof(double));
+  if (!out.p) return fail("computekeflux_", "device scratch");
+  if (!check(lk_ke_flux_from_fluxes((double*)out.p, &g, fl[*dir], velocities, vxface_velocities, vyface_velocities, *dir, *side,
+                                    *mass, nullptr)))
+    return;
+  check(lk_memcpy_d2h(ke_flux, out.p, sizeof(double)));
+}
+
+void computekevelspaceflux_(const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a,
+                            const int* nd3b, const int* nd4a, const int* nd4b, const int* n1a, const int* n1b,
+                            const int* n2a, const int* n2b, const int* n3a, const int* n3b, const int* n4a, const int* n4b,
+                            const int* ng1a, const int* ng1b, const int* ng2a, const int* ng2b, const int* ng3a,
+                            const int* ng3b, const int* ng4a, const int* ng4b, const double* dx, const double* face_flux3,
+                            const double* face_flux4, double* ke_flux, const double* mass, const double* vxface_velocities,
+                            const double* vyface_velocities, const int* side, const int* dir) {
+  (void)ng1a; (void)ng1b; (void)ng2a; (void)ng2b;
+  const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
+  const int* const n[8] = {n1a, n1b, n2a, n2b, n3a, n3b, n4a, n4b};
+  lk_geom g;
+  if (!geom_from("computekevelspaceflux_", nd, n, 0, &g)) return;
+  for (int k = 0; k < 4; ++k) g.dx[k] = dx[k];
+  g_status = LK_OK;
+  if (*dir != 2 && *dir != 3) return;   // the routine has no other branch (:2930, 2959)
+  const bool touches = (*dir == 2) ? ((*side == 0) ? (*n3a == *ng3a) : (*n3b == *ng3b)) : ((*side == 0) ? (*n4a == *ng4a) : (*n4b == *ng4b));
+  if (!touches) return;
+  if (!check(lk_ke_vel_space_flux(ke_flux, &g, (*dir == 2) ? face_flux3 : face_flux4, vxface_velocities, vyface_velocities, *dir,
+                                  *side, *mass, nullptr)))
+    return;
+  check(cudaDeviceSynchronize() == cudaSuccess ? LK_OK : LK_ERR_CUDA);
+}
+
 void appendkrook_(const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a, const int* nd3b,
                   const int* nd4a, const int* nd4b, const int* n1a, const int* n1b, const int* n2a, const int* n2b,
                   const int* n3a, const int* n3b, const int* n4a, const int* n4b, const double* dt, const int64_t* ic,

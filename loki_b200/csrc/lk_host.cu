@@ -1130,6 +1130,40 @@ int lk_vp_time_history(lk_vp_system* h, double* out, int capacity, int* written)
   *written = count;
   return LK_OK;
 }
+int lk_vp_flux_history(lk_vp_system* h, double* out, int capacity, int* written) {
+  // KineticSpecies::accumulateSequencesCommon (KineticSpecies.C:2052-2097): the kinetic-energy flux of every species
+  // through the eight phase-space boundaries, straight from the state (lk_ke_flux_boundaries: no face / flux arrays).
+  // Ghosts as there: x / y refreshed in the directions this rank wraps itself (a cut direction needs the caller's halo
+  // exchange of lk_vp_state_ptr first), then the velocity-boundary fill with the acceleration of the last evalRHS.
+  if (!h || !out || !written) return LK_ERR_ARG;
+  auto& S = h->sys;
+  const int ns = (int)S.species.size();
+  *written = 0;
+  if (capacity < 8 * ns) return LK_ERR_ARG;
+  loki::DevBuf<double> d;
+  int st = d.alloc(8 * ns);
+  if (st != LK_OK) return st;
+  for (int s = 0; s < ns; ++s) {
+    auto* ks = S.species[s];
+    double* f = ks->state();
+    st = ks->periodicFill(f, S.uncutDirs(), S.st);
+    if (st == LK_OK) st = ks->setAccelerationBCs(f, S.st);
+    if (st != LK_OK) return st;
+    lk_accel a = ks->accelDesc();
+    int at[8];
+    for (int k = 0; k < 2; ++k) {
+      at[2 * k] = (S.desc.tile_lo[k] == 0);
+      at[2 * k + 1] = (S.desc.tile_lo[k] + S.desc.tile_n[k] == S.desc.nglobal[k]);
+    }
+    at[4] = at[5] = at[6] = at[7] = 1;  // velocity space is whole on every rank
+    st = lk_ke_flux_boundaries(d.p + 8 * s, f, &ks->g, ks->velocities.p, &a, ks->mass, at, S.st);
+    if (st != LK_OK) return st;
+  }
+  if (cudaStreamSynchronize(S.st) != cudaSuccess) return LK_ERR_CUDA;
+  if (cudaMemcpy(out, d.p, sizeof(double) * 8 * ns, cudaMemcpyDeviceToHost) != cudaSuccess) return LK_ERR_CUDA;
+  *written = 8 * ns;
+  return LK_OK;
+}
 int lk_vp_ke_e_dot(lk_vp_system* h, int s, double* value) {
   if (!h || !value || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
   if (cudaStreamSynchronize(h->sys.st) != cudaSuccess) return LK_ERR_CUDA;

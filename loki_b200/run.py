@@ -93,6 +93,17 @@ class Runner:
         assert got.value == out.size
         return out
 
+    def flux_history(self):
+        """the `*_flux` time histories (KineticSpecies.C:2052-2097): per species the kinetic-energy flux through the
+        eight phase-space boundaries, [8 s + 2 dir + side]; Vlasov-Poisson systems"""
+        if self.vm:
+            raise NotImplementedError("flux histories of the Vlasov-Maxwell system")
+        out = np.zeros(8 * len(self.deck.species))
+        got = C.c_int()
+        capi.check(self.H.lk_vp_flux_history(self.sys, out.ctypes.data, out.size, C.byref(got)), "flux_history")
+        assert got.value == out.size
+        return out
+
     def advance(self):
         H, run = self.H, self.deck.run
         dt = C.c_double()

@@ -26,10 +26,13 @@ ROUTINES = {
     "KineticSpeciesF.f": ["xpby4d", "setphasespacevel4d", "setphasespacevelmaxwell4d", "weno43fit4d",
                           "weno65fit4d", "setaccelerationbcs4d", "setadvectionbcs4d", "setaccelerationbcs4djb", "setadvectionbcs4djb", "computeadvectionderivatives4d",
                           "computeaccelerationderivatives4d", "computecurrents", "computekeedot", "computeke",
-                          "computekemaxwell", "appendkrook"],
+                          "computekemaxwell", "appendkrook", "weno43avg4d", "weno65avg4d", "computeflux4d",
+                          "computeadvectionfluxes4d", "computeaccelerationfluxes4d", "accumfluxdiv4d", "computekeflux",
+                          "computekevelspaceflux"],
     "PoissonF.f": ["neutralizecharge4d", "computeefieldfrompotential"],
     "MaxwellF.f": ["maxwellevalrhs", "sgmetricfunction", "maxwellevalvzrhs", "xpby2d"],
 }
+ALL_WANTED = {r for rs in ROUTINES.values() for r in rs}
 INTRINSICS = {"max": "fmax", "min": "fmin", "abs": "fabs"}
 EXTERNAL_REAL_FUNCS = {"initialconditionatpoint"}
 
@@ -203,6 +206,8 @@ class Parser:
             a = self.expr()
             self.take(")")
             return a   # already parenthesised by the binary rules; keep grouping explicit
+        if tok in (".true.", ".false."):
+            return "1" if tok == ".true." else "0"
         if re.match(r"[0-9.]", tok):
             return self.number(tok)
         if re.match(r"[a-z_]", tok):
@@ -419,13 +424,31 @@ def translate(name, stmts):
             return
         mm = re.match(r"^call\s+(\w+)\s*\((.*)\)$", s)
         if mm:
-            args = []
+            if mm.group(1) not in ALL_WANTED:
+                # a routine outside the path (the reference only reaches these under `if (.false.)`: limiter and
+                # artificial-viscosity experiments): not translated, and loud if it were ever reached
+                emit('f77_untranslated("%s");' % mm.group(1))
+                return
+            args, temps = [], []
             for a in split_top(mm.group(2)):
                 toks = tokenize(a)
                 p = Parser(toks, ctx)
                 e = p.expr()
-                args.append(by_ref(ctx, (e, toks)))
-            emit("%s_(%s);" % (mm.group(1), ", ".join(args)))
+                try:
+                    args.append(by_ref(ctx, (e, toks)))
+                except SyntaxError:
+                    # an expression or a literal actual argument: Fortran passes the address of a temporary
+                    # (integer arithmetic on the box bounds and literal direction numbers in the routines we translate)
+                    if any(re.match(r"^\d*\.\d*|\d+[de]", t) for t in toks):
+                        raise
+                    t = "_arg%d" % len(temps)
+                    temps.append("int %s = %s;" % (t, e))
+                    args.append("&" + t)
+            if temps:
+                emit("{ " + " ".join(temps))
+                emit("  %s_(%s); }" % (mm.group(1), ", ".join(args)))
+            else:
+                emit("%s_(%s);" % (mm.group(1), ", ".join(args)))
             return
         # assignment: split at the top-level '='
         depth = 0
@@ -451,6 +474,9 @@ def translate(name, stmts):
 PRELUDE = """/* GENERATED by oracle/f77toc.py from the reference Fortran -- do not commit, do not edit. */
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+static inline void f77_untranslated(const char* name) { fprintf(stderr, "f77toc: %s is not translated\\n", name); abort(); }
 static inline double f77_powi2(double x) { return x * x; }
 static inline double f77_powi3(double x) { return (x * x) * x; }
 static inline double f77_powi4(double x) { double t = x * x; return t * t; }

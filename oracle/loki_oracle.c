@@ -392,6 +392,139 @@ void ok_acceleration_derivatives_4d(double* rhs, const double* f, const ok_geom*
     }
 }
 
+/* ------------------------------------------------------------------------------------------------------
+ * Flux-form diagnostics: WENO43Avg4D / WENO65Avg4D (KineticSpeciesF.f:630-720, 797-910) + computeFlux4D
+ * (:2359-2396) as computeadvectionfluxes4D (:1838-1945) and computeaccelerationfluxes4D (:2249-2355) call them.
+ * Direction d (0..3): face, vel and flux are the ROTATED arrays of KineticSpecies.C:1569-1584 -- extents
+ * (nd[d]+1, nd[d+1], nd[d+2], nd[d+3]) with the indices taken mod 4, face index j0 = the face below cell j0 of
+ * direction d.  The fit runs over faces j0 = w .. nd[d]-w (w = 2 at order 4, 3 at order 6: `f1a = nf1a+2`, `+3`) and
+ * the whole data box in the other directions; the flux = vel * face runs over the faces 2 .. extent-3 of ALL four
+ * rotated extents whatever the order (computeFlux4D's `+2 / -2`), so at order 6 it also multiplies two faces the fit
+ * never wrote.  Entries outside those ranges are left as the caller gave them.
+ * ---------------------------------------------------------------------------------------------------- */
+void ok_face_fluxes_4d(double* flux, double* face, const double* u, const ok_geom* g, const double* vel, int d) {
+  const int w = (g->order == 4) ? 2 : 3;
+  int64_t e[4], cs[4];     /* rotated extents; cell strides of the rotated index positions */
+  const int64_t s_cell[4] = {1, ND(0), ND(0) * ND(1), ND(0) * ND(1) * ND(2)};
+  for (int k = 0; k < 4; ++k) {
+    e[k] = ND((d + k) % 4) + (k == 0 ? 1 : 0);
+    cs[k] = s_cell[(d + k) % 4];
+  }
+  OK_PARALLEL_FOR2
+  for (int64_t j3 = 0; j3 < e[3]; ++j3)
+    for (int64_t j2 = 0; j2 < e[2]; ++j2)
+      for (int64_t j1 = 0; j1 < e[1]; ++j1)
+        for (int64_t j0 = w; j0 <= e[0] - 1 - w; ++j0) {
+          const int64_t fi = j0 + e[0] * (j1 + e[1] * (j2 + e[2] * j3));
+          const double* c = u + j0 * cs[0] + j1 * cs[1] + j2 * cs[2] + j3 * cs[3];   /* cell j0: the one above the face */
+          face[fi] = fit_right(c - cs[0], cs[0], g->order, vel[fi]);
+        }
+  OK_PARALLEL_FOR2
+  for (int64_t j3 = 2; j3 <= e[3] - 3; ++j3)
+    for (int64_t j2 = 2; j2 <= e[2] - 3; ++j2)
+      for (int64_t j1 = 2; j1 <= e[1] - 3; ++j1)
+        for (int64_t j0 = 2; j0 <= e[0] - 3; ++j0) {
+          const int64_t fi = j0 + e[0] * (j1 + e[1] * (j2 + e[2] * j3));
+          flux[fi] = vel[fi] * face[fi];
+        }
+}
+
+/* accumfluxdiv4D (KineticSpeciesF.f:985-1032): rhs = -div(flux) on the interior; the vy term is divided by dvx as
+ * in the reference (:1024) */
+void ok_accum_flux_div_4d(double* rhs, const ok_geom* g, const double* flux1, const double* flux2, const double* flux3,
+                          const double* flux4) {
+  const int ng = g->ng;
+  const double dx = g->dx[0], dy = g->dx[1], dvx = g->dx[2];
+  OK_PARALLEL_FOR2
+  for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
+    for (int i3 = ng; i3 < ng + g->n[2]; ++i3)
+      for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
+        for (int i1 = ng; i1 < ng + g->n[0]; ++i1) {
+          double temp = -(flux1[v1idx(g, i1 + 1, i2, i3, i4)] - flux1[v1idx(g, i1, i2, i3, i4)]) / dx -
+                        (flux2[v2idx(g, i2 + 1, i3, i4, i1)] - flux2[v2idx(g, i2, i3, i4, i1)]) / dy -
+                        (flux3[v3idx(g, i3 + 1, i4, i1, i2)] - flux3[v3idx(g, i3, i4, i1, i2)]) / dvx -
+                        (flux4[v4idx(g, i4 + 1, i1, i2, i3)] - flux4[v4idx(g, i4, i1, i2, i3)]) / dvx;
+          F4(rhs, i1, i2, i3, i4) = temp;
+        }
+}
+
+/* computekeflux (KineticSpeciesF.f:2734-2893): kinetic-energy flux through the phase-space boundary (dir, side) of a
+ * box that touches it (the caller decides: `n1a .eq. ng1a` etc. compare with the domain box); sequential sums in
+ * the reference's loop order */
+double ok_compute_ke_flux(const ok_geom* g, const double* flux1, const double* flux2, const double* flux3,
+                          const double* flux4, const double* velocities, const double* vxface_velocities,
+                          const double* vyface_velocities, int dir, int side, double mass) {
+  const int ng = g->ng;
+  const int a[4] = {ng, ng, ng, ng}, b[4] = {ng + g->n[0] - 1, ng + g->n[1] - 1, ng + g->n[2] - 1, ng + g->n[3] - 1};
+  const int fidx = side == 0 ? a[dir] : b[dir] + 1;
+  const int64_t n3d = ND(2), n4d = ND(3);
+  double ke = 0.0, ddir;
+  if (dir == 0) {
+    ddir = g->dx[1] * g->dx[2] * g->dx[3];
+    for (int i4 = a[3]; i4 <= b[3]; ++i4)
+      for (int i3 = a[2]; i3 <= b[2]; ++i3) {
+        const double vx = velocities[i3 + n3d * i4], vy = velocities[i3 + n3d * (i4 + n4d)];
+        const double v2 = vx * vx + vy * vy;
+        for (int i2 = a[1]; i2 <= b[1]; ++i2) ke = ke + 0.5 * flux1[v1idx(g, fidx, i2, i3, i4)] * v2;
+      }
+  } else if (dir == 1) {
+    ddir = g->dx[0] * g->dx[2] * g->dx[3];
+    for (int i4 = a[3]; i4 <= b[3]; ++i4)
+      for (int i3 = a[2]; i3 <= b[2]; ++i3) {
+        const double vx = velocities[i3 + n3d * i4], vy = velocities[i3 + n3d * (i4 + n4d)];
+        const double v2 = vx * vx + vy * vy;
+        for (int i1 = a[0]; i1 <= b[0]; ++i1) ke = ke + 0.5 * flux2[v2idx(g, fidx, i3, i4, i1)] * v2;
+      }
+  } else if (dir == 2) {
+    ddir = g->dx[0] * g->dx[1] * g->dx[3];
+    for (int i4 = a[3]; i4 <= b[3]; ++i4) {
+      const double vx = vxface_velocities[fidx + (n3d + 1) * i4], vy = vxface_velocities[fidx + (n3d + 1) * (i4 + n4d)];
+      const double v2 = vx * vx + vy * vy;
+      for (int i2 = a[1]; i2 <= b[1]; ++i2)
+        for (int i1 = a[0]; i1 <= b[0]; ++i1) ke = ke + 0.5 * flux3[v3idx(g, fidx, i4, i1, i2)] * v2;
+    }
+  } else {
+    ddir = g->dx[0] * g->dx[1] * g->dx[2];
+    for (int i3 = a[2]; i3 <= b[2]; ++i3) {
+      const double vx = vyface_velocities[i3 + n3d * fidx], vy = vyface_velocities[i3 + n3d * (fidx + (n4d + 1))];
+      const double v2 = vx * vx + vy * vy;
+      for (int i2 = a[1]; i2 <= b[1]; ++i2)
+        for (int i1 = a[0]; i1 <= b[0]; ++i1) ke = ke + 0.5 * flux4[v4idx(g, fidx, i1, i2, i3)] * v2;
+    }
+  }
+  return ke * mass * ddir;
+}
+
+/* computekevelspaceflux (KineticSpeciesF.f:2897-2990): the same through a velocity boundary (dir 2 / 3), left as a
+ * field over (x,y): ke_flux(n1d,n2d) accumulates */
+void ok_compute_ke_vel_space_flux(double* ke_flux, const ok_geom* g, const double* flux3, const double* flux4,
+                                  const double* vxface_velocities, const double* vyface_velocities, int dir, int side,
+                                  double mass) {
+  const int ng = g->ng;
+  const int64_t n3d = ND(2), n4d = ND(3);
+  if (dir == 2) {
+    const int i3 = side == 0 ? ng : ng + g->n[2];
+    const double ddir = g->dx[3];
+    for (int i4 = ng; i4 < ng + g->n[3]; ++i4) {
+      const double vx = vxface_velocities[i3 + (n3d + 1) * i4], vy = vxface_velocities[i3 + (n3d + 1) * (i4 + n4d)];
+      const double v2 = vx * vx + vy * vy;
+      for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
+        for (int i1 = ng; i1 < ng + g->n[0]; ++i1)
+          ke_flux[i1 + ND(0) * i2] = ke_flux[i1 + ND(0) * i2] + 0.5 * mass * flux3[v3idx(g, i3, i4, i1, i2)] * v2 * ddir;
+    }
+  } else if (dir == 3) {
+    const int i4 = side == 0 ? ng : ng + g->n[3];
+    const double ddir = g->dx[2];
+    for (int i3 = ng; i3 < ng + g->n[2]; ++i3) {
+      const double vx = vyface_velocities[i3 + n3d * i4], vy = vyface_velocities[i3 + n3d * (i4 + (n4d + 1))];
+      const double v2 = vx * vx + vy * vy;
+      for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
+        for (int i1 = ng; i1 < ng + g->n[0]; ++i1)
+          ke_flux[i1 + ND(0) * i2] = ke_flux[i1 + ND(0) * i2] + 0.5 * mass * flux4[v4idx(g, i4, i1, i2, i3)] * v2 * ddir;
+    }
+  }
+}
+
 /* computecurrents (KineticSpeciesF.f:2400-2443) */
 void ok_compute_currents(const ok_geom* g, const double* velocities, const double* u, const double* vz,
                          double* Jx, double* Jy, double* Jz) {

@@ -104,6 +104,16 @@ void ok_append_krook(double* rhs, const double* u, const ok_geom* g, const doubl
                      void* ic_ctx);
 /* time-history diagnostics: computeke / computekemaxwell (KineticSpeciesF.f:2447-2559) and the field
  * histories of Poisson / Maxwell ::accumulateSequences (Poisson.C:796-860, Maxwell.C:753-875) */
+/* flux-form diagnostics (KineticSpeciesF.f:630-720, 797-910, 1838-1945, 2249-2396, 985-1032, 2734-2990); d = 0..3 */
+void ok_face_fluxes_4d(double* flux, double* face, const double* u, const ok_geom* g, const double* vel, int d);
+void ok_accum_flux_div_4d(double* rhs, const ok_geom* g, const double* flux1, const double* flux2, const double* flux3,
+                          const double* flux4);
+double ok_compute_ke_flux(const ok_geom* g, const double* flux1, const double* flux2, const double* flux3,
+                          const double* flux4, const double* velocities, const double* vxface_velocities,
+                          const double* vyface_velocities, int dir, int side, double mass);
+void ok_compute_ke_vel_space_flux(double* ke_flux, const ok_geom* g, const double* flux3, const double* flux4,
+                                  const double* vxface_velocities, const double* vyface_velocities, int dir, int side,
+                                  double mass);
 void ok_compute_ke(const ok_geom* g, const double* u, double mass, const double* velocities, double* out5);
 void ok_compute_ke_maxwell(const ok_geom* g, const double* u, double mass, const double* velocities,
                            const double* vz_in, double* out3);
@@ -171,6 +181,8 @@ void ok_vp_rk6_step(ok_vp_work* w, double** f_new, double** f_old, double time, 
 /* KineticSpecies::computeDt + VPSystem::stableDt from given axmax/aymax */
 /* axmax/aymax of the most recent evalRHS (the last RK stage of the previous step): what
  * VPSystem::stableDt sees (KineticSpecies.C:771-772) */
+/* the eight boundary kinetic-energy fluxes per species (KineticSpecies.C:2052-2097): out[8 s + 2 dir + side] */
+void ok_vp_ke_flux_history(ok_vp_work* w, double** f, double* out);
 void ok_vp_last_accel_max(const ok_vp_work* w, double* axmax, double* aymax);
 double ok_vp_stable_dt(const ok_vp_work* w, const double* axmax, const double* aymax, int rk_order);
 

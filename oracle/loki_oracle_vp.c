@@ -206,6 +206,41 @@ void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double time, double
   }
 }
 
+/* KineticSpecies::accumulateSequencesCommon (KineticSpecies.C:2052-2097): the kinetic-energy flux of every species'
+ * state f[s] through the eight phase-space boundaries, out[8 s + 2 dir + side].  As there: ghosts refreshed
+ * (Simulation.C:119 updateGhosts, setPhysicalBCs: periodic here), advection fluxes, then the velocity-boundary fill
+ * and the acceleration fluxes with the face accelerations the LAST evalRHS left in vel3 / vel4 (the last stage of the
+ * step just taken), then computekeflux on a box that touches every boundary.  f's ghost cells are rewritten. */
+void ok_vp_ke_flux_history(ok_vp_work* w, double** f, double* out) {
+  for (int s = 0; s < w->ns; ++s) {
+    const ok_species* sp = &w->sp[s];
+    const ok_geom* g = &sp->g;
+    const int64_t n1d = ok_nd(g, 0), n2d = ok_nd(g, 1), n3d = ok_nd(g, 2), n4d = ok_nd(g, 3);
+    const int64_t len[4] = {(n1d + 1) * n2d * n3d * n4d, (n2d + 1) * n3d * n4d * n1d, (n3d + 1) * n4d * n1d * n2d,
+                            (n4d + 1) * n1d * n2d * n3d};
+    const double* vel[4] = {w->vel1[s], w->vel2[s], w->vel3[s], w->vel4[s]};
+    double *face[4], *flux[4];
+    for (int d = 0; d < 4; ++d) {
+      face[d] = (double*)calloc(len[d], sizeof(double));
+      flux[d] = (double*)calloc(len[d], sizeof(double));
+    }
+    ok_periodic_fill_4d(f[s], g, 1, 1);
+    ok_face_fluxes_4d(flux[0], face[0], f[s], g, vel[0], 0);
+    ok_face_fluxes_4d(flux[1], face[1], f[s], g, vel[1], 1);
+    ok_set_acceleration_bcs_4d(f[s], g, w->vel3[s], w->vel4[s], 1, 1, 1, 1, sp->ic, sp->ic_ctx);
+    ok_face_fluxes_4d(flux[2], face[2], f[s], g, vel[2], 2);
+    ok_face_fluxes_4d(flux[3], face[3], f[s], g, vel[3], 3);
+    for (int dir = 0; dir < 4; ++dir)
+      for (int side = 0; side < 2; ++side)
+        out[8 * s + 2 * dir + side] = ok_compute_ke_flux(g, flux[0], flux[1], flux[2], flux[3], w->velocities[s], w->vxface[s],
+                                                         w->vyface[s], dir, side, sp->mass);
+    for (int d = 0; d < 4; ++d) {
+      free(face[d]);
+      free(flux[d]);
+    }
+  }
+}
+
 /* RK4Integrator::advance with stageAdvance (RK4Integrator.H:66-171) */
 void ok_vp_rk4_step(ok_vp_work* w, double** f_new, double** f_old, double time, double dt, double* ke) {
   static const double THIRD = 1.0 / 3.0;

@@ -177,6 +177,35 @@ def kinetic_cases(B, ok, order):
            C.byref(k))
     B.finish()
     out["ke_e_dot"] = np.array([k.value])
+    # flux-form diagnostics: the face / flux arrays of the four directions, their divergence, the kinetic-energy flux
+    # through the eight boundaries (box == domain: every boundary is touched) and through the velocity boundaries as
+    # a field over (x,y)
+    vels = [s.vel1, s.vel2, vel3, vel4]
+    face = [np.zeros_like(v) for v in vels]
+    flux = [np.zeros_like(v) for v in vels]
+    B.call("computeadvectionfluxes4d_", B.arr(flux[0]), B.arr(flux[1]), *db, B.arr(vels[0]), B.arr(vels[1]), B.arr(face[0]),
+           B.arr(face[1]), B.arr(s.f), B.meta(dxs), B.i(order))
+    B.call("computeaccelerationfluxes4d_", B.arr(flux[2]), B.arr(flux[3]), *db, B.arr(vels[2]), B.arr(vels[3]), B.arr(face[2]),
+           B.arr(face[3]), B.arr(s.f), B.meta(dxs), B.i(order))
+    div = np.zeros_like(s.f)
+    B.call("accumfluxdiv4d_", B.arr(div), *db, *ib, *[B.arr(a) for a in flux], B.meta(dxs))
+    kef = np.zeros(8)
+    kev = [np.zeros((n2d, n1d)) for _ in range(4)]
+    for dr in range(4):
+        for side in range(2):
+            kk = C.c_double(0.0)
+            B.call("computekeflux_", *db, *ib, *ib, B.meta(dxs), *[B.arr(a) for a in flux], B.arr(s.velocities), B.arr(s.vxface),
+                   B.arr(s.vyface), B.i(dr), B.i(side), B.d(1.7), C.byref(kk))
+            kef[2 * dr + side] = kk.value
+            if dr >= 2:
+                B.call("computekevelspaceflux_", *db, *ib, *ib, B.meta(dxs), B.arr(flux[2]), B.arr(flux[3]),
+                       B.arr(kev[2 * (dr - 2) + side]), B.d(1.7), B.arr(s.vxface), B.arr(s.vyface), B.i(side), B.i(dr))
+    B.finish()
+    for d in range(4):
+        out["face%d" % (d + 1)], out["flux%d" % (d + 1)] = face[d], flux[d]
+    out["flux_div"], out["ke_flux"] = div, kef
+    for k in range(4):
+        out["ke_vel_flux%d" % k] = kev[k]
     # appendkrook: a layer over part of configuration space
     nu = np.zeros((n2d, n1d))
     nu[:, : n1d // 3] = rng.uniform(0.1, 1.0, size=(n2d, n1d // 3))

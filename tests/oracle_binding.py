@@ -77,6 +77,11 @@ def load():
     L.ok_reduce_4d_to_2d.argtypes = [dp, dp, G, d, d]
     L.ok_append_krook.argtypes = [dp, dp, G, dp, d, IC_FN, C.c_void_p]
     L.ok_compute_ke.argtypes = [G, dp, d, dp, dp]
+    L.ok_face_fluxes_4d.argtypes = [dp, dp, dp, G, dp, i]
+    L.ok_accum_flux_div_4d.argtypes = [dp, G, dp, dp, dp, dp]
+    L.ok_compute_ke_flux.restype = d
+    L.ok_compute_ke_flux.argtypes = [G, dp, dp, dp, dp, dp, dp, dp, i, i, d]
+    L.ok_compute_ke_vel_space_flux.argtypes = [dp, G, dp, dp, dp, dp, i, i, d]
     L.ok_compute_ke_maxwell.argtypes = [G, dp, d, dp, dp, dp]
     L.ok_field_history.argtypes = [dp, i, i, i, i, dp, dp]
     L.ok_periodic_fill_4d.argtypes = [dp, G, i, i]
@@ -98,6 +103,7 @@ def load():
     L.ok_vp_rk4_step.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), d, d, dp]
     L.ok_vp_rk6_step.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), d, d, dp]
     L.ok_vp_last_accel_max.argtypes = [C.c_void_p, dp, dp]
+    L.ok_vp_ke_flux_history.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), dp]
     L.ok_vp_stable_dt.restype = d
     L.ok_vp_stable_dt.argtypes = [C.c_void_p, dp, dp, i]
     L.ok_shaped_ramped_driver.argtypes = [dp, dp, i, i, i, i, dp, dp, i, d, dp, d, i]

@@ -546,7 +546,7 @@ def test_full_regression_run_plane_epw_reduced_grid(lk, ok, fast):
     ok.ok_vp_work_destroy(w)
 
 
-def _full_run_vs_oracle(ok, deck, final_time, save_times):
+def _full_run_vs_oracle(ok, deck, final_time, save_times, flux_traces=False):
     """Simulation::advance's loop on the device (loki_b200.run.Runner) and through the oracle, side by side;
     returns (steps, device traces, oracle traces, device states, oracle states).  Traces per step: e_max,
     e_tot, ex_max, e_sum_tot, then ke of every species."""
@@ -594,6 +594,13 @@ def _full_run_vs_oracle(ok, deck, final_time, save_times):
             ok.ok_compute_ke(C.byref(sp[s_].g), f_old[s_].ravel(), deck.species[s_].mass, vts[s_], o5)
             d_row.append(hist[5 + 6 * s_])
             o_row.append(o5[0])
+        if flux_traces:
+            # the eight boundary kinetic-energy fluxes per species (KineticSpecies.C:2052-2097), both sides with the
+            # face accelerations of the step's last stage
+            fo = np.zeros(8 * ns)
+            ok.ok_vp_ke_flux_history(w, _ptrs(f_old), fo)
+            d_row += list(r.flux_history())
+            o_row += list(fo)
         dev_tr.append(d_row)
         ora_tr.append(o_row)
     assert abs(r.time - final_time) < 1e-9
@@ -610,6 +617,22 @@ FULL_RUNS = [
     (lambda: decks.plane_iaw(n=(10, 10), nv=(16, 10), order=6, rk=6), 5.0, 1.0, 10),        # planeIAW_6, the deck's grid
     (lambda: decks.interpenetrating_streams(n=(32, 7), nv=(16, 12)), 5.0, 1.0, 10),         # InterpenetratingStreams
 ]
+
+
+def test_flux_histories_along_a_deck_run(lk, ok, fast):
+    """the `*_flux` time histories along planeIAW (reduced grid, both species, final_time = 2): 16 more traces, each
+    within 1e-10 of the oracle's in the norm of the run.  The x / y fluxes are odd in the normal velocity and cancel
+    to a fraction of their terms; every trace is held relative to the largest flux trace of its species."""
+    deck = decks.plane_iaw(n=(16, 8), nv=(24, 16))
+    steps, dev_tr, ora_tr, got, want = _full_run_vs_oracle(ok, deck, 2.0, 1.0, flux_traces=True)
+    ns = len(deck.species)
+    base = dev_tr.shape[1] - 8 * ns
+    assert steps >= 10 and base == 4 + ns
+    for s_ in range(ns):
+        d_, o_ = dev_tr[:, base + 8 * s_: base + 8 * s_ + 8], ora_tr[:, base + 8 * s_: base + 8 * s_ + 8]
+        scale = np.max(np.abs(o_))
+        assert scale > 0 and np.all(np.max(np.abs(o_), axis=0) > 0)
+        assert np.max(np.abs(d_ - o_)) <= 1e-10 * scale, np.max(np.abs(d_ - o_), axis=0) / scale
 
 
 @pytest.mark.parametrize("mk,final_time,save_times,min_steps", FULL_RUNS)

@@ -138,6 +138,36 @@ def test_pin_kinetic_kernels(ok, ref, n, order, lo):
     R.L.loki_ref_set_ic(cb, None, C.byref(lower))
     R.L.appendkrook_(*db, *ib, R._d(0.037), C.byref(C.c_int64(0)), R._p(nu), R._p(s.f), R._p(r2k))
     assert np.array_equal(r1k, r2k)
+    # flux-form diagnostics: computeadvectionfluxes4D / computeaccelerationfluxes4D (face fits + computeFlux4D),
+    # accumfluxdiv4D, computekeflux on all eight boundaries, computekevelspaceflux on the four velocity boundaries
+    vels = [s.vel1, s.vel2, vel3, vel4]
+    fl1, fc1 = [np.zeros_like(v) for v in vels], [np.zeros_like(v) for v in vels]
+    fl2, fc2 = [np.zeros_like(v) for v in vels], [np.zeros_like(v) for v in vels]
+    for d in range(4):
+        ok.ok_face_fluxes_4d(fl1[d], fc1[d], s.f.ravel(), C.byref(s.g), vels[d], d)
+    R.L.computeadvectionfluxes4d_(R._p(fl2[0]), R._p(fl2[1]), *db, R._p(vels[0]), R._p(vels[1]), R._p(fc2[0]), R._p(fc2[1]),
+                                  R._p(s.f), R._p(dxs), R._i(order))
+    R.L.computeaccelerationfluxes4d_(R._p(fl2[2]), R._p(fl2[3]), *db, R._p(vels[2]), R._p(vels[3]), R._p(fc2[2]), R._p(fc2[3]),
+                                     R._p(s.f), R._p(dxs), R._i(order))
+    for d in range(4):
+        assert np.array_equal(fc1[d], fc2[d]) and np.array_equal(fl1[d], fl2[d]) and np.any(fl1[d] != 0), d
+    r1, r2 = np.zeros_like(s.f), np.zeros_like(s.f)
+    ok.ok_accum_flux_div_4d(r1.ravel(), C.byref(s.g), *fl1)
+    R.L.accumfluxdiv4d_(R._p(r2), *db, *ib, *[R._p(a) for a in fl2], R._p(dxs))
+    assert np.array_equal(r1, r2) and np.any(r1 != 0)
+    for dr in range(4):
+        for side in range(2):
+            k1 = ok.ok_compute_ke_flux(C.byref(s.g), *fl1, s.velocities, s.vxface, s.vyface, dr, side, 1.7)
+            k2 = C.c_double(0.0)
+            R.L.computekeflux_(*db, *ib, *ib, R._p(dxs), *[R._p(a) for a in fl2], R._p(s.velocities), R._p(s.vxface),
+                               R._p(s.vyface), R._i(dr), R._i(side), R._d(1.7), C.byref(k2))
+            assert k1 == k2.value and k1 != 0.0, (dr, side)
+            if dr >= 2:
+                q1, q2 = np.zeros((n2d, n1d)), np.zeros((n2d, n1d))
+                ok.ok_compute_ke_vel_space_flux(q1.ravel(), C.byref(s.g), fl1[2], fl1[3], s.vxface, s.vyface, dr, side, 1.7)
+                R.L.computekevelspaceflux_(*db, *ib, *ib, R._p(dxs), R._p(fl2[2]), R._p(fl2[3]), R._p(q2), R._d(1.7),
+                                           R._p(s.vxface), R._p(s.vyface), R._i(side), R._i(dr))
+                assert np.array_equal(q1, q2) and np.any(q1 != 0)
     # time-history kinetic energies: computeke, computekemaxwell
     o5 = np.zeros(5)
     ok.ok_compute_ke(C.byref(s.g), s.f.ravel(), 1.7, s.velocities, o5)
