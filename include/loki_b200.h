@@ -199,6 +199,10 @@ typedef struct lk_stage_moments {
 int lk_stage_moment_parts(const lk_geom* g);
 int lk_vlasov_stage(double* rhs_out, const double* f, const lk_geom* g, const double* velocities,
                     const lk_accel* a, const lk_rk_update* upd, const lk_stage_moments* mom, void* stream);
+/* The stage update alone, from a materialised rhs: delta / pred of `upd` exactly as the fused kernel's epilogue forms
+ * them (RK4Integrator.H:149-171, RK6Integrator.H:96-131), on the interior.  For callers that modify the rhs between its
+ * evaluation and the update (completeRHS's Krook layer, KineticSpecies.C:1049-1062).  upd->wrap is ignored. */
+int lk_rk_stage_update(const double* rhs, const lk_geom* g, const lk_rk_update* upd, void* stream);
 /* 1 when lk_vlasov_stage(rhs_out, ., g, ., a, upd, ...) would fold upd->accel_bcs into the pipelined kernel (f's velocity
  * ghosts stay as they are), 0 when it would run lk_set_acceleration_bcs_4d on f first */
 int lk_vlasov_stage_folds_bcs(const double* rhs_out, const lk_geom* g, const lk_accel* a, const lk_rk_update* upd);

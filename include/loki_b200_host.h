@@ -67,6 +67,16 @@ int lk_vp_set_inflow(lk_vp_system* sys, int s, const double* fx, const double* f
  * reference's cache does (:240-252) */
 int lk_vp_set_inflow2(lk_vp_system* sys, int s, int kind, const double* fx, const double* fv, const double* fx2,
                       const double* fv2);
+/* Deck options beyond the benchmark decks.
+ * lk_vp_set_boundary_options: a non-periodic x / y direction gets setadvectionbcs4d_ at its two physical boundaries
+ * before every advection sweep (setPhysicalBCs, KineticSpecies.H:998-1031; inflow from the species' tables; the Poisson
+ * solve stays periodic as in Poisson.C:147-152); use_new_bcs selects the "JB" variants of both boundary fills
+ * (VPSystem.C:819-821, KineticSpecies.H:421-453).  Non-periodic directions need a single rank.
+ * lk_vp_set_krook: nu (n1d,n2d) of this rank incl. ghosts, host pointer (KrookLayer::initialize, KrookLayer.C:54-160);
+ * completeRHS then adds -nu/dt (f - f_IC) to the species' rhs (KineticSpecies.C:1049-1062; f_IC from the inflow
+ * tables).  NULL removes the layer.  A Krook species leaves the fused stage kernel for rhs + Krook + update passes. */
+int lk_vp_set_boundary_options(lk_vp_system* sys, int nonperiodic_x, int nonperiodic_y, int use_new_bcs);
+int lk_vp_set_krook(lk_vp_system* sys, int s, const double* nu_host);
 int lk_vp_set_time(lk_vp_system* sys, double t);
 double lk_vp_time(const lk_vp_system* sys);
 

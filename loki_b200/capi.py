@@ -76,6 +76,7 @@ _PROTOS = {
     "lk_ke_vel_space_flux": (C.c_int, [_vp, C.POINTER(Geom), _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, _vp]),
     "lk_ke_flux_boundaries": (C.c_int, [_vp, _vp, C.POINTER(Geom), _vp, C.POINTER(Accel), C.c_double, C.POINTER(C.c_int * 8), _vp]),
     "lk_preset_inflow_ghosts_4d": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Inflow), _vp]),
+    "lk_rk_stage_update": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(RkUpdate), _vp]),
     "lk_vlasov_stage_folds_bcs": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Accel), C.POINTER(RkUpdate)]),
     "lk_periodic_fill_4d": (C.c_int, [_vp, C.POINTER(Geom), C.c_int, C.c_int, _vp]),
     "lk_set_acceleration_bcs_4d_jb": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Accel), C.POINTER(Inflow),

@@ -307,6 +307,12 @@ int lk_vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const doub
                   const lk_rk_update* upd, void* stream) {
   return stage_impl(rhs_out, f, g, velocities, a, upd, nullptr, stream, "lk_vlasov_rhs");
 }
+int lk_rk_stage_update(const double* rhs, const lk_geom* g, const lk_rk_update* upd, void* stream) {
+  if (!geom_ok(g) || !rhs || !upd || !upd->f_old || !upd->pred) return fail(LK_ERR_ARG, "lk_rk_stage_update: bad argument");
+  if (upd->n_prev < 0 || upd->n_prev > 7) return fail(LK_ERR_ARG, "lk_rk_stage_update: n_prev out of range");
+  if (upd->use_delta && !upd->delta_in) return fail(LK_ERR_ARG, "lk_rk_stage_update: use_delta needs delta_in");
+  CHECK_LAUNCH(DISPATCH(rk_stage_update)(rhs, g, upd, (cudaStream_t)stream), "lk_rk_stage_update");
+}
 int lk_vlasov_stage_folds_bcs(const double* rhs_out, const lk_geom* g, const lk_accel* a, const lk_rk_update* upd) {
   if (!g || !a || !upd || !upd->accel_bcs || g_strict) return 0;
   return lkfast::stage_folds_bcs(g, a, upd, const_cast<double*>(rhs_out), 3, g_variant) ? 1 : 0;

@@ -209,6 +209,12 @@ struct KineticSpecies {
   double* state() { return farr[i_state].p; }
   // which of the rotating arrays currently hold the inflow sample in their velocity ghost layers
   // (lk_rk_update.inflow_preset: the pipelined stage kernel then needs no separate velocity-boundary fill)
+  // deck options beyond the benchmark decks: Krook layer nu(n1d,n2d) (KineticSpecies.C:1049-1062),
+  // the "JB" boundary conditions (use_new_bcs, VPSystem.C:819-821), non-periodic x / y (KineticSpecies.H:998-1031)
+  DevBuf<double> krook_nu;
+  bool has_krook = false, use_new_bcs = false;
+  int nonperiodic = 0;              // bit 0 x, bit 1 y
+  int at_xy[4] = {1, 1, 1, 1};      // this rank's tile touches x-lo, x-hi, y-lo, y-hi of the domain
   bool preset[3] = {false, false, false};
   int arrayIndex(const double* p) const { return (p == farr[0].p) ? 0 : ((p == farr[1].p) ? 1 : 2); }
   void forgetPresets() { preset[0] = preset[1] = preset[2] = false; }
@@ -308,7 +314,21 @@ struct KineticSpecies {
     preset[arrayIndex(f)] = false;
     lk_accel a = accelDesc();
     const int at[4] = {1, 1, 1, 1};
+    if (use_new_bcs) return lk_set_acceleration_bcs_4d_jb(f, &g, &a, &inflow, at, st);
     return lk_set_acceleration_bcs_4d(f, &g, &a, &inflow, at, st);
+  }
+  // fillAdvectionGhostCells on this rank (KineticSpecies.H:404-412, 998-1031): the physical boundary conditions of a
+  // non-periodic direction, then the periodic wrap of the periodic directions this rank is not cut in (`dirs`)
+  int fillAdvectionGhosts(double* f, int dirs, void* st) {
+    if (nonperiodic) {
+      const int xper = !(nonperiodic & 1), yper = !(nonperiodic & 2);
+      if (use_new_bcs) {
+        LKH_CHECK(lk_set_advection_bcs_4d_jb(f, &g, velocities.p, &inflow, at_xy, xper, yper, st));
+      } else {
+        LKH_CHECK(lk_set_advection_bcs_4d(f, &g, velocities.p, &inflow, at_xy, xper, yper, st));
+      }
+    }
+    return periodicFill(f, dirs & ~nonperiodic, st);
   }
 
   // computeDt (KineticSpecies.C:647-694) without collision operators
@@ -468,7 +488,7 @@ struct VPSystem {
     return (desc.tile_n[0] == desc.nglobal[0] ? 1 : 0) | (desc.tile_n[1] == desc.nglobal[1] ? 2 : 0);
   }
   int fillAdvectionGhostCellsLocal() {
-    for (auto* ks : species) LKH_CHECK(ks->periodicFill(ks->f_eval, 3, st));
+    for (auto* ks : species) LKH_CHECK(ks->fillAdvectionGhosts(ks->f_eval, 3, st));
     return LK_OK;
   }
 
@@ -508,8 +528,14 @@ struct VPSystem {
       lk_accel a = ks->accelDesc();
       lk_rk_update u;
       memset(&u, 0, sizeof(u));
-      u.accel_bcs = &ks->inflow;
-      u.inflow_preset = 1;
+      // the "JB" fill and a Krook-layer species take the separate passes below
+      const bool plain = !ks->use_new_bcs && !ks->has_krook;
+      if (plain) {
+        u.accel_bcs = &ks->inflow;
+        u.inflow_preset = 1;
+      } else {
+        LKH_CHECK(ks->setAccelerationBCs(ks->f_eval, st));
+      }
       double* pred = (ks->f_eval == ks->farr[ks->i_a].p) ? ks->farr[ks->i_b].p : ks->farr[ks->i_a].p;
       u.f_old = ks->state();
       u.pred = pred;
@@ -541,7 +567,7 @@ struct VPSystem {
         ke_coef[ke_ncoef++] = dt * coef[stage];
       }
       static const bool no_fuse = getenv("LK_NO_FUSED_MOMENTS") != nullptr;  // debugging aid
-      const bool fused_moments = !lk_get_strict() && !no_fuse;
+      const bool fused_moments = !lk_get_strict() && !no_fuse && !ks->has_krook;
       // completeRHS: the driver's energy input rate, integrated with the state (KineticSpecies.C:1084-1093).
       // Production: from the vx moment of f_eval that the previous stage kernel left behind (consumed
       // here, before this stage's kernel overwrites the partial buffer).
@@ -552,18 +578,28 @@ struct VPSystem {
           LKH_CHECK(lk_ke_e_dot(ks->ke.p + 3, ks->f_eval, &ks->g, ks->charge, ks->velocities.p, ks->ext_efield.p, st));
       }
       // production: the kernel also writes pred's periodic ghost copies in the directions this rank wraps itself
-      u.wrap = fused_moments ? ks->wrapFor(uncutDirs()) : 0;
-      {
+      u.wrap = fused_moments ? ks->wrapFor(uncutDirs() & ~ks->nonperiodic) : 0;
+      if (ks->has_krook) {
+        // completeRHS's Krook layer sits between the rhs and the stage update (KineticSpecies.C:1049-1062): rhs
+        // materialised (RK6: in m_k[stage], RK4: in a scratch array), damped, then the update alone
+        if (!rhs_out) {
+          if (!ks->rhs_tmp.p) LKH_CHECK(ks->rhs_tmp.alloc(ks->vol));
+          rhs_out = ks->rhs_tmp.p;
+        }
+        LKH_CHECK(lk_vlasov_rhs(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, nullptr, st));
+        LKH_CHECK(lk_append_krook(rhs_out, ks->f_eval, &ks->g, ks->krook_nu.p, dt, &ks->inflow, st));
+        LKH_CHECK(lk_rk_stage_update(rhs_out, &ks->g, &u, st));
+      } else {
         const int ie = ks->arrayIndex(ks->f_eval);
-        if (lk_vlasov_stage_folds_bcs(rhs_out, &ks->g, &a, &u)) {
+        if (plain && lk_vlasov_stage_folds_bcs(rhs_out, &ks->g, &a, &u)) {
           if (!ks->preset[ie]) LKH_CHECK(lk_preset_inflow_ghosts_4d(ks->f_eval, &ks->g, &ks->inflow, st));
           ks->preset[ie] = true;
         } else {
           u.inflow_preset = 0;     // the stage runs the separate fill: f_eval's ghosts get the extrapolations as well
           ks->preset[ie] = false;
         }
+        LKH_CHECK(lk_vlasov_stage(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, fused_moments ? &ks->mom : nullptr, st));
       }
-      LKH_CHECK(lk_vlasov_stage(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, fused_moments ? &ks->mom : nullptr, st));
       ks->wrap_ptr = pred;
       ks->wrap_bits = u.wrap;
       ks->mom_valid = fused_moments;  // moments of `pred`, the next stage's input
@@ -642,12 +678,13 @@ struct VPSystem {
       double* f = ks->state();
       ks->mom_valid = false;
       ks->wrap_ptr = nullptr;
-      LKH_CHECK(lk_periodic_fill_4d(f, &ks->g, 1, 1, st));
+      LKH_CHECK(ks->fillAdvectionGhosts(f, 3, st));
       LKH_CHECK(lk_advection_derivatives_4d(rhs_dev[s], f, &ks->g, ks->velocities.p, st));
       LKH_CHECK(ks->computeAcceleration(em_local.p, t, desc.xlo, desc.tile_lo, true, st));
       LKH_CHECK(ks->setAccelerationBCs(f, st));
       lk_accel a = ks->accelDesc();
       LKH_CHECK(lk_acceleration_derivatives_4d(rhs_dev[s], f, &ks->g, &a, st));
+      if (ks->has_krook) LKH_CHECK(lk_append_krook(rhs_dev[s], f, &ks->g, ks->krook_nu.p, dt, &ks->inflow, st));
       if (ks->has_driver)
         LKH_CHECK(lk_ke_e_dot(ks->ke.p + 3, f, &ks->g, ks->charge, ks->velocities.p, ks->ext_efield.p, st));
     }
@@ -1027,6 +1064,35 @@ int lk_vp_set_inflow2(lk_vp_system* h, int s, int kind, const double* fx, const 
   ks->forgetPresets();
   return LK_OK;
 }
+int lk_vp_set_boundary_options(lk_vp_system* h, int nonperiodic_x, int nonperiodic_y, int use_new_bcs) {
+  if (!h) return LK_ERR_ARG;
+  auto& S = h->sys;
+  if ((nonperiodic_x || nonperiodic_y) && S.desc.ntiles != 1) return LK_ERR_UNSUPPORTED;  // the exchanger wraps periodically
+  for (auto* ks : S.species) {
+    if ((nonperiodic_x || nonperiodic_y) && ks->inflow.kind == 3) return LK_ERR_UNSUPPORTED;  // ghost tables hold v ghosts only
+    ks->nonperiodic = (nonperiodic_x ? 1 : 0) | (nonperiodic_y ? 2 : 0);
+    ks->use_new_bcs = use_new_bcs != 0;
+    for (int k = 0; k < 2; ++k) {
+      ks->at_xy[2 * k] = (S.desc.tile_lo[k] == 0);
+      ks->at_xy[2 * k + 1] = (S.desc.tile_lo[k] + S.desc.tile_n[k] == S.desc.nglobal[k]);
+    }
+    ks->forgetPresets();
+    ks->wrap_ptr = nullptr;
+  }
+  return LK_OK;
+}
+int lk_vp_set_krook(lk_vp_system* h, int s, const double* nu_host) {
+  if (!h || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  auto* ks = h->sys.species[s];
+  ks->has_krook = false;
+  if (!nu_host) return LK_OK;
+  std::vector<double> a(nu_host, nu_host + (size_t)ks->n1d * ks->n2d);
+  int st = ks->krook_nu.upload(a);
+  if (st != LK_OK) return st;
+  ks->has_krook = true;
+  ks->mom_valid = false;
+  return LK_OK;
+}
 int lk_vp_set_time(lk_vp_system* h, double t) {
   if (!h) return LK_ERR_ARG;
   h->sys.time = t;
@@ -1146,7 +1212,7 @@ int lk_vp_flux_history(lk_vp_system* h, double* out, int capacity, int* written)
   for (int s = 0; s < ns; ++s) {
     auto* ks = S.species[s];
     double* f = ks->state();
-    st = ks->periodicFill(f, S.uncutDirs(), S.st);
+    st = ks->fillAdvectionGhosts(f, S.uncutDirs(), S.st);
     if (st == LK_OK) st = ks->setAccelerationBCs(f, S.st);
     if (st != LK_OK) return st;
     lk_accel a = ks->accelDesc();

@@ -318,6 +318,30 @@ cudaError_t set_accel_bcs(double* f, const lk_geom* g, const lk_accel* a, const 
   return cudaGetLastError();
 }
 
+// RK stage update from a materialised rhs (RK4Integrator.H:149-171, RK6Integrator.H:96-131: the addSolnData /
+// copySolnData sequence in the reference's order of roundings): what the fused stage kernel does in its epilogue, for
+// callers that put something between the rhs and the update (the Krook layer of completeRHS).  Interior cells.
+__global__ void k_rk_update(DGeo g, DUpd upd, const double* __restrict__ rhs) {
+  const i64 total = (i64)g.n[0] * g.n[1] * g.n[2] * g.n[3];
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+    const int i1 = (int)(t % g.n[0]);
+    i64 r = t / g.n[0];
+    const int i2 = (int)(r % g.n[1]);
+    r /= g.n[1];
+    const int i3 = (int)(r % g.n[2]), i4 = (int)(r / g.n[2]);
+    const i64 idx = gidx(g, i1 + g.ng, i2 + g.ng, i3 + g.ng, i4 + g.ng);
+    rk_update(upd, idx, rhs[idx]);
+  }
+}
+cudaError_t rk_stage_update(const double* rhs, const lk_geom* g, const lk_rk_update* upd, cudaStream_t st) {
+  DGeo d = make_geo(g);
+  DUpd du = make_upd(upd);
+  const i64 total = (i64)d.n[0] * d.n[1] * d.n[2] * d.n[3];
+  k_rk_update<<<(unsigned)min((i64)nblk(total, 256), (i64)148 * 32), 256, 0, st>>>(d, du, rhs);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
 // The inflow sample in EVERY velocity ghost cell of the data box (the value setAccelerationBCs4D gives a ghost whose
 // face has the acceleration pointing inward; it depends on the position only).  The pipelined stage kernel relies on
 // it (lk_rk_update.inflow_preset): it extrapolates the outflow ghosts on the fly and leaves memory alone.

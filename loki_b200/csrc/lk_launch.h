@@ -26,6 +26,7 @@
   cudaError_t vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const double* velocities,\
                          const lk_accel* a, const lk_rk_update* upd, int flags, int variant,          \
                          double* mom_part, int nmom, cudaStream_t st);                                \
+  cudaError_t rk_stage_update(const double* rhs, const lk_geom* g, const lk_rk_update* upd, cudaStream_t st); \
   cudaError_t preset_inflow(double* f, const lk_geom* g, const lk_inflow* ic, cudaStream_t st);       \
   /* true when vlasov_rhs would take the pipelined kernel (which folds upd->accel_bcs into its boundary tiles) */ \
   bool stage_folds_bcs(const lk_geom* g, const lk_accel* a, const lk_rk_update* upd, double* rhs_out, int flags, int variant); \

@@ -47,6 +47,54 @@ class Deck:
         self.name, self.n, self.xlim, self.species, self.order, self.rk, self.cfl = name, n, xlim, species, order, rk, cfl
         self.ng = 2 if order == 4 else 3
         self.dx = ((xlim[1] - xlim[0]) / n[0], (xlim[3] - xlim[2]) / n[1])
+        # options beyond the benchmark decks: periodic_dir (ProblemDomain), use_new_bcs (VPSystem.C:819-821); a species'
+        # Krook layer is Species.krook = dict(x1a=, x1b=, x2a=, x2b=, coefficient=) with absent ends = the domain's
+        self.periodic = (True, True)
+        self.use_new_bcs = False
+
+    def krook_nu(self, sp, tile_lo=(0, 0), tile_n=None):
+        """KrookLayer::initialize (KrookLayer.C:54-160): nu (n2d, n1d) of a tile, ghosts zero; None without a layer"""
+        kr = getattr(sp, "krook", None)
+        if not kr:
+            return None
+        tile_n = tile_n or self.n
+        ng = self.ng
+        xmin, xmax, ymin, ymax = self.xlim
+        dx, dy = self.dx
+        xlo, xhi = kr.get("x1a", xmin), kr.get("x1b", xmax)
+        ylo, yhi = kr.get("x2a", ymin), kr.get("x2b", ymax)
+        coef = kr.get("coefficient", 1.0)
+
+        def ramp(e):
+            if self.order == 4:
+                return -pow(e, 4) * (+20.0 * pow(e, 3) - 70.0 * pow(e, 2) + 84.0 * e - 35.0)
+            return -pow(e, 6) * (+252.0 * pow(e, 5) - 1386.0 * pow(e, 4) + 3080.0 * pow(e, 3) - 3465.0 * pow(e, 2) + 1980.0 * e - 462.0)
+
+        def frac(c, lo, hi, cmin, cmax):
+            if c < lo:
+                return (c - lo) / (cmin - lo)
+            if c > hi:
+                return (c - hi) / (cmax - hi)
+            return 0.0
+
+        nu = np.zeros((tile_n[1] + 2 * ng, tile_n[0] + 2 * ng))
+        for j in range(tile_n[1]):
+            i2 = tile_lo[1] + j
+            nuy = ramp(frac(ymin + (0.5 + i2) * dy, ylo, yhi, ymin, ymax))
+            for i in range(tile_n[0]):
+                i1 = tile_lo[0] + i
+                nux = ramp(frac(xmin + (0.5 + i1) * dx, xlo, xhi, xmin, xmax))
+                nu[j + ng, i + ng] = coef * ((1.0 - nuy) * nux + nuy)
+        return nu
+
+    def apply_options(self, H, sys_, tile_lo=(0, 0), tile_n=None):
+        """hand the deck's boundary options and Krook layers to a lk_vp_system (after lk_vp_set_inflow)"""
+        st = H.lk_vp_set_boundary_options(sys_, int(not self.periodic[0]), int(not self.periodic[1]), int(self.use_new_bcs))
+        for s, sp in enumerate(self.species):
+            nu = self.krook_nu(sp, tile_lo, tile_n)
+            if st == 0 and nu is not None:
+                st = H.lk_vp_set_krook(sys_, s, nu.ctypes.data)
+        return st
 
     def geom_of(self, sp):
         dvx = (sp.vlim[1] - sp.vlim[0]) / sp.nv[0]

@@ -75,6 +75,8 @@ _PROTOS = {
     "lk_vp_rho_ptr": (_vp, [_vp]),
     "lk_vp_ke_e_dot": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     "lk_vp_time_history": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int)]),
+    "lk_vp_set_boundary_options": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "lk_vp_set_krook": (C.c_int, [_vp, C.c_int, _vp]),
     "lk_vp_flux_history": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int)]),
     "lk_vm_time_history": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int)]),
 }

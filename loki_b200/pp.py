@@ -154,8 +154,18 @@ def _species(params, k):
             raise ValueError("species %d: ic.%s != 0 is not supported (MaxwellianThermal / PerturbedMaxwellianIC)" % (k, key))
     if int(_f(params, pre + "num_collision_operators", 0.0)) > 0:
         raise ValueError("species %d: collision operators are out of scope of the Vlasov RHS path" % k)
-    if any(key.startswith(pre + "krook.") or key.startswith(pre + "external_dist_krook.") for key in list(params.keys())):
-        raise ValueError("species %d: Krook layers are not wired into the host mirror (lk_append_krook is Level 0 only)" % k)
+    if any(key.startswith(pre + "external_dist_krook.") for key in list(params.keys())):
+        raise ValueError("species %d: external-distribution Krook layers are not supported" % k)
+    # KrookLayer::parseParameters (KrookLayer.C:163-190): x1a / x1b / x2a / x2b switch the layer on; `power` is read
+    # but unused by KrookLayer::initialize (the ramp is the order's polynomial)
+    krook = {}
+    for key in ("x1a", "x1b", "x2a", "x2b", "coefficient", "power"):
+        if (pre + "krook." + key) in params:
+            krook[key] = _f(params, pre + "krook." + key)
+    if krook.get("power", 3.0) <= 0.0 or krook.get("coefficient", 1.0) < 0.0:
+        raise ValueError("species %d: Krook layer needs a positive power and a non-negative coefficient" % k)   # KrookLayer.C:195-201
+    if not any(e in krook for e in ("x1a", "x1b", "x2a", "x2b")):
+        krook = None
     if any(key.startswith(pre + "tz.") for key in list(params.keys())):
         raise ValueError("species %d: twilight-zone sources are out of scope" % k)
     if icn == "Perturbed Maxwellian":
@@ -164,6 +174,7 @@ def _species(params, k):
                           vx0=g("vx0"), vy0=g("vy0"), x_wave_number=g("x_wave_number"), y_wave_number=g("y_wave_number"),
                           flow_phase=g("phase"))
         sp.driver_phase, sp.driver_shape_type = driver_phase, driver_shape_type
+        sp.krook = krook
         return sp
     if icn == "Interpenetrating Stream":
         if _s(params, pre + "ic.syntax", "half plane") != "half plane":
@@ -176,6 +187,7 @@ def _species(params, k):
             st["centered"] = True
         sp = _d.Species(name, nv, vlim, mass, charge, stream=st, driver=driver)
         sp.driver_phase, sp.driver_shape_type = driver_phase, driver_shape_type
+        sp.krook = krook
         return sp
     raise ValueError("unsupported initial condition %r" % icn)
 
@@ -183,15 +195,13 @@ def _species(params, k):
 def deck_from_params(params, name="deck"):
     n = (int(params["N"][0]), int(params["N"][1]))
     xlim = tuple(float(t) for t in params["domain_limits"][:4])
-    if params.get("periodic_dir", ["true", "true"])[:2] != ["true", "true"]:
-        raise ValueError("the host mirror is periodic in x and y")
+    periodic = tuple(t == "true" for t in params.get("periodic_dir", ["true", "true"])[:2])
     order = int(_f(params, "spatial_solution_order", 4.0))
     rk = int(_f(params, "temporal_solution_order", 4.0))
     cfl = _f(params, "cfl", 0.9)                      # Simulation.C:174
     if _s(params, "do_relativity", "false") == "true":
         raise ValueError("do_relativity = true is not supported (non-relativistic velocity tables)")
-    if _s(params, "use_new_bcs", "false") == "true":
-        raise ValueError("use_new_bcs = true: the JB boundary conditions are Level-0 kernels only, not wired into the host mirror")
+    use_new_bcs = _s(params, "use_new_bcs", "false") == "true"            # VPSystem.C:819-821
     if _s(params, "do_new_algorithm", "true") != "true":
         raise ValueError("do_new_algorithm = false (flux form) is not the path this library accelerates")
     ns = int(_f(params, "number_of_species"))
@@ -213,10 +223,15 @@ def deck_from_params(params, name="deck"):
             k += 1
         if rk != 4:
             raise ValueError("the Vlasov-Maxwell host mirror integrates with RK4")
+        if periodic != (True, True) or use_new_bcs or any(getattr(sp, "krook", None) for sp in species):
+            raise ValueError("the Vlasov-Maxwell host mirror is periodic, with the standard boundary fill and no Krook layers")
         deck = _d.VMDeck(name, n, xlim, species, _f(params, "light_speed"), _f(params, "maxwell.avWeak", 0.0),
                          _f(params, "maxwell.avStrong", 0.0), em_ics, vel_ics, order=order, cfl=cfl)
     else:
         deck = _d.Deck(name, n, xlim, species, order=order, rk=rk, cfl=cfl)
+        deck.periodic, deck.use_new_bcs = periodic, use_new_bcs
+        if periodic != (True, True) and any(not sp.factorable for sp in species if sp.stream is None):
+            raise ValueError("non-periodic x / y needs factorable initial conditions (the inflow tables cover x / y ghosts)")
     # time-step controls of Simulation (Simulation.C:415-440); not part of the deck's physics, kept aside
     # Simulation's defaults (Simulation.C:166-181): final_time 1, save_times 1, sequence_write_times 1, max_step 0
     deck.run = dict(final_time=_f(params, "final_time", 1.0), save_times=_f(params, "save_times", 1.0),

@@ -54,6 +54,8 @@ class Runner:
             else:
                 capi.check(H.lk_vp_set_state(self.sys, s, f.ctypes.data), "lk_vp_set_state")
                 capi.check(deck.set_inflow(H, self.sys, s), "inflow")
+        if not self.vm:
+            capi.check(deck.apply_options(H, self.sys), "boundary options / Krook layers")
         if self.vm:
             em, vz = deck.initial_fields()
             capi.check(H.lk_vm_set_fields(self.sys, em.ctypes.data), "lk_vm_set_fields")

@@ -169,6 +169,11 @@ void ok_shaped_ramped_driver(double* em_vars, double* ext_efield, int n1d, int n
 typedef struct ok_vp_work ok_vp_work;
 ok_vp_work* ok_vp_work_create(int nspecies, const ok_species* sp, const double* xlo, const double* xhi);
 void ok_vp_work_destroy(ok_vp_work* w);
+/* options beyond the benchmark decks: non-periodic x / y (KineticSpecies.H:998-1031; the Poisson solve stays periodic,
+ * Poisson.C:147-152), use_new_bcs (VPSystem.C:819-821), a Krook layer nu(n1d,n2d) of species s (KineticSpecies.C:1049-1062) */
+void ok_vp_set_options(ok_vp_work* w, int nonperiodic_x, int nonperiodic_y, int use_new_bcs);
+void ok_vp_set_krook(ok_vp_work* w, int s, const double* nu);
+void ok_vp_set_dt(ok_vp_work* w, double dt);   /* the a_dt of a bare ok_vp_eval_rhs call (completeRHS) */
 /* rhs[s], f[s]: 4D arrays incl. ghosts; f's ghosts are modified like the reference does.
  * ke_e_dot[s] receives rhs.m_integrated_ke_e_dot for driven species. */
 void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double time, double* ke_e_dot, double* axmax,

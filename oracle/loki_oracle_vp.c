@@ -26,6 +26,12 @@ struct ok_vp_work {
   /* m_lambda_max[V1], [V2] as the last evalRHS left them (KineticSpecies.C:771-772): what stableDt sees
    * at the start of the next step (VPSystem.C:489-505) */
   double *last_ax, *last_ay;
+  /* deck options beyond the five benchmark decks: non-periodic x / y (setPhysicalBCs,
+   * KineticSpecies.H:998-1031), the "JB" boundary conditions (use_new_bcs, VPSystem.C:819-821) and a Krook layer per
+   * species (KineticSpecies.C:1049-1062); cur_dt: the a_dt the integrators hand to completeRHS */
+  int nonperiodic[2], use_new_bcs;
+  double** krook_nu;
+  double cur_dt;
 };
 
 static int64_t vol4(const ok_geom* g) { return ok_nd(g, 0) * ok_nd(g, 1) * ok_nd(g, 2) * ok_nd(g, 3); }
@@ -95,7 +101,7 @@ ok_vp_work* ok_vp_work_create(int ns, const ok_species* sp, const double* xlo, c
   memcpy(w->sp, sp, sizeof(ok_species) * ns);
   for (int k = 0; k < 2; ++k) { w->xlo[k] = xlo[k]; w->xhi[k] = xhi[k]; }
 #define PP(name) w->name = (double**)calloc(ns, sizeof(double*))
-  PP(velocities); PP(vxface); PP(vyface); PP(vel1); PP(vel2); PP(vel3); PP(vel4); PP(accel); PP(rho_s); PP(ext);
+  PP(velocities); PP(vxface); PP(vyface); PP(vel1); PP(vel2); PP(vel3); PP(vel4); PP(accel); PP(rho_s); PP(ext); PP(krook_nu);
   PP(rhs); PP(delta);
   for (int i = 0; i < 8; ++i) { PP(k[i]); w->ke_k[i] = (double*)calloc(ns, sizeof(double)); }
 #undef PP
@@ -150,6 +156,8 @@ void ok_vp_work_destroy(ok_vp_work* w) {
   }
   for (int i = 0; i < 8; ++i) { free(w->k[i]); free(w->ke_k[i]); }
   free(w->last_ax); free(w->last_ay);
+  for (int s = 0; s < w->ns; ++s) free(w->krook_nu[s]);
+  free(w->krook_nu);
   free(w->velocities); free(w->vxface); free(w->vyface); free(w->vel1); free(w->vel2); free(w->vel3);
   free(w->vel4); free(w->accel); free(w->ext); free(w->rho_s); free(w->rhs); free(w->delta); free(w->ke_rhs);
   free(w->ke_delta); free(w->rho); free(w->phi); free(w->em); free(w->sx); free(w->sy); free(w->sp);
@@ -158,6 +166,43 @@ void ok_vp_work_destroy(ok_vp_work* w) {
 
 const double* ok_vp_em_vars(const ok_vp_work* w) { return w->em; }
 const double* ok_vp_rho(const ok_vp_work* w) { return w->rho; }
+
+void ok_vp_set_options(ok_vp_work* w, int nonperiodic_x, int nonperiodic_y, int use_new_bcs) {
+  w->nonperiodic[0] = nonperiodic_x;
+  w->nonperiodic[1] = nonperiodic_y;
+  w->use_new_bcs = use_new_bcs;
+}
+void ok_vp_set_dt(ok_vp_work* w, double dt) { w->cur_dt = dt; }
+/* nu: (n1d,n2d) of species s (KrookLayer::initialize, KrookLayer.C:54-160), copied; NULL removes the layer */
+void ok_vp_set_krook(ok_vp_work* w, int s, const double* nu) {
+  const int64_t pl = ok_nd(&w->sp[s].g, 0) * ok_nd(&w->sp[s].g, 1);
+  free(w->krook_nu[s]);
+  w->krook_nu[s] = NULL;
+  if (nu) {
+    w->krook_nu[s] = (double*)malloc(sizeof(double) * pl);
+    memcpy(w->krook_nu[s], nu, sizeof(double) * pl);
+  }
+}
+/* fillAdvectionGhostCells on one rank (KineticSpecies.H:404-412, 998-1031): physical boundary conditions of the
+ * non-periodic directions, then the periodic wrap of the periodic ones */
+static void vp_fill_advection_ghosts(ok_vp_work* w, int s, double* f) {
+  const ok_species* sp = &w->sp[s];
+  const int xper = !w->nonperiodic[0], yper = !w->nonperiodic[1];
+  if (!xper || !yper) {
+    if (w->use_new_bcs)
+      ok_set_advection_bcs_4d_jb(f, &sp->g, w->vel1[s], w->vel2[s], 1, 1, 1, 1, xper, yper, sp->ic, sp->ic_ctx);
+    else
+      ok_set_advection_bcs_4d(f, &sp->g, w->vel1[s], w->vel2[s], 1, 1, 1, 1, xper, yper, sp->ic, sp->ic_ctx);
+  }
+  ok_periodic_fill_4d(f, &sp->g, xper, yper);
+}
+static void vp_set_acceleration_bcs(ok_vp_work* w, int s, double* f) {
+  const ok_species* sp = &w->sp[s];
+  if (w->use_new_bcs)
+    ok_set_acceleration_bcs_4d_jb(f, &sp->g, w->vel3[s], w->vel4[s], 1, 1, 1, 1, sp->ic, sp->ic_ctx);
+  else
+    ok_set_acceleration_bcs_4d(f, &sp->g, w->vel3[s], w->vel4[s], 1, 1, 1, 1, sp->ic, sp->ic_ctx);
+}
 
 /* VPSystem::evalRHS on one rank */
 void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double time, double* ke_e_dot, double* axmax, double* aymax) {
@@ -183,7 +228,7 @@ void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double time, double
     const ok_species* sp = &w->sp[s];
     const ok_geom* g = &sp->g;
     /* 3. ghost fill + advection derivatives (KineticSpecies.H:404-412, 489-507) */
-    ok_periodic_fill_4d(f[s], g, 1, 1);
+    vp_fill_advection_ghosts(w, s, f[s]);
     ok_advection_derivatives_4d(rhs[s], f[s], g, w->vel1[s], w->vel2[s]);
     /* 4. acceleration (KineticSpecies.C:697-774): expansion, drivers, *= q/m, face accelerations */
     for (int64_t k = 0; k < 2 * pl; ++k) w->accel[s][k] = w->em[k];
@@ -199,8 +244,10 @@ void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double time, double
     w->last_ax[s] = axmax[s];
     w->last_ay[s] = aymax[s];
     /* 5. v-boundary fill, acceleration derivatives, completeRHS */
-    ok_set_acceleration_bcs_4d(f[s], g, w->vel3[s], w->vel4[s], 1, 1, 1, 1, sp->ic, sp->ic_ctx);
+    vp_set_acceleration_bcs(w, s, f[s]);
     ok_acceleration_derivatives_4d(rhs[s], f[s], g, w->vel3[s], w->vel4[s]);
+    /* completeRHS (KineticSpecies.C:1024-1093): Krook layer, then the driver's energy input rate */
+    if (w->krook_nu[s]) ok_append_krook(rhs[s], f[s], g, w->krook_nu[s], w->cur_dt, sp->ic, sp->ic_ctx);
     if (sp->has_driver && ke_e_dot)
       ke_e_dot[s] = ok_compute_ke_e_dot(g, f[s], sp->charge, w->velocities[s], w->ext[s], 0.0);
   }
@@ -224,10 +271,10 @@ void ok_vp_ke_flux_history(ok_vp_work* w, double** f, double* out) {
       face[d] = (double*)calloc(len[d], sizeof(double));
       flux[d] = (double*)calloc(len[d], sizeof(double));
     }
-    ok_periodic_fill_4d(f[s], g, 1, 1);
+    vp_fill_advection_ghosts(w, s, f[s]);
     ok_face_fluxes_4d(flux[0], face[0], f[s], g, vel[0], 0);
     ok_face_fluxes_4d(flux[1], face[1], f[s], g, vel[1], 1);
-    ok_set_acceleration_bcs_4d(f[s], g, w->vel3[s], w->vel4[s], 1, 1, 1, 1, sp->ic, sp->ic_ctx);
+    vp_set_acceleration_bcs(w, s, f[s]);
     ok_face_fluxes_4d(flux[2], face[2], f[s], g, vel[2], 2);
     ok_face_fluxes_4d(flux[3], face[3], f[s], g, vel[3], 3);
     for (int dir = 0; dir < 4; ++dir)
@@ -248,6 +295,7 @@ void ok_vp_rk4_step(ok_vp_work* w, double** f_new, double** f_old, double time, 
   const double w_eval[4] = {dtOn6, dtOn3, dtOn3, dtOn6};
   const double w_upd[4] = {dtOn2, dtOn2, dt, 1.0};
   const double t_stage[4] = {time, time + dtOn2, time + dtOn2, time + dt};
+  w->cur_dt = dt;
   double* ax = (double*)calloc(w->ns, sizeof(double));
   double* ay = (double*)calloc(w->ns, sizeof(double));
   double* ke_old = (double*)calloc(w->ns, sizeof(double));
@@ -295,6 +343,7 @@ void ok_vp_rk6_step(ok_vp_work* w, double** f_new, double** f_old, double time, 
        {-5101675.0/1767592.0, 112077.0/25994.0, 334875.0/441898.0, -973617.0/883796.0, -1421.0/1394.0, 333.0/5576.0, 36.0/41.0, 0.0}};
   static const double b[8] = {41.0/840.0, 0.0, 9.0/35.0, 9.0/280.0, 34.0/105.0, 9.0/280.0, 9.0/35.0, 41/840.0};
   static const double c[8] = {0.0, 1.0/9.0, 1.0/6.0, 1.0/3.0, 1.0/2.0, 2.0/3.0, 5.0/6.0, 1.0};
+  w->cur_dt = dt;
   double* ax = (double*)calloc(w->ns, sizeof(double));
   double* ay = (double*)calloc(w->ns, sizeof(double));
   double* ke_old = (double*)calloc(w->ns, sizeof(double));

@@ -103,6 +103,9 @@ def load():
     L.ok_vp_rk4_step.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), d, d, dp]
     L.ok_vp_rk6_step.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), d, d, dp]
     L.ok_vp_last_accel_max.argtypes = [C.c_void_p, dp, dp]
+    L.ok_vp_set_options.argtypes = [C.c_void_p, i, i, i]
+    L.ok_vp_set_krook.argtypes = [C.c_void_p, i, dp]
+    L.ok_vp_set_dt.argtypes = [C.c_void_p, d]
     L.ok_vp_ke_flux_history.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), dp]
     L.ok_vp_stable_dt.restype = d
     L.ok_vp_stable_dt.argtypes = [C.c_void_p, dp, dp, i]

@@ -322,7 +322,9 @@ def test_pp_reader_rejects_physics_it_does_not_implement():
     for extra in ("kinetic_species.1.num_collision_operators = 1\n",
                   "kinetic_species.1.collision_operator.1.name = \"Pitch Angle Collision Operator\"\n",
                   "kinetic_species.1.tz.name = \"TrigTZSource\"\n",
-                  "kinetic_species.1.krook.power = 3\n",
+                  "kinetic_species.1.krook.x1a = 0.0\n",      # a Krook layer / JB fills / open boundaries on the Vlasov-Maxwell mirror
+                  "kinetic_species.1.external_dist_krook.x1a = 0.0\n",
+                  "periodic_dir = false true\n",
                   "kinetic_species.1.ic.vflowinitx = 0.3\n",
                   "kinetic_species.1.num_external_drivers = 2\n",
                   "kinetic_species.1.external_driver.1.shape_type = \"gauss\"\n",
@@ -342,6 +344,51 @@ def test_pp_reader_rejects_physics_it_does_not_implement():
     minimal = "\n".join(l for l in base.splitlines() if not l.startswith("cfl"))
     d = pp.deck_from_params(pp.parse(minimal))
     assert d.cfl == 0.9 and d.run["max_step"] == 0 and d.run["sequence_write_times"] == 1.0
+
+
+VP_OPTIONS_DECK = """
+domain_limits = -10. 10. -30. 30.
+N = 12 6
+periodic_dir = false true
+use_new_bcs = true
+number_of_species = 1
+kinetic_species.1.name = "electron"
+kinetic_species.1.velocity_limits = -7 7 -7 7
+kinetic_species.1.Nv = 20 12
+kinetic_species.1.mass = 1.0
+kinetic_species.1.charge = -1.0
+kinetic_species.1.ic.name = "Perturbed Maxwellian"
+kinetic_species.1.krook.x1a = -6.0
+kinetic_species.1.krook.x1b = 7.0
+kinetic_species.1.krook.coefficient = 0.5
+kinetic_species.1.krook.power = 3
+"""
+
+
+def test_pp_reader_boundary_options_and_krook_layer():
+    """periodic_dir, use_new_bcs and kinetic_species.N.krook.* reach the deck; the layer profile is
+    KrookLayer::initialize's (KrookLayer.C:54-160): zero between x1a and x1b, the order's polynomial ramp to
+    `coefficient` at the domain ends, ghosts zero"""
+    from loki_b200 import pp
+    d = pp.deck_from_params(pp.parse(VP_OPTIONS_DECK), name="opts")
+    assert d.periodic == (False, True) and d.use_new_bcs
+    assert d.species[0].krook == dict(x1a=-6.0, x1b=7.0, coefficient=0.5, power=3.0)
+    nu = d.krook_nu(d.species[0])
+    ng = d.ng
+    assert nu.shape == (6 + 2 * ng, 12 + 2 * ng) and not nu[:ng].any() and not nu[:, :ng].any() and not nu[:, -ng:].any()
+    x = -10.0 + (np.arange(12) + 0.5) * (20.0 / 12)
+    inner = nu[ng:-ng, ng:-ng]
+    assert np.all(inner[:, (x > -6.0) & (x < 7.0)] == 0.0) and np.all(inner[:, x < -6.0] > 0.0) and np.all(inner[:, x > 7.0] > 0.0)
+    assert np.all(inner == inner[0]) and inner.max() < 0.5
+    e = (x[0] + 6.0) / (-10.0 + 6.0)
+    assert inner[0, 0] == 0.5 * (-pow(e, 4) * (20.0 * pow(e, 3) - 70.0 * pow(e, 2) + 84.0 * e - 35.0))
+    # a tile of a decomposed run sees its own window of the same profile
+    t = d.krook_nu(d.species[0], tile_lo=(6, 3), tile_n=(6, 3))
+    assert np.array_equal(t[ng:-ng, ng:-ng], inner[3:6, 6:12])
+    # no layer end given: no layer (KrookLayer.C:171-189)
+    d2 = pp.deck_from_params(pp.parse(VP_OPTIONS_DECK.replace("kinetic_species.1.krook.x1a = -6.0\n", "").replace(
+        "kinetic_species.1.krook.x1b = 7.0\n", "")))
+    assert d2.species[0].krook is None and d2.krook_nu(d2.species[0]) is None
 
 
 def _deck_fields(a, b, path=""):

@@ -18,6 +18,12 @@ def _oracle(ok, deck):
     xlo = (C.c_double * 2)(deck.xlim[0], deck.xlim[2])
     xhi = (C.c_double * 2)(deck.xlim[1], deck.xlim[3])
     w = ok.ok_vp_work_create(len(deck.species), sp, C.byref(xlo), C.byref(xhi))
+    # deck options beyond the benchmark decks: open boundaries, the JB fills, Krook layers
+    ok.ok_vp_set_options(w, int(not deck.periodic[0]), int(not deck.periodic[1]), int(deck.use_new_bcs))
+    for s_, sp_ in enumerate(deck.species):
+        nu = deck.krook_nu(sp_)
+        if nu is not None:
+            ok.ok_vp_set_krook(w, s_, np.ascontiguousarray(nu).ravel())
     return w, sp, keep
 
 
@@ -34,6 +40,7 @@ def _product(deck, states, tables):
     for s, f in enumerate(states):
         assert H.lk_vp_set_state(sys_, s, f.ctypes.data) == 0
         assert deck.set_inflow(H, sys_, s) == 0      # the inflow tables in the form the species' IC class has
+    assert deck.apply_options(H, sys_) == 0
     return H, sys_
 
 
@@ -144,6 +151,92 @@ def test_one_step_matches_oracle(lk, ok, mk, mode):
         ok.ok_vp_work_destroy(w)
     finally:
         lk.lk_set_strict(old)
+
+
+def _opt(deck, periodic=(True, True), jb=False, krook=None):
+    deck.periodic, deck.use_new_bcs = periodic, jb
+    if krook:
+        for sp_ in deck.species:
+            sp_.krook = dict(krook)
+    return deck
+
+
+OPTION_DECKS = {
+    # completeRHS's Krook layer (KineticSpecies.C:1049-1062): damping towards the IC in the outer thirds of x
+    "krook": lambda: _opt(decks.plane_epw(n=(16, 8), nv=(32, 16)), krook=dict(x1a=-3.0, x1b=3.0, coefficient=0.3)),
+    "krook_rk6": lambda: _opt(decks.plane_iaw(n=(10, 10), nv=(16, 10), order=6, rk=6), krook=dict(x2a=-100.0, x1b=4.0)),
+    # use_new_bcs (VPSystem.C:819-821): the JB velocity-boundary fill
+    "jb": lambda: _opt(decks.plane_iaw(n=(12, 10), nv=(16, 12)), jb=True),
+    # open boundaries in x, in y, in both with the JB advection fill (KineticSpecies.H:998-1031)
+    "open_x": lambda: _opt(decks.plane_epw(n=(16, 8), nv=(32, 16)), periodic=(False, True)),
+    "open_y": lambda: _opt(decks.plane_iaw(n=(12, 10), nv=(16, 12)), periodic=(True, False)),
+    "open_xy_jb_krook": lambda: _opt(decks.plane_epw(n=(16, 8), nv=(32, 16)), periodic=(False, False), jb=True,
+                                     krook=dict(x1a=-4.0, coefficient=0.5)),
+}
+
+
+@pytest.mark.parametrize("mode", ["strict", "production"])
+@pytest.mark.parametrize("name", sorted(OPTION_DECKS))
+def test_deck_options_steps_match_oracle(lk, ok, name, mode):
+    """Krook layers, the JB boundary conditions and open x / y boundaries wired into the stage loop: three RK steps
+    against the oracle (whose pieces are pinned to the reference Fortran).  Strict: the distribution bit for bit;
+    production: within 1e-12 of the stencil neighbourhood per step taken."""
+    deck = OPTION_DECKS[name]()
+    old = lk.lk_set_strict(1 if mode == "strict" else 0)
+    try:
+        w, sp, keep = _oracle(ok, deck)
+        states, tables = [], []
+        for k, s in enumerate(deck.species):
+            f, fx, fv, fnorm = deck.initial_state(s)
+            states.append(_perturb(f, 70 + k, amp=0.02))
+            tables.append((fx, fv, fnorm))
+        ns = len(states)
+        H, sys_ = _product(deck, states, tables)
+        f_old = [s.copy() for s in states]
+        f_new = [np.zeros_like(s) for s in states]
+        ke = np.zeros(ns)
+        t, dt = 0.25, 0.02
+        ng = deck.ng
+        I = (slice(ng, -ng),) * 4
+        for step in range(3):
+            (ok.ok_vp_rk4_step if deck.rk == 4 else ok.ok_vp_rk6_step)(w, _ptrs(f_new), _ptrs(f_old), t, dt, ke)
+            assert H.lk_vp_set_time(sys_, t) == 0
+            assert H.lk_vp_advance(sys_, dt) == 0, H.lk_last_error()
+            t += dt
+            f_old, f_new = f_new, f_old
+            for s in range(ns):
+                out = np.empty_like(states[s])
+                assert H.lk_vp_get_state(sys_, s, out.ctypes.data) == 0
+                if mode == "strict":
+                    assert np.array_equal(out[I], f_old[s][I]), (step, s)
+                else:
+                    assert star_rel_err(out, f_old[s], np.maximum(np.abs(states[s]), np.abs(f_old[s])), ng) <= (step + 1) * 1e-12
+        H.lk_vp_destroy(sys_)
+        ok.ok_vp_work_destroy(w)
+    finally:
+        lk.lk_set_strict(old)
+
+
+def test_deck_options_change_the_answer(lk, ok, fast):
+    """the options are not no-ops: each deck above differs from its plain periodic twin after one step"""
+    for name in sorted(OPTION_DECKS):
+        outs = []
+        for plain in (False, True):
+            deck = OPTION_DECKS[name]()
+            if plain:
+                deck.periodic, deck.use_new_bcs = (True, True), False
+                for sp_ in deck.species:
+                    sp_.krook = None
+            states = [_perturb(deck.initial_state(s)[0], 70 + k, amp=0.02) for k, s in enumerate(deck.species)]
+            H, sys_ = _product(deck, states, None)
+            assert H.lk_vp_set_time(sys_, 0.25) == 0 and H.lk_vp_advance(sys_, 0.02) == 0
+            out = np.empty_like(states[0])
+            assert H.lk_vp_get_state(sys_, 0, out.ctypes.data) == 0
+            outs.append(out)
+            H.lk_vp_destroy(sys_)
+        ng = 3 if "rk6" in name else 2
+        I = (slice(ng, -ng),) * 4
+        assert not np.array_equal(outs[0][I], outs[1][I]), name
 
 
 SMOOTH_DECKS = [
