@@ -106,6 +106,12 @@ typedef struct lk_rk_update {
                              rewritten nor invalidated (lk_vlasov_stage_folds_bcs tells whether a given call does this).
                              0, or a call the pipelined kernel does not take: lk_set_acceleration_bcs_4d runs on f first and
                              WRITES f's velocity ghosts (f is then no longer preset) */
+  int tile_set;           /* 0: the whole box.  1: only the CTA tiles (32 x 8 cells in x, y) that touch a face of a
+                             direction named in cut_dirs; 2: only the others.  The two launches together equal one launch
+                             with 0, bit for bit; a rank of a decomposed run issues 1, starts the halo exchange of pred, then
+                             issues 2.  Pipelined kernel only: lk_vlasov_stage_can_split tells, other calls fail with
+                             LK_ERR_UNSUPPORTED */
+  int cut_dirs;           /* with tile_set: bit 0 x, bit 1 y */
 } lk_rk_update;
 
 /* ---- library ---- */
@@ -203,6 +209,8 @@ int lk_vlasov_stage(double* rhs_out, const double* f, const lk_geom* g, const do
  * them (RK4Integrator.H:149-171, RK6Integrator.H:96-131), on the interior.  For callers that modify the rhs between its
  * evaluation and the update (completeRHS's Krook layer, KineticSpecies.C:1049-1062).  upd->wrap is ignored. */
 int lk_rk_stage_update(const double* rhs, const lk_geom* g, const lk_rk_update* upd, void* stream);
+/* 1 when lk_vlasov_stage(rhs_out, ., g, ., a, upd, ...) honours upd->tile_set (it takes the pipelined kernel) */
+int lk_vlasov_stage_can_split(const double* rhs_out, const lk_geom* g, const lk_accel* a, const lk_rk_update* upd);
 /* 1 when lk_vlasov_stage(rhs_out, ., g, ., a, upd, ...) would fold upd->accel_bcs into the pipelined kernel (f's velocity
  * ghosts stay as they are), 0 when it would run lk_set_acceleration_bcs_4d on f first */
 int lk_vlasov_stage_folds_bcs(const double* rhs_out, const lk_geom* g, const lk_accel* a, const lk_rk_update* upd);

@@ -119,6 +119,13 @@ int lk_vp_stage_finish(lk_vp_system* sys, int stage);
 /* the same for one species: lets the caller start the halo exchange of species s's new predictor
  * (lk_vp_eval_ptr(s) after this call) on another stream while the next species' stage kernel runs */
 int lk_vp_stage_finish_species(lk_vp_system* sys, int stage, int s);
+/* ... and in two launches, so that a species' own halo exchange overlaps its own stage kernel: part 1 runs the stage
+ * with the kernel restricted to the CTA tiles on a face of a cut direction (everything a neighbour needs of the new
+ * predictor; lk_vp_eval_ptr(s) is the new predictor from here on), part 2 launches the remaining tiles.  Between the two
+ * the caller queues the exchange on another stream behind an event recorded after part 1.  When the stage cannot be
+ * split (strict arithmetic, unaligned tiles, Krook species: not the pipelined kernel) part 1 is the whole stage and
+ * part 2 is a no-op: the caller's sequence stays the same. */
+int lk_vp_stage_finish_species_part(lk_vp_system* sys, int stage, int s, int part);
 int lk_vp_end_step(lk_vp_system* sys);
 
 /* reference-ordered, UNFUSED evaluation of one RHS (VPSystem::evalRHS) of the current state into

@@ -44,7 +44,8 @@ class RkUpdate(C.Structure):
     _fields_ = [("f_old", C.c_void_p), ("delta_in", C.c_void_p), ("delta_out", C.c_void_p),
                 ("pred", C.c_void_p), ("w_delta", C.c_double), ("c_pred", C.c_double),
                 ("use_delta", C.c_int), ("n_prev", C.c_int), ("k_prev", C.c_void_p * 7),
-                ("c_prev", C.c_double * 7), ("wrap", C.c_int), ("accel_bcs", C.c_void_p), ("inflow_preset", C.c_int)]
+                ("c_prev", C.c_double * 7), ("wrap", C.c_int), ("accel_bcs", C.c_void_p), ("inflow_preset", C.c_int),
+                ("tile_set", C.c_int), ("cut_dirs", C.c_int)]
 
 
 class StageMoments(C.Structure):
@@ -77,6 +78,7 @@ _PROTOS = {
     "lk_ke_flux_boundaries": (C.c_int, [_vp, _vp, C.POINTER(Geom), _vp, C.POINTER(Accel), C.c_double, C.POINTER(C.c_int * 8), _vp]),
     "lk_preset_inflow_ghosts_4d": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Inflow), _vp]),
     "lk_rk_stage_update": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(RkUpdate), _vp]),
+    "lk_vlasov_stage_can_split": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Accel), C.POINTER(RkUpdate)]),
     "lk_vlasov_stage_folds_bcs": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Accel), C.POINTER(RkUpdate)]),
     "lk_periodic_fill_4d": (C.c_int, [_vp, C.POINTER(Geom), C.c_int, C.c_int, _vp]),
     "lk_set_acceleration_bcs_4d_jb": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(Accel), C.POINTER(Inflow),

@@ -280,6 +280,10 @@ static int stage_impl(double* rhs_out, const double* f, const lk_geom* g, const 
   cudaStream_t st = (cudaStream_t)stream;
   // setaccelerationbcs4d_ on behalf of the caller: folded into the pipelined kernel's boundary tiles, or run here
   lk_rk_update upd_local;
+  if (upd && upd->tile_set) {
+    if (upd->tile_set < 0 || upd->tile_set > 2 || !(upd->cut_dirs & 3)) return fail(LK_ERR_ARG, "lk_vlasov_stage: bad tile_set / cut_dirs");
+    if (!lk_vlasov_stage_can_split(rhs_out, g, a, upd)) return fail(LK_ERR_UNSUPPORTED, "lk_vlasov_stage: tile_set needs the pipelined kernel");
+  }
   if (upd && upd->accel_bcs) {
     if (!lk_vlasov_stage_folds_bcs(rhs_out, g, a, upd)) {
       const int at[4] = {1, 1, 1, 1};
@@ -312,6 +316,10 @@ int lk_rk_stage_update(const double* rhs, const lk_geom* g, const lk_rk_update* 
   if (upd->n_prev < 0 || upd->n_prev > 7) return fail(LK_ERR_ARG, "lk_rk_stage_update: n_prev out of range");
   if (upd->use_delta && !upd->delta_in) return fail(LK_ERR_ARG, "lk_rk_stage_update: use_delta needs delta_in");
   CHECK_LAUNCH(DISPATCH(rk_stage_update)(rhs, g, upd, (cudaStream_t)stream), "lk_rk_stage_update");
+}
+int lk_vlasov_stage_can_split(const double* rhs_out, const lk_geom* g, const lk_accel* a, const lk_rk_update* upd) {
+  if (!g || !a || !upd || g_strict) return 0;
+  return lkfast::stage_uses_pipe(g, a, upd, const_cast<double*>(rhs_out), 3, g_variant) ? 1 : 0;
 }
 int lk_vlasov_stage_folds_bcs(const double* rhs_out, const lk_geom* g, const lk_accel* a, const lk_rk_update* upd) {
   if (!g || !a || !upd || !upd->accel_bcs || g_strict) return 0;

@@ -216,6 +216,12 @@ struct KineticSpecies {
   int nonperiodic = 0;              // bit 0 x, bit 1 y
   int at_xy[4] = {1, 1, 1, 1};      // this rank's tile touches x-lo, x-hi, y-lo, y-hi of the domain
   bool preset[3] = {false, false, false};
+  // a stage launched for the cut-face tiles only (stageFinish part 1): what part 2 needs to launch the rest
+  bool pending = false, pending_mom = false;
+  lk_rk_update pending_u;
+  lk_accel pending_a;
+  double* pending_rhs = nullptr;
+  const double* pending_f = nullptr;
   int arrayIndex(const double* p) const { return (p == farr[0].p) ? 0 : ((p == farr[1].p) ? 1 : 2); }
   void forgetPresets() { preset[0] = preset[1] = preset[2] = false; }
 
@@ -495,7 +501,21 @@ struct VPSystem {
   // ---- RK4Integrator::stageAdvance / RK6 stage, fused behind the RHS evaluation ----
   // `only`: restrict to one species (the multi-rank driver interleaves the species' halo exchanges with
   // the other species' stage kernels); nullptr = all species in order
-  int stageFinish(int stage, KineticSpecies* only = nullptr) {
+  // `part`: 0 = the whole stage.  1 / 2 = the same in two launches for a rank whose configuration space is cut: 1 does
+  // everything but restricts the stage kernel to the tiles on a cut face (lk_rk_update.tile_set), so that the caller
+  // can start the halo exchange of the new predictor; 2 launches the remaining tiles.  When the kernel cannot split
+  // (not the pipelined instantiation) part 1 is the whole stage and part 2 does nothing.
+  int stageFinish(int stage, KineticSpecies* only = nullptr, int part = 0) {
+    if (part == 2) {
+      for (auto* ks : species) {
+        if ((only && ks != only) || !ks->pending) continue;
+        ks->pending = false;
+        ks->pending_u.tile_set = 2;
+        LKH_CHECK(lk_vlasov_stage(ks->pending_rhs, ks->pending_f, &ks->g, ks->velocities.p, &ks->pending_a, &ks->pending_u,
+                                  ks->pending_mom ? &ks->mom : nullptr, st));
+      }
+      return LK_OK;
+    }
     const bool rk4 = desc.rk_order == 4;
     const int last = nstages() - 1;
     static const double A6[8][8] = {
@@ -597,6 +617,17 @@ struct VPSystem {
         } else {
           u.inflow_preset = 0;     // the stage runs the separate fill: f_eval's ghosts get the extrapolations as well
           ks->preset[ie] = false;
+        }
+        const int cut = 3 & ~uncutDirs();
+        if (part == 1 && cut && lk_vlasov_stage_can_split(rhs_out, &ks->g, &a, &u)) {
+          u.tile_set = 1;
+          u.cut_dirs = cut;
+          ks->pending = true;
+          ks->pending_u = u;
+          ks->pending_a = a;
+          ks->pending_rhs = rhs_out;
+          ks->pending_f = ks->f_eval;
+          ks->pending_mom = fused_moments;
         }
         LKH_CHECK(lk_vlasov_stage(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, fused_moments ? &ks->mom : nullptr, st));
       }
@@ -1159,6 +1190,10 @@ int lk_vp_stage_finish(lk_vp_system* h, int stage) {
 int lk_vp_stage_finish_species(lk_vp_system* h, int stage, int s) {
   if (!h || stage < 0 || stage >= h->sys.nstages() || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
   return h->sys.stageFinish(stage, h->sys.species[s]);
+}
+int lk_vp_stage_finish_species_part(lk_vp_system* h, int stage, int s, int part) {
+  if (!h || stage < 0 || stage >= h->sys.nstages() || s < 0 || s >= (int)h->sys.species.size() || part < 1 || part > 2) return LK_ERR_ARG;
+  return h->sys.stageFinish(stage, h->sys.species[s], part);
 }
 int lk_vp_end_step(lk_vp_system* h) { return h ? h->sys.endStep() : LK_ERR_ARG; }
 int lk_vp_eval_rhs(lk_vp_system* h, double** rhs_dev, double time) { return (h && rhs_dev) ? h->sys.evalRHS(rhs_dev, time) : LK_ERR_ARG; }

@@ -561,7 +561,8 @@ cudaError_t vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const
     if (!no_pipe && variant == 0 && pipe_eligible(d, da, du, rhs_out, flags)) {
       bool used = false;
       // velocity-boundary fill folded into the boundary tiles: f's ghosts hold the inflow sample (k_preset_inflow)
-      const int bcfold = (LK_PIPE_FOLD && upd && upd->accel_bcs && upd->inflow_preset) ? 3 : 0;
+      int bcfold = (LK_PIPE_FOLD && upd && upd->accel_bcs && upd->inflow_preset) ? 3 : 0;
+      if (upd && upd->tile_set) bcfold |= ((upd->tile_set & 3) << 4) | ((upd->cut_dirs & 3) << 6);
       cudaError_t e = (d.order == 4) ? launch_pipe<4>(d, f, velocities, da, du, dm, bcfold, st, &used)
                                      : launch_pipe<6>(d, f, velocities, da, du, dm, bcfold, st, &used);
       if (used) {
@@ -570,6 +571,7 @@ cudaError_t vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const
       }
     }
 #endif
+    if (upd && upd->tile_set) return cudaErrorNotSupported;   // tile subsets exist in the pipelined kernel only
     cudaError_t e = launch_stage_march(d, f, velocities, da, du, rhs_out, flags, dm, st);
     if (e == cudaSuccess) ++g_launches;
     return e;
@@ -582,17 +584,26 @@ cudaError_t vlasov_rhs(double* rhs_out, const double* f, const lk_geom* g, const
   return LK_LAUNCHED();
 }
 int stage_moment_parts(const lk_geom* g) { return march_moment_parts(make_geo(g)); }
-bool stage_folds_bcs(const lk_geom* g, const lk_accel* a, const lk_rk_update* upd, double* rhs_out, int flags, int variant) {
+bool stage_uses_pipe(const lk_geom* g, const lk_accel* a, const lk_rk_update* upd, double* rhs_out, int flags, int variant) {
 #if LK_STRICT
   (void)g; (void)a; (void)upd; (void)rhs_out; (void)flags; (void)variant;
   return false;
 #else
   static const bool no_pipe = getenv("LK_NO_PIPE") != nullptr;
-  if (no_pipe || variant != 0 || !a || !upd || !upd->inflow_preset) return false;
+  if (no_pipe || variant != 0 || !a || !upd) return false;
   DGeo d = make_geo(g);
   // the TMA path needs a 16-byte aligned array base and an even row length (get_map); every cudaMalloc'ed array has them
+  return pipe_eligible(d, make_accel(a), make_upd(upd), rhs_out, flags) && (d.nd[0] % 2 == 0);
+#endif
+}
+bool stage_folds_bcs(const lk_geom* g, const lk_accel* a, const lk_rk_update* upd, double* rhs_out, int flags, int variant) {
+#if LK_STRICT
+  (void)g; (void)a; (void)upd; (void)rhs_out; (void)flags; (void)variant;
+  return false;
+#else
   // ... and the extrapolations of the two ends of the march must not feed each other
-  return LK_PIPE_FOLD && pipe_eligible(d, make_accel(a), make_upd(upd), rhs_out, flags) && (d.nd[0] % 2 == 0) && d.n[3] >= 2 * d.ng;
+  return LK_PIPE_FOLD && upd && upd->inflow_preset && stage_uses_pipe(g, a, upd, rhs_out, flags, variant) &&
+         g->n[3] >= 2 * g->ng;
 #endif
 }
 #if defined(LK_PIPE_TRACE) && !LK_STRICT

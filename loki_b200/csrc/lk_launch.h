@@ -29,6 +29,7 @@
   cudaError_t rk_stage_update(const double* rhs, const lk_geom* g, const lk_rk_update* upd, cudaStream_t st); \
   cudaError_t preset_inflow(double* f, const lk_geom* g, const lk_inflow* ic, cudaStream_t st);       \
   /* true when vlasov_rhs would take the pipelined kernel (which folds upd->accel_bcs into its boundary tiles) */ \
+  bool stage_uses_pipe(const lk_geom* g, const lk_accel* a, const lk_rk_update* upd, double* rhs_out, int flags, int variant); \
   bool stage_folds_bcs(const lk_geom* g, const lk_accel* a, const lk_rk_update* upd, double* rhs_out, int flags, int variant); \
   int stage_moment_parts(const lk_geom* g);                                                           \
   cudaError_t moments_finish(double* d0, double* d1, double* d2, const double* part, int nparts,      \

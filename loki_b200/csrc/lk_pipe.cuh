@@ -261,6 +261,14 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
     o1 = (jy * gy + r % hy) * T1;
     o2 = (jv * gv + r / hy) * T2;
   }
+  // tile subsets (bcfold bits 4-5: 1 = only the tiles on a face of a cut direction, 2 = only the others; bits 6-7: the
+  // cut directions, 1 x, 2 y): a rank whose configuration space is cut launches the face tiles first, so that the halo
+  // exchange of the new predictor travels while the remaining tiles are still being computed
+  if (bcfold & 0x30) {
+    const int cutd = (bcfold >> 6) & 3;
+    const bool face = ((cutd & 1) && (o0 == 0 || o0 + T0 == g.n[0])) || ((cutd & 2) && (o1 == 0 || o1 + T1 == g.n[1]));
+    if (face != (((bcfold >> 4) & 3) == 1)) return;
+  }
   const int chunk = b;
   const int q0 = chunk * chunk_len;              // first interior vy plane of this CTA
   const int nq = min(chunk_len, g.n[3] - q0);

@@ -287,9 +287,11 @@ class DistributedVP:
                     self._start_exchange(s)       # first stage after a state upload
                 if self.comm_stream is not None:
                     self.main_stream.wait_event(self.ev_halo[s])
-                capi.check(H.lk_vp_stage_finish_species(self.sys, stage, s), "lk_vp_stage_finish_species")
-                # the new predictor's faces leave now, under the next species' stage kernel
+                # the stage kernel in two launches: the tiles on the cut faces first, then the new predictor's faces
+                # leave (second stream) under the launch of the remaining tiles and the next species' stage kernel
+                capi.check(H.lk_vp_stage_finish_species_part(self.sys, stage, s, 1), "lk_vp_stage_finish_species_part")
                 self._start_exchange(s)
+                capi.check(H.lk_vp_stage_finish_species_part(self.sys, stage, s, 2), "lk_vp_stage_finish_species_part")
         capi.check(H.lk_vp_end_step(self.sys), "lk_vp_end_step")
 
     def synchronize(self):

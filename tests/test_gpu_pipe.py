@@ -16,7 +16,7 @@ def chk(lk, status, what):
     assert status == 0, "%s: %s" % (what, lk.lk_last_error().decode())
 
 
-def _stage(lk, d, s, stage, nmom, wrap, variant, seed=5, bcs=None, f=None, preset=False):
+def _stage(lk, d, s, stage, nmom, wrap, variant, seed=5, bcs=None, f=None, preset=False, tile_sets=None, cut=0):
     """one RK4-shaped fused stage; returns (pred, delta, moment partials, pipelined launches used)"""
     import torch
     import loki_b200 as lkm
@@ -41,8 +41,10 @@ def _stage(lk, d, s, stage, nmom, wrap, variant, seed=5, bcs=None, f=None, prese
         m.nmom, m.partial, m.capacity = nmom, part.data_ptr(), part.numel()
     old = lk.lk_set_rhs_variant(variant)
     before = lk.lk_pipe_launch_count()
-    chk(lk, lk.lk_vlasov_stage(None, f.data_ptr(), C.byref(d.g), d.velocities.data_ptr(), C.byref(d.accel), C.byref(u),
-                               C.byref(m) if m else None, None), "stage")
+    for ts in (tile_sets or (0,)):
+        u.tile_set, u.cut_dirs = ts, cut
+        chk(lk, lk.lk_vlasov_stage(None, f.data_ptr(), C.byref(d.g), d.velocities.data_ptr(), C.byref(d.accel), C.byref(u),
+                                   C.byref(m) if m else None, None), "stage")
     torch.cuda.synchronize()
     used = lk.lk_pipe_launch_count() - before
     lk.lk_set_rhs_variant(old)
@@ -181,3 +183,47 @@ def test_pipe_folds_the_velocity_boundary_fill(lk, ok, fast, n, order, stage, ki
         f2 = d.f.clone()
         pc, dc, mc, used_c = _stage(lk, d, s, stage, 3, 3, variant, bcs=ic, f=f2, preset=preset)
         assert used_c == (1 if variant == 0 else 0) and torch.equal(pc, pb) and torch.equal(mc, mb) and torch.equal(f2, f_ref)
+
+
+@pytest.mark.parametrize("cut", [1, 2, 3])
+@pytest.mark.parametrize("stage", [1, 2, 4])
+@pytest.mark.parametrize("n,order", [((96, 24, 16, 12), 4), ((64, 16, 24, 18), 6), ((32, 8, 8, 9), 4)])
+def test_pipe_tile_subsets_add_up_to_one_launch(lk, ok, fast, n, order, stage, cut):
+    """lk_rk_update.tile_set: the tiles on the faces of the cut directions, then the others (or the other way round)
+    leave the same predictor, increment (stages 2-3 update it in place: a tile done twice would show) and moment
+    partials as one launch over the whole box; the first launch alone leaves the rest untouched"""
+    import torch
+    s = Setup(ok, n, order, rough=0.3)
+    d = Dev(lk, s)
+    chk(lk, lk.lk_periodic_fill_4d(d.f.data_ptr(), C.byref(d.g), 1, 1, None), "per")
+    ic, keep = _inflow(d, s, 1)
+    chk(lk, lk.lk_preset_inflow_ghosts_4d(d.f.data_ptr(), C.byref(d.g), C.byref(ic), None), "preset")
+    whole = _stage(lk, d, s, stage, 3, 3, 0, bcs=ic, preset=True)
+    for order_ in ((1, 2), (2, 1)):
+        parts = _stage(lk, d, s, stage, 3, 3, 0, bcs=ic, preset=True, tile_sets=order_, cut=cut)
+        assert parts[3] == 2 and whole[3] == 1
+        assert torch.equal(parts[0], whole[0]) and torch.equal(parts[1], whole[1]) and torch.equal(parts[2], whole[2])
+    first = _stage(lk, d, s, stage, 0, 0, 0, bcs=ic, preset=True, tile_sets=(1,), cut=cut)
+    ng = s.ng
+    inner = first[0][ng:-ng, ng:-ng, ng:-ng, ng:-ng]
+    done = inner != 3.0                       # _stage pre-fills the predictor with 3.0
+    want = torch.zeros_like(done)
+    if cut & 1:
+        want[..., :32] = True
+        want[..., -32:] = True
+    if cut & 2:
+        want[:, :, :8, :] = True
+        want[:, :, -8:, :] = True
+    assert torch.equal(done, want)
+    # the generic kernel has no tile subsets: the request fails instead of computing everything twice
+    old = lk.lk_set_rhs_variant(2)
+    try:
+        import loki_b200 as lkm
+        u = lkm.RkUpdate()
+        pred = torch.zeros_like(d.f)
+        u.f_old, u.pred, u.w_delta, u.c_pred, u.tile_set, u.cut_dirs = d.f.data_ptr(), pred.data_ptr(), 0.1, 0.1, 1, cut
+        u.delta_out = pred.data_ptr()
+        assert lk.lk_vlasov_stage_can_split(None, C.byref(d.g), C.byref(d.accel), C.byref(u)) == 0
+        assert lk.lk_vlasov_stage(None, d.f.data_ptr(), C.byref(d.g), d.velocities.data_ptr(), C.byref(d.accel), C.byref(u), None, None) != 0
+    finally:
+        lk.lk_set_rhs_variant(old)
