@@ -323,6 +323,17 @@ def run_own(args):
         cells_launch = cells_rank / nsp
         avg_bytes = cells_launch * (sum(STAGE_BYTES) / len(STAGE_BYTES))
         avg_ms = tot_ms.value / max(1, n_l.value)
+        share = tot_ms.value / ms if ms > 0 else None
+        split_note = None
+        n_eval = steps * stages * nsp
+        if n_l.value > n_eval:
+            # a cut rank evaluates a stage in two launches that run CONCURRENTLY on two streams (the tiles on the cut
+            # faces first, so that their halo exchange overlaps the rest): their event durations overlap and do not
+            # add up to a stage.  The figure that cannot flatter: everything the device did in a stage evaluation.
+            avg_ms = ms / n_eval
+            share = None
+            split_note = ("%d launches for %d stage evaluations (two-part stages, concurrent): avg_launch_ms is the whole device "
+                          "time per stage evaluation, halo exchange and field solve included" % (n_l.value, n_eval))
         achieved = avg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, averaged over the launches of
         # one step, from the committed ncu pass of this same command (tools/ncu_traffic.py writes the file)
@@ -338,9 +349,11 @@ def run_own(args):
                     "kernel": ("k_stage_pipe" if L.lk_pipe_launch_count() > pipe0 else "k_stage_march") +
                               " (fused WENO RHS + RK4 stage update + velocity moments)",
                     "algorithmic_bytes_per_launch": avg_bytes, "avg_launch_ms": avg_ms, "timed_launches": n_l.value,
-                    "kernel_share_of_step": tot_ms.value / ms if ms > 0 else None, "peak_source": peak_src,
+                    "kernel_share_of_step": share, "peak_source": peak_src,
                     "traffic_source": traffic_src,
                     "note": "co-limited by fp64 issue: see roofline.fp64 (measured ceiling, tools/fp64_peak.cu) and DESIGN.md section 3"}
+        if split_note:
+            roofline["launches_note"] = split_note
         # the second ceiling: fp64 instructions per cell-update (ncu, profiles/r2_*) against the MEASURED fp64 issue
         # rate of this part under sustained load (tools/fp64_peak.cu -> profiles/r2_fp64_peak.json)
         try:
@@ -461,9 +474,15 @@ def main():
     ap.add_argument("--workload", default="iaw", choices=["iaw", "iaw6", "streams"],
                     help="iaw: the headline configuration (BASELINE.json configs[1]); iaw6: the same at order 6; "
                          "streams: configs[4], 8 GPUs only")
+    ap.add_argument("--grid", default=None, help="process grid PXxPY in (x,y) instead of the default for this GPU count")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the secondary workload attached as config.secondary (N=1: iaw6; N=8: streams)")
     args = ap.parse_args()
+    if args.grid:
+        px, py = (int(v) for v in args.grid.lower().split("x"))
+        if px * py != args.gpus:
+            ap.error("--grid %s does not have %d tiles" % (args.grid, args.gpus))
+        GRIDS[args.gpus] = (px, py)
     if args.impl == "reference":
         return run_reference(args)
     return run_own(args)

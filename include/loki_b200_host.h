@@ -115,6 +115,8 @@ int lk_vp_stage_field(lk_vp_system* sys, int stage, const int* tiles);
 /* periodic wrap of lk_vp_eval_ptr(s) inside this rank for a direction that is not cut (0: x, 1: y); a
  * no-op when the fused stage kernel has already written those ghost cells (lk_rk_update::wrap) */
 int lk_vp_local_fill(lk_vp_system* sys, int s, int dir);
+/* 1 when that call would launch anything (lets the caller skip the stream ordering around it) */
+int lk_vp_local_fill_needed(lk_vp_system* sys, int s, int dir);
 int lk_vp_stage_finish(lk_vp_system* sys, int stage);
 /* the same for one species: lets the caller start the halo exchange of species s's new predictor
  * (lk_vp_eval_ptr(s) after this call) on another stream while the next species' stage kernel runs */
@@ -122,10 +124,15 @@ int lk_vp_stage_finish_species(lk_vp_system* sys, int stage, int s);
 /* ... and in two launches, so that a species' own halo exchange overlaps its own stage kernel: part 1 runs the stage
  * with the kernel restricted to the CTA tiles on a face of a cut direction (everything a neighbour needs of the new
  * predictor; lk_vp_eval_ptr(s) is the new predictor from here on), part 2 launches the remaining tiles.  Between the two
- * the caller queues the exchange on another stream behind an event recorded after part 1.  When the stage cannot be
+ * the caller queues the exchange on another stream behind lk_vp_wait_faces.  When the stage cannot be
  * split (strict arithmetic, unaligned tiles, Krook species: not the pipelined kernel) part 1 is the whole stage and
  * part 2 is a no-op: the caller's sequence stays the same. */
 int lk_vp_stage_finish_species_part(lk_vp_system* sys, int stage, int s, int part);
+/* The face tiles of part 1 run on a stream of their own (high priority), the remaining tiles on the system's stream
+ * without waiting for them: no idle tail between the two launches.  lk_vp_wait_faces makes `stream` (the caller's
+ * exchange stream) wait for the face tiles of species s -- or, when the stage was not split, for what the system's
+ * stream holds now.  Part 2 makes the system's stream wait for the face tiles as well. */
+int lk_vp_wait_faces(lk_vp_system* sys, int s, void* stream);
 int lk_vp_end_step(lk_vp_system* sys);
 
 /* reference-ordered, UNFUSED evaluation of one RHS (VPSystem::evalRHS) of the current state into

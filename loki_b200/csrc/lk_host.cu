@@ -218,6 +218,8 @@ struct KineticSpecies {
   bool preset[3] = {false, false, false};
   // a stage launched for the cut-face tiles only (stageFinish part 1): what part 2 needs to launch the rest
   bool pending = false, pending_mom = false;
+  cudaEvent_t ev_face = nullptr;   // the face tiles of the last two-part stage are done
+  bool face_in_flight = false;     // ... and `st` has not been made to wait for them yet
   lk_rk_update pending_u;
   lk_accel pending_a;
   double* pending_rhs = nullptr;
@@ -366,9 +368,26 @@ struct VPSystem {
   double time = 0.0, dt = 0.0;
   bool lambda_stale = true;
 
+  // second stream for the cut-face tiles of a two-part stage (stageFinish part 1): the remaining tiles are launched on
+  // `st` without waiting for them, so the two launches share the SMs with no idle tail between them
+  cudaStream_t st_face = nullptr;
+  cudaEvent_t ev_pre = nullptr;
   ~VPSystem() {
-    for (auto* s : species) delete s;
+    for (auto* s : species) {
+      if (s->ev_face) cudaEventDestroy(s->ev_face);
+      delete s;
+    }
     if (poisson) lk_poisson_plan_destroy(poisson);
+    if (st_face) cudaStreamDestroy(st_face);
+    if (ev_pre) cudaEventDestroy(ev_pre);
+  }
+  int faceStream() {
+    if (st_face) return LK_OK;
+    int lo = 0, hi = 0;
+    LKH_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    LKH_CUDA(cudaStreamCreateWithPriority(&st_face, cudaStreamNonBlocking, hi));
+    LKH_CUDA(cudaEventCreateWithFlags(&ev_pre, cudaEventDisableTiming));
+    return LK_OK;
   }
 
   int nstages() const { return desc.rk_order == 4 ? 4 : 8; }
@@ -513,6 +532,9 @@ struct VPSystem {
         ks->pending_u.tile_set = 2;
         LKH_CHECK(lk_vlasov_stage(ks->pending_rhs, ks->pending_f, &ks->g, ks->velocities.p, &ks->pending_a, &ks->pending_u,
                                   ks->pending_mom ? &ks->mom : nullptr, st));
+        // everything queued on the main stream from here on sees the whole stage
+        LKH_CUDA(cudaStreamWaitEvent(st, ks->ev_face, 0));
+        ks->face_in_flight = false;
       }
       return LK_OK;
     }
@@ -628,8 +650,17 @@ struct VPSystem {
           ks->pending_rhs = rhs_out;
           ks->pending_f = ks->f_eval;
           ks->pending_mom = fused_moments;
+          // the face tiles go to the high-priority stream, behind everything the main stream holds now
+          LKH_CHECK(faceStream());
+          if (!ks->ev_face) LKH_CUDA(cudaEventCreateWithFlags(&ks->ev_face, cudaEventDisableTiming));
+          LKH_CUDA(cudaEventRecord(ev_pre, st));
+          LKH_CUDA(cudaStreamWaitEvent(st_face, ev_pre, 0));
+          LKH_CHECK(lk_vlasov_stage(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, fused_moments ? &ks->mom : nullptr, st_face));
+          LKH_CUDA(cudaEventRecord(ks->ev_face, st_face));
+          ks->face_in_flight = true;
+        } else {
+          LKH_CHECK(lk_vlasov_stage(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, fused_moments ? &ks->mom : nullptr, st));
         }
-        LKH_CHECK(lk_vlasov_stage(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, fused_moments ? &ks->mom : nullptr, st));
       }
       ks->wrap_ptr = pred;
       ks->wrap_bits = u.wrap;
@@ -1178,6 +1209,12 @@ int lk_vp_stage_field(lk_vp_system* h, int stage, const int* tiles) {
   if (tiles == nullptr || h->sys.desc.ntiles == 1) return h->sys.fillAdvectionGhostCellsLocal();
   return LK_OK;
 }
+int lk_vp_local_fill_needed(lk_vp_system* h, int s, int dir) {
+  if (!h || s < 0 || s >= (int)h->sys.species.size() || dir < 0 || dir > 1) return 0;
+  auto* ks = h->sys.species[s];
+  const int dirs = 1 << dir;
+  return ((ks->f_eval == ks->wrap_ptr) ? (dirs & ~ks->wrap_bits) : dirs) ? 1 : 0;
+}
 int lk_vp_local_fill(lk_vp_system* h, int s, int dir) {
   if (!h || s < 0 || s >= (int)h->sys.species.size() || dir < 0 || dir > 1) return LK_ERR_ARG;
   auto* ks = h->sys.species[s];
@@ -1194,6 +1231,17 @@ int lk_vp_stage_finish_species(lk_vp_system* h, int stage, int s) {
 int lk_vp_stage_finish_species_part(lk_vp_system* h, int stage, int s, int part) {
   if (!h || stage < 0 || stage >= h->sys.nstages() || s < 0 || s >= (int)h->sys.species.size() || part < 1 || part > 2) return LK_ERR_ARG;
   return h->sys.stageFinish(stage, h->sys.species[s], part);
+}
+int lk_vp_wait_faces(lk_vp_system* h, int s, void* stream) {
+  // make `stream` wait until everything a neighbour needs of species s's new predictor has been written: the face
+  // tiles of a two-part stage (their own stream), else whatever the main stream holds now
+  if (!h || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  auto& S = h->sys;
+  auto* ks = S.species[s];
+  if (ks->face_in_flight) return cudaStreamWaitEvent((cudaStream_t)stream, ks->ev_face, 0) == cudaSuccess ? LK_OK : LK_ERR_CUDA;
+  if (S.faceStream() != LK_OK) return LK_ERR_CUDA;
+  if (cudaEventRecord(S.ev_pre, S.st) != cudaSuccess) return LK_ERR_CUDA;
+  return cudaStreamWaitEvent((cudaStream_t)stream, S.ev_pre, 0) == cudaSuccess ? LK_OK : LK_ERR_CUDA;
 }
 int lk_vp_end_step(lk_vp_system* h) { return h ? h->sys.endStep() : LK_ERR_ARG; }
 int lk_vp_eval_rhs(lk_vp_system* h, double** rhs_dev, double time) { return (h && rhs_dev) ? h->sys.evalRHS(rhs_dev, time) : LK_ERR_ARG; }

@@ -161,6 +161,13 @@ class DistributedVP:
             self.H.lk_vp_species_geom(self.sys, s, C.byref(g))
             self.geoms.append(g)
         self.world = layout.world
+        # Two-part stages (lk_vp_stage_finish_species_part) hide a species' exchange behind its OWN kernel.  With
+        # several species the exchange already travels under the next species' kernel and the split only costs (two
+        # launches, two tails: measured 96-108 ms against 91 ms per step at 4 GPUs, profiles/r2_multi_gpu.md), so it is
+        # the default for a single species only; LOKI_SPLIT_STAGES=0/1 overrides.
+        import os
+        env = os.environ.get("LOKI_SPLIT_STAGES", "")
+        self.split_stages = (self.nsp == 1) if env not in ("0", "1") else (env == "1")
         if self.world > 1:
             if dist is None:
                 raise ValueError("a cut layout needs torch.distributed")
@@ -226,6 +233,8 @@ class DistributedVP:
             # a direction that is not cut wraps inside the rank; the fused stage kernel has normally written
             # those ghost cells already and the call is a no-op.  It runs on the system's own stream, so the
             # two streams are ordered around it (x before y, ParallelArray.H:580-606).
+            if not H.lk_vp_local_fill_needed(self.sys, s, d):
+                return
             if stream is not None:
                 e = self.torch.cuda.Event()
                 e.record(stream)
@@ -248,9 +257,10 @@ class DistributedVP:
         if self.comm_stream is None:
             self._exchange_halos(s, None)
         else:
-            self.ev_stage[s].record(self.main_stream)
+            # behind the face tiles of a two-part stage (their own stream), else behind the main stream
+            from . import capi
+            capi.check(self.H.lk_vp_wait_faces(self.sys, s, C.c_void_p(self.comm_stream.cuda_stream)), "lk_vp_wait_faces")
             with torch.cuda.stream(self.comm_stream):
-                self.comm_stream.wait_event(self.ev_stage[s])
                 self._exchange_halos(s, self.comm_stream)
                 self.ev_halo[s].record(self.comm_stream)
         self.halo_ready[s] = True
@@ -287,11 +297,16 @@ class DistributedVP:
                     self._start_exchange(s)       # first stage after a state upload
                 if self.comm_stream is not None:
                     self.main_stream.wait_event(self.ev_halo[s])
-                # the stage kernel in two launches: the tiles on the cut faces first, then the new predictor's faces
-                # leave (second stream) under the launch of the remaining tiles and the next species' stage kernel
-                capi.check(H.lk_vp_stage_finish_species_part(self.sys, stage, s, 1), "lk_vp_stage_finish_species_part")
-                self._start_exchange(s)
-                capi.check(H.lk_vp_stage_finish_species_part(self.sys, stage, s, 2), "lk_vp_stage_finish_species_part")
+                if self.split_stages:
+                    # the stage kernel in two launches: the tiles on the cut faces first, then the new predictor's
+                    # faces leave (second stream) under the launch of the remaining tiles
+                    capi.check(H.lk_vp_stage_finish_species_part(self.sys, stage, s, 1), "lk_vp_stage_finish_species_part")
+                    self._start_exchange(s)
+                    capi.check(H.lk_vp_stage_finish_species_part(self.sys, stage, s, 2), "lk_vp_stage_finish_species_part")
+                else:
+                    capi.check(H.lk_vp_stage_finish_species(self.sys, stage, s), "lk_vp_stage_finish_species")
+                    # the new predictor's faces leave now, under the next species' stage kernel
+                    self._start_exchange(s)
         capi.check(H.lk_vp_end_step(self.sys), "lk_vp_end_step")
 
     def synchronize(self):

@@ -67,9 +67,11 @@ _PROTOS = {
     "lk_vp_rho_gather_ptr": (_vp, [_vp]),
     "lk_vp_stage_field": (C.c_int, [_vp, C.c_int, _vp]),
     "lk_vp_local_fill": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "lk_vp_local_fill_needed": (C.c_int, [_vp, C.c_int, C.c_int]),
     "lk_vp_stage_finish": (C.c_int, [_vp, C.c_int]),
     "lk_vp_stage_finish_species": (C.c_int, [_vp, C.c_int, C.c_int]),
     "lk_vp_stage_finish_species_part": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "lk_vp_wait_faces": (C.c_int, [_vp, C.c_int, _vp]),
     "lk_vp_end_step": (C.c_int, [_vp]),
     "lk_vp_eval_rhs": (C.c_int, [_vp, C.POINTER(_vp), C.c_double]),
     "lk_vp_em_vars_ptr": (_vp, [_vp]),

@@ -49,6 +49,8 @@ def _run_rank(rank, world, port, px, py, order, rk, nsteps, dt, out, kind="iaw")
     from loki_b200 import decomp
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    if kind == "iaw_tiles":
+        os.environ["LOKI_SPLIT_STAGES"] = "1"     # two-part stages are the default for a single species only
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     if world > 1:

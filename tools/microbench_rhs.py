@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--strict", action="store_true")
     ap.add_argument("--mode", default="stage", choices=["stage", "rhs"])
+    ap.add_argument("--split", type=int, default=0, help="two launches: the tiles on the faces of these cut directions (1 x, 2 y, 3 both), then the rest")
     ap.add_argument("--fold", action="store_true", help="hand the inflow over (lk_rk_update.accel_bcs): velocity-boundary fill inside the stage")
     a = ap.parse_args()
     lk = lkm.load()
@@ -67,6 +68,12 @@ def main():
         assert lk.lk_preset_inflow_ghosts_4d(f.data_ptr(), C.byref(g), C.byref(I), st) == 0
 
     def run():
+        if a.split:
+            for ts in (1, 2):
+                U.tile_set, U.cut_dirs = ts, a.split
+                s = lk.lk_vlasov_stage(None, f.data_ptr(), C.byref(g), vel.data_ptr(), C.byref(A), C.byref(U), None, st)
+                assert s == 0, lk.lk_last_error()
+            return
         if a.mode == "stage" and a.fold:
             s = lk.lk_vlasov_stage(None, f.data_ptr(), C.byref(g), vel.data_ptr(), C.byref(A), C.byref(U), None, st)
         elif a.mode == "stage":
@@ -87,8 +94,8 @@ def main():
     times = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
     ms = sum(times) / len(times)
     bpc = 40 if a.mode == "stage" else 16
-    print("n=%s order=%d variant=%d strict=%d mode=%s fold=%d: %.3f ms/launch, %.2f Gcell/s, %.1f GB/s algorithmic (%d B/cell)  [min %.3f median %.3f ms, %s]" % (
-        n, a.order, a.variant, int(a.strict), a.mode, int(a.fold), ms, cells / ms / 1e6, cells * bpc / ms / 1e6, bpc, times[0],
+    print("n=%s order=%d variant=%d strict=%d mode=%s fold=%d split=%d: %.3f ms/launch, %.2f Gcell/s, %.1f GB/s algorithmic (%d B/cell)  [min %.3f median %.3f ms, %s]" % (
+        n, a.order, a.variant, int(a.strict), a.mode, int(a.fold), a.split, ms, cells / ms / 1e6, cells * bpc / ms / 1e6, bpc, times[0],
         times[len(times) // 2], os.path.basename(os.environ.get("LOKI_B200_LIB", "libloki_b200.so"))))
 
 
