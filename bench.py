@@ -191,7 +191,7 @@ def run_own(args):
     import torch
     import torch.distributed as dist
     import loki_b200
-    from loki_b200 import decks, decomp, host
+    from loki_b200 import capi, decks, decomp, host
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -387,7 +387,20 @@ def run_own(args):
         for s in range(nsp):
             H.lk_vp_get_state(sys_, s, bufs[s].data_ptr())
 
-        def e2e_step():
+        # Every step takes its input from the host buffers and returns its result there.  The download of step k and
+        # the upload of step k+1 are in flight together (PCIe is full duplex) through the library's streaming calls:
+        # the three rotating arrays of a species are the double buffer.  Separate in / out buffers when they fit.
+        outs = bufs
+        if pinned and psutil.virtual_memory().available > 2 * need * max(1, world):
+            try:
+                outs = [torch.empty(v, dtype=torch.float64, pin_memory=True) for v in vols]
+            except RuntimeError:
+                outs = bufs
+        streamed = pinned and outs is not bufs
+        s_up, s_down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        c_up, c_down = C.c_void_p(s_up.cuda_stream), C.c_void_p(s_down.cuda_stream)
+
+        def e2e_blocking_step():
             for s in range(nsp):
                 H.lk_vp_set_state(sys_, s, bufs[s].data_ptr())
             vp.invalidate_halos()
@@ -396,12 +409,35 @@ def run_own(args):
             for s in range(nsp):
                 H.lk_vp_get_state(sys_, s, bufs[s].data_ptr())
 
-        e2e_step()
+        def upload():
+            for s in range(nsp):
+                capi.check(H.lk_vp_upload_next(sys_, s, bufs[s].data_ptr(), c_up), "lk_vp_upload_next")
+            capi.check(H.lk_vp_adopt_next(sys_), "lk_vp_adopt_next")
+            vp.invalidate_halos()
+
+        def e2e_streamed(nrep):
+            upload()
+            for k in range(nrep):
+                step(dt)
+                vp.synchronize()
+                for s in range(nsp):
+                    capi.check(H.lk_vp_download_state(sys_, s, outs[s].data_ptr(), c_down), "lk_vp_download_state")
+                if k + 1 < nrep:
+                    upload()
+            torch.cuda.synchronize(dev)
+
+        nrep = 10 if streamed else 2
+        if streamed:
+            e2e_streamed(2)
+        else:
+            e2e_blocking_step()
         barrier()
-        nrep = 2
         t0 = time.perf_counter()
-        for _ in range(nrep):
-            e2e_step()
+        if streamed:
+            e2e_streamed(nrep)
+        else:
+            for _ in range(nrep):
+                e2e_blocking_step()
         barrier()
         wall = time.perf_counter() - t0
         tt = torch.tensor([wall], dtype=torch.float64, device=dev)
@@ -410,8 +446,11 @@ def run_own(args):
         wall = float(tt.item())
         e2e = {"value": total_cells * stages * nrep / wall, "unit": UNIT, "h2d_bytes_per_step": need * world,
                "d2h_bytes_per_step": need * world, "steps": nrep, "pinned": bool(pinned),
-               "api": "lk_vp_set_state + lk_vp_advance + lk_vp_get_state (include/loki_b200_host.h)"}
-        del bufs
+               "api": ("lk_vp_upload_next + lk_vp_adopt_next + lk_vp_advance + lk_vp_download_state: every step uploads its "
+                       "input and downloads its result; the download of step k and the upload of step k+1 overlap "
+                       "(include/loki_b200_host.h)") if streamed else
+                      "lk_vp_set_state + lk_vp_advance + lk_vp_get_state (include/loki_b200_host.h)"}
+        del bufs, outs
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -56,6 +56,18 @@ int lk_vp_species_geom(const lk_vp_system* sys, int s, lk_geom* g);
  * (RestartWriter.C:543-560).  Synchronous. */
 int lk_vp_set_state(lk_vp_system* sys, int s, const double* f_host);
 int lk_vp_get_state(lk_vp_system* sys, int s, double* f_host);
+/* The same without stalling the device: a state can be on its way to the host while the next one arrives
+ * (full-duplex PCIe) -- the three rotating arrays of a species give the double buffer, nothing is copied twice.
+ *   lk_vp_download_state(sys, s, pinned, stream)  queue D2H of the current state on `stream`, behind the system's stream
+ *   lk_vp_upload_next(sys, s, pinned, stream)     queue H2D of the NEXT state on `stream` into the array the previous
+ *                                                 state occupied (free once the step the system's stream holds is done)
+ *   lk_vp_adopt_next(sys)                         the uploaded arrays become the states (the system's stream waits for
+ *                                                 the uploads); a later step waits for a pending download before it
+ *                                                 reuses the array that download reads
+ * The host buffers must stay valid until their stream has been synchronised. */
+int lk_vp_download_state(lk_vp_system* sys, int s, double* f_host_pinned, void* stream);
+int lk_vp_upload_next(lk_vp_system* sys, int s, const double* f_host_pinned, void* stream);
+int lk_vp_adopt_next(lk_vp_system* sys);
 /* device pointer of the current state / of the state the next evalRHS will read */
 double* lk_vp_state_ptr(lk_vp_system* sys, int s);
 double* lk_vp_eval_ptr(lk_vp_system* sys, int s);

@@ -218,6 +218,10 @@ struct KineticSpecies {
   bool preset[3] = {false, false, false};
   // a stage launched for the cut-face tiles only (stageFinish part 1): what part 2 needs to launch the rest
   bool pending = false, pending_mom = false;
+  // streaming the state through pinned host memory (lk_vp_upload_next / adopt / download_state)
+  cudaEvent_t ev_up = nullptr, ev_down = nullptr;
+  int next_idx = -1;               // array an upload of the next state is landing in
+  bool down_pending = false;       // a download of the state array is in flight
   cudaEvent_t ev_face = nullptr;   // the face tiles of the last two-part stage are done
   bool face_in_flight = false;     // ... and `st` has not been made to wait for them yet
   lk_rk_update pending_u;
@@ -375,6 +379,8 @@ struct VPSystem {
   ~VPSystem() {
     for (auto* s : species) {
       if (s->ev_face) cudaEventDestroy(s->ev_face);
+      if (s->ev_up) cudaEventDestroy(s->ev_up);
+      if (s->ev_down) cudaEventDestroy(s->ev_down);
       delete s;
     }
     if (poisson) lk_poisson_plan_destroy(poisson);
@@ -685,7 +691,13 @@ struct VPSystem {
 
   int beginStep(double a_dt) {
     dt = a_dt;
+    for (auto* ks : species)
+      if (ks->next_idx >= 0) return LK_ERR_ARG;  // an uploaded state waits for lk_vp_adopt_next
     for (auto* ks : species) {
+      if (ks->down_pending) {  // the array a download still reads becomes a predictor buffer of this step
+        LKH_CUDA(cudaStreamWaitEvent(st, ks->ev_down, 0));
+        ks->down_pending = false;
+      }
       ks->f_eval = ks->state();  // stage 1 evaluates the old solution
       if (ks->has_driver) k_copy_scalar<<<1, 1, 0, st>>>(ks->ke.p, 1, 0);  // copySolnData(old, state)
     }
@@ -1087,6 +1099,53 @@ int lk_vp_get_state(lk_vp_system* h, int s, double* f_host) {
   auto* ks = h->sys.species[s];
   if (cudaStreamSynchronize(h->sys.st) != cudaSuccess) return LK_ERR_CUDA;
   if (cudaMemcpy(f_host, ks->state(), sizeof(double) * ks->vol, cudaMemcpyDeviceToHost) != cudaSuccess) return LK_ERR_CUDA;
+  return LK_OK;
+}
+/* ---- streaming the state through the host without stalling (double buffering over the rotating arrays) ---- */
+int lk_vp_download_state(lk_vp_system* h, int s, double* f_host, void* stream) {
+  if (!h || !f_host || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  auto& S = h->sys;
+  auto* ks = S.species[s];
+  cudaStream_t cs = (cudaStream_t)stream;
+  if (S.faceStream() != LK_OK) return LK_ERR_CUDA;
+  if (!ks->ev_down && cudaEventCreateWithFlags(&ks->ev_down, cudaEventDisableTiming) != cudaSuccess) return LK_ERR_CUDA;
+  if (cudaEventRecord(S.ev_pre, S.st) != cudaSuccess || cudaStreamWaitEvent(cs, S.ev_pre, 0) != cudaSuccess) return LK_ERR_CUDA;
+  if (cudaMemcpyAsync(f_host, ks->state(), sizeof(double) * ks->vol, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return LK_ERR_CUDA;
+  if (cudaEventRecord(ks->ev_down, cs) != cudaSuccess) return LK_ERR_CUDA;
+  ks->down_pending = true;
+  return LK_OK;
+}
+int lk_vp_upload_next(lk_vp_system* h, int s, const double* f_host, void* stream) {
+  if (!h || !f_host || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  auto& S = h->sys;
+  auto* ks = S.species[s];
+  cudaStream_t cs = (cudaStream_t)stream;
+  if (S.faceStream() != LK_OK) return LK_ERR_CUDA;
+  if (!ks->ev_up && cudaEventCreateWithFlags(&ks->ev_up, cudaEventDisableTiming) != cudaSuccess) return LK_ERR_CUDA;
+  // the previous state's array: free once the step the main stream holds is done; never the array a download reads
+  ks->next_idx = ks->i_a;
+  if (cudaEventRecord(S.ev_pre, S.st) != cudaSuccess || cudaStreamWaitEvent(cs, S.ev_pre, 0) != cudaSuccess) return LK_ERR_CUDA;
+  if (cudaMemcpyAsync(ks->farr[ks->next_idx].p, f_host, sizeof(double) * ks->vol, cudaMemcpyHostToDevice, cs) != cudaSuccess) return LK_ERR_CUDA;
+  if (cudaEventRecord(ks->ev_up, cs) != cudaSuccess) return LK_ERR_CUDA;
+  return LK_OK;
+}
+int lk_vp_adopt_next(lk_vp_system* h) {
+  if (!h) return LK_ERR_ARG;
+  auto& S = h->sys;
+  for (auto* ks : S.species) {
+    if (ks->next_idx < 0) continue;
+    if (cudaStreamWaitEvent(S.st, ks->ev_up, 0) != cudaSuccess) return LK_ERR_CUDA;
+    // roles: uploaded array -> state; the old state's array (a download may still read it) -> written last
+    const int x = ks->i_state, y = ks->next_idx, z = (ks->i_a == y) ? ks->i_b : ks->i_a;
+    ks->i_state = y;
+    ks->i_a = z;
+    ks->i_b = x;
+    ks->next_idx = -1;
+    ks->f_eval = ks->state();
+    ks->mom_valid = false;
+    ks->wrap_ptr = nullptr;
+    ks->preset[y] = false;
+  }
   return LK_OK;
 }
 double* lk_vp_state_ptr(lk_vp_system* h, int s) { return (h && s >= 0 && s < (int)h->sys.species.size()) ? h->sys.species[s]->state() : nullptr; }

@@ -742,3 +742,52 @@ def test_full_regression_runs_vp(lk, ok, fast, mk, final_time, save_times, min_s
     for s_ in range(len(got)):
         assert star_rel_err(got[s_], want[s_], want[s_], deck.ng) <= 1e-10
     print("%s regression run: %d steps, worst trace difference %.2e" % (deck.name, steps, float(worst.max())))
+
+
+def test_streaming_state_equals_blocking_state_io(lk, ok, fast):
+    """lk_vp_download_state / lk_vp_upload_next / lk_vp_adopt_next (the double-buffered host streaming bench.py's e2e
+    leg uses): every step takes its input from pinned host memory and returns its result there, uploads and downloads
+    in flight together -- same bits as lk_vp_set_state + lk_vp_advance + lk_vp_get_state"""
+    import torch
+    deck = decks.plane_iaw(n=(32, 8), nv=(16, 8))
+    states = [_perturb(deck.initial_state(s)[0], 90 + k, amp=0.02) for k, s in enumerate(deck.species)]
+    ns = len(states)
+    nsteps, dt = 4, 0.02
+    # every step starts from a DIFFERENT host state (a scaled copy), as if a producer filled the buffer
+    inputs = [[np.ascontiguousarray(f * (1.0 + 0.01 * k)) for f in states] for k in range(nsteps)]
+    H, sys_ = _product(deck, states, None)
+    want = []
+    for k in range(nsteps):
+        for s in range(ns):
+            assert H.lk_vp_set_state(sys_, s, inputs[k][s].ctypes.data) == 0
+        assert H.lk_vp_set_time(sys_, 0.1) == 0 and H.lk_vp_advance(sys_, dt) == 0
+        outs = [np.empty_like(f) for f in states]
+        for s in range(ns):
+            assert H.lk_vp_get_state(sys_, s, outs[s].ctypes.data) == 0
+        want.append(outs)
+    H.lk_vp_destroy(sys_)
+    H, sys_ = _product(deck, states, None)
+    up, down = torch.cuda.Stream(), torch.cuda.Stream()
+    pin_in = [[torch.from_numpy(a).pin_memory() for a in step] for step in inputs]
+    pin_out = [[torch.empty(f.size, dtype=torch.float64).pin_memory() for f in states] for _ in range(nsteps)]
+    for s in range(ns):
+        assert H.lk_vp_upload_next(sys_, s, pin_in[0][s].data_ptr(), C.c_void_p(up.cuda_stream)) == 0
+    assert H.lk_vp_adopt_next(sys_) == 0
+    for k in range(nsteps):
+        assert H.lk_vp_set_time(sys_, 0.1) == 0 and H.lk_vp_advance(sys_, dt) == 0, H.lk_last_error()
+        for s in range(ns):
+            assert H.lk_vp_download_state(sys_, s, pin_out[k][s].data_ptr(), C.c_void_p(down.cuda_stream)) == 0
+        if k + 1 < nsteps:
+            for s in range(ns):
+                assert H.lk_vp_upload_next(sys_, s, pin_in[k + 1][s].data_ptr(), C.c_void_p(up.cuda_stream)) == 0
+            # a step must not start over an upload that has not been adopted
+            assert H.lk_vp_advance(sys_, dt) != 0
+            assert H.lk_vp_adopt_next(sys_) == 0
+    torch.cuda.synchronize()
+    ng = deck.ng
+    I = (slice(ng, -ng),) * 4
+    for k in range(nsteps):
+        for s in range(ns):
+            got = pin_out[k][s].numpy().reshape(states[s].shape)
+            assert np.array_equal(got[I], want[k][s][I]), (k, s)
+    H.lk_vp_destroy(sys_)
