@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -37,17 +38,33 @@ bool geom_ok(const lk_geom* g) {
   return true;
 }
 
-// scratch buffers keyed by slot, grown on demand (device memory stays resident between calls)
+// scratch buffers keyed by (device, stream, slot), grown on demand and kept: two systems on different streams or
+// devices of one process never share one.  A buffer that has to grow is replaced after its stream has drained.
+struct ScratchKey {
+  int device;
+  void* stream;
+  int slot;
+  bool operator<(const ScratchKey& o) const {
+    if (device != o.device) return device < o.device;
+    if (stream != o.stream) return stream < o.stream;
+    return slot < o.slot;
+  }
+};
 struct Scratch {
   void* p = nullptr;
   size_t bytes = 0;
 };
-Scratch g_scratch[4];
-double* scratch(int slot, size_t bytes) {
+std::map<ScratchKey, Scratch> g_scratch;
+double* scratch(int slot, size_t bytes, void* stream) {
   std::lock_guard<std::mutex> lk(g_mu);
-  Scratch& s = g_scratch[slot];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  Scratch& s = g_scratch[ScratchKey{dev, stream, slot}];
   if (s.bytes < bytes) {
-    if (s.p) cudaFree(s.p);
+    if (s.p) {
+      cudaStreamSynchronize((cudaStream_t)stream);  // earlier launches on this stream may still use the old buffer
+      cudaFree(s.p);
+    }
     s.p = nullptr;
     s.bytes = 0;
     if (cudaMalloc(&s.p, bytes) != cudaSuccess) return nullptr;
@@ -163,7 +180,7 @@ static bool accel_ok(const lk_accel* a) {
 
 int lk_max_accel(const lk_geom* g, const lk_accel* a, double* out, void* stream) {
   if (!geom_ok(g) || !accel_ok(a) || !out || a->kind == 2) return fail(LK_ERR_ARG, "lk_max_accel: bad argument");
-  double* s4 = scratch(2, sizeof(double) * 4);
+  double* s4 = scratch(2, sizeof(double) * 4, stream);
   if (!s4) return cuda_fail(cudaGetLastError(), "lk_max_accel: scratch");
   CHECK_LAUNCH(DISPATCH(max_accel)(g, a, out, s4, (cudaStream_t)stream), "lk_max_accel");
 }
@@ -360,7 +377,7 @@ int lk_ke_e_dot_from_moments(double* out, const lk_stage_moments* mom, const lk_
 int lk_reduce_4d_to_2d(double* dst, const double* f, const lk_geom* g, double dv, double weight, void* stream) {
   if (!geom_ok(g) || !dst || !f) return fail(LK_ERR_ARG, "lk_reduce_4d_to_2d: bad argument");
   const int chunks = moment_chunks(g);
-  double* s = scratch(0, sizeof(double) * (size_t)g->n[0] * g->n[1] * chunks);
+  double* s = scratch(0, sizeof(double) * (size_t)g->n[0] * g->n[1] * chunks, stream);
   if (!s) return cuda_fail(cudaGetLastError(), "lk_reduce_4d_to_2d: scratch");
   CHECK_LAUNCH(DISPATCH(reduce_4d_to_2d)(dst, f, g, dv, weight, s, chunks, (cudaStream_t)stream), "lk_reduce_4d_to_2d");
 }
@@ -368,7 +385,7 @@ int lk_current_density(double* Jx, double* Jy, double* Jz, const double* f, cons
                        const double* vz, double dv, double weight, void* stream) {
   if (!geom_ok(g) || !Jx || !Jy || !Jz || !f || !velocities || !vz) return fail(LK_ERR_ARG, "lk_current_density: bad argument");
   const int chunks = moment_chunks(g);
-  double* s = scratch(0, sizeof(double) * 3 * (size_t)g->n[0] * g->n[1] * chunks);
+  double* s = scratch(0, sizeof(double) * 3 * (size_t)g->n[0] * g->n[1] * chunks, stream);
   if (!s) return cuda_fail(cudaGetLastError(), "lk_current_density: scratch");
   CHECK_LAUNCH(DISPATCH(current_density)(Jx, Jy, Jz, f, g, velocities, vz, dv, weight, s, chunks, (cudaStream_t)stream),
                "lk_current_density");
@@ -377,7 +394,7 @@ int lk_ke_e_dot(double* out, const double* f, const lk_geom* g, double charge, c
                 const double* ext, void* stream) {
   if (!geom_ok(g) || !out || !f || !velocities || !ext) return fail(LK_ERR_ARG, "lk_ke_e_dot: bad argument");
   const int nblocks = 148 * 4;
-  double* s = scratch(1, sizeof(double) * nblocks);
+  double* s = scratch(1, sizeof(double) * nblocks, stream);
   if (!s) return cuda_fail(cudaGetLastError(), "lk_ke_e_dot: scratch");
   CHECK_LAUNCH(DISPATCH(ke_e_dot)(out, f, g, charge, velocities, ext, s, nblocks, (cudaStream_t)stream), "lk_ke_e_dot");
 }
@@ -472,7 +489,7 @@ int lk_efield_from_potential(double* em, const double* phi, int n1, int n2, int 
 int lk_compute_ke(double* out5, const double* f, const lk_geom* g, double mass, const double* velocities, const double* vz,
                   void* stream) {
   if (!geom_ok(g) || !out5 || !f || !velocities) return fail(LK_ERR_ARG, "lk_compute_ke: bad argument");
-  double* s = scratch(3, sizeof(double) * lkdiag::ke_scratch_doubles());
+  double* s = scratch(3, sizeof(double) * lkdiag::ke_scratch_doubles(), stream);
   if (!s) return cuda_fail(cudaGetLastError(), "lk_compute_ke: scratch");
   CHECK_LAUNCH(lkdiag::compute_ke(out5, f, g, mass, velocities, vz, s, (cudaStream_t)stream, &g_fft_launches), "lk_compute_ke");
 }

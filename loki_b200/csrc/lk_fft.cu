@@ -146,7 +146,10 @@ int neutralize_scratch_doubles() { return NEUT_BLOCKS; }
 
 cudaError_t poisson_fft(double* phi, const double* rho, int nx, int ny, int ng, const double* sx, const double* sy,
                         const double* cx, const double* cy, double* F1, double* F2, cudaStream_t st, int64_t* launches) {
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {false};   // the attribute belongs to the device's context
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  bool& attr_done = attr_done_dev[dev];
   if (!attr_done) {
     const int big = 2 * 4096 * (int)sizeof(double2);
     cudaError_t e = cudaFuncSetAttribute(k_fft_x_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big);

@@ -272,11 +272,19 @@ static inline unsigned nblk(i64 n, int t, i64 cap) {
 
 using namespace lkflux;
 
-// scratch for the per-block partial sums (one stream at a time, like the other diagnostics)
-static double* g_flux_part = nullptr;
-static double* flux_part() {
-  if (!g_flux_part && cudaMalloc(&g_flux_part, sizeof(double) * FLUX_BLOCKS) != cudaSuccess) g_flux_part = nullptr;
-  return g_flux_part;
+// scratch for the per-block partial sums, one per (device, stream)
+#include <map>
+#include <mutex>
+#include <utility>
+static std::mutex g_flux_mu;
+static std::map<std::pair<int, void*>, double*> g_flux_part;
+static double* flux_part(void* stream) {
+  std::lock_guard<std::mutex> lk(g_flux_mu);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  double*& p = g_flux_part[std::make_pair(dev, stream)];
+  if (!p && cudaMalloc(&p, sizeof(double) * FLUX_BLOCKS) != cudaSuccess) p = nullptr;
+  return p;
 }
 
 extern "C" {
@@ -311,7 +319,7 @@ int lk_ke_flux_from_fluxes(double* out_dev, const lk_geom* g, const double* flux
                            double mass, void* stream) {
   if (!out_dev || !g || !flux || dir < 0 || dir > 3 || side < 0 || side > 1) return LK_ERR_ARG;
   if ((dir <= 1 && !velocities) || (dir == 2 && !vxface_velocities) || (dir == 3 && !vyface_velocities)) return LK_ERR_ARG;
-  double* part = flux_part();
+  double* part = flux_part(stream);
   if (!part) return LK_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   DGeo d = make_geo(g);
@@ -339,7 +347,7 @@ int lk_ke_flux_boundaries(double* out8_dev, const double* f, const lk_geom* g, c
                           double mass, const int at_boundary[8], void* stream) {
   if (!out8_dev || !f || !g || !velocities || !a || !at_boundary) return LK_ERR_ARG;
   if (!a->vxface_velocities || !a->vyface_velocities || (a->kind != 2 && !a->field)) return LK_ERR_ARG;
-  double* part = flux_part();
+  double* part = flux_part(stream);
   if (!part) return LK_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   DGeo d = make_geo(g);

@@ -99,11 +99,14 @@ __global__ void k_scalar_rk4(double* v, double w_delta, double c_pred, int first
   v[2] = d;
   v[0] = __dadd_rn(v[1], __dmul_rn(c_pred, use_delta ? d : v[3]));
 }
-__global__ void k_scalar_rk6(double* v, double* k, int stage, const double* coef, int ncoef) {
-  // k[stage] = rhs; state = old + sum coef[j]*k[j]
+struct Rk6Coef {
+  double c[8];
+};
+__global__ void k_scalar_rk6(double* v, double* k, int stage, Rk6Coef coef, int ncoef) {
+  // k[stage] = rhs; state = old + sum coef[j]*k[j]; the coefficients travel as launch arguments (no host copy per stage)
   k[stage] = v[3];
   double p = v[1];
-  for (int j = 0; j < ncoef; ++j) p = __dadd_rn(p, __dmul_rn(coef[j], k[j]));
+  for (int j = 0; j < ncoef; ++j) p = __dadd_rn(p, __dmul_rn(coef.c[j], k[j]));
   v[0] = p;
 }
 __global__ void k_copy_scalar(double* v, int dst, int src) { v[dst] = v[src]; }
@@ -376,6 +379,7 @@ struct VPSystem {
   // `st` without waiting for them, so the two launches share the SMs with no idle tail between them
   cudaStream_t st_face = nullptr;
   cudaEvent_t ev_pre = nullptr;
+  DevBuf<double> hist_scratch, flux_scratch;   // device side of lk_vp_time_history / lk_vp_flux_history
   ~VPSystem() {
     for (auto* s : species) {
       if (s->ev_face) cudaEventDestroy(s->ev_face);
@@ -679,8 +683,9 @@ struct VPSystem {
           const double w_upd[4] = {dtOn2, dtOn2, dt, 1.0};
           k_scalar_rk4<<<1, 1, 0, st>>>(ks->ke.p, w_eval[stage], w_upd[stage], stage == 0, stage == 3);
         } else {
-          LKH_CUDA(cudaMemcpyAsync(ks->ke_coef.p, ke_coef, sizeof(double) * ke_ncoef, cudaMemcpyHostToDevice, st));
-          k_scalar_rk6<<<1, 1, 0, st>>>(ks->ke.p, ks->ke_k.p, stage, ks->ke_coef.p, ke_ncoef);
+          Rk6Coef cf;
+          for (int j = 0; j < 8; ++j) cf.c[j] = (j < ke_ncoef) ? ke_coef[j] : 0.0;
+          k_scalar_rk6<<<1, 1, 0, st>>>(ks->ke.p, ks->ke_k.p, stage, cf, ke_ncoef);
         }
       }
       ks->f_eval = pred;  // a_evalSoln of the next stage is the predictor
@@ -794,6 +799,7 @@ struct VMSystem {
   lk_vm_desc desc;
   std::vector<lk_species_desc> sdesc;
   std::vector<KineticSpecies*> species;
+  DevBuf<double> hist_scratch;   // device side of lk_vm_time_history
   cudaStream_t st = nullptr;
   int ng = 2, n1 = 0, n2 = 0, n1d = 0, n2d = 0;
   i64 pl = 0;
@@ -1315,8 +1321,8 @@ int lk_vp_time_history(lk_vp_system* h, double* out, int capacity, int* written)
   const int ns = (int)S.species.size(), count = 5 + 6 * ns;
   *written = 0;
   if (capacity < count) return LK_ERR_ARG;
-  loki::DevBuf<double> d;
-  int st = d.alloc(5 + 5 * ns);
+  loki::DevBuf<double>& d = S.hist_scratch;   // kept with the system: no cudaMalloc / cudaFree (implicit sync) per record
+  int st = (d.p && d.n >= (size_t)(5 + 5 * ns)) ? LK_OK : d.alloc(5 + 5 * ns);
   if (st != LK_OK) return st;
   st = lk_field_history(d.p, S.em_g.p, S.desc.nglobal[0], S.desc.nglobal[1], S.ng, 2, S.dxg, S.st);
   for (int s = 0; s < ns && st == LK_OK; ++s) {
@@ -1348,8 +1354,8 @@ int lk_vp_flux_history(lk_vp_system* h, double* out, int capacity, int* written)
   const int ns = (int)S.species.size();
   *written = 0;
   if (capacity < 8 * ns) return LK_ERR_ARG;
-  loki::DevBuf<double> d;
-  int st = d.alloc(8 * ns);
+  loki::DevBuf<double>& d = S.flux_scratch;
+  int st = (d.p && d.n >= (size_t)(8 * ns)) ? LK_OK : d.alloc(8 * ns);
   if (st != LK_OK) return st;
   for (int s = 0; s < ns; ++s) {
     auto* ks = S.species[s];
@@ -1503,8 +1509,8 @@ int lk_vm_time_history(lk_vm_system* h, double* out, int capacity, int* written)
   const int ns = (int)S.species.size(), count = 12 + 5 * ns;
   *written = 0;
   if (capacity < count) return LK_ERR_ARG;
-  loki::DevBuf<double> d;
-  int st = d.alloc(count);
+  loki::DevBuf<double>& d = S.hist_scratch;
+  int st = (d.p && d.n >= (size_t)count) ? LK_OK : d.alloc(count);
   if (st != LK_OK) return st;
   st = lk_field_history(d.p, S.emState(), S.n1, S.n2, S.ng, 6, S.dxg, S.st);
   for (int s = 0; s < ns && st == LK_OK; ++s) {
