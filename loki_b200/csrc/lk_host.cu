@@ -573,6 +573,7 @@ struct VPSystem {
     }
     for (auto* ks : species) {
       if (only && ks != only) continue;
+      if (ks->pending) return LK_ERR_ARG;  // part 2 of the previous two-part stage of this species was never issued
       // (4) acceleration; the maxima are only consumed by the next stableDt -> last stage
       LKH_CHECK(ks->computeAcceleration(em_local.p, t_stage, desc.xlo, desc.tile_lo, stage == last, st));
       // (5) velocity-boundary fill + advection + acceleration derivatives + RK update in one pass: the stage does
