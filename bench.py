@@ -391,7 +391,8 @@ def run_own(args):
         # the upload of step k+1 are in flight together (PCIe is full duplex) through the library's streaming calls:
         # the three rotating arrays of a species are the double buffer.  Separate in / out buffers when they fit.
         outs = bufs
-        if pinned and psutil.virtual_memory().available > 2 * need * max(1, world):
+        # (every rank of the box pins its own pair at the same moment: leave a wide margin before asking for the second set)
+        if pinned and psutil.virtual_memory().available > (2 if world == 1 else 4) * need * max(1, world):
             try:
                 outs = [torch.empty(v, dtype=torch.float64, pin_memory=True) for v in vols]
             except RuntimeError:
