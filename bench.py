@@ -30,7 +30,12 @@ sys.path.insert(0, ROOT)
 TILE = (256, 256)
 NV = (128, 128)
 ORDER, RK = 4, 4
-GRIDS = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
+# Process grids in (x,y).  The weak-scaling workload cuts y only: x is the contiguous axis, so y faces are long runs that
+# pack at full bandwidth, a rank has two neighbours instead of four, the x wrap stays inside the stage kernel, and the
+# halo volume is half that of a 2D grid (measured on one 4-GPU box: 1x4 359 G against 2x2 341 G, profiles/r2_multi_gpu.md).
+# configs[4] (streams) is a fixed 512 x 512 global box: 2x4 tiles of 256 x 128.  --grid overrides.
+GRIDS = {1: (1, 1), 2: (1, 2), 4: (1, 4), 8: (1, 8)}
+STREAMS_GRID = {8: (2, 4)}
 METRIC = "4D cell-updates/s per RK stage"
 UNIT = "cell-updates/s"
 # algorithmic bytes per cell-update of the fused RK4 stage kernel (SURVEY 8d / DESIGN.md):
@@ -41,8 +46,17 @@ STAGE_BYTES = (32, 40, 40, 32)
 FP64_INSTR_PER_CELL = {4: 110.3, 6: 221.0}
 
 
+def grid_of(n_gpus, workload):
+    if workload == "streams" and n_gpus in STREAMS_GRID and not GRID_OVERRIDE:
+        return STREAMS_GRID[n_gpus]
+    return GRIDS[n_gpus]
+
+
+GRID_OVERRIDE = []
+
+
 def config_dict(n_gpus, workload="iaw"):
-    px, py = GRIDS[n_gpus]
+    px, py = grid_of(n_gpus, workload)
     if workload == "iaw6":
         d = config_dict(n_gpus, "iaw")
         d["workload"] = d["workload"].replace("order 4 WENO", "order 6 WENO")
@@ -213,7 +227,7 @@ def run_own(args):
     def measure(workload, steps, warmup):
         """one workload: build the system, W warm-up steps, K timed steps (barrier + synchronize on both sides, CUDA
         events, MAX over ranks), live roofline of the stage kernel; returns the pieces of the JSON line"""
-        px, py = GRIDS[args.gpus]
+        px, py = grid_of(args.gpus, workload)
         tile = TILE if not args.small else (32, 32)
         nv = NV if not args.small else (32, 32)
         if workload == "streams":
@@ -523,6 +537,7 @@ def main():
         if px * py != args.gpus:
             ap.error("--grid %s does not have %d tiles" % (args.grid, args.gpus))
         GRIDS[args.gpus] = (px, py)
+        GRID_OVERRIDE.append(args.grid)
     if args.impl == "reference":
         return run_reference(args)
     return run_own(args)

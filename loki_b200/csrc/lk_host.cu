@@ -583,9 +583,10 @@ struct VPSystem {
       memset(&u, 0, sizeof(u));
       // the "JB" fill and a Krook-layer species take the separate passes below
       const bool plain = !ks->use_new_bcs && !ks->has_krook;
+      static const bool no_fold = getenv("LOKI_NO_FOLD") != nullptr;  // A/B aid: the separate fill before every stage
       if (plain) {
         u.accel_bcs = &ks->inflow;
-        u.inflow_preset = 1;
+        u.inflow_preset = no_fold ? 0 : 1;
       } else {
         LKH_CHECK(ks->setAccelerationBCs(ks->f_eval, st));
       }

@@ -83,8 +83,11 @@ class TileLayout:
 
 
 def grid_for(world):
-    """Process grids used on one box: cut y first (x is the contiguous axis, so y slabs are long runs)."""
-    return {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}[world]
+    """Process grids used on one box for a free-form (weak-scaling) domain: cut y only.  x is the contiguous axis, so y
+    faces are long runs that pack at full bandwidth, a rank has two neighbours instead of four, the x wrap stays inside
+    the stage kernel and the halo volume is half that of a 2D grid (measured: profiles/r2_multi_gpu.md).  Any px x py
+    TileLayout works (tests/test_gpu_multi.py runs 2x2, 4x1, 2x4, 4x2)."""
+    return {1: (1, 1), 2: (1, 2), 4: (1, 4), 8: (1, 8)}[world]
 
 
 class HaloExchanger:

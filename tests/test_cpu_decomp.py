@@ -37,7 +37,7 @@ def test_layout_neighbours_are_periodic_and_cover_the_domain():
     assert lay.neighbours(0, 1) == (6, 2) and lay.neighbours(7, 0) == (6, 6)
     with pytest.raises(ValueError):
         TileLayout((8, 8), 1, 2, min_tile=5)  # below stencil_width (KineticSpecies.C:495-504)
-    assert grid_for(8) == (2, 4) and grid_for(1) == (1, 1)
+    assert grid_for(8) == (1, 8) and grid_for(4) == (1, 4) and grid_for(1) == (1, 1)
 
 
 def _global_array(nx, ny, nv3, nv4):

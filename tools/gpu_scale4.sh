@@ -1,0 +1,22 @@
+#!/bin/bash
+# one 4-GPU box: the contract line at N = 1, 2, 4 back to back (weak-scaling efficiency on one box), and N = 4 with the
+# velocity-boundary fill as a separate pass (LOKI_NO_FOLD) for comparison
+mkdir -p gpurun_out
+run() { # name, nproc, extra env
+  if [ "$2" = "1" ]; then
+    env $3 timeout 600 python bench.py --gpus 1 --steps 4 --warmup 3 --no-cpu --no-e2e --no-secondary > gpurun_out/scale_$1.log 2> gpurun_out/scale_$1.err
+  else
+    env $3 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $2 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $2 --steps 4 --warmup 3 --no-cpu --no-e2e --no-secondary > gpurun_out/scale_$1.log 2> gpurun_out/scale_$1.err
+  fi
+  tail -1 gpurun_out/scale_$1.log | python -c "
+import sys, json
+d = json.loads(sys.stdin.read())
+r = d['roofline']
+print('$1', d['config']['decomposition'], 'value', round(d['value']/1e9,1), 'ms', round(d['ms_per_step'],2), 'kernel', round(r['avg_launch_ms'],2), 'share', r['kernel_share_of_step'], d['clocks']['sm_mhz'])
+"
+}
+run n1 1 A=1
+run n2 2 A=1
+run n4 4 A=1
+run n4_nofold 4 LOKI_NO_FOLD=1
+run n1_nofold 1 LOKI_NO_FOLD=1
