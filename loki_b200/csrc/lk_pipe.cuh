@@ -212,6 +212,9 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, double (&v)[8]) {
 #ifndef LK_PIPE_FOLD
 #define LK_PIPE_FOLD 1
 #endif
+#ifndef LK_PIPE_EDGE_FIRST
+#define LK_PIPE_EDGE_FIRST 0
+#endif
 
 // EK: 1 = RK4 stage 1 (delta = w rhs), 2 = stages 2,3 (delta += w rhs), 3 = stage 4 (pred = f_old + c (delta + w rhs))
 // NMOM: velocity moments of the new predictor left behind (0, 1: sum f, 3: + sum vx f, sum vy f)
@@ -259,7 +262,13 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
     r -= jy * gy * hv;
     const int hy = min(gy, nt1 - jy * gy);
     o1 = (jy * gy + r % hy) * T1;
-    o2 = (jv * gv + r / hy) * T2;
+    int iv = jv * gv + r / hy;
+#if LK_PIPE_EDGE_FIRST
+    // the two vx tiles that carry the folded velocity-boundary fill do a little more per plane: schedule them first
+    // instead of leaving the top one for the last, partly filled wave
+    if (nt2 > 2) iv = (iv == 0) ? 0 : ((iv == 1) ? nt2 - 1 : iv - 1);
+#endif
+    o2 = iv * T2;
   }
   // tile subsets (bcfold bits 4-5: 1 = only the tiles on a face of a cut direction, 2 = only the others; bits 6-7: the
   // cut directions, 1 x, 2 y): a rank whose configuration space is cut launches the face tiles first, so that the halo
