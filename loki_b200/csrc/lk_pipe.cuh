@@ -21,6 +21,11 @@
 //     issues the TMA for exactly that region itself -- no barrier between draining and refilling.
 //   * CTAs are rasterised in supertiles of gy x gv (y, vx) tiles over all x, so the y and vx star halos of a
 //     tile are the core boxes of CTAs resident at the same time (L2 hits instead of DRAM re-reads).
+//   * setAccelerationBCs4D (KineticSpeciesF.f:1036-1162) is folded into the tiles at the ends of the vx range and into
+//     the first / last planes of the march (`bcfold`): the caller keeps the inflow sample in the velocity ghost layers,
+//     the kernel overwrites the STAGED copy of an outflow column's ghosts with the extrapolation before it is read.
+//   * a launch can be restricted to the tiles on the faces of the cut directions, or to the others (`bcfold` bits
+//     4-7, lk_rk_update.tile_set): the two launches together are one, bit for bit.
 //
 // Reference arithmetic restated: KineticSpeciesF.f:723-790, 914-979 (fits), 1949-2245 (derivatives), 10-38
 // (xpby4d); RK4Integrator.H:149-171; ReductionSchedule.C:421-444 (moments of the new predictor).
