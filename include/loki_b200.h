@@ -106,6 +106,12 @@ typedef struct lk_rk_update {
                              rewritten nor invalidated (lk_vlasov_stage_folds_bcs tells whether a given call does this).
                              0, or a call the pipelined kernel does not take: lk_set_acceleration_bcs_4d runs on f first and
                              WRITES f's velocity ghosts (f is then no longer preset) */
+  const double* krook_nu; /* non-NULL: completeRHS's Krook layer (KineticSpecies.C:1049-1062, appendkrook_): where
+                             nu(n1d,n2d) != 0, rhs -= nu / krook_dt * (f - f_IC) before the update, f_IC sampled from
+                             krook_ic's tables (kinds 1, 2, 4).  Applied by the per-cell epilogue of the generic kernels
+                             (the pipelined kernel is not taken); with rhs_out the stored rhs includes the term */
+  double krook_dt;        /* the step's dt (the a_dt of completeRHS) */
+  const struct lk_inflow* krook_ic;
   int tile_set;           /* 0: the whole box.  1: only the CTA tiles (32 x 8 cells in x, y) that touch a face of a
                              direction named in cut_dirs; 2: only the others.  The two launches together equal one launch
                              with 0, bit for bit; a rank of a decomposed run issues 1, starts the halo exchange of pred, then

@@ -86,7 +86,8 @@ int lk_vp_set_inflow2(lk_vp_system* sys, int s, int kind, const double* fx, cons
  * (VPSystem.C:819-821, KineticSpecies.H:421-453).  Non-periodic directions need a single rank.
  * lk_vp_set_krook: nu (n1d,n2d) of this rank incl. ghosts, host pointer (KrookLayer::initialize, KrookLayer.C:54-160);
  * completeRHS then adds -nu/dt (f - f_IC) to the species' rhs (KineticSpecies.C:1049-1062; f_IC from the inflow
- * tables).  NULL removes the layer.  A Krook species leaves the fused stage kernel for rhs + Krook + update passes. */
+ * tables).  NULL removes the layer.  The term is applied inside the fused stage (generic kernel's per-cell epilogue,
+ * lk_rk_update.krook_*); a Krook species does not take the pipelined instantiation. */
 int lk_vp_set_boundary_options(lk_vp_system* sys, int nonperiodic_x, int nonperiodic_y, int use_new_bcs);
 int lk_vp_set_krook(lk_vp_system* sys, int s, const double* nu_host);
 int lk_vp_set_time(lk_vp_system* sys, double t);

@@ -45,6 +45,7 @@ class RkUpdate(C.Structure):
                 ("pred", C.c_void_p), ("w_delta", C.c_double), ("c_pred", C.c_double),
                 ("use_delta", C.c_int), ("n_prev", C.c_int), ("k_prev", C.c_void_p * 7),
                 ("c_prev", C.c_double * 7), ("wrap", C.c_int), ("accel_bcs", C.c_void_p), ("inflow_preset", C.c_int),
+                ("krook_nu", C.c_void_p), ("krook_dt", C.c_double), ("krook_ic", C.c_void_p),
                 ("tile_set", C.c_int), ("cut_dirs", C.c_int)]
 
 

@@ -297,6 +297,10 @@ static int stage_impl(double* rhs_out, const double* f, const lk_geom* g, const 
   cudaStream_t st = (cudaStream_t)stream;
   // setaccelerationbcs4d_ on behalf of the caller: folded into the pipelined kernel's boundary tiles, or run here
   lk_rk_update upd_local;
+  if (upd && upd->krook_nu) {
+    if (!upd->krook_ic || !(upd->krook_dt != 0.0) || !inflow_tables_ok(upd->krook_ic) || upd->krook_ic->kind == 3 || upd->krook_ic->kind == 0)
+      return fail(LK_ERR_ARG, "lk_vlasov_stage: the Krook term needs krook_dt != 0 and initial-condition tables of kind 1, 2 or 4");
+  }
   if (upd && upd->tile_set) {
     if (upd->tile_set < 0 || upd->tile_set > 2 || !(upd->cut_dirs & 3)) return fail(LK_ERR_ARG, "lk_vlasov_stage: bad tile_set / cut_dirs");
     if (!lk_vlasov_stage_can_split(rhs_out, g, a, upd)) return fail(LK_ERR_UNSUPPORTED, "lk_vlasov_stage: tile_set needs the pipelined kernel");

@@ -42,6 +42,13 @@ struct DAccel {
   double norm, bz;
 };
 
+// the initial-condition tables behind lk_inflow (inflow_value below samples them)
+struct DInflow {
+  int kind;
+  const double *fx, *fv, *fx2, *fv2, *ghost3, *ghost4;
+  double fnorm, frac;
+};
+
 struct DUpd {
   const double* f_old;
   const double* delta_in;
@@ -54,6 +61,11 @@ struct DUpd {
   const double* k_prev[7];
   double c_prev[7];
   int wrap;  // bit 0 / 1: write the periodic x / y ghost copies of pred too
+  // Krook layer of completeRHS (KineticSpecies.C:1049-1062, appendkrook KineticSpeciesF.f:2995-3034): where nu(x,y) != 0,
+  // rhs -= nu/dt (f - f_IC) before the stage update; nullptr = none
+  const double* krook_nu;
+  double krook_dt;
+  DInflow krook_ic;
 };
 
 __device__ __forceinline__ i64 gidx(const DGeo& g, int i1, int i2, int i3, int i4) {
@@ -107,11 +119,6 @@ __device__ __forceinline__ double accel_y(const DAccel& a, const DGeo& g, int i1
 __device__ __forceinline__ double bc_extrap(double a, double b, double c) {
   return ADD(ADD(MUL(3.0, a), -MUL(3.0, b)), c);
 }
-struct DInflow {
-  int kind;
-  const double *fx, *fv, *fx2, *fv2, *ghost3, *ghost4;
-  double fnorm, frac;
-};
 __device__ __forceinline__ double inflow_value(const DInflow& ic, const DGeo& g, int i1, int i2, int i3, int i4,
                                                int dir) {
   const i64 pxy = i1 + (i64)g.nd[0] * i2;
@@ -135,6 +142,14 @@ __device__ __forceinline__ double inflow_value(const DInflow& ic, const DGeo& g,
     default:
       return 0.0;
   }
+}
+
+// appendkrook (KineticSpeciesF.f:3021-3026) for one cell, the reference's expression
+__device__ __forceinline__ double krook_term(const DUpd& u, const DGeo& g, double rhs, double f, int i1, int i2, int i3, int i4) {
+  const double nu = __ldg(u.krook_nu + i1 + (i64)g.nd[0] * i2);
+  if (nu == 0.0) return rhs;
+  const double f0 = inflow_value(u.krook_ic, g, i1, i2, i3, i4, 3);
+  return rhs - nu / u.krook_dt * (f - f0);
 }
 
 // ---------------------------------------------------------------------------------------------

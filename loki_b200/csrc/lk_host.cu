@@ -621,7 +621,7 @@ struct VPSystem {
         ke_coef[ke_ncoef++] = dt * coef[stage];
       }
       static const bool no_fuse = getenv("LK_NO_FUSED_MOMENTS") != nullptr;  // debugging aid
-      const bool fused_moments = !lk_get_strict() && !no_fuse && !ks->has_krook;
+      const bool fused_moments = !lk_get_strict() && !no_fuse;
       // completeRHS: the driver's energy input rate, integrated with the state (KineticSpecies.C:1084-1093).
       // Production: from the vx moment of f_eval that the previous stage kernel left behind (consumed
       // here, before this stage's kernel overwrites the partial buffer).
@@ -633,9 +633,17 @@ struct VPSystem {
       }
       // production: the kernel also writes pred's periodic ghost copies in the directions this rank wraps itself
       u.wrap = fused_moments ? ks->wrapFor(uncutDirs() & ~ks->nonperiodic) : 0;
-      if (ks->has_krook) {
-        // completeRHS's Krook layer sits between the rhs and the stage update (KineticSpecies.C:1049-1062): rhs
-        // materialised (RK6: in m_k[stage], RK4: in a scratch array), damped, then the update alone
+      static const bool krook_passes = getenv("LOKI_KROOK_PASSES") != nullptr;  // debugging aid: the three-pass form
+      if (ks->has_krook && !krook_passes) {
+        // completeRHS's Krook layer (KineticSpecies.C:1049-1062) inside the fused stage: the per-cell epilogue of the
+        // generic kernel subtracts nu/dt (f - f_IC) from the rhs before the update (and before m_k[stage] is stored)
+        u.krook_nu = ks->krook_nu.p;
+        u.krook_dt = dt;
+        u.krook_ic = &ks->inflow;
+        LKH_CHECK(lk_vlasov_stage(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, fused_moments ? &ks->mom : nullptr, st));
+      } else if (ks->has_krook) {
+        // the same as three passes: rhs materialised (RK6: in m_k[stage], RK4: in a scratch array), damped, then the
+        // update alone
         if (!rhs_out) {
           if (!ks->rhs_tmp.p) LKH_CHECK(ks->rhs_tmp.alloc(ks->vol));
           rhs_out = ks->rhs_tmp.p;
@@ -676,7 +684,7 @@ struct VPSystem {
       }
       ks->wrap_ptr = pred;
       ks->wrap_bits = u.wrap;
-      ks->mom_valid = fused_moments;  // moments of `pred`, the next stage's input
+      ks->mom_valid = fused_moments && !(ks->has_krook && krook_passes);  // moments of `pred`, the next stage's input
       if (ks->has_driver) {
         if (rk4) {
           static const double THIRD = 1.0 / 3.0;

@@ -58,6 +58,13 @@ static DUpd make_upd(const lk_rk_update* u) {
       d.k_prev[j] = u->k_prev[j];
       d.c_prev[j] = u->c_prev[j];
     }
+    if (u->krook_nu && u->krook_ic) {
+      const lk_inflow* ic = u->krook_ic;
+      d.krook_nu = u->krook_nu;
+      d.krook_dt = u->krook_dt;
+      d.krook_ic.kind = ic->kind; d.krook_ic.fx = ic->fx; d.krook_ic.fv = ic->fv; d.krook_ic.fx2 = ic->fx2; d.krook_ic.fv2 = ic->fv2;
+      d.krook_ic.ghost3 = ic->ghost3; d.krook_ic.ghost4 = ic->ghost4; d.krook_ic.fnorm = ic->fnorm; d.krook_ic.frac = ic->frac;
+    }
   }
   return d;
 }
@@ -536,6 +543,7 @@ k_rhs_naive(DGeo g, const double* __restrict__ f, const double* __restrict__ vel
     faces(g.s[3], ay > 0.0, ayl > 0.0, uR, uL);
     rhs = sub_flux(rhs, ay, uR, uL, g.dx[3], (1.0 / g.dx[3]) * FS);
   }
+  if (upd.krook_nu && (flags & 2)) rhs = krook_term(upd, g, rhs, p[0], i1, i2, i3, i4);  // completeRHS, after the acceleration pass
   if (rhs_out) rhs_out[idx] = rhs;
   if (upd.active) rk_update(upd, idx, rhs);
 }

@@ -360,6 +360,7 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
     else if (upd.delta_in && upd.delta_out && !upd.use_delta) ekind = 2;
     else if (upd.delta_in && !upd.delta_out && upd.use_delta) ekind = 3;
   }
+  if (upd.krook_nu) ekind = 0;  // the Krook term goes between the rhs and the update: the per-cell epilogue
   // E (times q/m) at this thread's (x,y): constant along the whole march when vel3/vel4 do not depend
   // on the velocity indices
   const double ax0 = (do_acc && simple_acc) ? __ldg(a.field + pxy) : 0.0;
@@ -664,6 +665,7 @@ k_stage_march(const DGeo g, const double* __restrict__ f, const double* __restri
           for (int c = 0; c < T2; ++c) {
             if (c < ncv) {
               const i64 idx = idx0 + c * s2;
+              if (upd.krook_nu && do_acc) res[c] = krook_term(upd, g, res[c], f[idx], o0 + ea0 + ng, o1 + eb1 + ng, o2 + c + ng, p);
               if (rhs_out) rhs_out[idx] = res[c];
               if (!upd.active) continue;
               const double dl = rk_delta(upd, res[c], upd.delta_in ? upd.delta_in[idx] : 0.0, upd.delta_in != nullptr);
@@ -836,7 +838,7 @@ static cudaError_t launch_march_cfg(const DGeo& g, const double* f, const double
     kern<<<(unsigned)ctas, NT, C::SMEM_BYTES, st>>>(g, f, vel, a, u, rhs_out, flags, nt0, nt1, nt2, chunk_len, mom, maps);
     return cudaGetLastError();
   };
-  const bool lean = tma && flags == 3 && a.kind == 0 && a.bz == 0.0 && u.n_prev == 0;
+  const bool lean = tma && flags == 3 && a.kind == 0 && a.bz == 0.0 && u.n_prev == 0 && !u.krook_nu;
   if (lean) return launch(k_stage_march<ORDER, T0, T1, T2, NT, true, true>);
   if (tma) return launch(k_stage_march<ORDER, T0, T1, T2, NT, true, false>);
   return launch(k_stage_march<ORDER, T0, T1, T2, NT, false, false>);

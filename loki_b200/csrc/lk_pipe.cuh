@@ -769,7 +769,7 @@ k_stage_pipe(const DGeo g, const double* __restrict__ f, const double* __restric
 // ---- launch ----
 static bool pipe_eligible(const DGeo& g, const DAccel& a, const DUpd& u, const double* rhs_out, int flags) {
   using C4 = PipeCfg<4>;
-  if (!u.active || rhs_out || flags != 3 || u.n_prev != 0) return false;
+  if (!u.active || rhs_out || flags != 3 || u.n_prev != 0 || u.krook_nu) return false;
   if (a.kind != 0 || a.bz != 0.0) return false;
   if ((g.n[0] % C4::T0) || (g.n[1] % C4::T1) || (g.n[2] % C4::T2)) return false;
   const bool k1 = !u.delta_in && u.delta_out && !u.use_delta;

@@ -227,3 +227,66 @@ def test_pipe_tile_subsets_add_up_to_one_launch(lk, ok, fast, n, order, stage, c
         assert lk.lk_vlasov_stage(None, d.f.data_ptr(), C.byref(d.g), d.velocities.data_ptr(), C.byref(d.accel), C.byref(u), None, None) != 0
     finally:
         lk.lk_set_rhs_variant(old)
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("stage", [1, 2, 4])
+@pytest.mark.parametrize("n,order", [((32, 8, 8, 9), 4), ((14, 9, 10, 7), 4), ((12, 10, 8, 9), 6)])
+def test_krook_term_in_the_fused_stage(lk, ok, n, order, stage, variant, mode):
+    """lk_rk_update.krook_*: the fused stage with completeRHS's Krook layer (KineticSpecies.C:1049-1062) against the
+    three passes rhs -> lk_append_krook (pinned to appendkrook_) -> lk_rk_stage_update.  Strict arithmetic: the same
+    bits; production: the fused kernel contracts the term into an FMA, 1e-13 of the cell's neighbourhood.  The
+    aligned grid would take the pipelined kernel without the layer: with it the generic kernel runs."""
+    import torch
+    import loki_b200 as lkm
+    s = Setup(ok, n, order, rough=0.3)
+    d = Dev(lk, s)
+    chk(lk, lk.lk_periodic_fill_4d(d.f.data_ptr(), C.byref(d.g), 1, 1, None), "per")
+    ic, keep = _inflow(d, s, 1)
+    n1d, n2d = s.nd[0], s.nd[1]
+    nu = np.zeros((n2d, n1d))
+    nu[:, : n1d // 3] = np.random.default_rng(4).uniform(0.1, 1.0, size=(n2d, n1d // 3))
+    dnu = d.t(nu)
+    rng = np.random.default_rng(5)
+    f_old = d.t(s.f * (1.0 + 0.01 * rng.uniform(-1, 1, size=s.f.shape)))
+    delta0 = d.t(0.001 * s.f * rng.uniform(-1, 1, size=s.f.shape))
+    old_mode, old_var = lk.lk_set_strict(mode), lk.lk_set_rhs_variant(variant)
+    try:
+        def update(pred, delta):
+            u = lkm.RkUpdate()
+            u.f_old, u.pred = f_old.data_ptr(), pred.data_ptr()
+            u.delta_in = None if stage == 1 else delta.data_ptr()
+            u.delta_out = None if stage == 4 else delta.data_ptr()
+            u.w_delta, u.c_pred, u.use_delta = 0.0123, 0.05, int(stage == 4)
+            return u
+        # three passes
+        rhs = torch.zeros_like(d.f)
+        chk(lk, lk.lk_vlasov_rhs(rhs.data_ptr(), d.f.data_ptr(), C.byref(d.g), d.velocities.data_ptr(), C.byref(d.accel), None, None), "rhs")
+        plain = rhs.clone()
+        chk(lk, lk.lk_append_krook(rhs.data_ptr(), d.f.data_ptr(), C.byref(d.g), dnu.data_ptr(), 0.037, C.byref(ic), None), "krook")
+        assert not torch.equal(plain, rhs)
+        p3, d3 = torch.full_like(d.f, 3.0), delta0.clone()
+        u3 = update(p3, d3)
+        chk(lk, lk.lk_rk_stage_update(rhs.data_ptr(), C.byref(d.g), C.byref(u3), None), "update")
+        # fused
+        p1, d1 = torch.full_like(d.f, 3.0), delta0.clone()
+        u1 = update(p1, d1)
+        u1.krook_nu, u1.krook_dt, u1.krook_ic = dnu.data_ptr(), 0.037, C.addressof(ic)
+        before = lk.lk_pipe_launch_count()
+        chk(lk, lk.lk_vlasov_stage(None, d.f.data_ptr(), C.byref(d.g), d.velocities.data_ptr(), C.byref(d.accel), C.byref(u1), None, None), "stage")
+        torch.cuda.synchronize()
+        assert lk.lk_pipe_launch_count() == before
+        if mode == 1:
+            assert torch.equal(p1, p3) and torch.equal(d1, d3)
+        else:
+            scale = np.maximum(np.abs(s.f), 1e-3 * np.abs(s.f).max())
+            assert star_rel_err(p1.cpu().numpy(), p3.cpu().numpy(), scale, s.ng) <= 1e-13
+            if stage != 4:
+                assert star_rel_err(d1.cpu().numpy(), d3.cpu().numpy(), 1e-2 * scale, s.ng) <= 1e-12
+        # a layer without tables is refused
+        u1.krook_ic = None
+        assert lk.lk_vlasov_stage(None, d.f.data_ptr(), C.byref(d.g), d.velocities.data_ptr(), C.byref(d.accel), C.byref(u1), None, None) != 0
+    finally:
+        lk.lk_set_strict(old_mode)
+        lk.lk_set_rhs_variant(old_var)
