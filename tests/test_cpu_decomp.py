@@ -143,6 +143,25 @@ def test_halo_exchange_and_rho_gather_world2_gloo(px, py, nglobal, ng):
         assert ok_rho, "rank %d: gathered rho tiles do not assemble to the global field" % rank
 
 
+@pytest.mark.parametrize("px,py,nglobal,ng", [(2, 2, (9, 11), 2), (1, 4, (8, 21), 3)])
+def test_halo_exchange_world4_gloo_uneven_tiles(px, py, nglobal, ng):
+    """four ranks: a 2 x 2 grid with remainders in both directions (5+4, 6+5: the y messages span the x ghosts just
+    received, which is what fills the corner cells) and the y-only grid bench.py uses (1 x 4, tiles 6+5+5+5)"""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 4, port, px, py, nglobal, ng, out)) for r in range(4)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1, 2, 3]
+    for rank, ok_halo, ok_rho in res:
+        assert ok_halo, "rank %d: ghost cells differ from the periodic global array" % rank
+
+
 def _dt_worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
