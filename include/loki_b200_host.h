@@ -160,6 +160,11 @@ const double* lk_vp_rho_ptr(const lk_vp_system* sys);
  * *written receives the count.  Local to this rank: sums / maxima over ranks are the caller's
  * (Loki_Utilities::getSum / getMaxValue).  Synchronises. */
 int lk_vp_time_history(lk_vp_system* sys, double* out, int capacity, int* written);
+/* The probe histories of Poisson::accumulateSequences (Poisson.C:852-887): out[2k], out[2k+1] = Ex, Ey of the last
+ * evalRHS at the cell floor(frac_x[k] * Nx), floor(frac_y[k] * Ny) (global cell indices; Simulation.C:393-412 reads
+ * `number_of_probes` / `probe.N.location`, default one probe at (0.5, 0): the reference assigns m_probes[X1][0] twice).
+ * A rank reports the probes inside its own tile, 0 for the others: add over ranks.  Synchronises. */
+int lk_vp_probe_history(lk_vp_system* sys, int nprobes, const double* frac_x, const double* frac_y, double* out);
 /* The flux histories of KineticSpecies::accumulateSequencesCommon (KineticSpecies.C:2052-2097): per species the
  * kinetic-energy flux through the eight phase-space boundaries, out[8 s + 2 dir + side] (dir 0..3 = x, y, vx, vy; side
  * 0 = low), 8 * nspecies values.  Uses the face accelerations of the last evalRHS, as the reference does; rewrites the

@@ -1354,6 +1354,27 @@ int lk_vp_time_history(lk_vp_system* h, double* out, int capacity, int* written)
   *written = count;
   return LK_OK;
 }
+int lk_vp_probe_history(lk_vp_system* h, int nprobes, const double* frac_x, const double* frac_y, double* out) {
+  // Poisson::accumulateSequences, the probe part (Poisson.C:852-860): E at the cell floor(frac * N) of each probe, from
+  // the field of the last evalRHS; a rank reports the probes inside its own tile and 0 for the others (summed over
+  // ranks by the caller, Poisson.C:878-887)
+  if (!h || nprobes < 0 || (nprobes > 0 && (!frac_x || !frac_y || !out))) return LK_ERR_ARG;
+  auto& S = h->sys;
+  if (cudaStreamSynchronize(S.st) != cudaSuccess) return LK_ERR_CUDA;
+  const size_t pl = (size_t)S.n1d_g * S.n2d_g;
+  for (int k = 0; k < nprobes; ++k) {
+    const int ip = (int)floor(frac_x[k] * S.desc.nglobal[0]), jp = (int)floor(frac_y[k] * S.desc.nglobal[1]);
+    out[2 * k] = out[2 * k + 1] = 0.0;
+    if (ip < S.desc.tile_lo[0] || ip >= S.desc.tile_lo[0] + S.desc.tile_n[0] || jp < S.desc.tile_lo[1] ||
+        jp >= S.desc.tile_lo[1] + S.desc.tile_n[1])
+      continue;
+    const size_t o = (size_t)(ip + S.ng) + (size_t)S.n1d_g * (jp + S.ng);
+    if (cudaMemcpy(&out[2 * k], S.em_g.p + o, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(&out[2 * k + 1], S.em_g.p + pl + o, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+      return LK_ERR_CUDA;
+  }
+  return LK_OK;
+}
 int lk_vp_flux_history(lk_vp_system* h, double* out, int capacity, int* written) {
   // KineticSpecies::accumulateSequencesCommon (KineticSpecies.C:2052-2097): the kinetic-energy flux of every species
   // through the eight phase-space boundaries, straight from the state (lk_ke_flux_boundaries: no face / flux arrays).

@@ -51,6 +51,8 @@ class Deck:
         # Krook layer is Species.krook = dict(x1a=, x1b=, x2a=, x2b=, coefficient=) with absent ends = the domain's
         self.periodic = (True, True)
         self.use_new_bcs = False
+        # probe locations as fractions of the domain (Simulation.C:393-412; the default's y fraction is 0 there)
+        self.probes = [(0.5, 0.0)]
 
     def krook_nu(self, sp, tile_lo=(0, 0), tile_n=None):
         """KrookLayer::initialize (KrookLayer.C:54-160): nu (n2d, n1d) of a tile, ghosts zero; None without a layer"""

@@ -83,6 +83,7 @@ _PROTOS = {
     "lk_vp_download_state": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "lk_vp_upload_next": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "lk_vp_adopt_next": (C.c_int, [_vp]),
+    "lk_vp_probe_history": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "lk_vp_flux_history": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int)]),
     "lk_vm_time_history": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int)]),
 }

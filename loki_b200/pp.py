@@ -236,6 +236,13 @@ def deck_from_params(params, name="deck"):
     # Simulation's defaults (Simulation.C:166-181): final_time 1, save_times 1, sequence_write_times 1, max_step 0
     deck.run = dict(final_time=_f(params, "final_time", 1.0), save_times=_f(params, "save_times", 1.0),
                     sequence_write_times=_f(params, "sequence_write_times", 1.0), max_step=int(_f(params, "max_step", 0.0)))
+    # probes (Simulation.C:393-412): fractions of the domain; without number_of_probes one probe at (0.5, 0) -- the
+    # reference assigns m_probes[X1][0] twice and leaves the y fraction at 0
+    if "number_of_probes" in params:
+        npr = int(_f(params, "number_of_probes"))
+        deck.probes = [tuple(float(t) for t in params["probe.%d.location" % (k + 1)][:2]) for k in range(npr)]
+    else:
+        deck.probes = [(0.5, 0.0)]
     if isinstance(params, Params):
         left = sorted(key for key in params.keys() if key not in params.used and not _IGNORABLE.match(key))
         if left:

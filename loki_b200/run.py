@@ -95,6 +95,18 @@ class Runner:
         assert got.value == out.size
         return out
 
+    def probes(self):
+        """the probe time histories (Poisson.C:852-887): (Ex, Ey) of the last field solve at every probe of the deck
+        (Simulation.C:393-412; default: one probe at the fractions (0.5, 0)); Vlasov-Poisson systems"""
+        if self.vm:
+            raise NotImplementedError("probe histories of the Vlasov-Maxwell system")
+        locs = getattr(self.deck, "probes", None) or [(0.5, 0.0)]
+        fx = np.array([p[0] for p in locs], dtype=np.float64)
+        fy = np.array([p[1] for p in locs], dtype=np.float64)
+        out = np.zeros(2 * len(locs))
+        capi.check(self.H.lk_vp_probe_history(self.sys, len(locs), fx.ctypes.data, fy.ctypes.data, out.ctypes.data), "probe_history")
+        return out.reshape(len(locs), 2)
+
     def flux_history(self):
         """the `*_flux` time histories (KineticSpecies.C:2052-2097): per species the kinetic-energy flux through the
         eight phase-space boundaries, [8 s + 2 dir + side]; Vlasov-Poisson systems"""
@@ -169,6 +181,15 @@ def main(argv=None):
         rec = dict(step=r.step, time=r.time, dt=dt)
         if r.record or ap_every:   # time histories are collected every sequence_write_times (Simulation.C:318-321)
             rec.update(zip(names, r.history().tolist()))
+            if not r.vm:
+                # probes (Poisson.C:852-887) and the eight kinetic-energy fluxes per species (KineticSpecies.C:2052-2097)
+                for k, (ex, ey) in enumerate(r.probes().tolist()):
+                    rec["probe%d_ex" % (k + 1)], rec["probe%d_ey" % (k + 1)] = ex, ey
+                fl = r.flux_history().tolist()
+                for s_, sp in enumerate(deck.species):
+                    for d_, dn in enumerate(("x", "y", "vx", "vy")):
+                        for side, sn in enumerate(("lo", "hi")):
+                            rec["%s_ke_flux_%s_%s" % (sp.name, dn, sn)] = fl[8 * s_ + 2 * d_ + side]
         print(json.dumps(rec))
     r.close()
     return 0

@@ -372,6 +372,9 @@ def test_pp_reader_boundary_options_and_krook_layer():
     from loki_b200 import pp
     d = pp.deck_from_params(pp.parse(VP_OPTIONS_DECK), name="opts")
     assert d.periodic == (False, True) and d.use_new_bcs
+    assert d.probes == [(0.5, 0.0)]     # Simulation.C:408-412: the default probe's y fraction stays 0
+    dp = pp.deck_from_params(pp.parse(VP_OPTIONS_DECK + "number_of_probes = 2\nprobe.1.location = 0.25 0.5\nprobe.2.location = 0.9 0.1\n"))
+    assert dp.probes == [(0.25, 0.5), (0.9, 0.1)]
     assert d.species[0].krook == dict(x1a=-6.0, x1b=7.0, coefficient=0.5, power=3.0)
     nu = d.krook_nu(d.species[0])
     ng = d.ng
@@ -399,7 +402,7 @@ def _deck_fields(a, b, path=""):
             assert len(va) == len(vb)
             for i_, (sa, sb) in enumerate(zip(va, vb)):
                 out += _deck_fields(sa, sb, path + "species[%d]." % i_)
-        elif key not in ("name", "run") and va != vb:
+        elif key not in ("name", "run", "probes") and va != vb:
             out.append((path + key, va, vb))
     return out
 

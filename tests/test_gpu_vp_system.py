@@ -791,3 +791,49 @@ def test_streaming_state_equals_blocking_state_io(lk, ok, fast):
             got = pin_out[k][s].numpy().reshape(states[s].shape)
             assert np.array_equal(got[I], want[k][s][I]), (k, s)
     H.lk_vp_destroy(sys_)
+
+
+@pytest.mark.parametrize("mode", ["strict", "production"])
+def test_probe_histories(lk, ok, mode):
+    """the probe time histories (Poisson.C:852-887): E of the last field solve at the cell floor(frac * N) of every
+    probe, against the oracle's field -- strict: the same bits, production: 1e-8 of the field's maximum"""
+    from loki_b200 import run
+    deck = decks.plane_iaw(n=(16, 8), nv=(24, 16))
+    deck.probes = [(0.5, 0.0), (0.26, 0.51), (0.999, 0.999), (0.0, 0.3)]
+    deck.run = dict(final_time=1.0, save_times=1.0, max_step=1000000)
+    old = lk.lk_set_strict(1 if mode == "strict" else 0)
+    try:
+        r = run.Runner(deck)
+        w, sp, keep = _oracle(ok, deck)
+        ns = len(deck.species)
+        f_old = [deck.initial_state(s)[0] for s in deck.species]
+        f_new = [np.zeros_like(f) for f in f_old]
+        ng = deck.ng
+        n1d, n2d = deck.n[0] + 2 * ng, deck.n[1] + 2 * ng
+        ke = np.zeros(ns)
+        t, dt = 0.0, 0.05
+        for _ in range(3):
+            capi_ok = r.H.lk_vp_set_time(r.sys, t) == 0 and r.H.lk_vp_advance(r.sys, dt) == 0
+            assert capi_ok
+            ok.ok_vp_rk4_step(w, _ptrs(f_new), _ptrs(f_old), t, dt, ke)
+            f_old, f_new = f_new, f_old
+            t += dt
+        em_o = np.ctypeslib.as_array(ok.ok_vp_em_vars(w), shape=(2, n2d, n1d))
+        got = r.probes()
+        assert got.shape == (4, 2)
+        scale = np.max(np.abs(em_o))
+        for k, (fx, fy) in enumerate(deck.probes):
+            ip, jp = int(np.floor(fx * deck.n[0])), int(np.floor(fy * deck.n[1]))
+            want = em_o[:, jp + ng, ip + ng]
+            if mode == "strict":
+                assert got[k, 0] == want[0] and got[k, 1] == want[1], k
+            else:
+                # three steps into the run the field is still the response to a driver at 1e-3 of its amplitude: it carries
+                # the summation-order noise of a charge density that cancels to 1e-10 of its terms (the short-run note of
+                # tests/test_gpu_deck_grids.py); the regression-run tests hold the field traces to 1e-10
+                assert np.max(np.abs(got[k] - want)) <= 1e-8 * scale, k
+        assert np.any(got != 0.0)
+        r.close()
+        ok.ok_vp_work_destroy(w)
+    finally:
+        lk.lk_set_strict(old)
