@@ -275,6 +275,33 @@ int lk_maxwell_vz_rhs(double* dvz, const double* em, int n1, int n2, int ng, dou
 int lk_append_krook(double* rhs, const double* u, const lk_geom* g, const double* nu, double dt, const lk_inflow* ic,
                     void* stream);
 
+/* ---- pitch-angle collision operator (PitchAngleCollisionOperator.C, PitchAngleCollisionOperatorF.f) ----
+ * The operator's input keys (PitchAngleCollisionOperator::parseParameters, PitchAngleCollisionOperator.C:195-270). */
+typedef struct lk_pitch_angle {
+  double range_lo[2], range_hi[2]; /* collision_vel_range_lo / _hi (vx, vy)                                  */
+  double vfloor;                   /* collision_vfloor                                                         */
+  double vthermal_dt;              /* collision_vthermal_dt: only the time-step estimate uses it (computeRealLam) */
+  double nu_coef;                  /* collision_nuCoeff                                                        */
+  int conservative;                /* collision_conservative (default 1); 0 is defined for order 4 only        */
+} lk_pitch_angle;
+/* The reduced fields every evaluate() starts with (PitchAngleCollisionOperator.C:69-117:
+ * computepitchanglespeciesmoments_, three velocity-space sums times dvx dvy, ...reducedfields_, ...kec_, one more sum,
+ * ...vthermal_): flow velocity IVx, IVy and thermal speed IVth of max(|u|, 1e-10), each (n1d,n2d) device, over the
+ * whole configuration data box.  Sums in the reference's order (bit for bit); the rank must hold all of velocity space. */
+int lk_pitch_angle_fields(double* IVx, double* IVy, double* IVth, const double* u, const lk_geom* g,
+                          const double* velocities, void* stream);
+/* appendpitchanglecollision_ (PitchAngleCollisionOperatorF.f:1618-1702): rhs += C(f) on the interior cells; f's velocity
+ * ghosts must be filled.  vlo / vhi: the velocity domain (xlo(3:4), xhi(3:4)).  Conservative order 4 / 6: the scheme of
+ * the reference's generated code in operator form (equal to rounding, see lk_coll.cuh); non-conservative order 4: bit
+ * for bit; non-conservative order 6 applies nothing, as in the reference.  Non-relativistic. */
+int lk_append_pitch_angle_collision(double* rhs, const double* f, const lk_geom* g, const double* velocities,
+                                    const double* IVx, const double* IVy, const double* IVth, const double* vlo,
+                                    const double* vhi, const lk_pitch_angle* p, void* stream);
+/* PitchAngleCollisionOperator::computeRealLam (PitchAngleCollisionOperator.C:137-144); host arithmetic, no device work */
+double lk_pitch_angle_real_lam(const lk_geom* g, const lk_pitch_angle* p);
+/* PitchAngleCollisionOperator::parseParameters' sanity checks (:253-269): LK_OK or LK_ERR_ARG with lk_last_error */
+int lk_pitch_angle_check(const lk_geom* g, const double* vlo, const double* vhi, const lk_pitch_angle* p);
+
 /* ---- time-history diagnostics (called at sequence_write_times, not on the stage path) ----
  * computeke_ / computekemaxwell_ (KineticSpeciesF.f:2447-2559): out5_dev = {ke, ke_x, ke_y, px, py}; with
  * vz != NULL the Maxwell flavour: ke includes 0.5 m vz(x,y)^2 f and px = py = 0.  Tree sums (deterministic). */

@@ -128,6 +128,37 @@ void appendkrook_(const int* nd1a, const int* nd1b, const int* nd2a, const int* 
                   const int* nd4a, const int* nd4b, const int* n1a, const int* n1b, const int* n2a, const int* n2b,
                   const int* n3a, const int* n3b, const int* n4a, const int* n4b, const double* dt, const int64_t* ic,
                   const double* nu, const double* u, double* rhs);
+/* ---- PitchAngleCollisionOperatorF.H:13-17, 24-134 (PitchAngleCollisionOperatorF.f:1618-1852) ----
+ * Arrays on the device; xlo / xhi / dx / range_lo / range_hi / dparams / iparams are host references
+ * (PROBLEMDOMAIN_TO_FORT and the operator's parameter vectors: dparams = {vfloor, vthermal_dt, nuCoeff},
+ * iparams = {conservative, solution_order, do_relativity}; do_relativity must be 0). */
+void appendpitchanglecollision_(double* rhs, const double* f, const double* velocities, const double* ivx, const double* ivy,
+                                const double* vth, const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b,
+                                const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b, const int* n1a,
+                                const int* n1b, const int* n2a, const int* n2b, const int* n3a, const int* n3b,
+                                const int* n4a, const int* n4b, const double* xlo, const double* xhi, const double* dx,
+                                const double* range_lo, const double* range_hi, const double* dparams, const int* iparams);
+/* :1706-1750: rn, rgammax, rgammay (n1d,n2d) = sums of max(|u|, 1e-10) {1, vx, vy} over the interior velocity cells */
+void computepitchanglespeciesmoments_(double* rn, double* rgammax, double* rgammay, const double* u, const int* nd1a,
+                                      const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a, const int* nd3b,
+                                      const int* nd4a, const int* nd4b, const int* n1a, const int* n1b, const int* n2a,
+                                      const int* n2b, const int* n3a, const int* n3b, const int* n4a, const int* n4b,
+                                      const double* velocities);
+/* :1754-1781: vx = gammax / n, vy = gammay / n */
+void computepitchanglespeciesreducedfields_(double* vx, double* vy, const double* n, const double* gammax,
+                                            const double* gammay, const int* nd1a, const int* nd1b, const int* nd2a,
+                                            const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a,
+                                            const int* nd4b);
+/* :1785-1824: rkec += sum of ((vx - rvx0)^2 + (vy - rvy0)^2) max(|u|, 1e-10) */
+void computepitchanglespecieskec_(double* rkec, const double* rvx0, const double* rvy0, const double* u, const int* nd1a,
+                                  const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a, const int* nd3b,
+                                  const int* nd4a, const int* nd4b, const int* n1a, const int* n1b, const int* n2a,
+                                  const int* n2b, const int* n3a, const int* n3b, const int* n4a, const int* n4b,
+                                  const double* velocities);
+/* :1828-1852: vthsq = sqrt(0.5 kec / n) */
+void computepitchanglespeciesvthermal_(double* vthsq, const double* kec, const double* n, const int* nd1a, const int* nd1b,
+                                       const int* nd2a, const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a,
+                                       const int* nd4b);
 /* PoissonF.H (PoissonF.f:10-64): rhs -= mean(rhs) over the interior; comm is ignored (one rank solves) */
 void neutralizecharge4d_(const int* md1a, const int* md1b, const int* md2a, const int* md2b, const int* n1a, const int* n1b,
                          const int* n2a, const int* n2b, double* rhs, const int* comm);

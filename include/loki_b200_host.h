@@ -90,6 +90,12 @@ int lk_vp_set_inflow2(lk_vp_system* sys, int s, int kind, const double* fx, cons
  * lk_rk_update.krook_*); a Krook species does not take the pipelined instantiation. */
 int lk_vp_set_boundary_options(lk_vp_system* sys, int nonperiodic_x, int nonperiodic_y, int use_new_bcs);
 int lk_vp_set_krook(lk_vp_system* sys, int s, const double* nu_host);
+/* lk_vp_set_pitch_angle: a "Pitch Angle Collision Operator" on species s (KineticSpecies.C:1036-1046): every stage
+ * materialises the species' rhs, adds C(f) (lk_pitch_angle_fields + lk_append_pitch_angle_collision), then the Krook
+ * layer, then does the Runge-Kutta update (lk_rk_stage_update); lk_vp_stable_dt takes the operator's real eigenvalue
+ * into the step estimate (KineticSpecies.C:666-672).  NULL removes the operator.  Returns LK_ERR_ARG for a range the
+ * reference aborts on. */
+int lk_vp_set_pitch_angle(lk_vp_system* sys, int s, const lk_pitch_angle* p);
 int lk_vp_set_time(lk_vp_system* sys, double t);
 double lk_vp_time(const lk_vp_system* sys);
 

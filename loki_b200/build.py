@@ -41,6 +41,7 @@ def build(force=False, verbose=False):
         (["-fmad=false"], "lk_bcs.cu", "lk_bcs.o"),
         (["-fmad=false"], "lk_f77.cu", "lk_f77.o"),
         (["-fmad=false"], "lk_flux.cu", "lk_flux.o"),
+        (["-fmad=false"], "lk_coll.cu", "lk_coll.o"),
         ([], "lk_host.cu", "lk_host.o"),
     ]
     procs = []
@@ -58,6 +59,8 @@ def build(force=False, verbose=False):
             deps = [h for h in deps if not h.endswith("loki_b200_f77.h")]
         if "-DLK_STRICT=1" in flags or src != "lk_kernels.cu":  # the pipelined stage kernel: production build of lk_kernels.cu only
             deps = [h for h in deps if not h.endswith("lk_pipe.cuh")]
+        if src != "lk_coll.cu":  # the collision operator's per-cell header
+            deps = [h for h in deps if not h.endswith("lk_coll.cuh")]
         if not force and not verbose and _newer(o, [os.path.join(CSRC, src)] + deps):
             continue  # this object is current: only changed translation units are recompiled
         cmd = [nvcc] + ARCH + COMMON + extra + flags + ["-c", os.path.join(CSRC, src), "-o", o]
@@ -84,7 +87,7 @@ def build_variant(name, defines):
     cmd = [nvcc] + ARCH + COMMON + ["-DLK_STRICT=0"] + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, "lk_kernels.cu"), "-o", o]
     subprocess.check_call(cmd)
     out = os.path.join(HERE, "libloki_b200_%s.so" % name)
-    objs = [o] + [os.path.join(bdir, f) for f in ("lk_kernels_strict.o", "lk_capi.o", "lk_fft.o", "lk_diag.o", "lk_bcs.o", "lk_f77.o", "lk_flux.o", "lk_host.o")]
+    objs = [o] + [os.path.join(bdir, f) for f in ("lk_kernels_strict.o", "lk_capi.o", "lk_fft.o", "lk_diag.o", "lk_bcs.o", "lk_f77.o", "lk_flux.o", "lk_coll.o", "lk_host.o")]
     subprocess.check_call([nvcc] + ARCH + ["-shared", "-o", out] + objs)
     return out
 

@@ -49,6 +49,21 @@ class RkUpdate(C.Structure):
                 ("tile_set", C.c_int), ("cut_dirs", C.c_int)]
 
 
+class PitchAngle(C.Structure):
+    """lk_pitch_angle: the keys of PitchAngleCollisionOperator::parseParameters"""
+    _fields_ = [("range_lo", C.c_double * 2), ("range_hi", C.c_double * 2), ("vfloor", C.c_double),
+                ("vthermal_dt", C.c_double), ("nu_coef", C.c_double), ("conservative", C.c_int)]
+
+    @staticmethod
+    def make(range_lo, range_hi, vfloor, vthermal_dt, nu_coef, conservative=1):
+        p = PitchAngle()
+        for k in range(2):
+            p.range_lo[k] = float(range_lo[k])
+            p.range_hi[k] = float(range_hi[k])
+        p.vfloor, p.vthermal_dt, p.nu_coef, p.conservative = float(vfloor), float(vthermal_dt), float(nu_coef), int(conservative)
+        return p
+
+
 class StageMoments(C.Structure):
     _fields_ = [("nmom", C.c_int), ("partial", C.c_void_p), ("capacity", C.c_int64)]
 
@@ -115,6 +130,12 @@ _PROTOS = {
     "lk_maxwell_vz_rhs": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp]),
     "lk_f77_status": (C.c_int, []),
     "lk_append_krook": (C.c_int, [_vp, _vp, C.POINTER(Geom), _vp, C.c_double, C.POINTER(Inflow), _vp]),
+    "lk_pitch_angle_fields": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(Geom), _vp, _vp]),
+    "lk_append_pitch_angle_collision": (C.c_int, [_vp, _vp, C.POINTER(Geom), _vp, _vp, _vp, _vp, C.POINTER(C.c_double * 2),
+                                                  C.POINTER(C.c_double * 2), C.POINTER(PitchAngle), _vp]),
+    "lk_pitch_angle_real_lam": (C.c_double, [C.POINTER(Geom), C.POINTER(PitchAngle)]),
+    "lk_pitch_angle_check": (C.c_int, [C.POINTER(Geom), C.POINTER(C.c_double * 2), C.POINTER(C.c_double * 2),
+                                       C.POINTER(PitchAngle)]),
     "lk_compute_ke": (C.c_int, [_vp, _vp, C.POINTER(Geom), C.c_double, _vp, _vp, _vp]),
     "lk_field_history": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), _vp]),
     "lk_malloc": (C.c_int, [C.POINTER(_vp), C.c_int64]),

@@ -124,6 +124,14 @@ cudaError_t append_krook(double* rhs, const double* u, const lk_geom* g, const d
 cudaError_t set_bcs_jb(double* f, const lk_geom* g, const lk_accel* a, const double* velocities, const lk_inflow* ic,
                        const int sides[8], cudaStream_t st, int64_t* launches);
 }
+// lk_coll.cu: pitch-angle collision operator
+namespace lkcoll {
+cudaError_t fields(double* ivx, double* ivy, double* vth, const double* u, const lk_geom* g, const double* velocities,
+                   cudaStream_t st, int64_t* launches);
+cudaError_t append(double* rhs, const double* f, const lk_geom* g, const double* velocities, const double* ivx,
+                   const double* ivy, const double* vth, const double vlo[2], const double vhi[2],
+                   const lk_pitch_angle* pa, cudaStream_t st, int64_t* launches);
+}
 // lk_diag.cu: time-history diagnostics
 namespace lkdiag {
 int ke_scratch_doubles();
@@ -221,6 +229,41 @@ static int inflow_tables_ok(const lk_inflow* ic) {
   if ((ic->kind == 2 && (!ic->fx2 || !ic->fv2)) || (ic->kind == 4 && !ic->fx2)) return 0;
   if (ic->kind == 3 && (!ic->ghost3 || !ic->ghost4)) return 0;
   return 1;
+}
+int lk_pitch_angle_check(const lk_geom* g, const double* vlo, const double* vhi, const lk_pitch_angle* p) {
+  if (!geom_ok(g) || !vlo || !vhi || !p) return fail(LK_ERR_ARG, "lk_pitch_angle_check: bad argument");
+  if (p->conservative != 1 && g->order == 6)
+    return fail(LK_ERR_ARG, "Non-conservative operator in 6th order not supported.");  // PitchAngleCollisionOperator.C:216-218
+  // PitchAngleCollisionOperator.C:253-269
+  const double rolloff = g->order == 4 ? 3 : 4;
+  for (int k = 0; k < 2; ++k) {
+    const double vmin = vlo[k] + rolloff * g->dx[2 + k], vmax = vhi[k] - rolloff * g->dx[2 + k];
+    if (p->range_lo[k] <= vmin || p->range_hi[k] >= vmax)
+      return fail(LK_ERR_ARG, k == 0 ? "x collision_vel_range box too large" : "y collision_vel_range box too large");
+    if (p->range_lo[k] >= p->range_hi[k])
+      return fail(LK_ERR_ARG, k == 0 ? "x collision_vel_range_lo exceeds x collision_vel_range_hi"
+                                     : "y collision_vel_range_lo exceeds y collision_vel_range_hi");
+  }
+  return LK_OK;
+}
+double lk_pitch_angle_real_lam(const lk_geom* g, const lk_pitch_angle* p) {
+  if (!g || !p) return 0.0;
+  const double dv = fmin(g->dx[2], g->dx[3]);
+  const double pi = 4.0 * atan(1.0);
+  return p->nu_coef * pow(p->vthermal_dt, 3.0) * pi * pi / (dv * dv * fmax(dv, p->vfloor));
+}
+int lk_pitch_angle_fields(double* IVx, double* IVy, double* IVth, const double* u, const lk_geom* g, const double* velocities,
+                          void* stream) {
+  if (!geom_ok(g) || !IVx || !IVy || !IVth || !u || !velocities) return fail(LK_ERR_ARG, "lk_pitch_angle_fields: bad argument");
+  CHECK_LAUNCH(lkcoll::fields(IVx, IVy, IVth, u, g, velocities, (cudaStream_t)stream, &g_fft_launches), "lk_pitch_angle_fields");
+}
+int lk_append_pitch_angle_collision(double* rhs, const double* f, const lk_geom* g, const double* velocities, const double* IVx,
+                                    const double* IVy, const double* IVth, const double* vlo, const double* vhi,
+                                    const lk_pitch_angle* p, void* stream) {
+  if (!geom_ok(g) || !rhs || !f || !velocities || !IVx || !IVy || !IVth || !vlo || !vhi || !p || rhs == f)
+    return fail(LK_ERR_ARG, "lk_append_pitch_angle_collision: bad argument");
+  CHECK_LAUNCH(lkcoll::append(rhs, f, g, velocities, IVx, IVy, IVth, vlo, vhi, p, (cudaStream_t)stream, &g_fft_launches),
+               "lk_append_pitch_angle_collision");
 }
 int lk_append_krook(double* rhs, const double* u, const lk_geom* g, const double* nu, double dt, const lk_inflow* ic, void* stream) {
   if (!geom_ok(g) || !rhs || !u || !nu || !(dt != 0.0) || !inflow_tables_ok(ic)) return fail(LK_ERR_ARG, "lk_append_krook: bad argument");

@@ -11,6 +11,16 @@
 #include "../../include/loki_b200.h"
 #include "../../include/loki_b200_f77.h"
 
+// lk_coll.cu: the pieces of PitchAngleCollisionOperator::evaluate the Fortran ABI exposes one by one
+namespace lkcoll {
+cudaError_t moments(double* rn, double* rgx, double* rgy, const double* u, const lk_geom* g, const double* velocities,
+                    cudaStream_t st, int64_t* launches);
+cudaError_t kec(double* rk, const double* vx0, const double* vy0, const double* u, const lk_geom* g,
+                const double* velocities, cudaStream_t st, int64_t* launches);
+cudaError_t reduced(int mode, double* vx, double* vy, const double* n, const double* gx, const double* gy, int64_t pl,
+                    cudaStream_t st, int64_t* launches);
+}
+
 namespace {
 
 typedef long long i64;
@@ -409,6 +419,90 @@ void appendkrook_(const int* nd1a, const int* nd1b, const int* nd2a, const int* 
   if (!geom_from("appendkrook_", nd, n, 0, &g)) return;
   const lk_inflow* inflow = ic ? (const lk_inflow*)(intptr_t)*ic : nullptr;
   if (check(lk_append_krook(rhs, u, &g, nu, *dt, inflow, nullptr))) check(lk_sync(nullptr));
+}
+
+void appendpitchanglecollision_(double* rhs, const double* f, const double* velocities, const double* ivx, const double* ivy,
+                                const double* vth, const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b,
+                                const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b, const int* n1a,
+                                const int* n1b, const int* n2a, const int* n2b, const int* n3a, const int* n3b,
+                                const int* n4a, const int* n4b, const double* xlo, const double* xhi, const double* dx,
+                                const double* range_lo, const double* range_hi, const double* dparams, const int* iparams) {
+  const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
+  const int* const n[8] = {n1a, n1b, n2a, n2b, n3a, n3b, n4a, n4b};
+  lk_geom g;
+  if (!geom_from("appendpitchanglecollision_", nd, n, iparams[1], &g)) return;
+  if (iparams[2] != 0) return fail("appendpitchanglecollision_", "do_relativity = 1 is not supported");
+  for (int k = 0; k < 4; ++k) g.dx[k] = dx[k];
+  lk_pitch_angle p;
+  for (int k = 0; k < 2; ++k) {
+    p.range_lo[k] = range_lo[k];
+    p.range_hi[k] = range_hi[k];
+  }
+  p.vfloor = dparams[0];       // PitchAngleCollisionOperator.H: VFLOOR, VTHERMAL_DT, NU
+  p.vthermal_dt = dparams[1];
+  p.nu_coef = dparams[2];
+  p.conservative = (iparams[0] == 1) ? 1 : 0;
+  if (check(lk_append_pitch_angle_collision(rhs, f, &g, velocities, ivx, ivy, vth, xlo + 2, xhi + 2, &p, nullptr)))
+    check(lk_sync(nullptr));
+}
+
+void computepitchanglespeciesmoments_(double* rn, double* rgammax, double* rgammay, const double* u, const int* nd1a,
+                                      const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a, const int* nd3b,
+                                      const int* nd4a, const int* nd4b, const int* n1a, const int* n1b, const int* n2a,
+                                      const int* n2b, const int* n3a, const int* n3b, const int* n4a, const int* n4b,
+                                      const double* velocities) {
+  const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
+  const int* const n[8] = {n1a, n1b, n2a, n2b, n3a, n3b, n4a, n4b};
+  lk_geom g;
+  if (!geom_from("computepitchanglespeciesmoments_", nd, n, 0, &g)) return;
+  int64_t launches = 0;
+  if (lkcoll::moments(rn, rgammax, rgammay, u, &g, velocities, nullptr, &launches) != cudaSuccess) {
+    check(LK_ERR_CUDA);
+    return;
+  }
+  check(lk_sync(nullptr));
+}
+
+void computepitchanglespecieskec_(double* rkec, const double* rvx0, const double* rvy0, const double* u, const int* nd1a,
+                                  const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a, const int* nd3b,
+                                  const int* nd4a, const int* nd4b, const int* n1a, const int* n1b, const int* n2a,
+                                  const int* n2b, const int* n3a, const int* n3b, const int* n4a, const int* n4b,
+                                  const double* velocities) {
+  const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
+  const int* const n[8] = {n1a, n1b, n2a, n2b, n3a, n3b, n4a, n4b};
+  lk_geom g;
+  if (!geom_from("computepitchanglespecieskec_", nd, n, 0, &g)) return;
+  int64_t launches = 0;
+  if (lkcoll::kec(rkec, rvx0, rvy0, u, &g, velocities, nullptr, &launches) != cudaSuccess) {
+    check(LK_ERR_CUDA);
+    return;
+  }
+  check(lk_sync(nullptr));
+}
+
+static void reduced_2d(const char* who, int mode, double* a, double* b, const double* n, const double* gx, const double* gy,
+                       const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b) {
+  const int64_t n1d = (int64_t)*nd1b - *nd1a + 1, n2d = (int64_t)*nd2b - *nd2a + 1;
+  if (n1d < 1 || n2d < 1) return fail(who, "empty data box");
+  int64_t launches = 0;
+  if (lkcoll::reduced(mode, a, b, n, gx, gy, n1d * n2d, nullptr, &launches) != cudaSuccess) {
+    check(LK_ERR_CUDA);
+    return;
+  }
+  check(lk_sync(nullptr));
+}
+void computepitchanglespeciesreducedfields_(double* vx, double* vy, const double* n, const double* gammax,
+                                            const double* gammay, const int* nd1a, const int* nd1b, const int* nd2a,
+                                            const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a,
+                                            const int* nd4b) {
+  (void)nd3a; (void)nd3b; (void)nd4a; (void)nd4b;
+  reduced_2d("computepitchanglespeciesreducedfields_", 0, vx, vy, n, gammax, gammay, nd1a, nd1b, nd2a, nd2b);
+}
+void computepitchanglespeciesvthermal_(double* vthsq, const double* kec, const double* n, const int* nd1a, const int* nd1b,
+                                       const int* nd2a, const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a,
+                                       const int* nd4b) {
+  (void)nd3a; (void)nd3b; (void)nd4a; (void)nd4b;
+  reduced_2d("computepitchanglespeciesvthermal_", 1, vthsq, nullptr, n, kec, nullptr, nd1a, nd1b, nd2a, nd2b);
 }
 
 void neutralizecharge4d_(const int* md1a, const int* md1b, const int* md2a, const int* md2b, const int* n1a, const int* n1b,

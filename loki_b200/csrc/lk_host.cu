@@ -216,6 +216,19 @@ struct KineticSpecies {
   // the "JB" boundary conditions (use_new_bcs, VPSystem.C:819-821), non-periodic x / y (KineticSpecies.H:998-1031)
   DevBuf<double> krook_nu;
   bool has_krook = false, use_new_bcs = false;
+  // a pitch-angle collision operator (KineticSpecies.C:1036-1046; PitchAngleCollisionOperator.C): its parameters and
+  // the three reduced fields IVx, IVy, IVth (n1d,n2d) every evaluation recomputes
+  bool has_coll = false;
+  lk_pitch_angle coll;
+  DevBuf<double> coll_iv;
+  // completeRHS's collision term on a materialised rhs (PitchAngleCollisionOperator::evaluate)
+  int appendCollision(double* rhs, const double* f, void* st) {
+    const size_t pl = (size_t)n1d * n2d;
+    if (!coll_iv.p) LKH_CHECK(coll_iv.alloc(3 * pl));
+    double* iv = coll_iv.p;
+    LKH_CHECK(lk_pitch_angle_fields(iv, iv + pl, iv + 2 * pl, f, &g, velocities.p, st));
+    return lk_append_pitch_angle_collision(rhs, f, &g, velocities.p, iv, iv + pl, iv + 2 * pl, vlo, vhi, &coll, st);
+  }
   int nonperiodic = 0;              // bit 0 x, bit 1 y
   int at_xy[4] = {1, 1, 1, 1};      // this rank's tile touches x-lo, x-hi, y-lo, y-hi of the domain
   bool preset[3] = {false, false, false};
@@ -346,11 +359,15 @@ struct KineticSpecies {
     return periodicFill(f, dirs & ~nonperiodic, st);
   }
 
-  // computeDt (KineticSpecies.C:647-694) without collision operators
+  // computeDt (KineticSpecies.C:647-694); the real eigenvalue is the collision operator's (:666-672)
   double computeDt(int rk_order) const {
     const double pi = 4.0 * atan(1.0);
     double imLam = 0.0, reLam = 0.0;
     for (int dir = 0; dir < 4; ++dir) imLam += pi * lambda_max[dir] / g.dx[dir];
+    if (has_coll) {
+      const double thisReLam = lk_pitch_angle_real_lam(&g, &coll);
+      if (fabs(thisReLam) > reLam) reLam = thisReLam;
+    }
     double alpha = (rk_order == 4) ? 2.6 : 4.95, beta = (rk_order == 4) ? 2.6 : 3.168;
     return sqrt(1.0 / (reLam * reLam / (alpha * alpha) + imLam * imLam / (beta * beta)));
   }
@@ -582,7 +599,7 @@ struct VPSystem {
       lk_rk_update u;
       memset(&u, 0, sizeof(u));
       // the "JB" fill and a Krook-layer species take the separate passes below
-      const bool plain = !ks->use_new_bcs && !ks->has_krook;
+      const bool plain = !ks->use_new_bcs && !ks->has_krook && !ks->has_coll;
       static const bool no_fold = getenv("LOKI_NO_FOLD") != nullptr;  // A/B aid: the separate fill before every stage
       if (plain) {
         u.accel_bcs = &ks->inflow;
@@ -634,22 +651,25 @@ struct VPSystem {
       // production: the kernel also writes pred's periodic ghost copies in the directions this rank wraps itself
       u.wrap = fused_moments ? ks->wrapFor(uncutDirs() & ~ks->nonperiodic) : 0;
       static const bool krook_passes = getenv("LOKI_KROOK_PASSES") != nullptr;  // debugging aid: the three-pass form
-      if (ks->has_krook && !krook_passes) {
+      const bool passes = ks->has_coll || (ks->has_krook && krook_passes);  // the rhs is materialised between the passes
+      if (passes) u.wrap = 0;  // lk_rk_stage_update writes interior cells only: the next fill wraps pred itself
+      if (ks->has_krook && !passes) {
         // completeRHS's Krook layer (KineticSpecies.C:1049-1062) inside the fused stage: the per-cell epilogue of the
         // generic kernel subtracts nu/dt (f - f_IC) from the rhs before the update (and before m_k[stage] is stored)
         u.krook_nu = ks->krook_nu.p;
         u.krook_dt = dt;
         u.krook_ic = &ks->inflow;
         LKH_CHECK(lk_vlasov_stage(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, fused_moments ? &ks->mom : nullptr, st));
-      } else if (ks->has_krook) {
-        // the same as three passes: rhs materialised (RK6: in m_k[stage], RK4: in a scratch array), damped, then the
-        // update alone
+      } else if (passes) {
+        // completeRHS on a materialised rhs (RK6: in m_k[stage], RK4: in a scratch array): collision operator, then the
+        // Krook layer (KineticSpecies.C:1036-1062), then the update alone
         if (!rhs_out) {
           if (!ks->rhs_tmp.p) LKH_CHECK(ks->rhs_tmp.alloc(ks->vol));
           rhs_out = ks->rhs_tmp.p;
         }
         LKH_CHECK(lk_vlasov_rhs(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, nullptr, st));
-        LKH_CHECK(lk_append_krook(rhs_out, ks->f_eval, &ks->g, ks->krook_nu.p, dt, &ks->inflow, st));
+        if (ks->has_coll) LKH_CHECK(ks->appendCollision(rhs_out, ks->f_eval, st));
+        if (ks->has_krook) LKH_CHECK(lk_append_krook(rhs_out, ks->f_eval, &ks->g, ks->krook_nu.p, dt, &ks->inflow, st));
         LKH_CHECK(lk_rk_stage_update(rhs_out, &ks->g, &u, st));
       } else {
         const int ie = ks->arrayIndex(ks->f_eval);
@@ -684,7 +704,7 @@ struct VPSystem {
       }
       ks->wrap_ptr = pred;
       ks->wrap_bits = u.wrap;
-      ks->mom_valid = fused_moments && !(ks->has_krook && krook_passes);  // moments of `pred`, the next stage's input
+      ks->mom_valid = fused_moments && !passes;  // moments of `pred`, the next stage's input
       if (ks->has_driver) {
         if (rk4) {
           static const double THIRD = 1.0 / 3.0;
@@ -773,6 +793,7 @@ struct VPSystem {
       LKH_CHECK(ks->setAccelerationBCs(f, st));
       lk_accel a = ks->accelDesc();
       LKH_CHECK(lk_acceleration_derivatives_4d(rhs_dev[s], f, &ks->g, &a, st));
+      if (ks->has_coll) LKH_CHECK(ks->appendCollision(rhs_dev[s], f, st));
       if (ks->has_krook) LKH_CHECK(lk_append_krook(rhs_dev[s], f, &ks->g, ks->krook_nu.p, dt, &ks->inflow, st));
       if (ks->has_driver)
         LKH_CHECK(lk_ke_e_dot(ks->ke.p + 3, f, &ks->g, ks->charge, ks->velocities.p, ks->ext_efield.p, st));
@@ -1228,6 +1249,19 @@ int lk_vp_set_krook(lk_vp_system* h, int s, const double* nu_host) {
   if (st != LK_OK) return st;
   ks->has_krook = true;
   ks->mom_valid = false;
+  return LK_OK;
+}
+int lk_vp_set_pitch_angle(lk_vp_system* h, int s, const lk_pitch_angle* p) {
+  if (!h || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  auto* ks = h->sys.species[s];
+  ks->has_coll = false;
+  if (!p) return LK_OK;
+  int st = lk_pitch_angle_check(&ks->g, ks->vlo, ks->vhi, p);
+  if (st != LK_OK) return st;
+  ks->coll = *p;
+  ks->has_coll = true;
+  ks->mom_valid = false;
+  ks->forgetPresets();
   return LK_OK;
 }
 int lk_vp_set_time(lk_vp_system* h, double t) {

@@ -23,6 +23,8 @@ class Species:
         # makes the initial condition non-factorable (:395-397)
         self.vx0, self.vy0, self.x_wave_number, self.y_wave_number, self.flow_phase = vx0, vy0, x_wave_number, y_wave_number, flow_phase
 
+        # options beyond the benchmark decks: a Krook layer and a pitch-angle collision operator (see Deck.apply_options)
+        self.krook, self.collision = None, None
         # "Interpenetrating Stream" initial condition, half-plane syntax (InterpenetratingStreamIC.C:496-540):
         # dict(tl, tt, theta, d, beta, floor, frac, frac2, two_sided, centered)
         self.stream = stream
@@ -96,6 +98,14 @@ class Deck:
             nu = self.krook_nu(sp, tile_lo, tile_n)
             if st == 0 and nu is not None:
                 st = H.lk_vp_set_krook(sys_, s, nu.ctypes.data)
+            co = getattr(sp, "collision", None)
+            if st == 0 and co:
+                # a "Pitch Angle Collision Operator" (PitchAngleCollisionOperator.C): Species.collision = dict(range_lo=,
+                # range_hi=, vfloor=, vthermal_dt=, nu_coef=, conservative=)
+                from .capi import PitchAngle
+                pa = PitchAngle.make(co["range_lo"], co["range_hi"], co["vfloor"], co["vthermal_dt"], co["nu_coef"],
+                                     co.get("conservative", 1))
+                st = H.lk_vp_set_pitch_angle(sys_, s, pa)
         return st
 
     def geom_of(self, sp):
@@ -314,6 +324,18 @@ def interpenetrating_streams(n=(128, 7), nv=(24, 16), order=6, rk=6):
     cfrac = P(5.0 / 3.0)
     c = Species("C", nv, lim_c, P(m_c), 6.0, stream=dict(common, beta=0.768, floor=0.0, frac=cfrac, two_sided=True, frac2=cfrac))
     return Deck("InterpenetratingStreams", n, (P(xa), P(xb), P(ya), P(yb)), [e, he, c], order=order, rk=rk, cfl=0.95)
+
+
+def pitch_angle_collisions(n=(32, 5), nv=(64, 64), order=4, rk=4, A=0.0001, conservative=1):
+    """test/pitchAngleCollisions/pitchAngleCollisions.pp: one electron species with a "Pitch Angle Collision Operator"
+    (PitchAngleCollisionOperator.C), no driver, order 4 / RK4, cfl 0.8, six probes"""
+    klde = 0.3
+    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, A=A, kx1=klde, ky1=klde)
+    e.collision = dict(range_lo=(-5.25, -5.25), range_hi=(5.25, 5.25), vfloor=0.01, vthermal_dt=1.0, nu_coef=0.1,
+                       conservative=conservative)
+    d = Deck("pitchAngleCollisions", n, (P(-PI / klde), P(PI / klde), -0.1, 0.1), [e], order=order, rk=rk, cfl=0.8)
+    d.probes = [(0.5, 0.5), (0.25, 0.5), (0.75, 0.5), (0.95, 0.5), (0.5, 0.25), (0.5, 0.75)]
+    return d
 
 
 class VMDeck(Deck):

@@ -2,7 +2,7 @@
 integrators inside libloki_b200.so).  One-to-one, no logic."""
 import ctypes as C
 
-from .capi import Geom, load, check
+from .capi import Geom, PitchAngle, load, check
 
 _vp = C.c_void_p
 
@@ -80,6 +80,7 @@ _PROTOS = {
     "lk_vp_time_history": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int)]),
     "lk_vp_set_boundary_options": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
     "lk_vp_set_krook": (C.c_int, [_vp, C.c_int, _vp]),
+    "lk_vp_set_pitch_angle": (C.c_int, [_vp, C.c_int, C.POINTER(PitchAngle)]),
     "lk_vp_download_state": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "lk_vp_upload_next": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "lk_vp_adopt_next": (C.c_int, [_vp]),

@@ -152,8 +152,32 @@ def _species(params, k):
     for key in ("vflowinitx", "vflowinity", "phi"):
         if g(key) != 0.0:
             raise ValueError("species %d: ic.%s != 0 is not supported (MaxwellianThermal / PerturbedMaxwellianIC)" % (k, key))
-    if int(_f(params, pre + "num_collision_operators", 0.0)) > 0:
-        raise ValueError("species %d: collision operators are out of scope of the Vlasov RHS path" % k)
+    # collision operators (KineticSpecies.C:206-215, 1426-1430; CollisionOperatorFactory.C:30-55): the pitch-angle
+    # operator is implemented (one per species); the Rosenbluth operators are not
+    collision = None
+    ncoll = int(_f(params, pre + "num_collision_operators", 0.0))
+    if ncoll > 1:
+        raise ValueError("species %d: more than one collision operator is not supported" % k)
+    if ncoll == 1:
+        cp = pre + "collision_operator.1."
+        cname = _s(params, cp + "name")
+        if cname != "Pitch Angle Collision Operator":
+            raise ValueError("species %d: collision operator %r is not supported (only the pitch-angle operator)" % (k, cname))
+        # PitchAngleCollisionOperator::parseParameters (PitchAngleCollisionOperator.C:190-270): all but
+        # collision_conservative are required
+        for key in ("collision_vfloor", "collision_vthermal_dt", "collision_nuCoeff"):
+            if (cp + key) not in params:
+                raise ValueError("Must supply " + key)
+        for key in ("collision_vel_range_lo", "collision_vel_range_hi"):
+            if (cp + key) not in params:
+                raise ValueError("Must supply %s." % key)
+            if len(params[cp + key]) != 2:
+                raise ValueError("%s must have 2 entries." % key)
+        collision = dict(range_lo=tuple(float(t) for t in params[cp + "collision_vel_range_lo"]),
+                         range_hi=tuple(float(t) for t in params[cp + "collision_vel_range_hi"]),
+                         vfloor=_f(params, cp + "collision_vfloor"), vthermal_dt=_f(params, cp + "collision_vthermal_dt"),
+                         nu_coef=_f(params, cp + "collision_nuCoeff"),
+                         conservative=int(_f(params, cp + "collision_conservative", 1.0)))
     if any(key.startswith(pre + "external_dist_krook.") for key in list(params.keys())):
         raise ValueError("species %d: external-distribution Krook layers are not supported" % k)
     # KrookLayer::parseParameters (KrookLayer.C:163-190): x1a / x1b / x2a / x2b switch the layer on; `power` is read
@@ -175,6 +199,7 @@ def _species(params, k):
                           flow_phase=g("phase"))
         sp.driver_phase, sp.driver_shape_type = driver_phase, driver_shape_type
         sp.krook = krook
+        sp.collision = collision
         return sp
     if icn == "Interpenetrating Stream":
         if _s(params, pre + "ic.syntax", "half plane") != "half plane":
@@ -188,6 +213,7 @@ def _species(params, k):
         sp = _d.Species(name, nv, vlim, mass, charge, stream=st, driver=driver)
         sp.driver_phase, sp.driver_shape_type = driver_phase, driver_shape_type
         sp.krook = krook
+        sp.collision = collision
         return sp
     raise ValueError("unsupported initial condition %r" % icn)
 
@@ -223,8 +249,9 @@ def deck_from_params(params, name="deck"):
             k += 1
         if rk != 4:
             raise ValueError("the Vlasov-Maxwell host mirror integrates with RK4")
-        if periodic != (True, True) or use_new_bcs or any(getattr(sp, "krook", None) for sp in species):
-            raise ValueError("the Vlasov-Maxwell host mirror is periodic, with the standard boundary fill and no Krook layers")
+        if periodic != (True, True) or use_new_bcs or any(getattr(sp, "krook", None) or getattr(sp, "collision", None) for sp in species):
+            raise ValueError("the Vlasov-Maxwell host mirror is periodic, with the standard boundary fill, no Krook layers "
+                             "and no collision operators")
         deck = _d.VMDeck(name, n, xlim, species, _f(params, "light_speed"), _f(params, "maxwell.avWeak", 0.0),
                          _f(params, "maxwell.avStrong", 0.0), em_ics, vel_ics, order=order, cfl=cfl)
     else:

@@ -31,9 +31,14 @@ ROUTINES = {
                           "computekevelspaceflux"],
     "PoissonF.f": ["neutralizecharge4d", "computeefieldfrompotential"],
     "MaxwellF.f": ["maxwellevalrhs", "sgmetricfunction", "maxwellevalvzrhs", "xpby2d"],
+    "PitchAngleCollisionOperatorF.f": ["evaluatecollisionality", "conservativepitchangle_4th",
+                                       "conservativepitchangle_6th", "nonconservativepitchangle_4th",
+                                       "appendpitchanglecollision", "computepitchanglespeciesmoments",
+                                       "computepitchanglespeciesreducedfields", "computepitchanglespecieskec",
+                                       "computepitchanglespeciesvthermal"],
 }
 ALL_WANTED = {r for rs in ROUTINES.values() for r in rs}
-INTRINSICS = {"max": "fmax", "min": "fmin", "abs": "fabs"}
+INTRINSICS = {"max": "fmax", "min": "fmin", "abs": "fabs", "sqrt": "sqrt"}
 EXTERNAL_REAL_FUNCS = {"initialconditionatpoint"}
 
 
@@ -459,6 +464,12 @@ def translate(name, stmts):
                 depth -= 1
             elif ch == "=" and depth == 0:
                 lhs, rhs = s[:k].strip(), s[k + 1:].strip()
+                if lhs in ctx.dims:
+                    # whole-array assignment of a scalar (rN = 0.0): every element of the declared extent
+                    size = " * ".join("(int64_t)(%s - %s + 1)" % (hi, lo) for lo, hi in ctx.dims[lhs])
+                    emit("{ const int64_t n__ = %s; for (int64_t k__ = 0; k__ < n__; ++k__) %s[k__] = %s; }"
+                         % (size, lhs, cexpr(rhs, ctx)))
+                    return
                 emit("%s = %s;" % (cexpr(lhs, ctx), cexpr(rhs, ctx)))
                 return
         raise SyntaxError("%s: cannot translate statement %r" % (name, s))

@@ -102,6 +102,18 @@ double ok_compute_ke_e_dot(const ok_geom* g, const double* u, double charge, con
 /* appendkrook (KineticSpeciesF.f:2995-3034): rhs -= nu(x,y)/dt * (u - IC) where nu != 0; nu: (n1d,n2d) */
 void ok_append_krook(double* rhs, const double* u, const ok_geom* g, const double* nu, double dt, ok_ic_fn ic,
                      void* ic_ctx);
+/* ---- PitchAngleCollisionOperatorF.f / PitchAngleCollisionOperator.C (loki_oracle_coll.c) ---- */
+double ok_pitch_angle_collisionality(double vx, double vy, double vxgrid, double vygrid, const double* range_lo,
+                                     const double* range_hi, double vxmin, double vxmax, double vymin, double vymax,
+                                     double vfloor, double vthermal, double nu_coef, int order);
+/* IVx, IVy, IVth (n1d,n2d): flow and thermal velocity of max(|u|, 1e-10) over the interior velocity cells */
+void ok_pitch_angle_fields(double* IVx, double* IVy, double* IVth, const double* u, const ok_geom* g,
+                           const double* velocities);
+void ok_append_pitch_angle_collision(double* rhs, const double* f, const ok_geom* g, const double* velocities,
+                                     const double* IVx, const double* IVy, const double* IVth, const double* vlo,
+                                     const double* vhi, const double* range_lo, const double* range_hi, double vfloor,
+                                     double nu_coef, int conservative);
+double ok_pitch_angle_real_lam(const ok_geom* g, double nu_coef, double vthermal_dt, double vfloor);
 /* time-history diagnostics: computeke / computekemaxwell (KineticSpeciesF.f:2447-2559) and the field
  * histories of Poisson / Maxwell ::accumulateSequences (Poisson.C:796-860, Maxwell.C:753-875) */
 /* flux-form diagnostics (KineticSpeciesF.f:630-720, 797-910, 1838-1945, 2249-2396, 985-1032, 2734-2990); d = 0..3 */
@@ -173,6 +185,9 @@ void ok_vp_work_destroy(ok_vp_work* w);
  * Poisson.C:147-152), use_new_bcs (VPSystem.C:819-821), a Krook layer nu(n1d,n2d) of species s (KineticSpecies.C:1049-1062) */
 void ok_vp_set_options(ok_vp_work* w, int nonperiodic_x, int nonperiodic_y, int use_new_bcs);
 void ok_vp_set_krook(ok_vp_work* w, int s, const double* nu);
+/* a pitch-angle collision operator on species s (KineticSpecies.C:1036-1046, 666-672); p = {range_lo[2], range_hi[2],
+ * vfloor, vthermal_dt, nuCoeff, conservative}; NULL removes it */
+void ok_vp_set_pitch_angle(ok_vp_work* w, int s, const double* p);
 void ok_vp_set_dt(ok_vp_work* w, double dt);   /* the a_dt of a bare ok_vp_eval_rhs call (completeRHS) */
 /* rhs[s], f[s]: 4D arrays incl. ghosts; f's ghosts are modified like the reference does.
  * ke_e_dot[s] receives rhs.m_integrated_ke_e_dot for driven species. */

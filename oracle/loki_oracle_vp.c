@@ -31,6 +31,7 @@ struct ok_vp_work {
    * species (KineticSpecies.C:1049-1062); cur_dt: the a_dt the integrators hand to completeRHS */
   int nonperiodic[2], use_new_bcs;
   double** krook_nu;
+  double** coll;   /* pitch-angle operator parameters per species (8 doubles) or NULL */
   double cur_dt;
 };
 
@@ -101,7 +102,7 @@ ok_vp_work* ok_vp_work_create(int ns, const ok_species* sp, const double* xlo, c
   memcpy(w->sp, sp, sizeof(ok_species) * ns);
   for (int k = 0; k < 2; ++k) { w->xlo[k] = xlo[k]; w->xhi[k] = xhi[k]; }
 #define PP(name) w->name = (double**)calloc(ns, sizeof(double*))
-  PP(velocities); PP(vxface); PP(vyface); PP(vel1); PP(vel2); PP(vel3); PP(vel4); PP(accel); PP(rho_s); PP(ext); PP(krook_nu);
+  PP(velocities); PP(vxface); PP(vyface); PP(vel1); PP(vel2); PP(vel3); PP(vel4); PP(accel); PP(rho_s); PP(ext); PP(krook_nu); PP(coll);
   PP(rhs); PP(delta);
   for (int i = 0; i < 8; ++i) { PP(k[i]); w->ke_k[i] = (double*)calloc(ns, sizeof(double)); }
 #undef PP
@@ -156,8 +157,9 @@ void ok_vp_work_destroy(ok_vp_work* w) {
   }
   for (int i = 0; i < 8; ++i) { free(w->k[i]); free(w->ke_k[i]); }
   free(w->last_ax); free(w->last_ay);
-  for (int s = 0; s < w->ns; ++s) free(w->krook_nu[s]);
+  for (int s = 0; s < w->ns; ++s) { free(w->krook_nu[s]); free(w->coll[s]); }
   free(w->krook_nu);
+  free(w->coll);
   free(w->velocities); free(w->vxface); free(w->vyface); free(w->vel1); free(w->vel2); free(w->vel3);
   free(w->vel4); free(w->accel); free(w->ext); free(w->rho_s); free(w->rhs); free(w->delta); free(w->ke_rhs);
   free(w->ke_delta); free(w->rho); free(w->phi); free(w->em); free(w->sx); free(w->sy); free(w->sp);
@@ -181,6 +183,14 @@ void ok_vp_set_krook(ok_vp_work* w, int s, const double* nu) {
   if (nu) {
     w->krook_nu[s] = (double*)malloc(sizeof(double) * pl);
     memcpy(w->krook_nu[s], nu, sizeof(double) * pl);
+  }
+}
+void ok_vp_set_pitch_angle(ok_vp_work* w, int s, const double* p) {
+  free(w->coll[s]);
+  w->coll[s] = NULL;
+  if (p) {
+    w->coll[s] = (double*)malloc(sizeof(double) * 8);
+    memcpy(w->coll[s], p, sizeof(double) * 8);
   }
 }
 /* fillAdvectionGhostCells on one rank (KineticSpecies.H:404-412, 998-1031): physical boundary conditions of the
@@ -246,7 +256,15 @@ void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double time, double
     /* 5. v-boundary fill, acceleration derivatives, completeRHS */
     vp_set_acceleration_bcs(w, s, f[s]);
     ok_acceleration_derivatives_4d(rhs[s], f[s], g, w->vel3[s], w->vel4[s]);
-    /* completeRHS (KineticSpecies.C:1024-1093): Krook layer, then the driver's energy input rate */
+    /* completeRHS (KineticSpecies.C:1024-1093): collision operators, Krook layer, then the driver's energy input rate */
+    if (w->coll[s]) {
+      const double* p = w->coll[s];
+      double* iv = (double*)malloc(sizeof(double) * 3 * pl);
+      ok_pitch_angle_fields(iv, iv + pl, iv + 2 * pl, f[s], g, w->velocities[s]);
+      ok_append_pitch_angle_collision(rhs[s], f[s], g, w->velocities[s], iv, iv + pl, iv + 2 * pl, sp->vlo, sp->vhi, p, p + 2,
+                                      p[4], p[6], (int)p[7]);
+      free(iv);
+    }
     if (w->krook_nu[s]) ok_append_krook(rhs[s], f[s], g, w->krook_nu[s], w->cur_dt, sp->ic, sp->ic_ctx);
     if (sp->has_driver && ke_e_dot)
       ke_e_dot[s] = ok_compute_ke_e_dot(g, f[s], sp->charge, w->velocities[s], w->ext[s], 0.0);
@@ -397,6 +415,7 @@ double ok_vp_stable_dt(const ok_vp_work* w, const double* axmax, const double* a
     lam[3] = aymax[s];
     double imLam = 0.0, reLam = 0.0;
     for (int d = 0; d < 4; ++d) imLam += pi * lam[d] / g->dx[d];
+    if (w->coll[s]) reLam = fabs(ok_pitch_angle_real_lam(g, w->coll[s][6], w->coll[s][5], w->coll[s][4]));  /* KineticSpecies.C:666-672 */
     double alpha = rk_order == 4 ? 2.6 : 4.95, beta = rk_order == 4 ? 2.6 : 3.168;
     double ddt = sqrt(1.0 / (reLam * reLam / (alpha * alpha) + imLam * imLam / (beta * beta)));
     if (ddt < dt_stable) dt_stable = ddt;

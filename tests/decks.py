@@ -85,3 +85,7 @@ def plane_epw(*a, **k):
 
 def plane_iaw(*a, **k):
     return _wrap(_d.plane_iaw(*a, **k))
+
+
+def pitch_angle_collisions(*a, **k):
+    return _wrap(_d.pitch_angle_collisions(*a, **k))

@@ -254,3 +254,44 @@ def field_cases(B, order):
     B.finish()
     out["xpby2d"] = x
     return out
+
+
+COLL_GRIDS = {4: (5, 4, 14, 12), 6: (4, 5, 16, 14)}
+
+
+def collision_cases(B, ok, order):
+    """PitchAngleCollisionOperator::evaluate piece by piece through the Fortran ABI (PitchAngleCollisionOperatorF.H): raw
+    moments -> (times dvx dvy, the one-rank ReductionSchedule4D) -> flow -> kec -> thermal speed -> the operator,
+    conservative and not.  The collisional range leaves cells in every branch of evaluateCollisionality."""
+    s = Setup(ok, COLL_GRIDS[order], order, seed=500 + order, rough=0.3, vmax=(5.0, 4.0))
+    db, ib, data, inter = _boxes(B, s)
+    n1d, n2d, n3d, n4d = s.nd
+    out = {}
+    rn, rgx, rgy, rk = (np.zeros((n2d, n1d)) for _ in range(4))
+    B.call("computepitchanglespeciesmoments_", B.arr(rn), B.arr(rgx), B.arr(rgy), B.arr(s.f), *db, *ib, B.arr(s.velocities))
+    B.finish()
+    m = s.dx[2] * s.dx[3]
+    N, Gx, Gy = rn * m, rgx * m, rgy * m
+    vx, vy, vth = (np.zeros((n2d, n1d)) for _ in range(3))
+    B.call("computepitchanglespeciesreducedfields_", B.arr(vx), B.arr(vy), B.arr(N), B.arr(Gx), B.arr(Gy), *db)
+    B.call("computepitchanglespecieskec_", B.arr(rk), B.arr(vx), B.arr(vy), B.arr(s.f), *db, *ib, B.arr(s.velocities))
+    B.finish()
+    K = rk * m
+    B.call("computepitchanglespeciesvthermal_", B.arr(vth), B.arr(K), B.arr(N), *db)
+    B.finish()
+    out["moments"] = np.stack([rn, rgx, rgy, rk])
+    out["fields"] = np.stack([vx, vy, vth])
+    xlo = np.array([0.0, 0.0, s.vlo[0], s.vlo[1]])
+    xhi = np.array([s.L[0], s.L[1], -s.vlo[0], -s.vlo[1]])
+    dxs = np.array(s.dx)
+    rlo, rhi = np.array([-1.2, -0.9]), np.array([1.1, 1.3])
+    dpar = np.array([0.05, 1.0, 0.37])
+    rng = np.random.default_rng(23 + order)
+    for cons in (0, 1):
+        r = np.ascontiguousarray(rng.uniform(-1, 1, size=s.f.shape) * 1e-3)
+        ipar = np.array([cons, order, 0], dtype=np.int32)
+        B.call("appendpitchanglecollision_", B.arr(r), B.arr(s.f), B.arr(s.velocities), B.arr(vx), B.arr(vy), B.arr(vth), *db, *ib,
+               B.meta(xlo), B.meta(xhi), B.meta(dxs), B.meta(rlo), B.meta(rhi), B.meta(dpar), B.meta(ipar))
+        B.finish()
+        out["coll_cons" if cons else "coll_noncons"] = r
+    return out

@@ -71,7 +71,7 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes")
     # every routine of the Fortran ABI the CUDA library re-exports (include/loki_b200_f77.h), through the argument
     # lists of tests/f77_cases.py: the GPU tests replay the same calls on device arrays and compare bits
-    from f77_cases import HostBackend, kinetic_cases, field_cases
+    from f77_cases import HostBackend, kinetic_cases, field_cases, collision_cases
     B = HostBackend(R.L, R.L.loki_ref_set_ic)
     out2 = {}
     for order in (4, 6):
@@ -79,6 +79,8 @@ def main():
             out2["k%d_%s" % (order, k)] = v
         for k, v in field_cases(B, order).items():
             out2["f%d_%s" % (order, k)] = v
+        for k, v in collision_cases(B, ok, order).items():
+            out2["c%d_%s" % (order, k)] = v
     path = os.path.join(HERE, "f77abi_golden.npz")
     np.savez_compressed(path, **out2)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -49,7 +49,7 @@ def load():
     if _L is not None:
         return _L
     so = os.path.join(ODIR, "libloki_oracle.so")
-    srcs = [os.path.join(ODIR, f) for f in ("loki_oracle.c", "loki_oracle_vp.c", "loki_oracle_vm.c", "loki_oracle.h")]
+    srcs = [os.path.join(ODIR, f) for f in ("loki_oracle.c", "loki_oracle_vp.c", "loki_oracle_vm.c", "loki_oracle_coll.c", "loki_oracle.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", ODIR, "libloki_oracle.so"], stdout=subprocess.DEVNULL)
     L = C.CDLL(so)
@@ -106,6 +106,13 @@ def load():
     L.ok_vp_set_options.argtypes = [C.c_void_p, i, i, i]
     L.ok_vp_set_krook.argtypes = [C.c_void_p, i, dp]
     L.ok_vp_set_dt.argtypes = [C.c_void_p, d]
+    L.ok_vp_set_pitch_angle.argtypes = [C.c_void_p, i, C.c_void_p]
+    L.ok_pitch_angle_collisionality.restype = d
+    L.ok_pitch_angle_collisionality.argtypes = [d, d, d, d, dp, dp, d, d, d, d, d, d, d, i]
+    L.ok_pitch_angle_fields.argtypes = [dp, dp, dp, dp, G, dp]
+    L.ok_append_pitch_angle_collision.argtypes = [dp, dp, G, dp, dp, dp, dp, dp, dp, dp, dp, d, d, i]
+    L.ok_pitch_angle_real_lam.restype = d
+    L.ok_pitch_angle_real_lam.argtypes = [G, d, d, d]
     L.ok_vp_ke_flux_history.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), dp]
     L.ok_vp_stable_dt.restype = d
     L.ok_vp_stable_dt.argtypes = [C.c_void_p, dp, dp, i]

@@ -409,12 +409,14 @@ def _deck_fields(a, b, path=""):
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/test"), reason="the reference's decks are only mounted in the build container")
 def test_deck_mirrors_equal_the_reference_decks():
-    """every number of the five benchmark decks, read from the reference's own .pp files, equals the mirror
+    """every number of the five benchmark decks and of the pitch-angle collision deck, read from the reference's own
+    .pp files, equals the mirror
     in loki_b200/decks.py that the tests, smoke() and bench.py are built from"""
     from loki_b200 import pp, decks
     mirrors = {"planeEPW_fixedIons": decks.plane_epw(), "planeIAW": decks.plane_iaw(),
                "planeIAW_6": decks.plane_iaw(n=(10, 10), nv=(16, 10), order=6, rk=6), "emDamping": decks.em_damping(),
-               "InterpenetratingStreams": decks.interpenetrating_streams()}
+               "InterpenetratingStreams": decks.interpenetrating_streams(),
+               "pitchAngleCollisions": decks.pitch_angle_collisions()}
     for name, mirror in mirrors.items():
         d = pp.load(os.path.join("/root/reference/test", name, name + ".pp"))
         assert _deck_fields(d, mirror) == [], name

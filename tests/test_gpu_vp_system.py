@@ -24,6 +24,11 @@ def _oracle(ok, deck):
         nu = deck.krook_nu(sp_)
         if nu is not None:
             ok.ok_vp_set_krook(w, s_, np.ascontiguousarray(nu).ravel())
+        co = getattr(sp_, "collision", None)
+        if co:   # a pitch-angle collision operator: {range_lo[2], range_hi[2], vfloor, vthermal_dt, nuCoeff, conservative}
+            p = np.array(list(co["range_lo"]) + list(co["range_hi"]) + [co["vfloor"], co["vthermal_dt"], co["nu_coef"],
+                                                                        float(co.get("conservative", 1))])
+            ok.ok_vp_set_pitch_angle(w, s_, p.ctypes.data)
     return w, sp, keep
 
 

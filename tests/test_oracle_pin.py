@@ -270,4 +270,78 @@ def test_fortran_abi_golden_file_is_current(ok, ref):
         for k, v in f77_cases.field_cases(B, order).items():
             assert np.array_equal(v, gold["f%d_%s" % (order, k)]), k
             n += 1
+        for k, v in f77_cases.collision_cases(B, ok, order).items():
+            assert np.array_equal(v, gold["c%d_%s" % (order, k)]), k
+            n += 1
     assert n == len(gold.files)
+
+
+def _pitch_case(ok, order, seed=5):
+    """a small box, a rough positive distribution, flow / thermal fields of the oracle, a collisional range that
+    puts cells into every branch of evaluateCollisionality (inside, both roll-offs, outside)"""
+    n = (5, 4, 14, 12) if order == 4 else (4, 5, 16, 14)
+    s = Setup(ok, n, order, seed=seed, rough=0.3, vmax=(5.0, 4.0))
+    n1d, n2d, n3d, n4d = s.nd
+    iv = np.zeros((3, n2d, n1d))
+    ok.ok_pitch_angle_fields(iv[0].ravel(), iv[1].ravel(), iv[2].ravel(), s.f.ravel(), C.byref(s.g), s.velocities)
+    xlo = np.array([0.0, 0.0, s.vlo[0], s.vlo[1]])
+    xhi = np.array([s.L[0], s.L[1], -s.vlo[0], -s.vlo[1]])
+    rlo, rhi = np.array([-1.2, -0.9]), np.array([1.1, 1.3])
+    return s, iv, xlo, xhi, rlo, rhi
+
+
+@needs_ref
+@pytest.mark.parametrize("order", [4, 6])
+def test_pin_pitch_angle_operator(ok, ref, order):
+    """PitchAngleCollisionOperatorF.f: collisionality, the four moment routines and the non-conservative operator bit
+    for bit; the two Maple-generated conservative operators to rounding (the oracle writes them in operator form)"""
+    R = ref
+    s, iv, xlo, xhi, rlo, rhi = _pitch_case(ok, order)
+    db, ib, data, inter = R.boxes(s)
+    n1d, n2d, n3d, n4d = s.nd
+    rng = np.random.default_rng(11)
+    # evaluateCollisionality over every branch
+    vr = 3 if order == 4 else 4
+    for _ in range(2000):
+        vxg, vyg = rng.uniform(-5.5, 5.5), rng.uniform(-4.5, 4.5)
+        wx, wy = vxg - rng.uniform(-0.3, 0.3), vyg - rng.uniform(-0.3, 0.3)
+        args = (wx, wy, vxg, vyg, rlo, rhi, -5.0 + vr * s.dx[2], 5.0 - vr * s.dx[2], -4.0 + vr * s.dx[3], 4.0 - vr * s.dx[3],
+                0.05, 0.9, 0.37)
+        out = C.c_double()
+        R.L.evaluatecollisionality_(C.byref(out), *[R._d(a) for a in args[:4]], R._p(rlo), R._p(rhi),
+                                    *[R._d(a) for a in args[6:]], R._i(order))
+        assert ok.ok_pitch_angle_collisionality(*args, order) == out.value
+    # moments -> flow -> kec -> vthermal: the reduction on one rank is the local sum times dvx*dvy
+    rn, rgx, rgy, rk = (np.zeros((n2d, n1d)) for _ in range(4))
+    R.L.computepitchanglespeciesmoments_(R._p(rn), R._p(rgx), R._p(rgy), R._p(s.f), *db, *ib, R._p(s.velocities))
+    m = s.dx[2] * s.dx[3]
+    N, Gx, Gy = rn * m, rgx * m, rgy * m
+    vx, vy, vth = (np.zeros((n2d, n1d)) for _ in range(3))
+    R.L.computepitchanglespeciesreducedfields_(R._p(vx), R._p(vy), R._p(N), R._p(Gx), R._p(Gy), *db)
+    R.L.computepitchanglespecieskec_(R._p(rk), R._p(vx), R._p(vy), R._p(s.f), *db, *ib, R._p(s.velocities))
+    K = rk * m
+    R.L.computepitchanglespeciesvthermal_(R._p(vth), R._p(K), R._p(N), *db)
+    assert np.array_equal(iv[0], vx) and np.array_equal(iv[1], vy) and np.array_equal(iv[2], vth)
+    # appendPitchAngleCollision: dparams(1) = vfloor, dparams(3) = nuCoeff; iparams = (icons, order, relativity)
+    for cons in (0, 1):
+        r1 = rng.uniform(-1, 1, size=s.f.shape) * 1e-3
+        r2 = r1.copy()
+        base = r1.copy()
+        ok.ok_append_pitch_angle_collision(r1.ravel(), s.f.ravel(), C.byref(s.g), s.velocities, iv[0].ravel(),
+                                           iv[1].ravel(), iv[2].ravel(), xlo[2:].copy(), xhi[2:].copy(), rlo, rhi, 0.05, 0.37, cons)
+        dpar = np.array([0.05, 1.0, 0.37])
+        ipar = (C.c_int * 3)(cons, order, 0)
+        R.L.appendpitchanglecollision_(R._p(r2), R._p(s.f), R._p(s.velocities), R._p(iv[0]), R._p(iv[1]), R._p(iv[2]),
+                                       *db, *ib, R._p(xlo), R._p(xhi), R._p(np.array(s.dx)), R._p(rlo), R._p(rhi),
+                                       R._p(dpar), ipar)
+        if cons == 0:
+            assert np.array_equal(r1, r2)
+            assert (order == 4) == bool(np.any(r2 != base))      # order 6 has no non-conservative form
+        else:
+            assert np.any(r2 != base)
+            scale = np.abs(r2 - base).max()
+            assert np.abs(r1 - r2).max() <= 1e-13 * scale, np.abs(r1 - r2).max() / scale
+            ng = s.ng
+            g = np.ones(s.f.shape, bool)
+            g[ng:-ng, ng:-ng, ng:-ng, ng:-ng] = False
+            assert np.array_equal(r1[g], base[g]) and np.array_equal(r2[g], base[g])
