@@ -69,31 +69,37 @@ void ok_pitch_angle_fields(double* IVx, double* IVy, double* IVth, const double*
   double* rGx = (double*)calloc(pl, sizeof(double));
   double* rGy = (double*)calloc(pl, sizeof(double));
   double* rK = (double*)calloc(pl, sizeof(double));
-  for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
-    for (int i3 = ng; i3 < ng + g->n[2]; ++i3) {
-      const double vx = velocities[i3 + n3d * i4], vy = velocities[i3 + n3d * (i4 + n4d)];
-      const double* up = u + (int64_t)(i4 * n3d + i3) * pl;
-      for (int64_t k = 0; k < pl; ++k) {
-        double uval = fmax(fabs(up[k]), eps);
-        rN[k] = rN[k] + uval;
-        rGx[k] = rGx[k] + vx * uval;
-        rGy[k] = rGy[k] + vy * uval;
+  /* chunks of configuration-space points on all host cores; every point keeps the reference's order of additions */
+  const int64_t CH = 256, nch = (pl + CH - 1) / CH;
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < nch; ++c) {
+    const int64_t k0 = c * CH, k1 = (k0 + CH < pl) ? k0 + CH : pl;
+    for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
+      for (int i3 = ng; i3 < ng + g->n[2]; ++i3) {
+        const double vx = velocities[i3 + n3d * i4], vy = velocities[i3 + n3d * (i4 + n4d)];
+        const double* up = u + (int64_t)(i4 * n3d + i3) * pl;
+        for (int64_t k = k0; k < k1; ++k) {
+          double uval = fmax(fabs(up[k]), eps);
+          rN[k] = rN[k] + uval;
+          rGx[k] = rGx[k] + vx * uval;
+          rGy[k] = rGy[k] + vy * uval;
+        }
       }
-    }
-  for (int64_t k = 0; k < pl; ++k) { rN[k] *= measure; rGx[k] *= measure; rGy[k] *= measure; }
-  for (int64_t k = 0; k < pl; ++k) { IVx[k] = rGx[k] / rN[k]; IVy[k] = rGy[k] / rN[k]; }
-  for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
-    for (int i3 = ng; i3 < ng + g->n[2]; ++i3) {
-      const double vx = velocities[i3 + n3d * i4], vy = velocities[i3 + n3d * (i4 + n4d)];
-      const double* up = u + (int64_t)(i4 * n3d + i3) * pl;
-      for (int64_t k = 0; k < pl; ++k) {
-        double uval = fmax(fabs(up[k]), eps);
-        double wx = vx - IVx[k], wy = vy - IVy[k];
-        rK[k] = rK[k] + (wx * wx + wy * wy) * uval;
+    for (int64_t k = k0; k < k1; ++k) { rN[k] *= measure; rGx[k] *= measure; rGy[k] *= measure; }
+    for (int64_t k = k0; k < k1; ++k) { IVx[k] = rGx[k] / rN[k]; IVy[k] = rGy[k] / rN[k]; }
+    for (int i4 = ng; i4 < ng + g->n[3]; ++i4)
+      for (int i3 = ng; i3 < ng + g->n[2]; ++i3) {
+        const double vx = velocities[i3 + n3d * i4], vy = velocities[i3 + n3d * (i4 + n4d)];
+        const double* up = u + (int64_t)(i4 * n3d + i3) * pl;
+        for (int64_t k = k0; k < k1; ++k) {
+          double uval = fmax(fabs(up[k]), eps);
+          double wx = vx - IVx[k], wy = vy - IVy[k];
+          rK[k] = rK[k] + (wx * wx + wy * wy) * uval;
+        }
       }
-    }
-  for (int64_t k = 0; k < pl; ++k) rK[k] *= measure;
-  for (int64_t k = 0; k < pl; ++k) IVth[k] = sqrt(0.5 * rK[k] / rN[k]);
+    for (int64_t k = k0; k < k1; ++k) rK[k] *= measure;
+    for (int64_t k = k0; k < k1; ++k) IVth[k] = sqrt(0.5 * rK[k] / rN[k]);
+  }
   free(rN); free(rGx); free(rGy); free(rK);
 }
 
@@ -208,9 +214,14 @@ void ok_append_pitch_angle_collision(double* rhs, const double* f, const ok_geom
   /* conservative: the operator form of the header comment, one configuration-space point at a time */
   pdim dd = {(int)n3d, (int)n4d};
   const int64_t pv = n3d * n4d;
+  /* configuration-space points are independent (disjoint outputs): all host cores, each with its own work planes; the
+   * bits do not depend on the split */
+#pragma omp parallel
+  {
   double* buf = (double*)malloc(sizeof(double) * pv * 13);
   double *F = buf, *A = buf + pv, *B = buf + 2 * pv, *Cc = buf + 3 * pv, *out = buf + 4 * pv, *w[8];
   for (int k = 0; k < 8; ++k) w[k] = buf + (5 + k) * pv;
+#pragma omp for collapse(2) schedule(static)
   for (int i2 = ng; i2 < ng + g->n[1]; ++i2)
     for (int i1 = ng; i1 < ng + g->n[0]; ++i1) {
       const int64_t c2 = i1 + n1d * i2;
@@ -238,6 +249,7 @@ void ok_append_pitch_angle_collision(double* rhs, const double* f, const ok_geom
         }
     }
   free(buf);
+  }
 }
 
 /* PitchAngleCollisionOperator::computeRealLam, PitchAngleCollisionOperator.C:137-144 */

@@ -150,3 +150,58 @@ def test_em_damping_regression_run_at_the_decks_own_grid(lk, ok, fast):
     res = tvm._em_damping_full_run(ok, decks.em_damping())
     _record(test="run", deck="emDamping", final_time=10.0, **res)
     assert res["worst_trace"] <= 1e-10 and res["stencil_neighbourhood_max"] <= 1e-10
+
+
+@pytest.mark.parametrize("mode", ["strict", "production"])
+def test_pitch_angle_collisions_one_step_at_the_decks_own_grid(lk, ok, mode):
+    """test/pitchAngleCollisions at 32 x 5 x 64 x 64 with the deck's own initial condition and collision operator
+    (conservative, order 4): one RK4 step.  Strict: the Vlasov part carries the reference's bits and the operator is
+    the reference's scheme in operator form (equal to rounding): 1e-14 of the peak; production: both metrics <= 1e-12."""
+    deck = decks.pitch_angle_collisions()
+    assert deck.n == (32, 5) and deck.species[0].nv == (64, 64) and deck.species[0].collision["conservative"] == 1
+    old = lk.lk_set_strict(1 if mode == "strict" else 0)
+    try:
+        w, sp, keep = tvp._oracle(ok, deck)
+        f, fx, fv, fnorm = deck.initial_state(deck.species[0])
+        t0, dt = 0.0, 0.003
+        f_old, f_new = [f.copy()], [np.zeros_like(f)]
+        ok.ok_vp_rk4_step(w, tvp._ptrs(f_new), tvp._ptrs(f_old), t0, dt, np.zeros(1))
+        H, sys_ = tvp._product(deck, [f], [(fx, fv, fnorm)])
+        assert H.lk_vp_set_time(sys_, t0) == 0
+        assert H.lk_vp_advance(sys_, dt) == 0, H.lk_last_error()
+        ng = deck.ng
+        I = (slice(ng, -ng),) * 4
+        out = np.empty_like(f)
+        assert H.lk_vp_get_state(sys_, 0, out.ctypes.data) == 0
+        assert np.any(out[I] != f[I])
+        if mode == "strict":
+            assert np.abs(out[I] - f_new[0][I]).max() <= 1e-14 * np.abs(f_new[0][I]).max()
+        else:
+            per_cell = cell_rel_err(out[I], f_new[0][I])
+            star = star_rel_err(out, f_new[0], np.maximum(np.abs(f), np.abs(f_new[0])), ng)
+            _record(test="one_step", deck="pitchAngleCollisions", species="electron", grid=[32, 5, 64, 64], per_cell_max=per_cell,
+                    stencil_neighbourhood_max=star)
+            assert star <= 1e-12 and per_cell <= 1e-12, (per_cell, star)
+        H.lk_vp_destroy(sys_)
+        ok.ok_vp_work_destroy(w)
+    finally:
+        lk.lk_set_strict(old)
+
+
+def test_pitch_angle_collisions_run_at_the_decks_own_grid(lk, ok, fast):
+    """the first steps of the deck through the runner (pp-style options -> lk_vp_set_pitch_angle, the collisional step
+    limit in every stableDt) against the oracle: the same dt sequence, the kinetic-energy trace within 1e-10, the field
+    traces within 1e-8 (the deck's perturbation is 1e-4 of the charge density, whose summation-order noise is 1e-14),
+    the distribution within 1e-10.  The whole deck (final_time 5: 1 400 steps) is too long for the oracle."""
+    deck = decks.pitch_angle_collisions()
+    steps, dev_tr, ora_tr, got, want = tvp._full_run_vs_oracle(ok, deck, 0.03, 0.03)
+    assert steps >= 8
+    worst = np.max(np.abs(dev_tr - ora_tr), axis=0) / np.max(np.abs(ora_tr), axis=0)
+    ng = deck.ng
+    I = (slice(ng, -ng),) * 4
+    per_cell = cell_rel_err(got[0][I], want[0][I])
+    star = star_rel_err(got[0], want[0], want[0], ng)
+    _record(test="run", deck="pitchAngleCollisions", final_time=0.03, steps=steps, worst_trace=float(worst.max()),
+            ke_trace=float(worst[4]), per_cell_max_all_cells=per_cell, stencil_neighbourhood_max=star)
+    assert np.all(worst[:4] <= 1e-8) and worst[4] <= 1e-10, worst
+    assert star <= 1e-10 and per_cell <= 1e-8, (per_cell, star)
