@@ -180,6 +180,17 @@ int lk_vp_probe_history(lk_vp_system* sys, int nprobes, const double* frac_x, co
 int lk_vp_flux_history(lk_vp_system* sys, double* out, int capacity, int* written);
 /* integrated_ke_e_dot of species s (KineticSpecies.C:282-284); synchronises */
 int lk_vp_ke_e_dot(lk_vp_system* sys, int s, double* value);
+/* VPSystem::updateGhosts (VPSystem.C:779-797) before a restart dump (Simulation.C:148-151): the x / y ghost layers of
+ * every species' state on this rank -- boundary conditions of a non-periodic direction, periodic wrap of the
+ * directions this rank is not cut in (a cut direction's halos are the caller's exchange) */
+int lk_vp_update_ghosts(lk_vp_system* sys);
+/* restore integrated_ke_e_dot of species s from a restart dump (KineticSpecies.C:925); synchronises */
+int lk_vp_set_ke_e_dot(lk_vp_system* sys, int s, double value);
+/* The driver histories of KineticSpecies::accumulateSequencesCommon (KineticSpecies.C:2099-2150): *ke_e_dot =
+ * computekeedot_ of the current state against the external driver evaluated at `time` (this rank's part: add over
+ * ranks), *envel = the driver's time envelope (ShapedRampedCosineDriver::evaluateTimeEnvelope); both 0 for a species
+ * without a driver.  Overwrites the species' m_ext_efield as the reference does.  Synchronises. */
+int lk_vp_driver_history(lk_vp_system* sys, int s, double time, double* ke_e_dot, double* envel);
 
 /* ---------------------------------------------------------------------------------------------
  * Vlasov-Maxwell: the host mirror of VMSystem / VMState / Maxwell (VMSystem.C:407-581, Maxwell.C:299-353,

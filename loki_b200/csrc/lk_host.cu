@@ -309,23 +309,29 @@ struct KineticSpecies {
   }
   lk_stage_moments mom0;
 
+  // m_ext_efield = 0.0, then the driver summed into it (KineticSpecies.C:735-751, :2109-2130)
+  int evaluateDriver(double time, const double xlo[2], const int tile_lo[2], void* st) {
+    LKH_CUDA(cudaMemsetAsync(ext_efield.p, 0, sizeof(double) * 2 * n1d * n2d, (cudaStream_t)st));  // m_ext_efield = 0.0
+    if (driver.active(time)) {
+      const double pi = 4.0 * atan(1.0);
+      const double envel = driver.envelope(time);
+      std::vector<double> gh(n1d), hh(n2d);
+      for (int i1 = 0; i1 < n1d; ++i1) gh[i1] = driver.ghat(xlo[0] + g.dx[0] * (0.5 + (tile_lo[0] + i1 - g.ng)), time, pi);
+      for (int i2 = 0; i2 < n2d; ++i2) hh[i2] = driver.hfun(xlo[1] + g.dx[1] * (0.5 + (tile_lo[1] + i2 - g.ng)), pi);
+      // stream-ordered copies from pageable memory are synchronous with respect to the host buffer
+      LKH_CUDA(cudaMemcpyAsync(drv_g.p, gh.data(), sizeof(double) * n1d, cudaMemcpyHostToDevice, (cudaStream_t)st));
+      LKH_CUDA(cudaMemcpyAsync(drv_h.p, hh.data(), sizeof(double) * n2d, cudaMemcpyHostToDevice, (cudaStream_t)st));
+      k_driver_field<<<nb((i64)n1d * n2d, 128), 128, 0, (cudaStream_t)st>>>(ext_efield.p, drv_g.p, drv_h.p, envel, n1d, n2d);
+    }
+    return LK_OK;
+  }
+
   // computeAcceleration (KineticSpecies.C:697-774).  em_local: this rank's window of E incl. ghosts.
   int computeAcceleration(const double* em_local, double time, const double xlo[2], const int tile_lo[2], bool want_max,
                           void* st) {
     const double* ext = nullptr;
     if (has_driver) {
-      LKH_CUDA(cudaMemsetAsync(ext_efield.p, 0, sizeof(double) * 2 * n1d * n2d, (cudaStream_t)st));  // m_ext_efield = 0.0
-      if (driver.active(time)) {
-        const double pi = 4.0 * atan(1.0);
-        const double envel = driver.envelope(time);
-        std::vector<double> gh(n1d), hh(n2d);
-        for (int i1 = 0; i1 < n1d; ++i1) gh[i1] = driver.ghat(xlo[0] + g.dx[0] * (0.5 + (tile_lo[0] + i1 - g.ng)), time, pi);
-        for (int i2 = 0; i2 < n2d; ++i2) hh[i2] = driver.hfun(xlo[1] + g.dx[1] * (0.5 + (tile_lo[1] + i2 - g.ng)), pi);
-        // stream-ordered copies from pageable memory are synchronous with respect to the host buffer
-        LKH_CUDA(cudaMemcpyAsync(drv_g.p, gh.data(), sizeof(double) * n1d, cudaMemcpyHostToDevice, (cudaStream_t)st));
-        LKH_CUDA(cudaMemcpyAsync(drv_h.p, hh.data(), sizeof(double) * n2d, cudaMemcpyHostToDevice, (cudaStream_t)st));
-        k_driver_field<<<nb((i64)n1d * n2d, 128), 128, 0, (cudaStream_t)st>>>(ext_efield.p, drv_g.p, drv_h.p, envel, n1d, n2d);
-      }
+      LKH_CHECK(evaluateDriver(time, xlo, tile_lo, st));
       ext = ext_efield.p;
     }
     // m_accel = 0; expansion of E; drivers add; m_accel *= normalization
@@ -1447,6 +1453,41 @@ int lk_vp_ke_e_dot(lk_vp_system* h, int s, double* value) {
   if (!h || !value || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
   if (cudaStreamSynchronize(h->sys.st) != cudaSuccess) return LK_ERR_CUDA;
   if (cudaMemcpy(value, h->sys.species[s]->ke.p, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return LK_ERR_CUDA;
+  return LK_OK;
+}
+
+int lk_vp_update_ghosts(lk_vp_system* h) {
+  // VPSystem::updateGhosts (VPSystem.C:779-797), the species part: fillAdvectionGhostCells of the state on this rank
+  if (!h) return LK_ERR_ARG;
+  return h->sys.fillAdvectionGhostCellsLocal();
+}
+int lk_vp_set_ke_e_dot(lk_vp_system* h, int s, double value) {
+  // KineticSpecies::getFromRestart (KineticSpecies.C:925): m_integrated_ke_e_dot as a restart dump recorded it
+  if (!h || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  if (!h->sys.species[s]->has_driver) return LK_OK;   // the reference only records it for driven species (KineticSpecies.C:1011-1015)
+  if (cudaStreamSynchronize(h->sys.st) != cudaSuccess) return LK_ERR_CUDA;
+  if (cudaMemcpy(h->sys.species[s]->ke.p, &value, sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return LK_ERR_CUDA;
+  return LK_OK;
+}
+int lk_vp_driver_history(lk_vp_system* h, int s, double time, double* ke_e_dot, double* envel) {
+  // KineticSpecies::accumulateSequencesCommon, the driver part (KineticSpecies.C:2099-2150): the driver evaluated at
+  // `time` into m_ext_efield, computekeedot of the state against it, and the driver's time envelope
+  if (!h || !ke_e_dot || !envel || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  auto& S = h->sys;
+  auto* ks = S.species[s];
+  *ke_e_dot = 0.0;
+  *envel = 0.0;
+  if (!ks->has_driver) return LK_OK;
+  loki::DevBuf<double>& d = S.hist_scratch;
+  int st = (d.p && d.n >= 1) ? LK_OK : d.alloc(16);
+  if (st != LK_OK) return st;
+  st = ks->evaluateDriver(time, S.desc.xlo, S.desc.tile_lo, S.st);
+  if (st != LK_OK) return st;
+  st = lk_ke_e_dot(d.p, ks->state(), &ks->g, ks->charge, ks->velocities.p, ks->ext_efield.p, S.st);
+  if (st != LK_OK) return st;
+  if (cudaStreamSynchronize(S.st) != cudaSuccess) return LK_ERR_CUDA;
+  if (cudaMemcpy(ke_e_dot, d.p, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return LK_ERR_CUDA;
+  *envel = ks->driver.active(time) ? ks->driver.envelope(time) : 0.0;
   return LK_OK;
 }
 

@@ -263,6 +263,22 @@ def deck_from_params(params, name="deck"):
     # Simulation's defaults (Simulation.C:166-181): final_time 1, save_times 1, sequence_write_times 1, max_step 0
     deck.run = dict(final_time=_f(params, "final_time", 1.0), save_times=_f(params, "save_times", 1.0),
                     sequence_write_times=_f(params, "sequence_write_times", 1.0), max_step=int(_f(params, "max_step", 0.0)))
+    # restart cadence and paths (RestartManager.C:150-192); start_from_restart (Simulation.C:211-215)
+    rs = {}
+    for key, conv in (("time_interval", float), ("step_interval", int), ("max_files_for_write", int)):
+        if ("restart." + key) in params:
+            v = params["restart." + key]
+            rs["max_files" if key == "max_files_for_write" else key] = conv(float(v[0] if isinstance(v, (list, tuple)) else v))
+    for key in ("write_directory", "read_directory"):
+        if ("restart." + key) in params:
+            v = params["restart." + key]
+            rs[key] = str(v[0] if isinstance(v, (list, tuple)) else v).strip('"')
+    if "time_interval" in rs and "step_interval" in rs:
+        raise ValueError("Must set restart frequency for only one of steps or time, not both.")
+    if "start_from_restart" in params:
+        v = params["start_from_restart"]
+        rs["start_from_restart"] = str(v[0] if isinstance(v, (list, tuple)) else v).strip('"') == "true"
+    deck.run["restart"] = rs
     # probes (Simulation.C:393-412): fractions of the domain; without number_of_probes one probe at (0.5, 0) -- the
     # reference assigns m_probes[X1][0] twice and leaves the y fraction at 0
     if "number_of_probes" in params:

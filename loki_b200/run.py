@@ -3,8 +3,12 @@
 The loop is Simulation::advance (Simulation.C:302-351): dt = cfl * stableDt snapped to the next multiple of
 save_times (selectTimeStep, :464-485), System::advance, and a time-history record every sequence_write_times
 (VPSystem::accumulateSequences / the Maxwell analogue) printed as a JSON line.  Vlasov-Poisson (RK4/RK6) and
-Vlasov-Maxwell (RK4) decks with the initial conditions and the driver the five benchmark decks use.  No
-restart / plot files (HDF5 is out of scope)."""
+Vlasov-Maxwell (RK4) decks with the initial conditions and the driver the five benchmark decks use.
+
+With --write-directory (or the deck's restart.write_directory under --save-data) a Vlasov-Poisson run also writes
+what Simulation writes: <dir>.time_hists_<n>.hdf and <dir>.fields_<k>.hdf at every save time and restart dumps
+<dir>/dist_<n>.hdf + .g0 on the deck's restart.time_interval / step_interval (outputs.py); --restart resumes from
+the newest dump of the deck's restart.read_directory."""
 import argparse
 import ctypes as C
 import json
@@ -13,7 +17,7 @@ import sys
 
 import numpy as np
 
-from . import capi, host, pp
+from . import capi, host, outputs, pp
 
 
 def select_dt(time, dt_stable_cfl, last_save, save_times, max_time):
@@ -131,15 +135,157 @@ class Runner:
             capi.check(H.lk_vp_advance(self.sys, step), "lk_vp_advance")
         self.time += step
         self.step += 1
+        if getattr(self, "out", None):
+            self.out["dt"] = step
         # exact comparisons as in Simulation::advance (Simulation.C:318-327): when rounding leaves the time one ulp
         # short of a save time, selectTimeStep's remaining * (1 + 10 eps) micro-step closes the gap next
         self.record = False
         if self.time >= (self.last_seq + 1) * run.get("sequence_write_times", 1.0):
             self.record = True          # accumulateSequences()
             self.last_seq += 1
+        self.save = False
         if self.time >= (self.last_save + 1) * run["save_times"]:
-            self.last_save += 1         # writePlotFile()
+            self.save = True            # writePlotFile()
+            self.last_save += 1
+        if getattr(self, "out", None):
+            if self.record:
+                self.accumulate_sequences()
+            if self.save:
+                self.write_plot_file()
+            self.write_checkpoint_file()
         return step
+
+    # ---- Simulation's output side (Simulation.C:66-160, :262-290) ----
+
+    def sequence_record(self):
+        """one column of VPSystem::accumulateSequences (VPSystem.C:591-636) in Poisson::buildTimeHistoryNames order:
+        5 field histories, (Ex, Ey) per probe, then 16 per species"""
+        if self.vm:
+            raise NotImplementedError("time-history files of the Vlasov-Maxwell system")
+        ns = len(self.deck.species)
+        h = self.history()
+        pr = self.probes().reshape(-1)
+        fl = self.flux_history()
+        out = list(h[:5]) + list(pr)
+        for s in range(ns):
+            ked, env = C.c_double(), C.c_double()
+            capi.check(self.H.lk_vp_driver_history(self.sys, s, self.time, C.byref(ked), C.byref(env)), "driver_history")
+            out += list(h[5 + 6 * s:5 + 6 * s + 5]) + list(fl[8 * s:8 * s + 8]) + [ked.value, h[5 + 6 * s + 5], env.value]
+        return out
+
+    def em_vars(self):
+        """(2, n2d, n1d): Ex, Ey of the last field solve with their ghost layers (EMSolverBase::plotCommon's m_em_vars)"""
+        d = self.deck
+        n1d, n2d = d.n[0] + 2 * d.ng, d.n[1] + 2 * d.ng
+        out = np.empty((2, n2d, n1d))
+        capi.check(self.L.lk_sync(None), "lk_sync")
+        capi.check(self.L.lk_memcpy_d2h(out.ctypes.data, self.H.lk_vp_em_vars_ptr(self.sys), out.nbytes), "lk_memcpy_d2h")
+        return out
+
+    def open_outputs(self, write_dir, restart_time_interval=None, restart_step_interval=None, max_files=16,
+                     restart_index=0):
+        """what Simulation's constructor sets up (Simulation.C:262-290): the sequences, the field writer, the restart
+        cadence; then the time-0 history, plot and dump"""
+        if self.vm:
+            raise NotImplementedError("output files of the Vlasov-Maxwell system")
+        d = self.deck
+        # after a restore the next dump is due at once (RestartManager::resetNextWriteTime, Simulation.C:251-254)
+        self.out = dict(dir=write_dir, saved_seq=0, saved_save=0, time_seq=[], restart_index=restart_index,
+                        max_files=max_files, t_int=restart_time_interval, s_int=restart_step_interval,
+                        next_write=self.time, dt=0.0)
+        names = [sp.name for sp in d.species]
+        self.out["names"] = outputs.poisson_time_history_names(len(d.probes), 0, names)
+        self.out["seq"] = [[] for _ in self.out["names"]]
+        self.out["fields"] = outputs.FieldWriter(write_dir, (d.xlim[0], d.xlim[2]), d.dx, d.n, d.order, 1)
+        self.accumulate_sequences()
+        self.write_plot_file()
+        self.write_checkpoint_file()
+
+    def accumulate_sequences(self):
+        o = self.out
+        o["time_seq"].append(self.time)
+        for seq, v in zip(o["seq"], self.sequence_record()):
+            seq.append(v)
+        o["saved_seq"] += 1
+
+    def write_plot_file(self):
+        """Poisson::plot (Poisson.C:687-784): one time slice of EX, EY, then the time histories so far"""
+        o, d = self.out, self.deck
+        fw = o["fields"]
+        npr = len(d.probes)
+        fw.start_time_slice(self.time, o["dt"], outputs.poisson_plot_names(False, []), 0, npr,
+                            ([p[0] for p in d.probes], [p[1] for p in d.probes]), d.n)
+        em = self.em_vars()
+        for k, name in enumerate(("EX", "EY")):
+            fw.write_field(name, em[k], (-d.ng, -d.ng), (-d.ng, -d.ng), (d.n[0] + 2 * d.ng, d.n[1] + 2 * d.ng), d.ng)
+        fw.end_time_slice()
+        outputs.write_time_histories(o["dir"] + ".time_hists", o["saved_save"], o["names"], o["seq"], o["time_seq"],
+                                     o["saved_seq"], npr, 0)
+        o["saved_save"] += 1
+
+    def write_checkpoint_file(self):
+        """Simulation::writeCheckpointFile (Simulation.C:133-160) with RestartManager::requiresAction's rule"""
+        o, d = self.out, self.deck
+        if o["t_int"] is not None:
+            if not self.time >= o["next_write"]:
+                return None
+        elif o["s_int"] is not None:
+            if self.step % o["s_int"] != 0:
+                return None
+        else:
+            return None
+        # m_system->updateGhosts(): the dump holds the ghost cells the next step would start from
+        capi.check(self.H.lk_vp_update_ghosts(self.sys), "lk_vp_update_ghosts")
+        items = []
+        for s, sp in enumerate(d.species):
+            f = self.state(s)
+            vlim = sp.vlim
+            ncell = [d.n[0], d.n[1], sp.nv[0], sp.nv[1]]
+            x_lo = [d.xlim[0], d.xlim[2], vlim[0], vlim[2]]
+            x_hi = [d.xlim[1], d.xlim[3], vlim[1], vlim[3]]
+            dx = [(x_hi[k] - x_lo[k]) / ncell[k] for k in range(4)]
+            item = dict(sp=dict(name=sp.name, mass=sp.mass, charge=sp.charge, bz_const=getattr(sp, "bz", 0.0)),
+                        domain=(ncell, x_lo, x_hi, dx, d.periodic), tiles={0: f},
+                        info=outputs.distrib_info(0, 0, d.ng, ncell, [1, 1, 1, 1]))
+            if sp.driver:
+                v = C.c_double()
+                capi.check(self.H.lk_vp_ke_e_dot(self.sys, s, C.byref(v)), "lk_vp_ke_e_dot")
+                item["integrated_e_dot_j"] = {0: v.value}
+                item["sp"]["driver_state"] = (0, float(getattr(sp, "driver_phase", 0.0)), 0.0)
+            items.append(item)
+        name = outputs.write_vp_restart(o["dir"], o["restart_index"], items, d.ng, self.time, o["dt"], d.cfl,
+                                        d.run["final_time"], max_files=o["max_files"])
+        o["restart_index"] += 1
+        if o["t_int"] is not None:
+            o["next_write"] += o["t_int"]
+        return name
+
+    def restore(self, read_dir):
+        """RestartManager::restore (RestartManager.C:197-228): resume from the newest dist_<n>.hdf of read_dir"""
+        import os
+        idx = -1
+        while os.path.exists(os.path.join(read_dir, "dist_%d.hdf" % (idx + 1))):
+            idx += 1
+        if idx < 0:
+            raise FileNotFoundError("No distributions found from which to restart ... quitting")
+        dump = outputs.read_vp_restart(os.path.join(read_dir, "dist_%d.hdf" % idx))
+        if dump["num_procs"] != 1:
+            raise NotImplementedError("restart dumps of more than one generating process")
+        for s, item in enumerate(dump["species"]):
+            f = np.ascontiguousarray(item["distribution"], dtype=np.float64)
+            if f.shape != tuple(self.shapes[s]):
+                raise ValueError("dump of %s has extents %s, the deck %s" % (item["name"], f.shape, self.shapes[s]))
+            capi.check(self.H.lk_vp_set_state(self.sys, s, f.ctypes.data), "lk_vp_set_state")
+            if item["integrated_e_dot_j"] is not None:
+                capi.check(self.H.lk_vp_set_ke_e_dot(self.sys, s, item["integrated_e_dot_j"]), "lk_vp_set_ke_e_dot")
+        self.time = dump["time"]
+        run = self.deck.run
+        # Simulation's constructor after a restore (Simulation.C:246-260): the counters follow from the time
+        self.last_save = int(self.time / run["save_times"])
+        self.last_seq = int(self.time / run.get("sequence_write_times", 1.0))
+        capi.check(self.H.lk_vp_set_time(self.sys, self.time), "set_time")
+        self._seed()
+        return idx
 
     def done(self):
         """!Simulation::notDone (Simulation.H:126-129)"""
@@ -163,6 +309,10 @@ def main(argv=None):
     ap.add_argument("--max-steps", type=int, default=None)
     ap.add_argument("--final-time", type=float, default=None)
     ap.add_argument("--every-step", action="store_true", help="emit the time histories after every step, not every sequence_write_times")
+    ap.add_argument("--write-directory", default=None, help="write time-history, field and restart files under this "
+                    "base path (default with --save-data: the deck's restart.write_directory)")
+    ap.add_argument("--save-data", action="store_true", help="write the output files the deck asks for")
+    ap.add_argument("--restart", action="store_true", help="resume from the newest dump of the deck's restart.read_directory")
     a = ap.parse_args(argv)
     deck = pp.load(a.deck)
     if a.max_steps is not None:
@@ -170,6 +320,13 @@ def main(argv=None):
     if a.final_time is not None:
         deck.run["final_time"] = a.final_time
     r = Runner(deck)
+    rs = deck.run.get("restart", {})
+    restart_index = 0
+    if a.restart or rs.get("start_from_restart"):
+        restart_index = r.restore(rs.get("read_directory") or rs.get("write_directory")) + 1
+    wdir = a.write_directory or (rs.get("write_directory") if a.save_data else None)
+    if wdir:
+        r.open_outputs(wdir, rs.get("time_interval"), rs.get("step_interval"), rs.get("max_files", 16), restart_index)
     names = (["e_max", "e_tot", "ex_max", "ey_max", "ez_max", "e_sum_tot", "b_max", "b_tot", "bx_max", "by_max", "bz_max",
               "b_sum_tot"] if r.vm else ["e_max", "e_tot", "ex_max", "ey_max", "e_sum_tot"])
     per = ["ke", "ke_x", "ke_y", "px", "py"] + ([] if r.vm else ["ke_e_dot"])
@@ -191,6 +348,8 @@ def main(argv=None):
                         for side, sn in enumerate(("lo", "hi")):
                             rec["%s_ke_flux_%s_%s" % (sp.name, dn, sn)] = fl[8 * s_ + 2 * d_ + side]
         print(json.dumps(rec))
+    if wdir:
+        r.write_checkpoint_file()       # Simulation::finalize (Simulation.C:354-359)
     r.close()
     return 0
 
