@@ -123,6 +123,14 @@ void computekevelspaceflux_(const int* nd1a, const int* nd1b, const int* nd2a, c
                             const int* ng3b, const int* ng4a, const int* ng4b, const double* dx, const double* face_flux3,
                             const double* face_flux4, double* ke_flux, const double* mass, const double* vxface_velocities,
                             const double* vyface_velocities, const int* side, const int* dir);
+/* TZSourceF.f:10-27, :79-97 (declared in TZSourceF.H; called from TrigTZSource.C:44-82) */
+void settrigtzsource_(double* f, const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a,
+                      const int* nd3b, const int* nd4a, const int* nd4b, const double* xlo, const double* xhi, const double* dx,
+                      const double* time, const double* velocities, const double* dparams);
+void computetrigtzsourceerror_(double* error, const double* soln, const int* nd1a, const int* nd1b, const int* nd2a,
+                               const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b,
+                               const double* xlo, const double* xhi, const double* dx, const double* time,
+                               const double* velocities, const double* dparams);
 /* KineticSpeciesF.f:2995-3034 */
 void appendkrook_(const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a, const int* nd3b,
                   const int* nd4a, const int* nd4b, const int* n1a, const int* n1b, const int* n2a, const int* n2b,

@@ -180,6 +180,13 @@ int lk_vp_probe_history(lk_vp_system* sys, int nprobes, const double* frac_x, co
 int lk_vp_flux_history(lk_vp_system* sys, double* out, int capacity, int* written);
 /* integrated_ke_e_dot of species s (KineticSpecies.C:282-284); synchronises */
 int lk_vp_ke_e_dot(lk_vp_system* sys, int s, double* value);
+/* kinetic_species.N.tz.name = "TrigTZSource" with tz.amp (TrigTZSource.C:21-42, KineticSpecies.C:186, :1077-1080): on != 0
+ * adds the twilight-zone source (lk_set_trig_tz_source) to species s's right-hand side in completeRHS, after the
+ * collision operator and the Krook layer.  Such a species takes the three-pass stage (rhs materialised). */
+int lk_vp_set_trig_tz(lk_vp_system* sys, int s, int on, double amp);
+/* TrigTZSource::computeError (TrigTZSource.C:63-82): error_host (the state's extents, host) = state - f_exact(time) over
+ * the whole data box; what a restart dump holds in place of the distribution (KineticSpecies.C:987-1004).  Synchronises. */
+int lk_vp_trig_tz_error(lk_vp_system* sys, int s, double time, double* error_host);
 /* VPSystem::updateGhosts (VPSystem.C:779-797) before a restart dump (Simulation.C:148-151): the x / y ghost layers of
  * every species' state on this rank -- boundary conditions of a non-periodic direction, periodic wrap of the
  * directions this rank is not cut in (a cut direction's halos are the caller's exchange) */

@@ -129,6 +129,10 @@ _PROTOS = {
     "lk_efield_from_potential": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp]),
     "lk_maxwell_vz_rhs": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp]),
     "lk_f77_status": (C.c_int, []),
+    "lk_trig_tz_table_count": (C.c_int, [C.POINTER(Geom), C.POINTER(C.c_int64)]),
+    "lk_trig_tz_tables": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(C.c_int * 2), C.POINTER(C.c_double * 2), _vp, _vp]),
+    "lk_set_trig_tz_source": (C.c_int, [_vp, C.POINTER(Geom), _vp, _vp, C.c_double, C.c_double, _vp]),
+    "lk_compute_trig_tz_source_error": (C.c_int, [_vp, _vp, C.POINTER(Geom), _vp, _vp, C.c_double, C.c_double, _vp]),
     "lk_append_krook": (C.c_int, [_vp, _vp, C.POINTER(Geom), _vp, C.c_double, C.POINTER(Inflow), _vp]),
     "lk_pitch_angle_fields": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(Geom), _vp, _vp]),
     "lk_append_pitch_angle_collision": (C.c_int, [_vp, _vp, C.POINTER(Geom), _vp, _vp, _vp, _vp, C.POINTER(C.c_double * 2),

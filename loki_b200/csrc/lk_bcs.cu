@@ -246,4 +246,84 @@ cudaError_t append_krook(double* rhs, const double* u, const lk_geom* g, const d
   return cudaGetLastError();
 }
 
+// ---- TrigTZSource (TZSourceF.f:10-137): the twilight-zone source h(x, y, vx, vy, t) added to a right-hand side over the
+// whole data box, and error = soln - f_exact.  The transcendental factors are separable -- sin / cos of x (per i1), of y
+// (per i2), exp(-alpha v^2 / 2) (per (i3, i4)), sin t / cos t (scalars) -- and come from host tables built with libm, so
+// the kernel evaluates Maple's expression tree in the Fortran's parse order on the same operand bits (-fmad=false).
+// tab: {sin(kx x)[n1d], cos(kx x)[n1d], sin(ky y)[n2d], cos(ky y)[n2d], exp(..)[n3d n4d]}
+__global__ void k_trig_tz(Geo g, const double* __restrict__ tab, const double* __restrict__ velocities, double A, double st,
+                          double ct, double pi, const double* __restrict__ soln, double* __restrict__ out) {
+  const double kx = 1.0, ky = 1.0, kt = 1.0, alpha = 1.0;
+  const double* sx = tab;
+  const double* cx = sx + g.nd[0];
+  const double* sy = cx + g.nd[0];
+  const double* cy = sy + g.nd[1];
+  const double* ev = cy + g.nd[1];
+  const i64 total = (i64)g.nd[0] * g.nd[1] * g.nd[2] * g.nd[3];
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+    const int i1 = (int)(t % g.nd[0]);
+    i64 r = t / g.nd[0];
+    const int i2 = (int)(r % g.nd[1]);
+    r /= g.nd[1];
+    const int i3 = (int)(r % g.nd[2]), i4 = (int)(r / g.nd[2]);
+    const i64 pv = i3 + (i64)g.nd[2] * i4;
+    const double vx = velocities[pv], vy = velocities[pv + (i64)g.nd[2] * g.nd[3]];
+    const double e = ev[pv], sinx = sx[i1], cosx = cx[i1], siny = sy[i2], cosy = cy[i2];
+    if (soln) {
+      const double fexact = alpha / pi * e * (0.1e1 + A * cosx * cosy * st) / 0.2e1;
+      out[t] = soln[t] - fexact;
+    } else {
+      const double h =
+          -0.1e1 / (kx * kx + ky * ky) * A * sinx * kx * cosy * st * (alpha * alpha) / pi * vx * e * (0.1e1 + A * cosx * cosy * st) / 0.2e1 -
+          0.1e1 / (kx * kx + ky * ky) * A * cosx * siny * ky * st * (alpha * alpha) / pi * vy * e * (0.1e1 + A * cosx * cosy * st) / 0.2e1 -
+          alpha / pi * e * A * sinx * kx * cosy * st * vx / 0.2e1 - alpha / pi * e * A * cosx * siny * ky * st * vy / 0.2e1 +
+          alpha / pi * e * A * cosx * cosy * ct * kt / 0.2e1;
+      out[t] = out[t] + h;
+    }
+  }
+}
+
+// host side of the tables: libm, the Fortran's argument expressions; vel_host: (n3d, n4d, 2)
+void trig_tz_tables(double* tab, const lk_geom* g, const int lo[2], const double xlo[2], const double* vel_host) {
+  const double kx = 1.0, ky = 1.0, alpha = 1.0;
+  const int n1d = g->n[0] + 2 * g->ng, n2d = g->n[1] + 2 * g->ng, n3d = g->n[2] + 2 * g->ng, n4d = g->n[3] + 2 * g->ng;
+  double* sx = tab;
+  double* cx = sx + n1d;
+  double* sy = cx + n1d;
+  double* cy = sy + n2d;
+  double* ev = cy + n2d;
+  for (int i1 = 0; i1 < n1d; ++i1) {
+    const double x = xlo[0] + ((lo[0] + i1) + 0.5) * g->dx[0];
+    sx[i1] = sin(kx * x);
+    cx[i1] = cos(kx * x);
+  }
+  for (int i2 = 0; i2 < n2d; ++i2) {
+    const double y = xlo[1] + ((lo[1] + i2) + 0.5) * g->dx[1];
+    sy[i2] = sin(ky * y);
+    cy[i2] = cos(ky * y);
+  }
+  for (i64 pv = 0; pv < (i64)n3d * n4d; ++pv) {
+    const double vx = vel_host[pv], vy = vel_host[pv + (i64)n3d * n4d];
+    ev[pv] = exp(-(alpha * (vx * vx + vy * vy) / 0.2e1));
+  }
+}
+size_t trig_tz_table_count(const lk_geom* g) {
+  const size_t n1d = g->n[0] + 2 * g->ng, n2d = g->n[1] + 2 * g->ng, n3d = g->n[2] + 2 * g->ng, n4d = g->n[3] + 2 * g->ng;
+  return 2 * n1d + 2 * n2d + n3d * n4d;
+}
+
+// out += h (soln == nullptr) or out = soln - f_exact; tab_dev: trig_tz_tables on the device
+cudaError_t trig_tz(double* out, const double* soln, const lk_geom* g, const double* tab_dev, const double* velocities,
+                    double time, double amp, cudaStream_t st, int64_t* launches) {
+  Geo d = make_geo(g);
+  const double kt = 1.0;
+  const double pi = 4.0 * atan(1.0);
+  const i64 total = (i64)d.nd[0] * d.nd[1] * d.nd[2] * d.nd[3];
+  i64 blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_trig_tz<<<(unsigned)blocks, 256, 0, st>>>(d, tab_dev, velocities, amp, sin(kt * time), cos(kt * time), pi, soln, out);
+  ++*launches;
+  return cudaGetLastError();
+}
+
 }  // namespace lkbcs

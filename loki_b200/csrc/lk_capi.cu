@@ -124,6 +124,12 @@ cudaError_t append_krook(double* rhs, const double* u, const lk_geom* g, const d
 cudaError_t set_bcs_jb(double* f, const lk_geom* g, const lk_accel* a, const double* velocities, const lk_inflow* ic,
                        const int sides[8], cudaStream_t st, int64_t* launches);
 }
+namespace lkbcs {
+void trig_tz_tables(double* tab, const lk_geom* g, const int lo[2], const double xlo[2], const double* vel_host);
+size_t trig_tz_table_count(const lk_geom* g);
+cudaError_t trig_tz(double* out, const double* soln, const lk_geom* g, const double* tab_dev, const double* velocities,
+                    double time, double amp, cudaStream_t st, int64_t* launches);
+}
 // lk_coll.cu: pitch-angle collision operator
 namespace lkcoll {
 cudaError_t fields(double* ivx, double* ivy, double* vth, const double* u, const lk_geom* g, const double* velocities,
@@ -264,6 +270,38 @@ int lk_append_pitch_angle_collision(double* rhs, const double* f, const lk_geom*
     return fail(LK_ERR_ARG, "lk_append_pitch_angle_collision: bad argument");
   CHECK_LAUNCH(lkcoll::append(rhs, f, g, velocities, IVx, IVy, IVth, vlo, vhi, p, (cudaStream_t)stream, &g_fft_launches),
                "lk_append_pitch_angle_collision");
+}
+int lk_trig_tz_table_count(const lk_geom* g, int64_t* count) {
+  if (!geom_ok(g) || !count) return fail(LK_ERR_ARG, "lk_trig_tz_table_count: bad argument");
+  *count = (int64_t)lkbcs::trig_tz_table_count(g);
+  return LK_OK;
+}
+int lk_trig_tz_tables(double* tables, const lk_geom* g, const int lo[2], const double xlo[2], const double* velocities,
+                      void* stream) {
+  // the time-independent factors of the source, built on the host with libm and left on the device in `tables`
+  if (!geom_ok(g) || !tables || !lo || !xlo || !velocities) return fail(LK_ERR_ARG, "lk_trig_tz_tables: bad argument");
+  const size_t nv = (size_t)(g->n[2] + 2 * g->ng) * (g->n[3] + 2 * g->ng) * 2;
+  std::vector<double> vel(nv), tab(lkbcs::trig_tz_table_count(g));
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaMemcpy(vel.data(), velocities, sizeof(double) * nv, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return cuda_fail(e, "lk_trig_tz_tables");
+  lkbcs::trig_tz_tables(tab.data(), g, lo, xlo, vel.data());
+  e = cudaMemcpy(tables, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return cuda_fail(e, "lk_trig_tz_tables");
+  return LK_OK;
+}
+int lk_set_trig_tz_source(double* rhs, const lk_geom* g, const double* tables, const double* velocities, double time, double amp,
+                          void* stream) {
+  if (!geom_ok(g) || !rhs || !tables || !velocities) return fail(LK_ERR_ARG, "lk_set_trig_tz_source: bad argument");
+  CHECK_LAUNCH(lkbcs::trig_tz(rhs, nullptr, g, tables, velocities, time, amp, (cudaStream_t)stream, &g_fft_launches),
+               "lk_set_trig_tz_source");
+}
+int lk_compute_trig_tz_source_error(double* error, const double* soln, const lk_geom* g, const double* tables,
+                                    const double* velocities, double time, double amp, void* stream) {
+  if (!geom_ok(g) || !error || !soln || !tables || !velocities)
+    return fail(LK_ERR_ARG, "lk_compute_trig_tz_source_error: bad argument");
+  CHECK_LAUNCH(lkbcs::trig_tz(error, soln, g, tables, velocities, time, amp, (cudaStream_t)stream, &g_fft_launches),
+               "lk_compute_trig_tz_source_error");
 }
 int lk_append_krook(double* rhs, const double* u, const lk_geom* g, const double* nu, double dt, const lk_inflow* ic, void* stream) {
   if (!geom_ok(g) || !rhs || !u || !nu || !(dt != 0.0) || !inflow_tables_ok(ic)) return fail(LK_ERR_ARG, "lk_append_krook: bad argument");

@@ -219,6 +219,10 @@ struct KineticSpecies {
   // a pitch-angle collision operator (KineticSpecies.C:1036-1046; PitchAngleCollisionOperator.C): its parameters and
   // the three reduced fields IVx, IVy, IVth (n1d,n2d) every evaluation recomputes
   bool has_coll = false;
+  // TrigTZSource (KineticSpecies.C:1077-1080): the manufactured-solution forcing; tables of lk_trig_tz_tables
+  bool has_tz = false;
+  double tz_amp = 0.0;
+  DevBuf<double> tz_tab;
   lk_pitch_angle coll;
   DevBuf<double> coll_iv;
   // completeRHS's collision term on a materialised rhs (PitchAngleCollisionOperator::evaluate)
@@ -605,7 +609,7 @@ struct VPSystem {
       lk_rk_update u;
       memset(&u, 0, sizeof(u));
       // the "JB" fill and a Krook-layer species take the separate passes below
-      const bool plain = !ks->use_new_bcs && !ks->has_krook && !ks->has_coll;
+      const bool plain = !ks->use_new_bcs && !ks->has_krook && !ks->has_coll && !ks->has_tz;
       static const bool no_fold = getenv("LOKI_NO_FOLD") != nullptr;  // A/B aid: the separate fill before every stage
       if (plain) {
         u.accel_bcs = &ks->inflow;
@@ -657,7 +661,7 @@ struct VPSystem {
       // production: the kernel also writes pred's periodic ghost copies in the directions this rank wraps itself
       u.wrap = fused_moments ? ks->wrapFor(uncutDirs() & ~ks->nonperiodic) : 0;
       static const bool krook_passes = getenv("LOKI_KROOK_PASSES") != nullptr;  // debugging aid: the three-pass form
-      const bool passes = ks->has_coll || (ks->has_krook && krook_passes);  // the rhs is materialised between the passes
+      const bool passes = ks->has_coll || ks->has_tz || (ks->has_krook && krook_passes);  // the rhs is materialised between the passes
       if (passes) u.wrap = 0;  // lk_rk_stage_update writes interior cells only: the next fill wraps pred itself
       if (ks->has_krook && !passes) {
         // completeRHS's Krook layer (KineticSpecies.C:1049-1062) inside the fused stage: the per-cell epilogue of the
@@ -676,6 +680,7 @@ struct VPSystem {
         LKH_CHECK(lk_vlasov_rhs(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, nullptr, st));
         if (ks->has_coll) LKH_CHECK(ks->appendCollision(rhs_out, ks->f_eval, st));
         if (ks->has_krook) LKH_CHECK(lk_append_krook(rhs_out, ks->f_eval, &ks->g, ks->krook_nu.p, dt, &ks->inflow, st));
+        if (ks->has_tz) LKH_CHECK(lk_set_trig_tz_source(rhs_out, &ks->g, ks->tz_tab.p, ks->velocities.p, t_stage, ks->tz_amp, st));
         LKH_CHECK(lk_rk_stage_update(rhs_out, &ks->g, &u, st));
       } else {
         const int ie = ks->arrayIndex(ks->f_eval);
@@ -801,6 +806,7 @@ struct VPSystem {
       LKH_CHECK(lk_acceleration_derivatives_4d(rhs_dev[s], f, &ks->g, &a, st));
       if (ks->has_coll) LKH_CHECK(ks->appendCollision(rhs_dev[s], f, st));
       if (ks->has_krook) LKH_CHECK(lk_append_krook(rhs_dev[s], f, &ks->g, ks->krook_nu.p, dt, &ks->inflow, st));
+      if (ks->has_tz) LKH_CHECK(lk_set_trig_tz_source(rhs_dev[s], &ks->g, ks->tz_tab.p, ks->velocities.p, t, ks->tz_amp, st));
       if (ks->has_driver)
         LKH_CHECK(lk_ke_e_dot(ks->ke.p + 3, f, &ks->g, ks->charge, ks->velocities.p, ks->ext_efield.p, st));
     }
@@ -1456,6 +1462,38 @@ int lk_vp_ke_e_dot(lk_vp_system* h, int s, double* value) {
   return LK_OK;
 }
 
+int lk_vp_set_trig_tz(lk_vp_system* h, int s, int on, double amp) {
+  // kinetic_species.N.tz.name = "TrigTZSource", tz.amp (TrigTZSource.C:21-42): the forcing of completeRHS
+  if (!h || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  auto& S = h->sys;
+  auto* ks = S.species[s];
+  ks->has_tz = false;
+  if (!on) return LK_OK;
+  int64_t count = 0;
+  int st = lk_trig_tz_table_count(&ks->g, &count);
+  if (st != LK_OK) return st;
+  st = ks->tz_tab.alloc((size_t)count);
+  if (st != LK_OK) return st;
+  const int lo[2] = {S.desc.tile_lo[0] - ks->g.ng, S.desc.tile_lo[1] - ks->g.ng};
+  st = lk_trig_tz_tables(ks->tz_tab.p, &ks->g, lo, S.desc.xlo, ks->velocities.p, S.st);
+  if (st != LK_OK) return st;
+  ks->has_tz = true;
+  ks->tz_amp = amp;
+  return LK_OK;
+}
+int lk_vp_trig_tz_error(lk_vp_system* h, int s, double time, double* error_host) {
+  // TrigTZSource::computeError (TrigTZSource.C:63-82) of the state: what putToRestart dumps instead of the
+  // distribution when a twilight zone is defined (KineticSpecies.C:987-1004)
+  if (!h || !error_host || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
+  auto& S = h->sys;
+  auto* ks = S.species[s];
+  if (!ks->has_tz) return LK_ERR_ARG;
+  if (!ks->rhs_tmp.p) LKH_CHECK(ks->rhs_tmp.alloc(ks->vol));
+  LKH_CHECK(lk_compute_trig_tz_source_error(ks->rhs_tmp.p, ks->state(), &ks->g, ks->tz_tab.p, ks->velocities.p, time, ks->tz_amp, S.st));
+  LKH_CUDA(cudaStreamSynchronize(S.st));
+  LKH_CUDA(cudaMemcpy(error_host, ks->rhs_tmp.p, sizeof(double) * ks->vol, cudaMemcpyDeviceToHost));
+  return LK_OK;
+}
 int lk_vp_update_ghosts(lk_vp_system* h) {
   // VPSystem::updateGhosts (VPSystem.C:779-797), the species part: fillAdvectionGhostCells of the state on this rank
   if (!h) return LK_ERR_ARG;

@@ -25,6 +25,8 @@ class Species:
 
         # options beyond the benchmark decks: a Krook layer and a pitch-angle collision operator (see Deck.apply_options)
         self.krook, self.collision = None, None
+        # a TrigTZSource (TrigTZSource.C): Species.tz = dict(amp=) adds the manufactured-solution forcing to the rhs
+        self.tz = None
         # "Interpenetrating Stream" initial condition, half-plane syntax (InterpenetratingStreamIC.C:496-540):
         # dict(tl, tt, theta, d, beta, floor, frac, frac2, two_sided, centered)
         self.stream = stream
@@ -106,6 +108,9 @@ class Deck:
                 pa = PitchAngle.make(co["range_lo"], co["range_hi"], co["vfloor"], co["vthermal_dt"], co["nu_coef"],
                                      co.get("conservative", 1))
                 st = H.lk_vp_set_pitch_angle(sys_, s, pa)
+            tz = getattr(sp, "tz", None)
+            if st == 0 and tz:
+                st = H.lk_vp_set_trig_tz(sys_, s, 1, float(tz["amp"]))
         return st
 
     def geom_of(self, sp):

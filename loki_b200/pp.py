@@ -119,7 +119,7 @@ def _species(params, k):
     vlim = tuple(float(t) for t in params[pre + "velocity_limits"][:4])
     mass, charge = _f(params, pre + "mass"), _f(params, pre + "charge")
     name = _s(params, pre + "name", "species%d" % k)
-    icn = _s(params, pre + "ic.name")
+    icn = _s(params, pre + "ic.name", "Perturbed Maxwellian")      # the factory's default (ICFactory.C:26-27)
     g = lambda key, dflt=0.0: _f(params, pre + "ic." + key, dflt)
     driver, driver_phase, driver_shape_type = None, 0.0, 0
     ndrv = int(_f(params, pre + "num_external_drivers", 0.0))
@@ -190,8 +190,18 @@ def _species(params, k):
         raise ValueError("species %d: Krook layer needs a positive power and a non-negative coefficient" % k)   # KrookLayer.C:195-201
     if not any(e in krook for e in ("x1a", "x1b", "x2a", "x2b")):
         krook = None
-    if any(key.startswith(pre + "tz.") for key in list(params.keys())):
-        raise ValueError("species %d: twilight-zone sources are out of scope" % k)
+    # TZSourceFactory::create (TZSourceFactory.C:22-56): the twilight-zone (manufactured-solution) forcing; TrigTZSource
+    # (one species, TrigTZSource.C:21-42) is implemented, the two-species ion-acoustic sources are not
+    tz = None
+    if (pre + "tz.name") in params:
+        tzname = _s(params, pre + "tz.name")
+        if tzname != "TrigTZSource":
+            raise ValueError("species %d: twilight-zone source %r is not supported (only TrigTZSource)" % (k, tzname))
+        if (pre + "tz.amp") not in params:
+            raise ValueError("Must supply amp")                                   # TrigTZSource.C:28-31
+        tz = dict(amp=_f(params, pre + "tz.amp"))
+    elif any(key.startswith(pre + "tz.") for key in list(params.keys())):
+        raise ValueError("species %d: tz.* keys without tz.name" % k)
     if icn == "Perturbed Maxwellian":
         sp = _d.Species(name, nv, vlim, mass, charge, tx=g("tx", 1.0), ty=g("ty", 1.0), A=g("A"), B=g("B"), Cc=g("C"),
                           kx1=g("kx1"), ky1=g("ky1"), kx2=g("kx2"), ky2=g("ky2"), frac=g("frac", 1.0), driver=driver,
@@ -200,6 +210,7 @@ def _species(params, k):
         sp.driver_phase, sp.driver_shape_type = driver_phase, driver_shape_type
         sp.krook = krook
         sp.collision = collision
+        sp.tz = tz
         return sp
     if icn == "Interpenetrating Stream":
         if _s(params, pre + "ic.syntax", "half plane") != "half plane":
@@ -214,6 +225,7 @@ def _species(params, k):
         sp.driver_phase, sp.driver_shape_type = driver_phase, driver_shape_type
         sp.krook = krook
         sp.collision = collision
+        sp.tz = tz
         return sp
     raise ValueError("unsupported initial condition %r" % icn)
 

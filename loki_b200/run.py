@@ -239,6 +239,9 @@ class Runner:
         items = []
         for s, sp in enumerate(d.species):
             f = self.state(s)
+            if getattr(sp, "tz", None):
+                # with a twilight zone the dump holds the error against the exact solution (KineticSpecies.C:987-1004)
+                capi.check(self.H.lk_vp_trig_tz_error(self.sys, s, self.time, f.ctypes.data), "lk_vp_trig_tz_error")
             vlim = sp.vlim
             ncell = [d.n[0], d.n[1], sp.nv[0], sp.nv[1]]
             x_lo = [d.xlim[0], d.xlim[2], vlim[0], vlim[2]]

@@ -36,9 +36,11 @@ ROUTINES = {
                                        "appendpitchanglecollision", "computepitchanglespeciesmoments",
                                        "computepitchanglespeciesreducedfields", "computepitchanglespecieskec",
                                        "computepitchanglespeciesvthermal"],
+    "TZSourceF.f": ["settrigtzsource", "computetrigtzsourceerror"],
 }
 ALL_WANTED = {r for rs in ROUTINES.values() for r in rs}
-INTRINSICS = {"max": "fmax", "min": "fmin", "abs": "fabs", "sqrt": "sqrt"}
+INTRINSICS = {"max": "fmax", "min": "fmin", "abs": "fabs", "sqrt": "sqrt", "sin": "sin", "cos": "cos", "exp": "exp",
+              "atan": "atan"}
 EXTERNAL_REAL_FUNCS = {"initialconditionatpoint"}
 
 

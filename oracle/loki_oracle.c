@@ -1056,6 +1056,60 @@ void ok_append_krook(double* rhs, const double* u, const ok_geom* g, const doubl
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Twilight-zone (manufactured-solution) source of TrigTZSource (TZSourceF.f:10-75 settrigtzsource, :79-137
+ * computetrigtzsourceerror; called from completeRHS, KineticSpecies.C:1077-1080, and putToRestart, :987-1004).
+ * The exact solution is f = alpha/(2 pi) exp(-alpha v^2/2) (1 + A cos(kx x) cos(ky y) sin(kt t)) with kx = ky = kt = alpha = 1;
+ * h is what must be added to the Vlasov-Poisson right-hand side so that f solves the forced equation.  Maple's
+ * expression, evaluated in the Fortran's parse order.  lo: global index of array cell 0 (the dataBox lower bound).
+ * ------------------------------------------------------------------------------------------ */
+void ok_set_trig_tz_source(double* f, const ok_geom* g, const int* lo, const double* xlo, const double* dx, double time,
+                           const double* velocities, double amp) {
+  const int64_t n3d = ND(2), n4d = ND(3);
+  const double kx = 1.0, ky = 1.0, kt = 1.0, alpha = 1.0, A = amp, t = time;
+  const double pi = 4.0 * atan(1.0);
+  for (int i4 = 0; i4 < n4d; ++i4)
+    for (int i3 = 0; i3 < n3d; ++i3) {
+      const double vx = velocities[i3 + n3d * (i4 + n4d * 0)];
+      const double vy = velocities[i3 + n3d * (i4 + n4d * 1)];
+      for (int i2 = 0; i2 < ND(1); ++i2) {
+        const double y = xlo[1] + ((lo[1] + i2) + 0.5) * dx[1];
+        for (int i1 = 0; i1 < ND(0); ++i1) {
+          const double x = xlo[0] + ((lo[0] + i1) + 0.5) * dx[0];
+          const double h =
+              -0.1e1 / (kx * kx + ky * ky) * A * sin(kx * x) * kx * cos(ky * y) * sin(kt * t) * (alpha * alpha) / pi * vx *
+                  exp(-(alpha * (vx * vx + vy * vy) / 0.2e1)) * (0.1e1 + A * cos(kx * x) * cos(ky * y) * sin(kt * t)) / 0.2e1 -
+              0.1e1 / (kx * kx + ky * ky) * A * cos(kx * x) * sin(ky * y) * ky * sin(kt * t) * (alpha * alpha) / pi * vy *
+                  exp(-(alpha * (vx * vx + vy * vy) / 0.2e1)) * (0.1e1 + A * cos(kx * x) * cos(ky * y) * sin(kt * t)) / 0.2e1 -
+              alpha / pi * exp(-(alpha * (vx * vx + vy * vy) / 0.2e1)) * A * sin(kx * x) * kx * cos(ky * y) * sin(kt * t) * vx / 0.2e1 -
+              alpha / pi * exp(-(alpha * (vx * vx + vy * vy) / 0.2e1)) * A * cos(kx * x) * sin(ky * y) * ky * sin(kt * t) * vy / 0.2e1 +
+              alpha / pi * exp(-(alpha * (vx * vx + vy * vy) / 0.2e1)) * A * cos(kx * x) * cos(ky * y) * cos(kt * t) * kt / 0.2e1;
+          F4(f, i1, i2, i3, i4) = F4(f, i1, i2, i3, i4) + h;
+        }
+      }
+    }
+}
+void ok_compute_trig_tz_source_error(double* error, const double* soln, const ok_geom* g, const int* lo, const double* xlo,
+                                     const double* dx, double time, const double* velocities, double amp) {
+  const int64_t n3d = ND(2), n4d = ND(3);
+  const double kx = 1.0, ky = 1.0, kt = 1.0, alpha = 1.0, A = amp, t = time;
+  const double pi = 4.0 * atan(1.0);
+  for (int i4 = 0; i4 < n4d; ++i4)
+    for (int i3 = 0; i3 < n3d; ++i3) {
+      const double vx = velocities[i3 + n3d * (i4 + n4d * 0)];
+      const double vy = velocities[i3 + n3d * (i4 + n4d * 1)];
+      for (int i2 = 0; i2 < ND(1); ++i2) {
+        const double y = xlo[1] + ((lo[1] + i2) + 0.5) * dx[1];
+        for (int i1 = 0; i1 < ND(0); ++i1) {
+          const double x = xlo[0] + ((lo[0] + i1) + 0.5) * dx[0];
+          const double fexact = alpha / pi * exp(-(alpha * (vx * vx + vy * vy) / 0.2e1)) *
+                                (0.1e1 + A * cos(kx * x) * cos(ky * y) * sin(kt * t)) / 0.2e1;
+          F4(error, i1, i2, i3, i4) = F4(soln, i1, i2, i3, i4) - fexact;
+        }
+      }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Time-history diagnostics.
  * computeke (KineticSpeciesF.f:2447-2500): out = {ke, ke_x, ke_y, px, py}; the running sums start from
  * the incoming values like the Fortran's (the caller zeroes them, KineticSpecies.C:1198-1213).

@@ -100,6 +100,12 @@ double ok_compute_ke_e_dot(const ok_geom* g, const double* u, double charge, con
                            const double* ext_efield, double ke_e_dot_in);
 
 /* appendkrook (KineticSpeciesF.f:2995-3034): rhs -= nu(x,y)/dt * (u - IC) where nu != 0; nu: (n1d,n2d) */
+/* TrigTZSource (TZSourceF.f:10-137): the manufactured-solution source added to rhs over the whole data box, and
+ * error = soln - f_exact; lo = global index of array cell 0 in x and y */
+void ok_set_trig_tz_source(double* f, const ok_geom* g, const int* lo, const double* xlo, const double* dx, double time,
+                           const double* velocities, double amp);
+void ok_compute_trig_tz_source_error(double* error, const double* soln, const ok_geom* g, const int* lo, const double* xlo,
+                                     const double* dx, double time, const double* velocities, double amp);
 void ok_append_krook(double* rhs, const double* u, const ok_geom* g, const double* nu, double dt, ok_ic_fn ic,
                      void* ic_ctx);
 /* ---- PitchAngleCollisionOperatorF.f / PitchAngleCollisionOperator.C (loki_oracle_coll.c) ---- */
@@ -188,6 +194,8 @@ void ok_vp_set_krook(ok_vp_work* w, int s, const double* nu);
 /* a pitch-angle collision operator on species s (KineticSpecies.C:1036-1046, 666-672); p = {range_lo[2], range_hi[2],
  * vfloor, vthermal_dt, nuCoeff, conservative}; NULL removes it */
 void ok_vp_set_pitch_angle(ok_vp_work* w, int s, const double* p);
+/* TrigTZSource of species s: on != 0 adds ok_set_trig_tz_source(amp) in completeRHS */
+void ok_vp_set_trig_tz(ok_vp_work* w, int s, int on, double amp);
 void ok_vp_set_dt(ok_vp_work* w, double dt);   /* the a_dt of a bare ok_vp_eval_rhs call (completeRHS) */
 /* rhs[s], f[s]: 4D arrays incl. ghosts; f's ghosts are modified like the reference does.
  * ke_e_dot[s] receives rhs.m_integrated_ke_e_dot for driven species. */

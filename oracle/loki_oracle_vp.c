@@ -32,6 +32,7 @@ struct ok_vp_work {
   int nonperiodic[2], use_new_bcs;
   double** krook_nu;
   double** coll;   /* pitch-angle operator parameters per species (8 doubles) or NULL */
+  double** tz;     /* TrigTZSource amplitude per species (1 double) or NULL (KineticSpecies.C:1077-1080) */
   double cur_dt;
 };
 
@@ -102,7 +103,7 @@ ok_vp_work* ok_vp_work_create(int ns, const ok_species* sp, const double* xlo, c
   memcpy(w->sp, sp, sizeof(ok_species) * ns);
   for (int k = 0; k < 2; ++k) { w->xlo[k] = xlo[k]; w->xhi[k] = xhi[k]; }
 #define PP(name) w->name = (double**)calloc(ns, sizeof(double*))
-  PP(velocities); PP(vxface); PP(vyface); PP(vel1); PP(vel2); PP(vel3); PP(vel4); PP(accel); PP(rho_s); PP(ext); PP(krook_nu); PP(coll);
+  PP(velocities); PP(vxface); PP(vyface); PP(vel1); PP(vel2); PP(vel3); PP(vel4); PP(accel); PP(rho_s); PP(ext); PP(krook_nu); PP(coll); PP(tz);
   PP(rhs); PP(delta);
   for (int i = 0; i < 8; ++i) { PP(k[i]); w->ke_k[i] = (double*)calloc(ns, sizeof(double)); }
 #undef PP
@@ -157,9 +158,10 @@ void ok_vp_work_destroy(ok_vp_work* w) {
   }
   for (int i = 0; i < 8; ++i) { free(w->k[i]); free(w->ke_k[i]); }
   free(w->last_ax); free(w->last_ay);
-  for (int s = 0; s < w->ns; ++s) { free(w->krook_nu[s]); free(w->coll[s]); }
+  for (int s = 0; s < w->ns; ++s) { free(w->krook_nu[s]); free(w->coll[s]); free(w->tz[s]); }
   free(w->krook_nu);
   free(w->coll);
+  free(w->tz);
   free(w->velocities); free(w->vxface); free(w->vyface); free(w->vel1); free(w->vel2); free(w->vel3);
   free(w->vel4); free(w->accel); free(w->ext); free(w->rho_s); free(w->rhs); free(w->delta); free(w->ke_rhs);
   free(w->ke_delta); free(w->rho); free(w->phi); free(w->em); free(w->sx); free(w->sy); free(w->sp);
@@ -191,6 +193,14 @@ void ok_vp_set_pitch_angle(ok_vp_work* w, int s, const double* p) {
   if (p) {
     w->coll[s] = (double*)malloc(sizeof(double) * 8);
     memcpy(w->coll[s], p, sizeof(double) * 8);
+  }
+}
+void ok_vp_set_trig_tz(ok_vp_work* w, int s, int on, double amp) {
+  free(w->tz[s]);
+  w->tz[s] = NULL;
+  if (on) {
+    w->tz[s] = (double*)malloc(sizeof(double));
+    w->tz[s][0] = amp;
   }
 }
 /* fillAdvectionGhostCells on one rank (KineticSpecies.H:404-412, 998-1031): physical boundary conditions of the
@@ -266,6 +276,11 @@ void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double time, double
       free(iv);
     }
     if (w->krook_nu[s]) ok_append_krook(rhs[s], f[s], g, w->krook_nu[s], w->cur_dt, sp->ic, sp->ic_ctx);
+    if (w->tz[s]) {
+      /* the twilight-zone source (KineticSpecies.C:1077-1080) */
+      const int lo[2] = {-g->ng, -g->ng};
+      ok_set_trig_tz_source(rhs[s], g, lo, w->xlo, g->dx, time, w->velocities[s], w->tz[s][0]);
+    }
     if (sp->has_driver && ke_e_dot)
       ke_e_dot[s] = ok_compute_ke_e_dot(g, f[s], sp->charge, w->velocities[s], w->ext[s], 0.0);
   }

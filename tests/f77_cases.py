@@ -213,6 +213,18 @@ def kinetic_cases(B, ok, order):
     B.call("appendkrook_", *db, *ib, B.d(0.037), B.ic(s, [data[2 * k] for k in range(4)]), B.arr(nu), B.arr(s.f), B.arr(rk))
     B.finish()
     out["krook"] = rk
+    # TrigTZSource (TZSourceF.f:10-137): the twilight-zone source added to a right-hand side over the data box, and the
+    # error of a state against the exact solution; only the data box is passed, the domain arrays stay on the host
+    xlo4 = np.array([-2 * np.pi, -1.5, -7.0, -7.0])
+    xhi4 = -xlo4
+    tz = np.ascontiguousarray(rng.uniform(-1, 1, size=s.f.shape))
+    amp = np.array([0.7])
+    B.call("settrigtzsource_", B.arr(tz), *db, B.meta(xlo4), B.meta(xhi4), B.meta(dxs), B.d(0.37), B.arr(s.velocities), B.meta(amp))
+    err = np.zeros_like(s.f)
+    B.call("computetrigtzsourceerror_", B.arr(err), B.arr(s.f), *db, B.meta(xlo4), B.meta(xhi4), B.meta(dxs), B.d(0.37),
+           B.arr(s.velocities), B.meta(amp))
+    B.finish()
+    out["tz_source"], out["tz_error"] = tz, err
     return out
 
 

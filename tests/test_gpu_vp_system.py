@@ -29,6 +29,9 @@ def _oracle(ok, deck):
             p = np.array(list(co["range_lo"]) + list(co["range_hi"]) + [co["vfloor"], co["vthermal_dt"], co["nu_coef"],
                                                                         float(co.get("conservative", 1))])
             ok.ok_vp_set_pitch_angle(w, s_, p.ctypes.data)
+        tz = getattr(sp_, "tz", None)
+        if tz:   # a TrigTZSource: the manufactured-solution forcing in completeRHS
+            ok.ok_vp_set_trig_tz(w, s_, 1, float(tz["amp"]))
     return w, sp, keep
 
 

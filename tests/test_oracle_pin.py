@@ -345,3 +345,28 @@ def test_pin_pitch_angle_operator(ok, ref, order):
             g = np.ones(s.f.shape, bool)
             g[ng:-ng, ng:-ng, ng:-ng, ng:-ng] = False
             assert np.array_equal(r1[g], base[g]) and np.array_equal(r2[g], base[g])
+
+
+@needs_ref
+@pytest.mark.parametrize("n,order,lo", CASES)
+def test_pin_trig_tz_source(ok, ref, n, order, lo):
+    """settrigtzsource / computetrigtzsourceerror (TZSourceF.f:10-137): the oracle's restatement against the
+    transliterated Fortran, bit for bit, on a box whose data-box lower bound is not zero"""
+    s = Setup(ok, n, order, bz=0.0)
+    R = ref
+    db, ib, data, inter = R.boxes(s, lo)
+    xlo = np.array([-2 * np.pi, -1.5, -7.0, -7.0])
+    xhi = -xlo
+    dx = np.array(s.dx)
+    lo2 = (C.c_int * 2)(data[0], data[2])
+    for time, amp in ((0.0, 1.0), (0.37, 0.1), (2.5, 1.0)):
+        base = np.random.default_rng(3).uniform(-1, 1, size=s.f.shape)
+        r1, r2 = base.copy(), base.copy()
+        ok.ok_set_trig_tz_source(r1.ravel(), C.byref(s.g), lo2, xlo, dx, time, s.velocities, amp)
+        R.L.settrigtzsource_(R._p(r2), *db, R._p(xlo), R._p(xhi), R._p(dx), R._d(time), R._p(s.velocities), R._p(np.array([amp])))
+        assert np.array_equal(r1, r2) and not np.array_equal(r1, base)
+        e1, e2 = np.zeros_like(base), np.zeros_like(base)
+        ok.ok_compute_trig_tz_source_error(e1.ravel(), s.f.ravel(), C.byref(s.g), lo2, xlo, dx, time, s.velocities, amp)
+        R.L.computetrigtzsourceerror_(R._p(e2), R._p(s.f), *db, R._p(xlo), R._p(xhi), R._p(dx), R._d(time), R._p(s.velocities),
+                                      R._p(np.array([amp])))
+        assert np.array_equal(e1, e2)
