@@ -266,6 +266,24 @@ int lk_maxwell_rhs(double* rhs, const double* em, const double* Jx, const double
                    int n1, int n2, int ng, int order, const double* dx, double light_speed, double av_weak,
                    double av_strong, void* stream);
 
+/* The boundary routines of MaxwellF.f that Maxwell::fillGhostCells / evalRHS call when a direction is not periodic
+ * (Maxwell.C:562-623), and the antenna source (Maxwell.C:299-353).  Arrays are device (n1d, n2d, ncomp) over the interior
+ * n1 x n2 grown by ng; at[4] = {x low, x high, y low, y high}: this rank's box touches that physical boundary (the
+ * Fortran's m1a .eq. 0, m1b .eq. nx-1, m2a .eq. 0, m2b .eq. ny-1).
+ *   lk_zero_ghost_2d               zeroghost2d_ (MaxwellF.f:10-58): ghost layers of all ncomp components = 0
+ *   lk_maxwell_add_antenna_source  maxwelladdantennasource_ (:359-389): dEMvars -= antenna_source, interior, 6 components
+ *   lk_maxwell_set_em_bcs          maxwellsetembcs_ (:473-657): third-order extrapolation into the ghost layers of the
+ *                                  six fields, then the incoming characteristic of (Ey,Bz), (-Ez,By) [x edges] and
+ *                                  (-Ex,Bz), (Ez,Bx) [y edges] zeroed; interior rows / columns only, corners untouched
+ *   lk_maxwell_set_vz_bcs          maxwellsetvzbcs_ (:661-731): even reflection of vz about the boundary cell, x edges
+ *                                  over every row of the data box, then y edges over every column */
+int lk_zero_ghost_2d(double* u, int n1, int n2, int ng, int ncomp, void* stream);
+int lk_maxwell_add_antenna_source(double* dem, const double* antenna_source, int n1, int n2, int ng, void* stream);
+int lk_maxwell_set_em_bcs(double* em, int n1, int n2, int order, const int at[4], int x_periodic, int y_periodic,
+                          double light_speed, void* stream);
+int lk_maxwell_set_vz_bcs(double* vz, int n1, int n2, int order, const int at[4], int x_periodic, int y_periodic,
+                          void* stream);
+
 /* maxwellevalvzrhs_ (MaxwellF.f:442-469): dvz = (q/m) Ez on the interior of a (n1d,n2d) array */
 int lk_maxwell_vz_rhs(double* dvz, const double* em, int n1, int n2, int ng, double charge_per_mass, void* stream);
 

@@ -183,6 +183,18 @@ void maxwellevalrhs_(const int* md1a, const int* md1b, const int* md2a, const in
 /* MaxwellF.f:442-469 */
 void maxwellevalvzrhs_(const int* md1a, const int* md1b, const int* md2a, const int* md2b, const int* m1a, const int* m1b,
                        const int* m2a, const int* m2b, const double* charge_per_mass, const double* emvars, double* dvz);
+/* MaxwellF.H:26-37 (MaxwellF.f:10-58), :77-89 (:359-389), :105-121 (:473-657), :123-133 (:661-731) */
+void zeroghost2d_(double* u, const int* n1a, const int* n1b, const int* n2a, const int* n2b, const int* nd1a, const int* nd1b,
+                  const int* nd2a, const int* nd2b, const int* dim);
+void maxwelladdantennasource_(const int* md1a, const int* md1b, const int* md2a, const int* md2b, const int* m1a, const int* m1b,
+                              const int* m2a, const int* m2b, const double* xlo, const double* xhi, const double* dx,
+                              const double* antenna_source, double* dEMvars);
+void maxwellsetembcs_(const int* md1a, const int* md1b, const int* md2a, const int* md2b, const int* m1a, const int* m1b,
+                      const int* m2a, const int* m2b, double* EMvars, const int* nx, const int* ny, const int* xPeriodic,
+                      const int* yPeriodic, const int* solution_order, const double* c);
+void maxwellsetvzbcs_(const int* md1a, const int* md1b, const int* md2a, const int* md2b, const int* m1a, const int* m1b,
+                      const int* m2a, const int* m2b, double* vz, const int* nx, const int* ny, const int* xPeriodic,
+                      const int* yPeriodic, const int* solution_order);
 /* MaxwellF.f:62-93 */
 void xpby2d_(double* x, const double* y, const double* b, const int* nd1a, const int* nd1b, const int* nd2a,
              const int* nd2b, const int* n1a, const int* n1b, const int* n2a, const int* n2b, const int* dim);

@@ -326,4 +326,120 @@ cudaError_t trig_tz(double* out, const double* soln, const lk_geom* g, const dou
   return cudaGetLastError();
 }
 
+// ---- MaxwellF.f boundary routines (zeroghost2d :10-58, maxwelladdantennasource :359-389, maxwellsetembcs :473-657,
+// maxwellsetvzbcs :661-731).  Arrays (n1d, n2d, ncomp); the ghost layers are filled outward one after the other, each
+// from the three cells inside it, so a thread owns one boundary line and walks its ghosts in the Fortran's order.
+#define E3(a, i1, i2, c) (a)[(i1) + (i64)n1d * ((i2) + (i64)n2d * (c))]
+__global__ void k_zero_ghost_2d(double* __restrict__ u, int n1, int n2, int ng, int dim) {
+  const int n1d = n1 + 2 * ng, n2d = n2 + 2 * ng;
+  const i64 total = (i64)n1d * n2d * dim;
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+    const int i1 = (int)(t % n1d), i2 = (int)((t / n1d) % n2d);
+    if (i1 < ng || i1 >= ng + n1 || i2 < ng || i2 >= ng + n2) u[t] = 0.0;
+  }
+}
+__global__ void k_antenna_source(double* __restrict__ dem, const double* __restrict__ src, int n1, int n2, int ng) {
+  const int n1d = n1 + 2 * ng, n2d = n2 + 2 * ng;
+  const i64 total = (i64)n1 * n2 * 6;
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+    const int i1 = (int)(t % n1) + ng, i2 = (int)((t / n1) % n2) + ng, c = (int)(t / ((i64)n1 * n2));
+    E3(dem, i1, i2, c) = E3(dem, i1, i2, c) - E3(src, i1, i2, c);
+  }
+}
+// the outgoing characteristic of the pair (s1 * a, b) is kept, the incoming one zeroed (MaxwellF.f:519-541)
+__device__ __forceinline__ void em_characteristic(double* pa, double* pb, double s1, double c, int high) {
+  double u1 = s1 * *pa, u2 = *pb;
+  double w1 = +u1 / (2. * c) + u2 / 2.;
+  double w2 = -u1 / (2. * c) + u2 / 2.;
+  if (high) w2 = 0.0; else w1 = 0.0;
+  u1 = c * (w1 - w2);
+  u2 = w1 + w2;
+  *pa = s1 * u1;
+  *pb = u2;
+}
+// dir 0: x edges (one thread per interior row i2), dir 1: y edges (one thread per interior column i1)
+__global__ void k_em_bcs(double* __restrict__ em, int n1, int n2, int ng, int dir, int at_lo, int at_hi, double c) {
+  const int n1d = n1 + 2 * ng, n2d = n2 + 2 * ng;
+  const int lines = dir == 0 ? n2 : n1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * lines) return;
+  const int high = t / lines, line = t % lines + ng;
+  if (high ? !at_hi : !at_lo) return;
+  const int d = high ? 1 : -1;
+  if (dir == 0) {
+    const int i1 = high ? ng + n1 - 1 : ng, i2 = line;
+    for (int i4 = 1; i4 <= ng; ++i4) {
+      const int ig = i1 + d * i4;
+      for (int k = 0; k < 6; ++k)
+        E3(em, ig, i2, k) = +3.0 * E3(em, ig - d, i2, k) - 3.0 * E3(em, ig - 2 * d, i2, k) + 1.0 * E3(em, ig - 3 * d, i2, k);
+      em_characteristic(&E3(em, ig, i2, 1), &E3(em, ig, i2, 5), 1.0, c, high);   // Ey, Bz
+      em_characteristic(&E3(em, ig, i2, 2), &E3(em, ig, i2, 4), -1.0, c, high);  // -Ez, By
+    }
+  } else {
+    const int i2 = high ? ng + n2 - 1 : ng, i1 = line;
+    for (int i4 = 1; i4 <= ng; ++i4) {
+      const int ig = i2 + d * i4;
+      for (int k = 0; k < 6; ++k)
+        E3(em, i1, ig, k) = +3.0 * E3(em, i1, ig - d, k) - 3.0 * E3(em, i1, ig - 2 * d, k) + 1.0 * E3(em, i1, ig - 3 * d, k);
+      em_characteristic(&E3(em, i1, ig, 0), &E3(em, i1, ig, 5), -1.0, c, high);  // -Ex, Bz
+      em_characteristic(&E3(em, i1, ig, 2), &E3(em, i1, ig, 3), 1.0, c, high);   // Ez, Bx
+    }
+  }
+}
+// even reflection about the boundary cell; dir 0 over every row of the data box, dir 1 over every column
+__global__ void k_vz_bcs(double* __restrict__ vz, int n1, int n2, int ng, int dir, int at_lo, int at_hi) {
+  const int n1d = n1 + 2 * ng, n2d = n2 + 2 * ng;
+  const int lines = dir == 0 ? n2d : n1d;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * lines) return;
+  const int high = t / lines, line = t % lines;
+  if (high ? !at_hi : !at_lo) return;
+  for (int i3 = 1; i3 <= ng; ++i3) {
+    if (dir == 0) {
+      const int i1 = high ? ng + n1 - 1 : ng;
+      E3(vz, high ? i1 + i3 : i1 - i3, line, 0) = E3(vz, high ? i1 - i3 : i1 + i3, line, 0);
+    } else {
+      const int i2 = high ? ng + n2 - 1 : ng;
+      E3(vz, line, high ? i2 + i3 : i2 - i3, 0) = E3(vz, line, high ? i2 - i3 : i2 + i3, 0);
+    }
+  }
+}
+#undef E3
+cudaError_t zero_ghost_2d(double* u, int n1, int n2, int ng, int dim, cudaStream_t st, int64_t* launches) {
+  const i64 total = (i64)(n1 + 2 * ng) * (n2 + 2 * ng) * dim;
+  k_zero_ghost_2d<<<(unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256), 256, 0, st>>>(u, n1, n2, ng, dim);
+  ++*launches;
+  return cudaGetLastError();
+}
+cudaError_t antenna_source(double* dem, const double* src, int n1, int n2, int ng, cudaStream_t st, int64_t* launches) {
+  const i64 total = (i64)n1 * n2 * 6;
+  k_antenna_source<<<(unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256), 256, 0, st>>>(dem, src, n1, n2, ng);
+  ++*launches;
+  return cudaGetLastError();
+}
+cudaError_t em_bcs(double* em, int n1, int n2, int ng, const int at[4], int x_periodic, int y_periodic, double c, cudaStream_t st,
+                   int64_t* launches) {
+  if (x_periodic == 0 && (at[0] || at[1])) {
+    k_em_bcs<<<(2 * n2 + 127) / 128, 128, 0, st>>>(em, n1, n2, ng, 0, at[0], at[1], c);
+    ++*launches;
+  }
+  if (y_periodic == 0 && (at[2] || at[3])) {
+    k_em_bcs<<<(2 * n1 + 127) / 128, 128, 0, st>>>(em, n1, n2, ng, 1, at[2], at[3], c);
+    ++*launches;
+  }
+  return cudaGetLastError();
+}
+cudaError_t vz_bcs(double* vz, int n1, int n2, int ng, const int at[4], int x_periodic, int y_periodic, cudaStream_t st,
+                   int64_t* launches) {
+  if (x_periodic == 0 && (at[0] || at[1])) {
+    k_vz_bcs<<<(2 * (n2 + 2 * ng) + 127) / 128, 128, 0, st>>>(vz, n1, n2, ng, 0, at[0], at[1]);
+    ++*launches;
+  }
+  if (y_periodic == 0 && (at[2] || at[3])) {
+    k_vz_bcs<<<(2 * (n1 + 2 * ng) + 127) / 128, 128, 0, st>>>(vz, n1, n2, ng, 1, at[2], at[3]);
+    ++*launches;
+  }
+  return cudaGetLastError();
+}
+
 }  // namespace lkbcs

@@ -130,6 +130,14 @@ size_t trig_tz_table_count(const lk_geom* g);
 cudaError_t trig_tz(double* out, const double* soln, const lk_geom* g, const double* tab_dev, const double* velocities,
                     double time, double amp, cudaStream_t st, int64_t* launches);
 }
+namespace lkbcs {
+cudaError_t zero_ghost_2d(double* u, int n1, int n2, int ng, int dim, cudaStream_t st, int64_t* launches);
+cudaError_t antenna_source(double* dem, const double* src, int n1, int n2, int ng, cudaStream_t st, int64_t* launches);
+cudaError_t em_bcs(double* em, int n1, int n2, int ng, const int at[4], int x_periodic, int y_periodic, double c, cudaStream_t st,
+                   int64_t* launches);
+cudaError_t vz_bcs(double* vz, int n1, int n2, int ng, const int at[4], int x_periodic, int y_periodic, cudaStream_t st,
+                   int64_t* launches);
+}
 // lk_coll.cu: pitch-angle collision operator
 namespace lkcoll {
 cudaError_t fields(double* ivx, double* ivy, double* vth, const double* u, const lk_geom* g, const double* velocities,
@@ -589,6 +597,26 @@ int lk_periodic_fill_2d(double* u, int n1, int n2, int ng, int ncomp, int px, in
 int lk_xpby2d(double* x, const double* y, double b, int n1, int n2, int ng, int ncomp, void* stream) {
   if (!x || !y || n1 < 1 || n2 < 1 || ng < 0 || ncomp < 1) return fail(LK_ERR_ARG, "lk_xpby2d: bad argument");
   CHECK_LAUNCH(DISPATCH(xpby2d)(x, y, b, n1, n2, ng, ncomp, (cudaStream_t)stream), "lk_xpby2d");
+}
+int lk_zero_ghost_2d(double* u, int n1, int n2, int ng, int ncomp, void* stream) {
+  if (!u || n1 < 1 || n2 < 1 || ng < 0 || ncomp < 1) return fail(LK_ERR_ARG, "lk_zero_ghost_2d: bad argument");
+  CHECK_LAUNCH(lkbcs::zero_ghost_2d(u, n1, n2, ng, ncomp, (cudaStream_t)stream, &g_fft_launches), "lk_zero_ghost_2d");
+}
+int lk_maxwell_add_antenna_source(double* dem, const double* antenna_source, int n1, int n2, int ng, void* stream) {
+  if (!dem || !antenna_source || n1 < 1 || n2 < 1 || ng < 0) return fail(LK_ERR_ARG, "lk_maxwell_add_antenna_source: bad argument");
+  CHECK_LAUNCH(lkbcs::antenna_source(dem, antenna_source, n1, n2, ng, (cudaStream_t)stream, &g_fft_launches), "lk_maxwell_add_antenna_source");
+}
+int lk_maxwell_set_em_bcs(double* em, int n1, int n2, int order, const int at[4], int x_periodic, int y_periodic, double light_speed,
+                          void* stream) {
+  if (!em || !at || (order != 4 && order != 6) || n1 < 3 || n2 < 3 || !(light_speed > 0.0))
+    return fail(LK_ERR_ARG, "lk_maxwell_set_em_bcs: bad argument");
+  CHECK_LAUNCH(lkbcs::em_bcs(em, n1, n2, order == 4 ? 2 : 3, at, x_periodic, y_periodic, light_speed, (cudaStream_t)stream, &g_fft_launches),
+               "lk_maxwell_set_em_bcs");
+}
+int lk_maxwell_set_vz_bcs(double* vz, int n1, int n2, int order, const int at[4], int x_periodic, int y_periodic, void* stream) {
+  if (!vz || !at || (order != 4 && order != 6) || n1 < 4 || n2 < 4) return fail(LK_ERR_ARG, "lk_maxwell_set_vz_bcs: bad argument");
+  CHECK_LAUNCH(lkbcs::vz_bcs(vz, n1, n2, order == 4 ? 2 : 3, at, x_periodic, y_periodic, (cudaStream_t)stream, &g_fft_launches),
+               "lk_maxwell_set_vz_bcs");
 }
 int lk_form_accel(double* accel, const double* em, const double* ext, double normalization, int n1, int n2, int ng,
                   void* stream) {

@@ -603,4 +603,56 @@ void xpby2d_(double* x, const double* y, const double* b, const int* nd1a, const
   if (check(lk_xpby2d(x, y, *b, n1, n2, ng, *dim, nullptr))) check(lk_sync(nullptr));
 }
 
+// MaxwellF.H:26-37, :77-89, :105-133.  Arrays on the device; boxes, nx / ny, flags and c by reference on the host.
+void zeroghost2d_(double* u, const int* n1a, const int* n1b, const int* n2a, const int* n2b, const int* nd1a, const int* nd1b,
+                  const int* nd2a, const int* nd2b, const int* dim) {
+  const int* const nd[4] = {nd1a, nd1b, nd2a, nd2b};
+  const int* const n[4] = {n1a, n1b, n2a, n2b};
+  int n1, n2, ng;
+  if (!geom2_from("zeroghost2d_", nd, n, &n1, &n2, &ng)) return;
+  if (check(lk_zero_ghost_2d(u, n1, n2, ng, *dim, nullptr))) check(lk_sync(nullptr));
+}
+void maxwelladdantennasource_(const int* md1a, const int* md1b, const int* md2a, const int* md2b, const int* m1a, const int* m1b,
+                              const int* m2a, const int* m2b, const double* xlo, const double* xhi, const double* dx,
+                              const double* antenna_source, double* dEMvars) {
+  (void)xlo; (void)xhi; (void)dx;
+  const int* const nd[4] = {md1a, md1b, md2a, md2b};
+  const int* const n[4] = {m1a, m1b, m2a, m2b};
+  int n1, n2, ng;
+  if (!geom2_from("maxwelladdantennasource_", nd, n, &n1, &n2, &ng)) return;
+  if (check(lk_maxwell_add_antenna_source(dEMvars, antenna_source, n1, n2, ng, nullptr))) check(lk_sync(nullptr));
+}
+static bool bc_geom(const char* who, const int* const nd[4], const int* const n[4], const int* nx, const int* ny, const int* order,
+                    int* n1, int* n2, int at[4]) {
+  int ng;
+  if (!geom2_from(who, nd, n, n1, n2, &ng)) return false;
+  if ((*order == 4 ? 2 : 3) != ng) {
+    fail(who, "ghost width does not match solution_order");
+    return false;
+  }
+  at[0] = *n[0] == 0;
+  at[1] = *n[1] == *nx - 1;
+  at[2] = *n[2] == 0;
+  at[3] = *n[3] == *ny - 1;
+  return true;
+}
+void maxwellsetembcs_(const int* md1a, const int* md1b, const int* md2a, const int* md2b, const int* m1a, const int* m1b,
+                      const int* m2a, const int* m2b, double* EMvars, const int* nx, const int* ny, const int* xPeriodic,
+                      const int* yPeriodic, const int* solution_order, const double* c) {
+  const int* const nd[4] = {md1a, md1b, md2a, md2b};
+  const int* const n[4] = {m1a, m1b, m2a, m2b};
+  int n1, n2, at[4];
+  if (!bc_geom("maxwellsetembcs_", nd, n, nx, ny, solution_order, &n1, &n2, at)) return;
+  if (check(lk_maxwell_set_em_bcs(EMvars, n1, n2, *solution_order, at, *xPeriodic, *yPeriodic, *c, nullptr))) check(lk_sync(nullptr));
+}
+void maxwellsetvzbcs_(const int* md1a, const int* md1b, const int* md2a, const int* md2b, const int* m1a, const int* m1b,
+                      const int* m2a, const int* m2b, double* vz, const int* nx, const int* ny, const int* xPeriodic,
+                      const int* yPeriodic, const int* solution_order) {
+  const int* const nd[4] = {md1a, md1b, md2a, md2b};
+  const int* const n[4] = {m1a, m1b, m2a, m2b};
+  int n1, n2, at[4];
+  if (!bc_geom("maxwellsetvzbcs_", nd, n, nx, ny, solution_order, &n1, &n2, at)) return;
+  if (check(lk_maxwell_set_vz_bcs(vz, n1, n2, *solution_order, at, *xPeriodic, *yPeriodic, nullptr))) check(lk_sync(nullptr));
+}
+
 }  // extern "C"

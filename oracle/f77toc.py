@@ -30,7 +30,8 @@ ROUTINES = {
                           "computeadvectionfluxes4d", "computeaccelerationfluxes4d", "accumfluxdiv4d", "computekeflux",
                           "computekevelspaceflux"],
     "PoissonF.f": ["neutralizecharge4d", "computeefieldfrompotential"],
-    "MaxwellF.f": ["maxwellevalrhs", "sgmetricfunction", "maxwellevalvzrhs", "xpby2d"],
+    "MaxwellF.f": ["maxwellevalrhs", "sgmetricfunction", "maxwellevalvzrhs", "xpby2d", "zeroghost2d",
+                   "maxwelladdantennasource", "maxwellsetembcs", "maxwellsetvzbcs"],
     "PitchAngleCollisionOperatorF.f": ["evaluatecollisionality", "conservativepitchangle_4th",
                                        "conservativepitchangle_6th", "nonconservativepitchangle_4th",
                                        "appendpitchanglecollision", "computepitchanglespeciesmoments",

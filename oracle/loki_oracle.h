@@ -162,6 +162,12 @@ void ok_xpby2d(double* x, const double* y, double b, int n1, int n2, int ng, int
 void ok_maxwell_eval_rhs(double* rhs, const double* em, const double* Jx, const double* Jy,
                          const double* Jz, int n1, int n2, int ng, int order, const double* dx,
                          double light_speed, double av_weak, double av_strong);
+/* MaxwellF.f:10-58 zeroghost2d, :359-389 maxwelladdantennasource, :473-657 maxwellsetembcs, :661-731 maxwellsetvzbcs;
+ * at[4] = {x low, x high, y low, y high}: the box touches that physical boundary */
+void ok_zero_ghost_2d(double* u, int n1, int n2, int ng, int dim);
+void ok_maxwell_add_antenna_source(double* dem, const double* antenna, int n1, int n2, int ng);
+void ok_maxwell_set_em_bcs(double* em, int n1, int n2, int order, const int* at, int x_periodic, int y_periodic, double c);
+void ok_maxwell_set_vz_bcs(double* vz, int n1, int n2, int order, const int* at, int x_periodic, int y_periodic);
 void ok_maxwell_eval_vz_rhs(double* rhs, const double* em, double charge_per_mass, int n1, int n2, int ng);
 
 /* ---- composite: one single-rank VP RHS evaluation and one RK4 step (VPSystem.C:372-476,

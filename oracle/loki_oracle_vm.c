@@ -280,3 +280,94 @@ double ok_vm_stable_dt(const ok_vm_work* w, const double* axmax, const double* a
   if (dt_maxwell < dt_stable) dt_stable = dt_maxwell;
   return dt_stable;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * The boundary routines of MaxwellF.f that the periodic decks never reach (Maxwell.C:562-623 calls them when a
+ * direction is not periodic) and the antenna source.  Arrays are (n1d, n2d, ncomp) over the interior n1 x n2 grown by ng;
+ * at[4] = {x low, x high, y low, y high}: this box touches that physical boundary (the Fortran's m1a .eq. 0,
+ * m1b .eq. nx-1, m2a .eq. 0, m2b .eq. ny-1).
+ * ------------------------------------------------------------------------------------------ */
+#define E3(a, i1, i2, c) (a)[(i1) + n1d * ((i2) + n2d * (int64_t)(c))]
+/* zeroghost2d (MaxwellF.f:10-58) */
+void ok_zero_ghost_2d(double* u, int n1, int n2, int ng, int dim) {
+  const int64_t n1d = n1 + 2 * ng, n2d = n2 + 2 * ng;
+  for (int c = 0; c < dim; ++c)
+    for (int i2 = 0; i2 < n2d; ++i2)
+      for (int i1 = 0; i1 < n1d; ++i1)
+        if (i1 < ng || i1 >= ng + n1 || i2 < ng || i2 >= ng + n2) E3(u, i1, i2, c) = 0.0;
+}
+/* maxwelladdantennasource (MaxwellF.f:359-389): dEMvars -= antenna_source on the interior, all six components */
+void ok_maxwell_add_antenna_source(double* dem, const double* antenna, int n1, int n2, int ng) {
+  const int64_t n1d = n1 + 2 * ng, n2d = n2 + 2 * ng;
+  for (int c = 0; c < 6; ++c)
+    for (int i2 = ng; i2 < ng + n2; ++i2)
+      for (int i1 = ng; i1 < ng + n1; ++i1) E3(dem, i1, i2, c) = E3(dem, i1, i2, c) - E3(antenna, i1, i2, c);
+}
+/* one ghost cell of maxwellsetembcs: the outgoing characteristic of the pair (s1 * comp a, comp b) is kept, the incoming
+ * one zeroed (MaxwellF.f:519-541): low side w1 = 0, high side w2 = 0 */
+static void em_characteristic(double* pa, double* pb, double s1, double c, int high) {
+  double u1 = s1 * *pa, u2 = *pb;
+  double w1 = +u1 / (2. * c) + u2 / 2.;
+  double w2 = -u1 / (2. * c) + u2 / 2.;
+  if (high) w2 = 0.0; else w1 = 0.0;
+  u1 = c * (w1 - w2);
+  u2 = w1 + w2;
+  *pa = s1 * u1;
+  *pb = u2;
+}
+/* maxwellsetembcs (MaxwellF.f:473-657) */
+void ok_maxwell_set_em_bcs(double* em, int n1, int n2, int order, const int* at, int x_periodic, int y_periodic, double c) {
+  const int ng = (order == 4) ? 2 : 3;
+  const int64_t n1d = n1 + 2 * ng, n2d = n2 + 2 * ng;
+  if (x_periodic == 0) {
+    for (int high = 0; high < 2; ++high) {
+      if (!at[high]) continue;
+      const int i1 = high ? ng + n1 - 1 : ng, d = high ? 1 : -1;
+      for (int i2 = ng; i2 < ng + n2; ++i2)
+        for (int i4 = 1; i4 <= ng; ++i4) {
+          const int ig = i1 + d * i4;
+          for (int k = 0; k < 6; ++k)
+            E3(em, ig, i2, k) = +3.0 * E3(em, ig - d, i2, k) - 3.0 * E3(em, ig - 2 * d, i2, k) + 1.0 * E3(em, ig - 3 * d, i2, k);
+          em_characteristic(&E3(em, ig, i2, 1), &E3(em, ig, i2, 5), 1.0, c, high);   /* Ey, Bz */
+          em_characteristic(&E3(em, ig, i2, 2), &E3(em, ig, i2, 4), -1.0, c, high);  /* -Ez, By */
+        }
+    }
+  }
+  if (y_periodic == 0) {
+    for (int high = 0; high < 2; ++high) {
+      if (!at[2 + high]) continue;
+      const int i2 = high ? ng + n2 - 1 : ng, d = high ? 1 : -1;
+      for (int i1 = ng; i1 < ng + n1; ++i1)
+        for (int i4 = 1; i4 <= ng; ++i4) {
+          const int ig = i2 + d * i4;
+          for (int k = 0; k < 6; ++k)
+            E3(em, i1, ig, k) = +3.0 * E3(em, i1, ig - d, k) - 3.0 * E3(em, i1, ig - 2 * d, k) + 1.0 * E3(em, i1, ig - 3 * d, k);
+          em_characteristic(&E3(em, i1, ig, 0), &E3(em, i1, ig, 5), -1.0, c, high);  /* -Ex, Bz */
+          em_characteristic(&E3(em, i1, ig, 2), &E3(em, i1, ig, 3), 1.0, c, high);   /* Ez, Bx */
+        }
+    }
+  }
+}
+/* maxwellsetvzbcs (MaxwellF.f:661-731): even reflection about the boundary cell, x edges over the whole y extent of the
+ * data box first, then y edges over the whole x extent */
+void ok_maxwell_set_vz_bcs(double* vz, int n1, int n2, int order, const int* at, int x_periodic, int y_periodic) {
+  const int ng = (order == 4) ? 2 : 3;
+  const int64_t n1d = n1 + 2 * ng, n2d = n2 + 2 * ng;
+  if (x_periodic == 0) {
+    if (at[0])
+      for (int i2 = 0; i2 < n2d; ++i2)
+        for (int i3 = 1; i3 <= ng; ++i3) E3(vz, ng - i3, i2, 0) = E3(vz, ng + i3, i2, 0);
+    if (at[1])
+      for (int i2 = 0; i2 < n2d; ++i2)
+        for (int i3 = 1; i3 <= ng; ++i3) E3(vz, ng + n1 - 1 + i3, i2, 0) = E3(vz, ng + n1 - 1 - i3, i2, 0);
+  }
+  if (y_periodic == 0) {
+    if (at[2])
+      for (int i1 = 0; i1 < n1d; ++i1)
+        for (int i3 = 1; i3 <= ng; ++i3) E3(vz, i1, ng - i3, 0) = E3(vz, i1, ng + i3, 0);
+    if (at[3])
+      for (int i1 = 0; i1 < n1d; ++i1)
+        for (int i3 = 1; i3 <= ng; ++i3) E3(vz, i1, ng + n2 - 1 + i3, 0) = E3(vz, i1, ng + n2 - 1 - i3, 0);
+  }
+}
+#undef E3

@@ -265,6 +265,27 @@ def field_cases(B, order):
     B.call("xpby2d_", B.arr(x), B.arr(out["maxwell_av"]), B.d(0.01), *db, *ib, B.i(6))
     B.finish()
     out["xpby2d"] = x
+    # the boundary routines a non-periodic Vlasov-Maxwell run reaches (MaxwellF.f:10-58, 359-389, 473-731): the box in the
+    # low-x / high-y corner of a 2 x 2 decomposition and in the other corner, every periodicity
+    nx, ny = 2 * n1, 2 * n2
+    for tag, (l1, l2) in (("lo_hi", (0, n2)), ("hi_lo", (n1, 0))):
+        dbb = [B.i(l1 - ng), B.i(l1 + n1 - 1 + ng), B.i(l2 - ng), B.i(l2 + n2 - 1 + ng)]
+        ibb = [B.i(l1), B.i(l1 + n1 - 1), B.i(l2), B.i(l2 + n2 - 1)]
+        for xper, yper in ((0, 0), (1, 0), (0, 1)):
+            e = np.ascontiguousarray(rng.uniform(-1, 1, size=(6, n2d, n1d)))
+            B.call("maxwellsetembcs_", *dbb, *ibb, B.arr(e), B.i(nx), B.i(ny), B.i(xper), B.i(yper), B.i(order), B.d(22.36))
+            v = np.ascontiguousarray(rng.uniform(-1, 1, size=(n2d, n1d)))
+            B.call("maxwellsetvzbcs_", *dbb, *ibb, B.arr(v), B.i(nx), B.i(ny), B.i(xper), B.i(yper), B.i(order))
+            B.finish()
+            out["embcs_%s_%d%d" % (tag, xper, yper)], out["vzbcs_%s_%d%d" % (tag, xper, yper)] = e, v
+    z = np.ascontiguousarray(rng.uniform(-1, 1, size=(6, n2d, n1d)))
+    B.call("zeroghost2d_", B.arr(z), *ib, *db, B.i(6))
+    src = np.ascontiguousarray(rng.uniform(-1, 1, size=(6, n2d, n1d)))
+    dem = np.ascontiguousarray(rng.uniform(-1, 1, size=(6, n2d, n1d)))
+    z4 = np.zeros(4)
+    B.call("maxwelladdantennasource_", *db, *ib, B.meta(z4), B.meta(z4), B.meta(z4), B.arr(src), B.arr(dem))
+    B.finish()
+    out["zeroghost"], out["antenna"] = z, dem
     return out
 
 

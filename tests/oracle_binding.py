@@ -124,6 +124,10 @@ def load():
     L.ok_xpby2d.argtypes = [dp, dp, d, i, i, i, i]
     L.ok_maxwell_eval_rhs.argtypes = [dp, dp, dp, dp, dp, i, i, i, i, dp, d, d, d]
     L.ok_maxwell_eval_vz_rhs.argtypes = [dp, dp, d, i, i, i]
+    L.ok_zero_ghost_2d.argtypes = [dp, i, i, i, i]
+    L.ok_maxwell_add_antenna_source.argtypes = [dp, dp, i, i, i]
+    L.ok_maxwell_set_em_bcs.argtypes = [dp, i, i, i, C.c_void_p, i, i, d]
+    L.ok_maxwell_set_vz_bcs.argtypes = [dp, i, i, i, C.c_void_p, i, i]
     L.ok_vm_work_create.restype = vp
     L.ok_vm_work_create.argtypes = [i, C.POINTER(OkSpecies), C.POINTER(d * 2), C.POINTER(d * 2), d, d, d]
     L.ok_vm_work_destroy.argtypes = [vp]

@@ -370,3 +370,48 @@ def test_pin_trig_tz_source(ok, ref, n, order, lo):
         R.L.computetrigtzsourceerror_(R._p(e2), R._p(s.f), *db, R._p(xlo), R._p(xhi), R._p(dx), R._d(time), R._p(s.velocities),
                                       R._p(np.array([amp])))
         assert np.array_equal(e1, e2)
+
+
+@needs_ref
+@pytest.mark.parametrize("order", [4, 6])
+def test_pin_maxwell_boundary_routines(ok, ref, order):
+    """zeroghost2d, maxwelladdantennasource, maxwellsetembcs, maxwellsetvzbcs (MaxwellF.f:10-58, 359-389, 473-731): a
+    box in every position of a 3 x 3 decomposition (touching no, one or two physical boundaries), every periodicity"""
+    R = ref
+    ng = 2 if order == 4 else 3
+    n1, n2 = 9, 7
+    n1d, n2d = n1 + 2 * ng, n2 + 2 * ng
+    rng = np.random.default_rng(60 + order)
+    nx, ny = 3 * n1, 3 * n2
+    for bx in range(3):
+        for by in range(3):
+            lo1, lo2 = bx * n1, by * n2
+            db = [R._i(lo1 - ng), R._i(lo1 + n1 - 1 + ng), R._i(lo2 - ng), R._i(lo2 + n2 - 1 + ng)]
+            ib = [R._i(lo1), R._i(lo1 + n1 - 1), R._i(lo2), R._i(lo2 + n2 - 1)]
+            at = (C.c_int * 4)(int(lo1 == 0), int(lo1 + n1 == nx), int(lo2 == 0), int(lo2 + n2 == ny))
+            for xper, yper in ((0, 0), (1, 0), (0, 1), (1, 1)):
+                em = rng.uniform(-1, 1, size=(6, n2d, n1d))
+                e1, e2 = em.copy(), em.copy()
+                ok.ok_maxwell_set_em_bcs(e1.ravel(), n1, n2, order, at, xper, yper, 22.36)
+                R.L.maxwellsetembcs_(*db, *ib, R._p(e2), R._i(nx), R._i(ny), R._i(xper), R._i(yper), R._i(order), R._d(22.36))
+                assert np.array_equal(e1, e2)
+                touched = (not xper and (at[0] or at[1])) or (not yper and (at[2] or at[3]))
+                assert np.array_equal(e1, em) != bool(touched)
+                vz = rng.uniform(-1, 1, size=(n2d, n1d))
+                v1, v2 = vz.copy(), vz.copy()
+                ok.ok_maxwell_set_vz_bcs(v1.ravel(), n1, n2, order, at, xper, yper)
+                R.L.maxwellsetvzbcs_(*db, *ib, R._p(v2), R._i(nx), R._i(ny), R._i(xper), R._i(yper), R._i(order))
+                assert np.array_equal(v1, v2)
+    db = [R._i(-ng), R._i(n1 - 1 + ng), R._i(-ng), R._i(n2 - 1 + ng)]
+    ib = [R._i(0), R._i(n1 - 1), R._i(0), R._i(n2 - 1)]
+    u = rng.uniform(-1, 1, size=(6, n2d, n1d))
+    u1, u2 = u.copy(), u.copy()
+    ok.ok_zero_ghost_2d(u1.ravel(), n1, n2, ng, 6)
+    R.L.zeroghost2d_(R._p(u2), *ib, *db, R._i(6))
+    assert np.array_equal(u1, u2) and np.array_equal(u1[:, ng:-ng, ng:-ng], u[:, ng:-ng, ng:-ng]) and u1[0, 0, 0] == 0.0
+    src = rng.uniform(-1, 1, size=(6, n2d, n1d))
+    d1, d2 = u.copy(), u.copy()
+    z4 = np.zeros(4)
+    ok.ok_maxwell_add_antenna_source(d1.ravel(), src.ravel(), n1, n2, ng)
+    R.L.maxwelladdantennasource_(*db, *ib, R._p(z4), R._p(z4), R._p(z4), R._p(src), R._p(d2))
+    assert np.array_equal(d1, d2) and not np.array_equal(d1, u)
