@@ -323,6 +323,20 @@ def poisson_plot_names(plot_ke_vel_bdy_flux, species_names):
     return names
 
 
+def maxwell_plot_names(plot_ke_vel_bdy_flux, species_names):
+    """Maxwell::buildPlotNames (Maxwell.C:1124-1157): the six fields, then per species its transverse drift velocity"""
+    names = ["EX", "EY", "EZ", "BX", "BY", "BZ"]
+    for sp in species_names:
+        names.append("%s VZ" % sp)
+        if plot_ke_vel_bdy_flux:
+            names += ["%s ke flux %s" % (sp, k) for k in ("vx lo", "vx hi", "vy lo", "vy hi")]
+    return names
+
+
+MAXWELL_FIELD_HISTORIES = ["E_max", "norm E", "Ex_max", "Ey_max", "Ez_max", "E_tot", "B_max", "norm B", "Bx_max", "By_max",
+                           "Bz_max", "B_tot"]                     # Maxwell::buildTimeHistoryNames (Maxwell.C:976-987)
+
+
 def write_time_histories(file_name_base, saved_save, names, sequences, time_seq, saved_seq, num_probes,
                          num_tracking_particles=0):
     """EMSolverBase::writeTimeHistories (EMSolverBase.C:510-537): <base>_<saved_save>.hdf holding the first saved_seq
@@ -430,6 +444,41 @@ def write_vp_restart(write_dir, index, species, n_ghosts, time, dt, cfl, tf, bz_
     return name
 
 
+def write_vm_restart(write_dir, index, species, n_ghosts, em_vars, vz, field_info, time, dt, cfl, tf, bz_const=0.0,
+                     plot_ke_vel_bdy_flux=False, max_files=16):
+    """RestartManager::write for a Vlasov-Maxwell run on one process: VMSystem (VMSystem.C:757-785), each KineticSpecies,
+    Maxwell (Maxwell.C:942-964: nGhost, isMaxwell = 1, group "Maxwell" with EMVars (6, n2d, n1d) and vz<k> (n2d, n1d)),
+    Simulation.  field_info = (distribInfo of EMVars, distribInfo of a vz array)."""
+    name = os.path.join(write_dir, "dist_%d.hdf" % index)
+    w = RestartWriter(name, max_files, 1)
+    w.write_integer_value("species_list_size", len(species))
+    w.write_double_value("bz_const", bz_const)
+    w.write_integer_value("plot_ke_vel_bdy_flux", int(plot_ke_vel_bdy_flux))
+    w.push_sub_dir("species_list")
+    for s, item in enumerate(species):
+        w.write_string("species.%d" % (s + 1), item["sp"]["name"])
+    w.pop_sub_dir()
+    for s, item in enumerate(species):
+        put_species(w, s, item["sp"], item["domain"], item["tiles"], item["info"], item.get("integrated_e_dot_j"),
+                    item.get("krook"))
+    w.write_integer_value("nGhost", n_ghosts)
+    w.write_integer_value("isMaxwell", 1)
+    w.push_sub_dir("Maxwell")
+    w.write_parallel_array("EMVars", {0: em_vars}, field_info[0])
+    for k, v in enumerate(vz):
+        w.write_parallel_array("vz%d" % k, {0: v}, field_info[1])
+    w.pop_sub_dir()
+    w.write_integer_value("generating processes", 1)
+    for key, v in zip(("major version", "minor version", "patch level"), LOKI_VERSION):
+        w.write_integer_value(key, v)
+    w.write_double_value("time", time)
+    w.write_double_value("time step", dt)
+    w.write_double_value("CFL", cfl)
+    w.write_double_value("tf", tf)
+    w.close()
+    return name
+
+
 def read_vp_restart(name, max_files=16):
     """the inverse of write_vp_restart for a one-process dump: time, dt and per species the distribution (dataBox) and
     the integrated driver work (VPSystem / KineticSpecies / Simulation::getFromRestart)"""
@@ -452,4 +501,9 @@ def read_vp_restart(name, max_files=16):
             item["integrated_e_dot_j"] = None
         r.pop_sub_dir()
         out["species"].append(item)
+    if r.read_integer_value("isMaxwell"):
+        r.push_sub_dir("Maxwell")
+        out["em_vars"] = r.read_parallel_array("EMVars", 0)[1]
+        out["vz"] = [r.read_parallel_array("vz%d" % k, 0)[1] for k in range(n)]
+        r.pop_sub_dir()
     return out

@@ -161,7 +161,9 @@ class Runner:
         """one column of VPSystem::accumulateSequences (VPSystem.C:591-636) in Poisson::buildTimeHistoryNames order:
         5 field histories, (Ex, Ey) per probe, then 16 per species"""
         if self.vm:
-            raise NotImplementedError("time-history files of the Vlasov-Maxwell system")
+            # the histories the device computes today: Maxwell's twelve field histories and computekemaxwell's five per
+            # species (VMSystem::accumulateSequences; probes, flux and driver histories of the Maxwell system are not built)
+            return list(self.history())
         ns = len(self.deck.species)
         h = self.history()
         pr = self.probes().reshape(-1)
@@ -177,24 +179,35 @@ class Runner:
         """(2, n2d, n1d): Ex, Ey of the last field solve with their ghost layers (EMSolverBase::plotCommon's m_em_vars)"""
         d = self.deck
         n1d, n2d = d.n[0] + 2 * d.ng, d.n[1] + 2 * d.ng
+        if self.vm:
+            out = np.empty((6, n2d, n1d))                      # Ex, Ey, Ez, Bx, By, Bz of the state
+            capi.check(self.H.lk_vm_get_fields(self.sys, out.ctypes.data), "lk_vm_get_fields")
+            return out
         out = np.empty((2, n2d, n1d))
         capi.check(self.L.lk_sync(None), "lk_sync")
         capi.check(self.L.lk_memcpy_d2h(out.ctypes.data, self.H.lk_vp_em_vars_ptr(self.sys), out.nbytes), "lk_memcpy_d2h")
+        return out
+
+    def vz(self, s):
+        d = self.deck
+        out = np.empty((d.n[1] + 2 * d.ng, d.n[0] + 2 * d.ng))
+        capi.check(self.H.lk_vm_get_vz(self.sys, s, out.ctypes.data), "lk_vm_get_vz")
         return out
 
     def open_outputs(self, write_dir, restart_time_interval=None, restart_step_interval=None, max_files=16,
                      restart_index=0):
         """what Simulation's constructor sets up (Simulation.C:262-290): the sequences, the field writer, the restart
         cadence; then the time-0 history, plot and dump"""
-        if self.vm:
-            raise NotImplementedError("output files of the Vlasov-Maxwell system")
         d = self.deck
         # after a restore the next dump is due at once (RestartManager::resetNextWriteTime, Simulation.C:251-254)
         self.out = dict(dir=write_dir, saved_seq=0, saved_save=0, time_seq=[], restart_index=restart_index,
                         max_files=max_files, t_int=restart_time_interval, s_int=restart_step_interval,
                         next_write=self.time, dt=0.0)
         names = [sp.name for sp in d.species]
-        self.out["names"] = outputs.poisson_time_history_names(len(d.probes), 0, names)
+        if self.vm:
+            self.out["names"] = outputs.MAXWELL_FIELD_HISTORIES + [n + "_" + k for n in names for k in ("ke", "ke_x", "ke_y", "px", "py")]
+        else:
+            self.out["names"] = outputs.poisson_time_history_names(len(d.probes), 0, names)
         self.out["seq"] = [[] for _ in self.out["names"]]
         self.out["fields"] = outputs.FieldWriter(write_dir, (d.xlim[0], d.xlim[2]), d.dx, d.n, d.order, 1)
         self.accumulate_sequences()
@@ -213,11 +226,13 @@ class Runner:
         o, d = self.out, self.deck
         fw = o["fields"]
         npr = len(d.probes)
-        fw.start_time_slice(self.time, o["dt"], outputs.poisson_plot_names(False, []), 0, npr,
-                            ([p[0] for p in d.probes], [p[1] for p in d.probes]), d.n)
+        plot_names = (outputs.maxwell_plot_names(False, [sp.name for sp in d.species]) if self.vm else
+                      outputs.poisson_plot_names(False, []))
+        fw.start_time_slice(self.time, o["dt"], plot_names, 0, npr, ([p[0] for p in d.probes], [p[1] for p in d.probes]), d.n)
         em = self.em_vars()
-        for k, name in enumerate(("EX", "EY")):
-            fw.write_field(name, em[k], (-d.ng, -d.ng), (-d.ng, -d.ng), (d.n[0] + 2 * d.ng, d.n[1] + 2 * d.ng), d.ng)
+        planes = list(em) + ([self.vz(s) for s in range(len(d.species))] if self.vm else [])
+        for name, plane in zip(plot_names, planes):
+            fw.write_field(name, plane, (-d.ng, -d.ng), (-d.ng, -d.ng), (d.n[0] + 2 * d.ng, d.n[1] + 2 * d.ng), d.ng)
         fw.end_time_slice()
         outputs.write_time_histories(o["dir"] + ".time_hists", o["saved_save"], o["names"], o["seq"], o["time_seq"],
                                      o["saved_seq"], npr, 0)
@@ -235,7 +250,8 @@ class Runner:
         else:
             return None
         # m_system->updateGhosts(): the dump holds the ghost cells the next step would start from
-        capi.check(self.H.lk_vp_update_ghosts(self.sys), "lk_vp_update_ghosts")
+        if not self.vm:
+            capi.check(self.H.lk_vp_update_ghosts(self.sys), "lk_vp_update_ghosts")
         items = []
         for s, sp in enumerate(d.species):
             f = self.state(s)
@@ -250,14 +266,21 @@ class Runner:
             item = dict(sp=dict(name=sp.name, mass=sp.mass, charge=sp.charge, bz_const=getattr(sp, "bz", 0.0)),
                         domain=(ncell, x_lo, x_hi, dx, d.periodic), tiles={0: f},
                         info=outputs.distrib_info(0, 0, d.ng, ncell, [1, 1, 1, 1]))
-            if sp.driver:
+            if sp.driver and not self.vm:
                 v = C.c_double()
                 capi.check(self.H.lk_vp_ke_e_dot(self.sys, s, C.byref(v)), "lk_vp_ke_e_dot")
                 item["integrated_e_dot_j"] = {0: v.value}
                 item["sp"]["driver_state"] = (0, float(getattr(sp, "driver_phase", 0.0)), 0.0)
             items.append(item)
-        name = outputs.write_vp_restart(o["dir"], o["restart_index"], items, d.ng, self.time, o["dt"], d.cfl,
-                                        d.run["final_time"], max_files=o["max_files"])
+        if self.vm:
+            n2 = [d.n[0], d.n[1]]
+            info = (outputs.distrib_info(0, 0, d.ng, n2 + [6], [1, 1, 1]), outputs.distrib_info(0, 0, d.ng, n2, [1, 1]))
+            name = outputs.write_vm_restart(o["dir"], o["restart_index"], items, d.ng, self.em_vars(),
+                                            [self.vz(s) for s in range(len(d.species))], info, self.time, o["dt"], d.cfl,
+                                            d.run["final_time"], max_files=o["max_files"])
+        else:
+            name = outputs.write_vp_restart(o["dir"], o["restart_index"], items, d.ng, self.time, o["dt"], d.cfl,
+                                            d.run["final_time"], max_files=o["max_files"])
         o["restart_index"] += 1
         if o["t_int"] is not None:
             o["next_write"] += o["t_int"]
@@ -278,15 +301,23 @@ class Runner:
             f = np.ascontiguousarray(item["distribution"], dtype=np.float64)
             if f.shape != tuple(self.shapes[s]):
                 raise ValueError("dump of %s has extents %s, the deck %s" % (item["name"], f.shape, self.shapes[s]))
+            if self.vm:
+                capi.check(self.H.lk_vm_set_state(self.sys, s, f.ctypes.data), "lk_vm_set_state")
+                vz = np.ascontiguousarray(dump["vz"][s], dtype=np.float64)
+                capi.check(self.H.lk_vm_set_vz(self.sys, s, vz.ctypes.data), "lk_vm_set_vz")
+                continue
             capi.check(self.H.lk_vp_set_state(self.sys, s, f.ctypes.data), "lk_vp_set_state")
             if item["integrated_e_dot_j"] is not None:
                 capi.check(self.H.lk_vp_set_ke_e_dot(self.sys, s, item["integrated_e_dot_j"]), "lk_vp_set_ke_e_dot")
+        if self.vm:
+            em = np.ascontiguousarray(dump["em_vars"], dtype=np.float64)
+            capi.check(self.H.lk_vm_set_fields(self.sys, em.ctypes.data), "lk_vm_set_fields")
         self.time = dump["time"]
         run = self.deck.run
         # Simulation's constructor after a restore (Simulation.C:246-260): the counters follow from the time
         self.last_save = int(self.time / run["save_times"])
         self.last_seq = int(self.time / run.get("sequence_write_times", 1.0))
-        capi.check(self.H.lk_vp_set_time(self.sys, self.time), "set_time")
+        capi.check((self.H.lk_vm_set_time if self.vm else self.H.lk_vp_set_time)(self.sys, self.time), "set_time")
         self._seed()
         return idx
 

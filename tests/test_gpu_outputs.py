@@ -150,3 +150,48 @@ def test_resumed_run_continues_bit_for_bit(lk, tmp_path, mode):
         second.close()
     finally:
         lk.lk_set_strict(old)
+
+
+def test_vlasov_maxwell_dump_and_resume(lk, strict, tmp_path):
+    """emDamping physics on a small grid: field files carry the six fields and the species' vz, the dump carries group
+    "Maxwell" (EMVars, vz0) with isMaxwell = 1 (Maxwell.C:942-964), and a system restored from it continues bit for bit"""
+    from loki_b200 import decks as pdecks
+
+    def mk(final_time):
+        deck = pdecks.em_damping(n=(16, 5), nv=(16, 12))
+        deck.run = dict(final_time=final_time, save_times=0.05, sequence_write_times=0.05, max_step=100, restart={})
+        return run.Runner(deck), deck
+
+    whole, _ = mk(0.1)
+    while not whole.done():
+        whole.advance()
+    want_f, want_em, want_vz, t_want = whole.state(0), whole.em_vars(), whole.vz(0), whole.time
+    whole.close()
+
+    base = str(tmp_path / "emDamping")
+    first, deck = mk(0.05)
+    first.open_outputs(base, 0.05)
+    while not first.done():
+        first.advance()
+    first.write_checkpoint_file()
+    em_mid = first.em_vars()
+    first.close()
+    f1 = h5lite.read(base + ".fields_1.hdf")["root"]
+    assert sorted(n for n in f1.names() if n.startswith("time_slice_1_")) == sorted(
+        "time_slice_1_" + n for n in ["EX", "EY", "EZ", "BX", "BY", "BZ", "electron VZ", "time", "dt"])
+    assert np.array_equal(f1["time_slice_1_EY"].data, em_mid[1]) and np.array_equal(f1["time_slice_1_BZ"].data, em_mid[5])
+    hist = h5lite.read(base + ".time_hists_1.hdf")["root"]
+    assert hist["E_max"].data.shape == (2,) and hist["electron_ke"].data[1] > 0 and hist["Bz_max"].data[0] > 0
+    meta = h5lite.read(os.path.join(base, "dist_1.hdf"))["root"]
+    assert int(meta["isMaxwell"].data) == 1 and meta["Maxwell"]["EMVars"]["distribInfo"].data.tolist()[:5] == [0, 0, -2, -2, -2]
+    bulk = h5lite.read(os.path.join(base, "dist_1.hdf.g0"))["root"]
+    assert bulk["Maxwell\\EMVars.p0"].data.shape == (6, 5 + 4, 16 + 4) and bulk["Maxwell\\vz0.p0"].data.shape == (9, 20)
+
+    second, _ = mk(0.1)
+    assert second.restore(base) == 1 and abs(second.time - 0.05) < 1e-12
+    while not second.done():
+        second.advance()
+    assert second.time == t_want
+    assert np.array_equal(second.state(0), want_f)
+    assert np.array_equal(second.em_vars(), want_em) and np.array_equal(second.vz(0), want_vz)
+    second.close()
