@@ -195,3 +195,40 @@ def test_vlasov_maxwell_dump_and_resume(lk, strict, tmp_path):
     assert np.array_equal(second.state(0), want_f)
     assert np.array_equal(second.em_vars(), want_em) and np.array_equal(second.vz(0), want_vz)
     second.close()
+
+
+def test_regression_chain_run_post_process_check(lk, tmp_path):
+    """the reference's regression chain (test/*/Makefile.in): run -> vp4DPostProcess -> checkTests, here with the strict
+    run as the baseline of the production run, under tolerance files in the reference's format"""
+    from loki_b200 import post
+    prefixes = {}
+    for mode in ("strict", "fast"):
+        old = lk.lk_set_strict(1 if mode == "strict" else 0)
+        try:
+            d = tmp_path / mode
+            d.mkdir()
+            r, deck = _runner(d)
+            base = str(d / "two_species")
+            r.open_outputs(base, 0.2)
+            while not r.done():
+                r.advance()
+            r.write_checkpoint_file()
+            r.close()
+            meta = post.post_process(base)
+            assert meta["species"] == ["electron", "ion"] and meta["nxy"] == tuple(deck.n)
+            prefixes[mode] = base
+        finally:
+            lk.lk_set_strict(old)
+    ts = h5lite.read(prefixes["fast"] + "_timeSeries.hdf")["root"]
+    assert ts["series_time"].data.shape == (5,) and ts["electron_ke"].data.shape == (5,)
+    fl = h5lite.read(prefixes["fast"] + "_fields.hdf")["root"]
+    assert fl["EX"].data.shape == (5, 6, 12)
+    (tmp_path / "dist_tol").write_text("electron\n1.0e-10\nion\n1.0e-10\n")
+    (tmp_path / "tstol").write_text("E_max\n1.0e-10\nfield_energy\n1.0e-10\nelectron_ke\n1.0e-10\nion_ke\n1.0e-10\n"
+                                    "electron_integrated_ke_e_dot\n1.0e-10\nelectron_driver_time_envel\n1.0e-10\n")
+    (tmp_path / "field_tol").write_text("EX\n1.0e-8\n")
+    args = (prefixes["fast"], prefixes["strict"], 2, str(tmp_path / "dist_tol"), str(tmp_path / "tstol"), str(tmp_path / "field_tol"))
+    assert post.check_tests(*args) == []
+    (tmp_path / "dist_tol").write_text("electron\n1.0e-20\nion\n1.0e-10\n")
+    fails = post.check_tests(*args)
+    assert len(fails) == 1 and "species electron" in fails[0]
