@@ -201,13 +201,14 @@ int lk_vp_driver_history(lk_vp_system* sys, int s, double time, double* ke_e_dot
 
 /* ---------------------------------------------------------------------------------------------
  * Vlasov-Maxwell: the host mirror of VMSystem / VMState / Maxwell (VMSystem.C:407-581, Maxwell.C:299-353,
- * 562-623, Maxwell.H:199-204, 371-381) driven by RK4Integrator (RK4Integrator.H:66-171).  The RK state is
+ * 562-623, Maxwell.H:199-204, 371-381) driven by RK4Integrator (RK4Integrator.H:66-171) or RK6Integrator
+ * (RK6Integrator.H:69-133).  The RK state is
  * the distribution functions plus em_vars (n1d,n2d,6: Ex,Ey,Ez,Bx,By,Bz) and one transverse drift
  * velocity vz (n1d,n2d) per species; x and y periodic; no E-field drivers, antennae or particles.
  * Runs on one GPU (base.ntiles must be 1 and the tile must be the whole configuration space).
  * --------------------------------------------------------------------------------------------- */
 typedef struct lk_vm_desc {
-  lk_vp_desc base;      /* rk_order must be 4 */
+  lk_vp_desc base;      /* rk_order 4 (RK4Integrator) or 6 (RK6Integrator) */
   double light_speed;   /* Simulation::s_LIGHT_SPEED */
   double av_weak, av_strong; /* maxwell.avWeak / avStrong (MaxwellF.f:298-352) */
 } lk_vm_desc;

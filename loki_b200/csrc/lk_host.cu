@@ -383,6 +383,23 @@ struct KineticSpecies {
   }
 };
 
+// RK6Integrator's tableau (RK6Integrator.H:77-103), shared by the Vlasov-Poisson and Vlasov-Maxwell stage loops
+namespace rk6tab {
+static const double A[8][8] = {
+    {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {1.0 / 9.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {1.0 / 24.0, 1.0 / 8.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {1.0 / 6.0, -1.0 / 2.0, 2.0 / 3.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {935.0 / 2536.0, -2781.0 / 2536.0, 309.0 / 317.0, 321.0 / 1268.0, 0.0, 0.0, 0.0, 0.0},
+    {-12710.0 / 951.0, 8287.0 / 317.0, -40.0 / 317.0, -6335.0 / 317.0, 8.0, 0.0, 0.0, 0.0},
+    {5840285.0 / 3104064.0, -7019.0 / 2536.0, -52213.0 / 86224.0, 1278709.0 / 517344.0, -433.0 / 2448.0,
+     33.0 / 1088.0, 0.0, 0.0},
+    {-5101675.0 / 1767592.0, 112077.0 / 25994.0, 334875.0 / 441898.0, -973617.0 / 883796.0, -1421.0 / 1394.0,
+     333.0 / 5576.0, 36.0 / 41.0, 0.0}};
+static const double b[8] = {41.0 / 840.0, 0.0, 9.0 / 35.0, 9.0 / 280.0, 34.0 / 105.0, 9.0 / 280.0, 9.0 / 35.0, 41 / 840.0};
+static const double c[8] = {0.0, 1.0 / 9.0, 1.0 / 6.0, 1.0 / 3.0, 1.0 / 2.0, 2.0 / 3.0, 5.0 / 6.0, 1.0};
+}  // namespace rk6tab
+
 // ---------------------------------------------------------------------------------------------
 // VPSystem (+ VPState, Poisson, the RK integrators): one rank
 // ---------------------------------------------------------------------------------------------
@@ -577,19 +594,9 @@ struct VPSystem {
     }
     const bool rk4 = desc.rk_order == 4;
     const int last = nstages() - 1;
-    static const double A6[8][8] = {
-        {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
-        {1.0 / 9.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
-        {1.0 / 24.0, 1.0 / 8.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
-        {1.0 / 6.0, -1.0 / 2.0, 2.0 / 3.0, 0.0, 0.0, 0.0, 0.0, 0.0},
-        {935.0 / 2536.0, -2781.0 / 2536.0, 309.0 / 317.0, 321.0 / 1268.0, 0.0, 0.0, 0.0, 0.0},
-        {-12710.0 / 951.0, 8287.0 / 317.0, -40.0 / 317.0, -6335.0 / 317.0, 8.0, 0.0, 0.0, 0.0},
-        {5840285.0 / 3104064.0, -7019.0 / 2536.0, -52213.0 / 86224.0, 1278709.0 / 517344.0, -433.0 / 2448.0,
-         33.0 / 1088.0, 0.0, 0.0},
-        {-5101675.0 / 1767592.0, 112077.0 / 25994.0, 334875.0 / 441898.0, -973617.0 / 883796.0, -1421.0 / 1394.0,
-         333.0 / 5576.0, 36.0 / 41.0, 0.0}};
-    static const double b6[8] = {41.0 / 840.0, 0.0, 9.0 / 35.0, 9.0 / 280.0, 34.0 / 105.0, 9.0 / 280.0, 9.0 / 35.0, 41 / 840.0};
-    static const double c6[8] = {0.0, 1.0 / 9.0, 1.0 / 6.0, 1.0 / 3.0, 1.0 / 2.0, 2.0 / 3.0, 5.0 / 6.0, 1.0};
+    const auto& A6 = rk6tab::A;
+    const double* b6 = rk6tab::b;
+    const double* c6 = rk6tab::c;
     // stage time (RK4Integrator.H:84-120, RK6Integrator.H:109-121)
     double t_stage;
     if (rk4) {
@@ -850,6 +857,9 @@ struct VMSystem {
   // Maxwell state: em_vars (n1d,n2d,6) and vz per species; [0] = state/old, [1] = new (predictor)
   DevBuf<double> em[2], em_rhs, em_delta, Jx, Jy, Jz, sumf;
   std::vector<DevBuf<double>*> vz[2], vz_rhs, vz_delta;
+  // RK6Integrator's m_k[8] of the Maxwell part of the state (RK6Integrator.H:135-150); species keep theirs in karr
+  DevBuf<double> em_k[8];
+  std::vector<DevBuf<double>*> vz_k[8];
   int i_state = 0;
   double time = 0.0, dt = 0.0;
   bool lambda_stale = true;
@@ -859,6 +869,7 @@ struct VMSystem {
     for (int k = 0; k < 2; ++k) for (auto* b : vz[k]) delete b;
     for (auto* b : vz_rhs) delete b;
     for (auto* b : vz_delta) delete b;
+    for (int k = 0; k < 8; ++k) for (auto* b : vz_k[k]) delete b;
   }
   double* emState() { return em[i_state].p; }
   double* emNew() { return em[1 - i_state].p; }
@@ -871,7 +882,7 @@ struct VMSystem {
     sdesc.assign(b.species, b.species + b.nspecies);
     desc.base.species = sdesc.data();
     st = (cudaStream_t)stream;
-    if (!(b.order == 4 || b.order == 6) || b.rk_order != 4 || b.nspecies < 1) return LK_ERR_ARG;
+    if (!(b.order == 4 || b.order == 6) || !(b.rk_order == 4 || b.rk_order == 6) || b.nspecies < 1) return LK_ERR_ARG;
     if (b.ntiles != 1 || b.tile_lo[0] != 0 || b.tile_lo[1] != 0 || b.tile_n[0] != b.nglobal[0] || b.tile_n[1] != b.nglobal[1])
       return LK_ERR_UNSUPPORTED;  // the Maxwell path runs on one GPU
     ng = b.order == 4 ? 2 : 3;
@@ -886,6 +897,11 @@ struct VMSystem {
     }
     LKH_CHECK(em_rhs.alloc(pl * 6));
     LKH_CHECK(em_delta.alloc(pl * 6));
+    if (b.rk_order == 6)
+      for (int k = 0; k < 8; ++k) {
+        LKH_CHECK(em_k[k].alloc(pl * 6));
+        LKH_CUDA(cudaMemset(em_k[k].p, 0, sizeof(double) * pl * 6));
+      }
     LKH_CUDA(cudaMemset(em_rhs.p, 0, sizeof(double) * pl * 6));
     LKH_CUDA(cudaMemset(em_delta.p, 0, sizeof(double) * pl * 6));
     LKH_CHECK(Jx.alloc(pl)); LKH_CHECK(Jy.alloc(pl)); LKH_CHECK(Jz.alloc(pl)); LKH_CHECK(sumf.alloc(pl));
@@ -925,6 +941,14 @@ struct VMSystem {
         vz[k].push_back(new DevBuf<double>());
         LKH_CHECK(vz[k].back()->alloc(pl));
         LKH_CUDA(cudaMemset(vz[k].back()->p, 0, sizeof(double) * pl));
+      }
+      if (b.rk_order == 6) {
+        for (int k = 0; k < 8; ++k) {
+          LKH_CHECK(ks->karr[k].alloc(ks->vol));
+          vz_k[k].push_back(new DevBuf<double>());
+          LKH_CHECK(vz_k[k].back()->alloc(pl));
+          LKH_CUDA(cudaMemset(vz_k[k].back()->p, 0, sizeof(double) * pl));   // ghosts of a rhs stay zero
+        }
       }
       vz_rhs.push_back(new DevBuf<double>());
       vz_delta.push_back(new DevBuf<double>());
@@ -1048,10 +1072,68 @@ struct VMSystem {
     return LK_OK;
   }
 
+  // one RK6 stage (RK6Integrator.H:105-133) over the whole VMState: k[stg] = rhs(predictor), then the next predictor
+  // (or, after the last stage, the new state) = old + dt * sum_j coef_j k[j], added in the order j = 0 .. stg
+  int stage6(int stg) {
+    const int last = 7;
+    const double* coef = (stg == last) ? rk6tab::b : rk6tab::A[stg + 1];
+    double* em_eval = (stg == 0) ? emState() : emNew();
+    std::vector<double*> vz_eval(species.size()), rhs_vz(species.size());
+    std::vector<const double*> f_of(species.size());
+    for (size_t s = 0; s < species.size(); ++s) {
+      vz_eval[s] = (stg == 0) ? vzState((int)s) : vzNew((int)s);
+      rhs_vz[s] = vz_k[stg][s]->p;
+      f_of[s] = species[s]->f_eval;
+    }
+    LKH_CHECK(currentsOf(f_of.data(), em_eval, vz_eval.data(), true));
+    static const bool no_fuse = getenv("LK_NO_FUSED_MOMENTS") != nullptr;
+    const bool fused_moments = !lk_get_strict() && !no_fuse;
+    for (size_t s = 0; s < species.size(); ++s) {
+      KineticSpecies* ks = species[s];
+      LKH_CHECK(ks->periodicFill(ks->f_eval, 3, st));
+      lk_accel a = accelDesc(ks, em_eval, vz_eval[s]);
+      if (stg == last) LKH_CHECK(lk_max_accel(&ks->g, &a, ks->lam.p, st));
+      const int at[4] = {1, 1, 1, 1};
+      LKH_CHECK(lk_set_acceleration_bcs_4d(ks->f_eval, &ks->g, &a, &ks->inflow, at, st));
+      lk_rk_update u;
+      memset(&u, 0, sizeof(u));
+      double* pred = (ks->f_eval == ks->farr[ks->i_a].p) ? ks->farr[ks->i_b].p : ks->farr[ks->i_a].p;
+      u.f_old = ks->state();
+      u.pred = pred;
+      int np = 0;
+      for (int j = 0; j < stg; ++j) {
+        u.k_prev[np] = ks->karr[j].p;
+        u.c_prev[np] = dt * coef[j];
+        ++np;
+      }
+      u.n_prev = np;
+      u.c_pred = dt * coef[stg];
+      u.wrap = fused_moments ? ks->wrapFor(3) : 0;
+      LKH_CHECK(lk_vlasov_stage(ks->karr[stg].p, ks->f_eval, &ks->g, ks->velocities.p, &a, &u, fused_moments ? &ks->mom : nullptr, st));
+      ks->wrap_ptr = pred;
+      ks->wrap_bits = u.wrap;
+      ks->mom_valid = fused_moments;
+      ks->f_eval = pred;
+    }
+    LKH_CHECK(maxwellRHS(em_k[stg].p, rhs_vz.data(), em_eval));
+    LKH_CUDA(cudaMemcpyAsync(emNew(), emState(), sizeof(double) * pl * 6, cudaMemcpyDeviceToDevice, st));
+    for (int j = 0; j <= stg; ++j) LKH_CHECK(lk_xpby2d(emNew(), em_k[j].p, dt * coef[j], n1, n2, ng, 6, st));
+    for (size_t s = 0; s < species.size(); ++s) {
+      LKH_CUDA(cudaMemcpyAsync(vzNew((int)s), vzState((int)s), sizeof(double) * pl, cudaMemcpyDeviceToDevice, st));
+      for (int j = 0; j <= stg; ++j) LKH_CHECK(lk_xpby2d(vzNew((int)s), vz_k[j][s]->p, dt * coef[j], n1, n2, ng, 1, st));
+    }
+    lambda_stale = true;
+    return LK_OK;
+  }
+
   int advance(double a_dt) {
     dt = a_dt;
     for (auto* ks : species) ks->f_eval = ks->state();
-    for (int stg = 0; stg < 4; ++stg) LKH_CHECK(stage(stg));
+    if (desc.base.rk_order == 6) {
+      for (int stg = 0; stg < 8; ++stg) LKH_CHECK(stage6(stg));
+    } else {
+      for (int stg = 0; stg < 4; ++stg) LKH_CHECK(stage(stg));
+    }
     for (auto* ks : species) {
       int i_new = (ks->f_eval == ks->farr[ks->i_a].p) ? ks->i_a : ks->i_b;
       int i_other = (i_new == ks->i_a) ? ks->i_b : ks->i_a;
@@ -1632,7 +1714,7 @@ int lk_vm_stable_dt(lk_vm_system* h, double* dt) {
   int s = h->sys.refreshLambda();
   if (s != LK_OK) return s;
   double v = std::numeric_limits<double>::max();
-  for (auto* ks : h->sys.species) v = std::min(v, ks->computeDt(4));
+  for (auto* ks : h->sys.species) v = std::min(v, ks->computeDt(h->sys.desc.base.rk_order));
   const double dt_maxwell = 1.0 / (h->sys.desc.light_speed * (1.0 / h->sys.dxg[0] + 1.0 / h->sys.dxg[1]));  // Maxwell.H:199-204
   *dt = std::min(v, dt_maxwell);
   return LK_OK;

@@ -347,8 +347,8 @@ class VMDeck(Deck):
     """a Vlasov-Maxwell deck: Deck + light speed, Maxwell hyper-dissipation and the field initial conditions
     (SimpleEMIC / SimpleVELIC single waves)"""
 
-    def __init__(self, name, n, xlim, species, light_speed, av_weak, av_strong, em_ics, vel_ics, order=4, cfl=0.9):
-        Deck.__init__(self, name, n, xlim, species, order=order, rk=4, cfl=cfl)
+    def __init__(self, name, n, xlim, species, light_speed, av_weak, av_strong, em_ics, vel_ics, order=4, cfl=0.9, rk=4):
+        Deck.__init__(self, name, n, xlim, species, order=order, rk=rk, cfl=cfl)
         self.light_speed, self.av_weak, self.av_strong = light_speed, av_weak, av_strong
         self.em_ics, self.vel_ics = em_ics, vel_ics
 
@@ -383,7 +383,7 @@ class VMDeck(Deck):
         return d
 
 
-def em_damping(n=(32, 5), nv=(64, 64), order=4):
+def em_damping(n=(32, 5), nv=(64, 64), order=4, rk=4):
     """test/emDamping/emDamping.pp: one electron species, Vlasov-Maxwell, order 4 / RK4, cfl 0.8"""
     omega, clight = 3.16, 22.36
     klde = math.sqrt(omega ** 2 - 1) / clight
@@ -397,4 +397,4 @@ def em_damping(n=(32, 5), nv=(64, 64), order=4):
               dict(field="B", xamp=0.0, yamp=0.0, zamp=P(Bz), kx=P(klde), ky=0.0, phase=0.0)]
     vel_ics = [dict(amp=0.0, kx=0.0, ky=0.0, phase=0.0)]
     return VMDeck("emDamping", n, (P(xa), P(xb), -10.0, 10.0), [e], P(clight), 0.0, P(av_strong), em_ics, vel_ics, order=order,
-                  cfl=0.8)
+                  cfl=0.8, rk=rk)

@@ -259,13 +259,11 @@ def deck_from_params(params, name="deck"):
             vel_ics.append(dict(amp=_f(params, pre + "amp", 0.0), kx=_f(params, pre + "x_wave_number", 0.0),
                                 ky=_f(params, pre + "y_wave_number", 0.0), phase=_f(params, pre + "phase", 0.0)))
             k += 1
-        if rk != 4:
-            raise ValueError("the Vlasov-Maxwell host mirror integrates with RK4")
         if periodic != (True, True) or use_new_bcs or any(getattr(sp, "krook", None) or getattr(sp, "collision", None) for sp in species):
             raise ValueError("the Vlasov-Maxwell host mirror is periodic, with the standard boundary fill, no Krook layers "
                              "and no collision operators")
         deck = _d.VMDeck(name, n, xlim, species, _f(params, "light_speed"), _f(params, "maxwell.avWeak", 0.0),
-                         _f(params, "maxwell.avStrong", 0.0), em_ics, vel_ics, order=order, cfl=cfl)
+                         _f(params, "maxwell.avStrong", 0.0), em_ics, vel_ics, order=order, cfl=cfl, rk=rk)
     else:
         deck = _d.Deck(name, n, xlim, species, order=order, rk=rk, cfl=cfl)
         deck.periodic, deck.use_new_bcs = periodic, use_new_bcs

@@ -231,6 +231,8 @@ void ok_vm_eval_rhs(ok_vm_work* w, double** rhs, double* rhs_em, double** rhs_vz
 const double* ok_vm_net_current(const ok_vm_work* w, int comp); /* net Jx/Jy/Jz of the last evalRHS */
 void ok_vm_rk4_step(ok_vm_work* w, double** f_new, double** f_old, double* em_new, double* em_old,
                     double** vz_new, double** vz_old, double time, double dt);
+void ok_vm_rk6_step(ok_vm_work* w, double** f_new, double** f_old, double* em_new, double* em_old,
+                    double** vz_new, double** vz_old, double time, double dt);
 void ok_vm_last_accel_max(const ok_vm_work* w, double* axmax, double* aymax);
 double ok_vm_stable_dt(const ok_vm_work* w, const double* axmax, const double* aymax, int rk_order);
 /* SimpleEMICF.f:10-47 (field = 1: E, 4: B) and SimpleVELICF.f:10-40, one wave, whole data box */

@@ -249,6 +249,70 @@ void ok_vm_rk4_step(ok_vm_work* w, double** f_new, double** f_old, double* em_ne
   free(ax); free(ay);
 }
 
+/* RK6Integrator::advance (RK6Integrator.H:69-133) over the whole VMState (distributions, em_vars, vz) */
+void ok_vm_rk6_step(ok_vm_work* w, double** f_new, double** f_old, double* em_new, double* em_old, double** vz_new,
+                    double** vz_old, double time, double dt) {
+  static const double A[8][8] =
+      {{0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+       {1.0/9.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+       {1.0/24.0, 1.0/8.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+       {1.0/6.0, -1.0/2.0, 2.0/3.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+       {935.0/2536.0, -2781.0/2536.0, 309.0/317.0, 321.0/1268.0, 0.0, 0.0, 0.0, 0.0},
+       {-12710.0/951.0, 8287.0/317.0, -40.0/317.0, -6335.0/317.0, 8.0, 0.0, 0.0, 0.0},
+       {5840285.0/3104064.0, -7019.0/2536.0, -52213.0/86224.0, 1278709.0/517344.0, -433.0/2448.0, 33.0/1088.0, 0.0, 0.0},
+       {-5101675.0/1767592.0, 112077.0/25994.0, 334875.0/441898.0, -973617.0/883796.0, -1421.0/1394.0, 333.0/5576.0, 36.0/41.0, 0.0}};
+  static const double b[8] = {41.0/840.0, 0.0, 9.0/35.0, 9.0/280.0, 34.0/105.0, 9.0/280.0, 9.0/35.0, 41/840.0};
+  static const double c[8] = {0.0, 1.0/9.0, 1.0/6.0, 1.0/3.0, 1.0/2.0, 2.0/3.0, 5.0/6.0, 1.0};
+  const ok_geom* g0 = &w->sp[0].g;
+  const int ng = g0->ng, n1 = g0->n[0], n2 = g0->n[1], ns = w->ns;
+  const int64_t pl = ok_nd(g0, 0) * ok_nd(g0, 1);
+  double* ax = (double*)calloc(ns, sizeof(double));
+  double* ay = (double*)calloc(ns, sizeof(double));
+  double** kf[8];
+  double** kvz[8];
+  double* kem[8];
+  for (int i = 0; i < 8; ++i) {
+    kf[i] = (double**)calloc(ns, sizeof(double*));
+    kvz[i] = (double**)calloc(ns, sizeof(double*));
+    kem[i] = (double*)calloc(pl * 6, sizeof(double));
+    for (int s = 0; s < ns; ++s) {
+      kf[i][s] = (double*)calloc(vol4(&w->sp[s].g), sizeof(double));
+      kvz[i][s] = (double*)calloc(pl, sizeof(double));
+    }
+  }
+  for (int i = 0; i < 8; ++i) {
+    /* the predictor of stage i: old + dt * sum_{j<i} a_ij k_j (stage 0: the old state itself) */
+    for (int s = 0; s < ns; ++s) {
+      const ok_geom* g = &w->sp[s].g;
+      memcpy(f_new[s], f_old[s], sizeof(double) * vol4(g));
+      memcpy(vz_new[s], vz_old[s], sizeof(double) * pl);
+      for (int j = 0; j < i; ++j) {
+        ok_xpby4d(f_new[s], kf[j][s], dt * A[i][j], g);
+        ok_xpby2d(vz_new[s], kvz[j][s], dt * A[i][j], n1, n2, ng, 1);
+      }
+    }
+    memcpy(em_new, em_old, sizeof(double) * pl * 6);
+    for (int j = 0; j < i; ++j) ok_xpby2d(em_new, kem[j], dt * A[i][j], n1, n2, ng, 6);
+    ok_vm_eval_rhs(w, kf[i], kem[i], kvz[i], f_new, em_new, vz_new, time + c[i] * dt, ax, ay);
+  }
+  for (int s = 0; s < ns; ++s) {
+    const ok_geom* g = &w->sp[s].g;
+    memcpy(f_new[s], f_old[s], sizeof(double) * vol4(g));
+    memcpy(vz_new[s], vz_old[s], sizeof(double) * pl);
+    for (int i = 0; i < 8; ++i) {
+      ok_xpby4d(f_new[s], kf[i][s], dt * b[i], g);
+      ok_xpby2d(vz_new[s], kvz[i][s], dt * b[i], n1, n2, ng, 1);
+    }
+  }
+  memcpy(em_new, em_old, sizeof(double) * pl * 6);
+  for (int i = 0; i < 8; ++i) ok_xpby2d(em_new, kem[i], dt * b[i], n1, n2, ng, 6);
+  for (int i = 0; i < 8; ++i) {
+    for (int s = 0; s < ns; ++s) { free(kf[i][s]); free(kvz[i][s]); }
+    free(kf[i]); free(kvz[i]); free(kem[i]);
+  }
+  free(ax); free(ay);
+}
+
 void ok_vm_last_accel_max(const ok_vm_work* w, double* axmax, double* aymax) {
   for (int s = 0; s < w->ns; ++s) { axmax[s] = w->last_ax[s]; aymax[s] = w->last_ay[s]; }
 }

@@ -135,6 +135,7 @@ def load():
     L.ok_vm_net_current.restype = C.POINTER(d)
     L.ok_vm_net_current.argtypes = [vp, i]
     L.ok_vm_rk4_step.argtypes = [vp, pvp, pvp, dp, dp, pvp, pvp, d, d]
+    L.ok_vm_rk6_step.argtypes = [vp, pvp, pvp, dp, dp, pvp, pvp, d, d]
     L.ok_vm_last_accel_max.argtypes = [vp, dp, dp]
     L.ok_vm_stable_dt.restype = d
     L.ok_vm_stable_dt.argtypes = [vp, dp, dp, i]

@@ -66,6 +66,11 @@ DECKS = [
     lambda: decks.em_damping(n=(32, 5), nv=(24, 24)),       # the deck's own configuration-space grid
     lambda: decks.em_damping(n=(10, 8), nv=(16, 10), order=6),
 ]
+# the sixth-order integrator over the whole VMState (RK6Integrator.H:69-133), with both spatial orders
+RK6_DECKS = [
+    lambda: decks.em_damping(n=(10, 8), nv=(16, 10), order=6, rk=6),
+    lambda: decks.em_damping(n=(12, 5), nv=(16, 12), order=4, rk=6),
+]
 
 
 @pytest.mark.parametrize("mk", DECKS)
@@ -120,9 +125,9 @@ def test_vm_eval_rhs_strict_matches_reference_order(lk, ok, strict, mk):
 
 
 @pytest.mark.parametrize("mode", ["strict", "production"])
-@pytest.mark.parametrize("mk", DECKS)
+@pytest.mark.parametrize("mk", DECKS + RK6_DECKS)
 def test_vm_one_step_matches_oracle(lk, ok, mk, mode):
-    """one RK4 step of the whole VMState.  Strict arithmetic: distribution, fields and vz bit-identical.
+    """one RK4 (or RK6) step of the whole VMState.  Strict arithmetic: distribution, fields and vz bit-identical.
     Production arithmetic (fused stage kernel, currents from its velocity moments): <= 1e-12 per cell on
     the distribution, 1e-12 relative on the fields."""
     deck = mk()
@@ -136,7 +141,8 @@ def test_vm_one_step_matches_oracle(lk, ok, mk, mode):
         f_new = [np.zeros_like(s) for s in states]
         em_old, em_new = em.copy(), np.zeros_like(em)
         vz_old, vz_new = [v.copy() for v in vz], [np.zeros_like(v) for v in vz]
-        ok.ok_vm_rk4_step(w, _ptrs(f_new), _ptrs(f_old), em_new, em_old, _ptrs(vz_new), _ptrs(vz_old), t0, dt)
+        step = ok.ok_vm_rk6_step if deck.rk == 6 else ok.ok_vm_rk4_step
+        step(w, _ptrs(f_new), _ptrs(f_old), em_new, em_old, _ptrs(vz_new), _ptrs(vz_old), t0, dt)
         H, sys_ = _product(deck, states, em, vz)
         assert H.lk_vm_set_time(sys_, t0) == 0
         assert H.lk_vm_advance(sys_, dt) == 0, H.lk_last_error()
