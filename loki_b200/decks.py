@@ -25,6 +25,9 @@ class Species:
 
         # options beyond the benchmark decks: a Krook layer and a pitch-angle collision operator (see Deck.apply_options)
         self.krook, self.collision = None, None
+        # "External 2D" initial condition (External2DIC.C): `external` = the file's "2D dist" dataset, the spatial factor
+        # of the WHOLE configuration space with its ghost layers, (Ny + 2 ng, Nx + 2 ng); `external_frac` = ic.frac
+        self.external, self.external_frac = None, 1.0
         # a TrigTZSource (TrigTZSource.C): Species.tz = dict(amp=) adds the manufactured-solution forcing to the rhs
         self.tz = None
         # "Interpenetrating Stream" initial condition, half-plane syntax (InterpenetratingStreamIC.C:496-540):
@@ -139,6 +142,18 @@ class Deck:
         thx, thy = sp.tx / sp.mass, sp.ty / sp.mass
         fv = np.exp(-0.5 * ((x3 ** 2)[None, :] / thx + (x4 ** 2)[:, None] / thy))
         fnorm = sp.mass / (2.0 * math.pi * math.sqrt(sp.tx * sp.ty))
+        if getattr(sp, "external", None) is not None:
+            # External2DIC::cache, factorable branch (External2DIC.C:147-198): m_fx(i1, i2) = the file's value at the cell,
+            # a ghost cell of a periodic direction taking its periodic image; getIC_At_Pt multiplies
+            # m_frac * fnorm * m_fv * m_fx in this order (:282-284), i.e. the Perturbed Maxwellian's product with
+            # fnorm -> frac * fnorm and frac -> 1 (Species.frac stays 1 for such a species)
+            ext = np.asarray(sp.external, dtype=np.float64)
+            if ext.shape != (self.n[1] + 2 * ng, self.n[0] + 2 * ng):
+                raise ValueError("Distribution size does not match configuration space.")      # External2DIC.C:101-103
+            idx1 = np.where(i1 < 0, i1 + self.n[0], np.where(i1 > self.n[0] - 1, i1 - self.n[0], i1)) if self.periodic[0] else i1
+            idx2 = np.where(i2 < 0, i2 + self.n[1], np.where(i2 > self.n[1] - 1, i2 - self.n[1], i2)) if self.periodic[1] else i2
+            fx = ext[(idx2 + ng)[:, None], (idx1 + ng)[None, :]]
+            fnorm = sp.external_frac * fnorm
         return np.ascontiguousarray(fx), np.ascontiguousarray(fv), fnorm
 
     def stream_tables(self, sp, tile_lo=(0, 0), tile_n=None):

@@ -415,6 +415,39 @@ class _Reader:
             for name, e in self.group_entries(bt, hp):
                 g.children[name] = self.load(e)
             return g
+        if 0x0006 in types or 0x0002 in types:
+            # a "new style" group with compact link storage: one Link message per member in the object header (what
+            # h5py / libhdf5 >= 1.8 write for small groups unless told to stay with symbol tables)
+            g = Group()
+            g.attrs = attrs
+            for t, _, d in msgs:
+                if t == 0x0002 and len(d) >= 18:
+                    flags = d[1]
+                    p = 2 + (8 if flags & 1 else 0)
+                    if struct.unpack_from("<Q", d, p)[0] != UNDEF:
+                        raise FormatError("dense link storage (fractal heap) is not read")
+                if t != 0x0006:
+                    continue
+                flags = d[1]
+                p = 2
+                ltype = 0
+                if flags & 0x08:
+                    ltype = d[p]
+                    p += 1
+                if flags & 0x04:
+                    p += 8
+                if flags & 0x10:
+                    p += 1
+                nlen_size = 1 << (flags & 3)
+                nlen = int.from_bytes(bytes(d[p:p + nlen_size]), "little")
+                p += nlen_size
+                name = bytes(d[p:p + nlen]).decode()
+                p += nlen
+                if ltype != 0:
+                    continue                                   # soft / external links carry no data
+                addr = struct.unpack_from("<Q", d, p)[0]
+                g.children[name] = self.load(dict(name_off=0, oh=addr, cache=0, btree=0, heap=0))
+            return g
         dt = shape = None
         layout = None
         filters = []

@@ -13,6 +13,8 @@ import math
 import operator
 import re
 
+import numpy as np
+
 from . import decks as _d
 
 _CONST = re.compile(r"^\s*\$([A-Za-z_]\w*)\s*=\s*(.+?);\s*(#.*)?$")
@@ -212,6 +214,29 @@ def _species(params, k):
         sp.collision = collision
         sp.tz = tz
         return sp
+    if icn == "External 2D":
+        # External2DIC::parseParameters (External2DIC.C:318-353) and its constructor's read of "2D dist" (:74-126)
+        if (pre + "ic.file_name") not in params:
+            raise ValueError("Must supply name of external 2D distribution file.")
+        if _s(params, pre + "ic.maxwellian_thermal", "true") != "true":
+            raise ValueError("species %d: the Juttner thermal factor is not supported" % k)
+        if g("vx0") != 0.0 or g("vy0") != 0.0:
+            raise ValueError("species %d: a non-factorable External 2D initial condition (vx0 / vy0) is not supported" % k)
+        import os
+        from . import h5lite
+        fname = _s(params, pre + "ic.file_name")
+        path = fname if os.path.isabs(fname) else os.path.join(getattr(params, "base_dir", None) or ".", fname)
+        root = h5lite.read(path)
+        if "2D dist" not in root:
+            raise ValueError('Can not open dataset "2D dist".')
+        sp = _d.Species(name, nv, vlim, mass, charge, tx=g("tx", 1.0), ty=g("ty", 1.0), driver=driver)
+        sp.external = np.array(root["2D dist"].data, dtype=np.float64)
+        sp.external_frac = g("frac", 1.0)
+        sp.driver_phase, sp.driver_shape_type = driver_phase, driver_shape_type
+        sp.krook = krook
+        sp.collision = collision
+        sp.tz = tz
+        return sp
     if icn == "Interpenetrating Stream":
         if _s(params, pre + "ic.syntax", "half plane") != "half plane":
             raise ValueError("only the half-plane syntax of the Interpenetrating Stream IC is supported")
@@ -305,4 +330,6 @@ def deck_from_params(params, name="deck"):
 
 def load(path):
     import os
-    return deck_from_params(parse(open(path).read()), name=os.path.splitext(os.path.basename(path))[0])
+    params = parse(open(path).read())
+    params.base_dir = os.path.dirname(os.path.abspath(path))      # external files are named relative to the deck
+    return deck_from_params(params, name=os.path.splitext(os.path.basename(path))[0])

@@ -1,0 +1,82 @@
+"""The reference's External2D regression deck (test/External2D: three species -- electrons, He2+, C6+ -- whose spatial
+profiles come from the reference's own HDF5 files, order 6 / RK6, 128 x 7 x 24 x 16) at its own grid: one step against
+the oracle, and the first steps through the runner."""
+import numpy as np
+import pytest
+
+import decks
+import test_gpu_vp_system as tvp
+from loki_b200 import pp, run
+from test_cpu_outputs import EXTERNAL_2D
+from util import cell_rel_err, star_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _deck(tmp_path):
+    path = tmp_path / "External2D.pp"
+    path.write_text(EXTERNAL_2D)
+    return decks._wrap(pp.load(str(path)))
+
+
+@pytest.mark.parametrize("mode", ["strict", "production"])
+def test_external2d_one_step_at_the_decks_own_grid(lk, ok, mode, tmp_path):
+    deck = _deck(tmp_path)
+    assert deck.n == (128, 7) and deck.rk == 6 and len(deck.species) == 3
+    old = lk.lk_set_strict(1 if mode == "strict" else 0)
+    try:
+        w, sp, keep = tvp._oracle(ok, deck)
+        states, tables = [], []
+        for s in deck.species:
+            f, fx, fv, fnorm = deck.initial_state(s)
+            states.append(f)
+            tables.append((fx, fv, fnorm))
+        ns = len(states)
+        t0, dt = 0.0, 0.02
+        f_old = [s.copy() for s in states]
+        f_new = [np.zeros_like(s) for s in states]
+        ok.ok_vp_rk6_step(w, tvp._ptrs(f_new), tvp._ptrs(f_old), t0, dt, np.zeros(ns))
+        H, sys_ = tvp._product(deck, states, tables)
+        assert H.lk_vp_set_time(sys_, t0) == 0
+        assert H.lk_vp_advance(sys_, dt) == 0, H.lk_last_error()
+        ng = deck.ng
+        I = (slice(ng, -ng),) * 4
+        for s in range(ns):
+            out = np.empty_like(states[s])
+            assert H.lk_vp_get_state(sys_, s, out.ctypes.data) == 0
+            assert np.any(out[I] != states[s][I])           # the density step at x = +-25 moves the plasma
+            if mode == "strict":
+                assert np.array_equal(out[I], f_new[s][I])
+            else:
+                assert star_rel_err(out, f_new[s], np.maximum(np.abs(states[s]), np.abs(f_new[s])), ng) <= 1e-12
+                # per cell (checkTests.C:345-358) where the distribution is above 1e-6 of its peak: the profile is a step
+                # of 200 : 1 across two cells, rough data on which the nonlinear weights amplify rounding differences,
+                # and the Maxwellian tails next to the step sit at 1e-12 of the peak (2e-11 per cell there)
+                bulk = f_new[s][I] >= 1e-6 * f_new[s][I].max()
+                assert cell_rel_err(out[I][bulk], f_new[s][I][bulk]) <= 1e-11
+        H.lk_vp_destroy(sys_)
+        ok.ok_vp_work_destroy(w)
+    finally:
+        lk.lk_set_strict(old)
+
+
+def test_external2d_deck_through_the_runner(lk, fast, tmp_path):
+    """Simulation::advance on the deck: the plasma stays neutral to rounding, the field grows out of the density step,
+    the kinetic energies are those of Maxwellians at the three species' temperatures"""
+    deck = _deck(tmp_path)
+    deck.run["max_step"] = 3
+    r = run.Runner(deck)
+    h0 = r.history()
+    while not r.done():
+        r.advance()
+    h = r.history()
+    assert r.step == 3 and r.time > 0
+    ns = 3
+    ke0 = [h0[5 + 6 * s] for s in range(ns)]
+    ke = [h[5 + 6 * s] for s in range(ns)]
+    # <m v^2 / 2> = T = 1 per particle for every species: n_e : n_He : n_C = 10 : 0.025 : 1.667 over the same area,
+    # up to the truncation of the Maxwellian at 7.5 thermal speeds and the density step
+    assert abs(ke0[0] / ke0[2] - 6.0) < 0.3 and ke0[1] > 0
+    assert all(abs(a - b) <= 1e-3 * b for a, b in zip(ke, ke0))
+    assert h[0] > 0.0                                     # E_max: a field has grown
+    r.close()
