@@ -294,14 +294,16 @@ int lk_maxwell_vz_rhs(double* dvz, const double* em, int n1, int n2, int ng, dou
  * them on the HOST with libm (the Fortran's argument expressions; lo = global index of array cell 0 in x and y, xlo = the
  * domain's lower corner) and stores lk_trig_tz_table_count doubles on the device; the two kernels then evaluate the
  * Fortran's expression tree on those operands, so the result carries the reference's bits.  Both run over the whole
- * data box like the Fortran.  lk_trig_tz_tables synchronises. */
+ * data box like the Fortran.  lk_trig_tz_tables synchronises.
+ * kind 0 = TrigTZSource (kx = ky = 1); kind 1 = ElectronTrigTZSource, setelectrontrigtzsource_ /
+ * computeelectrontrigtzsourceerror_ (ElectronTZSourceF.f:10-143, deck test/EPWTZ): the same solution with kx = ky = 4. */
 int lk_trig_tz_table_count(const lk_geom* g, int64_t* count);
 int lk_trig_tz_tables(double* tables, const lk_geom* g, const int lo[2], const double xlo[2], const double* velocities,
-                      void* stream);
+                      int kind, void* stream);
 int lk_set_trig_tz_source(double* rhs, const lk_geom* g, const double* tables, const double* velocities, double time, double amp,
-                          void* stream);
+                          int kind, void* stream);
 int lk_compute_trig_tz_source_error(double* error, const double* soln, const lk_geom* g, const double* tables,
-                                    const double* velocities, double time, double amp, void* stream);
+                                    const double* velocities, double time, double amp, int kind, void* stream);
 /* appendkrook_ (KineticSpeciesF.f:2995-3034; completeRHS, KineticSpecies.C:1049-1080): Krook-layer damping of an
  * UNFUSED rhs towards the initial condition, rhs -= nu(x,y)/dt * (u - IC) where nu != 0; nu: (n1d,n2d) device.
  * Level-0 only: the fused stage never materialises rhs, and no benchmark deck has a Krook layer. */

@@ -131,6 +131,14 @@ void computetrigtzsourceerror_(double* error, const double* soln, const int* nd1
                                const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b,
                                const double* xlo, const double* xhi, const double* dx, const double* time,
                                const double* velocities, const double* dparams);
+/* ElectronTZSourceF.f:10-27, :79-97 (ElectronTZSourceF.H; called from ElectronTrigTZSource.C:44-82) */
+void setelectrontrigtzsource_(double* f, const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a,
+                              const int* nd3b, const int* nd4a, const int* nd4b, const double* xlo, const double* xhi,
+                              const double* dx, const double* time, const double* velocities, const double* dparams);
+void computeelectrontrigtzsourceerror_(double* error, const double* soln, const int* nd1a, const int* nd1b, const int* nd2a,
+                                       const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b,
+                                       const double* xlo, const double* xhi, const double* dx, const double* time,
+                                       const double* velocities, const double* dparams);
 /* KineticSpeciesF.f:2995-3034 */
 void appendkrook_(const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a, const int* nd3b,
                   const int* nd4a, const int* nd4b, const int* n1a, const int* n1b, const int* n2a, const int* n2b,

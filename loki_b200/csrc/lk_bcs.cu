@@ -251,9 +251,10 @@ cudaError_t append_krook(double* rhs, const double* u, const lk_geom* g, const d
 // (per i2), exp(-alpha v^2 / 2) (per (i3, i4)), sin t / cos t (scalars) -- and come from host tables built with libm, so
 // the kernel evaluates Maple's expression tree in the Fortran's parse order on the same operand bits (-fmad=false).
 // tab: {sin(kx x)[n1d], cos(kx x)[n1d], sin(ky y)[n2d], cos(ky y)[n2d], exp(..)[n3d n4d]}
+// kind 0: TrigTZSource (kx = ky = 1), kind 1: ElectronTrigTZSource (ElectronTZSourceF.f, kx = ky = 4, other term order)
 __global__ void k_trig_tz(Geo g, const double* __restrict__ tab, const double* __restrict__ velocities, double A, double st,
-                          double ct, double pi, const double* __restrict__ soln, double* __restrict__ out) {
-  const double kx = 1.0, ky = 1.0, kt = 1.0, alpha = 1.0;
+                          double ct, double pi, const double* __restrict__ soln, double* __restrict__ out, int kind) {
+  const double kx = kind ? 4.0 : 1.0, ky = kx, kt = 1.0, alpha = 1.0;
   const double* sx = tab;
   const double* cx = sx + g.nd[0];
   const double* sy = cx + g.nd[0];
@@ -272,6 +273,13 @@ __global__ void k_trig_tz(Geo g, const double* __restrict__ tab, const double* _
     if (soln) {
       const double fexact = alpha / pi * e * (0.1e1 + A * cosx * cosy * st) / 0.2e1;
       out[t] = soln[t] - fexact;
+    } else if (kind) {
+      const double h =
+          alpha / pi * e * A * cosx * cosy * kt * ct / 0.2e1 - vx * alpha / pi * e * A * kx * sinx * cosy * st / 0.2e1 -
+          vy * alpha / pi * e * A * cosx * ky * siny * st / 0.2e1 -
+          A * kx * sinx * cosy * st / (kx * kx + ky * ky) * (alpha * alpha) / pi * vx * e * (0.1e1 + A * cosx * cosy * st) / 0.2e1 -
+          A * cosx * ky * siny * st / (kx * kx + ky * ky) * (alpha * alpha) / pi * vy * e * (0.1e1 + A * cosx * cosy * st) / 0.2e1;
+      out[t] = out[t] + h;
     } else {
       const double h =
           -0.1e1 / (kx * kx + ky * ky) * A * sinx * kx * cosy * st * (alpha * alpha) / pi * vx * e * (0.1e1 + A * cosx * cosy * st) / 0.2e1 -
@@ -284,8 +292,8 @@ __global__ void k_trig_tz(Geo g, const double* __restrict__ tab, const double* _
 }
 
 // host side of the tables: libm, the Fortran's argument expressions; vel_host: (n3d, n4d, 2)
-void trig_tz_tables(double* tab, const lk_geom* g, const int lo[2], const double xlo[2], const double* vel_host) {
-  const double kx = 1.0, ky = 1.0, alpha = 1.0;
+void trig_tz_tables(double* tab, const lk_geom* g, const int lo[2], const double xlo[2], const double* vel_host, int kind) {
+  const double kx = kind ? 4.0 : 1.0, ky = kx, alpha = 1.0;
   const int n1d = g->n[0] + 2 * g->ng, n2d = g->n[1] + 2 * g->ng, n3d = g->n[2] + 2 * g->ng, n4d = g->n[3] + 2 * g->ng;
   double* sx = tab;
   double* cx = sx + n1d;
@@ -314,14 +322,14 @@ size_t trig_tz_table_count(const lk_geom* g) {
 
 // out += h (soln == nullptr) or out = soln - f_exact; tab_dev: trig_tz_tables on the device
 cudaError_t trig_tz(double* out, const double* soln, const lk_geom* g, const double* tab_dev, const double* velocities,
-                    double time, double amp, cudaStream_t st, int64_t* launches) {
+                    double time, double amp, int kind, cudaStream_t st, int64_t* launches) {
   Geo d = make_geo(g);
   const double kt = 1.0;
   const double pi = 4.0 * atan(1.0);
   const i64 total = (i64)d.nd[0] * d.nd[1] * d.nd[2] * d.nd[3];
   i64 blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_trig_tz<<<(unsigned)blocks, 256, 0, st>>>(d, tab_dev, velocities, amp, sin(kt * time), cos(kt * time), pi, soln, out);
+  k_trig_tz<<<(unsigned)blocks, 256, 0, st>>>(d, tab_dev, velocities, amp, sin(kt * time), cos(kt * time), pi, soln, out, kind);
   ++*launches;
   return cudaGetLastError();
 }

@@ -413,14 +413,14 @@ void computekevelspaceflux_(const int* nd1a, const int* nd1b, const int* nd2a, c
 // over all of it, so the split into interior and ghosts does not matter (order 4's is assumed).  f, soln, error and
 // velocities are device arrays; xlo, xhi, dx, dparams are the host-side heads PROBLEMDOMAIN_TO_FORT passes.
 static bool tz_tables(const char* who, const int* const nd[8], const double* xlo, const double* dx, const double* velocities,
-                      lk_geom* g, double** tab) {
+                      lk_geom* g, double** tab, int kind) {
   if (!geom_from_data(who, nd, 4, dx, g)) return false;
   int64_t count = 0;
   if (!check(lk_trig_tz_table_count(g, &count))) return false;
   if (!check(lk_malloc((void**)tab, sizeof(double) * count))) return false;
   const int lo[2] = {*nd[0], *nd[2]};
   const double x0[2] = {xlo[0], xlo[1]};
-  if (!check(lk_trig_tz_tables(*tab, g, lo, x0, velocities, nullptr))) {
+  if (!check(lk_trig_tz_tables(*tab, g, lo, x0, velocities, kind, nullptr))) {
     lk_free(*tab);
     return false;
   }
@@ -433,8 +433,8 @@ void settrigtzsource_(double* f, const int* nd1a, const int* nd1b, const int* nd
   const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
   lk_geom g;
   double* tab = nullptr;
-  if (!tz_tables("settrigtzsource_", nd, xlo, dx, velocities, &g, &tab)) return;
-  if (check(lk_set_trig_tz_source(f, &g, tab, velocities, *time, dparams[0], nullptr))) check(lk_sync(nullptr));
+  if (!tz_tables("settrigtzsource_", nd, xlo, dx, velocities, &g, &tab, 0)) return;
+  if (check(lk_set_trig_tz_source(f, &g, tab, velocities, *time, dparams[0], 0, nullptr))) check(lk_sync(nullptr));
   lk_free(tab);
 }
 void computetrigtzsourceerror_(double* error, const double* soln, const int* nd1a, const int* nd1b, const int* nd2a,
@@ -445,8 +445,33 @@ void computetrigtzsourceerror_(double* error, const double* soln, const int* nd1
   const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
   lk_geom g;
   double* tab = nullptr;
-  if (!tz_tables("computetrigtzsourceerror_", nd, xlo, dx, velocities, &g, &tab)) return;
-  if (check(lk_compute_trig_tz_source_error(error, soln, &g, tab, velocities, *time, dparams[0], nullptr))) check(lk_sync(nullptr));
+  if (!tz_tables("computetrigtzsourceerror_", nd, xlo, dx, velocities, &g, &tab, 0)) return;
+  if (check(lk_compute_trig_tz_source_error(error, soln, &g, tab, velocities, *time, dparams[0], 0, nullptr))) check(lk_sync(nullptr));
+  lk_free(tab);
+}
+
+// ElectronTZSourceF.f:10-27, :79-97: the same argument lists, kx = ky = 4
+void setelectrontrigtzsource_(double* f, const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a,
+                              const int* nd3b, const int* nd4a, const int* nd4b, const double* xlo, const double* xhi,
+                              const double* dx, const double* time, const double* velocities, const double* dparams) {
+  (void)xhi;
+  const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
+  lk_geom g;
+  double* tab = nullptr;
+  if (!tz_tables("setelectrontrigtzsource_", nd, xlo, dx, velocities, &g, &tab, 1)) return;
+  if (check(lk_set_trig_tz_source(f, &g, tab, velocities, *time, dparams[0], 1, nullptr))) check(lk_sync(nullptr));
+  lk_free(tab);
+}
+void computeelectrontrigtzsourceerror_(double* error, const double* soln, const int* nd1a, const int* nd1b, const int* nd2a,
+                                       const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b,
+                                       const double* xlo, const double* xhi, const double* dx, const double* time,
+                                       const double* velocities, const double* dparams) {
+  (void)xhi;
+  const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
+  lk_geom g;
+  double* tab = nullptr;
+  if (!tz_tables("computeelectrontrigtzsourceerror_", nd, xlo, dx, velocities, &g, &tab, 1)) return;
+  if (check(lk_compute_trig_tz_source_error(error, soln, &g, tab, velocities, *time, dparams[0], 1, nullptr))) check(lk_sync(nullptr));
   lk_free(tab);
 }
 

@@ -221,6 +221,7 @@ struct KineticSpecies {
   bool has_coll = false;
   // TrigTZSource (KineticSpecies.C:1077-1080): the manufactured-solution forcing; tables of lk_trig_tz_tables
   bool has_tz = false;
+  int tz_kind = 0;   // 0 TrigTZSource, 1 ElectronTrigTZSource
   double tz_amp = 0.0;
   DevBuf<double> tz_tab;
   lk_pitch_angle coll;
@@ -687,7 +688,7 @@ struct VPSystem {
         LKH_CHECK(lk_vlasov_rhs(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, nullptr, st));
         if (ks->has_coll) LKH_CHECK(ks->appendCollision(rhs_out, ks->f_eval, st));
         if (ks->has_krook) LKH_CHECK(lk_append_krook(rhs_out, ks->f_eval, &ks->g, ks->krook_nu.p, dt, &ks->inflow, st));
-        if (ks->has_tz) LKH_CHECK(lk_set_trig_tz_source(rhs_out, &ks->g, ks->tz_tab.p, ks->velocities.p, t_stage, ks->tz_amp, st));
+        if (ks->has_tz) LKH_CHECK(lk_set_trig_tz_source(rhs_out, &ks->g, ks->tz_tab.p, ks->velocities.p, t_stage, ks->tz_amp, ks->tz_kind, st));
         LKH_CHECK(lk_rk_stage_update(rhs_out, &ks->g, &u, st));
       } else {
         const int ie = ks->arrayIndex(ks->f_eval);
@@ -813,7 +814,7 @@ struct VPSystem {
       LKH_CHECK(lk_acceleration_derivatives_4d(rhs_dev[s], f, &ks->g, &a, st));
       if (ks->has_coll) LKH_CHECK(ks->appendCollision(rhs_dev[s], f, st));
       if (ks->has_krook) LKH_CHECK(lk_append_krook(rhs_dev[s], f, &ks->g, ks->krook_nu.p, dt, &ks->inflow, st));
-      if (ks->has_tz) LKH_CHECK(lk_set_trig_tz_source(rhs_dev[s], &ks->g, ks->tz_tab.p, ks->velocities.p, t, ks->tz_amp, st));
+      if (ks->has_tz) LKH_CHECK(lk_set_trig_tz_source(rhs_dev[s], &ks->g, ks->tz_tab.p, ks->velocities.p, t, ks->tz_amp, ks->tz_kind, st));
       if (ks->has_driver)
         LKH_CHECK(lk_ke_e_dot(ks->ke.p + 3, f, &ks->g, ks->charge, ks->velocities.p, ks->ext_efield.p, st));
     }
@@ -1551,15 +1552,18 @@ int lk_vp_set_trig_tz(lk_vp_system* h, int s, int on, double amp) {
   auto* ks = S.species[s];
   ks->has_tz = false;
   if (!on) return LK_OK;
+  if (on != 1 && on != 2) return LK_ERR_ARG;
+  const int kind = on - 1;
   int64_t count = 0;
   int st = lk_trig_tz_table_count(&ks->g, &count);
   if (st != LK_OK) return st;
   st = ks->tz_tab.alloc((size_t)count);
   if (st != LK_OK) return st;
   const int lo[2] = {S.desc.tile_lo[0] - ks->g.ng, S.desc.tile_lo[1] - ks->g.ng};
-  st = lk_trig_tz_tables(ks->tz_tab.p, &ks->g, lo, S.desc.xlo, ks->velocities.p, S.st);
+  st = lk_trig_tz_tables(ks->tz_tab.p, &ks->g, lo, S.desc.xlo, ks->velocities.p, kind, S.st);
   if (st != LK_OK) return st;
   ks->has_tz = true;
+  ks->tz_kind = kind;
   ks->tz_amp = amp;
   return LK_OK;
 }
@@ -1571,7 +1575,7 @@ int lk_vp_trig_tz_error(lk_vp_system* h, int s, double time, double* error_host)
   auto* ks = S.species[s];
   if (!ks->has_tz) return LK_ERR_ARG;
   if (!ks->rhs_tmp.p) LKH_CHECK(ks->rhs_tmp.alloc(ks->vol));
-  LKH_CHECK(lk_compute_trig_tz_source_error(ks->rhs_tmp.p, ks->state(), &ks->g, ks->tz_tab.p, ks->velocities.p, time, ks->tz_amp, S.st));
+  LKH_CHECK(lk_compute_trig_tz_source_error(ks->rhs_tmp.p, ks->state(), &ks->g, ks->tz_tab.p, ks->velocities.p, time, ks->tz_amp, ks->tz_kind, S.st));
   LKH_CUDA(cudaStreamSynchronize(S.st));
   LKH_CUDA(cudaMemcpy(error_host, ks->rhs_tmp.p, sizeof(double) * ks->vol, cudaMemcpyDeviceToHost));
   return LK_OK;

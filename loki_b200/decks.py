@@ -28,7 +28,8 @@ class Species:
         # "External 2D" initial condition (External2DIC.C): `external` = the file's "2D dist" dataset, the spatial factor
         # of the WHOLE configuration space with its ghost layers, (Ny + 2 ng, Nx + 2 ng); `external_frac` = ic.frac
         self.external, self.external_frac = None, 1.0
-        # a TrigTZSource (TrigTZSource.C): Species.tz = dict(amp=) adds the manufactured-solution forcing to the rhs
+        # a twilight-zone source: Species.tz = dict(amp=, kind= 1 TrigTZSource | 2 ElectronTrigTZSource) adds the
+        # manufactured-solution forcing to the rhs
         self.tz = None
         # "Interpenetrating Stream" initial condition, half-plane syntax (InterpenetratingStreamIC.C:496-540):
         # dict(tl, tt, theta, d, beta, floor, frac, frac2, two_sided, centered)
@@ -113,7 +114,7 @@ class Deck:
                 st = H.lk_vp_set_pitch_angle(sys_, s, pa)
             tz = getattr(sp, "tz", None)
             if st == 0 and tz:
-                st = H.lk_vp_set_trig_tz(sys_, s, 1, float(tz["amp"]))
+                st = H.lk_vp_set_trig_tz(sys_, s, int(tz.get("kind", 1)), float(tz["amp"]))
         return st
 
     def geom_of(self, sp):

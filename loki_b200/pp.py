@@ -197,11 +197,11 @@ def _species(params, k):
     tz = None
     if (pre + "tz.name") in params:
         tzname = _s(params, pre + "tz.name")
-        if tzname != "TrigTZSource":
-            raise ValueError("species %d: twilight-zone source %r is not supported (only TrigTZSource)" % (k, tzname))
+        if tzname not in ("TrigTZSource", "ElectronTrigTZSource"):
+            raise ValueError("species %d: twilight-zone source %r is not supported (only TrigTZSource / ElectronTrigTZSource)" % (k, tzname))
         if (pre + "tz.amp") not in params:
             raise ValueError("Must supply amp")                                   # TrigTZSource.C:28-31
-        tz = dict(amp=_f(params, pre + "tz.amp"))
+        tz = dict(amp=_f(params, pre + "tz.amp"), kind=1 if tzname == "TrigTZSource" else 2)
     elif any(key.startswith(pre + "tz.") for key in list(params.keys())):
         raise ValueError("species %d: tz.* keys without tz.name" % k)
     if icn == "Perturbed Maxwellian":

@@ -38,6 +38,7 @@ ROUTINES = {
                                        "computepitchanglespeciesreducedfields", "computepitchanglespecieskec",
                                        "computepitchanglespeciesvthermal"],
     "TZSourceF.f": ["settrigtzsource", "computetrigtzsourceerror"],
+    "ElectronTZSourceF.f": ["setelectrontrigtzsource", "computeelectrontrigtzsourceerror"],
 }
 ALL_WANTED = {r for rs in ROUTINES.values() for r in rs}
 INTRINSICS = {"max": "fmax", "min": "fmin", "abs": "fabs", "sqrt": "sqrt", "sin": "sin", "cos": "cos", "exp": "exp",

@@ -1109,6 +1109,56 @@ void ok_compute_trig_tz_source_error(double* error, const double* soln, const ok
     }
 }
 
+/* ElectronTrigTZSource (ElectronTZSourceF.f:10-75 setelectrontrigtzsource, :79-143 computeelectrontrigtzsourceerror;
+ * deck test/EPWTZ): the same manufactured solution with kx = ky = 4; Maple ordered the source's terms differently */
+void ok_set_electron_trig_tz_source(double* f, const ok_geom* g, const int* lo, const double* xlo, const double* dx, double time,
+                                    const double* velocities, double amp) {
+  const int64_t n3d = ND(2), n4d = ND(3);
+  const double kx = 4.0, ky = 4.0, kt = 1.0, alpha = 1.0, A = amp, t = time;
+  const double pi = 4.0 * atan(1.0);
+  for (int i4 = 0; i4 < n4d; ++i4)
+    for (int i3 = 0; i3 < n3d; ++i3) {
+      const double vx = velocities[i3 + n3d * (i4 + n4d * 0)];
+      const double vy = velocities[i3 + n3d * (i4 + n4d * 1)];
+      for (int i2 = 0; i2 < ND(1); ++i2) {
+        const double y = xlo[1] + ((lo[1] + i2) + 0.5) * dx[1];
+        for (int i1 = 0; i1 < ND(0); ++i1) {
+          const double x = xlo[0] + ((lo[0] + i1) + 0.5) * dx[0];
+          const double h =
+              alpha / pi * exp(-(alpha * (vx * vx + vy * vy) / 0.2e1)) * A * cos(kx * x) * cos(ky * y) * kt * cos(kt * t) / 0.2e1 -
+              vx * alpha / pi * exp(-(alpha * (vx * vx + vy * vy) / 0.2e1)) * A * kx * sin(kx * x) * cos(ky * y) * sin(kt * t) / 0.2e1 -
+              vy * alpha / pi * exp(-(alpha * (vx * vx + vy * vy) / 0.2e1)) * A * cos(kx * x) * ky * sin(ky * y) * sin(kt * t) / 0.2e1 -
+              A * kx * sin(kx * x) * cos(ky * y) * sin(kt * t) / (kx * kx + ky * ky) * (alpha * alpha) / pi * vx *
+                  exp(-(alpha * (vx * vx + vy * vy) / 0.2e1)) * (0.1e1 + A * cos(kx * x) * cos(ky * y) * sin(kt * t)) / 0.2e1 -
+              A * cos(kx * x) * ky * sin(ky * y) * sin(kt * t) / (kx * kx + ky * ky) * (alpha * alpha) / pi * vy *
+                  exp(-(alpha * (vx * vx + vy * vy) / 0.2e1)) * (0.1e1 + A * cos(kx * x) * cos(ky * y) * sin(kt * t)) / 0.2e1;
+          F4(f, i1, i2, i3, i4) = F4(f, i1, i2, i3, i4) + h;
+        }
+      }
+    }
+}
+void ok_compute_electron_trig_tz_source_error(double* error, const double* soln, const ok_geom* g, const int* lo,
+                                              const double* xlo, const double* dx, double time, const double* velocities,
+                                              double amp) {
+  const int64_t n3d = ND(2), n4d = ND(3);
+  const double kx = 4.0, ky = 4.0, kt = 1.0, alpha = 1.0, A = amp, t = time;
+  const double pi = 4.0 * atan(1.0);
+  for (int i4 = 0; i4 < n4d; ++i4)
+    for (int i3 = 0; i3 < n3d; ++i3) {
+      const double vx = velocities[i3 + n3d * (i4 + n4d * 0)];
+      const double vy = velocities[i3 + n3d * (i4 + n4d * 1)];
+      for (int i2 = 0; i2 < ND(1); ++i2) {
+        const double y = xlo[1] + ((lo[1] + i2) + 0.5) * dx[1];
+        for (int i1 = 0; i1 < ND(0); ++i1) {
+          const double x = xlo[0] + ((lo[0] + i1) + 0.5) * dx[0];
+          const double fexact = alpha / pi * exp(-(alpha * (vx * vx + vy * vy) / 0.2e1)) *
+                                (0.1e1 + A * cos(kx * x) * cos(ky * y) * sin(kt * t)) / 0.2e1;
+          F4(error, i1, i2, i3, i4) = F4(soln, i1, i2, i3, i4) - fexact;
+        }
+      }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------
  * Time-history diagnostics.
  * computeke (KineticSpeciesF.f:2447-2500): out = {ke, ke_x, ke_y, px, py}; the running sums start from

@@ -32,7 +32,7 @@ struct ok_vp_work {
   int nonperiodic[2], use_new_bcs;
   double** krook_nu;
   double** coll;   /* pitch-angle operator parameters per species (8 doubles) or NULL */
-  double** tz;     /* TrigTZSource amplitude per species (1 double) or NULL (KineticSpecies.C:1077-1080) */
+  double** tz;     /* twilight-zone source per species {amp, kind 1 / 2} or NULL (KineticSpecies.C:1077-1080) */
   double cur_dt;
 };
 
@@ -199,8 +199,9 @@ void ok_vp_set_trig_tz(ok_vp_work* w, int s, int on, double amp) {
   free(w->tz[s]);
   w->tz[s] = NULL;
   if (on) {
-    w->tz[s] = (double*)malloc(sizeof(double));
+    w->tz[s] = (double*)malloc(2 * sizeof(double));
     w->tz[s][0] = amp;
+    w->tz[s][1] = (double)on;
   }
 }
 /* fillAdvectionGhostCells on one rank (KineticSpecies.H:404-412, 998-1031): physical boundary conditions of the
@@ -279,7 +280,10 @@ void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double time, double
     if (w->tz[s]) {
       /* the twilight-zone source (KineticSpecies.C:1077-1080) */
       const int lo[2] = {-g->ng, -g->ng};
-      ok_set_trig_tz_source(rhs[s], g, lo, w->xlo, g->dx, time, w->velocities[s], w->tz[s][0]);
+      if (w->tz[s][1] == 2.0)
+        ok_set_electron_trig_tz_source(rhs[s], g, lo, w->xlo, g->dx, time, w->velocities[s], w->tz[s][0]);
+      else
+        ok_set_trig_tz_source(rhs[s], g, lo, w->xlo, g->dx, time, w->velocities[s], w->tz[s][0]);
     }
     if (sp->has_driver && ke_e_dot)
       ke_e_dot[s] = ok_compute_ke_e_dot(g, f[s], sp->charge, w->velocities[s], w->ext[s], 0.0);

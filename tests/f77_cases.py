@@ -225,6 +225,14 @@ def kinetic_cases(B, ok, order):
            B.arr(s.velocities), B.meta(amp))
     B.finish()
     out["tz_source"], out["tz_error"] = tz, err
+    # ElectronTrigTZSource (ElectronTZSourceF.f:10-143): the same lists, kx = ky = 4
+    tze = np.ascontiguousarray(rng.uniform(-1, 1, size=s.f.shape))
+    B.call("setelectrontrigtzsource_", B.arr(tze), *db, B.meta(xlo4), B.meta(xhi4), B.meta(dxs), B.d(0.37), B.arr(s.velocities), B.meta(amp))
+    erre = np.zeros_like(s.f)
+    B.call("computeelectrontrigtzsourceerror_", B.arr(erre), B.arr(s.f), *db, B.meta(xlo4), B.meta(xhi4), B.meta(dxs), B.d(0.37),
+           B.arr(s.velocities), B.meta(amp))
+    B.finish()
+    out["etz_source"], out["etz_error"] = tze, erre
     return out
 
 

@@ -110,6 +110,8 @@ def load():
     L.ok_vp_set_trig_tz.argtypes = [C.c_void_p, i, i, d]
     L.ok_set_trig_tz_source.argtypes = [dp, G, C.c_void_p, dp, dp, d, dp, d]
     L.ok_compute_trig_tz_source_error.argtypes = [dp, dp, G, C.c_void_p, dp, dp, d, dp, d]
+    L.ok_set_electron_trig_tz_source.argtypes = [dp, G, C.c_void_p, dp, dp, d, dp, d]
+    L.ok_compute_electron_trig_tz_source_error.argtypes = [dp, dp, G, C.c_void_p, dp, dp, d, dp, d]
     L.ok_pitch_angle_collisionality.restype = d
     L.ok_pitch_angle_collisionality.argtypes = [d, d, d, d, dp, dp, d, d, d, d, d, d, d, i]
     L.ok_pitch_angle_fields.argtypes = [dp, dp, dp, dp, G, dp]

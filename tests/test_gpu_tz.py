@@ -45,8 +45,9 @@ def _deck(tmp_path):
     return decks._wrap(pp.load(str(path)))
 
 
+@pytest.mark.parametrize("kind", [0, 1])
 @pytest.mark.parametrize("order", [4, 6])
-def test_trig_tz_kernels_equal_the_oracle_bits(lk, ok, order):
+def test_trig_tz_kernels_equal_the_oracle_bits(lk, ok, order, kind):
     """lk_trig_tz_tables + lk_set_trig_tz_source / lk_compute_trig_tz_source_error on a box whose lower corner is not
     the domain's: bit for bit (the kernels take their sines, cosines and exponentials from host tables)"""
     import torch
@@ -62,28 +63,31 @@ def test_trig_tz_kernels_equal_the_oracle_bits(lk, ok, order):
     assert count.value == 2 * n1d + 2 * n2d + n3d * n4d
     tab = torch.zeros(count.value, dtype=torch.float64, device="cuda")
     vel = torch.from_numpy(s.velocities).cuda()
-    assert lk.lk_trig_tz_tables(tab.data_ptr(), C.byref(g), C.byref(lo), C.byref((C.c_double * 2)(*xlo)), vel.data_ptr(), None) == 0
+    assert lk.lk_trig_tz_tables(tab.data_ptr(), C.byref(g), C.byref(lo), C.byref((C.c_double * 2)(*xlo)), vel.data_ptr(), kind, None) == 0
+    ok_set = ok.ok_set_electron_trig_tz_source if kind else ok.ok_set_trig_tz_source       # kind 1: ElectronTrigTZSource
+    ok_err = ok.ok_compute_electron_trig_tz_source_error if kind else ok.ok_compute_trig_tz_source_error
     for time, amp in ((0.0, 1.0), (0.37, 0.1), (2.5, 1.0)):
         base = np.random.default_rng(3).uniform(-1, 1, size=s.f.shape)
         want = base.copy()
-        ok.ok_set_trig_tz_source(want.ravel(), C.byref(s.g), lo, xlo, dx, time, s.velocities, amp)
+        ok_set(want.ravel(), C.byref(s.g), lo, xlo, dx, time, s.velocities, amp)
         d = torch.from_numpy(base).cuda()
-        assert lk.lk_set_trig_tz_source(d.data_ptr(), C.byref(g), tab.data_ptr(), vel.data_ptr(), time, amp, None) == 0
+        assert lk.lk_set_trig_tz_source(d.data_ptr(), C.byref(g), tab.data_ptr(), vel.data_ptr(), time, amp, kind, None) == 0
         got = d.cpu().numpy()
         assert np.array_equal(got, want) and not np.array_equal(got, base)
         e_want = np.zeros_like(base)
-        ok.ok_compute_trig_tz_source_error(e_want.ravel(), s.f.ravel(), C.byref(s.g), lo, xlo, dx, time, s.velocities, amp)
+        ok_err(e_want.ravel(), s.f.ravel(), C.byref(s.g), lo, xlo, dx, time, s.velocities, amp)
         e = torch.zeros_like(d)
         f = torch.from_numpy(s.f).cuda()
-        assert lk.lk_compute_trig_tz_source_error(e.data_ptr(), f.data_ptr(), C.byref(g), tab.data_ptr(), vel.data_ptr(), time, amp, None) == 0
+        assert lk.lk_compute_trig_tz_source_error(e.data_ptr(), f.data_ptr(), C.byref(g), tab.data_ptr(), vel.data_ptr(), time, amp, kind, None) == 0
         assert np.array_equal(e.cpu().numpy(), e_want)
-    assert lk.lk_set_trig_tz_source(None, C.byref(g), tab.data_ptr(), vel.data_ptr(), 0.0, 1.0, None) != 0
+    assert lk.lk_set_trig_tz_source(None, C.byref(g), tab.data_ptr(), vel.data_ptr(), 0.0, 1.0, kind, None) != 0
+    assert lk.lk_set_trig_tz_source(tab.data_ptr(), C.byref(g), tab.data_ptr(), vel.data_ptr(), 0.0, 1.0, 2, None) != 0
 
 
 @pytest.mark.parametrize("mode", ["strict", "production"])
 def test_trig_tz_deck_one_step_at_its_own_grid(lk, ok, mode, tmp_path):
     deck = _deck(tmp_path)
-    assert deck.n == (16, 16) and deck.species[0].nv == (64, 64) and deck.species[0].tz == dict(amp=1.0)
+    assert deck.n == (16, 16) and deck.species[0].nv == (64, 64) and deck.species[0].tz == dict(amp=1.0, kind=1)
     old = lk.lk_set_strict(1 if mode == "strict" else 0)
     try:
         w, sp, keep = tvp._oracle(ok, deck)
@@ -146,3 +150,68 @@ def test_trig_tz_run_tracks_the_exact_solution(lk, fast, tmp_path):
         r.close()
     assert 1e-6 < errs[16] < 5e-5, errs
     assert errs[8] / errs[16] > 6.0, errs          # fourth order in x, y (the velocity grid is not refined)
+
+
+EPW_TZ = """
+# test/EPWTZ/EPWTZ.pp of the reference, restated (same numbers): ElectronTrigTZSource, order 6 / RK6, 16^4 cells
+$pi = 3.1415926535897932384626;
+$xa = -2*$pi;
+$xb =  2*$pi;
+$ya = -1*$pi;
+$yb =  1*$pi;
+temporal_solution_order = 6
+spatial_solution_order = 6
+domain_limits = $xa $xb $ya $yb
+N = 16 16
+periodic_dir = true true
+cfl = 1.0
+final_time = 1
+save_times = .2
+sequence_write_times = .2
+max_step = 1000000
+number_of_species = 1
+kinetic_species.1.name = "electron"
+kinetic_species.1.velocity_limits = -7 7 -9 9
+kinetic_species.1.Nv = 16 16
+kinetic_species.1.mass = 1
+kinetic_species.1.charge = -1.0
+kinetic_species.1.tz.name = "ElectronTrigTZSource"
+kinetic_species.1.tz.amp = 0.1
+kinetic_species.1.ic.name = "Perturbed Maxwellian"
+kinetic_species.1.ic.tx = 1.0
+kinetic_species.1.ic.ty = 1.0
+kinetic_species.1.ic.kx2 = 1.0
+"""
+
+
+@pytest.mark.parametrize("mode", ["strict", "production"])
+def test_epw_tz_deck_one_step_at_its_own_grid(lk, ok, mode, tmp_path):
+    """the reference's EPWTZ deck (ElectronTrigTZSource, kx = ky = 4, sixth order in space and time) against the oracle"""
+    path = tmp_path / "EPWTZ.pp"
+    path.write_text(EPW_TZ)
+    deck = decks._wrap(pp.load(str(path)))
+    assert deck.order == 6 and deck.rk == 6 and deck.species[0].tz == dict(amp=0.1, kind=2)
+    old = lk.lk_set_strict(1 if mode == "strict" else 0)
+    try:
+        w, sp, keep = tvp._oracle(ok, deck)
+        s0 = deck.species[0]
+        f, fx, fv, fnorm = deck.initial_state(s0)
+        t0, dt = 0.4, 0.03
+        f_old, f_new = [f.copy()], [np.zeros_like(f)]
+        ok.ok_vp_rk6_step(w, tvp._ptrs(f_new), tvp._ptrs(f_old), t0, dt, np.zeros(1))
+        H, sys_ = tvp._product(deck, [f], [(fx, fv, fnorm)])
+        assert H.lk_vp_set_time(sys_, t0) == 0
+        assert H.lk_vp_advance(sys_, dt) == 0, H.lk_last_error()
+        out = np.empty_like(f)
+        assert H.lk_vp_get_state(sys_, 0, out.ctypes.data) == 0
+        ng = deck.ng
+        I = (slice(ng, -ng),) * 4
+        assert np.max(np.abs(out[I] - f[I])) > 1e-5
+        if mode == "strict":
+            assert np.array_equal(out[I], f_new[0][I])
+        else:
+            assert star_rel_err(out, f_new[0], np.maximum(np.abs(f), np.abs(f_new[0])), ng) <= 1e-12
+        H.lk_vp_destroy(sys_)
+        ok.ok_vp_work_destroy(w)
+    finally:
+        lk.lk_set_strict(old)

@@ -359,17 +359,21 @@ def test_pin_trig_tz_source(ok, ref, n, order, lo):
     xhi = -xlo
     dx = np.array(s.dx)
     lo2 = (C.c_int * 2)(data[0], data[2])
-    for time, amp in ((0.0, 1.0), (0.37, 0.1), (2.5, 1.0)):
-        base = np.random.default_rng(3).uniform(-1, 1, size=s.f.shape)
-        r1, r2 = base.copy(), base.copy()
-        ok.ok_set_trig_tz_source(r1.ravel(), C.byref(s.g), lo2, xlo, dx, time, s.velocities, amp)
-        R.L.settrigtzsource_(R._p(r2), *db, R._p(xlo), R._p(xhi), R._p(dx), R._d(time), R._p(s.velocities), R._p(np.array([amp])))
-        assert np.array_equal(r1, r2) and not np.array_equal(r1, base)
-        e1, e2 = np.zeros_like(base), np.zeros_like(base)
-        ok.ok_compute_trig_tz_source_error(e1.ravel(), s.f.ravel(), C.byref(s.g), lo2, xlo, dx, time, s.velocities, amp)
-        R.L.computetrigtzsourceerror_(R._p(e2), R._p(s.f), *db, R._p(xlo), R._p(xhi), R._p(dx), R._d(time), R._p(s.velocities),
-                                      R._p(np.array([amp])))
-        assert np.array_equal(e1, e2)
+    pairs = ((ok.ok_set_trig_tz_source, ok.ok_compute_trig_tz_source_error, R.L.settrigtzsource_, R.L.computetrigtzsourceerror_),
+             # ElectronTrigTZSource (ElectronTZSourceF.f): kx = ky = 4
+             (ok.ok_set_electron_trig_tz_source, ok.ok_compute_electron_trig_tz_source_error, R.L.setelectrontrigtzsource_,
+              R.L.computeelectrontrigtzsourceerror_))
+    for ok_set, ok_err, ref_set, ref_err in pairs:
+        for time, amp in ((0.0, 1.0), (0.37, 0.1), (2.5, 1.0)):
+            base = np.random.default_rng(3).uniform(-1, 1, size=s.f.shape)
+            r1, r2 = base.copy(), base.copy()
+            ok_set(r1.ravel(), C.byref(s.g), lo2, xlo, dx, time, s.velocities, amp)
+            ref_set(R._p(r2), *db, R._p(xlo), R._p(xhi), R._p(dx), R._d(time), R._p(s.velocities), R._p(np.array([amp])))
+            assert np.array_equal(r1, r2) and not np.array_equal(r1, base)
+            e1, e2 = np.zeros_like(base), np.zeros_like(base)
+            ok_err(e1.ravel(), s.f.ravel(), C.byref(s.g), lo2, xlo, dx, time, s.velocities, amp)
+            ref_err(R._p(e2), R._p(s.f), *db, R._p(xlo), R._p(xhi), R._p(dx), R._d(time), R._p(s.velocities), R._p(np.array([amp])))
+            assert np.array_equal(e1, e2)
 
 
 @needs_ref
