@@ -287,23 +287,25 @@ int lk_maxwell_set_vz_bcs(double* vz, int n1, int n2, int order, const int at[4]
 /* maxwellevalvzrhs_ (MaxwellF.f:442-469): dvz = (q/m) Ez on the interior of a (n1d,n2d) array */
 int lk_maxwell_vz_rhs(double* dvz, const double* em, int n1, int n2, int ng, double charge_per_mass, void* stream);
 
-/* TrigTZSource, the reference's twilight-zone (manufactured-solution) forcing: settrigtzsource_ /
- * computetrigtzsourceerror_ (TZSourceF.f:10-137; TrigTZSource.C:44-82; called from KineticSpecies::completeRHS,
- * KineticSpecies.C:1077-1080, and putToRestart, :987-1004).  f_exact = 1/(2 pi) exp(-v^2/2) (1 + amp cos x cos y sin t).
- * The source's transcendental factors are separable and time-independent except sin t / cos t: lk_trig_tz_tables builds
- * them on the HOST with libm (the Fortran's argument expressions; lo = global index of array cell 0 in x and y, xlo = the
- * domain's lower corner) and stores lk_trig_tz_table_count doubles on the device; the two kernels then evaluate the
- * Fortran's expression tree on those operands, so the result carries the reference's bits.  Both run over the whole
- * data box like the Fortran.  lk_trig_tz_tables synchronises.
- * kind 0 = TrigTZSource (kx = ky = 1); kind 1 = ElectronTrigTZSource, setelectrontrigtzsource_ /
- * computeelectrontrigtzsourceerror_ (ElectronTZSourceF.f:10-143, deck test/EPWTZ): the same solution with kx = ky = 4. */
+/* The reference's twilight-zone (manufactured-solution) forcings, called from KineticSpecies::completeRHS
+ * (KineticSpecies.C:1077-1080: source added to the rhs) and putToRestart (:987-1004: error against the exact solution):
+ *   kind 0  TrigTZSource                      settrigtzsource_ / computetrigtzsourceerror_ (TZSourceF.f:10-137), deck TrigTZ
+ *   kind 1  ElectronTrigTZSource              setelectrontrigtzsource_ / ...error_ (ElectronTZSourceF.f:10-143), deck EPWTZ
+ *   kind 2  TwoSpecies_ElectronTrigTZSource   settwoelectrontrigtzsource_ / ...error_ (TwoSpecies_ElectronTZSourceF.f), deck IAWTZ
+ *   kind 3  TwoSpecies_IonTrigTZSource        settwoiontrigtzsource_ / ...error_ (TwoSpecies_IonTZSourceF.f), deck IAWTZ
+ * params = the Fortran's dparams {amp, electron_mass, ion_mass} (the masses matter for kinds 2 / 3 only).
+ * The sources' transcendental factors are separable and time-independent except the sines / cosines of t:
+ * lk_trig_tz_tables builds them on the HOST with libm (the Fortran's argument expressions; lo = global index of array
+ * cell 0 in x and y, xlo = the domain's lower corner) and stores lk_trig_tz_table_count doubles on the device; the two
+ * kernels then evaluate the Fortran's expression tree on those operands, so the result carries the reference's bits.
+ * Both run over the whole data box like the Fortran.  lk_trig_tz_tables synchronises. */
 int lk_trig_tz_table_count(const lk_geom* g, int64_t* count);
 int lk_trig_tz_tables(double* tables, const lk_geom* g, const int lo[2], const double xlo[2], const double* velocities,
-                      int kind, void* stream);
-int lk_set_trig_tz_source(double* rhs, const lk_geom* g, const double* tables, const double* velocities, double time, double amp,
-                          int kind, void* stream);
+                      int kind, const double* params, void* stream);
+int lk_set_trig_tz_source(double* rhs, const lk_geom* g, const double* tables, const double* velocities, double time, int kind,
+                          const double* params, void* stream);
 int lk_compute_trig_tz_source_error(double* error, const double* soln, const lk_geom* g, const double* tables,
-                                    const double* velocities, double time, double amp, int kind, void* stream);
+                                    const double* velocities, double time, int kind, const double* params, void* stream);
 /* appendkrook_ (KineticSpeciesF.f:2995-3034; completeRHS, KineticSpecies.C:1049-1080): Krook-layer damping of an
  * UNFUSED rhs towards the initial condition, rhs -= nu(x,y)/dt * (u - IC) where nu != 0; nu: (n1d,n2d) device.
  * Level-0 only: the fused stage never materialises rhs, and no benchmark deck has a Krook layer. */

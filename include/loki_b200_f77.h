@@ -139,6 +139,22 @@ void computeelectrontrigtzsourceerror_(double* error, const double* soln, const 
                                        const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b,
                                        const double* xlo, const double* xhi, const double* dx, const double* time,
                                        const double* velocities, const double* dparams);
+/* TwoSpecies_ElectronTZSourceF.f:10-27, :165-183 and TwoSpecies_IonTZSourceF.f:10-27, :143-161 (called from
+ * TwoSpecies_ElectronTrigTZSource.C / TwoSpecies_IonTrigTZSource.C); dparams = {amp, electron_mass, ion_mass} */
+void settwoelectrontrigtzsource_(double* f, const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a,
+                                 const int* nd3b, const int* nd4a, const int* nd4b, const double* xlo, const double* xhi,
+                                 const double* dx, const double* time, const double* velocities, const double* dparams);
+void computetwoelectrontrigtzsourceerror_(double* error, const double* soln, const int* nd1a, const int* nd1b, const int* nd2a,
+                                          const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b,
+                                          const double* xlo, const double* xhi, const double* dx, const double* time,
+                                          const double* velocities, const double* dparams);
+void settwoiontrigtzsource_(double* f, const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a,
+                            const int* nd3b, const int* nd4a, const int* nd4b, const double* xlo, const double* xhi,
+                            const double* dx, const double* time, const double* velocities, const double* dparams);
+void computetwoiontrigtzsourceerror_(double* error, const double* soln, const int* nd1a, const int* nd1b, const int* nd2a,
+                                     const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b,
+                                     const double* xlo, const double* xhi, const double* dx, const double* time,
+                                     const double* velocities, const double* dparams);
 /* KineticSpeciesF.f:2995-3034 */
 void appendkrook_(const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a, const int* nd3b,
                   const int* nd4a, const int* nd4b, const int* n1a, const int* n1b, const int* n2a, const int* n2b,

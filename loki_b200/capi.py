@@ -130,9 +130,11 @@ _PROTOS = {
     "lk_maxwell_vz_rhs": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp]),
     "lk_f77_status": (C.c_int, []),
     "lk_trig_tz_table_count": (C.c_int, [C.POINTER(Geom), C.POINTER(C.c_int64)]),
-    "lk_trig_tz_tables": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(C.c_int * 2), C.POINTER(C.c_double * 2), _vp, C.c_int, _vp]),
-    "lk_set_trig_tz_source": (C.c_int, [_vp, C.POINTER(Geom), _vp, _vp, C.c_double, C.c_double, C.c_int, _vp]),
-    "lk_compute_trig_tz_source_error": (C.c_int, [_vp, _vp, C.POINTER(Geom), _vp, _vp, C.c_double, C.c_double, C.c_int, _vp]),
+    "lk_trig_tz_tables": (C.c_int, [_vp, C.POINTER(Geom), C.POINTER(C.c_int * 2), C.POINTER(C.c_double * 2), _vp, C.c_int,
+                                    C.POINTER(C.c_double * 3), _vp]),
+    "lk_set_trig_tz_source": (C.c_int, [_vp, C.POINTER(Geom), _vp, _vp, C.c_double, C.c_int, C.POINTER(C.c_double * 3), _vp]),
+    "lk_compute_trig_tz_source_error": (C.c_int, [_vp, _vp, C.POINTER(Geom), _vp, _vp, C.c_double, C.c_int,
+                                                  C.POINTER(C.c_double * 3), _vp]),
     "lk_zero_ghost_2d": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "lk_maxwell_add_antenna_source": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "lk_maxwell_set_em_bcs": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int * 4), C.c_int, C.c_int, C.c_double, _vp]),

@@ -246,20 +246,34 @@ cudaError_t append_krook(double* rhs, const double* u, const lk_geom* g, const d
   return cudaGetLastError();
 }
 
-// ---- TrigTZSource (TZSourceF.f:10-137): the twilight-zone source h(x, y, vx, vy, t) added to a right-hand side over the
-// whole data box, and error = soln - f_exact.  The transcendental factors are separable -- sin / cos of x (per i1), of y
-// (per i2), exp(-alpha v^2 / 2) (per (i3, i4)), sin t / cos t (scalars) -- and come from host tables built with libm, so
-// the kernel evaluates Maple's expression tree in the Fortran's parse order on the same operand bits (-fmad=false).
-// tab: {sin(kx x)[n1d], cos(kx x)[n1d], sin(ky y)[n2d], cos(ky y)[n2d], exp(..)[n3d n4d]}
-// kind 0: TrigTZSource (kx = ky = 1), kind 1: ElectronTrigTZSource (ElectronTZSourceF.f, kx = ky = 4, other term order)
-__global__ void k_trig_tz(Geo g, const double* __restrict__ tab, const double* __restrict__ velocities, double A, double st,
-                          double ct, double pi, const double* __restrict__ soln, double* __restrict__ out, int kind) {
-  const double kx = kind ? 4.0 : 1.0, ky = kx, kt = 1.0, alpha = 1.0;
-  const double* sx = tab;
-  const double* cx = sx + g.nd[0];
-  const double* sy = cx + g.nd[0];
-  const double* cy = sy + g.nd[1];
-  const double* ev = cy + g.nd[1];
+// ---- Twilight-zone sources (TZSourceF.f, ElectronTZSourceF.f, TwoSpecies_ElectronTZSourceF.f, TwoSpecies_IonTZSourceF.f):
+// the forcing h(x, y, vx, vy, t) added to a right-hand side over the whole data box, and error = soln - f_exact.  The
+// transcendental factors are separable -- sines / cosines of x (per i1) and of y (per i2) at the electron and the ion wave
+// numbers, exp(-alpha^2 v^2 / 2) (per (i3, i4)), sines / cosines of t (scalars) -- and come from host tables built with libm,
+// so the kernel evaluates Maple's expression trees in the Fortran's parse order on the same operand bits (-fmad=false).
+// kind 0 TrigTZSource (kx = ky = 1), 1 ElectronTrigTZSource (kx = ky = 4), 2 TwoSpecies_ElectronTrigTZSource,
+// 3 TwoSpecies_IonTrigTZSource (kxE = 4, kyE = 2, kxI = 2, kyI = 4; alpha = sqrt(mass)).
+// tab: {sin(kxE x), cos(kxE x), sin(kxI x), cos(kxI x)}[n1d] {sin(kyE y), cos(kyE y), sin(kyI y), cos(kyI y)}[n2d] exp(..)[n3d n4d];
+// kinds 0 / 1 use the "E" tables for their single wave number
+struct TzScalars {
+  double A, mass, alpha, ste, cte, sti, cti, pi;
+  int kind;
+};
+__device__ __forceinline__ double tz_powi2(double x) { return x * x; }
+__device__ __forceinline__ double tz_powi4(double x) { const double t = x * x; return t * t; }   // gfortran's x**4
+__global__ void k_trig_tz(Geo g, const double* __restrict__ tab, const double* __restrict__ velocities, TzScalars q,
+                          const double* __restrict__ soln, double* __restrict__ out) {
+  const int kind = q.kind;
+  const double* sxe_t = tab;
+  const double* cxe_t = sxe_t + g.nd[0];
+  const double* sxi_t = cxe_t + g.nd[0];
+  const double* cxi_t = sxi_t + g.nd[0];
+  const double* sye_t = cxi_t + g.nd[0];
+  const double* cye_t = sye_t + g.nd[1];
+  const double* syi_t = cye_t + g.nd[1];
+  const double* cyi_t = syi_t + g.nd[1];
+  const double* ev = cyi_t + g.nd[1];
+  const double a = q.A, pi = q.pi;
   const i64 total = (i64)g.nd[0] * g.nd[1] * g.nd[2] * g.nd[3];
   for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
     const int i1 = (int)(t % g.nd[0]);
@@ -269,67 +283,122 @@ __global__ void k_trig_tz(Geo g, const double* __restrict__ tab, const double* _
     const int i3 = (int)(r % g.nd[2]), i4 = (int)(r / g.nd[2]);
     const i64 pv = i3 + (i64)g.nd[2] * i4;
     const double vx = velocities[pv], vy = velocities[pv + (i64)g.nd[2] * g.nd[3]];
-    const double e = ev[pv], sinx = sx[i1], cosx = cx[i1], siny = sy[i2], cosy = cy[i2];
-    if (soln) {
-      const double fexact = alpha / pi * e * (0.1e1 + A * cosx * cosy * st) / 0.2e1;
-      out[t] = soln[t] - fexact;
-    } else if (kind) {
-      const double h =
-          alpha / pi * e * A * cosx * cosy * kt * ct / 0.2e1 - vx * alpha / pi * e * A * kx * sinx * cosy * st / 0.2e1 -
-          vy * alpha / pi * e * A * cosx * ky * siny * st / 0.2e1 -
-          A * kx * sinx * cosy * st / (kx * kx + ky * ky) * (alpha * alpha) / pi * vx * e * (0.1e1 + A * cosx * cosy * st) / 0.2e1 -
-          A * cosx * ky * siny * st / (kx * kx + ky * ky) * (alpha * alpha) / pi * vy * e * (0.1e1 + A * cosx * cosy * st) / 0.2e1;
-      out[t] = out[t] + h;
+    const double e = ev[pv];
+    if (kind < 2) {
+      const double kx = kind ? 4.0 : 1.0, ky = kx, kt = 1.0, alpha = 1.0;
+      const double sinx = sxe_t[i1], cosx = cxe_t[i1], siny = sye_t[i2], cosy = cye_t[i2], st = q.ste, ct = q.cte;
+      if (soln) {
+        const double fexact = alpha / pi * e * (0.1e1 + a * cosx * cosy * st) / 0.2e1;
+        out[t] = soln[t] - fexact;
+      } else if (kind) {
+        const double h =
+            alpha / pi * e * a * cosx * cosy * kt * ct / 0.2e1 - vx * alpha / pi * e * a * kx * sinx * cosy * st / 0.2e1 -
+            vy * alpha / pi * e * a * cosx * ky * siny * st / 0.2e1 -
+            a * kx * sinx * cosy * st / (kx * kx + ky * ky) * (alpha * alpha) / pi * vx * e * (0.1e1 + a * cosx * cosy * st) / 0.2e1 -
+            a * cosx * ky * siny * st / (kx * kx + ky * ky) * (alpha * alpha) / pi * vy * e * (0.1e1 + a * cosx * cosy * st) / 0.2e1;
+        out[t] = out[t] + h;
+      } else {
+        const double h =
+            -0.1e1 / (kx * kx + ky * ky) * a * sinx * kx * cosy * st * (alpha * alpha) / pi * vx * e * (0.1e1 + a * cosx * cosy * st) / 0.2e1 -
+            0.1e1 / (kx * kx + ky * ky) * a * cosx * siny * ky * st * (alpha * alpha) / pi * vy * e * (0.1e1 + a * cosx * cosy * st) / 0.2e1 -
+            alpha / pi * e * a * sinx * kx * cosy * st * vx / 0.2e1 - alpha / pi * e * a * cosx * siny * ky * st * vy / 0.2e1 +
+            alpha / pi * e * a * cosx * cosy * ct * kt / 0.2e1;
+        out[t] = out[t] + h;
+      }
+      continue;
+    }
+    // the two-species sources (TwoSpecies_ElectronTZSourceF.f:134-152, :245-247; TwoSpecies_IonTZSourceF.f:112-129, :221-223)
+    const double kxi = 0.2e1, kyi = 0.4e1, kti = 0.1e1, kxe = 0.4e1, kye = 0.2e1, kte = 0.1e1;
+    const double kI2 = tz_powi2(kxi) + tz_powi2(kyi), kE2 = tz_powi2(kxe) + tz_powi2(kye);
+    const double sxe = sxe_t[i1], cxe = cxe_t[i1], sxi = sxi_t[i1], cxi = cxi_t[i1];
+    const double sye = sye_t[i2], cye = cye_t[i2], syi = syi_t[i2], cyi = cyi_t[i2];
+    const double ste = q.ste, cte = q.cte, sti = q.sti, cti = q.cti, m = q.mass;
+    const double al2 = tz_powi2(q.alpha), al4 = tz_powi4(q.alpha);
+    if (kind == 2) {
+      const double wave = 0.1e1 + (((a * cxe) * cye) * ste);
+      if (soln) {
+        out[t] = soln[t] - ((((al2 / pi) * e) * wave) / 0.2e1);
+        continue;
+      }
+      const double T1 = (((((((al2 / pi) * e) * a) * cxe) * cye) * kte) * cte) / 0.2e1;
+      const double T2 = ((((((((vx * al2) / pi) * e) * a) * kxe) * sxe) * cye) * ste) / 0.2e1;
+      const double T3 = ((((((((vy * al2) / pi) * e) * a) * cxe) * kye) * sye) * ste) / 0.2e1;
+      const double T4 = ((((((((((0.1e1 / m) * (((((ste * sxe) * kxe) * kI2) * cye) - (((((0.2e1 * cyi) * sti) * sxi) * kxi) * kE2))) * a) / kI2) / kE2) * al4) / pi) * vx) * e) * wave) / 0.2e1;
+      const double T5 = ((((((((((0.1e1 / m) * a) * (((((ste * sye) * kye) * kI2) * cxe) - (((((0.2e1 * kyi) * cxi) * sti) * syi) * kE2))) / kI2) / kE2) * al4) / pi) * vy) * e) * wave) / 0.2e1;
+      out[t] = out[t] + ((((T1 - T2) - T3) - T4) - T5);
     } else {
-      const double h =
-          -0.1e1 / (kx * kx + ky * ky) * A * sinx * kx * cosy * st * (alpha * alpha) / pi * vx * e * (0.1e1 + A * cosx * cosy * st) / 0.2e1 -
-          0.1e1 / (kx * kx + ky * ky) * A * cosx * siny * ky * st * (alpha * alpha) / pi * vy * e * (0.1e1 + A * cosx * cosy * st) / 0.2e1 -
-          alpha / pi * e * A * sinx * kx * cosy * st * vx / 0.2e1 - alpha / pi * e * A * cosx * siny * ky * st * vy / 0.2e1 +
-          alpha / pi * e * A * cosx * cosy * ct * kt / 0.2e1;
-      out[t] = out[t] + h;
+      const double wave = 0.1e1 + ((((0.2e1 * a) * cxi) * cyi) * sti);
+      if (soln) {
+        out[t] = soln[t] - ((((al2 / pi) * e) * wave) / 0.2e1);
+        continue;
+      }
+      const double U1 = ((((((al2 / pi) * e) * a) * cxi) * cyi) * kti) * cti;
+      const double U2 = (((((((vx * al2) / pi) * e) * a) * kxi) * sxi) * cyi) * sti;
+      const double U3 = (((((((vy * al2) / pi) * e) * a) * cxi) * kyi) * syi) * sti;
+      const double U4 = ((((((((((0.1e1 / m) * (((((ste * sxe) * kxe) * kI2) * cye) - (((((0.2e1 * cyi) * sti) * sxi) * kxi) * kE2))) * a) / kI2) / kE2) * al4) / pi) * vx) * e) * wave) / 0.2e1;
+      const double U5 = ((((((((((0.1e1 / m) * a) * (((((ste * sye) * kye) * kI2) * cxe) - (((((0.2e1 * kyi) * cxi) * sti) * syi) * kE2))) / kI2) / kE2) * al4) / pi) * vy) * e) * wave) / 0.2e1;
+      out[t] = out[t] + ((((U1 - U2) - U3) + U4) + U5);
     }
   }
 }
 
+// params = {amp, electron_mass, ion_mass} (dparams of the Fortran; the masses only matter for kinds 2 / 3)
+static double tz_alpha(int kind, const double* params) {
+  return kind == 2 ? sqrt(params[1]) : kind == 3 ? sqrt(params[2]) : 1.0;
+}
 // host side of the tables: libm, the Fortran's argument expressions; vel_host: (n3d, n4d, 2)
-void trig_tz_tables(double* tab, const lk_geom* g, const int lo[2], const double xlo[2], const double* vel_host, int kind) {
-  const double kx = kind ? 4.0 : 1.0, ky = kx, alpha = 1.0;
+void trig_tz_tables(double* tab, const lk_geom* g, const int lo[2], const double xlo[2], const double* vel_host, int kind,
+                    const double* params) {
+  const double kxe = kind >= 2 ? 0.4e1 : (kind ? 4.0 : 1.0), kye = kind >= 2 ? 0.2e1 : kxe, kxi = 0.2e1, kyi = 0.4e1;
   const int n1d = g->n[0] + 2 * g->ng, n2d = g->n[1] + 2 * g->ng, n3d = g->n[2] + 2 * g->ng, n4d = g->n[3] + 2 * g->ng;
-  double* sx = tab;
-  double* cx = sx + n1d;
-  double* sy = cx + n1d;
-  double* cy = sy + n2d;
-  double* ev = cy + n2d;
+  double* xs = tab;
+  double* ys = tab + 4 * (size_t)n1d;
+  double* ev = ys + 4 * (size_t)n2d;
   for (int i1 = 0; i1 < n1d; ++i1) {
     const double x = xlo[0] + ((lo[0] + i1) + 0.5) * g->dx[0];
-    sx[i1] = sin(kx * x);
-    cx[i1] = cos(kx * x);
+    xs[i1] = sin(kxe * x);
+    xs[n1d + i1] = cos(kxe * x);
+    xs[2 * n1d + i1] = kind >= 2 ? sin(kxi * x) : 0.0;
+    xs[3 * n1d + i1] = kind >= 2 ? cos(kxi * x) : 0.0;
   }
   for (int i2 = 0; i2 < n2d; ++i2) {
     const double y = xlo[1] + ((lo[1] + i2) + 0.5) * g->dx[1];
-    sy[i2] = sin(ky * y);
-    cy[i2] = cos(ky * y);
+    ys[i2] = sin(kye * y);
+    ys[n2d + i2] = cos(kye * y);
+    ys[2 * n2d + i2] = kind >= 2 ? sin(kyi * y) : 0.0;
+    ys[3 * n2d + i2] = kind >= 2 ? cos(kyi * y) : 0.0;
   }
+  const double alpha = tz_alpha(kind, params);
   for (i64 pv = 0; pv < (i64)n3d * n4d; ++pv) {
     const double vx = vel_host[pv], vy = vel_host[pv + (i64)n3d * n4d];
-    ev[pv] = exp(-(alpha * (vx * vx + vy * vy) / 0.2e1));
+    // kinds 0 / 1: exp(-alpha * v^2 / 2) with alpha = 1; kinds 2 / 3: exp(-alpha**2 * v^2 / 2)
+    ev[pv] = kind >= 2 ? exp(-((alpha * alpha) * (vx * vx + vy * vy) / 0.2e1)) : exp(-(alpha * (vx * vx + vy * vy) / 0.2e1));
   }
 }
 size_t trig_tz_table_count(const lk_geom* g) {
   const size_t n1d = g->n[0] + 2 * g->ng, n2d = g->n[1] + 2 * g->ng, n3d = g->n[2] + 2 * g->ng, n4d = g->n[3] + 2 * g->ng;
-  return 2 * n1d + 2 * n2d + n3d * n4d;
+  return 4 * n1d + 4 * n2d + n3d * n4d;
 }
 
 // out += h (soln == nullptr) or out = soln - f_exact; tab_dev: trig_tz_tables on the device
 cudaError_t trig_tz(double* out, const double* soln, const lk_geom* g, const double* tab_dev, const double* velocities,
-                    double time, double amp, int kind, cudaStream_t st, int64_t* launches) {
+                    double time, int kind, const double* params, cudaStream_t st, int64_t* launches) {
   Geo d = make_geo(g);
-  const double kt = 1.0;
-  const double pi = 4.0 * atan(1.0);
+  TzScalars q;
+  q.kind = kind;
+  q.A = params[0];
+  q.mass = kind == 2 ? params[1] : kind == 3 ? params[2] : 1.0;
+  q.alpha = tz_alpha(kind, params);
+  q.pi = 4.0 * atan(1.0);
+  const double kte = 1.0, kti = 1.0;
+  q.ste = sin(kte * time);
+  q.cte = cos(kte * time);
+  q.sti = sin(kti * time);
+  q.cti = cos(kti * time);
   const i64 total = (i64)d.nd[0] * d.nd[1] * d.nd[2] * d.nd[3];
   i64 blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_trig_tz<<<(unsigned)blocks, 256, 0, st>>>(d, tab_dev, velocities, amp, sin(kt * time), cos(kt * time), pi, soln, out, kind);
+  k_trig_tz<<<(unsigned)blocks, 256, 0, st>>>(d, tab_dev, velocities, q, soln, out);
   ++*launches;
   return cudaGetLastError();
 }

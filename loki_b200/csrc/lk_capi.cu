@@ -125,10 +125,11 @@ cudaError_t set_bcs_jb(double* f, const lk_geom* g, const lk_accel* a, const dou
                        const int sides[8], cudaStream_t st, int64_t* launches);
 }
 namespace lkbcs {
-void trig_tz_tables(double* tab, const lk_geom* g, const int lo[2], const double xlo[2], const double* vel_host, int kind);
+void trig_tz_tables(double* tab, const lk_geom* g, const int lo[2], const double xlo[2], const double* vel_host, int kind,
+                    const double* params);
 size_t trig_tz_table_count(const lk_geom* g);
 cudaError_t trig_tz(double* out, const double* soln, const lk_geom* g, const double* tab_dev, const double* velocities,
-                    double time, double amp, int kind, cudaStream_t st, int64_t* launches);
+                    double time, int kind, const double* params, cudaStream_t st, int64_t* launches);
 }
 namespace lkbcs {
 cudaError_t zero_ghost_2d(double* u, int n1, int n2, int ng, int dim, cudaStream_t st, int64_t* launches);
@@ -284,33 +285,39 @@ int lk_trig_tz_table_count(const lk_geom* g, int64_t* count) {
   *count = (int64_t)lkbcs::trig_tz_table_count(g);
   return LK_OK;
 }
+static bool tz_args_ok(int kind, const double* params) {
+  if (kind < 0 || kind > 3 || !params) return false;
+  if (kind == 2 && !(params[1] > 0.0)) return false;
+  if (kind == 3 && !(params[2] > 0.0)) return false;
+  return true;
+}
 int lk_trig_tz_tables(double* tables, const lk_geom* g, const int lo[2], const double xlo[2], const double* velocities,
-                      int kind, void* stream) {
+                      int kind, const double* params, void* stream) {
   // the time-independent factors of the source, built on the host with libm and left on the device in `tables`
-  if (!geom_ok(g) || !tables || !lo || !xlo || !velocities || (kind != 0 && kind != 1))
+  if (!geom_ok(g) || !tables || !lo || !xlo || !velocities || !tz_args_ok(kind, params))
     return fail(LK_ERR_ARG, "lk_trig_tz_tables: bad argument");
   const size_t nv = (size_t)(g->n[2] + 2 * g->ng) * (g->n[3] + 2 * g->ng) * 2;
   std::vector<double> vel(nv), tab(lkbcs::trig_tz_table_count(g));
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   if (e == cudaSuccess) e = cudaMemcpy(vel.data(), velocities, sizeof(double) * nv, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return cuda_fail(e, "lk_trig_tz_tables");
-  lkbcs::trig_tz_tables(tab.data(), g, lo, xlo, vel.data(), kind);
+  lkbcs::trig_tz_tables(tab.data(), g, lo, xlo, vel.data(), kind, params);
   e = cudaMemcpy(tables, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return cuda_fail(e, "lk_trig_tz_tables");
   return LK_OK;
 }
-int lk_set_trig_tz_source(double* rhs, const lk_geom* g, const double* tables, const double* velocities, double time, double amp,
-                          int kind, void* stream) {
-  if (!geom_ok(g) || !rhs || !tables || !velocities || (kind != 0 && kind != 1))
+int lk_set_trig_tz_source(double* rhs, const lk_geom* g, const double* tables, const double* velocities, double time, int kind,
+                          const double* params, void* stream) {
+  if (!geom_ok(g) || !rhs || !tables || !velocities || !tz_args_ok(kind, params))
     return fail(LK_ERR_ARG, "lk_set_trig_tz_source: bad argument");
-  CHECK_LAUNCH(lkbcs::trig_tz(rhs, nullptr, g, tables, velocities, time, amp, kind, (cudaStream_t)stream, &g_fft_launches),
+  CHECK_LAUNCH(lkbcs::trig_tz(rhs, nullptr, g, tables, velocities, time, kind, params, (cudaStream_t)stream, &g_fft_launches),
                "lk_set_trig_tz_source");
 }
 int lk_compute_trig_tz_source_error(double* error, const double* soln, const lk_geom* g, const double* tables,
-                                    const double* velocities, double time, double amp, int kind, void* stream) {
-  if (!geom_ok(g) || !error || !soln || !tables || !velocities || (kind != 0 && kind != 1))
+                                    const double* velocities, double time, int kind, const double* params, void* stream) {
+  if (!geom_ok(g) || !error || !soln || !tables || !velocities || !tz_args_ok(kind, params))
     return fail(LK_ERR_ARG, "lk_compute_trig_tz_source_error: bad argument");
-  CHECK_LAUNCH(lkbcs::trig_tz(error, soln, g, tables, velocities, time, amp, kind, (cudaStream_t)stream, &g_fft_launches),
+  CHECK_LAUNCH(lkbcs::trig_tz(error, soln, g, tables, velocities, time, kind, params, (cudaStream_t)stream, &g_fft_launches),
                "lk_compute_trig_tz_source_error");
 }
 int lk_append_krook(double* rhs, const double* u, const lk_geom* g, const double* nu, double dt, const lk_inflow* ic, void* stream) {

@@ -409,71 +409,48 @@ void computekevelspaceflux_(const int* nd1a, const int* nd1b, const int* nd2a, c
   check(cudaDeviceSynchronize() == cudaSuccess ? LK_OK : LK_ERR_CUDA);
 }
 
-// settrigtzsource_ / computetrigtzsourceerror_ (TZSourceF.f:10-27, :79-97): only the data box is passed; the kernels run
-// over all of it, so the split into interior and ghosts does not matter (order 4's is assumed).  f, soln, error and
-// velocities are device arrays; xlo, xhi, dx, dparams are the host-side heads PROBLEMDOMAIN_TO_FORT passes.
-static bool tz_tables(const char* who, const int* const nd[8], const double* xlo, const double* dx, const double* velocities,
-                      lk_geom* g, double** tab, int kind) {
-  if (!geom_from_data(who, nd, 4, dx, g)) return false;
+// The twilight-zone routines (TZSourceF.f, ElectronTZSourceF.f, TwoSpecies_ElectronTZSourceF.f, TwoSpecies_IonTZSourceF.f)
+// share one argument list; only the data box is passed and the kernels run over all of it, so the split into interior and
+// ghosts does not matter (order 4's is assumed).  f, soln, error and velocities are device arrays; xlo, xhi, dx, dparams
+// are the host-side heads PROBLEMDOMAIN_TO_FORT and the source classes pass.
+static void tz_call(const char* who, int kind, double* out, const double* soln, const int* const nd[8], const double* xlo,
+                    const double* dx, const double* time, const double* velocities, const double* dparams) {
+  lk_geom g;
+  if (!geom_from_data(who, nd, 4, dx, &g)) return;
+  const double params[3] = {dparams[0], kind >= 2 ? dparams[1] : 1.0, kind >= 2 ? dparams[2] : 1.0};
   int64_t count = 0;
-  if (!check(lk_trig_tz_table_count(g, &count))) return false;
-  if (!check(lk_malloc((void**)tab, sizeof(double) * count))) return false;
+  if (!check(lk_trig_tz_table_count(&g, &count))) return;
+  double* tab = nullptr;
+  if (!check(lk_malloc((void**)&tab, sizeof(double) * count))) return;
   const int lo[2] = {*nd[0], *nd[2]};
   const double x0[2] = {xlo[0], xlo[1]};
-  if (!check(lk_trig_tz_tables(*tab, g, lo, x0, velocities, kind, nullptr))) {
-    lk_free(*tab);
-    return false;
+  if (check(lk_trig_tz_tables(tab, &g, lo, x0, velocities, kind, params, nullptr))) {
+    const int st = soln ? lk_compute_trig_tz_source_error(out, soln, &g, tab, velocities, *time, kind, params, nullptr)
+                        : lk_set_trig_tz_source(out, &g, tab, velocities, *time, kind, params, nullptr);
+    if (check(st)) check(lk_sync(nullptr));
   }
-  return true;
-}
-void settrigtzsource_(double* f, const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a,
-                      const int* nd3b, const int* nd4a, const int* nd4b, const double* xlo, const double* xhi, const double* dx,
-                      const double* time, const double* velocities, const double* dparams) {
-  (void)xhi;
-  const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
-  lk_geom g;
-  double* tab = nullptr;
-  if (!tz_tables("settrigtzsource_", nd, xlo, dx, velocities, &g, &tab, 0)) return;
-  if (check(lk_set_trig_tz_source(f, &g, tab, velocities, *time, dparams[0], 0, nullptr))) check(lk_sync(nullptr));
   lk_free(tab);
 }
-void computetrigtzsourceerror_(double* error, const double* soln, const int* nd1a, const int* nd1b, const int* nd2a,
-                               const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b,
-                               const double* xlo, const double* xhi, const double* dx, const double* time,
-                               const double* velocities, const double* dparams) {
-  (void)xhi;
-  const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
-  lk_geom g;
-  double* tab = nullptr;
-  if (!tz_tables("computetrigtzsourceerror_", nd, xlo, dx, velocities, &g, &tab, 0)) return;
-  if (check(lk_compute_trig_tz_source_error(error, soln, &g, tab, velocities, *time, dparams[0], 0, nullptr))) check(lk_sync(nullptr));
-  lk_free(tab);
-}
-
-// ElectronTZSourceF.f:10-27, :79-97: the same argument lists, kx = ky = 4
-void setelectrontrigtzsource_(double* f, const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a,
-                              const int* nd3b, const int* nd4a, const int* nd4b, const double* xlo, const double* xhi,
-                              const double* dx, const double* time, const double* velocities, const double* dparams) {
-  (void)xhi;
-  const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
-  lk_geom g;
-  double* tab = nullptr;
-  if (!tz_tables("setelectrontrigtzsource_", nd, xlo, dx, velocities, &g, &tab, 1)) return;
-  if (check(lk_set_trig_tz_source(f, &g, tab, velocities, *time, dparams[0], 1, nullptr))) check(lk_sync(nullptr));
-  lk_free(tab);
-}
-void computeelectrontrigtzsourceerror_(double* error, const double* soln, const int* nd1a, const int* nd1b, const int* nd2a,
-                                       const int* nd2b, const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b,
-                                       const double* xlo, const double* xhi, const double* dx, const double* time,
-                                       const double* velocities, const double* dparams) {
-  (void)xhi;
-  const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};
-  lk_geom g;
-  double* tab = nullptr;
-  if (!tz_tables("computeelectrontrigtzsourceerror_", nd, xlo, dx, velocities, &g, &tab, 1)) return;
-  if (check(lk_compute_trig_tz_source_error(error, soln, &g, tab, velocities, *time, dparams[0], 1, nullptr))) check(lk_sync(nullptr));
-  lk_free(tab);
-}
+#define LK_TZ_PAIR(set_name, err_name, kind)                                                                                  \
+  void set_name(double* f, const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a,               \
+                const int* nd3b, const int* nd4a, const int* nd4b, const double* xlo, const double* xhi, const double* dx,    \
+                const double* time, const double* velocities, const double* dparams) {                                        \
+    (void)xhi;                                                                                                                \
+    const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};                                                \
+    tz_call(#set_name, kind, f, nullptr, nd, xlo, dx, time, velocities, dparams);                                            \
+  }                                                                                                                           \
+  void err_name(double* error, const double* soln, const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b,        \
+                const int* nd3a, const int* nd3b, const int* nd4a, const int* nd4b, const double* xlo, const double* xhi,     \
+                const double* dx, const double* time, const double* velocities, const double* dparams) {                      \
+    (void)xhi;                                                                                                                \
+    const int* const nd[8] = {nd1a, nd1b, nd2a, nd2b, nd3a, nd3b, nd4a, nd4b};                                                \
+    tz_call(#err_name, kind, error, soln, nd, xlo, dx, time, velocities, dparams);                                           \
+  }
+LK_TZ_PAIR(settrigtzsource_, computetrigtzsourceerror_, 0)
+LK_TZ_PAIR(setelectrontrigtzsource_, computeelectrontrigtzsourceerror_, 1)
+LK_TZ_PAIR(settwoelectrontrigtzsource_, computetwoelectrontrigtzsourceerror_, 2)
+LK_TZ_PAIR(settwoiontrigtzsource_, computetwoiontrigtzsourceerror_, 3)
+#undef LK_TZ_PAIR
 
 void appendkrook_(const int* nd1a, const int* nd1b, const int* nd2a, const int* nd2b, const int* nd3a, const int* nd3b,
                   const int* nd4a, const int* nd4b, const int* n1a, const int* n1b, const int* n2a, const int* n2b,

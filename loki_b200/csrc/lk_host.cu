@@ -221,8 +221,8 @@ struct KineticSpecies {
   bool has_coll = false;
   // TrigTZSource (KineticSpecies.C:1077-1080): the manufactured-solution forcing; tables of lk_trig_tz_tables
   bool has_tz = false;
-  int tz_kind = 0;   // 0 TrigTZSource, 1 ElectronTrigTZSource
-  double tz_amp = 0.0;
+  int tz_kind = 0;   // 0 TrigTZSource, 1 ElectronTrigTZSource, 2 / 3 TwoSpecies_Electron / IonTrigTZSource
+  double tz_params[3] = {0.0, 1.0, 1.0};   // the Fortran's dparams: amp, electron_mass, ion_mass
   DevBuf<double> tz_tab;
   lk_pitch_angle coll;
   DevBuf<double> coll_iv;
@@ -688,7 +688,7 @@ struct VPSystem {
         LKH_CHECK(lk_vlasov_rhs(rhs_out, ks->f_eval, &ks->g, ks->velocities.p, &a, nullptr, st));
         if (ks->has_coll) LKH_CHECK(ks->appendCollision(rhs_out, ks->f_eval, st));
         if (ks->has_krook) LKH_CHECK(lk_append_krook(rhs_out, ks->f_eval, &ks->g, ks->krook_nu.p, dt, &ks->inflow, st));
-        if (ks->has_tz) LKH_CHECK(lk_set_trig_tz_source(rhs_out, &ks->g, ks->tz_tab.p, ks->velocities.p, t_stage, ks->tz_amp, ks->tz_kind, st));
+        if (ks->has_tz) LKH_CHECK(lk_set_trig_tz_source(rhs_out, &ks->g, ks->tz_tab.p, ks->velocities.p, t_stage, ks->tz_kind, ks->tz_params, st));
         LKH_CHECK(lk_rk_stage_update(rhs_out, &ks->g, &u, st));
       } else {
         const int ie = ks->arrayIndex(ks->f_eval);
@@ -814,7 +814,7 @@ struct VPSystem {
       LKH_CHECK(lk_acceleration_derivatives_4d(rhs_dev[s], f, &ks->g, &a, st));
       if (ks->has_coll) LKH_CHECK(ks->appendCollision(rhs_dev[s], f, st));
       if (ks->has_krook) LKH_CHECK(lk_append_krook(rhs_dev[s], f, &ks->g, ks->krook_nu.p, dt, &ks->inflow, st));
-      if (ks->has_tz) LKH_CHECK(lk_set_trig_tz_source(rhs_dev[s], &ks->g, ks->tz_tab.p, ks->velocities.p, t, ks->tz_amp, ks->tz_kind, st));
+      if (ks->has_tz) LKH_CHECK(lk_set_trig_tz_source(rhs_dev[s], &ks->g, ks->tz_tab.p, ks->velocities.p, t, ks->tz_kind, ks->tz_params, st));
       if (ks->has_driver)
         LKH_CHECK(lk_ke_e_dot(ks->ke.p + 3, f, &ks->g, ks->charge, ks->velocities.p, ks->ext_efield.p, st));
     }
@@ -1545,26 +1545,27 @@ int lk_vp_ke_e_dot(lk_vp_system* h, int s, double* value) {
   return LK_OK;
 }
 
-int lk_vp_set_trig_tz(lk_vp_system* h, int s, int on, double amp) {
-  // kinetic_species.N.tz.name = "TrigTZSource", tz.amp (TrigTZSource.C:21-42): the forcing of completeRHS
+int lk_vp_set_trig_tz(lk_vp_system* h, int s, int on, double amp, double electron_mass, double ion_mass) {
+  // kinetic_species.N.tz.name / tz.amp / tz.electron_mass / tz.ion_mass (TZSourceFactory.C:22-56): the forcing of completeRHS
   if (!h || s < 0 || s >= (int)h->sys.species.size()) return LK_ERR_ARG;
   auto& S = h->sys;
   auto* ks = S.species[s];
   ks->has_tz = false;
   if (!on) return LK_OK;
-  if (on != 1 && on != 2) return LK_ERR_ARG;
+  if (on < 1 || on > 4) return LK_ERR_ARG;
   const int kind = on - 1;
+  const double params[3] = {amp, kind >= 2 ? electron_mass : 1.0, kind >= 2 ? ion_mass : 1.0};
   int64_t count = 0;
   int st = lk_trig_tz_table_count(&ks->g, &count);
   if (st != LK_OK) return st;
   st = ks->tz_tab.alloc((size_t)count);
   if (st != LK_OK) return st;
   const int lo[2] = {S.desc.tile_lo[0] - ks->g.ng, S.desc.tile_lo[1] - ks->g.ng};
-  st = lk_trig_tz_tables(ks->tz_tab.p, &ks->g, lo, S.desc.xlo, ks->velocities.p, kind, S.st);
+  st = lk_trig_tz_tables(ks->tz_tab.p, &ks->g, lo, S.desc.xlo, ks->velocities.p, kind, params, S.st);
   if (st != LK_OK) return st;
   ks->has_tz = true;
   ks->tz_kind = kind;
-  ks->tz_amp = amp;
+  for (int k = 0; k < 3; ++k) ks->tz_params[k] = params[k];
   return LK_OK;
 }
 int lk_vp_trig_tz_error(lk_vp_system* h, int s, double time, double* error_host) {
@@ -1575,7 +1576,7 @@ int lk_vp_trig_tz_error(lk_vp_system* h, int s, double time, double* error_host)
   auto* ks = S.species[s];
   if (!ks->has_tz) return LK_ERR_ARG;
   if (!ks->rhs_tmp.p) LKH_CHECK(ks->rhs_tmp.alloc(ks->vol));
-  LKH_CHECK(lk_compute_trig_tz_source_error(ks->rhs_tmp.p, ks->state(), &ks->g, ks->tz_tab.p, ks->velocities.p, time, ks->tz_amp, ks->tz_kind, S.st));
+  LKH_CHECK(lk_compute_trig_tz_source_error(ks->rhs_tmp.p, ks->state(), &ks->g, ks->tz_tab.p, ks->velocities.p, time, ks->tz_kind, ks->tz_params, S.st));
   LKH_CUDA(cudaStreamSynchronize(S.st));
   LKH_CUDA(cudaMemcpy(error_host, ks->rhs_tmp.p, sizeof(double) * ks->vol, cudaMemcpyDeviceToHost));
   return LK_OK;

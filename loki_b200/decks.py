@@ -28,7 +28,8 @@ class Species:
         # "External 2D" initial condition (External2DIC.C): `external` = the file's "2D dist" dataset, the spatial factor
         # of the WHOLE configuration space with its ghost layers, (Ny + 2 ng, Nx + 2 ng); `external_frac` = ic.frac
         self.external, self.external_frac = None, 1.0
-        # a twilight-zone source: Species.tz = dict(amp=, kind= 1 TrigTZSource | 2 ElectronTrigTZSource) adds the
+        # a twilight-zone source: Species.tz = dict(amp=, kind= 1 TrigTZSource | 2 ElectronTrigTZSource |
+        # 3 TwoSpecies_ElectronTrigTZSource | 4 TwoSpecies_IonTrigTZSource[, electron_mass=, ion_mass=]) adds the
         # manufactured-solution forcing to the rhs
         self.tz = None
         # "Interpenetrating Stream" initial condition, half-plane syntax (InterpenetratingStreamIC.C:496-540):
@@ -114,7 +115,8 @@ class Deck:
                 st = H.lk_vp_set_pitch_angle(sys_, s, pa)
             tz = getattr(sp, "tz", None)
             if st == 0 and tz:
-                st = H.lk_vp_set_trig_tz(sys_, s, int(tz.get("kind", 1)), float(tz["amp"]))
+                st = H.lk_vp_set_trig_tz(sys_, s, int(tz.get("kind", 1)), float(tz["amp"]), float(tz.get("electron_mass", 1.0)),
+                                         float(tz.get("ion_mass", 1.0)))
         return st
 
     def geom_of(self, sp):

@@ -77,7 +77,7 @@ _PROTOS = {
     "lk_vp_em_vars_ptr": (_vp, [_vp]),
     "lk_vp_rho_ptr": (_vp, [_vp]),
     "lk_vp_ke_e_dot": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
-    "lk_vp_set_trig_tz": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double]),
+    "lk_vp_set_trig_tz": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
     "lk_vp_trig_tz_error": (C.c_int, [_vp, C.c_int, C.c_double, _vp]),
     "lk_vp_update_ghosts": (C.c_int, [_vp]),
     "lk_vp_set_ke_e_dot": (C.c_int, [_vp, C.c_int, C.c_double]),

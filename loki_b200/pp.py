@@ -192,16 +192,24 @@ def _species(params, k):
         raise ValueError("species %d: Krook layer needs a positive power and a non-negative coefficient" % k)   # KrookLayer.C:195-201
     if not any(e in krook for e in ("x1a", "x1b", "x2a", "x2b")):
         krook = None
-    # TZSourceFactory::create (TZSourceFactory.C:22-56): the twilight-zone (manufactured-solution) forcing; TrigTZSource
-    # (one species, TrigTZSource.C:21-42) is implemented, the two-species ion-acoustic sources are not
+    # TZSourceFactory::create (TZSourceFactory.C:22-56): the twilight-zone (manufactured-solution) forcings of the
+    # reference's TrigTZ, EPWTZ and IAWTZ decks
     tz = None
     if (pre + "tz.name") in params:
         tzname = _s(params, pre + "tz.name")
-        if tzname not in ("TrigTZSource", "ElectronTrigTZSource"):
-            raise ValueError("species %d: twilight-zone source %r is not supported (only TrigTZSource / ElectronTrigTZSource)" % (k, tzname))
+        kinds = {"TrigTZSource": 1, "ElectronTrigTZSource": 2, "TwoSpecies_ElectronTrigTZSource": 3,
+                 "TwoSpecies_IonTrigTZSource": 4}
+        if tzname not in kinds:
+            raise ValueError("species %d: twilight-zone source %r is not supported" % (k, tzname))
         if (pre + "tz.amp") not in params:
             raise ValueError("Must supply amp")                                   # TrigTZSource.C:28-31
-        tz = dict(amp=_f(params, pre + "tz.amp"), kind=1 if tzname == "TrigTZSource" else 2)
+        tz = dict(amp=_f(params, pre + "tz.amp"), kind=kinds[tzname])
+        if kinds[tzname] >= 3:
+            # TwoSpecies_ElectronTrigTZSource.C:28-41: amp, electron_mass and ion_mass are all required
+            for key in ("electron_mass", "ion_mass"):
+                if (pre + "tz." + key) not in params:
+                    raise ValueError("Must supply " + key.replace("_", " "))
+                tz[key] = _f(params, pre + "tz." + key)
     elif any(key.startswith(pre + "tz.") for key in list(params.keys())):
         raise ValueError("species %d: tz.* keys without tz.name" % k)
     if icn == "Perturbed Maxwellian":

@@ -39,6 +39,8 @@ ROUTINES = {
                                        "computepitchanglespeciesvthermal"],
     "TZSourceF.f": ["settrigtzsource", "computetrigtzsourceerror"],
     "ElectronTZSourceF.f": ["setelectrontrigtzsource", "computeelectrontrigtzsourceerror"],
+    "TwoSpecies_ElectronTZSourceF.f": ["settwoelectrontrigtzsource", "computetwoelectrontrigtzsourceerror"],
+    "TwoSpecies_IonTZSourceF.f": ["settwoiontrigtzsource", "computetwoiontrigtzsourceerror"],
 }
 ALL_WANTED = {r for rs in ROUTINES.values() for r in rs}
 INTRINSICS = {"max": "fmax", "min": "fmin", "abs": "fabs", "sqrt": "sqrt", "sin": "sin", "cos": "cos", "exp": "exp",
@@ -69,7 +71,8 @@ def logical_lines(path):
             out[-1] += body.strip()
         else:
             out.append(body.strip())
-    return [s.lower() for s in out]
+    # a trailing `;` (an empty second statement, TwoSpecies_*TZSourceF.f:60-61) is not part of the statement
+    return [s.lower().rstrip().rstrip(";").rstrip() for s in out]
 
 
 def split_routines(stmts):

@@ -1159,6 +1159,98 @@ void ok_compute_electron_trig_tz_source_error(double* error, const double* soln,
     }
 }
 
+/* TwoSpecies_ElectronTrigTZSource / TwoSpecies_IonTrigTZSource (TwoSpecies_ElectronTZSourceF.f:10-160, :165-262;
+ * TwoSpecies_IonTZSourceF.f:10-139, :143-238; deck test/IAWTZ): electrons carry the wave (kxE, kyE) = (4, 2), ions
+ * (kxI, kyI) = (2, 4) at twice the amplitude; alpha = sqrt(mass); each species' source couples to both through the field.
+ * Only the last assignment of each routine is live in the Fortran (cg, cg1; the exact solutions cg0, cg2).
+ * species: 0 = the electron routines, 1 = the ion routines; dparams = {amp, electron_mass, ion_mass}. */
+#define TZ2_COMMON                                                                                                  \
+  const int64_t n3d = ND(2), n4d = ND(3);                                                                           \
+  const double me = dparams[1], mi = dparams[2], A = dparams[0], t = time;                                          \
+  const double kxI = 0.2e1, kyI = 0.4e1, ktI = 0.1e1, kxE = 0.4e1, kyE = 0.2e1, ktE = 0.1e1;                        \
+  const double pi = 4.0 * atan(1.0);                                                                                \
+  const double alphaE = sqrt(me), alphaI = sqrt(mi);                                                                \
+  (void)alphaE; (void)alphaI; (void)ktI; (void)ktE; (void)kxI; (void)kyI; (void)kxE; (void)kyE; (void)me; (void)mi;
+static inline double tz_p2(double x) { return x * x; }
+static inline double tz_p4(double x) { double t = x * x; return t * t; }   /* gfortran's x**4 */
+void ok_set_two_species_trig_tz_source(double* f, const ok_geom* g, const int* lo, const double* xlo, const double* dx,
+                                       double time, const double* velocities, const double* dparams, int species) {
+  TZ2_COMMON
+  for (int i4 = 0; i4 < n4d; ++i4)
+    for (int i3 = 0; i3 < n3d; ++i3) {
+      const double vx = velocities[i3 + n3d * (i4 + n4d * 0)];
+      const double vy = velocities[i3 + n3d * (i4 + n4d * 1)];
+      for (int i2 = 0; i2 < ND(1); ++i2) {
+        const double y = xlo[1] + ((lo[1] + i2) + 0.5) * dx[1];
+        for (int i1 = 0; i1 < ND(0); ++i1) {
+          const double x = xlo[0] + ((lo[0] + i1) + 0.5) * dx[0];
+          double cg;
+          if (species == 0) {
+            cg = tz_p2(alphaE) / pi * exp(-(tz_p2(alphaE) * (vx * vx + vy * vy) / 0.2e1)) * A * cos(kxE * x) * cos(kyE * y) * ktE *
+                     cos(ktE * t) / 0.2e1 -
+                 vx * tz_p2(alphaE) / pi * exp(-(tz_p2(alphaE) * (vx * vx + vy * vy) / 0.2e1)) * A * kxE * sin(kxE * x) * cos(kyE * y) *
+                     sin(ktE * t) / 0.2e1 -
+                 vy * tz_p2(alphaE) / pi * exp(-(tz_p2(alphaE) * (vx * vx + vy * vy) / 0.2e1)) * A * cos(kxE * x) * kyE * sin(kyE * y) *
+                     sin(ktE * t) / 0.2e1 -
+                 0.1e1 / me *
+                     (sin(ktE * t) * sin(kxE * x) * kxE * (tz_p2(kxI) + tz_p2(kyI)) * cos(kyE * y) -
+                      0.2e1 * cos(kyI * y) * sin(ktI * t) * sin(kxI * x) * kxI * (tz_p2(kxE) + tz_p2(kyE))) *
+                     A / (tz_p2(kxI) + tz_p2(kyI)) / (tz_p2(kxE) + tz_p2(kyE)) * tz_p4(alphaE) / pi * vx *
+                     exp(-(tz_p2(alphaE) * (vx * vx + vy * vy) / 0.2e1)) * (0.1e1 + A * cos(kxE * x) * cos(kyE * y) * sin(ktE * t)) / 0.2e1 -
+                 0.1e1 / me * A *
+                     (sin(ktE * t) * sin(kyE * y) * kyE * (tz_p2(kxI) + tz_p2(kyI)) * cos(kxE * x) -
+                      0.2e1 * kyI * cos(kxI * x) * sin(ktI * t) * sin(kyI * y) * (tz_p2(kxE) + tz_p2(kyE))) /
+                     (tz_p2(kxI) + tz_p2(kyI)) / (tz_p2(kxE) + tz_p2(kyE)) * tz_p4(alphaE) / pi * vy *
+                     exp(-(tz_p2(alphaE) * (vx * vx + vy * vy) / 0.2e1)) * (0.1e1 + A * cos(kxE * x) * cos(kyE * y) * sin(ktE * t)) / 0.2e1;
+          } else {
+            cg = tz_p2(alphaI) / pi * exp(-(tz_p2(alphaI) * (vx * vx + vy * vy) / 0.2e1)) * A * cos(kxI * x) * cos(kyI * y) * ktI *
+                     cos(ktI * t) -
+                 vx * tz_p2(alphaI) / pi * exp(-(tz_p2(alphaI) * (vx * vx + vy * vy) / 0.2e1)) * A * kxI * sin(kxI * x) * cos(kyI * y) *
+                     sin(ktI * t) -
+                 vy * tz_p2(alphaI) / pi * exp(-(tz_p2(alphaI) * (vx * vx + vy * vy) / 0.2e1)) * A * cos(kxI * x) * kyI * sin(kyI * y) *
+                     sin(ktI * t) +
+                 0.1e1 / mi *
+                     (sin(ktE * t) * sin(kxE * x) * kxE * (tz_p2(kxI) + tz_p2(kyI)) * cos(kyE * y) -
+                      0.2e1 * cos(kyI * y) * sin(ktI * t) * sin(kxI * x) * kxI * (tz_p2(kxE) + tz_p2(kyE))) *
+                     A / (tz_p2(kxI) + tz_p2(kyI)) / (tz_p2(kxE) + tz_p2(kyE)) * tz_p4(alphaI) / pi * vx *
+                     exp(-(tz_p2(alphaI) * (vx * vx + vy * vy) / 0.2e1)) * (0.1e1 + 0.2e1 * A * cos(kxI * x) * cos(kyI * y) * sin(ktI * t)) /
+                     0.2e1 +
+                 0.1e1 / mi * A *
+                     (sin(ktE * t) * sin(kyE * y) * kyE * (tz_p2(kxI) + tz_p2(kyI)) * cos(kxE * x) -
+                      0.2e1 * kyI * cos(kxI * x) * sin(ktI * t) * sin(kyI * y) * (tz_p2(kxE) + tz_p2(kyE))) /
+                     (tz_p2(kxI) + tz_p2(kyI)) / (tz_p2(kxE) + tz_p2(kyE)) * tz_p4(alphaI) / pi * vy *
+                     exp(-(tz_p2(alphaI) * (vx * vx + vy * vy) / 0.2e1)) * (0.1e1 + 0.2e1 * A * cos(kxI * x) * cos(kyI * y) * sin(ktI * t)) /
+                     0.2e1;
+          }
+          F4(f, i1, i2, i3, i4) = F4(f, i1, i2, i3, i4) + cg;
+        }
+      }
+    }
+}
+void ok_compute_two_species_trig_tz_source_error(double* error, const double* soln, const ok_geom* g, const int* lo,
+                                                 const double* xlo, const double* dx, double time, const double* velocities,
+                                                 const double* dparams, int species) {
+  TZ2_COMMON
+  for (int i4 = 0; i4 < n4d; ++i4)
+    for (int i3 = 0; i3 < n3d; ++i3) {
+      const double vx = velocities[i3 + n3d * (i4 + n4d * 0)];
+      const double vy = velocities[i3 + n3d * (i4 + n4d * 1)];
+      for (int i2 = 0; i2 < ND(1); ++i2) {
+        const double y = xlo[1] + ((lo[1] + i2) + 0.5) * dx[1];
+        for (int i1 = 0; i1 < ND(0); ++i1) {
+          const double x = xlo[0] + ((lo[0] + i1) + 0.5) * dx[0];
+          const double fexact =
+              species == 0 ? tz_p2(alphaE) / pi * exp(-(tz_p2(alphaE) * (vx * vx + vy * vy) / 0.2e1)) *
+                                 (0.1e1 + A * cos(kxE * x) * cos(kyE * y) * sin(ktE * t)) / 0.2e1
+                           : tz_p2(alphaI) / pi * exp(-(tz_p2(alphaI) * (vx * vx + vy * vy) / 0.2e1)) *
+                                 (0.1e1 + 0.2e1 * A * cos(kxI * x) * cos(kyI * y) * sin(ktI * t)) / 0.2e1;
+          F4(error, i1, i2, i3, i4) = F4(soln, i1, i2, i3, i4) - fexact;
+        }
+      }
+    }
+}
+#undef TZ2_COMMON
+
 /* ------------------------------------------------------------------------------------------
  * Time-history diagnostics.
  * computeke (KineticSpeciesF.f:2447-2500): out = {ke, ke_x, ke_y, px, py}; the running sums start from

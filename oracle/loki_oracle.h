@@ -112,6 +112,12 @@ void ok_set_electron_trig_tz_source(double* f, const ok_geom* g, const int* lo, 
 void ok_compute_electron_trig_tz_source_error(double* error, const double* soln, const ok_geom* g, const int* lo,
                                               const double* xlo, const double* dx, double time, const double* velocities,
                                               double amp);
+/* TwoSpecies_ElectronTrigTZSource (species 0) / TwoSpecies_IonTrigTZSource (species 1); dparams = {amp, me, mi} */
+void ok_set_two_species_trig_tz_source(double* f, const ok_geom* g, const int* lo, const double* xlo, const double* dx,
+                                       double time, const double* velocities, const double* dparams, int species);
+void ok_compute_two_species_trig_tz_source_error(double* error, const double* soln, const ok_geom* g, const int* lo,
+                                                 const double* xlo, const double* dx, double time, const double* velocities,
+                                                 const double* dparams, int species);
 void ok_append_krook(double* rhs, const double* u, const ok_geom* g, const double* nu, double dt, ok_ic_fn ic,
                      void* ic_ctx);
 /* ---- PitchAngleCollisionOperatorF.f / PitchAngleCollisionOperator.C (loki_oracle_coll.c) ---- */
@@ -206,8 +212,9 @@ void ok_vp_set_krook(ok_vp_work* w, int s, const double* nu);
 /* a pitch-angle collision operator on species s (KineticSpecies.C:1036-1046, 666-672); p = {range_lo[2], range_hi[2],
  * vfloor, vthermal_dt, nuCoeff, conservative}; NULL removes it */
 void ok_vp_set_pitch_angle(ok_vp_work* w, int s, const double* p);
-/* twilight-zone source of species s in completeRHS: on = 0 none, 1 TrigTZSource, 2 ElectronTrigTZSource */
-void ok_vp_set_trig_tz(ok_vp_work* w, int s, int on, double amp);
+/* twilight-zone source of species s in completeRHS: on = 0 none, 1 TrigTZSource, 2 ElectronTrigTZSource,
+ * 3 / 4 TwoSpecies_Electron / IonTrigTZSource (these two with the masses) */
+void ok_vp_set_trig_tz(ok_vp_work* w, int s, int on, double amp, double electron_mass, double ion_mass);
 void ok_vp_set_dt(ok_vp_work* w, double dt);   /* the a_dt of a bare ok_vp_eval_rhs call (completeRHS) */
 /* rhs[s], f[s]: 4D arrays incl. ghosts; f's ghosts are modified like the reference does.
  * ke_e_dot[s] receives rhs.m_integrated_ke_e_dot for driven species. */

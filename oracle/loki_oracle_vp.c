@@ -32,7 +32,7 @@ struct ok_vp_work {
   int nonperiodic[2], use_new_bcs;
   double** krook_nu;
   double** coll;   /* pitch-angle operator parameters per species (8 doubles) or NULL */
-  double** tz;     /* twilight-zone source per species {amp, kind 1 / 2} or NULL (KineticSpecies.C:1077-1080) */
+  double** tz;     /* twilight-zone source per species {amp, me, mi, kind 1..4} or NULL (KineticSpecies.C:1077-1080) */
   double cur_dt;
 };
 
@@ -195,13 +195,15 @@ void ok_vp_set_pitch_angle(ok_vp_work* w, int s, const double* p) {
     memcpy(w->coll[s], p, sizeof(double) * 8);
   }
 }
-void ok_vp_set_trig_tz(ok_vp_work* w, int s, int on, double amp) {
+void ok_vp_set_trig_tz(ok_vp_work* w, int s, int on, double amp, double electron_mass, double ion_mass) {
   free(w->tz[s]);
   w->tz[s] = NULL;
   if (on) {
-    w->tz[s] = (double*)malloc(2 * sizeof(double));
+    w->tz[s] = (double*)malloc(4 * sizeof(double));
     w->tz[s][0] = amp;
-    w->tz[s][1] = (double)on;
+    w->tz[s][1] = electron_mass;
+    w->tz[s][2] = ion_mass;
+    w->tz[s][3] = (double)on;
   }
 }
 /* fillAdvectionGhostCells on one rank (KineticSpecies.H:404-412, 998-1031): physical boundary conditions of the
@@ -280,7 +282,10 @@ void ok_vp_eval_rhs(ok_vp_work* w, double** rhs, double** f, double time, double
     if (w->tz[s]) {
       /* the twilight-zone source (KineticSpecies.C:1077-1080) */
       const int lo[2] = {-g->ng, -g->ng};
-      if (w->tz[s][1] == 2.0)
+      const int on = (int)w->tz[s][3];
+      if (on >= 3)
+        ok_set_two_species_trig_tz_source(rhs[s], g, lo, w->xlo, g->dx, time, w->velocities[s], w->tz[s], on - 3);
+      else if (on == 2)
         ok_set_electron_trig_tz_source(rhs[s], g, lo, w->xlo, g->dx, time, w->velocities[s], w->tz[s][0]);
       else
         ok_set_trig_tz_source(rhs[s], g, lo, w->xlo, g->dx, time, w->velocities[s], w->tz[s][0]);

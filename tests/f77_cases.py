@@ -233,6 +233,17 @@ def kinetic_cases(B, ok, order):
            B.arr(s.velocities), B.meta(amp))
     B.finish()
     out["etz_source"], out["etz_error"] = tze, erre
+    # the two-species sources (TwoSpecies_ElectronTZSourceF.f, TwoSpecies_IonTZSourceF.f): dparams = {amp, me, mi}
+    dpar = np.array([0.7, 0.5, 25.0])
+    for tag, set_name, err_name in (("tz2e", "settwoelectrontrigtzsource_", "computetwoelectrontrigtzsourceerror_"),
+                                    ("tz2i", "settwoiontrigtzsource_", "computetwoiontrigtzsourceerror_")):
+        src2 = np.ascontiguousarray(rng.uniform(-1, 1, size=s.f.shape))
+        B.call(set_name, B.arr(src2), *db, B.meta(xlo4), B.meta(xhi4), B.meta(dxs), B.d(0.37), B.arr(s.velocities), B.meta(dpar))
+        err2 = np.zeros_like(s.f)
+        B.call(err_name, B.arr(err2), B.arr(s.f), *db, B.meta(xlo4), B.meta(xhi4), B.meta(dxs), B.d(0.37), B.arr(s.velocities),
+               B.meta(dpar))
+        B.finish()
+        out[tag + "_source"], out[tag + "_error"] = src2, err2
     return out
 
 

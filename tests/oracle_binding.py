@@ -107,7 +107,9 @@ def load():
     L.ok_vp_set_krook.argtypes = [C.c_void_p, i, dp]
     L.ok_vp_set_dt.argtypes = [C.c_void_p, d]
     L.ok_vp_set_pitch_angle.argtypes = [C.c_void_p, i, C.c_void_p]
-    L.ok_vp_set_trig_tz.argtypes = [C.c_void_p, i, i, d]
+    L.ok_vp_set_trig_tz.argtypes = [C.c_void_p, i, i, d, d, d]
+    L.ok_set_two_species_trig_tz_source.argtypes = [dp, G, C.c_void_p, dp, dp, d, dp, dp, i]
+    L.ok_compute_two_species_trig_tz_source_error.argtypes = [dp, dp, G, C.c_void_p, dp, dp, d, dp, dp, i]
     L.ok_set_trig_tz_source.argtypes = [dp, G, C.c_void_p, dp, dp, d, dp, d]
     L.ok_compute_trig_tz_source_error.argtypes = [dp, dp, G, C.c_void_p, dp, dp, d, dp, d]
     L.ok_set_electron_trig_tz_source.argtypes = [dp, G, C.c_void_p, dp, dp, d, dp, d]

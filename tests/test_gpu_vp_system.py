@@ -31,7 +31,8 @@ def _oracle(ok, deck):
             ok.ok_vp_set_pitch_angle(w, s_, p.ctypes.data)
         tz = getattr(sp_, "tz", None)
         if tz:   # a TrigTZSource: the manufactured-solution forcing in completeRHS
-            ok.ok_vp_set_trig_tz(w, s_, int(tz.get("kind", 1)), float(tz["amp"]))
+            ok.ok_vp_set_trig_tz(w, s_, int(tz.get("kind", 1)), float(tz["amp"]), float(tz.get("electron_mass", 1.0)),
+                                 float(tz.get("ion_mass", 1.0)))
     return w, sp, keep
 
 

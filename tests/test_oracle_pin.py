@@ -374,6 +374,22 @@ def test_pin_trig_tz_source(ok, ref, n, order, lo):
             ok_err(e1.ravel(), s.f.ravel(), C.byref(s.g), lo2, xlo, dx, time, s.velocities, amp)
             ref_err(R._p(e2), R._p(s.f), *db, R._p(xlo), R._p(xhi), R._p(dx), R._d(time), R._p(s.velocities), R._p(np.array([amp])))
             assert np.array_equal(e1, e2)
+    # the two-species sources of the IAWTZ deck (TwoSpecies_ElectronTZSourceF.f, TwoSpecies_IonTZSourceF.f): dparams =
+    # {amp, electron_mass, ion_mass}
+    two = ((0, R.L.settwoelectrontrigtzsource_, R.L.computetwoelectrontrigtzsourceerror_),
+           (1, R.L.settwoiontrigtzsource_, R.L.computetwoiontrigtzsourceerror_))
+    for species, ref_set, ref_err in two:
+        for time, dparams in ((0.0, [0.1, 1.0, 4.0]), (0.37, [0.1, 1.0, 4.0]), (2.5, [0.7, 0.5, 25.0])):
+            dp = np.array(dparams)
+            base = np.random.default_rng(3).uniform(-1, 1, size=s.f.shape)
+            r1, r2 = base.copy(), base.copy()
+            ok.ok_set_two_species_trig_tz_source(r1.ravel(), C.byref(s.g), lo2, xlo, dx, time, s.velocities, dp, species)
+            ref_set(R._p(r2), *db, R._p(xlo), R._p(xhi), R._p(dx), R._d(time), R._p(s.velocities), R._p(dp))
+            assert np.array_equal(r1, r2) and not np.array_equal(r1, base)
+            e1, e2 = np.zeros_like(base), np.zeros_like(base)
+            ok.ok_compute_two_species_trig_tz_source_error(e1.ravel(), s.f.ravel(), C.byref(s.g), lo2, xlo, dx, time, s.velocities, dp, species)
+            ref_err(R._p(e2), R._p(s.f), *db, R._p(xlo), R._p(xhi), R._p(dx), R._d(time), R._p(s.velocities), R._p(dp))
+            assert np.array_equal(e1, e2)
 
 
 @needs_ref
