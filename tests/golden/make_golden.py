@@ -88,3 +88,19 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def external2d_profiles():
+    """tests/golden/External2D_profiles.npz: the "2D dist" datasets of the reference's test/External2D/rho_init_*.h5 (read
+    with loki_b200/h5lite.py, which test_cpu_outputs.py pins against those very files when the reference tree is present);
+    the tests write them back out as HDF5 files for the "External 2D" initial condition"""
+    from loki_b200 import h5lite
+    ref = "/root/reference/test/External2D"
+    out = {n: np.array(h5lite.read(os.path.join(ref, "rho_init_%s.h5" % n))["2D dist"].data) for n in ("e", "He", "C")}
+    path = os.path.join(HERE, "External2D_profiles.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__" and os.path.isdir("/root/reference/test/External2D"):
+    external2d_profiles()

@@ -276,8 +276,8 @@ def test_deck_reader_keeps_the_restart_cadence():
 
 
 EXTERNAL_2D = """
-# test/External2D/External2D.pp of the reference, restated (same numbers); the three "2D dist" files are the
-# reference's own (test/External2D/rho_init_*.h5), kept under tests/golden/
+# test/External2D/External2D.pp of the reference, restated (same numbers); the three "2D dist" files beside the deck
+# are written by write_external2d_files from tests/golden/External2D_profiles.npz (the reference's rho_init_*.h5 data)
 $mp_over_me = 1836.;
 $m_he   = 4.*$mp_over_me;
 $m_c    = 12.*$mp_over_me;
@@ -311,38 +311,52 @@ kinetic_species.1.Nv = 24 16
 kinetic_species.1.mass = 1.0
 kinetic_species.1.charge = -1.0
 kinetic_species.1.ic.name = "External 2D"
-kinetic_species.1.ic.file_name = "GOLDEN/External2D_rho_init_e.h5"
+kinetic_species.1.ic.file_name = "rho_init_e.h5"
 kinetic_species.2.name = "He"
 kinetic_species.2.velocity_limits = $vmin_he $vmax_he $vmin_he $vmax_he
 kinetic_species.2.Nv = 24 16
 kinetic_species.2.mass = $m_he
 kinetic_species.2.charge = 2.
 kinetic_species.2.ic.name = "External 2D"
-kinetic_species.2.ic.file_name = "GOLDEN/External2D_rho_init_He.h5"
+kinetic_species.2.ic.file_name = "rho_init_He.h5"
 kinetic_species.3.name = "C"
 kinetic_species.3.velocity_limits = $vmin_c $vmax_c $vmin_c $vmax_c
 kinetic_species.3.Nv = 24 16
 kinetic_species.3.mass = $m_c
 kinetic_species.3.charge = 6.
 kinetic_species.3.ic.name = "External 2D"
-kinetic_species.3.ic.file_name = "GOLDEN/External2D_rho_init_C.h5"
+kinetic_species.3.ic.file_name = "rho_init_C.h5"
 number_of_probes = 0
-""".replace("GOLDEN", os.path.join(HERE, "golden"))
+"""
+
+
+def write_external2d_files(directory):
+    """the deck's three external files, written with h5lite from the committed profiles (tests/golden/make_golden.py)"""
+    prof = np.load(os.path.join(HERE, "golden", "External2D_profiles.npz"))
+    for n in ("e", "He", "C"):
+        root = h5lite.Group()
+        root.put("2D dist", prof[n])
+        h5lite.write(os.path.join(str(directory), "rho_init_%s.h5" % n), root)
+    return prof
 
 
 def test_reader_reads_the_references_own_hdf5_files():
     """test/External2D/rho_init_*.h5: written by libhdf5 with compact new-style groups (Link messages in a version-1
-    object header) -- a second, differently laid out pin of the reader"""
-    dens = {}
+    object header) -- a second, differently laid out pin of the reader, where the reference tree is present; the
+    committed profiles are those files' data"""
+    prof = np.load(os.path.join(HERE, "golden", "External2D_profiles.npz"))
+    assert prof["e"].shape == (7 + 6, 128 + 6)                       # (Ny + 2 ng, Nx + 2 ng), order 6
+    assert prof["e"].max() == 10.0 and prof["e"].min() == 0.05
+    # the deck's plasma is neutral cell by cell: n_e = 2 n_He + 6 n_C
+    assert np.max(np.abs(prof["e"] - 2.0 * prof["He"] - 6.0 * prof["C"])) <= 1e-14 * 10.0
+    ref = "/root/reference/test/External2D"
+    if not os.path.isdir(ref):
+        pytest.skip("the reference tree is not on this machine")
     for n in ("e", "He", "C"):
-        root = h5lite.read(os.path.join(HERE, "golden", "External2D_rho_init_%s.h5" % n))
+        root = h5lite.read(os.path.join(ref, "rho_init_%s.h5" % n))
         assert root.names() == ["2D dist"]
         d = root["2D dist"].data
-        assert d.dtype == np.dtype("<f8") and d.shape == (7 + 6, 128 + 6)       # (Ny + 2 ng, Nx + 2 ng), order 6
-        dens[n] = np.array(d)
-    assert dens["e"].max() == 10.0 and dens["e"].min() == 0.05
-    # the deck's plasma is neutral cell by cell: n_e = 2 n_He + 6 n_C
-    assert np.max(np.abs(dens["e"] - 2.0 * dens["He"] - 6.0 * dens["C"])) <= 1e-14 * 10.0
+        assert d.dtype == np.dtype("<f8") and np.array_equal(d, prof[n])
 
 
 def test_external_2d_deck_loads_like_the_reference_deck(tmp_path):
@@ -351,7 +365,9 @@ def test_external_2d_deck_loads_like_the_reference_deck(tmp_path):
     from loki_b200 import pp
     path = tmp_path / "External2D.pp"
     path.write_text(EXTERNAL_2D)
+    prof = write_external2d_files(tmp_path)
     deck = pp.load(str(path))
+    assert all(np.array_equal(sp.external, prof[n]) for sp, n in zip(deck.species, ("e", "He", "C")))
     assert deck.n == (128, 7) and deck.order == 6 and deck.rk == 6 and [s.name for s in deck.species] == ["electron", "He", "C"]
     ng = deck.ng
     total = 0.0

@@ -7,7 +7,7 @@ import pytest
 import decks
 import test_gpu_vp_system as tvp
 from loki_b200 import pp, run
-from test_cpu_outputs import EXTERNAL_2D
+from test_cpu_outputs import EXTERNAL_2D, write_external2d_files
 from util import cell_rel_err, star_rel_err
 
 pytestmark = pytest.mark.gpu
@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 def _deck(tmp_path):
     path = tmp_path / "External2D.pp"
     path.write_text(EXTERNAL_2D)
+    write_external2d_files(tmp_path)              # rho_init_*.h5 beside the deck, as in the reference's test directory
     return decks._wrap(pp.load(str(path)))
 
 
