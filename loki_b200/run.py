@@ -104,7 +104,11 @@ class Runner:
         (Simulation.C:393-412; default: one probe at the fractions (0.5, 0)); Vlasov-Poisson systems"""
         if self.vm:
             raise NotImplementedError("probe histories of the Vlasov-Maxwell system")
-        locs = getattr(self.deck, "probes", None) or [(0.5, 0.0)]
+        locs = getattr(self.deck, "probes", None)
+        if locs is None:
+            locs = [(0.5, 0.0)]
+        if not locs:                       # number_of_probes = 0 (e.g. the External2D deck): no probe histories
+            return np.zeros((0, 2))
         fx = np.array([p[0] for p in locs], dtype=np.float64)
         fy = np.array([p[1] for p in locs], dtype=np.float64)
         out = np.zeros(2 * len(locs))
@@ -217,7 +221,9 @@ class Runner:
     def accumulate_sequences(self):
         o = self.out
         o["time_seq"].append(self.time)
-        for seq, v in zip(o["seq"], self.sequence_record()):
+        rec = self.sequence_record()
+        assert len(rec) == len(o["seq"]), "time-history names and values out of step"
+        for seq, v in zip(o["seq"], rec):
             seq.append(v)
         o["saved_seq"] += 1
 
