@@ -7,9 +7,13 @@ symbol-table nodes plus a local heap of names), version-1 dataspace / datatype /
 layout (contiguous).  Those are the structures the reference's calls produce: H5Fcreate / H5Gcreate / H5Dcreate /
 H5Acreate with default property lists (ReaderWriterBase.C:24-330, RestartWriter.C:55-470).
 
-The reader walks the same structures and is pinned (tests/test_cpu_h5lite.py) against a file libhdf5 itself wrote:
-scipy's MATLAB v7.3 fixture.  It also understands chunked layouts with the deflate filter and object-header
-continuation blocks because such files are what a LOKI baseline would be.
+The reader walks the same structures and is pinned (tests/test_cpu_outputs.py) against files libhdf5 itself wrote:
+scipy's MATLAB v7.3 fixture (tests/golden/libhdf5_written_*.mat: user block, symbol-table group, version-1/2 layout) and,
+where the reference tree is present, the reference's own test/External2D/rho_init_*.h5 (compact new-style groups: Link
+messages in a version-1 object header).  It also understands chunked layouts with the deflate filter and object-header
+continuation blocks because such files are what a LOKI baseline would be.  PARITY OF THE WRITER IS UNPINNED against
+libhdf5 itself (none in the image): its message bytes are compared with the genuine file's where they describe the
+same thing, and everything it writes is read back by the pinned reader.
 
 Datasets hold numpy arrays; the three element types LOKI writes are '<f8' (H5T_NATIVE_DOUBLE), '>i4' (H5T_STD_I32BE)
 and 'u1' (H5T_NATIVE_UCHAR).  A dataset of shape () is a scalar dataspace (H5Screate(H5S_SCALAR))."""

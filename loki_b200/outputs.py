@@ -10,6 +10,8 @@ Host-side mirror of the reference's writer classes, same names, same call order,
                                                          per field and time slice
   RestartWriter           RestartWriter.C:15-613         <write_dir>/dist_<n>.hdf (metadata) + .g<k> (bulk data)
   RestartReader           RestartReader.C                the inverse, for resuming a run
+  FieldReader             FieldReader.C:15-104           what the post processor reads the field series with
+  TimeHistReader          TimeHistReader.C:15-52         ... and the time histories
 
 plus the putToRestart methods of Simulation / VPSystem / Poisson / KineticSpecies / ProblemDomain / KrookLayer /
 ExternalDistKrookLayer / ShapedRampedCosineDriver that decide what goes into a dump.  The HDF5 bytes come from
@@ -155,6 +157,45 @@ class FieldWriter(ReaderWriterBase):
             h5lite.write(self.file_name(index), self.files[index][0])
         for index in [k for k in self.files if k not in (0, self.current_file_index)]:
             del self.files[index]                           # complete files need not stay in memory
+
+
+class TimeHistReader:
+    """TimeHistReader.C:15-52: one time-history file (raw `.time_hists_<n>.hdf` or post-processed `_timeSeries.hdf`)"""
+
+    def __init__(self, name):
+        self.root = h5lite.read(name)["root"]
+
+    def read_time_history(self, hist_name):
+        return np.array(self.root[hist_name].data, dtype=np.float64)
+
+    def read_num_probes(self):
+        return int(self.root["numProbes"].data[0])
+
+    def read_num_tracking_particles(self):
+        return int(self.root["numTrackingParticles"].data[0])
+
+
+class FieldReader:
+    """FieldReader.C:15-104: one field file of the series (or the post-processed `_fields.hdf`)"""
+
+    def __init__(self, name):
+        self.root = h5lite.read(name)["root"]
+
+    def read_time(self, name):
+        return float(self.root[name].data.reshape(-1)[0])
+
+    def read_coords(self):
+        return np.array(self.root["x"].data), np.array(self.root["y"].data)
+
+    def read_field(self, field_name):
+        """the dataset flattened, as the reference hands it back (a vector of Ny * Nx values, x fastest)"""
+        return np.array(self.root[field_name].data, dtype=np.float64).reshape(-1)
+
+    def read_total_num_time_slices(self):
+        return int(self.root["total_num_time_slices"].data[0])
+
+    def read_num_time_slices_in_file(self):
+        return int(self.root["num_time_slices_in_this_file"].data[0])
 
 
 def distrib_info(proc_lo, proc_hi, n_ghosts, num_cells, dim_partitions):

@@ -165,25 +165,25 @@ def write_time_series(prefix, is_maxwell, species_names):
         idx += 1
     if idx < 0:
         raise FileNotFoundError(prefix + ".time_hists_0.hdf")
-    root = h5lite.read("%s.time_hists_%d.hdf" % (prefix, idx))["root"]
-    nprobes = int(root["numProbes"].data[0]) if "numProbes" in root else 0
-    nparticles = int(root["numTrackingParticles"].data[0]) if "numTrackingParticles" in root else 0
+    th_reader = outputs.TimeHistReader("%s.time_hists_%d.hdf" % (prefix, idx))
+    root = th_reader.root
+    nprobes = th_reader.read_num_probes() if "numProbes" in root else 0
+    nparticles = th_reader.read_num_tracking_particles() if "numTrackingParticles" in root else 0
     if is_maxwell:
         # the Maxwell system writes the histories its device side computes (run.py); every dataset but the bookkeeping
         names = [n for n in root.names() if n not in ("sequence_times", "numProbes", "numTrackingParticles")]
     else:
         names = outputs.poisson_time_history_names(nprobes, nparticles, species_names)
-    w = outputs.TimeHistWriter(prefix + "_timeSeries.hdf", root["sequence_times"].data, for_post_proc=True)
+    w = outputs.TimeHistWriter(prefix + "_timeSeries.hdf", th_reader.read_time_history("sequence_times"), for_post_proc=True)
     for n in names:
-        w.write_time_history(n, root[n].data)
+        w.write_time_history(n, th_reader.read_time_history(n))
     w.close()
     return w.name
 
 
 def write_fields(prefix, nx, ny, n_ghosts, is_maxwell, species_names, plot_ke_vel_bdy_flux):
     """writeFields (vp4DPostProcess.C:215-385)"""
-    first = h5lite.read(prefix + ".fields_0.hdf")["root"]
-    total = int(first["total_num_time_slices"].data[0])
+    total = outputs.FieldReader(prefix + ".fields_0.hdf").read_total_num_time_slices()
     names = (outputs.maxwell_plot_names if is_maxwell else outputs.poisson_plot_names)(bool(plot_ke_vel_bdy_flux), species_names)
     top, root = outputs.ReaderWriterBase.create_file_and_root()
     data = {n: np.zeros((total, ny, nx)) for n in names}
@@ -192,13 +192,14 @@ def write_fields(prefix, nx, ny, n_ghosts, is_maxwell, species_names, plot_ke_ve
     k = 0
     ng = n_ghosts
     while which < total and os.path.exists("%s.fields_%d.hdf" % (prefix, k)):
-        fr = h5lite.read("%s.fields_%d.hdf" % (prefix, k))["root"]
+        fr = outputs.FieldReader("%s.fields_%d.hdf" % (prefix, k))
         if k == 0:
-            x, y = np.array(fr["x"].data), np.array(fr["y"].data)
-        for _ in range(int(fr["num_time_slices_in_this_file"].data[0])):
-            times.append(float(fr["time_slice_%d_time" % which].data[0]))
+            x, y = fr.read_coords()
+        for _ in range(fr.read_num_time_slices_in_file()):
+            times.append(fr.read_time("time_slice_%d_time" % which))
             for n in names:
-                data[n][which] = fr["time_slice_%d_%s" % (which, n)].data[ng:ng + ny, ng:ng + nx]
+                plane = fr.read_field("time_slice_%d_%s" % (which, n)).reshape(ny + 2 * ng, nx + 2 * ng)
+                data[n][which] = plane[ng:ng + ny, ng:ng + nx]
             which += 1
             if which == total:
                 break

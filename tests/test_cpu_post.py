@@ -127,3 +127,22 @@ def test_check_tests_passes_and_fails_like_the_reference(tmp_path):
     if os.path.exists(ref):
         tol = dict(post._tolerances(ref))
         assert tol["electron_ke"] == 1.0e-14 and tol["electron_driver_time_envel"] == 1.0e-10
+
+
+def test_reader_classes(tmp_path):
+    """FieldReader / TimeHistReader (FieldReader.C, TimeHistReader.C) over the raw and the post-processed files"""
+    base = str(tmp_path / "deck")
+    n, ng = (7, 8, 6, 5), 2
+    fs, fields, names, seqs, times = _write_run(base, 3, n, ng)
+    post.post_process(base)
+    fr = outputs.FieldReader(base + ".fields_1.hdf")
+    assert fr.read_num_time_slices_in_file() == 1 and fr.read_time("time_slice_2_time") == 0.5
+    assert np.array_equal(fr.read_field("time_slice_2_EX"), fields[2][0].reshape(-1))
+    assert outputs.FieldReader(base + ".fields_0.hdf").read_total_num_time_slices() == 3
+    x, y = fr.read_coords()
+    assert x.shape == (n[0],) and y.shape == (n[1],)
+    th = outputs.TimeHistReader(base + ".time_hists_2.hdf")
+    assert th.read_num_probes() == 1 and th.read_num_tracking_particles() == 0
+    assert np.array_equal(th.read_time_history("electron_ke"), seqs[names.index("electron_ke")])
+    assert np.array_equal(outputs.TimeHistReader(base + "_timeSeries.hdf").read_time_history("series_time"), times)
+    assert np.array_equal(outputs.FieldReader(base + "_fields.hdf").read_field("EY").reshape(3, n[1], n[0])[1], fields[1][1][ng:-ng, ng:-ng])
