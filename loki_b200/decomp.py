@@ -62,6 +62,21 @@ class TileLayout:
         rx, ry = self.coords(rank)
         return self.xs[rx][0], self.ys[ry][0], self.xs[rx][1], self.ys[ry][1]
 
+    def reference_rank(self, rank):
+        """the rank ParallelArray gives this tile: dimension 0 varies slowest there (getIndexRank, ParallelArray.C:609-626),
+        fastest here; a restart dump names a tile's dataset by it (RestartWriter.C:556-559)"""
+        rx, ry = self.coords(rank)
+        return rx * self.py + ry
+
+    def restart_tiles(self, tiles_by_rank, n_ghosts, nv):
+        """({reference rank: tile}, distribInfo) for outputs.RestartWriter.write_parallel_array / outputs.put_species from
+        every rank's dataBox (lk_vp_get_state of each rank, gathered by the caller): the split is ParallelArray's
+        (split_extent), only the numbering of the ranks differs"""
+        from . import outputs
+        info = outputs.distrib_info(0, self.world - 1, n_ghosts, [self.nglobal[0], self.nglobal[1], nv[0], nv[1]],
+                                    [self.px, self.py, 1, 1])
+        return {self.reference_rank(r): t for r, t in tiles_by_rank.items()}, info
+
     def tiles_flat(self):
         out = []
         for r in range(self.world):

@@ -146,3 +146,32 @@ def test_reader_classes(tmp_path):
     assert np.array_equal(th.read_time_history("electron_ke"), seqs[names.index("electron_ke")])
     assert np.array_equal(outputs.TimeHistReader(base + "_timeSeries.hdf").read_time_history("series_time"), times)
     assert np.array_equal(outputs.FieldReader(base + "_fields.hdf").read_field("EY").reshape(3, n[1], n[0])[1], fields[1][1][ng:-ng, ng:-ng])
+
+
+@pytest.mark.parametrize("px,py", [(2, 3), (1, 4), (3, 1)])
+def test_decomp_tiles_become_a_reference_dump(tmp_path, px, py):
+    """a multi-GPU run's tiles (decomp.TileLayout: rank = ry * px + rx) written as the dump LOKI would write for the same
+    decomposition (rank = ix * py + iy) and assembled back by the post processor: the split rule is the same one"""
+    from loki_b200 import decomp
+    n, ng = (7, 9, 4, 3), 2
+    layout = decomp.TileLayout((n[0], n[1]), px, py)
+    rng = np.random.default_rng(9)
+    f = rng.random(tuple(k + 2 * ng for k in reversed(n)))
+    tiles = {}
+    for r in range(layout.world):
+        lx, ly, nx, ny = layout.tile(r)
+        tiles[r] = np.ascontiguousarray(f[:, :, ly:ly + ny + 2 * ng, lx:lx + nx + 2 * ng])
+    ref_tiles, info = layout.restart_tiles(tiles, ng, (n[2], n[3]))
+    assert sorted(ref_tiles) == list(range(layout.world))
+    for r in range(layout.world):
+        lo, hi = post._tile_box(np.array(info), layout.reference_rank(r))
+        lx, ly, nx, ny = layout.tile(r)
+        assert (lo[0], lo[1], hi[0] - lo[0] + 1, hi[1] - lo[1] + 1) == (lx, ly, nx, ny)
+    x_lo, x_hi = [-1.0, -2.0, -7.0, -7.0], [1.0, 2.0, 7.0, 7.0]
+    dx = [(x_hi[k] - x_lo[k]) / n[k] for k in range(4)]
+    item = dict(sp=dict(name="electron", mass=1.0, charge=-1.0), domain=(list(n), x_lo, x_hi, dx, (True, True)), tiles=ref_tiles, info=info)
+    base = str(tmp_path / "deck")
+    outputs.write_vp_restart(base, 0, [item], ng, 0.0, 0.01, 0.9, 1.0, num_procs=layout.world, max_files=2)
+    r = outputs.RestartReader(os.path.join(base, "dist_0.hdf"), 2)
+    r.push_sub_dir("electron")
+    assert np.array_equal(post.assemble_parallel_array(r, "distribution", list(n), ng), f)
