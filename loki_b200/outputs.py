@@ -415,6 +415,22 @@ def put_krook_layer(w, x_lo, x_hi, krook=None):
     w.write_integer_value("krookHasLayer_hi_1", int(has_hi[1]))
 
 
+def krook_state(deck_krook, x_lo, x_hi):
+    """KrookLayer::parseParameters (KrookLayer.C:163-189) on a deck's krook.* keys {x1a, x1b, x2a, x2b, power, coefficient}:
+    the layer state put_krook_layer records; None for a species without the keys"""
+    if not deck_krook:
+        return None
+    lo, hi = [float(x_lo[0]), float(x_lo[1])], [float(x_hi[0]), float(x_hi[1])]
+    has_lo, has_hi = [0, 0], [0, 0]
+    for d in range(2):
+        if ("x%da" % (d + 1)) in deck_krook:
+            lo[d], has_lo[d] = float(deck_krook["x%da" % (d + 1)]), 1
+        if ("x%db" % (d + 1)) in deck_krook:
+            hi[d], has_hi[d] = float(deck_krook["x%db" % (d + 1)]), 1
+    return dict(x_lo=lo, x_hi=hi, power=float(deck_krook.get("power", 3.0)), coefficient=float(deck_krook.get("coefficient", 1.0)),
+                has_lo=has_lo, has_hi=has_hi)
+
+
 def put_external_dist_krook(w, x_lo, x_hi):
     """ExternalDistKrookLayer::putToDatabase (ExternalDistKrook.C:308-350) of a species without such a layer
     (constructor defaults, ExternalDistKrook.C:22-42)"""

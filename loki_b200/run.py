@@ -271,6 +271,7 @@ class Runner:
             dx = [(x_hi[k] - x_lo[k]) / ncell[k] for k in range(4)]
             item = dict(sp=dict(name=sp.name, mass=sp.mass, charge=sp.charge, bz_const=getattr(sp, "bz", 0.0)),
                         domain=(ncell, x_lo, x_hi, dx, d.periodic), tiles={0: f},
+                        krook=outputs.krook_state(getattr(sp, "krook", None), x_lo, x_hi),
                         info=outputs.distrib_info(0, 0, d.ng, ncell, [1, 1, 1, 1]))
             if sp.driver and not self.vm:
                 v = C.c_double()

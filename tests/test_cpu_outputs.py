@@ -391,3 +391,19 @@ def test_external_2d_deck_loads_like_the_reference_deck(tmp_path):
     with pytest.raises(ValueError, match="does not match configuration space"):
         d2 = pp.load(str(bad))
         d2.initial_state(d2.species[0])
+
+
+def test_krook_layer_state_in_a_dump(tmp_path):
+    """KrookLayer::putToDatabase (KrookLayer.C:249-282) from a deck's krook.* keys (parseParameters, :163-189)"""
+    assert outputs.krook_state(None, [-1.0, -2.0], [1.0, 2.0]) is None
+    k = outputs.krook_state(dict(x1a=-0.5, x2b=1.5, coefficient=2.0), [-1.0, -2.0, -7.0, -7.0], [1.0, 2.0, 7.0, 7.0])
+    assert k == dict(x_lo=[-0.5, -2.0], x_hi=[1.0, 1.5], power=3.0, coefficient=2.0, has_lo=[1, 0], has_hi=[0, 1])
+    items = _restart_items(np.random.default_rng(4))
+    items[0]["krook"] = k
+    name = outputs.write_vp_restart(str(tmp_path / "d"), 0, items, 2, 0.0, 0.01, 0.9, 1.0)
+    el = h5lite.read(name)["root"]["electron"]
+    assert el["x_lo_krook"].data.tolist() == [-0.5, -2.0] and el["x_hi_krook"].data.tolist() == [1.0, 1.5]
+    assert float(el["krookCoeff"].data) == 2.0 and float(el["krookPower"].data) == 3.0
+    assert [int(el["krookHasLayer" + t].data) for t in ("", "_lo_0", "_lo_1", "_hi_0", "_hi_1")] == [1, 1, 0, 0, 1]
+    ion = h5lite.read(name)["root"]["ion"]
+    assert int(ion["krookHasLayer"].data) == 0 and ion["x_lo_krook"].data.tolist() == [-1.0, -2.0]
