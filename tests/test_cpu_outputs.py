@@ -407,3 +407,45 @@ def test_krook_layer_state_in_a_dump(tmp_path):
     assert [int(el["krookHasLayer" + t].data) for t in ("", "_lo_0", "_lo_1", "_hi_0", "_hi_1")] == [1, 1, 0, 0, 1]
     ion = h5lite.read(name)["root"]["ion"]
     assert int(ion["krookHasLayer"].data) == 0 and ion["x_lo_krook"].data.tolist() == [-1.0, -2.0]
+
+
+def test_writer_structures_equal_libhdf5s_for_the_same_content(tmp_path):
+    """the genuine libhdf5 file holds one dataset in the root group; the same content written by h5lite must come out as
+    the same structures: superblock constants, root symbol-table entry, B-tree node, symbol-table node and local heap
+    compared field by field (addresses aside), the heap's free list encoded by the same rule"""
+    g = h5lite.read(GENUINE)
+    root = h5lite.Group()
+    root.put("testdouble", np.array(g["testdouble"].data))
+    p = str(tmp_path / "same.hdf")
+    h5lite.write(p, root)
+    mine, theirs = open(p, "rb").read(), open(GENUINE, "rb").read()                # theirs: behind MATLAB's 512-byte user block
+
+    def parts(b):
+        r = h5lite._Reader(memoryview(b))
+        e = r.root_entry
+        sb = b.index(h5lite.SIGNATURE)
+        out = dict(sb_versions=bytes(b[sb + 8:sb + 16]), ks=struct.unpack_from("<HH", b, sb + 16), root_cache=e["cache"])
+        bt, hp = r.base + e["btree"], r.base + e["heap"]
+        out["tree_head"] = bytes(b[bt:bt + 8])                                      # TREE, type 0, level 0, 1 entry
+        out["tree_siblings"] = bytes(b[bt + 8:bt + 24])
+        key0, child, key1 = struct.unpack_from("<QQQ", b, bt + 24)
+        out["tree_keys"] = (key0, key1)
+        sn = r.base + child
+        out["snod_head"] = bytes(b[sn:sn + 8])                                      # SNOD, version 1, 1 symbol
+        name_off, _, cache, resv = struct.unpack_from("<QQII", b, sn + 8)
+        out["snod_entry"] = (name_off, cache, resv, bytes(b[sn + 24:sn + 40]))
+        out["heap_head"] = bytes(b[hp:hp + 8])
+        seg_size, free_head, seg = struct.unpack_from("<QQQ", b, hp + 8)
+        seg += r.base
+        out["heap_names"] = bytes(b[seg:seg + free_head])                           # "" then "testdouble", 8-byte padded
+        nxt, fsize = struct.unpack_from("<QQ", b, seg + free_head)
+        out["heap_free_rule"] = (nxt, fsize == seg_size - free_head)
+        # the dataset's object header: version 1, reference count 1, 8-aligned message block
+        oh = r.base + r.group_entries(e["btree"], e["heap"])[0][1]["oh"]
+        ver, _, nmsg, refs, size = struct.unpack_from("<BBHII", b, oh)
+        out["ohdr"] = (ver, refs, size % 8, oh % 8)
+        msgs = {t: bytes(d) for t, _, d in r.messages(r.group_entries(e["btree"], e["heap"])[0][1]["oh"])}
+        out["dtype_msg"], out["dspace_msg"] = msgs[0x0003][:20], msgs[0x0001]
+        return out
+    a, b = parts(mine), parts(theirs)
+    assert a == b, {k: (a[k], b[k]) for k in a if a[k] != b[k]}
