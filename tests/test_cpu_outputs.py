@@ -449,3 +449,23 @@ def test_writer_structures_equal_libhdf5s_for_the_same_content(tmp_path):
         return out
     a, b = parts(mine), parts(theirs)
     assert a == b, {k: (a[k], b[k]) for k in a if a[k] != b[k]}
+
+
+def test_every_regression_deck_of_the_reference_loads_or_is_rejected_loudly():
+    """the reference's test/*/*.pp through pp.py: ten decks load (the systems the library runs), the two Rosenbluth decks
+    are refused with a ValueError instead of running as something else"""
+    import glob
+    from loki_b200 import pp
+    decks_ = sorted(glob.glob("/root/reference/test/*/*.pp"))
+    if not decks_:
+        pytest.skip("the reference tree is not on this machine")
+    loaded, refused = [], []
+    for f in decks_:
+        try:
+            pp.load(f)
+            loaded.append(os.path.basename(f))
+        except ValueError:
+            refused.append(os.path.basename(f))
+    assert loaded == ["EPWTZ.pp", "External2D.pp", "IAWTZ.pp", "InterpenetratingStreams.pp", "TrigTZ.pp", "emDamping.pp",
+                      "pitchAngleCollisions.pp", "planeEPW_fixedIons.pp", "planeIAW.pp", "planeIAW_6.pp"]
+    assert refused == ["rosenbluthCollisions_no_br.pp", "rosenbluthCollisions_w_br.pp"]
