@@ -24,6 +24,8 @@ class Species:
         self.vx0, self.vy0, self.x_wave_number, self.y_wave_number, self.flow_phase = vx0, vy0, x_wave_number, y_wave_number, flow_phase
 
         # options beyond the benchmark decks: a Krook layer and a pitch-angle collision operator (see Deck.apply_options)
+        # ic.vflowinitx / ic.vflowinity: the constant drift of the Maxwellian (MaxwellianThermal.C:48-49)
+        self.vflowinitx, self.vflowinity = 0.0, 0.0
         self.krook, self.collision = None, None
         # "External 2D" initial condition (External2DIC.C): `external` = the file's "2D dist" dataset, the spatial factor
         # of the WHOLE configuration space with its ghost layers, (Ny + 2 ng, Nx + 2 ng); `external_frac` = ic.frac
@@ -143,7 +145,10 @@ class Deck:
         x3 = sp.vlim[0] + (np.arange(-ng, sp.nv[0] + ng) + 0.5) * dx[2]
         x4 = sp.vlim[2] + (np.arange(-ng, sp.nv[1] + ng) + 0.5) * dx[3]
         thx, thy = sp.tx / sp.mass, sp.ty / sp.mass
-        fv = np.exp(-0.5 * ((x3 ** 2)[None, :] / thx + (x4 ** 2)[:, None] / thy))
+        # MaxwellianThermal::thermalFactor(0, x3, x4) (MaxwellianThermal.C:40-59): the drift is m_x0 * 0 + m_flowinitx
+        d3 = x3 - (sp.vx0 * 0.0 + getattr(sp, "vflowinitx", 0.0))
+        d4 = x4 - (sp.vy0 * 0.0 + getattr(sp, "vflowinity", 0.0))
+        fv = np.exp(-0.5 * ((d3 ** 2)[None, :] / thx + (d4 ** 2)[:, None] / thy))
         fnorm = sp.mass / (2.0 * math.pi * math.sqrt(sp.tx * sp.ty))
         if getattr(sp, "external", None) is not None:
             # External2DIC::cache, factorable branch (External2DIC.C:147-198): m_fx(i1, i2) = the file's value at the cell,
@@ -234,8 +239,8 @@ class Deck:
         x4 = sp.vlim[2] + (np.arange(-ng, sp.nv[1] + ng) + 0.5) * dx[3]
         sf = np.cos(sp.x_wave_number * x1[None, :] + sp.y_wave_number * x2[:, None] + sp.flow_phase)  # (n2d,n1d)
         thx, thy = sp.tx / sp.mass, sp.ty / sp.mass
-        c3 = sp.vx0 * sf + 0.0   # m_x0*spatial_factor + m_flowinitx (MaxwellianThermal.C:48-49)
-        c4 = sp.vy0 * sf + 0.0
+        c3 = sp.vx0 * sf + getattr(sp, "vflowinitx", 0.0)   # m_x0*spatial_factor + m_flowinitx (MaxwellianThermal.C:48-49)
+        c4 = sp.vy0 * sf + getattr(sp, "vflowinity", 0.0)
         d3 = x3[None, :, None, None] - c3[None, None, :, :]
         d4 = x4[:, None, None, None] - c4[None, None, :, :]
         fv = np.exp(-0.5 * ((d3 * d3) / thx + (d4 * d4) / thy))

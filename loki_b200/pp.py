@@ -151,9 +151,8 @@ def _species(params, k):
             if (dp + old) in params:
                 raise ValueError("driver key %r (old k/L syntax) is not supported; use xwidth / ywidth / lwidth" % old)
     # physics this mirror does not implement must not be dropped silently
-    for key in ("vflowinitx", "vflowinity", "phi"):
-        if g(key) != 0.0:
-            raise ValueError("species %d: ic.%s != 0 is not supported (MaxwellianThermal / PerturbedMaxwellianIC)" % (k, key))
+    if g("phi") != 0.0:
+        raise ValueError("species %d: ic.phi != 0 is not supported (PerturbedMaxwellianIC)" % k)
     # collision operators (KineticSpecies.C:206-215, 1426-1430; CollisionOperatorFactory.C:30-55): the pitch-angle
     # operator is implemented (one per species); the Rosenbluth operators are not
     collision = None
@@ -218,6 +217,7 @@ def _species(params, k):
                           vx0=g("vx0"), vy0=g("vy0"), x_wave_number=g("x_wave_number"), y_wave_number=g("y_wave_number"),
                           flow_phase=g("phase"))
         sp.driver_phase, sp.driver_shape_type = driver_phase, driver_shape_type
+        sp.vflowinitx, sp.vflowinity = g("vflowinitx"), g("vflowinity")      # MaxwellianThermal.C:48-49
         sp.krook = krook
         sp.collision = collision
         sp.tz = tz
@@ -240,6 +240,7 @@ def _species(params, k):
         sp = _d.Species(name, nv, vlim, mass, charge, tx=g("tx", 1.0), ty=g("ty", 1.0), driver=driver)
         sp.external = np.array(root["2D dist"].data, dtype=np.float64)
         sp.external_frac = g("frac", 1.0)
+        sp.vflowinitx, sp.vflowinity = g("vflowinitx"), g("vflowinity")
         sp.driver_phase, sp.driver_shape_type = driver_phase, driver_shape_type
         sp.krook = krook
         sp.collision = collision

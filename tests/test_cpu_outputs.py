@@ -469,3 +469,32 @@ def test_every_regression_deck_of_the_reference_loads_or_is_rejected_loudly():
     assert loaded == ["EPWTZ.pp", "External2D.pp", "IAWTZ.pp", "InterpenetratingStreams.pp", "TrigTZ.pp", "emDamping.pp",
                       "pitchAngleCollisions.pp", "planeEPW_fixedIons.pp", "planeIAW.pp", "planeIAW_6.pp"]
     assert refused == ["rosenbluthCollisions_no_br.pp", "rosenbluthCollisions_w_br.pp"]
+
+
+def test_flow_velocity_of_the_initial_maxwellian(tmp_path):
+    """ic.vflowinitx / vflowinity (MaxwellianThermal.C:40-59): a constant drift of the Maxwellian, also for factorable ICs"""
+    from loki_b200 import pp
+    from test_gpu_vp_system import RUN_DECK
+    text = RUN_DECK + "kinetic_species.1.ic.vflowinitx = 0.75\nkinetic_species.1.ic.vflowinity = -0.5\n"
+    path = tmp_path / "flow.pp"
+    path.write_text(text)
+    deck = pp.load(str(path))
+    sp = deck.species[0]
+    assert (sp.vflowinitx, sp.vflowinity) == (0.75, -0.5) and deck.species[1].vflowinitx == 0.0
+    f, fx, fv, fnorm = deck.initial_state(sp)
+    ng = deck.ng
+    n, dx = deck.geom_of(sp)
+    x3 = sp.vlim[0] + (np.arange(-ng, sp.nv[0] + ng) + 0.5) * dx[2]
+    x4 = sp.vlim[2] + (np.arange(-ng, sp.nv[1] + ng) + 0.5) * dx[3]
+    want = np.exp(-0.5 * (((x3 - 0.75) ** 2)[None, :] / (sp.tx / sp.mass) + ((x4 + 0.5) ** 2)[:, None] / (sp.ty / sp.mass)))
+    assert np.array_equal(fv, want)
+    # the mean velocity of the state is the drift (up to the truncation of the Maxwellian at the velocity limits)
+    I = (slice(ng, -ng),) * 4
+    w = f[I].sum(axis=(2, 3))
+    assert abs((w * x3[ng:-ng][None, :]).sum() / w.sum() - 0.75) < 1e-2       # midpoint rule on a coarse velocity grid
+    assert abs((w * x4[ng:-ng][:, None]).sum() / w.sum() + 0.5) < 1e-2
+    # the Rosenbluth decks of the reference carry a flow velocity too; they are refused for their collision operator now
+    ref = "/root/reference/test/rosenbluthCollisions/rosenbluthCollisions_w_br.pp"
+    if os.path.exists(ref):
+        with pytest.raises(ValueError, match="collision operator"):
+            pp.load(ref)
