@@ -314,7 +314,7 @@ def test_pp_reader_constants_and_interpolation():
 
 def test_pp_reader_rejects_physics_it_does_not_implement():
     """a deck key that would change the run is an error, never silently dropped (collision operators, twilight
-    zones, Krook layers, a flow-shifted Maxwellian, several drivers, relativity, the JB boundary conditions,
+    zones, Krook layers, a phase-shifted perturbation, several drivers, relativity, the JB boundary conditions,
     anything unknown); output-only keys are fine; constants are arithmetic, not Python"""
     from loki_b200 import pp
     base = OWN_DECK
@@ -325,7 +325,7 @@ def test_pp_reader_rejects_physics_it_does_not_implement():
                   "kinetic_species.1.krook.x1a = 0.0\n",      # a Krook layer / JB fills / open boundaries on the Vlasov-Maxwell mirror
                   "kinetic_species.1.external_dist_krook.x1a = 0.0\n",
                   "periodic_dir = false true\n",
-                  "kinetic_species.1.ic.vflowinitx = 0.3\n",
+                  "kinetic_species.1.ic.phi = 0.3\n",
                   "kinetic_species.1.num_external_drivers = 2\n",
                   "kinetic_species.1.external_driver.1.shape_type = \"gauss\"\n",
                   "do_relativity = true\n", "use_new_bcs = true\n", "do_new_algorithm = false\n",
