@@ -10,9 +10,10 @@ import numpy as np
 
 
 class Species:
-    def __init__(self, name, nv, vlim, mass, charge, tx=1.0, ty=1.0, A=0.0, B=0.0, Cc=0.0, kx1=0.0, ky1=0.0,
-                 kx2=0.0, ky2=0.0, frac=1.0, driver=None, bz=0.0, vx0=0.0, vy0=0.0, x_wave_number=0.0,
+    def __init__(self, name, nv, vlim, mass, charge, tx=1.0, ty=1.0, A=0.0, B=0.0, Cc=0.0, kx1=0.5, ky1=0.5,
+                 kx2=0.5, ky2=0.5, frac=1.0, driver=None, bz=0.0, vx0=0.0, vy0=0.0, x_wave_number=0.0,
                  y_wave_number=0.0, flow_phase=0.0, stream=None):
+        # defaults as PerturbedMaxwellianIC's constructor sets them (PerturbedMaxwellianIC.C:44-61): the wave numbers 0.5
         self.name, self.nv, self.vlim, self.mass, self.charge = name, nv, vlim, mass, charge
         self.tx, self.ty, self.A, self.B, self.Cc = tx, ty, A, B, Cc
         self.kx1, self.ky1, self.kx2, self.ky2, self.frac = kx1, ky1, kx2, ky2, frac
@@ -26,6 +27,9 @@ class Species:
         # options beyond the benchmark decks: a Krook layer and a pitch-angle collision operator (see Deck.apply_options)
         # ic.vflowinitx / ic.vflowinity: the constant drift of the Maxwellian (MaxwellianThermal.C:48-49)
         self.vflowinitx, self.vflowinity = 0.0, 0.0
+        # the three variants of PerturbedMaxwellianIC (PerturbedMaxwellianIC.C:351-362): 1 "Perturbed Maxwellian",
+        # 2 "Landau damping", 3 "Maxwellian with noise" (noise_amp / noise_phase per mode, :380-386); ic.spatial_phase (:411)
+        self.ic_option, self.spatial_phase, self.noise_amp, self.noise_phase = 1, 0.0, (), ()
         self.krook, self.collision = None, None
         # "External 2D" initial condition (External2DIC.C): `external` = the file's "2D dist" dataset, the spatial factor
         # of the WHOLE configuration space with its ghost layers, (Ny + 2 ng, Nx + 2 ng); `external_frac` = ic.frac
@@ -126,8 +130,19 @@ class Deck:
         dvy = (sp.vlim[3] - sp.vlim[2]) / sp.nv[1]
         return (self.n[0], self.n[1], sp.nv[0], sp.nv[1]), (self.dx[0], self.dx[1], dvx, dvy)
 
+    def _periodic_image(self, x1, x2, Lx, Ly):
+        """a cell centre outside a PERIODIC direction's limits is moved by the box length; a non-periodic direction's
+        ghost cells keep their own coordinates (PerturbedMaxwellianIC.C:123-143, External2DIC.C:168-187,
+        InterpenetratingStreamIC.C:153-172)"""
+        per = getattr(self, "periodic", (True, True))
+        if per[0]:
+            x1 = np.where(x1 < self.xlim[0], x1 + Lx, np.where(x1 > self.xlim[1], x1 - Lx, x1))
+        if per[1]:
+            x2 = np.where(x2 < self.xlim[2], x2 + Ly, np.where(x2 > self.xlim[3], x2 - Ly, x2))
+        return x1, x2
+
     def ic_tables(self, sp, tile_lo=(0, 0), tile_n=None):
-        """fx (n2d,n1d), fv (n4d,n3d), fnorm -- PerturbedMaxwellianIC::cache, factorable, ic_option 1"""
+        """fx (n2d,n1d), fv (n4d,n3d), fnorm -- PerturbedMaxwellianIC::cache, factorable branch, the three ic_options"""
         ng = self.ng
         tile_n = tile_n or self.n
         n, dx = self.geom_of(sp)
@@ -137,11 +152,22 @@ class Deck:
         i2 = np.arange(-ng, tile_n[1] + ng) + tile_lo[1]
         x1 = xlo + (i1 + 0.5) * dx[0]
         x2 = ylo + (i2 + 0.5) * dx[1]
-        x1 = np.where(x1 < self.xlim[0], x1 + Lx, np.where(x1 > self.xlim[1], x1 - Lx, x1))
-        x2 = np.where(x2 < self.xlim[2], x2 + Ly, np.where(x2 > self.xlim[3], x2 - Ly, x2))
-        phi = 0.0
-        fx = (1.0 + sp.A * np.cos(sp.kx1 * x1 + phi)[None, :] * np.cos(sp.ky1 * x2 + phi)[:, None] +
-              sp.B * np.cos(sp.kx2 * x1 + phi)[None, :] + sp.Cc * np.cos(sp.ky2 * x2 + phi)[:, None])
+        x1, x2 = self._periodic_image(x1, x2, Lx, Ly)
+        phi = float(getattr(sp, "spatial_phase", 0.0))
+        option = int(getattr(sp, "ic_option", 1))
+        if option == 1:      # PerturbedMaxwellianIC.C:145-150
+            fx = (1.0 + sp.A * np.cos(sp.kx1 * x1 + phi)[None, :] * np.cos(sp.ky1 * x2 + phi)[:, None] +
+                  sp.B * np.cos(sp.kx2 * x1 + phi)[None, :] + sp.Cc * np.cos(sp.ky2 * x2 + phi)[:, None])
+        elif option == 2:    # "Landau damping" (:151-154)
+            fx = 1.0 + sp.A * np.cos((sp.kx1 * x1)[None, :] + (sp.ky1 * x2)[:, None] + phi)
+        elif option == 3:    # "Maxwellian with noise" (:155-162): a sum over the modes of the box length, in mode order
+            pi = 4.0 * math.atan(1.0)
+            fx1 = np.ones_like(x1)
+            for k in range(1, len(sp.noise_amp) + 1):
+                fx1 = fx1 + sp.noise_amp[k - 1] * np.cos(2.0 * pi * k * (x1 + sp.noise_phase[k - 1]) / Lx + phi)
+            fx = np.broadcast_to(fx1[None, :], (x2.size, x1.size)).copy()
+        else:
+            raise ValueError("ic_option %r" % option)
         x3 = sp.vlim[0] + (np.arange(-ng, sp.nv[0] + ng) + 0.5) * dx[2]
         x4 = sp.vlim[2] + (np.arange(-ng, sp.nv[1] + ng) + 0.5) * dx[3]
         thx, thy = sp.tx / sp.mass, sp.ty / sp.mass
@@ -150,6 +176,12 @@ class Deck:
         d4 = x4 - (sp.vy0 * 0.0 + getattr(sp, "vflowinity", 0.0))
         fv = np.exp(-0.5 * ((d3 ** 2)[None, :] / thx + (d4 ** 2)[:, None] / thy))
         fnorm = sp.mass / (2.0 * math.pi * math.sqrt(sp.tx * sp.ty))
+        if option == 3:
+            # getIC_At_Pt multiplies m_fx * fnorm * m_fv * m_frac for this variant (PerturbedMaxwellianIC.C:276-278, and
+            # :240 for the cached m_f) instead of fnorm * m_fv * m_fx * m_frac: the first product is taken here and
+            # fnorm handed on as 1, so that every consumer's fnorm * fv * fx * frac (host and device, lk_device.cuh
+            # inflow kind 1) has the reference's bits -- 1 * fv is exact and IEEE products commute
+            fx, fnorm = fx * fnorm, 1.0
         if getattr(sp, "external", None) is not None:
             # External2DIC::cache, factorable branch (External2DIC.C:147-198): m_fx(i1, i2) = the file's value at the cell,
             # a ghost cell of a periodic direction taking its periodic image; getIC_At_Pt multiplies
@@ -174,8 +206,7 @@ class Deck:
         Lx, Ly = self.n[0] * dx[0], self.n[1] * dx[1]
         x1 = self.xlim[0] + (np.arange(-ng, tile_n[0] + ng) + tile_lo[0] + 0.5) * dx[0]
         x2 = self.xlim[2] + (np.arange(-ng, tile_n[1] + ng) + tile_lo[1] + 0.5) * dx[1]
-        x1 = np.where(x1 < self.xlim[0], x1 + Lx, np.where(x1 > self.xlim[1], x1 - Lx, x1))
-        x2 = np.where(x2 < self.xlim[2], x2 + Ly, np.where(x2 > self.xlim[3], x2 - Ly, x2))
+        x1, x2 = self._periodic_image(x1, x2, Lx, Ly)
         erf = np.vectorize(math.erf)
         th, beta, floor = st["theta"], st["beta"], st.get("floor", 0.0)
         xi0 = -st["d"]
@@ -233,8 +264,7 @@ class Deck:
         Lx, Ly = self.n[0] * dx[0], self.n[1] * dx[1]
         x1 = self.xlim[0] + (np.arange(-ng, self.n[0] + ng) + 0.5) * dx[0]
         x2 = self.xlim[2] + (np.arange(-ng, self.n[1] + ng) + 0.5) * dx[1]
-        x1 = np.where(x1 < self.xlim[0], x1 + Lx, np.where(x1 > self.xlim[1], x1 - Lx, x1))
-        x2 = np.where(x2 < self.xlim[2], x2 + Ly, np.where(x2 > self.xlim[3], x2 - Ly, x2))
+        x1, x2 = self._periodic_image(x1, x2, Lx, Ly)
         x3 = sp.vlim[0] + (np.arange(-ng, sp.nv[0] + ng) + 0.5) * dx[2]
         x4 = sp.vlim[2] + (np.arange(-ng, sp.nv[1] + ng) + 0.5) * dx[3]
         sf = np.cos(sp.x_wave_number * x1[None, :] + sp.y_wave_number * x2[:, None] + sp.flow_phase)  # (n2d,n1d)
@@ -266,6 +296,12 @@ class Deck:
         if sp.stream is not None:
             fx, fx2, fv, fv2 = self.stream_tables(sp, tile_lo, tile_n)
             return H.lk_vp_set_inflow(sys_, s, fx.ctypes.data, fv.ctypes.data, 1.0, 1.0)
+        if kind == 3:
+            # the cached m_f of a drifting Maxwellian (vx0 / vy0 != 0) at the velocity ghosts: lk_vm_set_inflow_ghosts
+            # carries it for a Vlasov-Maxwell system; the Vlasov-Poisson host mirror has no such entry point, and the
+            # factored tables would put a different Maxwellian into the velocity ghosts
+            raise ValueError("species %r: a non-factorable initial condition (ic.vx0 / ic.vy0 != 0) is not supported "
+                             "in a Vlasov-Poisson system" % sp.name)
         fx, fv, fnorm = self.ic_tables(sp, tile_lo, tile_n)
         return H.lk_vp_set_inflow(sys_, s, fx.ctypes.data, fv.ctypes.data, fnorm, sp.frac)
 
@@ -415,7 +451,8 @@ def em_damping(n=(32, 5), nv=(64, 64), order=4, rk=4):
     uy = -Ey / omega
     av_strong = 1.6 / clight
     xa, xb = -PI / klde, PI / klde
-    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, vy0=P(uy), x_wave_number=P(klde), flow_phase=P(PI / 2.0))
+    e = Species("electron", nv, (-7.0, 7.0, -7.0, 7.0), 1.0, -1.0, kx1=0.0, ky1=0.0, vy0=P(uy), x_wave_number=P(klde),
+                flow_phase=P(PI / 2.0))
     em_ics = [dict(field="E", xamp=0.0, yamp=P(Ey), zamp=0.0, kx=P(klde), ky=0.0, phase=0.0),
               dict(field="B", xamp=0.0, yamp=0.0, zamp=P(Bz), kx=P(klde), ky=0.0, phase=0.0)]
     vel_ics = [dict(amp=0.0, kx=0.0, ky=0.0, phase=0.0)]

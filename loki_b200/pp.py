@@ -151,8 +151,6 @@ def _species(params, k):
             if (dp + old) in params:
                 raise ValueError("driver key %r (old k/L syntax) is not supported; use xwidth / ywidth / lwidth" % old)
     # physics this mirror does not implement must not be dropped silently
-    if g("phi") != 0.0:
-        raise ValueError("species %d: ic.phi != 0 is not supported (PerturbedMaxwellianIC)" % k)
     # collision operators (KineticSpecies.C:206-215, 1426-1430; CollisionOperatorFactory.C:30-55): the pitch-angle
     # operator is implemented (one per species); the Rosenbluth operators are not
     collision = None
@@ -211,11 +209,25 @@ def _species(params, k):
                 tz[key] = _f(params, pre + "tz." + key)
     elif any(key.startswith(pre + "tz.") for key in list(params.keys())):
         raise ValueError("species %d: tz.* keys without tz.name" % k)
-    if icn == "Perturbed Maxwellian":
+    _pm = {"Perturbed Maxwellian": 1, "Landau damping": 2, "Maxwellian with noise": 3}   # PerturbedMaxwellianIC.C:22-33, 351-362
+    if icn in _pm:
+        if _s(params, pre + "ic.maxwellian_thermal", "true") != "true":
+            raise ValueError("species %d: the Juttner thermal factor is not supported" % k)
+        if (pre + "ic.alpha") in params or (pre + "ic.beta") in params:
+            raise ValueError("Parameters alpha and beta are deprecated in favor of tx and ty.")   # :388-390
+        # the constructor's defaults (PerturbedMaxwellianIC.C:44-61): the four wave numbers default to 0.5, not 0
         sp = _d.Species(name, nv, vlim, mass, charge, tx=g("tx", 1.0), ty=g("ty", 1.0), A=g("A"), B=g("B"), Cc=g("C"),
-                          kx1=g("kx1"), ky1=g("ky1"), kx2=g("kx2"), ky2=g("ky2"), frac=g("frac", 1.0), driver=driver,
-                          vx0=g("vx0"), vy0=g("vy0"), x_wave_number=g("x_wave_number"), y_wave_number=g("y_wave_number"),
-                          flow_phase=g("phase"))
+                          kx1=g("kx1", 0.5), ky1=g("ky1", 0.5), kx2=g("kx2", 0.5), ky2=g("ky2", 0.5), frac=g("frac", 1.0),
+                          driver=driver, vx0=g("vx0"), vy0=g("vy0"), x_wave_number=g("x_wave_number"),
+                          y_wave_number=g("y_wave_number"), flow_phase=g("phase"))
+        sp.ic_option, sp.spatial_phase = _pm[icn], g("spatial_phase")                           # :410-411
+        if (pre + "ic.number_of_noisy_modes") in params:                                        # :380-386, both arrays required
+            nn = int(_f(params, pre + "ic.number_of_noisy_modes"))
+            for key in ("noise_amplitudes", "noise_phases"):
+                if len(params[pre + "ic." + key]) < nn:
+                    raise ValueError("species %d: ic.%s needs %d values" % (k, key, nn))
+            sp.noise_amp = tuple(float(t) for t in params[pre + "ic.noise_amplitudes"][:nn])
+            sp.noise_phase = tuple(float(t) for t in params[pre + "ic.noise_phases"][:nn])
         sp.driver_phase, sp.driver_shape_type = driver_phase, driver_shape_type
         sp.vflowinitx, sp.vflowinity = g("vflowinitx"), g("vflowinity")      # MaxwellianThermal.C:48-49
         sp.krook = krook
@@ -301,8 +313,10 @@ def deck_from_params(params, name="deck"):
     else:
         deck = _d.Deck(name, n, xlim, species, order=order, rk=rk, cfl=cfl)
         deck.periodic, deck.use_new_bcs = periodic, use_new_bcs
-        if periodic != (True, True) and any(not sp.factorable for sp in species if sp.stream is None):
-            raise ValueError("non-periodic x / y needs factorable initial conditions (the inflow tables cover x / y ghosts)")
+        for sp in species:
+            if sp.stream is None and not sp.factorable:
+                raise ValueError("species %r: a non-factorable initial condition (ic.vx0 / ic.vy0 != 0) is not supported in "
+                                 "a Vlasov-Poisson system (its velocity ghosts need the cached distribution)" % sp.name)
     # time-step controls of Simulation (Simulation.C:415-440); not part of the deck's physics, kept aside
     # Simulation's defaults (Simulation.C:166-181): final_time 1, save_times 1, sequence_write_times 1, max_step 0
     deck.run = dict(final_time=_f(params, "final_time", 1.0), save_times=_f(params, "save_times", 1.0),
