@@ -132,24 +132,37 @@ def _species(params, k):
         if _s(params, dp + "name") != "Shaped Ramped Cosine Driver":
             raise ValueError("unsupported driver %r" % _s(params, dp + "name"))
         q = lambda key, dflt=0.0: _f(params, dp + key, dflt)
-        # ShapedRampedCosineDriver.C:255-320: old t_ramp / t_off syntax maps to (t_rampup, t_hold = 0, t_rampdown)
+        # the constructor's defaults (ShapedRampedCosineDriver.C:44-57): widths 0.5, shape 1, omega 1, E_0 0.01, ramps 10
+        # old t_ramp / t_off syntax maps to (t_rampup, t_hold = 0, t_rampdown) (:305-317)
         if (dp + "t_ramp") in params:
-            tr, th, td = q("t_ramp"), 0.0, q("t_off")
+            tr, th, td = q("t_ramp", 10.0), 0.0, q("t_off", 10.0)
         else:
-            tr, th, td = q("t_rampup"), q("t_hold"), q("t_rampdown")
+            tr, th, td = q("t_rampup", 10.0), q("t_hold", 0.0), q("t_rampdown", 10.0)
+
+        def width(new, k_key, l_key):
+            # old wave-number / length syntax (:241-291): width = L / (2 k), each defaulting to 1; mixing the two aborts
+            if (dp + k_key) in params or (dp + l_key) in params:
+                if (dp + new) in params:
+                    raise ValueError("Mixed old and new syntax for %s/%s" % (k_key, l_key))
+                return q(l_key, 1.0) / (2.0 * q(k_key, 1.0))
+            return q(new, 0.5)
         driver = [0.0] * 16
-        driver[0], driver[1], driver[2], driver[3], driver[4], driver[5] = q("xwidth"), q("ywidth"), q("shape"), q("omega"), q("E_0"), q("t0")
+        driver[0], driver[1] = width("xwidth", "kx", "Lx"), width("ywidth", "ky", "Ly")
+        driver[2], driver[3], driver[4], driver[5] = q("shape", 1.0), q("omega", 1.0), q("E_0", 0.01), q("t0", 0.0)
         driver[6], driver[7], driver[8] = tr, th, td
-        driver[9], driver[10], driver[11], driver[12], driver[13] = q("x_shape"), q("lwidth"), q("x0"), q("alpha"), q("t_res")
-        # ShapedRampedCosineDriver.C:262-268: phase (radians) and shape_type (0 sinusoidal / 1 exponential envelope)
-        driver_phase = q("phase")
+        driver[9], driver[10], driver[11], driver[12], driver[13] = q("x_shape"), width("lwidth", "kl", "Ll"), q("x0"), q("alpha"), q("t_res")
+        # the driver's phase is restart state, not deck input: 0 at start (ShapedRampedCosineDriver.C:30), restored from a dump
+        # and random-walked only by a noisy driver (:181-186, 365-370).  parseParameters never reads a "phase" key, so the
+        # reference would ignore one; refused here rather than silently dropped or silently applied.  Noisy drivers
+        # (phase_decay_time_steps / fwhm, :325-351) are not implemented: their keys stay unread and are refused below
+        if (dp + "phase") in params:
+            raise ValueError("external_driver.1.phase is not a deck key of the Shaped Ramped Cosine Driver (the reference "
+                             "never reads it; the phase is restart state)")
+        # shape_type (:292-303): 0 sinusoidal / 1 exponential envelope
         st = _s(params, dp + "shape_type", "sin2")
         if st not in ("sin2", "exp"):
             raise ValueError("unknown driver shape_type %r" % st)   # LOKI_ABORT("Unknown shape type")
         driver_shape_type = 0 if st == "sin2" else 1
-        for old in ("kx", "Lx", "ky", "Ly", "kl", "Ll"):
-            if (dp + old) in params:
-                raise ValueError("driver key %r (old k/L syntax) is not supported; use xwidth / ywidth / lwidth" % old)
     # physics this mirror does not implement must not be dropped silently
     # collision operators (KineticSpecies.C:206-215, 1426-1430; CollisionOperatorFactory.C:30-55): the pitch-angle
     # operator is implemented (one per species); the Rosenbluth operators are not
@@ -261,11 +274,30 @@ def _species(params, k):
     if icn == "Interpenetrating Stream":
         if _s(params, pre + "ic.syntax", "half plane") != "half plane":
             raise ValueError("only the half-plane syntax of the Interpenetrating Stream IC is supported")
+        if _s(params, pre + "ic.maxwellian_thermal", "true") != "true":
+            raise ValueError("species %d: the Juttner thermal factor is not supported" % k)
+        # parseParametersHalfPlane (InterpenetratingStreamIC.C:489-537): these six are required, each with its own message
+        required = (("tl", "Longitudinal temperature is required."), ("tt", "Transverse temperature is required."),
+                    ("theta", "Drift direction is required."), ("d", "Distance from origin is required."),
+                    ("beta", "Transition sharpness parameter is required."),
+                    ("frac", "Species relative weight parameter is required."))
+        for key, msg in required:
+            if (pre + "ic." + key) not in params:
+                raise ValueError(msg)
+        for key in ("vl0", "vt0"):                                                              # :507-512
+            if (pre + "ic." + key) in params:
+                raise ValueError("InterpenetratingStream %s input no longer used in favor of vflowinit%s." % (key, "xy"[key == "vt0"]))
         st = dict(tl=g("tl"), tt=g("tt"), theta=g("theta"), d=g("d"), beta=g("beta"), floor=g("floor", 0.0), frac=g("frac"))
-        if _s(params, pre + "ic.two_sided", "false") == "true":
+        two_sided = _s(params, pre + "ic.two_sided", "false") == "true"
+        centered = _s(params, pre + "ic.centered", "false") == "true"
+        if two_sided and centered:
+            raise ValueError("Only one of a two sided or centered slab may be specified.")        # :531-533
+        if two_sided:
+            if (pre + "ic.frac2") not in params:
+                raise ValueError("Two sided species relative weight parameter is required.")     # :534-536
             st["two_sided"] = True
             st["frac2"] = g("frac2")
-        if _s(params, pre + "ic.centered", "false") == "true":
+        if centered:
             st["centered"] = True
         sp = _d.Species(name, nv, vlim, mass, charge, stream=st, driver=driver)
         sp.driver_phase, sp.driver_shape_type = driver_phase, driver_shape_type

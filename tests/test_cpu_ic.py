@@ -163,3 +163,52 @@ def test_vp_inflow_tables_refuse_a_drifting_maxwellian():
     deck = decks.Deck("ic", (7, 5), (-9.0, 9.5, -6.0, 6.5), [sp], order=4)
     with pytest.raises(ValueError):
         deck.set_inflow(None, None, 0)
+
+
+DRIVER = ('kinetic_species.1.num_external_drivers = 1\n'
+          'kinetic_species.1.external_driver.1.name = "Shaped Ramped Cosine Driver"\n')
+
+
+def test_pp_driver_defaults_and_old_syntax():
+    """ShapedRampedCosineDriver's constructor defaults (ShapedRampedCosineDriver.C:44-57) and the old k / L and
+    t_ramp / t_off syntax (:241-291, 305-317)"""
+    d = _load(DRIVER)
+    drv = d.species[0].driver
+    #        xwidth ywidth shape omega E_0  t0  rampup hold rampdown x_shape lwidth x0  alpha t_res
+    assert drv[:14] == [0.5, 0.5, 1.0, 1.0, 0.01, 0.0, 10.0, 0.0, 10.0, 0.0, 0.5, 0.0, 0.0, 0.0]
+    assert d.species[0].driver_phase == 0.0 and d.species[0].driver_shape_type == 0
+    p = "kinetic_species.1.external_driver.1."
+    d = _load(DRIVER + p + "kx = 0.25\n" + p + "Lx = 3.0\n" + p + "Ly = 5.0\n" + p + "kl = 4.0\n" + p + "t_ramp = 2.0\n")
+    drv = d.species[0].driver
+    assert drv[0] == 3.0 / (2.0 * 0.25) and drv[1] == 5.0 / (2.0 * 1.0) and drv[10] == 1.0 / (2.0 * 4.0)
+    assert drv[6:9] == [2.0, 0.0, 10.0]                # t_off left out: the ramp-down keeps its default
+    for bad in (p + "kx = 0.25\n" + p + "xwidth = 2.0\n", p + "Ly = 1\n" + p + "ywidth = 2.0\n",
+                p + "phase = 0.1\n", p + "fwhm = 0.1\n" + p + "phase_decay_time_steps = 10\n"):
+        with pytest.raises(ValueError):
+            _load(DRIVER + bad)
+
+
+STREAM = ('kinetic_species.1.ic.name = "Interpenetrating Stream"\nkinetic_species.1.ic.tl = 1.0\nkinetic_species.1.ic.tt = 1.0\n'
+          "kinetic_species.1.ic.theta = 0.0\nkinetic_species.1.ic.d = 5.0\nkinetic_species.1.ic.beta = 0.768\n"
+          "kinetic_species.1.ic.frac = 1.0\n")
+
+
+def test_pp_stream_ic_required_keys():
+    """parseParametersHalfPlane (InterpenetratingStreamIC.C:489-537): six required keys, frac2 with two_sided, not both
+    slab forms, vl0 / vt0 retired"""
+    d = _load(STREAM)
+    assert d.species[0].stream["floor"] == 0.0 and "two_sided" not in d.species[0].stream
+    for key, msg in (("tl", "Longitudinal"), ("tt", "Transverse"), ("theta", "Drift direction"), ("d ", "Distance"),
+                     ("beta", "sharpness"), ("frac", "relative weight")):
+        text = "".join(l + "\n" for l in STREAM.splitlines() if not l.startswith("kinetic_species.1.ic." + key.strip() + " "))
+        with pytest.raises(ValueError) as e:
+            _load(text)
+        assert msg in str(e.value), (key, str(e.value))
+    for extra, msg in (("kinetic_species.1.ic.two_sided = true\n", "Two sided"),
+                       ("kinetic_species.1.ic.two_sided = true\nkinetic_species.1.ic.frac2 = 1\nkinetic_species.1.ic.centered = true\n", "Only one"),
+                       ("kinetic_species.1.ic.vl0 = 0.1\n", "no longer used"),
+                       ("kinetic_species.1.ic.maxwellian_thermal = false\n", "Juttner"),
+                       ('kinetic_species.1.ic.syntax = "box"\n', "half-plane")):
+        with pytest.raises(ValueError) as e:
+            _load(STREAM + extra)
+        assert msg in str(e.value), (extra, str(e.value))

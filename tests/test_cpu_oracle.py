@@ -328,13 +328,14 @@ def test_pp_reader_rejects_physics_it_does_not_implement():
                   "kinetic_species.1.ic.phi = 0.3\n",
                   "kinetic_species.1.num_external_drivers = 2\n",
                   "kinetic_species.1.external_driver.1.shape_type = \"gauss\"\n",
+                  "kinetic_species.1.external_driver.1.phase = 0.25\n",       # restart state, never a deck key in the reference
+                  "kinetic_species.1.external_driver.1.fwhm = 0.1\n",         # noisy drivers are not implemented
                   "do_relativity = true\n", "use_new_bcs = true\n", "do_new_algorithm = false\n",
                   "some_future_switch = 1\n"):
         with pytest.raises(ValueError):
             pp.deck_from_params(pp.parse(base + extra))
-    d = pp.deck_from_params(pp.parse(base + "kinetic_species.1.external_driver.1.shape_type = \"exp\"\n"
-                                            "kinetic_species.1.external_driver.1.phase = 0.25\n"))
-    assert d.species[0].driver_shape_type == 1 and d.species[0].driver_phase == 0.25
+    d = pp.deck_from_params(pp.parse(base + "kinetic_species.1.external_driver.1.shape_type = \"exp\"\n"))
+    assert d.species[0].driver_shape_type == 1 and d.species[0].driver_phase == 0.0
     assert d.product_vm_desc().base.species[0].driver_shape_type == 1
     with pytest.raises(ValueError):
         pp.parse("$x = ().__class__.__bases__[0];\n")

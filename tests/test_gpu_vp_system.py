@@ -515,10 +515,12 @@ kinetic_species.1.charge = -1.0
 kinetic_species.1.ic.name = "Perturbed Maxwellian"
 kinetic_species.1.ic.A = 0.02
 kinetic_species.1.ic.kx1 = $klde
+kinetic_species.1.ic.ky1 = 0.0
 kinetic_species.1.num_external_drivers = 1
 kinetic_species.1.external_driver.1.name = "Shaped Ramped Cosine Driver"
 kinetic_species.1.external_driver.1.xwidth = 9.42477796076938
 kinetic_species.1.external_driver.1.ywidth = 200
+kinetic_species.1.external_driver.1.shape = 0.0
 kinetic_species.1.external_driver.1.omega = 1.1
 kinetic_species.1.external_driver.1.E_0 = 0.05
 kinetic_species.1.external_driver.1.t_ramp = 1.0
